@@ -1,0 +1,228 @@
+"""Pins the C restatement (oracle/orbc_oracle.c) against the reference itself: the unmodified
+headers of /root/reference/src compiled behind oracle/ref_harness.cpp (strict IEEE flags, one thread).
+Integer structures must be equal; single-call fp32 outputs are bit-exact where the summation order
+is the same and within 2e-5 where only the stencil visiting order differs."""
+import numpy as np
+import pytest
+
+from oracle import port, ref as refmod
+from tests.common import needs_ref, ref_sphere, ref_vesicle, rel_err
+
+pytestmark = needs_ref
+
+
+def world_from(r, **kw):
+    return port.World(r.state(), **kw)
+
+
+def sync_forces(r, w):
+    for s, f, t in ((0, w.lf, w.lt), (1, w.pf, w.pt)):
+        r.set(s, "f", f); r.set(s, "t", t)
+
+
+@pytest.fixture(scope="module")
+def ves():
+    return ref_vesicle(1)
+
+
+def test_forcefield_bytes():
+    r = refmod.Ref("strict", threads=1)
+    a = r.forcefield()
+    b = port.forcefield().as_array()
+    assert a.tobytes() == b.tobytes()
+
+
+def test_uint2u11_and_morton_encode():
+    r = refmod.Ref("strict", threads=1)
+    rng = np.random.default_rng(1)
+    for u in list(rng.integers(0, 2**32, 200)) + [0, 1, 2**31, 2**32 - 1]:
+        assert r.uint2u11(u) == port.lib().orc_uint2u11(int(u))
+    pts = rng.uniform(-990, 990, (3000, 3)).astype(np.float32)
+    for p in pts:
+        assert r.morton_encode(*p) == port.morton_encode(*p)
+
+
+def test_morton_sort_permutation():
+    r = ref_sphere(20.0)
+    c = r.centroids()
+    rng = np.random.default_rng(2)
+    c = c[rng.permutation(len(c))]
+    perm, keys = port.morton_perm(c)
+    assert len(np.unique(keys)) == len(keys)  # no duplicate keys => std::sort order is unique
+    np.testing.assert_array_equal(r.reorder_morton(c), c[perm])
+
+
+def _advance(r, steps, seed=3):
+    """Move the system a little so that the partition actually changes (noise-free Langevin steps)."""
+    r.set_param("kBT", 0.0)
+    for _ in range(steps):
+        r.integrate(refmod.CLEAR_FORCE)
+        r.compute_pairwise_fused(); r.compute_bonded()
+        r.integrate(refmod.VERLET_LANGEVIN)
+
+
+@pytest.mark.parametrize("nstep", [2, 24])
+def test_rebuild_integer_exact(ves, nstep):
+    r = ves
+    _advance(r, 3)
+    w = world_from(r)
+    w.nstep = nstep
+    r.set_param("nstep", nstep)
+    # centroids (+ Morton sort when nstep % 24 == 0)
+    r.voronoi_update(); w.voronoi_update()
+    np.testing.assert_array_equal(r.centroids(), w.centroids)
+    for s in (0, 1):
+        x_before = r.get(s, "x")
+        r.cell_update(s); w.cell_update(s)
+        aff_ref = r.cell_array(s, "affiliation")  # pre-reorder index order, voronoi.h:212
+        aff, tie = (w.aff_l, w.tie_l) if s == 0 else (w.aff_p, w.tie_p)
+        bad = aff_ref != aff
+        assert not (bad & ~tie).any(), f"{bad.sum()} affiliation mismatches, {(bad & ~tie).sum()} not ties"
+        if not bad.any():
+            np.testing.assert_array_equal(r.cell_array(s, "cell_start"), w.cs_l if s == 0 else w.cs_p)
+            np.testing.assert_array_equal(r.cell_array(s, "cells"), w.cells_l if s == 0 else w.cells_p)
+            np.testing.assert_array_equal(r.get(s, "x"), w.lx if s == 0 else w.px)
+            np.testing.assert_array_equal(r.get(s, "x"), x_before[w.cells_l if s == 0 else w.cells_p])
+    t, g = r.protein_ids()
+    np.testing.assert_array_equal(t, w.ptype); np.testing.assert_array_equal(g, w.ptag)
+
+
+def test_stencil_sets(ves):
+    r = ves
+    c = r.centroids()
+    for cell in range(0, r.n_cells, 7):
+        s9, s8, s6 = r.stencil_refined(cell)
+        for rmax, s in ((9.0, s9), (8.0, s8), (6.0, s6)):
+            np.testing.assert_array_equal(np.sort(s), port.stencil(c, cell, rmax))
+        assert cell in s6
+
+
+@pytest.mark.parametrize("maker", [lambda: ref_sphere(20.0), lambda: ref_vesicle(1)])
+def test_pairwise_and_bonded(maker):
+    r = maker()
+    w = world_from(r)
+    r.integrate(refmod.CLEAR_FORCE)
+    r.compute_pairwise_fused(); w.compute_pairwise_fused()
+    for s, f, t in ((0, w.lf, w.lt), (1, w.pf, w.pt)):
+        assert rel_err(f, r.get(s, "f")) < 2e-5
+        assert rel_err(t, r.get(s, "t")) < 2e-5
+    assert w.counters[1] > 0
+    sync_forces(r, w)
+    r.compute_bonded(); w.compute_bonded()
+    np.testing.assert_array_equal(r.get(1, "f"), w.pf)  # same sequential order => bit-exact
+
+
+def test_langevin_noise_free_bitexact(ves):
+    r = ves
+    w = world_from(r, kBT=0.0)
+    r.set_param("kBT", 0.0)
+    r.integrate(refmod.CLEAR_FORCE); r.compute_pairwise_fused(); r.compute_bonded()
+    for s, f, t in ((0, "lf", "lt"), (1, "pf", "pt")):
+        setattr(w, f, r.get(s, "f")); setattr(w, t, r.get(s, "t"))
+    r.integrate(refmod.VERLET_LANGEVIN); w.verlet_langevin()
+    for s, p in ((0, "l"), (1, "p")):
+        for fld in "xvno":
+            np.testing.assert_array_equal(r.get(s, fld), getattr(w, p + fld), err_msg=p + fld)
+        assert not r.get(s, "f").any() and not r.get(s, "t").any()
+
+
+def test_langevin_reference_noise_stream():
+    """MT19937 (signed-shift variant) + xorshift128 + uint2u11 restated: the reference's own noisy step reproduced."""
+    seed = 0xBAD5EED
+    r = ref_vesicle(1)
+    mt0 = port.mt_init(seed)                       # param.rng.init(rseed)        runtime_parameter.h:108
+    prng0 = port.mt_init(port.lib().orc_mt_uint(port.C.byref(mt0)))  # prng[0].init(rng.uint())     :110
+    w = world_from(r, kBT=0.22)
+    for it in range(2):
+        r.integrate(refmod.CLEAR_FORCE); r.compute_pairwise_fused(); r.compute_bonded()
+        for s, f, t in ((0, "lf", "lt"), (1, "pf", "pt")):
+            setattr(w, f, r.get(s, "f")); setattr(w, t, r.get(s, "t"))
+        nl = port.langevin_noise(prng0, len(w.lx))
+        npr = port.langevin_noise(prng0, len(w.px))
+        assert nl.min() >= -1.0 and nl.max() <= 1.0 and abs(nl.var() - 1 / 3) < 0.01
+        r.integrate(refmod.VERLET_LANGEVIN); w.verlet_langevin(nl, npr)
+        for s, p in ((0, "l"), (1, "p")):
+            for fld in "xvno":
+                np.testing.assert_array_equal(r.get(s, fld), getattr(w, p + fld), err_msg=f"{p}{fld} it{it}")
+
+
+def test_nose_hoover_fused_bitexact(ves):
+    r = ves
+    rng = np.random.default_rng(5)
+    for s in (0, 1):
+        r.set(s, "v", rng.normal(0, 0.3, (r.size(s), 3)))
+    r.set_param("kBT", 0.22); r.set_param("zeta", 0.05); r.set_param("Q", 0.0)
+    w = world_from(r, kBT=0.22); w.zeta = 0.05
+    r.integrate(refmod.CLEAR_FORCE); r.compute_pairwise_fused(); r.compute_bonded()
+    for s, f, t in ((0, "lf", "lt"), (1, "pf", "pt")):
+        setattr(w, f, r.get(s, "f")); setattr(w, t, r.get(s, "t"))
+    r.integrate(refmod.NH_FINAL_FUSED); w.nh_final_fused()
+    assert np.float32(r.get_param("zeta")) == np.float32(w.zeta)
+    assert np.float32(r.get_param("Q")) == np.float32(w.Q.value)
+    for s, p in ((0, "l"), (1, "p")):
+        for fld in "vot":
+            np.testing.assert_array_equal(r.get(s, fld), getattr(w, p + fld), err_msg=p + fld)
+    # put one particle outside the box to exercise bounce-back
+    x = r.get(0, "x"); x[0] = (1000.5, -1001.0, 3.0); r.set(0, "x", x); w.lx[0] = x[0]
+    r.integrate(refmod.NH_INITIAL_FUSED); w.nh_initial_fused()
+    assert np.float32(r.get_param("zeta")) == np.float32(w.zeta)
+    for s, p in ((0, "l"), (1, "p")):
+        for fld in "xvnoft":
+            np.testing.assert_array_equal(r.get(s, fld), getattr(w, p + fld), err_msg=p + fld)
+    assert abs(r.compute_temperature() - w.compute_temperature()) == 0.0
+
+
+def test_small_kernels_bitexact(ves):
+    r = ves
+    w = world_from(r)
+    r.integrate(refmod.CLEAR_FORCE); r.compute_pairwise_fused(); r.compute_bonded()
+    for s, f, t in ((0, "lf", "lt"), (1, "pf", "pt")):
+        setattr(w, f, r.get(s, "f")); setattr(w, t, r.get(s, "t"))
+    r.integrate(refmod.POST_TORQUE); w.post_torque()
+    np.testing.assert_array_equal(r.get(0, "t"), w.lt); np.testing.assert_array_equal(r.get(1, "t"), w.pt)
+    r.opt_move(); w.opt_move()
+    for s, p in ((0, "l"), (1, "p")):
+        np.testing.assert_array_equal(r.get(s, "x"), getattr(w, p + "x")); np.testing.assert_array_equal(r.get(s, "n"), getattr(w, p + "n"))
+    x = r.get(1, "x"); x[3] = (-1002.0, 5.0, 1000.25); r.set(1, "x", x); w.px[3] = x[3]
+    r.integrate(refmod.BOUNCE_BACK); w.bounce_back()
+    np.testing.assert_array_equal(r.get(1, "x"), w.px); np.testing.assert_array_equal(r.get(1, "v"), w.pv)
+
+
+def test_delete_lipid():
+    r = ref_sphere(20.0)
+    x = r.get(0, "x")
+    cs = r.cell_array(0, "cell_start")
+    x[cs[5]] *= 1.4; x[cs[40] + 1] *= 0.7   # two strays
+    r.set(0, "x", x)
+    w = world_from(r)
+    r.set_param("stray_tolerance", 2.5)
+    n_ref = r.delete_lipid()
+    kept = w.delete_lipid(2.5)
+    assert n_ref == kept and kept <= len(x) - 2
+    if not w.tie_l.any():
+        np.testing.assert_array_equal(r.get(0, "x"), w.lx)
+        np.testing.assert_array_equal(r.cell_array(0, "cell_start"), w.cs_l)
+
+
+def test_constrain_volume():
+    """The reference's cell_normal scratch is a function-static that is never cleared (constrain_volume.h:34,55):
+    recover its state from the first call's forces, then compare the second call."""
+    r = ref_vesicle(1)
+    w = world_from(r)
+    cs = r.cell_array(0, "cell_start")
+    assert (np.diff(cs) > 0).all()
+    r.integrate(refmod.CLEAR_FORCE)
+    r.constrain_volume(3.15, 0.05)
+    fl = r.get(0, "f")
+    c = r.centroids()
+    nrm = fl[cs[:-1]] / np.linalg.norm(fl[cs[:-1]], axis=1, keepdims=True)
+    outward = ((c - c.mean(0)) * nrm).sum(1)
+    nrm[outward < 0] *= -1          # the stored normal is the outward one whatever the sign of the force
+    # second call from a known scratch state: seed the port with the reference's normals (to fp32 rounding)
+    w.cell_normal[...] = nrm.astype(np.float32)
+    r.integrate(refmod.CLEAR_FORCE)
+    r.constrain_volume(3.15, 0.05)
+    vol = w.constrain_volume(3.15, 0.05)
+    assert np.isfinite(vol)
+    assert rel_err(w.lf, r.get(0, "f")) < 1e-5
+    assert rel_err(w.pf, r.get(1, "f")) < 1e-5
