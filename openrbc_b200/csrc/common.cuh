@@ -1,0 +1,131 @@
+// common.cuh — context, error handling and small device helpers shared by every kernel file.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdint>
+#include <cstring>
+
+#include "../../include/orbc_b200.h"
+
+namespace orbc {
+
+// ------------------------------------------------------------------------------------------------
+// errors: thread-local message, negative status codes (include/orbc_b200.h)
+// ------------------------------------------------------------------------------------------------
+inline char *err_buf() { static thread_local char buf[512] = "no error"; return buf; }
+inline int fail(int code, const char *fmt, ...) {
+    va_list ap; va_start(ap, fmt); vsnprintf(err_buf(), 512, fmt, ap); va_end(ap);
+    return code;
+}
+#define ORBC_CUDA(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) return ::orbc::fail(ORBC_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #x, cudaGetErrorString(e__)); } while (0)
+#define ORBC_TRY(x) do { int r__ = (x); if (r__ != ORBC_OK) return r__; } while (0)
+
+constexpr int kNType = 6;              // forcefield_canonical.h:37
+constexpr int kStencilStride = ORBC_STENCIL_STRIDE;
+constexpr float kBin = 9.0f;           // centroid grid bin = largest centroid stencil radius (compute_pairwise_fused.h:183)
+
+// device image of the force field + derived Langevin coefficients, in __constant__ memory
+struct DevForceField {
+    orbc_forcefield ff;
+};
+
+// one container (container.h:65-157) on the device.  SoA of float4:
+//   x  = (x, y, z, type as int bits)      n = (nx, ny, nz, tag as int bits)
+//   v, o, f, t = (.., .., .., unused)
+// x, n, v, o are double-buffered for the out-of-place reorder (reorder.h:73-149), like the reference's shadow arrays.
+struct Species {
+    size_t n = 0, cap = 0;
+    int cur = 0;
+    float4 *x[2] = {nullptr, nullptr}, *nn[2] = {nullptr, nullptr}, *v[2] = {nullptr, nullptr}, *o[2] = {nullptr, nullptr};
+    float4 *f = nullptr, *t = nullptr;
+    int *cellid[2] = {nullptr, nullptr};  // cell of every particle in storage order (-1: unknown), double-buffered with x
+    int *aff = nullptr;                   // nearest centroid per particle, pre-reorder order (VCellList::affiliation)
+    int *li = nullptr;                    // arrival slot inside the new cell (VCellList::local_index, order fixed later)
+    int *cells = nullptr, *cells_tmp = nullptr;  // gather permutation (VCellList::cells)
+    int *cell_start = nullptr;            // n_cells + 1 (VCellList::cell_start)
+    bool has_partition = false;
+    float4 *X() const { return x[cur]; }
+    float4 *N() const { return nn[cur]; }
+    float4 *V() const { return v[cur]; }
+    float4 *O() const { return o[cur]; }
+    int *C() const { return cellid[cur]; }
+};
+
+struct Grid {                // uniform grid over the centroids (replaces the k-d tree, kdtree.h)
+    float lo[3] = {0, 0, 0};
+    float h = kBin;
+    int dim[3] = {1, 1, 1};
+    int nbins = 1;
+    int *bin_start = nullptr;   // nbins + 1
+    int *bin_items = nullptr;   // n_cells
+    int *bin_of = nullptr;      // n_cells
+    int *bin_slot = nullptr;    // n_cells
+    size_t cap_bins = 0;
+};
+
+} // namespace orbc
+
+struct orbc_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr, own_stream = nullptr;
+    orbc::Species sp[2];
+    // Voronoi diagram
+    int n_cells = 0;
+    float4 *centroid = nullptr, *centroid_tmp = nullptr;
+    uint32_t *keys = nullptr, *keys_tmp = nullptr;
+    int *perm = nullptr, *perm_tmp = nullptr;     // new -> old of the last Morton sort
+    int *inv = nullptr;                           // old -> new
+    bool inv_identity = true;
+    orbc::Grid grid;
+    int *stencil = nullptr;                       // n_cells x kStencilStride
+    int *stencil_cnt = nullptr;                   // n_cells, packed n6 | n8 << 8 | n9 << 16
+    bool stencil_valid = false;
+    float4 *cell_normal = nullptr;                // constrain_volume's persistent scratch
+    // bonds
+    size_t n_bonds = 0;
+    int *bonds = nullptr;                         // (type, tag_i, tag_j)
+    int *tag2idx = nullptr; size_t tag2idx_size = 0;
+    // scratch
+    int *scan_tmp = nullptr; size_t scan_tmp_cap = 0;
+    int *radix_hist = nullptr; size_t radix_hist_cap = 0;
+    float *stage = nullptr; size_t stage_cap = 0;         // device staging for strided host<->device packing
+    double *d_acc = nullptr;                              // 8 doubles: reductions
+    unsigned long long *d_counters = nullptr;             // 8 counters
+    int *d_flags = nullptr;                               // 4 ints: device-side error flags
+    float *d_nh = nullptr;                                // zeta, Q on the device for orbc_run_nh
+    double *h_acc = nullptr; int *h_flags = nullptr; unsigned long long *h_counters = nullptr; float *h_nh = nullptr;  // pinned mirrors
+    float *noise[2] = {nullptr, nullptr}; size_t noise_cap[2] = {0, 0};
+    cudaEvent_t ev[16] = {};
+    unsigned long long launches = 0;
+    bool ff_set = false;
+};
+
+namespace orbc {
+
+// launch helper: counts launches (bench.py reports gpu_launches from this)
+#define ORBC_LAUNCH(ctx, kernel, grid, block, smem, ...) do { \
+        kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__); (ctx)->launches++; \
+        ORBC_CUDA(cudaGetLastError()); } while (0)
+
+inline unsigned blocks_for(size_t n, unsigned block) { return (unsigned)((n + block - 1) / block); }
+
+template <class T> inline int dev_alloc(T **p, size_t n) {
+    if (*p) { cudaFree(*p); *p = nullptr; }
+    ORBC_CUDA(cudaMalloc((void **)p, sizeof(T) * (n ? n : 1)));
+    return ORBC_OK;
+}
+template <class T> inline void dev_free(T *&p) { if (p) cudaFree(p); p = nullptr; }
+
+// strict fp32 (no FMA contraction) helpers — used wherever integer structures are derived from floating point so that
+// they match the reference built without contraction (SURVEY.md §7 "bit-exact integer structures")
+__device__ __forceinline__ float sq3_rn(float dx, float dy, float dz) {
+    // ((0 + dx*dx) + dy*dy) + dz*dz — math_vector_base.h:209-213
+    return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+__device__ __forceinline__ float dist2_rn(float4 a, float4 b) {
+    return sq3_rn(__fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y), __fsub_rn(a.z, b.z));
+}
+
+} // namespace orbc

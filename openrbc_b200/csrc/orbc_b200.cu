@@ -1,0 +1,713 @@
+// orbc_b200.cu — the C ABI of include/orbc_b200.h over the sm_100a kernels in rebuild.cuh / pair.cuh / pair_tiled.cuh /
+// integrate.cuh.  One context per GPU, every launch on the context's stream, no host synchronisation inside the
+// per-step calls (only download / reductions returned to the host synchronise).
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#include "common.cuh"
+#include "primitives.cuh"
+#include "rebuild.cuh"
+#include "pair.cuh"
+#include "integrate.cuh"
+
+using namespace orbc;
+
+namespace {
+
+constexpr int kBlock = 256;
+
+// ---- packing between the host's strided vect arrays and the device's float4 SoA ------------------------------------------------
+__global__ void k_pack4(const float *__restrict__ src, size_t stride, size_t n, float4 *__restrict__ dst, const int *__restrict__ w) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float *p = src + i * stride;
+    dst[i] = make_float4(p[0], p[1], p[2], w ? __int_as_float(w[i]) : 0.f);
+}
+__global__ void k_zero4(float4 *__restrict__ dst, size_t n, const int *__restrict__ w) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = make_float4(0.f, 0.f, 0.f, w ? __int_as_float(w[i]) : 0.f);
+}
+__global__ void k_set3(const float *__restrict__ src, size_t stride, size_t n, float4 *__restrict__ dst) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float *p = src + i * stride;
+    float4 d = dst[i]; d.x = p[0]; d.y = p[1]; d.z = p[2]; dst[i] = d;
+}
+__global__ void k_unpack3(const float4 *__restrict__ src, size_t n, size_t stride, float *__restrict__ dst) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 s = src[i];
+    float *p = dst + i * stride;
+    p[0] = s.x; p[1] = s.y; p[2] = s.z;
+    for (size_t d = 3; d < stride; ++d) p[d] = 0.f;
+}
+__global__ void k_unpack_w(const float4 *__restrict__ src, size_t n, int *__restrict__ dst) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = __float_as_int(src[i].w);
+}
+__global__ void k_morton_keys_only(const float4 *__restrict__ pts, int n, uint32_t *__restrict__ keys) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) keys[i] = morton_encode(pts[i]);
+}
+
+int ensure_stage(orbc_ctx *c, size_t floats) {
+    if (c->stage_cap < floats) { ORBC_TRY(dev_alloc(&c->stage, floats)); c->stage_cap = floats; }
+    return ORBC_OK;
+}
+
+int alloc_species(orbc_ctx *c, Species &s, size_t n) {
+    if (n > s.cap) {
+        const size_t cap = n + 64;
+        for (int b = 0; b < 2; ++b) {
+            ORBC_TRY(dev_alloc(&s.x[b], cap)); ORBC_TRY(dev_alloc(&s.nn[b], cap)); ORBC_TRY(dev_alloc(&s.v[b], cap)); ORBC_TRY(dev_alloc(&s.o[b], cap));
+            ORBC_TRY(dev_alloc(&s.cellid[b], cap));
+        }
+        ORBC_TRY(dev_alloc(&s.f, cap)); ORBC_TRY(dev_alloc(&s.t, cap));
+        ORBC_TRY(dev_alloc(&s.aff, cap + 1)); ORBC_TRY(dev_alloc(&s.li, cap + 1));
+        ORBC_TRY(dev_alloc(&s.cells, cap)); ORBC_TRY(dev_alloc(&s.cells_tmp, cap));
+        s.cap = cap;
+    }
+    s.n = n; s.cur = 0; s.has_partition = false;
+    (void)c;
+    return ORBC_OK;
+}
+
+void free_species(Species &s) {
+    for (int b = 0; b < 2; ++b) { dev_free(s.x[b]); dev_free(s.nn[b]); dev_free(s.v[b]); dev_free(s.o[b]); dev_free(s.cellid[b]); }
+    dev_free(s.f); dev_free(s.t); dev_free(s.aff); dev_free(s.li); dev_free(s.cells); dev_free(s.cells_tmp); dev_free(s.cell_start);
+    s = Species();
+}
+
+GridDev grid_dev(const orbc_ctx *c) {
+    GridDev g;
+    g.lox = c->grid.lo[0]; g.loy = c->grid.lo[1]; g.loz = c->grid.lo[2];
+    g.h = c->grid.h; g.inv_h = 1.0f / c->grid.h;
+    g.dx = c->grid.dim[0]; g.dy = c->grid.dim[1]; g.dz = c->grid.dim[2];
+    g.bin_start = c->grid.bin_start; g.bin_items = c->grid.bin_items;
+    return g;
+}
+
+// device-side consistency flags -> status (synchronises)
+int check_flags(orbc_ctx *c) {
+    ORBC_CUDA(cudaMemcpyAsync(c->h_flags, c->d_flags, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    ORBC_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->h_flags[0]) return fail(ORBC_ERR_STATE, "centroid stencil of cell %d holds more than %d cells", c->h_flags[0] - 1, kStencilStride);
+    if (c->h_flags[1]) return fail(ORBC_ERR_STATE, "particle %d has no nearest centroid (NaN position?)", c->h_flags[1] - 1);
+    if (c->h_flags[2]) return fail(ORBC_ERR_STATE, "protein %d carries a tag outside the tag->index map", c->h_flags[2] - 1);
+    return ORBC_OK;
+}
+
+// grid + stencils from the current centroids (the part of VoronoiDiagram::update that replaces tree.build, voronoi.h:83)
+int build_index(orbc_ctx *c) {
+    const int nc = c->n_cells;
+    Grid &g = c->grid;
+    ORBC_CUDA(cudaMemsetAsync(g.bin_start, 0, sizeof(int) * ((size_t)g.nbins + 1), c->stream));
+    const GridDev gd = grid_dev(c);
+    ORBC_LAUNCH(c, k_bin_count, blocks_for(nc, kBlock), kBlock, 0, c->centroid, nc, gd, g.bin_start, g.bin_of, g.bin_slot);
+    ORBC_TRY(scan_exclusive(c, g.bin_start, g.nbins));
+    ORBC_LAUNCH(c, k_bin_fill, blocks_for(nc, kBlock), kBlock, 0, nc, g.bin_start, g.bin_of, g.bin_slot, g.bin_items);
+    ORBC_LAUNCH(c, k_stencil_build, blocks_for(nc, kStencilWarps), kStencilWarps * 32, 0, c->centroid, nc, gd, c->stencil, c->stencil_cnt, c->d_flags);
+    c->stencil_valid = true;
+    return ORBC_OK;
+}
+
+// fit the uniform grid to the centroids' bounding box (host side, at upload); centroids that later drift outside are
+// clamped into the boundary bins, which keeps every search exact
+int fit_grid(orbc_ctx *c, const float *centroids3, int nc) {
+    float lo[3] = {1e30f, 1e30f, 1e30f}, hi[3] = {-1e30f, -1e30f, -1e30f};
+    for (int i = 0; i < nc; ++i) for (int d = 0; d < 3; ++d) {
+        const float v = centroids3[3 * i + d];
+        if (v == v) { lo[d] = std::min(lo[d], v); hi[d] = std::max(hi[d], v); }
+    }
+    for (int d = 0; d < 3; ++d) if (lo[d] > hi[d]) { lo[d] = 0; hi[d] = 0; }
+    Grid &g = c->grid;
+    float h = kBin;
+    const float margin = 4 * kBin;
+    for (;;) {
+        size_t nb = 1;
+        for (int d = 0; d < 3; ++d) {
+            g.lo[d] = lo[d] - margin;
+            g.dim[d] = std::max(1, (int)std::ceil((hi[d] - lo[d] + 2 * margin) / h));
+            nb *= (size_t)g.dim[d];
+        }
+        if (nb <= ((size_t)12 << 20)) { g.nbins = (int)nb; break; }
+        h *= 1.25f;
+    }
+    g.h = h;
+    if (g.cap_bins < (size_t)g.nbins + 1) { ORBC_TRY(dev_alloc(&g.bin_start, (size_t)g.nbins + 1)); g.cap_bins = (size_t)g.nbins + 1; }
+    return ORBC_OK;
+}
+
+// forcefield_canonical.h:23-28
+float pow_chain(float base, int expo) { return expo != 0 ? base * pow_chain(base, expo - 1) : 1.0f; }
+float ff_rep(float cut, float req, float eps) { return eps / pow_chain(cut - req, 8); }
+float ff_att(float cut, float req, float eps) { return (float)(-2.0 * eps / pow_chain(cut - req, 4)); }
+
+void fill_integ(IntegArgs &a, orbc_ctx *c, int sp, const orbc_step_params *p) {
+    Species &s = c->sp[sp];
+    a.x = s.X(); a.v = s.V(); a.f = s.f; a.nn = s.N(); a.o = s.O(); a.t = s.t;
+    a.n = s.n; a.species = sp;
+    a.dt = (float)p->dt; a.dt_d = p->dt;
+    for (int i = 0; i < kNType; ++i) a.gamma[i] = a.sigma[i] = 0.f;
+    a.zeta = p->zeta;
+    a.dlo = p->box_lo; a.dhi = p->box_hi; a.lo = (float)p->box_lo; a.hi = (float)p->box_hi;
+    a.dr_opt = p->dr_opt; a.dn_opt = p->dn_opt;
+    a.seed = p->seed; a.step = (uint32_t)p->nstep;
+    a.noise = nullptr; a.acc = c->d_acc; a.zeta_dev = nullptr;
+}
+
+orbc_forcefield g_host_ff;   // host copy of the table last installed (radius feeds the Langevin coefficients)
+
+// integrate_langevin.h:110-114: gamma = 6 pi eta R (fp64 -> fp32), sigma = sqrtf(2 kBT gamma) * sqrt(3 / dt)
+void langevin_coeffs(IntegArgs &a, const orbc_step_params *p) {
+    for (int i = 0; i < kNType; ++i) {
+        a.gamma[i] = (float)(6.0 * M_PI * p->eta * g_host_ff.radius[i]);
+        a.sigma[i] = (float)(std::sqrt((float)(2 * p->kBT * a.gamma[i])) * std::sqrt(3.0 / p->dt));
+    }
+}
+
+int launch_pairwise(orbc_ctx *c) {
+    Species &L = c->sp[0], &P = c->sp[1];
+    if (!c->n_cells || !L.has_partition) return fail(ORBC_ERR_ARG, "compute_pairwise_fused: no Voronoi partition (call orbc_voronoi_upload / orbc_rebuild first)");
+    if (P.n && !P.has_partition) return fail(ORBC_ERR_ARG, "compute_pairwise_fused: proteins are not partitioned");
+    PairArgs a;
+    a.xl = L.X(); a.nl = L.N(); a.cs_l = L.cell_start; a.cell_l = L.C(); a.n_l = (int)L.n;
+    a.xp = P.X(); a.np = P.N(); a.cs_p = P.cell_start; a.cell_p = P.C(); a.n_p = (int)P.n;
+    a.stencil = c->stencil; a.stencil_cnt = c->stencil_cnt;
+    a.fl = L.f; a.tl = L.t; a.fp = P.f; a.tp = P.t;
+    if (L.n) ORBC_LAUNCH(c, k_pair_lipid, blocks_for(L.n, 128), 128, 0, a);
+    if (P.n) ORBC_LAUNCH(c, k_pair_protein, blocks_for(P.n, 128), 128, 0, a);
+    return ORBC_OK;
+}
+
+int launch_bonded(orbc_ctx *c) {
+    Species &P = c->sp[1];
+    if (!c->n_bonds) return ORBC_OK;
+    ORBC_LAUNCH(c, k_bonded, blocks_for(c->n_bonds, kBlock), kBlock, 0, c->bonds, c->n_bonds, c->tag2idx, P.X(), P.f);
+    return ORBC_OK;
+}
+
+int build_tag2idx(orbc_ctx *c) {
+    Species &P = c->sp[1];
+    if (!P.n || !c->tag2idx) return ORBC_OK;
+    ORBC_LAUNCH(c, k_build_tag2idx, blocks_for(P.n, kBlock), kBlock, 0, P.N(), P.n, c->tag2idx, c->tag2idx_size, c->d_flags);
+    return ORBC_OK;
+}
+
+int do_voronoi_update(orbc_ctx *c, int nstep, int freq_sort_ctrd) {
+    Species &L = c->sp[0];
+    if (!c->n_cells || !L.has_partition) return fail(ORBC_ERR_ARG, "voronoi_update: no previous partition (orbc_voronoi_upload with cell_start first)");
+    const int nc = c->n_cells;
+    ORBC_LAUNCH(c, k_centroid_update, blocks_for(nc, kBlock), kBlock, 0, L.cell_start, L.X(), nc, c->centroid_tmp);
+    if (freq_sort_ctrd > 0 && nstep % freq_sort_ctrd == 0) {
+        ORBC_LAUNCH(c, k_morton_keys, blocks_for(nc, kBlock), kBlock, 0, c->centroid_tmp, nc, c->keys, c->perm);
+        ORBC_TRY(radix_sort_pairs(c, c->keys, c->perm, c->keys_tmp, c->perm_tmp, nc));
+        ORBC_LAUNCH(c, k_permute_centroids, blocks_for(nc, kBlock), kBlock, 0, c->centroid_tmp, c->perm, nc, c->centroid, c->inv);
+        // cells were renumbered: carry every particle's previous cell into the new numbering (it is only a search hint)
+        for (int s = 0; s < 2; ++s) if (c->sp[s].n) ORBC_LAUNCH(c, k_remap_cellid, blocks_for(c->sp[s].n, kBlock), kBlock, 0, c->sp[s].C(), c->sp[s].n, c->inv);
+    } else {
+        std::swap(c->centroid, c->centroid_tmp);
+    }
+    return build_index(c);
+}
+
+int do_cell_update(orbc_ctx *c, int sp) {
+    Species &S = c->sp[sp];
+    if (!c->n_cells || !c->stencil_valid) return fail(ORBC_ERR_ARG, "cell_update: no Voronoi diagram");
+    const int nc = c->n_cells;
+    if (!S.cell_start) ORBC_TRY(dev_alloc(&S.cell_start, (size_t)nc + 1));
+    ORBC_CUDA(cudaMemsetAsync(S.cell_start, 0, sizeof(int) * ((size_t)nc + 1), c->stream));
+    if (S.n) {
+        const GridDev gd = grid_dev(c);
+        ORBC_LAUNCH(c, k_assign_nearest, blocks_for(S.n, kBlock), kBlock, 0, S.X(), S.has_partition ? S.C() : nullptr, S.n, c->centroid, nc,
+                    c->stencil, c->stencil_cnt, gd, S.aff, S.li, S.cell_start, c->d_counters, c->d_flags);
+    }
+    ORBC_TRY(scan_exclusive(c, S.cell_start, nc));
+    if (S.n) {
+        ORBC_LAUNCH(c, k_cell_scatter, blocks_for(S.n, kBlock), kBlock, 0, S.aff, S.li, S.n, S.cell_start, S.cells_tmp);
+        ORBC_LAUNCH(c, k_cell_sort, blocks_for((size_t)nc * 32, kBlock), kBlock, 0, S.cell_start, nc, S.cells_tmp, S.cells);
+        const int nx = S.cur ^ 1;
+        ORBC_LAUNCH(c, k_gather_reorder, blocks_for(S.n, kBlock), kBlock, 0, S.cells, S.aff, S.n, S.X(), S.N(), S.V(), S.O(),
+                    S.x[nx], S.nn[nx], S.v[nx], S.o[nx], S.cellid[nx]);
+        S.cur = nx;
+    }
+    S.has_partition = true;
+    if (sp == ORBC_PROTEIN) ORBC_TRY(build_tag2idx(c));
+    return ORBC_OK;
+}
+
+int do_integrate_langevin(orbc_ctx *c, const orbc_step_params *p) {
+    for (int sp = 0; sp < 2; ++sp) {
+        Species &S = c->sp[sp];
+        if (!S.n) continue;
+        IntegArgs a; fill_integ(a, c, sp, p); langevin_coeffs(a, p);
+        const float *hn = sp == 0 ? p->noise_lipid : p->noise_protein;
+        if (hn) {
+            if (c->noise_cap[sp] < 3 * S.n) { ORBC_TRY(dev_alloc(&c->noise[sp], 3 * S.n)); c->noise_cap[sp] = 3 * S.n; }
+            ORBC_CUDA(cudaMemcpyAsync(c->noise[sp], hn, sizeof(float) * 3 * S.n, cudaMemcpyHostToDevice, c->stream));
+            a.noise = c->noise[sp];
+        }
+        ORBC_LAUNCH(c, k_verlet_langevin, blocks_for(S.n, 256), 256, 0, a);
+    }
+    return ORBC_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+const char *orbc_last_error(void) { return err_buf(); }
+
+int orbc_forcefield_canonical(orbc_forcefield *ff) {
+    // forcefield_canonical.h:30-156: the same constants and the same derivations (rep in fp32, att and lj_* in fp64)
+    if (!ff) return fail(ORBC_ERR_ARG, "null forcefield");
+    memset(ff, 0, sizeof(*ff));
+    const float mass[6] = {1, 4, 4, 1, 10, 10}, radius[6] = {0.56125f, 1.12375f, 1.12375f, 0.56125f, 1.5f, 0.5f};
+    const float cutlp[6] = {2.6f, 2.6f, 2.6f, 2.6f, 0, 0}, reqlp[6] = {1.1225f, 1.685f, 1.685f, 1.1225f, 0, 0};
+    const float epslp[6] = {1.2f, 1.4f, 2.8f, 2.8f, 0, 0}, alphalp[6] = {1.55f, 5, 5, 5, 0, 0};
+    for (int i = 0; i < 6; ++i) { ff->mass[i] = mass[i]; ff->radius[i] = radius[i]; ff->cutlp[i] = cutlp[i]; ff->alphalp[i] = alphalp[i]; }
+    for (int i = 0; i < 4; ++i) {
+        ff->cutsqlp[i] = cutlp[i] * cutlp[i];
+        ff->replp[i] = ff_rep(cutlp[i], reqlp[i], epslp[i]);
+        ff->attlp[i] = ff_att(cutlp[i], reqlp[i], epslp[i]);
+    }
+    ff->cutll = cutlp[0]; ff->cutsqll = ff->cutsqlp[0]; ff->repll = ff->replp[0]; ff->attll = ff->attlp[0]; ff->alphall = alphalp[0];
+    // protein-protein: row/column 0 repeat the lipid-protein entries, the 3x3 block {1,2,3}^2 has its own req, eps = 1
+    const float reqpp_in[3][3] = {{2.245f, 2.245f, 1.685f}, {2.245f, 2.245f, 1.685f}, {1.685f, 1.685f, 1.1225f}};
+    for (int r = 0; r < 4; ++r) for (int q = 0; q < 4; ++q) {
+        const int k = 6 * r + q;
+        if (r == 0 || q == 0) { const int t = r + q; ff->cutpp[k] = cutlp[t]; ff->cutsqpp[k] = ff->cutsqlp[t]; ff->reppp[k] = ff->replp[t]; }
+        else { ff->cutpp[k] = 2.6f; ff->cutsqpp[k] = 2.6f * 2.6f; ff->reppp[k] = ff_rep(2.6f, reqpp_in[r - 1][q - 1], 1.0f); }
+    }
+    // 12-6 LJ between {lipid, band-3} and {actin, spectrin}
+    const float c1 = 1.1225f, c34 = (float)(3.4 * 1.1225);
+    const float eps[36] = {0, 0, 0, 0, 1, 1, 0, 0, 0, 0, 1, 1, 0, 0, 0, 0, 1, 1, 0, 0, 0, 0, 0, 0, 1, 1, 1, 0, 0, 0, 1, 1, 1, 0, 0, 0};
+    const float sig[36] = {0, 0, 0, 0, 1, 1, 0, 0, 0, 0, 3.4f, 3.4f, 0, 0, 0, 0, 3.4f, 1, 0, 0, 0, 0, 0, 0, 1, 3.4f, 3.4f, 0, 3, 1.8f, 1, 3.4f, 1, 0, 1.8f, 1};
+    const float cut[36] = {0, 0, 0, 0, c1, c1, 0, 0, 0, 0, c34, c34, 0, 0, 0, 0, c34, c1, 0, 0, 0, 0, 0, 0, c1, c34, c34, 0, 0, 0, c1, c34, c1, 0, 0, 0};
+    for (int i = 0; i < 36; ++i) {
+        ff->lj_cutsq[i] = cut[i] * cut[i];
+        ff->lj_lj1[i] = (float)(48.0 * eps[i] * std::pow((double)sig[i], 12.0));
+        ff->lj_lj2[i] = (float)(24.0 * eps[i] * std::pow((double)sig[i], 6.0));
+    }
+    const float r0[4] = {2.25f, 1.1225f, 2.25f, 2.24f};
+    for (int i = 0; i < 4; ++i) { ff->r0[i] = r0[i]; ff->K[i] = 57.f; }
+    return ORBC_OK;
+}
+
+int orbc_set_forcefield(orbc_ctx *c, const orbc_forcefield *ff) {
+    if (!c || !ff) return fail(ORBC_ERR_ARG, "null argument");
+    ORBC_CUDA(cudaMemcpyToSymbolAsync(c_ff, ff, sizeof(*ff), 0, cudaMemcpyHostToDevice, c->stream));
+    ORBC_CUDA(cudaStreamSynchronize(c->stream));
+    g_host_ff = *ff;
+    c->ff_set = true;
+    return ORBC_OK;
+}
+
+int orbc_create(orbc_ctx **out, int device) {
+    if (!out) return fail(ORBC_ERR_ARG, "null ctx pointer");
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) return fail(ORBC_ERR_NO_DEVICE, "no CUDA device: this library has no CPU fallback");
+    if (device < 0 || device >= n_dev) return fail(ORBC_ERR_ARG, "device %d out of range (%d devices)", device, n_dev);
+    ORBC_CUDA(cudaSetDevice(device));
+    orbc_ctx *c = new orbc_ctx();
+    c->device = device;
+    ORBC_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
+    for (auto &e : c->ev) ORBC_CUDA(cudaEventCreate(&e));
+    ORBC_TRY(dev_alloc(&c->d_acc, 8)); ORBC_TRY(dev_alloc(&c->d_counters, 8)); ORBC_TRY(dev_alloc(&c->d_flags, 4)); ORBC_TRY(dev_alloc(&c->d_nh, 2));
+    ORBC_CUDA(cudaMemset(c->d_acc, 0, 8 * sizeof(double))); ORBC_CUDA(cudaMemset(c->d_counters, 0, 8 * sizeof(unsigned long long)));
+    ORBC_CUDA(cudaMemset(c->d_flags, 0, 4 * sizeof(int))); ORBC_CUDA(cudaMemset(c->d_nh, 0, 2 * sizeof(float)));
+    ORBC_CUDA(cudaMallocHost((void **)&c->h_acc, 8 * sizeof(double))); ORBC_CUDA(cudaMallocHost((void **)&c->h_flags, 4 * sizeof(int)));
+    ORBC_CUDA(cudaMallocHost((void **)&c->h_counters, 8 * sizeof(unsigned long long))); ORBC_CUDA(cudaMallocHost((void **)&c->h_nh, 2 * sizeof(float)));
+    orbc_forcefield ff; orbc_forcefield_canonical(&ff);
+    *out = c;
+    return orbc_set_forcefield(c, &ff);
+}
+
+void orbc_destroy(orbc_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    free_species(c->sp[0]); free_species(c->sp[1]);
+    dev_free(c->centroid); dev_free(c->centroid_tmp); dev_free(c->keys); dev_free(c->keys_tmp); dev_free(c->perm); dev_free(c->perm_tmp); dev_free(c->inv);
+    dev_free(c->grid.bin_start); dev_free(c->grid.bin_items); dev_free(c->grid.bin_of); dev_free(c->grid.bin_slot);
+    dev_free(c->stencil); dev_free(c->stencil_cnt); dev_free(c->cell_normal); dev_free(c->bonds); dev_free(c->tag2idx);
+    dev_free(c->scan_tmp); dev_free(c->radix_hist); dev_free(c->stage); dev_free(c->d_acc); dev_free(c->d_counters); dev_free(c->d_flags); dev_free(c->d_nh);
+    dev_free(c->noise[0]); dev_free(c->noise[1]);
+    if (c->h_acc) cudaFreeHost(c->h_acc); if (c->h_flags) cudaFreeHost(c->h_flags); if (c->h_counters) cudaFreeHost(c->h_counters); if (c->h_nh) cudaFreeHost(c->h_nh);
+    for (auto &e : c->ev) if (e) cudaEventDestroy(e);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+}
+
+int orbc_synchronize(orbc_ctx *c) { ORBC_CUDA(cudaStreamSynchronize(c->stream)); return check_flags(c); }
+int orbc_set_stream(orbc_ctx *c, void *s) { ORBC_CUDA(cudaStreamSynchronize(c->stream)); c->stream = s ? (cudaStream_t)s : c->own_stream; return ORBC_OK; }
+
+int orbc_upload(orbc_ctx *c, int sp, size_t n, size_t stride, const float *x, const float *v, const float *n_, const float *o, const int *type, const int *tag) {
+    if (!c || sp < 0 || sp > 1 || stride < 3) return fail(ORBC_ERR_ARG, "orbc_upload: bad argument");
+    if (n && (!x || !n_)) return fail(ORBC_ERR_ARG, "orbc_upload: x and n are required");
+    if (n >= (size_t)1 << 31) return fail(ORBC_ERR_ARG, "orbc_upload: more than 2^31 particles per container");
+    Species &S = c->sp[sp];
+    ORBC_TRY(alloc_species(c, S, n));
+    if (!n) return ORBC_OK;
+    ORBC_TRY(ensure_stage(c, n * stride + 2 * n));
+    int *w = (int *)(c->stage + n * stride);
+    const unsigned nb = blocks_for(n, kBlock);
+    auto put = [&](const float *src, float4 *dst, const int *wsrc) -> int {
+        const int *wd = nullptr;
+        if (wsrc) { ORBC_CUDA(cudaMemcpyAsync(w, wsrc, sizeof(int) * n, cudaMemcpyHostToDevice, c->stream)); wd = w; }
+        if (src) {
+            ORBC_CUDA(cudaMemcpyAsync(c->stage, src, sizeof(float) * n * stride, cudaMemcpyHostToDevice, c->stream));
+            ORBC_LAUNCH(c, k_pack4, nb, kBlock, 0, c->stage, stride, n, dst, wd);
+        } else ORBC_LAUNCH(c, k_zero4, nb, kBlock, 0, dst, n, wd);
+        return ORBC_OK;
+    };
+    ORBC_TRY(put(x, S.X(), type));
+    ORBC_TRY(put(n_, S.N(), tag));
+    ORBC_TRY(put(v, S.V(), nullptr));
+    ORBC_TRY(put(o, S.O(), nullptr));
+    ORBC_LAUNCH(c, k_zero4, nb, kBlock, 0, S.f, n, (const int *)nullptr);
+    ORBC_LAUNCH(c, k_zero4, nb, kBlock, 0, S.t, n, (const int *)nullptr);
+    ORBC_LAUNCH(c, k_fill_int, nb, kBlock, 0, S.C(), n, -1);
+    ORBC_CUDA(cudaStreamSynchronize(c->stream));   // host arrays are borrowed only for the duration of the call
+    if (sp == ORBC_PROTEIN && tag) {
+        int mx = 0;
+        for (size_t i = 0; i < n; ++i) { if (tag[i] < 0) return fail(ORBC_ERR_ARG, "negative protein tag"); mx = std::max(mx, tag[i]); }
+        if (c->tag2idx_size < (size_t)mx + 1) { ORBC_TRY(dev_alloc(&c->tag2idx, (size_t)mx + 1)); c->tag2idx_size = (size_t)mx + 1; }
+        ORBC_CUDA(cudaMemsetAsync(c->tag2idx, 0xff, sizeof(int) * c->tag2idx_size, c->stream));
+        ORBC_TRY(build_tag2idx(c));
+    }
+    return ORBC_OK;
+}
+
+int orbc_upload_bonds(orbc_ctx *c, size_t n_bonds, const int *tij) {
+    if (!c || (n_bonds && !tij)) return fail(ORBC_ERR_ARG, "orbc_upload_bonds: bad argument");
+    for (size_t b = 0; b < n_bonds; ++b) {
+        if (tij[3 * b] < 0 || tij[3 * b] >= 4) return fail(ORBC_ERR_ARG, "bond %zu has type %d outside [0,4)", b, tij[3 * b]);
+        if ((size_t)tij[3 * b + 1] >= c->tag2idx_size || (size_t)tij[3 * b + 2] >= c->tag2idx_size || tij[3 * b + 1] < 0 || tij[3 * b + 2] < 0)
+            return fail(ORBC_ERR_ARG, "bond %zu refers to a tag that no uploaded protein carries (upload proteins first)", b);
+    }
+    ORBC_TRY(dev_alloc(&c->bonds, 3 * n_bonds));
+    if (n_bonds) ORBC_CUDA(cudaMemcpyAsync(c->bonds, tij, sizeof(int) * 3 * n_bonds, cudaMemcpyHostToDevice, c->stream));
+    ORBC_CUDA(cudaStreamSynchronize(c->stream));
+    c->n_bonds = n_bonds;
+    return ORBC_OK;
+}
+
+int orbc_voronoi_upload(orbc_ctx *c, int nc, const float *centroids3, const int *csl, const int *csp) {
+    if (!c || nc <= 0 || !centroids3) return fail(ORBC_ERR_ARG, "orbc_voronoi_upload: bad argument");
+    if (nc >= (1 << 28)) return fail(ORBC_ERR_ARG, "more than 2^28 Voronoi cells");
+    if (nc != c->n_cells) {
+        ORBC_TRY(dev_alloc(&c->centroid, nc)); ORBC_TRY(dev_alloc(&c->centroid_tmp, nc));
+        ORBC_TRY(dev_alloc(&c->keys, nc)); ORBC_TRY(dev_alloc(&c->keys_tmp, nc)); ORBC_TRY(dev_alloc(&c->perm, nc)); ORBC_TRY(dev_alloc(&c->perm_tmp, nc)); ORBC_TRY(dev_alloc(&c->inv, nc));
+        ORBC_TRY(dev_alloc(&c->grid.bin_items, nc)); ORBC_TRY(dev_alloc(&c->grid.bin_of, nc)); ORBC_TRY(dev_alloc(&c->grid.bin_slot, nc));
+        ORBC_TRY(dev_alloc(&c->stencil, (size_t)nc * kStencilStride)); ORBC_TRY(dev_alloc(&c->stencil_cnt, nc));
+        ORBC_TRY(dev_alloc(&c->cell_normal, nc));
+        for (int s = 0; s < 2; ++s) ORBC_TRY(dev_alloc(&c->sp[s].cell_start, (size_t)nc + 1));
+        c->n_cells = nc;
+    }
+    ORBC_CUDA(cudaMemsetAsync(c->cell_normal, 0, sizeof(float4) * nc, c->stream));
+    ORBC_TRY(ensure_stage(c, (size_t)3 * nc));
+    ORBC_CUDA(cudaMemcpyAsync(c->stage, centroids3, sizeof(float) * 3 * nc, cudaMemcpyHostToDevice, c->stream));
+    ORBC_LAUNCH(c, k_pack4, blocks_for(nc, kBlock), kBlock, 0, c->stage, (size_t)3, (size_t)nc, c->centroid, (const int *)nullptr);
+    ORBC_TRY(fit_grid(c, centroids3, nc));
+    for (int s = 0; s < 2; ++s) {
+        Species &S = c->sp[s];
+        const int *cs = s == 0 ? csl : csp;
+        S.has_partition = false;
+        if (cs) {
+            if ((size_t)cs[nc] != S.n || cs[0] != 0) return fail(ORBC_ERR_ARG, "cell_start of species %d does not cover its %zu particles", s, S.n);
+            ORBC_CUDA(cudaMemcpyAsync(S.cell_start, cs, sizeof(int) * ((size_t)nc + 1), cudaMemcpyHostToDevice, c->stream));
+            if (S.n) ORBC_LAUNCH(c, k_fill_cellid, blocks_for(nc, kBlock), kBlock, 0, S.cell_start, nc, S.C());
+            S.has_partition = true;
+        }
+    }
+    ORBC_TRY(build_index(c));
+    ORBC_CUDA(cudaStreamSynchronize(c->stream));   // host arrays are borrowed only for the duration of the call
+    return ORBC_OK;
+}
+
+int orbc_set_field(orbc_ctx *c, int sp, char field, size_t stride, const float *src) {
+    if (!c || sp < 0 || sp > 1 || stride < 3 || !src) return fail(ORBC_ERR_ARG, "orbc_set_field: bad argument");
+    Species &S = c->sp[sp];
+    float4 *dst = field == 'f' ? S.f : field == 't' ? S.t : field == 'v' ? S.V() : field == 'x' ? S.X() : field == 'n' ? S.N() : field == 'o' ? S.O() : nullptr;
+    if (!dst) return fail(ORBC_ERR_ARG, "orbc_set_field: unknown field '%c'", field);
+    if (!S.n) return ORBC_OK;
+    ORBC_TRY(ensure_stage(c, S.n * stride));
+    ORBC_CUDA(cudaMemcpyAsync(c->stage, src, sizeof(float) * S.n * stride, cudaMemcpyHostToDevice, c->stream));
+    ORBC_LAUNCH(c, k_set3, blocks_for(S.n, kBlock), kBlock, 0, c->stage, stride, S.n, dst);
+    ORBC_CUDA(cudaStreamSynchronize(c->stream));
+    return ORBC_OK;
+}
+
+int orbc_voronoi_update(orbc_ctx *c, int nstep, int freq_sort_ctrd) { if (!c) return fail(ORBC_ERR_ARG, "null ctx"); return do_voronoi_update(c, nstep, freq_sort_ctrd); }
+
+int orbc_cell_update(orbc_ctx *c, int sp, int nstep, int freq_sort_bond) {
+    (void)nstep; (void)freq_sort_bond;   // reorder_bond (reorder.h:33-68) only permutes bond storage for CPU cache locality
+    if (!c || sp < 0 || sp > 1) return fail(ORBC_ERR_ARG, "orbc_cell_update: bad argument");
+    return do_cell_update(c, sp);
+}
+
+int orbc_rebuild(orbc_ctx *c, int nstep, int freq_sort_ctrd, int freq_sort_bond) {
+    (void)freq_sort_bond;
+    if (!c) return fail(ORBC_ERR_ARG, "null ctx");
+    ORBC_TRY(do_voronoi_update(c, nstep, freq_sort_ctrd));
+    ORBC_TRY(do_cell_update(c, ORBC_LIPID));
+    return do_cell_update(c, ORBC_PROTEIN);
+}
+
+int orbc_delete_lipid(orbc_ctx *c, float tol, size_t *n_out) {
+    if (!c) return fail(ORBC_ERR_ARG, "null ctx");
+    Species &L = c->sp[0];
+    if (!L.has_partition) return fail(ORBC_ERR_ARG, "delete_lipid: lipids are not partitioned");
+    const int nc = c->n_cells;
+    const size_t n = L.n;
+    int *keep = L.aff, *newpos = L.li;
+    ORBC_LAUNCH(c, k_stray_mask, blocks_for((size_t)nc * 32, kBlock), kBlock, 0, L.cell_start, nc, c->centroid, L.X(), tol, keep);
+    ORBC_CUDA(cudaMemcpyAsync(newpos, keep, sizeof(int) * n, cudaMemcpyDeviceToDevice, c->stream));
+    ORBC_TRY(scan_exclusive(c, newpos, (int)n));
+    int total = 0;
+    ORBC_CUDA(cudaMemcpyAsync(&total, newpos + n, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    ORBC_CUDA(cudaStreamSynchronize(c->stream));
+    if ((size_t)total < n) {
+        const int nx = L.cur ^ 1;
+        ORBC_LAUNCH(c, k_compact, blocks_for(n, kBlock), kBlock, 0, keep, newpos, n, L.X(), L.N(), L.V(), L.O(), L.C(),
+                    L.x[nx], L.nn[nx], L.v[nx], L.o[nx], L.cellid[nx]);
+        L.cur = nx; L.n = (size_t)total;
+        // f and t are zero at this point of the loop (cleared by the integrator); keep them so for the survivors
+        ORBC_LAUNCH(c, k_zero4, blocks_for(n, kBlock), kBlock, 0, L.f, n, (const int *)nullptr);
+        ORBC_LAUNCH(c, k_zero4, blocks_for(n, kBlock), kBlock, 0, L.t, n, (const int *)nullptr);
+        ORBC_TRY(do_cell_update(c, ORBC_LIPID));   // cleanup.h:85
+    }
+    if (n_out) *n_out = L.n;
+    return ORBC_OK;
+}
+
+int orbc_compute_pairwise_fused(orbc_ctx *c) { if (!c) return fail(ORBC_ERR_ARG, "null ctx"); return launch_pairwise(c); }
+int orbc_compute_bonded(orbc_ctx *c) { if (!c) return fail(ORBC_ERR_ARG, "null ctx"); return launch_bonded(c); }
+
+int orbc_constrain_volume(orbc_ctx *c, float target, float strength, float *volume_out) {
+    if (!c) return fail(ORBC_ERR_ARG, "null ctx");
+    Species &L = c->sp[0], &P = c->sp[1];
+    if (!L.has_partition) return fail(ORBC_ERR_ARG, "constrain_volume: lipids are not partitioned");
+    const int nc = c->n_cells;
+    ORBC_CUDA(cudaMemsetAsync(c->d_acc + 1, 0, 4 * sizeof(double), c->stream));
+    ORBC_LAUNCH(c, k_cv_center, blocks_for(nc, 256), 256, 0, c->centroid, nc, c->d_acc);
+    ORBC_LAUNCH(c, k_cv_normal_volume, blocks_for(nc, 256), 256, 0, c->centroid, nc, L.cell_start, L.N(), c->cell_normal, c->d_acc);
+    if (L.n) ORBC_LAUNCH(c, k_cv_apply, blocks_for(L.n, kBlock), kBlock, 0, L.C(), L.n, c->cell_normal, (const float4 *)nullptr, (size_t)0, target, strength, c->d_acc, L.f);
+    if (P.n && P.has_partition) ORBC_LAUNCH(c, k_cv_apply, blocks_for(P.n, kBlock), kBlock, 0, P.C(), P.n, c->cell_normal, P.X(), P.n, target, strength, c->d_acc, P.f);
+    if (volume_out) {
+        ORBC_CUDA(cudaMemcpyAsync(c->h_acc, c->d_acc, 8 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        ORBC_CUDA(cudaStreamSynchronize(c->stream));
+        *volume_out = (float)c->h_acc[4];
+    }
+    return ORBC_OK;
+}
+
+float orbc_nh_zeta_update(float zeta, float *Q, double dt, float kBT, double ke, long n) {
+    // destructor of verlet_initial_bounce_clearforce_update / post_toque_final_update (integrate_nh.h:181-185, 240-244)
+    if (!*Q) *Q = (float)(n * 0.01);
+    zeta += 0.5 * dt / *Q * (ke - 0.5 * 3.0 * n * kBT);
+    return zeta;
+}
+
+int orbc_integrate(orbc_ctx *c, int kernel, const orbc_step_params *p, orbc_step_result *res) {
+    if (!c) return fail(ORBC_ERR_ARG, "null ctx");
+    const bool needs_p = kernel != ORBC_CLEAR_FORCE && kernel != ORBC_POST_TORQUE;
+    if (needs_p && !p) return fail(ORBC_ERR_ARG, "orbc_integrate: this kernel needs step parameters");
+    const bool reduces = kernel == ORBC_NH_INITIAL_FUSED || kernel == ORBC_NH_FINAL_FUSED || kernel == ORBC_NH_UPDATE;
+    if (reduces) ORBC_CUDA(cudaMemsetAsync(c->d_acc, 0, sizeof(double), c->stream));
+    if (kernel == ORBC_VERLET_LANGEVIN) ORBC_TRY(do_integrate_langevin(c, p));
+    else for (int sp = 0; sp < 2; ++sp) {
+        Species &S = c->sp[sp];
+        if (!S.n) continue;
+        const unsigned nb = blocks_for(S.n, 256);
+        IntegArgs a;
+        if (p) fill_integ(a, c, sp, p);
+        switch (kernel) {
+        case ORBC_CLEAR_FORCE: ORBC_LAUNCH(c, k_clear_force, nb, 256, 0, S.f, S.t, S.n); break;
+        case ORBC_POST_TORQUE: ORBC_LAUNCH(c, k_post_torque, nb, 256, 0, S.N(), S.t, S.n); break;
+        case ORBC_BOUNCE_BACK: ORBC_LAUNCH(c, k_bounce_back, nb, 256, 0, a); break;
+        case ORBC_NH_INITIAL_FUSED: ORBC_LAUNCH(c, k_nh_initial_fused, nb, 256, 0, a); break;
+        case ORBC_NH_FINAL_FUSED: ORBC_LAUNCH(c, k_nh_final_fused, nb, 256, 0, a); break;
+        case ORBC_NH_FINAL: ORBC_LAUNCH(c, k_nh_final, nb, 256, 0, a); break;
+        case ORBC_NH_UPDATE: ORBC_LAUNCH(c, k_kinetic, nb, 256, 0, S.X(), S.V(), S.n, 0.5f, c->d_acc); break;
+        case ORBC_OPT_MOVE: ORBC_LAUNCH(c, k_opt_move, nb, 256, 0, a); break;
+        default: return fail(ORBC_ERR_ARG, "orbc_integrate: unknown kernel id %d", kernel);
+        }
+    }
+    if (res) {
+        res->ke = 0.0; res->n = (long)(c->sp[0].n + c->sp[1].n);
+        if (reduces) {
+            ORBC_CUDA(cudaMemcpyAsync(c->h_acc, c->d_acc, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+            ORBC_CUDA(cudaStreamSynchronize(c->stream));
+            res->ke = c->h_acc[0];
+        }
+    }
+    return ORBC_OK;
+}
+
+int orbc_compute_temperature(orbc_ctx *c, double *T) {
+    if (!c || !T) return fail(ORBC_ERR_ARG, "null argument");
+    ORBC_CUDA(cudaMemsetAsync(c->d_acc, 0, sizeof(double), c->stream));
+    size_t n = 0;
+    for (int sp = 0; sp < 2; ++sp) {
+        Species &S = c->sp[sp];
+        n += S.n;
+        if (S.n) ORBC_LAUNCH(c, k_kinetic, blocks_for(S.n, 256), 256, 0, S.X(), S.V(), S.n, 1.0f, c->d_acc);
+    }
+    ORBC_CUDA(cudaMemcpyAsync(c->h_acc, c->d_acc, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    ORBC_CUDA(cudaStreamSynchronize(c->stream));
+    *T = c->h_acc[0] / (3.0 * (double)n);
+    return ORBC_OK;
+}
+
+int orbc_run_langevin(orbc_ctx *c, const orbc_step_params *p, int n_steps, int freq_voronoi, int freq_sort_ctrd) {
+    if (!c || !p || freq_voronoi <= 0) return fail(ORBC_ERR_ARG, "orbc_run_langevin: bad argument");
+    orbc_step_params q = *p;
+    q.noise_lipid = q.noise_protein = nullptr;
+    for (int s = 0; s < n_steps; ++s, ++q.nstep) {
+        if (q.nstep % freq_voronoi == 0) {
+            ORBC_TRY(do_voronoi_update(c, q.nstep, freq_sort_ctrd));
+            ORBC_TRY(do_cell_update(c, ORBC_LIPID));
+            ORBC_TRY(do_cell_update(c, ORBC_PROTEIN));
+        }
+        ORBC_TRY(launch_pairwise(c));
+        ORBC_TRY(launch_bonded(c));
+        ORBC_TRY(do_integrate_langevin(c, &q));
+    }
+    return ORBC_OK;
+}
+
+int orbc_run_nh(orbc_ctx *c, const orbc_step_params *p, int n_steps, int freq_voronoi, int freq_sort_ctrd, float *zeta_io, float *Q_io) {
+    if (!c || !p || !zeta_io || !Q_io || freq_voronoi <= 0) return fail(ORBC_ERR_ARG, "orbc_run_nh: bad argument");
+    c->h_nh[0] = *zeta_io; c->h_nh[1] = *Q_io;
+    ORBC_CUDA(cudaMemcpyAsync(c->d_nh, c->h_nh, 2 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    ORBC_CUDA(cudaMemsetAsync(c->d_acc, 0, sizeof(double), c->stream));
+    orbc_step_params q = *p;
+    const long n = (long)(c->sp[0].n + c->sp[1].n);
+    for (int s = 0; s < n_steps; ++s, ++q.nstep) {
+        for (int sp = 0; sp < 2; ++sp) if (c->sp[sp].n) {
+            IntegArgs a; fill_integ(a, c, sp, &q); a.zeta_dev = c->d_nh;
+            ORBC_LAUNCH(c, k_nh_initial_fused, blocks_for(c->sp[sp].n, 256), 256, 0, a);
+        }
+        ORBC_LAUNCH(c, k_nh_zeta_update, 1, 32, 0, c->d_nh, c->d_acc, q.dt, q.kBT, n);
+        if (q.nstep % freq_voronoi == 0) {
+            ORBC_TRY(do_voronoi_update(c, q.nstep, freq_sort_ctrd));
+            ORBC_TRY(do_cell_update(c, ORBC_LIPID));
+            ORBC_TRY(do_cell_update(c, ORBC_PROTEIN));
+        }
+        ORBC_TRY(launch_pairwise(c));
+        ORBC_TRY(launch_bonded(c));
+        for (int sp = 0; sp < 2; ++sp) if (c->sp[sp].n) {
+            IntegArgs a; fill_integ(a, c, sp, &q); a.zeta_dev = c->d_nh;
+            ORBC_LAUNCH(c, k_nh_final_fused, blocks_for(c->sp[sp].n, 256), 256, 0, a);
+        }
+        ORBC_LAUNCH(c, k_nh_zeta_update, 1, 32, 0, c->d_nh, c->d_acc, q.dt, q.kBT, n);
+    }
+    ORBC_CUDA(cudaMemcpyAsync(c->h_nh, c->d_nh, 2 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    ORBC_CUDA(cudaStreamSynchronize(c->stream));
+    *zeta_io = c->h_nh[0]; *Q_io = c->h_nh[1];
+    return check_flags(c);
+}
+
+int orbc_size(orbc_ctx *c, int sp, size_t *n) { if (!c || sp < 0 || sp > 1 || !n) return fail(ORBC_ERR_ARG, "bad argument"); *n = c->sp[sp].n; return ORBC_OK; }
+int orbc_n_cells(orbc_ctx *c, int *n) { if (!c || !n) return fail(ORBC_ERR_ARG, "bad argument"); *n = c->n_cells; return ORBC_OK; }
+
+int orbc_download(orbc_ctx *c, int sp, size_t stride, float *x, float *v, float *n_, float *o, float *f, float *t,
+                  int *affiliation, int *type, int *tag, size_t *n_out) {
+    if (!c || sp < 0 || sp > 1 || stride < 3) return fail(ORBC_ERR_ARG, "orbc_download: bad argument");
+    Species &S = c->sp[sp];
+    if (n_out) *n_out = S.n;
+    if (!S.n) return check_flags(c);
+    ORBC_TRY(ensure_stage(c, S.n * stride));
+    const unsigned nb = blocks_for(S.n, kBlock);
+    auto get3 = [&](const float4 *src, float *dst) -> int {
+        if (!dst) return ORBC_OK;
+        ORBC_LAUNCH(c, k_unpack3, nb, kBlock, 0, src, S.n, stride, c->stage);
+        ORBC_CUDA(cudaMemcpyAsync(dst, c->stage, sizeof(float) * S.n * stride, cudaMemcpyDeviceToHost, c->stream));
+        ORBC_CUDA(cudaStreamSynchronize(c->stream));
+        return ORBC_OK;
+    };
+    auto getw = [&](const float4 *src, int *dst) -> int {
+        if (!dst) return ORBC_OK;
+        ORBC_LAUNCH(c, k_unpack_w, nb, kBlock, 0, src, S.n, (int *)c->stage);
+        ORBC_CUDA(cudaMemcpyAsync(dst, c->stage, sizeof(int) * S.n, cudaMemcpyDeviceToHost, c->stream));
+        ORBC_CUDA(cudaStreamSynchronize(c->stream));
+        return ORBC_OK;
+    };
+    ORBC_TRY(get3(S.X(), x)); ORBC_TRY(get3(S.V(), v)); ORBC_TRY(get3(S.N(), n_)); ORBC_TRY(get3(S.O(), o)); ORBC_TRY(get3(S.f, f)); ORBC_TRY(get3(S.t, t));
+    ORBC_TRY(getw(S.X(), type)); ORBC_TRY(getw(S.N(), tag));
+    if (affiliation) {
+        ORBC_CUDA(cudaMemcpyAsync(affiliation, S.C(), sizeof(int) * S.n, cudaMemcpyDeviceToHost, c->stream));
+        ORBC_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    return check_flags(c);
+}
+
+int orbc_debug_dump(orbc_ctx *c, int what, void *dst, size_t bytes) {
+    if (!c || !dst) return fail(ORBC_ERR_ARG, "bad argument");
+    const int nc = c->n_cells;
+    const void *src = nullptr; size_t need = 0;
+    switch (what) {
+    case ORBC_DUMP_CENTROIDS: {
+        need = sizeof(float) * 3 * nc;
+        if (bytes < need) return fail(ORBC_ERR_ARG, "dump buffer too small");
+        ORBC_TRY(ensure_stage(c, (size_t)3 * nc));
+        ORBC_LAUNCH(c, k_unpack3, blocks_for(nc, kBlock), kBlock, 0, c->centroid, (size_t)nc, (size_t)3, c->stage);
+        src = c->stage; break; }
+    case ORBC_DUMP_CELL_START_L: src = c->sp[0].cell_start; need = sizeof(int) * ((size_t)nc + 1); break;
+    case ORBC_DUMP_CELL_START_P: src = c->sp[1].cell_start; need = sizeof(int) * ((size_t)nc + 1); break;
+    case ORBC_DUMP_CELLS_L: src = c->sp[0].cells; need = sizeof(int) * c->sp[0].n; break;
+    case ORBC_DUMP_CELLS_P: src = c->sp[1].cells; need = sizeof(int) * c->sp[1].n; break;
+    case ORBC_DUMP_AFF_L: src = c->sp[0].aff; need = sizeof(int) * c->sp[0].n; break;
+    case ORBC_DUMP_AFF_P: src = c->sp[1].aff; need = sizeof(int) * c->sp[1].n; break;
+    case ORBC_DUMP_MORTON_KEYS:
+        need = sizeof(uint32_t) * nc;
+        ORBC_LAUNCH(c, k_morton_keys_only, blocks_for(nc, kBlock), kBlock, 0, c->centroid, nc, c->keys_tmp);
+        src = c->keys_tmp; break;
+    case ORBC_DUMP_MORTON_PERM: src = c->perm; need = sizeof(int) * nc; break;
+    case ORBC_DUMP_STENCIL_COUNTS: {
+        need = sizeof(int) * 3 * nc;
+        if (bytes < need) return fail(ORBC_ERR_ARG, "dump buffer too small");
+        std::vector<int> packed(nc);
+        ORBC_CUDA(cudaMemcpyAsync(packed.data(), c->stencil_cnt, sizeof(int) * nc, cudaMemcpyDeviceToHost, c->stream));
+        ORBC_CUDA(cudaStreamSynchronize(c->stream));
+        int *o = (int *)dst;
+        for (int i = 0; i < nc; ++i) { o[3 * i] = packed[i] & 255; o[3 * i + 1] = (packed[i] >> 8) & 255; o[3 * i + 2] = packed[i] >> 16; }
+        return check_flags(c); }
+    case ORBC_DUMP_STENCIL: src = c->stencil; need = sizeof(int) * (size_t)nc * kStencilStride; break;
+    case ORBC_DUMP_TAG2IDX: src = c->tag2idx; need = sizeof(int) * c->tag2idx_size; break;
+    case ORBC_DUMP_COUNTERS: src = c->d_counters; need = 8 * sizeof(unsigned long long); break;
+    default: return fail(ORBC_ERR_ARG, "unknown dump id %d", what);
+    }
+    if (bytes < need) return fail(ORBC_ERR_ARG, "dump buffer too small: %zu < %zu", bytes, need);
+    if (need) ORBC_CUDA(cudaMemcpyAsync(dst, src, need, cudaMemcpyDeviceToHost, c->stream));
+    ORBC_CUDA(cudaStreamSynchronize(c->stream));
+    return check_flags(c);
+}
+
+int orbc_debug_noise(orbc_ctx *c, uint64_t seed, int nstep, int species, size_t n, float *dst) {
+    if (!c || !dst) return fail(ORBC_ERR_ARG, "bad argument");
+    ORBC_TRY(ensure_stage(c, 3 * n));
+    ORBC_LAUNCH(c, k_noise, blocks_for(n, kBlock), kBlock, 0, seed, (uint32_t)nstep, (uint32_t)species, n, c->stage);
+    ORBC_CUDA(cudaMemcpyAsync(dst, c->stage, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, c->stream));
+    ORBC_CUDA(cudaStreamSynchronize(c->stream));
+    return ORBC_OK;
+}
+
+int orbc_event_record(orbc_ctx *c, int slot) {
+    if (!c || slot < 0 || slot >= 16) return fail(ORBC_ERR_ARG, "bad event slot");
+    ORBC_CUDA(cudaEventRecord(c->ev[slot], c->stream));
+    return ORBC_OK;
+}
+int orbc_event_elapsed_ms(orbc_ctx *c, int a, int b, float *ms) {
+    if (!c || a < 0 || a >= 16 || b < 0 || b >= 16 || !ms) return fail(ORBC_ERR_ARG, "bad event slot");
+    ORBC_CUDA(cudaEventSynchronize(c->ev[b]));
+    ORBC_CUDA(cudaEventElapsedTime(ms, c->ev[a], c->ev[b]));
+    return ORBC_OK;
+}
+int orbc_launch_count(orbc_ctx *c, unsigned long long *n) { if (!c || !n) return fail(ORBC_ERR_ARG, "bad argument"); *n = c->launches; return ORBC_OK; }
+
+} // extern "C"

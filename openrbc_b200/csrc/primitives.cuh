@@ -1,0 +1,147 @@
+// primitives.cuh — hand-written device-wide exclusive scan and stable LSD radix sort (key,value pairs).
+// Used by the spatial-index rebuild: counting sort of centroids into grid bins, counting sort of particles into
+// Voronoi cells (voronoi.h:217-231) and the Morton sort of the centroids (reorder_morton.h:44-122).
+#pragma once
+#include "common.cuh"
+
+namespace orbc {
+
+constexpr int kScanThreads = 1024;
+constexpr int kScanItems = 4;
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+// exclusive scan of `v` across the block; returns the exclusive prefix for this thread and the block total
+__device__ __forceinline__ int block_exclusive_scan(int v, int &total) {
+    __shared__ int warp_sums[33];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    int incl = v;
+    #pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { int y = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += y; }
+    if (lane == 31) warp_sums[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        const int w = lane < nw ? warp_sums[lane] : 0;
+        int wi = w;
+        #pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { int y = __shfl_up_sync(0xffffffffu, wi, d); if (lane >= d) wi += y; }
+        warp_sums[lane] = wi - w;             // exclusive warp offsets
+        if (lane == 31) warp_sums[32] = wi;   // block total
+    }
+    __syncthreads();
+    total = warp_sums[32];
+    return warp_sums[wid] + incl - v;
+}
+
+__global__ void __launch_bounds__(kScanThreads) k_scan_tile_sums(const int *__restrict__ data, int n, int *__restrict__ tile_sums) {
+    const int base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
+    int s = 0;
+    #pragma unroll
+    for (int k = 0; k < kScanItems; ++k) if (base + k < n) s += data[base + k];
+    int total; block_exclusive_scan(s, total);
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(kScanThreads) k_scan_sums(int *__restrict__ tile_sums, int n_tiles) {
+    // single block: up to kScanTile tiles
+    const int base = threadIdx.x * kScanItems;
+    int v[kScanItems], s = 0;
+    #pragma unroll
+    for (int k = 0; k < kScanItems; ++k) { v[k] = base + k < n_tiles ? tile_sums[base + k] : 0; s += v[k]; }
+    int total; int off = block_exclusive_scan(s, total);
+    #pragma unroll
+    for (int k = 0; k < kScanItems; ++k) { if (base + k < n_tiles) tile_sums[base + k] = off; off += v[k]; }
+    if (threadIdx.x == 0) tile_sums[n_tiles] = total;
+}
+
+// data[0..n) counts -> exclusive offsets in place; data[n] = grand total
+__global__ void __launch_bounds__(kScanThreads) k_scan_apply(int *__restrict__ data, int n, const int *__restrict__ tile_sums) {
+    const int base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
+    int v[kScanItems], s = 0;
+    #pragma unroll
+    for (int k = 0; k < kScanItems; ++k) { v[k] = base + k < n ? data[base + k] : 0; s += v[k]; }
+    int total; int off = block_exclusive_scan(s, total) + tile_sums[blockIdx.x];
+    #pragma unroll
+    for (int k = 0; k < kScanItems; ++k) { if (base + k < n) data[base + k] = off; off += v[k]; }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) data[n] = tile_sums[gridDim.x];
+}
+
+// counts in data[0..n) -> exclusive offsets in data[0..n], data[n] = total.  n <= kScanTile^2 (16.7 M).
+inline int scan_exclusive(orbc_ctx *c, int *data, int n) {
+    if (n <= 0) return ORBC_OK;
+    const int n_tiles = (n + kScanTile - 1) / kScanTile;
+    if (n_tiles > kScanTile) return fail(ORBC_ERR_ARG, "scan_exclusive: %d elements exceed the two-level limit", n);
+    if (c->scan_tmp_cap < (size_t)n_tiles + 1) { ORBC_TRY(dev_alloc(&c->scan_tmp, (size_t)n_tiles + 1)); c->scan_tmp_cap = (size_t)n_tiles + 1; }
+    ORBC_LAUNCH(c, k_scan_tile_sums, n_tiles, kScanThreads, 0, data, n, c->scan_tmp);
+    ORBC_LAUNCH(c, k_scan_sums, 1, kScanThreads, 0, c->scan_tmp, n_tiles);
+    ORBC_LAUNCH(c, k_scan_apply, n_tiles, kScanThreads, 0, data, n, c->scan_tmp);
+    return ORBC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stable LSD radix sort of (uint32 key, int value), 8 bits per pass.  One warp owns one tile of kRadixTile keys and
+// walks it 32 keys at a time; __match_any_sync gives each key its rank among equal digits of the same row, a per-warp
+// shared-memory counter carries the running count across rows, so equal keys keep their input order (stable).
+// ------------------------------------------------------------------------------------------------
+constexpr int kRadixTile = 1024;
+constexpr int kRadixWarps = 4;
+
+__global__ void __launch_bounds__(kRadixWarps * 32) k_radix_hist(const uint32_t *__restrict__ keys, int n, int shift, int n_tiles, int *__restrict__ hist) {
+    __shared__ int cnt[kRadixWarps][256];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile = blockIdx.x * kRadixWarps + w;
+    for (int d = lane; d < 256; d += 32) cnt[w][d] = 0;
+    __syncwarp();
+    if (tile < n_tiles) {
+        const int beg = tile * kRadixTile, end = min(n, beg + kRadixTile);
+        for (int i = beg + lane; i < end; i += 32) atomicAdd(&cnt[w][(keys[i] >> shift) & 255], 1);
+    }
+    __syncwarp();
+    if (tile < n_tiles) for (int d = lane; d < 256; d += 32) hist[d * n_tiles + tile] = cnt[w][d];
+}
+
+__global__ void __launch_bounds__(kRadixWarps * 32) k_radix_scatter(const uint32_t *__restrict__ keys_in, const int *__restrict__ vals_in,
+                                                                     uint32_t *__restrict__ keys_out, int *__restrict__ vals_out,
+                                                                     int n, int shift, int n_tiles, const int *__restrict__ hist) {
+    __shared__ int off[kRadixWarps][256];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile = blockIdx.x * kRadixWarps + w;
+    if (tile >= n_tiles) return;
+    for (int d = lane; d < 256; d += 32) off[w][d] = hist[d * n_tiles + tile];
+    __syncwarp();
+    const int beg = tile * kRadixTile, end = min(n, beg + kRadixTile);
+    for (int row = beg; row < end; row += 32) {
+        const int i = row + lane;
+        const bool live = i < end;
+        const uint32_t key = live ? keys_in[i] : 0xffffffffu;
+        const int val = live ? vals_in[i] : 0;
+        const unsigned digit = live ? (key >> shift) & 255u : 256u + lane; // dead lanes never match a live digit
+        const unsigned peers = __match_any_sync(0xffffffffu, digit);
+        const int rank = __popc(peers & ((1u << lane) - 1u));
+        int base = 0;
+        if (live) base = off[w][digit];
+        __syncwarp();
+        if (live && rank == 0) off[w][digit] = base + __popc(peers);
+        __syncwarp();
+        if (live) { keys_out[base + rank] = key; vals_out[base + rank] = val; }
+    }
+}
+
+// sorts (keys, vals) ascending by key, stable; result ends up back in keys/vals (4 passes = even number of swaps)
+inline int radix_sort_pairs(orbc_ctx *c, uint32_t *keys, int *vals, uint32_t *keys_tmp, int *vals_tmp, int n) {
+    if (n <= 1) return ORBC_OK;
+    const int n_tiles = (n + kRadixTile - 1) / kRadixTile;
+    const size_t hist_n = (size_t)256 * n_tiles;
+    if (c->radix_hist_cap < hist_n + 1) { ORBC_TRY(dev_alloc(&c->radix_hist, hist_n + 1)); c->radix_hist_cap = hist_n + 1; }
+    const int blocks = (n_tiles + kRadixWarps - 1) / kRadixWarps;
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 8 * pass;
+        ORBC_LAUNCH(c, k_radix_hist, blocks, kRadixWarps * 32, 0, keys, n, shift, n_tiles, c->radix_hist);
+        ORBC_TRY(scan_exclusive(c, c->radix_hist, (int)hist_n));
+        ORBC_LAUNCH(c, k_radix_scatter, blocks, kRadixWarps * 32, 0, keys, vals, keys_tmp, vals_tmp, n, shift, n_tiles, c->radix_hist);
+        uint32_t *tk = keys; keys = keys_tmp; keys_tmp = tk;
+        int *tv = vals; vals = vals_tmp; vals_tmp = tv;
+    }
+    return ORBC_OK;
+}
+
+} // namespace orbc

@@ -1,0 +1,290 @@
+// rebuild.cuh — the spatial index on the device: Voronoi centroids, Morton order of the centroids, the uniform grid that
+// stands in for the reference's k-d tree, per-cell centroid stencils (r < 9 / 8 / 6), nearest-centroid partition of the
+// particles, stable counting sort into cells and the gather-reorder.
+//
+// Replaces (results identical, integer outputs bit-exact): voronoi.h:77-86,105-117,123-140,153-237, kdtree.h:116-285,
+// reorder.h:73-149, reorder_morton.h:25-122, container.h:39-58, cleanup.h:29-91.
+//
+// All floating-point expressions that decide an integer outcome use the _rn intrinsics in the reference's operation
+// order (no FMA contraction), so centroids, Morton keys, nearest-centroid choices and stencil sets match the
+// reference's strict build bit for bit.
+#pragma once
+#include "common.cuh"
+#include "primitives.cuh"
+
+namespace orbc {
+
+struct GridDev {
+    float lox, loy, loz, inv_h, h;
+    int dx, dy, dz;
+    const int *bin_start;
+    const int *bin_items;
+};
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+__device__ __forceinline__ void grid_bin(const GridDev &g, float4 p, int &bx, int &by, int &bz) {
+    bx = clampi((int)floorf((p.x - g.lox) * g.inv_h), 0, g.dx - 1);
+    by = clampi((int)floorf((p.y - g.loy) * g.inv_h), 0, g.dy - 1);
+    bz = clampi((int)floorf((p.z - g.loz) * g.inv_h), 0, g.dz - 1);
+}
+
+// ---- voronoi.h:123-140 — centroid = fp32 sequential sum over the cell's slots, times 1/count --------------------------
+__global__ void k_centroid_update(const int *__restrict__ cell_start, const float4 *__restrict__ x, int n_cells, float4 *__restrict__ centroid) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_cells) return;
+    const int b = cell_start[i], e = cell_start[i + 1];
+    float cx = 0.f, cy = 0.f, cz = 0.f;
+    for (int j = b; j < e; ++j) {
+        const float4 p = x[j];
+        cx = __fadd_rn(cx, p.x); cy = __fadd_rn(cy, p.y); cz = __fadd_rn(cz, p.z);
+    }
+    const float s = __fdiv_rn(1.0f, __int2float_rn(e - b));   // empty cell: inf -> NaN centroid, as in the reference
+    centroid[i] = make_float4(__fmul_rn(cx, s), __fmul_rn(cy, s), __fmul_rn(cz, s), 0.f);
+}
+
+// ---- reorder_morton.h:25-42 ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t bit_space3(uint32_t x) {
+    x = (x | (x << 12)) & 0X00FC003FU;
+    x = (x | (x << 6)) & 0X381C0E07U;
+    x = (x | (x << 4)) & 0X190C8643U;
+    x = (x | (x << 2)) & 0X49249249U;
+    return x;
+}
+__device__ __forceinline__ uint32_t morton_axis(float x) {
+    // static_cast<unsigned>(2 * x + bsize): 2*x in fp32, the sum in fp64 (bsize = 2000.0 is a double, runtime_parameter.h:46)
+    return (uint32_t)__double2uint_rz(__dadd_rn((double)__fmul_rn(2.0f, x), 2000.0));
+}
+__device__ __forceinline__ uint32_t morton_encode(float4 p) {
+    return bit_space3(morton_axis(p.x)) | (bit_space3(morton_axis(p.y)) << 1) | (bit_space3(morton_axis(p.z)) << 2);
+}
+__global__ void k_morton_keys(const float4 *__restrict__ pts, int n, uint32_t *__restrict__ keys, int *__restrict__ idx) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    keys[i] = morton_encode(pts[i]);
+    if (idx) idx[i] = i;
+}
+__global__ void k_permute_centroids(const float4 *__restrict__ src, const int *__restrict__ perm, int n, float4 *__restrict__ dst, int *__restrict__ inv) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int o = perm[i];
+    dst[i] = src[o];
+    inv[o] = i;
+}
+__global__ void k_remap_cellid(int *__restrict__ cellid, size_t n, const int *__restrict__ inv) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int c = cellid[i];
+    if (c >= 0) cellid[i] = inv[c];
+}
+__global__ void k_fill_cellid(const int *__restrict__ cell_start, int n_cells, int *__restrict__ cellid) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_cells) return;
+    for (int j = cell_start[c]; j < cell_start[c + 1]; ++j) cellid[j] = c;
+}
+__global__ void k_fill_int(int *__restrict__ a, size_t n, int v) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] = v;
+}
+
+// ---- uniform grid over the centroids (counting sort into bins) --------------------------------------------------------------
+__global__ void k_bin_count(const float4 *__restrict__ centroid, int n, GridDev g, int *__restrict__ bin_cnt, int *__restrict__ bin_of, int *__restrict__ bin_slot) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = centroid[i];
+    if (!(p.x == p.x) || !(p.y == p.y) || !(p.z == p.z)) { bin_of[i] = -1; return; }   // NaN centroid of an empty cell
+    int bx, by, bz; grid_bin(g, p, bx, by, bz);
+    const int b = (bz * g.dy + by) * g.dx + bx;
+    bin_of[i] = b;
+    bin_slot[i] = atomicAdd(&bin_cnt[b], 1);
+}
+__global__ void k_bin_fill(int n, const int *__restrict__ bin_start, const int *__restrict__ bin_of, const int *__restrict__ bin_slot, int *__restrict__ bin_items) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int b = bin_of[i];
+    if (b >= 0) bin_items[bin_start[b] + bin_slot[i]] = i;
+}
+
+// ---- per-cell centroid stencils: {c2 : |c2 - c1|^2 < 81}, classed by < 36 / < 64 / < 81, ordered (class, id) -------------
+// voronoi.h:105-117 (get_stencil_whole / refine_stencil) and kdtree.h:263-285 (find_within); the sets are identical, the
+// reference's order is tree-traversal order.  One warp per cell; the 27 surrounding bins are 9 x-contiguous runs.
+constexpr int kStencilWarps = 8;
+__global__ void __launch_bounds__(kStencilWarps * 32) k_stencil_build(const float4 *__restrict__ centroid, int n_cells, GridDev g,
+                                                                       int *__restrict__ stencil, int *__restrict__ stencil_cnt, int *__restrict__ flags) {
+    __shared__ int s_key[kStencilWarps][kStencilStride];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c = blockIdx.x * kStencilWarps + w;
+    if (c >= n_cells) return;
+    const float4 q = centroid[c];
+    int count = 0;
+    if (q.x == q.x && q.y == q.y && q.z == q.z) {
+        int bx, by, bz; grid_bin(g, q, bx, by, bz);
+        const int x0 = max(bx - 1, 0), x1 = min(bx + 1, g.dx - 1);
+        for (int zz = max(bz - 1, 0); zz <= min(bz + 1, g.dz - 1); ++zz)
+            for (int yy = max(by - 1, 0); yy <= min(by + 1, g.dy - 1); ++yy) {
+                const int row = (zz * g.dy + yy) * g.dx;
+                const int beg = g.bin_start[row + x0], end = g.bin_start[row + x1 + 1];
+                for (int k0 = beg; k0 < end; k0 += 32) {
+                    const int k = k0 + lane;
+                    int key = -1;
+                    if (k < end) {
+                        const int j = g.bin_items[k];
+                        const float d2 = dist2_rn(centroid[j], q);     // normsq(pts_[i] - q), kdtree.h:274
+                        if (d2 < 81.0f) key = ((d2 < 36.0f ? 0 : (d2 < 64.0f ? 1 : 2)) << 28) | j;
+                    }
+                    const unsigned m = __ballot_sync(0xffffffffu, key >= 0);
+                    const int pos = count + __popc(m & ((1u << lane) - 1u));
+                    if (key >= 0 && pos < kStencilStride) s_key[w][pos] = key;
+                    count += __popc(m);
+                }
+            }
+    }
+    if (count > kStencilStride) { if (lane == 0) atomicExch(&flags[0], c + 1); count = kStencilStride; }
+    __syncwarp();
+    int n6 = 0, n8 = 0;
+    for (int e = lane; e < count; e += 32) {
+        const int key = s_key[w][e];
+        int rank = 0;
+        for (int k = 0; k < count; ++k) rank += (s_key[w][k] < key);
+        stencil[(size_t)c * kStencilStride + rank] = key & 0x0fffffff;
+        n6 += (key >> 28) == 0; n8 += (key >> 28) <= 1;
+    }
+    #pragma unroll
+    for (int d = 16; d > 0; d >>= 1) { n6 += __shfl_xor_sync(0xffffffffu, n6, d); n8 += __shfl_xor_sync(0xffffffffu, n8, d); }
+    if (lane == 0) stencil_cnt[c] = n6 | (n8 << 8) | (count << 16);
+}
+
+// ---- nearest centroid (voronoi.h:179-216 + kdtree.h:206-236) ------------------------------------------------------------------
+// exact fallback: expanding shells of grid bins around the particle until the best distance is covered
+__device__ int nearest_by_grid(float4 p, const GridDev &g, const float4 *__restrict__ centroid, float &best_out) {
+    int bx, by, bz; grid_bin(g, p, bx, by, bz);
+    const int maxring = max(g.dx, max(g.dy, g.dz));
+    float best = INFINITY; int bi = -1;
+    for (int k = 0; k <= maxring; ++k) {
+        for (int zz = bz - k; zz <= bz + k; ++zz) {
+            if (zz < 0 || zz >= g.dz) continue;
+            for (int yy = by - k; yy <= by + k; ++yy) {
+                if (yy < 0 || yy >= g.dy) continue;
+                const bool face = (abs(zz - bz) == k) || (abs(yy - by) == k);
+                const int step = face ? 1 : 2 * k;                      // interior rows: only the two end bins belong to shell k
+                for (int xx = bx - k; xx <= bx + k; xx += (step > 0 ? step : 1)) {
+                    if (xx < 0 || xx >= g.dx) continue;
+                    const int b = (zz * g.dy + yy) * g.dx + xx;
+                    for (int q = g.bin_start[b]; q < g.bin_start[b + 1]; ++q) {
+                        const int j = g.bin_items[q];
+                        const float d2 = dist2_rn(p, centroid[j]);
+                        if (d2 < best || (d2 == best && j < bi)) { best = d2; bi = j; }
+                    }
+                }
+            }
+        }
+        const float reach = (float)k * g.h;       // every bin outside shells 0..k is at least k*h away from p
+        if (bi >= 0 && best <= reach * reach) break;
+    }
+    best_out = best;
+    return bi;
+}
+
+// One thread per particle.  Fast path: the particle's previous cell g and g's r<9 centroid stencil; it is exact whenever
+// d(best) + d(g) < 9 (every centroid at least that close to the particle is then inside the stencil).  Otherwise the grid
+// search above.  Ties in the squared distance go to the lower cell id.
+__global__ void k_assign_nearest(const float4 *__restrict__ x, const int *__restrict__ cellid, size_t n, const float4 *__restrict__ centroid, int n_cells,
+                                 const int *__restrict__ stencil, const int *__restrict__ stencil_cnt, GridDev g,
+                                 int *__restrict__ aff, int *__restrict__ li, int *__restrict__ cell_cnt,
+                                 unsigned long long *__restrict__ counters, int *__restrict__ flags) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = x[i];
+    const int guess = cellid ? cellid[i] : -1;
+    float best = INFINITY; int bi = -1; bool ok = false;
+    if (guess >= 0 && guess < n_cells) {
+        const int n9 = stencil_cnt[guess] >> 16;
+        const int *st = stencil + (size_t)guess * kStencilStride;
+        for (int k = 0; k < n9; ++k) {
+            const int j = st[k];
+            const float d2 = dist2_rn(p, centroid[j]);
+            if (d2 < best || (d2 == best && j < bi)) { best = d2; bi = j; }
+        }
+        if (bi >= 0) {
+            const float dg = dist2_rn(p, centroid[guess]);
+            ok = sqrtf(best) + sqrtf(dg) < 9.0f - 1e-3f;
+        }
+    }
+    if (!ok) {
+        bi = nearest_by_grid(p, g, centroid, best);
+        atomicAdd(&counters[0], 1ULL);
+    }
+    if (bi < 0) { atomicExch(&flags[1], (int)(i & 0x7fffffff) + 1); bi = 0; }   // NaN position: keep the structure consistent, report
+    aff[i] = bi;
+    li[i] = atomicAdd(&cell_cnt[bi], 1);
+}
+
+// cells_tmp[cell_start[aff] + arrival slot] = i   (voronoi.h:228-231 with an arbitrary arrival order ...)
+__global__ void k_cell_scatter(const int *__restrict__ aff, const int *__restrict__ li, size_t n, const int *__restrict__ cell_start, int *__restrict__ cells_tmp) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    cells_tmp[cell_start[aff[i]] + li[i]] = (int)i;
+}
+// ... then every cell's segment is sorted ascending, which is the arrival order of the reference at one thread
+// (omp atomic capture in index order, voronoi.h:214-215): a stable counting sort.
+__global__ void k_cell_sort(const int *__restrict__ cell_start, int n_cells, const int *__restrict__ cells_tmp, int *__restrict__ cells) {
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (c >= n_cells) return;
+    const int b = cell_start[c], m = cell_start[c + 1] - b;
+    for (int e = lane; e < m; e += 32) {
+        const int v = cells_tmp[b + e];
+        int rank = 0;
+        for (int k = 0; k < m; ++k) rank += (cells_tmp[b + k] < v);
+        cells[b + rank] = v;
+    }
+}
+
+// reorder.h:73-149: out-of-place gather of x, v, n, o (type and tag ride in x.w / n.w) + the particle's cell
+__global__ void k_gather_reorder(const int *__restrict__ cells, const int *__restrict__ aff, size_t n,
+                                 const float4 *__restrict__ x0, const float4 *__restrict__ n0, const float4 *__restrict__ v0, const float4 *__restrict__ o0,
+                                 float4 *__restrict__ x1, float4 *__restrict__ n1, float4 *__restrict__ v1, float4 *__restrict__ o1, int *__restrict__ cellid1) {
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const int s = cells[j];
+    x1[j] = x0[s]; n1[j] = n0[s]; v1[j] = v0[s]; o1[j] = o0[s];
+    cellid1[j] = aff[s];
+}
+
+// container.h:39-58
+__global__ void k_build_tag2idx(const float4 *__restrict__ nn, size_t n, int *__restrict__ map, size_t map_size, int *__restrict__ flags) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int tag = __float_as_int(nn[i].w);
+    if (tag >= 0 && (size_t)tag < map_size) map[tag] = (int)i; else atomicExch(&flags[2], (int)i + 1);
+}
+
+// ---- cleanup.h:29-60: per cell, median squared distance to the centroid; keep = dr2 < median * tol^2 ------------------------
+__global__ void k_stray_mask(const int *__restrict__ cell_start, int n_cells, const float4 *__restrict__ centroid, const float4 *__restrict__ x,
+                             float tol, int *__restrict__ keep) {
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (c >= n_cells) return;
+    const int b = cell_start[c], m = cell_start[c + 1] - b;
+    if (m <= 0) return;
+    const float4 q = centroid[c];
+    // the element of rank m/2 in the sorted list (std::sort + dr2[size/2]); rank by (value, slot)
+    float med = 0.f; int have = 0;
+    for (int e = lane; e < m; e += 32) {
+        const float d = dist2_rn(x[b + e], q);
+        int rank = 0;
+        for (int k = 0; k < m; ++k) { const float dk = dist2_rn(x[b + k], q); rank += (dk < d) || (dk == d && k < e); }
+        if (rank == m / 2) { med = d; have = 1; }
+    }
+    const unsigned who = __ballot_sync(0xffffffffu, have);
+    med = __shfl_sync(0xffffffffu, med, __ffs(who) - 1);
+    const float threshold = __fmul_rn(__fmul_rn(med, tol), tol);
+    for (int e = lane; e < m; e += 32) keep[b + e] = dist2_rn(x[b + e], q) < threshold ? 1 : 0;
+}
+__global__ void k_compact(const int *__restrict__ keep, const int *__restrict__ newpos, size_t n,
+                          const float4 *__restrict__ x0, const float4 *__restrict__ n0, const float4 *__restrict__ v0, const float4 *__restrict__ o0, const int *__restrict__ c0,
+                          float4 *__restrict__ x1, float4 *__restrict__ n1, float4 *__restrict__ v1, float4 *__restrict__ o1, int *__restrict__ c1) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !keep[i]) return;
+    const int j = newpos[i];
+    x1[j] = x0[i]; n1[j] = n0[i]; v1[j] = v0[i]; o1[j] = o0[i]; c1[j] = c0[i];
+}
+
+} // namespace orbc

@@ -1,0 +1,354 @@
+"""ctypes binding of include/orbc_b200.h and the `Simulation` host mirror.
+
+`Simulation` keeps the vocabulary of the reference (containers `lipid` / `protein`, Voronoi cells,
+centroid stencils, functor-kernel names of integrate()) so that the parity tests read like the
+reference's own main loop (src/openrbc.cpp:189-256).
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "liborbc_b200.so")
+
+LIPID, PROTEIN = 0, 1
+CLEAR_FORCE, POST_TORQUE, BOUNCE_BACK, VERLET_LANGEVIN, NH_INITIAL_FUSED, NH_FINAL_FUSED, NH_FINAL, NH_UPDATE = range(8)
+OPT_MOVE = 9
+STENCIL_STRIDE = 64
+DUMP = dict(centroids=0, cell_start_l=1, cell_start_p=2, cells_l=3, cells_p=4, aff_l=5, aff_p=6, morton_keys=7, morton_perm=8,
+            stencil_counts=9, stencil=10, tag2idx=11, counters=12)
+
+EXPORTS = [
+    "orbc_create", "orbc_destroy", "orbc_last_error", "orbc_synchronize", "orbc_set_stream", "orbc_forcefield_canonical",
+    "orbc_set_forcefield", "orbc_upload", "orbc_upload_bonds", "orbc_voronoi_upload", "orbc_set_field", "orbc_voronoi_update",
+    "orbc_cell_update", "orbc_rebuild", "orbc_delete_lipid", "orbc_compute_pairwise_fused", "orbc_compute_bonded",
+    "orbc_constrain_volume", "orbc_integrate", "orbc_nh_zeta_update", "orbc_compute_temperature", "orbc_run_langevin",
+    "orbc_run_nh", "orbc_download", "orbc_size", "orbc_n_cells", "orbc_debug_dump", "orbc_debug_noise", "orbc_event_record",
+    "orbc_event_elapsed_ms", "orbc_launch_count",
+]
+
+
+class OrbcError(RuntimeError):
+    pass
+
+
+class ForceField(C.Structure):
+    _fields_ = [(n, C.c_float * k) for n, k in (
+        ("mass", 6), ("radius", 6), ("cutlp", 6), ("cutsqlp", 6), ("replp", 6), ("attlp", 6), ("alphalp", 6),
+        ("cutpp", 36), ("cutsqpp", 36), ("reppp", 36), ("lj_cutsq", 36), ("lj_lj1", 36), ("lj_lj2", 36),
+        ("r0", 4), ("K", 4))] + [(n, C.c_float) for n in ("cutll", "cutsqll", "repll", "attll", "alphall")]
+
+    def as_array(self):
+        return np.frombuffer(bytes(self), np.float32).copy()
+
+
+class StepParams(C.Structure):
+    _fields_ = [("dt", C.c_double), ("kBT", C.c_float), ("eta", C.c_float), ("zeta", C.c_float),
+                ("box_lo", C.c_double), ("box_hi", C.c_double), ("dr_opt", C.c_double), ("dn_opt", C.c_double),
+                ("nstep", C.c_int), ("seed", C.c_uint64), ("noise_lipid", C.c_void_p), ("noise_protein", C.c_void_p)]
+
+
+class StepResult(C.Structure):
+    _fields_ = [("ke", C.c_double), ("n", C.c_long)]
+
+
+def library_path():
+    return _SO
+
+
+def build_library(verbose=False):
+    """Compile csrc/ for sm_100a into the in-tree liborbc_b200.so (nvcc cross-compiles without a GPU)."""
+    out = None if verbose else subprocess.DEVNULL
+    subprocess.check_call(["make", "-C", os.path.join(_HERE, "csrc")], stdout=out)
+    return _SO
+
+
+_lib = None
+
+
+def load_library():
+    """Load liborbc_b200.so; fails loudly when it has not been built (no fallback path exists)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            raise OrbcError(f"{_SO} is missing: build it with `make -C openrbc_b200/csrc` (python __graft_entry__.py build); "
+                            "openrbc_b200 has no CPU fallback")
+        lib = C.CDLL(_SO)
+        lib.orbc_last_error.restype = C.c_char_p
+        lib.orbc_nh_zeta_update.restype = C.c_float
+        lib.orbc_nh_zeta_update.argtypes = [C.c_float, C.POINTER(C.c_float), C.c_double, C.c_float, C.c_double, C.c_long]
+        lib.orbc_constrain_volume.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_void_p]
+        lib.orbc_delete_lipid.argtypes = [C.c_void_p, C.c_float, C.c_void_p]
+        lib.orbc_debug_noise.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_size_t, C.c_void_p]
+        lib.orbc_upload.argtypes = [C.c_void_p, C.c_int, C.c_size_t, C.c_size_t] + [C.c_void_p] * 6
+        lib.orbc_upload_bonds.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
+        lib.orbc_voronoi_upload.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.orbc_set_field.argtypes = [C.c_void_p, C.c_int, C.c_char, C.c_size_t, C.c_void_p]
+        lib.orbc_download.argtypes = [C.c_void_p, C.c_int, C.c_size_t] + [C.c_void_p] * 10
+        lib.orbc_debug_dump.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
+        lib.orbc_integrate.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        lib.orbc_run_langevin.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
+        lib.orbc_run_nh.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        for name in ("orbc_synchronize", "orbc_compute_pairwise_fused", "orbc_compute_bonded"):
+            getattr(lib, name).argtypes = [C.c_void_p]
+        lib.orbc_voronoi_update.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        lib.orbc_cell_update.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        lib.orbc_rebuild.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        lib.orbc_compute_temperature.argtypes = [C.c_void_p, C.c_void_p]
+        lib.orbc_event_record.argtypes = [C.c_void_p, C.c_int]
+        lib.orbc_event_elapsed_ms.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        lib.orbc_launch_count.argtypes = [C.c_void_p, C.c_void_p]
+        lib.orbc_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+        lib.orbc_destroy.argtypes = [C.c_void_p]
+        lib.orbc_destroy.restype = None
+        _lib = lib
+    return _lib
+
+
+def forcefield_canonical():
+    ff = ForceField()
+    load_library().orbc_forcefield_canonical(C.byref(ff))
+    return ff
+
+
+def _f3(a):
+    return np.ascontiguousarray(a, np.float32).reshape(-1, 3)
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Simulation:
+    """Device-resident copy of the reference's containers and Voronoi state, driven through the C ABI.
+
+    `st` is the state dictionary produced by the reference's own initialisation (oracle.ref.Ref.state(),
+    tools/make_states.py) or by the synthetic generators: lx lv ln lo, px pv pn po (N x 3 float32), ptype, ptag,
+    bonds (B x 3: type, tag_i, tag_j), centroids (C x 3), cs_l, cs_p (C + 1).
+    """
+
+    def __init__(self, st, dt=1e-2, kBT=0.22, eta=0.01, seed=0xBAD5EED, device=0, box=(-1000.0, 1000.0)):
+        self.lib = load_library()
+        self.ctx = C.c_void_p()
+        self._ck(self.lib.orbc_create(C.byref(self.ctx), int(device)))
+        self.dt, self.kBT, self.eta, self.seed = dt, kBT, eta, seed
+        self.box = box
+        self.zeta, self.Q = 0.0, C.c_float(0.0)
+        self.nstep = 0
+        self.freq_sort_ctrd, self.freq_sort_bond, self.freq_voronoi = 24, 120, 2
+        self.dr_opt = self.dn_opt = 5e-2
+        self.last_ke = 0.0
+        if st is not None:
+            self.upload(st)
+
+    # ---- plumbing ---------------------------------------------------------------------------------
+    def _ck(self, rc):
+        if rc != 0:
+            raise OrbcError(f"orbc error {rc}: {self.lib.orbc_last_error().decode()}")
+
+    def close(self):
+        if self.ctx:
+            self.lib.orbc_destroy(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def params(self, noise_l=None, noise_p=None):
+        p = StepParams()
+        p.dt, p.kBT, p.eta, p.zeta = self.dt, self.kBT, self.eta, self.zeta
+        p.box_lo, p.box_hi = self.box
+        p.dr_opt, p.dn_opt = self.dr_opt, self.dn_opt
+        p.nstep, p.seed = self.nstep, self.seed
+        self._keep = (None if noise_l is None else _f3(noise_l), None if noise_p is None else _f3(noise_p))
+        p.noise_lipid = None if self._keep[0] is None else self._keep[0].ctypes.data
+        p.noise_protein = None if self._keep[1] is None else self._keep[1].ctypes.data
+        return p
+
+    # ---- upload / download ------------------------------------------------------------------------------
+    def upload(self, st):
+        lx, lv, ln, lo = (_f3(st["l" + f]) for f in "xvno")
+        self._ck(self.lib.orbc_upload(self.ctx, LIPID, len(lx), 3, _p(lx), _p(lv), _p(ln), _p(lo), None, None))
+        px, pv, pn, po = (_f3(st["p" + f]) for f in "xvno")
+        ty = np.ascontiguousarray(st["ptype"], np.int32)
+        tg = np.ascontiguousarray(st["ptag"], np.int32)
+        self._ck(self.lib.orbc_upload(self.ctx, PROTEIN, len(px), 3, _p(px), _p(pv), _p(pn), _p(po), _p(ty), _p(tg)))
+        bd = np.ascontiguousarray(st["bonds"], np.int32).reshape(-1, 3)
+        self._ck(self.lib.orbc_upload_bonds(self.ctx, len(bd), _p(bd)))
+        if "centroids" in st:
+            c = _f3(st["centroids"])
+            csl = np.ascontiguousarray(st["cs_l"], np.int32)
+            csp = np.ascontiguousarray(st["cs_p"], np.int32)
+            self._ck(self.lib.orbc_voronoi_upload(self.ctx, len(c), _p(c), _p(csl), _p(csp)))
+
+    def size(self, s):
+        n = C.c_size_t()
+        self._ck(self.lib.orbc_size(self.ctx, s, C.byref(n)))
+        return n.value
+
+    @property
+    def n_cells(self):
+        n = C.c_int()
+        self._ck(self.lib.orbc_n_cells(self.ctx, C.byref(n)))
+        return n.value
+
+    def download(self, s, fields="xvnoft", ids=False, affiliation=False):
+        n = self.size(s)
+        out = {f: np.empty((n, 3), np.float32) for f in fields}
+        ptr = [_p(out[f]) if f in out else None for f in "xvnoft"]
+        aff = np.empty(n, np.int32) if affiliation else None
+        ty = np.empty(n, np.int32) if ids else None
+        tg = np.empty(n, np.int32) if ids else None
+        nn = C.c_size_t()
+        self._ck(self.lib.orbc_download(self.ctx, s, 3, *ptr, _p(aff), _p(ty), _p(tg), C.byref(nn)))
+        if affiliation:
+            out["affiliation"] = aff
+        if ids:
+            out["type"], out["tag"] = ty, tg
+        return out
+
+    def get(self, s, field):
+        return self.download(s, field)[field]
+
+    def set_field(self, s, field, a):
+        a = _f3(a)
+        assert len(a) == self.size(s)
+        self._ck(self.lib.orbc_set_field(self.ctx, s, field.encode(), 3, _p(a)))
+
+    def dump(self, what):
+        nc = self.n_cells
+        shape, dt = {
+            "centroids": ((nc, 3), np.float32), "cell_start_l": ((nc + 1,), np.int32), "cell_start_p": ((nc + 1,), np.int32),
+            "cells_l": ((self.size(0),), np.int32), "cells_p": ((self.size(1),), np.int32),
+            "aff_l": ((self.size(0),), np.int32), "aff_p": ((self.size(1),), np.int32),
+            "morton_keys": ((nc,), np.uint32), "morton_perm": ((nc,), np.int32), "stencil_counts": ((nc, 3), np.int32),
+            "stencil": ((nc, STENCIL_STRIDE), np.int32), "counters": ((8,), np.uint64),
+        }[what]
+        out = np.empty(shape, dt)
+        self._ck(self.lib.orbc_debug_dump(self.ctx, DUMP[what], _p(out), out.nbytes))
+        return out
+
+    def stencils(self):
+        """Per-cell centroid stencils as three lists of sorted arrays: r < 9, r < 8, r < 6."""
+        cnt = self.dump("stencil_counts")
+        st = self.dump("stencil")
+        s9 = [np.sort(st[c, :cnt[c, 2]]) for c in range(len(cnt))]
+        s8 = [np.sort(st[c, :cnt[c, 1]]) for c in range(len(cnt))]
+        s6 = [np.sort(st[c, :cnt[c, 0]]) for c in range(len(cnt))]
+        return s9, s8, s6
+
+    def noise(self, nstep, species, n):
+        out = np.empty((n, 3), np.float32)
+        self._ck(self.lib.orbc_debug_noise(self.ctx, self.seed, nstep, species, n, _p(out)))
+        return out
+
+    def synchronize(self):
+        self._ck(self.lib.orbc_synchronize(self.ctx))
+
+    # ---- the reference's hot-path calls -------------------------------------------------------------------
+    def voronoi_update(self):                                    # voronoi.update(lipid, cell_lipid, param)      openrbc.cpp:202
+        self._ck(self.lib.orbc_voronoi_update(self.ctx, self.nstep, self.freq_sort_ctrd))
+
+    def cell_update(self, s):                                    # cell_*.update(container, voronoi, param)      :203-204
+        self._ck(self.lib.orbc_cell_update(self.ctx, s, self.nstep, self.freq_sort_bond))
+
+    def rebuild(self):
+        self._ck(self.lib.orbc_rebuild(self.ctx, self.nstep, self.freq_sort_ctrd, self.freq_sort_bond))
+
+    def compute_pairwise_fused(self):                            # :219
+        self._ck(self.lib.orbc_compute_pairwise_fused(self.ctx))
+
+    def compute_bonded(self):                                    # :225
+        self._ck(self.lib.orbc_compute_bonded(self.ctx))
+
+    def integrate(self, kernel, noise_l=None, noise_p=None, want_result=False):
+        p = self.params(noise_l, noise_p)
+        res = StepResult()
+        self._ck(self.lib.orbc_integrate(self.ctx, kernel, C.byref(p), C.byref(res) if want_result else None))
+        return res
+
+    def clear_force(self):
+        self.integrate(CLEAR_FORCE)
+
+    def post_torque(self):
+        self.integrate(POST_TORQUE)
+
+    def bounce_back(self):
+        self.integrate(BOUNCE_BACK)
+
+    def verlet_langevin(self, noise_l=None, noise_p=None):      # :233
+        self.integrate(VERLET_LANGEVIN, noise_l, noise_p)
+
+    def _zeta(self, res):
+        self.last_ke = res.ke
+        self.zeta = self.lib.orbc_nh_zeta_update(self.zeta, C.byref(self.Q), self.dt, self.kBT, res.ke, res.n)
+
+    def nh_initial_fused(self):                                  # :193, destructor updates zeta
+        res = self.integrate(NH_INITIAL_FUSED, want_result=True)
+        self._zeta(res)
+        return res.ke
+
+    def nh_final_fused(self):                                    # :236
+        res = self.integrate(NH_FINAL_FUSED, want_result=True)
+        self._zeta(res)
+        return res.ke
+
+    def opt_move(self):                                          # :114-131
+        self.integrate(OPT_MOVE)
+
+    def compute_temperature(self):                               # :253
+        t = C.c_double()
+        self._ck(self.lib.orbc_compute_temperature(self.ctx, C.byref(t)))
+        return t.value
+
+    def constrain_volume(self, target, strength):                # :229
+        v = C.c_float()
+        self._ck(self.lib.orbc_constrain_volume(self.ctx, target, strength, C.byref(v)))
+        return v.value
+
+    def delete_lipid(self, stray_tolerance):                     # :201
+        n = C.c_size_t()
+        self._ck(self.lib.orbc_delete_lipid(self.ctx, stray_tolerance, C.byref(n)))
+        return n.value
+
+    # ---- whole-loop entry points ----------------------------------------------------------------------
+    def run_langevin(self, n_steps):
+        p = self.params()
+        self._ck(self.lib.orbc_run_langevin(self.ctx, C.byref(p), n_steps, self.freq_voronoi, self.freq_sort_ctrd))
+        self.nstep += n_steps
+
+    def run_nh(self, n_steps):
+        p = self.params()
+        z = C.c_float(self.zeta)
+        self._ck(self.lib.orbc_run_nh(self.ctx, C.byref(p), n_steps, self.freq_voronoi, self.freq_sort_ctrd, C.byref(z), C.byref(self.Q)))
+        self.zeta = z.value
+        self.nstep += n_steps
+
+    def step_langevin(self, noise=None):
+        """One iteration of the reference's while-loop (openrbc.cpp:189-244), call for call."""
+        if self.nstep % self.freq_voronoi == 0:
+            self.rebuild()
+        self.compute_pairwise_fused()
+        self.compute_bonded()
+        nl, npr = noise if noise is not None else (None, None)
+        self.verlet_langevin(nl, npr)
+        self.nstep += 1
+
+    # ---- timing ------------------------------------------------------------------------------------------
+    def event_record(self, slot):
+        self._ck(self.lib.orbc_event_record(self.ctx, slot))
+
+    def event_elapsed_ms(self, a, b):
+        ms = C.c_float()
+        self._ck(self.lib.orbc_event_elapsed_ms(self.ctx, a, b, C.byref(ms)))
+        return ms.value
+
+    def launch_count(self):
+        n = C.c_ulonglong()
+        self._ck(self.lib.orbc_launch_count(self.ctx, C.byref(n)))
+        return n.value
