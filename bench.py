@@ -1,0 +1,371 @@
+#!/usr/bin/env python
+"""bench.py — particle-timesteps/s of OpenRBC's per-timestep force/integrate loop on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload rbc|sphere|patch:<n_lipids>] [--impl ours|reference]
+
+One "step" is one iteration of the reference's main MD loop (src/openrbc.cpp:189-256, default LANGEVIN build) over the
+whole system: [every 2nd step: Voronoi/cell rebuild] -> pair forces -> bonded forces -> Langevin integrator, with the
+stray-lipid cleanup every 60 steps.  Default workload = BASELINE.json configs[1]: the full red blood cell
+(`-i trimesh -m rbc`, 3 205 506 particles, 188 549 Voronoi cells), initial state produced by the reference's own host-side
+initialisation (init_rbc + VoronoiDiagram::init + 100 minimisation steps; tools/make_states.py), which the north star
+leaves in place.
+
+Printed JSON (one line, rank 0):
+  value     device-resident throughput of the fused whole-loop entry point orbc_run_langevin (state already in HBM)
+  e2e       same loop driven call by call through the reference-facing C ABI from HOST buffers: upload of the containers
+            from pinned memory, K x (rebuild / compute_pairwise_fused / compute_bonded / integrate + status read-back),
+            temperature every 100 steps, and the download a save_frame needs at the end — all inside the timed region
+  roofline  dominant kernel (lipid pair forces): algorithmic bytes per launch / mean launch duration (CUDA events on the
+            launching stream, recorded live in the timed region) against the measured HBM peak
+  cpu_baseline  the unmodified reference (oracle/_ref/libref_fast.so, as-shipped flags) on this box's host cores
+
+`--impl reference` times only the reference's own OpenMP implementation of the same loop on the same state.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "particle-timesteps/sec"
+UNIT = "particle-steps/s"
+B_ALG_STEP = 96.0            # algorithmic bytes per particle-timestep: read + write x, v, n, o as 3 x fp32
+B_ALG_PAIR = 48.0            # pair-force kernel: read x, n (24 B), write f, t (24 B) per particle and launch
+FREQ_CLEANUP, FREQ_DISPLAY = 60, 100      # runtime_parameter.h:59-60
+HBM_FALLBACK_GBS = 6650.0    # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# workloads
+# ---------------------------------------------------------------------------------------------------------------------
+def state_path(workload):
+    return os.path.join(ROOT, "data", "_gen", workload.replace(":", "_") + ".npz")
+
+
+def ensure_state(workload):
+    """Input state of the workload.  rbc / sphere come from the reference's host-side initialisation (code the north star
+    leaves in place), run once through tools/make_states.py and cached; patch:<n> is the synthetic bilayer of §8(d)."""
+    path = state_path(workload)
+    if os.path.exists(path):
+        return path
+    t0 = time.time()
+    if workload.startswith("patch:"):
+        from openrbc_b200.synthetic import flat_patch_state
+        st = flat_patch_state(int(float(workload.split(":")[1])))
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        np.savez(path, **st)
+    else:
+        kind = {"rbc": ["rbc", "--opt", "100"], "sphere": ["sphere", "--radius", "100", "--opt", "20"]}[workload]
+        env = dict(os.environ, OMP_PROC_BIND="close", OMP_PLACES="cores")
+        out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "make_states.py"), *kind, "--out", path],
+                             env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if out.returncode != 0 or not os.path.exists(path):
+            raise SystemExit("could not generate the %s state (needs oracle/_ref/libref_fast.so built by `python __graft_entry__.py build`):\n%s"
+                             % (workload, out.stdout[-2000:]))
+    print(f"[bench] generated {path} in {time.time() - t0:.1f}s", file=sys.stderr, flush=True)
+    return path
+
+
+def load_state(workload):
+    return dict(np.load(ensure_state(workload)))
+
+
+def workload_name(workload, st):
+    n = len(st["lx"]) + len(st["px"])
+    base = {"rbc": "full RBC, -i trimesh -m rbc (example-large), Langevin", "sphere": "lipid sphere R=100, -i lipid, Langevin"}.get(
+        workload, f"synthetic flat bilayer {workload}, Langevin")
+    return f"{base}: {n} particles, {len(st['centroids'])} Voronoi cells, {len(st['bonds'])} bonds"
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# reference arm: the unmodified reference on the host cores
+# ---------------------------------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import ref as refmod
+    if not refmod.available("fast"):
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libref_fast.so is not built (python __graft_entry__.py build where /root/reference exists)"}))
+        return
+    st = load_state(args.workload)
+    n = len(st["lx"]) + len(st["px"])
+    threads = args.threads or (os.cpu_count() or 1)
+    r = refmod.Ref("fast", threads=threads, args=["-i", "trimesh"])
+    r.load_state(st)
+    r.set_param("kBT", 0.22)
+    budget = args.ref_budget
+    t0 = time.time()
+    r.run_langevin(args.warmup, cleanup=True)
+    per = max((time.time() - t0) / max(args.warmup, 1), 1e-3)
+    steps = int(max(2, min(args.steps, (budget - (time.time() - t0)) / per)))
+    sec = r.run_langevin(steps, cleanup=True)
+    value = n * steps / sec
+    sample = f"{steps} MD steps of the whole system after {args.warmup} warm-up steps ({sec:.2f} s)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * sec / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args.workload, st), "impl": "unmodified reference headers, g++ -O3 -ffast-math -mrecip -fopenmp (oracle/Makefile FAST), compute_pairwise_fused path",
+                   "omp_threads": threads, "omp_binding": "OMP_PROC_BIND=%s OMP_PLACES=%s" % (os.environ.get("OMP_PROC_BIND", "unset"), os.environ.get("OMP_PLACES", "unset")),
+                   "pair_timer_s_per_step": r.timer("compute_pairwise_fused") / max(steps + args.warmup, 1)},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_subprocess(args):
+    """Reference timed on this box's host cores in its own process (one OpenMP runtime, one thread count per process)."""
+    env = dict(os.environ, OMP_PROC_BIND="close", OMP_PLACES="cores")
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
+        env.pop(k, None)
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", args.workload, "--steps", str(args.cpu_steps),
+           "--warmup", "2", "--ref-budget", "40"]
+    try:
+        out = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=600)
+        for ln in reversed(out.stdout.strip().splitlines()):
+            if ln.startswith("{"):
+                d = json.loads(ln)
+                if "cpu_baseline" in d:
+                    return d["cpu_baseline"]
+                return {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": d.get("unavailable", "no output")}
+    except Exception as e:  # noqa: BLE001
+        return {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"failed: {e}"}
+    return {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "no output"}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# ---------------------------------------------------------------------------------------------------------------------
+class Clocks:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.stop, self.index = [], False, index
+        self.th = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self.stop:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.splitlines()[0].split(",")])
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.1)
+
+    def __enter__(self):
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop = True
+        self.th.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(int(float(r[0])) for r in self.rows)
+        reasons = []
+        for k, name in enumerate(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")):
+            if any(r[3 + k].lower().startswith("active") for r in self.rows):
+                reasons.append(name)
+        pw = [float(r[2]) for r in self.rows if r[2].replace(".", "", 1).isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(float(self.rows[0][1])), "reasons": reasons, "samples": len(sm),
+                "power_w_max": max(pw) if pw else None}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------------------------
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            for k in ("hbm_gbs", "hbm_gbs_sustained"):
+                if k in d:
+                    return float(d[k]), "measured (MEASURED_PEAKS.json %s)" % k
+        except Exception:  # noqa: BLE001
+            pass
+    return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+
+
+def run_chunked(sim, n_steps):
+    """n_steps of the main loop through the fused entry point, with delete_lipid at multiples of freq_cleanup (openrbc.cpp:201)."""
+    done = 0
+    while done < n_steps:
+        if sim.nstep % FREQ_CLEANUP == 0:
+            sim.delete_lipid(sim.stray_tolerance)
+        k = min(n_steps - done, FREQ_CLEANUP - sim.nstep % FREQ_CLEANUP)
+        sim.run_langevin(k)
+        done += k
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import openrbc_b200 as orbc
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — openrbc_b200 has no CPU path (use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if rank == 0:
+        ensure_state(args.workload)
+    if world > 1:
+        dist.barrier()
+    st = load_state(args.workload)
+    n_total = len(st["lx"]) + len(st["px"])
+
+    def make_sim(state):
+        s = orbc.Simulation(state, kBT=0.22, device=local)
+        s.stray_tolerance = 2.5
+        return s
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident leg ------------------------------------------------------------------------------------------
+    sim = make_sim(st)
+    run_chunked(sim, args.warmup)
+    sim.synchronize()
+    sim.profile_enable(True)
+    l0 = sim.launch_count()
+    barrier()
+    with Clocks(local) as clk:
+        sim.event_record(0)
+        run_chunked(sim, args.steps)
+        sim.event_record(1)
+        sim.synchronize()
+        barrier()
+    ms = sim.event_elapsed_ms(0, 1)
+    launches = sim.launch_count() - l0
+    prof = {k: sim.profile_read(k) for k in orbc.engine.PROF}
+    sim.profile_enable(False)
+    n_now = sim.size(0) + sim.size(1)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    # N>1: independent replicas of the whole cell, one per GPU (spatial decomposition of one cell: see DESIGN.md §multi-GPU)
+    value = world * n_total * args.steps / (ms * 1e-3)
+    temperature = sim.compute_temperature()
+    sim.close()
+
+    # ---- end-to-end leg: host buffers through the per-call C ABI ---------------------------------------------------------
+    pinned = {}
+    for k in ("lx", "lv", "ln", "lo", "px", "pv", "pn", "po"):
+        tns = torch.empty(st[k].shape, dtype=torch.float32, pin_memory=True)
+        tns.numpy()[...] = st[k]
+        pinned[k] = tns
+    host = dict(st)
+    host.update({k: v.numpy() for k, v in pinned.items()})
+    out_l = {f: torch.empty((len(st["lx"]), 3), dtype=torch.float32, pin_memory=True) for f in "xn"}
+    out_p = {f: torch.empty((len(st["px"]), 3), dtype=torch.float32, pin_memory=True) for f in "xn"}
+    e2e_sim = orbc.Simulation(None, kBT=0.22, device=local)
+    e2e_sim.stray_tolerance = 2.5
+    # warm-up of the e2e path (allocations, first-touch): one upload + W steps, then the timed job starts from a fresh upload
+    e2e_sim.upload(host)
+    for _ in range(min(args.warmup, 4)):
+        e2e_sim.step_langevin_checked()
+    e2e_sim.nstep = 0
+    barrier()
+    e2e_sim.event_record(2)
+    t_wall = time.perf_counter()
+    e2e_sim.upload(host)
+    h2d = sum(host[k].nbytes for k in ("lx", "lv", "ln", "lo", "px", "pv", "pn", "po", "ptype", "ptag", "bonds", "centroids", "cs_l", "cs_p"))
+    d2h = 0
+    for _ in range(args.steps):
+        if e2e_sim.nstep % FREQ_CLEANUP == 0:
+            e2e_sim.delete_lipid(e2e_sim.stray_tolerance); d2h += 8
+        e2e_sim.step_langevin_checked(); d2h += 16
+        if e2e_sim.nstep % FREQ_DISPLAY == 0:
+            e2e_sim.compute_temperature(); d2h += 8
+    fl = e2e_sim.download_into(0, x=out_l["x"].numpy(), n=out_l["n"].numpy(), affiliation=True)
+    fp = e2e_sim.download_into(1, x=out_p["x"].numpy(), n=out_p["n"].numpy(), affiliation=True)
+    d2h += fl + fp
+    e2e_sim.event_record(3)
+    e2e_sim.synchronize()
+    wall_ms = (time.perf_counter() - t_wall) * 1e3
+    barrier()
+    e2e_ms = max(e2e_sim.event_elapsed_ms(2, 3), wall_ms)
+    if world > 1:
+        t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_value = world * n_total * args.steps / (e2e_ms * 1e-3)
+    e2e_sim.close()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = hbm_peak()
+    pl_ms, pl_cnt = prof["pair_lipid"]
+    n_l = len(st["lx"])
+    achieved = (B_ALG_PAIR * n_l / (pl_ms / pl_cnt * 1e-3) / 1e9) if pl_cnt else None
+    shares = {k: round(v[0] / ms, 4) for k, v in prof.items()}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak" if world > 1 else "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args.workload, st), "l2": "inputs larger than L2 (state %.0f MB resident in HBM, no flush needed)" % (n_total * 6 * 16 / 1e6),
+                   "multi_gpu": "single GPU" if world == 1 else f"{world} independent replicas of the whole cell (no data-path collective)",
+                   "integrator": "verlet_langevin kBT=0.22 dt=0.01, rebuild every 2 steps, Morton sort every 24, cleanup every 60",
+                   "particles_at_end": n_now, "temperature_at_end": temperature,
+                   "hbm_roofline_frac_step": value / world * B_ALG_STEP / 1e9 / peak, "device_time_shares": shares},
+        "roofline": {"bound": "hbm", "kernel": "k_pair_lipid (lipid side of compute_pairwise_fused)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+                     "launch_ms": pl_ms / pl_cnt if pl_cnt else None, "launches_timed": pl_cnt,
+                     "algorithmic_bytes_per_launch": B_ALG_PAIR * n_l,
+                     "note": "pair forces are FP32-ALU bound (~1.6-3 kFLOP per 48 B), see DESIGN.md; HBM fraction reported as the contract asks"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d / args.steps, "d2h_bytes_per_step": d2h / args.steps,
+                "ms_per_step": e2e_ms / args.steps, "what": "upload from pinned host containers + K per-call steps with status read-back + frame download, all timed"},
+        "gpu_launches": int(launches),
+        "clocks": clk.summary(),
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline_subprocess(args)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=240)
+    ap.add_argument("--warmup", type=int, default=24)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="rbc")
+    ap.add_argument("--threads", type=int, default=0, help="reference arm: OpenMP threads (0 = all host cores)")
+    ap.add_argument("--ref-budget", type=float, default=150.0, help="reference arm: wall-clock bound in seconds")
+    ap.add_argument("--cpu-steps", type=int, default=40, help="steps of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        os.environ.setdefault("OMP_PROC_BIND", "close")
+        os.environ.setdefault("OMP_PLACES", "cores")
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

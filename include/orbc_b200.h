@@ -170,6 +170,19 @@ ORBC_API int  orbc_debug_noise(orbc_ctx *ctx, uint64_t seed, int nstep, int spec
 /* ---- timing on the context's stream (CUDA events) ----------------------------------------------------------------- */
 ORBC_API int  orbc_event_record(orbc_ctx *ctx, int slot /* 0..15 */);
 ORBC_API int  orbc_event_elapsed_ms(orbc_ctx *ctx, int slot_a, int slot_b, float *ms);
+/* per-kernel-class device time, measured with CUDA event pairs recorded on the context's stream around every launch
+ * of the class while profiling is enabled (bench.py's roofline figures come from here).  orbc_profile_read synchronises,
+ * returns the summed duration and launch count since the last read of that class, and resets them. */
+typedef enum {
+    ORBC_PROF_PAIR_LIPID = 0,    /* lipid side of compute_pairwise_fused (LL + lipid side of protein-lipid) */
+    ORBC_PROF_PAIR_PROTEIN = 1,  /* protein side (PP + protein side of protein-lipid) */
+    ORBC_PROF_BONDED = 2,
+    ORBC_PROF_INTEGRATE = 3,
+    ORBC_PROF_REBUILD = 4,       /* voronoi.update + both cell updates, all kernels together */
+    ORBC_PROF_N = 5
+} orbc_prof_class;
+ORBC_API int  orbc_profile_enable(orbc_ctx *ctx, int on);
+ORBC_API int  orbc_profile_read(orbc_ctx *ctx, int cls, double *total_ms, unsigned long long *count);
 /* number of kernels this context has launched since creation */
 ORBC_API int  orbc_launch_count(orbc_ctx *ctx, unsigned long long *n);
 

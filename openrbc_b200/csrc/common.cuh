@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdint>
 #include <cstring>
+#include <vector>
 
 #include "../../include/orbc_b200.h"
 
@@ -100,6 +101,10 @@ struct orbc_ctx {
     cudaEvent_t ev[16] = {};
     unsigned long long launches = 0;
     bool ff_set = false;
+    // per-class event-pair profiling (orbc_profile_*)
+    bool prof_on = false;
+    std::vector<cudaEvent_t> prof_ev[ORBC_PROF_N];   // even = start, odd = stop
+    size_t prof_used[ORBC_PROF_N] = {};
 };
 
 namespace orbc {
@@ -108,6 +113,24 @@ namespace orbc {
 #define ORBC_LAUNCH(ctx, kernel, grid, block, smem, ...) do { \
         kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__); (ctx)->launches++; \
         ORBC_CUDA(cudaGetLastError()); } while (0)
+
+// event pair around the launches of one kernel class; no-ops unless profiling is on
+inline int prof_mark(orbc_ctx *c, int cls, bool stop) {
+    if (!c->prof_on) return ORBC_OK;
+    auto &v = c->prof_ev[cls];
+    size_t &u = c->prof_used[cls];
+    if (u >= ((size_t)1 << 17)) return ORBC_OK;          // bounded: the oldest 65536 launches are kept
+    if (u >= v.size()) { cudaEvent_t e; ORBC_CUDA(cudaEventCreate(&e)); v.push_back(e); }
+    if (stop != (bool)(u & 1)) return ORBC_OK;           // unmatched stop / nested start: ignore
+    ORBC_CUDA(cudaEventRecord(v[u], c->stream));
+    ++u;
+    return ORBC_OK;
+}
+struct ProfScope {
+    orbc_ctx *c; int cls;
+    ProfScope(orbc_ctx *c_, int cls_) : c(c_), cls(cls_) { prof_mark(c, cls, false); }
+    ~ProfScope() { prof_mark(c, cls, true); }
+};
 
 inline unsigned blocks_for(size_t n, unsigned block) { return (unsigned)((n + block - 1) / block); }
 

@@ -176,14 +176,15 @@ int launch_pairwise(orbc_ctx *c) {
     a.xp = P.X(); a.np = P.N(); a.cs_p = P.cell_start; a.cell_p = P.C(); a.n_p = (int)P.n;
     a.stencil = c->stencil; a.stencil_cnt = c->stencil_cnt;
     a.fl = L.f; a.tl = L.t; a.fp = P.f; a.tp = P.t;
-    if (L.n) ORBC_LAUNCH(c, k_pair_lipid, blocks_for(L.n, 128), 128, 0, a);
-    if (P.n) ORBC_LAUNCH(c, k_pair_protein, blocks_for(P.n, 128), 128, 0, a);
+    if (L.n) { ProfScope ps(c, ORBC_PROF_PAIR_LIPID); ORBC_LAUNCH(c, k_pair_lipid, blocks_for(L.n, 128), 128, 0, a); }
+    if (P.n) { ProfScope ps(c, ORBC_PROF_PAIR_PROTEIN); ORBC_LAUNCH(c, k_pair_protein, blocks_for(P.n, 128), 128, 0, a); }
     return ORBC_OK;
 }
 
 int launch_bonded(orbc_ctx *c) {
     Species &P = c->sp[1];
     if (!c->n_bonds) return ORBC_OK;
+    ProfScope ps(c, ORBC_PROF_BONDED);
     ORBC_LAUNCH(c, k_bonded, blocks_for(c->n_bonds, kBlock), kBlock, 0, c->bonds, c->n_bonds, c->tag2idx, P.X(), P.f);
     return ORBC_OK;
 }
@@ -238,6 +239,7 @@ int do_cell_update(orbc_ctx *c, int sp) {
 }
 
 int do_integrate_langevin(orbc_ctx *c, const orbc_step_params *p) {
+    ProfScope ps(c, ORBC_PROF_INTEGRATE);
     for (int sp = 0; sp < 2; ++sp) {
         Species &S = c->sp[sp];
         if (!S.n) continue;
@@ -337,6 +339,7 @@ void orbc_destroy(orbc_ctx *c) {
     dev_free(c->noise[0]); dev_free(c->noise[1]);
     if (c->h_acc) cudaFreeHost(c->h_acc); if (c->h_flags) cudaFreeHost(c->h_flags); if (c->h_counters) cudaFreeHost(c->h_counters); if (c->h_nh) cudaFreeHost(c->h_nh);
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
+    for (auto &v : c->prof_ev) for (auto &e : v) cudaEventDestroy(e);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -432,7 +435,7 @@ int orbc_set_field(orbc_ctx *c, int sp, char field, size_t stride, const float *
     if (!c || sp < 0 || sp > 1 || stride < 3 || !src) return fail(ORBC_ERR_ARG, "orbc_set_field: bad argument");
     Species &S = c->sp[sp];
     float4 *dst = field == 'f' ? S.f : field == 't' ? S.t : field == 'v' ? S.V() : field == 'x' ? S.X() : field == 'n' ? S.N() : field == 'o' ? S.O() : nullptr;
-    if (!dst) return fail(ORBC_ERR_ARG, "orbc_set_field: unknown field '%c'", field);
+    if (!strchr("ftvxno", field)) return fail(ORBC_ERR_ARG, "orbc_set_field: unknown field '%c'", field);
     if (!S.n) return ORBC_OK;
     ORBC_TRY(ensure_stage(c, S.n * stride));
     ORBC_CUDA(cudaMemcpyAsync(c->stage, src, sizeof(float) * S.n * stride, cudaMemcpyHostToDevice, c->stream));
@@ -449,12 +452,17 @@ int orbc_cell_update(orbc_ctx *c, int sp, int nstep, int freq_sort_bond) {
     return do_cell_update(c, sp);
 }
 
-int orbc_rebuild(orbc_ctx *c, int nstep, int freq_sort_ctrd, int freq_sort_bond) {
-    (void)freq_sort_bond;
-    if (!c) return fail(ORBC_ERR_ARG, "null ctx");
+int do_rebuild(orbc_ctx *c, int nstep, int freq_sort_ctrd) {
+    ProfScope ps(c, ORBC_PROF_REBUILD);
     ORBC_TRY(do_voronoi_update(c, nstep, freq_sort_ctrd));
     ORBC_TRY(do_cell_update(c, ORBC_LIPID));
     return do_cell_update(c, ORBC_PROTEIN);
+}
+
+int orbc_rebuild(orbc_ctx *c, int nstep, int freq_sort_ctrd, int freq_sort_bond) {
+    (void)freq_sort_bond;
+    if (!c) return fail(ORBC_ERR_ARG, "null ctx");
+    return do_rebuild(c, nstep, freq_sort_ctrd);
 }
 
 int orbc_delete_lipid(orbc_ctx *c, float tol, size_t *n_out) {
@@ -568,11 +576,7 @@ int orbc_run_langevin(orbc_ctx *c, const orbc_step_params *p, int n_steps, int f
     orbc_step_params q = *p;
     q.noise_lipid = q.noise_protein = nullptr;
     for (int s = 0; s < n_steps; ++s, ++q.nstep) {
-        if (q.nstep % freq_voronoi == 0) {
-            ORBC_TRY(do_voronoi_update(c, q.nstep, freq_sort_ctrd));
-            ORBC_TRY(do_cell_update(c, ORBC_LIPID));
-            ORBC_TRY(do_cell_update(c, ORBC_PROTEIN));
-        }
+        if (q.nstep % freq_voronoi == 0) ORBC_TRY(do_rebuild(c, q.nstep, freq_sort_ctrd));
         ORBC_TRY(launch_pairwise(c));
         ORBC_TRY(launch_bonded(c));
         ORBC_TRY(do_integrate_langevin(c, &q));
@@ -593,11 +597,7 @@ int orbc_run_nh(orbc_ctx *c, const orbc_step_params *p, int n_steps, int freq_vo
             ORBC_LAUNCH(c, k_nh_initial_fused, blocks_for(c->sp[sp].n, 256), 256, 0, a);
         }
         ORBC_LAUNCH(c, k_nh_zeta_update, 1, 32, 0, c->d_nh, c->d_acc, q.dt, q.kBT, n);
-        if (q.nstep % freq_voronoi == 0) {
-            ORBC_TRY(do_voronoi_update(c, q.nstep, freq_sort_ctrd));
-            ORBC_TRY(do_cell_update(c, ORBC_LIPID));
-            ORBC_TRY(do_cell_update(c, ORBC_PROTEIN));
-        }
+        if (q.nstep % freq_voronoi == 0) ORBC_TRY(do_rebuild(c, q.nstep, freq_sort_ctrd));
         ORBC_TRY(launch_pairwise(c));
         ORBC_TRY(launch_bonded(c));
         for (int sp = 0; sp < 2; ++sp) if (c->sp[sp].n) {
@@ -706,6 +706,22 @@ int orbc_event_elapsed_ms(orbc_ctx *c, int a, int b, float *ms) {
     if (!c || a < 0 || a >= 16 || b < 0 || b >= 16 || !ms) return fail(ORBC_ERR_ARG, "bad event slot");
     ORBC_CUDA(cudaEventSynchronize(c->ev[b]));
     ORBC_CUDA(cudaEventElapsedTime(ms, c->ev[a], c->ev[b]));
+    return ORBC_OK;
+}
+int orbc_profile_enable(orbc_ctx *c, int on) {
+    if (!c) return fail(ORBC_ERR_ARG, "null ctx");
+    ORBC_CUDA(cudaStreamSynchronize(c->stream));
+    c->prof_on = on != 0;
+    for (auto &u : c->prof_used) u = 0;
+    return ORBC_OK;
+}
+int orbc_profile_read(orbc_ctx *c, int cls, double *total_ms, unsigned long long *count) {
+    if (!c || cls < 0 || cls >= ORBC_PROF_N || !total_ms || !count) return fail(ORBC_ERR_ARG, "orbc_profile_read: bad argument");
+    ORBC_CUDA(cudaStreamSynchronize(c->stream));
+    double sum = 0.0; const size_t pairs = c->prof_used[cls] / 2;
+    for (size_t k = 0; k < pairs; ++k) { float ms = 0.f; ORBC_CUDA(cudaEventElapsedTime(&ms, c->prof_ev[cls][2 * k], c->prof_ev[cls][2 * k + 1])); sum += ms; }
+    *total_ms = sum; *count = pairs;
+    c->prof_used[cls] = 0;
     return ORBC_OK;
 }
 int orbc_launch_count(orbc_ctx *c, unsigned long long *n) { if (!c || !n) return fail(ORBC_ERR_ARG, "bad argument"); *n = c->launches; return ORBC_OK; }

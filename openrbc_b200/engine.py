@@ -20,13 +20,15 @@ STENCIL_STRIDE = 64
 DUMP = dict(centroids=0, cell_start_l=1, cell_start_p=2, cells_l=3, cells_p=4, aff_l=5, aff_p=6, morton_keys=7, morton_perm=8,
             stencil_counts=9, stencil=10, tag2idx=11, counters=12)
 
+PROF = dict(pair_lipid=0, pair_protein=1, bonded=2, integrate=3, rebuild=4)
+
 EXPORTS = [
     "orbc_create", "orbc_destroy", "orbc_last_error", "orbc_synchronize", "orbc_set_stream", "orbc_forcefield_canonical",
     "orbc_set_forcefield", "orbc_upload", "orbc_upload_bonds", "orbc_voronoi_upload", "orbc_set_field", "orbc_voronoi_update",
     "orbc_cell_update", "orbc_rebuild", "orbc_delete_lipid", "orbc_compute_pairwise_fused", "orbc_compute_bonded",
     "orbc_constrain_volume", "orbc_integrate", "orbc_nh_zeta_update", "orbc_compute_temperature", "orbc_run_langevin",
     "orbc_run_nh", "orbc_download", "orbc_size", "orbc_n_cells", "orbc_debug_dump", "orbc_debug_noise", "orbc_event_record",
-    "orbc_event_elapsed_ms", "orbc_launch_count",
+    "orbc_event_elapsed_ms", "orbc_launch_count", "orbc_profile_enable", "orbc_profile_read",
 ]
 
 
@@ -100,6 +102,8 @@ def load_library():
         lib.orbc_event_record.argtypes = [C.c_void_p, C.c_int]
         lib.orbc_event_elapsed_ms.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         lib.orbc_launch_count.argtypes = [C.c_void_p, C.c_void_p]
+        lib.orbc_profile_enable.argtypes = [C.c_void_p, C.c_int]
+        lib.orbc_profile_read.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         lib.orbc_set_stream.argtypes = [C.c_void_p, C.c_void_p]
         lib.orbc_destroy.argtypes = [C.c_void_p]
         lib.orbc_destroy.restype = None
@@ -211,6 +215,17 @@ class Simulation:
         if ids:
             out["type"], out["tag"] = ty, tg
         return out
+
+    def download_into(self, s, x=None, v=None, n=None, o=None, f=None, t=None, affiliation=False):
+        """Download selected fields into caller-owned (e.g. pinned) N x 3 float32 arrays; returns the bytes copied."""
+        cnt = self.size(s)
+        aff = np.empty(cnt, np.int32) if affiliation else None
+        arrs = [x, v, n, o, f, t]
+        for a in arrs:
+            assert a is None or (a.dtype == np.float32 and a.flags.c_contiguous and len(a) >= cnt)
+        nn = C.c_size_t()
+        self._ck(self.lib.orbc_download(self.ctx, s, 3, *[_p(a) for a in arrs], _p(aff), None, None, C.byref(nn)))
+        return sum(12 * cnt for a in arrs if a is not None) + (4 * cnt if affiliation else 0)
 
     def get(self, s, field):
         return self.download(s, field)[field]
@@ -339,6 +354,11 @@ class Simulation:
         self.verlet_langevin(nl, npr)
         self.nstep += 1
 
+    def step_langevin_checked(self):
+        """One loop iteration call by call, then wait for it and read the device status back (16 B D2H)."""
+        self.step_langevin()
+        self.synchronize()
+
     # ---- timing ------------------------------------------------------------------------------------------
     def event_record(self, slot):
         self._ck(self.lib.orbc_event_record(self.ctx, slot))
@@ -347,6 +367,15 @@ class Simulation:
         ms = C.c_float()
         self._ck(self.lib.orbc_event_elapsed_ms(self.ctx, a, b, C.byref(ms)))
         return ms.value
+
+    def profile_enable(self, on=True):
+        self._ck(self.lib.orbc_profile_enable(self.ctx, int(on)))
+
+    def profile_read(self, cls):
+        """(total device ms, launches) of one kernel class since the last read; cls is a key of PROF."""
+        ms, cnt = C.c_double(), C.c_ulonglong()
+        self._ck(self.lib.orbc_profile_read(self.ctx, PROF[cls], C.byref(ms), C.byref(cnt)))
+        return ms.value, cnt.value
 
     def launch_count(self):
         n = C.c_ulonglong()
