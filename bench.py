@@ -99,7 +99,7 @@ def run_reference(args):
     st = load_state(args.workload)
     n = len(st["lx"]) + len(st["px"])
     threads = args.threads or (os.cpu_count() or 1)
-    r = refmod.Ref("fast", threads=threads, args=["-i", "trimesh"])
+    r = refmod.Ref("fast", threads=threads, args=["-i", "lipid"])   # the state is loaded below; "lipid" only satisfies the CLI check
     r.load_state(st)
     r.set_param("kBT", 0.22)
     budget = args.ref_budget
@@ -147,25 +147,32 @@ def cpu_baseline_subprocess(args):
 # clocks sampler (nvidia-smi during the timed region)
 # ---------------------------------------------------------------------------------------------------------------------
 class Clocks:
-    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """SM clock / power / throttle reasons sampled every 20 ms through NVML while the timed region runs."""
 
     def __init__(self, index):
         self.rows, self.stop, self.index = [], False, index
         self.th = threading.Thread(target=self._run, daemon=True)
+        self.max_sm = None
+        self.err = None
 
     def _run(self):
-        while not self.stop:
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
-                                     stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.splitlines()[0].split(",")])
-            except Exception:  # noqa: BLE001
-                pass
-            time.sleep(0.1)
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.index]) if vis and all(t.strip().isdigit() for t in vis.split(",")) else self.index
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.max_sm = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            while not self.stop:
+                self.rows.append((nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), nv.nvmlDeviceGetPowerUsage(h) / 1e3,
+                                  nv.nvmlDeviceGetCurrentClocksEventReasons(h)))
+                time.sleep(0.02)
+        except Exception as e:  # noqa: BLE001
+            self.err = repr(e)
 
     def __enter__(self):
         self.th.start()
+        time.sleep(0.05)
         return self
 
     def __exit__(self, *a):
@@ -174,15 +181,14 @@ class Clocks:
 
     def summary(self):
         if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        sm = sorted(int(float(r[0])) for r in self.rows)
-        reasons = []
-        for k, name in enumerate(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")):
-            if any(r[3 + k].lower().startswith("active") for r in self.rows):
-                reasons.append(name)
-        pw = [float(r[2]) for r in self.rows if r[2].replace(".", "", 1).isdigit()]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(float(self.rows[0][1])), "reasons": reasons, "samples": len(sm),
-                "power_w_max": max(pw) if pw else None}
+            return {"sm_mhz": None, "sm_max_mhz": self.max_sm, "reasons": ["nvml unavailable: %s" % self.err]}
+        sm = sorted(r[0] for r in self.rows)
+        bits = 0
+        for r in self.rows:
+            bits |= r[2]
+        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap", 0x80: "hw_power_brake_slowdown"}
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_sm, "reasons": [n for b, n in names.items() if bits & b], "samples": len(sm),
+                "power_w_max": max(r[1] for r in self.rows)}
 
 
 # ---------------------------------------------------------------------------------------------------------------------

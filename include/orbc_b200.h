@@ -91,6 +91,10 @@ ORBC_API int  orbc_synchronize(orbc_ctx *ctx);
 /* adopt an existing CUDA stream (cudaStream_t passed as void*); NULL = the context's own stream */
 ORBC_API int  orbc_set_stream(orbc_ctx *ctx, void *cuda_stream);
 
+/* tuning / test switches, by name.  "pair_impl": 2 = queued lipid kernel + warp-per-cell protein kernel (default),
+ * 1 = the simple thread-per-particle kernels kept as an independent cross-check. */
+ORBC_API int  orbc_set_option(orbc_ctx *ctx, const char *name, double value);
+
 /* ---- force field (forcefield_canonical.h) ------------------------------------------------------------------ */
 ORBC_API int  orbc_forcefield_canonical(orbc_forcefield *ff);
 ORBC_API int  orbc_set_forcefield(orbc_ctx *ctx, const orbc_forcefield *ff);

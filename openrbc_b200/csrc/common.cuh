@@ -84,6 +84,8 @@ struct orbc_ctx {
     int *stencil_cnt = nullptr;                   // n_cells, packed n6 | n8 << 8 | n9 << 16
     bool stencil_valid = false;
     float4 *cell_normal = nullptr;                // constrain_volume's persistent scratch
+    float4 *lbound = nullptr, *pbound = nullptr;  // per-cell bounding spheres of the current lipids / proteins (pair_queue.cuh)
+    unsigned type_mask = 0;                       // protein types present (bit t), from the last protein upload
     // bonds
     size_t n_bonds = 0;
     int *bonds = nullptr;                         // (type, tag_i, tag_j)
@@ -101,6 +103,7 @@ struct orbc_ctx {
     cudaEvent_t ev[16] = {};
     unsigned long long launches = 0;
     bool ff_set = false;
+    int pair_impl = 2;
     // per-class event-pair profiling (orbc_profile_*)
     bool prof_on = false;
     std::vector<cudaEvent_t> prof_ev[ORBC_PROF_N];   // even = start, odd = stop

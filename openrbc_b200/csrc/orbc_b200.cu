@@ -9,6 +9,7 @@
 #include "primitives.cuh"
 #include "rebuild.cuh"
 #include "pair.cuh"
+#include "pair_queue.cuh"
 #include "integrate.cuh"
 
 using namespace orbc;
@@ -176,8 +177,28 @@ int launch_pairwise(orbc_ctx *c) {
     a.xp = P.X(); a.np = P.N(); a.cs_p = P.cell_start; a.cell_p = P.C(); a.n_p = (int)P.n;
     a.stencil = c->stencil; a.stencil_cnt = c->stencil_cnt;
     a.fl = L.f; a.tl = L.t; a.fp = P.f; a.tp = P.t;
-    if (L.n) { ProfScope ps(c, ORBC_PROF_PAIR_LIPID); ORBC_LAUNCH(c, k_pair_lipid, blocks_for(L.n, 128), 128, 0, a); }
-    if (P.n) { ProfScope ps(c, ORBC_PROF_PAIR_PROTEIN); ORBC_LAUNCH(c, k_pair_protein, blocks_for(P.n, 128), 128, 0, a); }
+    if (c->pair_impl == 1) {
+        if (L.n) { ProfScope ps(c, ORBC_PROF_PAIR_LIPID); ORBC_LAUNCH(c, k_pair_lipid, blocks_for(L.n, 128), 128, 0, a); }
+        if (P.n) { ProfScope ps(c, ORBC_PROF_PAIR_PROTEIN); ORBC_LAUNCH(c, k_pair_protein, blocks_for(P.n, 128), 128, 0, a); }
+        return ORBC_OK;
+    }
+    {
+        ProfScope ps(c, ORBC_PROF_PAIR_LIPID);
+        ORBC_LAUNCH(c, k_cell_bounds, blocks_for(c->n_cells, 128), 128, 0, c->centroid, c->n_cells, L.cell_start, L.X(), P.n ? P.cell_start : nullptr, P.X(), c->lbound, c->pbound);
+        if (L.n) ORBC_LAUNCH(c, k_pair_ll<true>, blocks_for(L.n, kLLBlock), kLLBlock, 0, a);
+    }
+    if (P.n) {
+        // largest interaction range of every protein type against lipids and against the protein types present
+        CullTable ct;
+        for (int t = 0; t < kNType; ++t) {
+            ct.cut_l[t] = std::sqrt(std::max(g_host_ff.cutsqlp[t], g_host_ff.lj_cutsq[t]));
+            float m = 0.f;
+            for (int u = 0; u < kNType; ++u) if (c->type_mask >> u & 1) m = std::max(m, std::max(g_host_ff.cutsqpp[t + kNType * u], g_host_ff.lj_cutsq[t + kNType * u]));
+            ct.cut_p[t] = std::sqrt(m);
+        }
+        ProfScope ps(c, ORBC_PROF_PAIR_PROTEIN);
+        ORBC_LAUNCH(c, k_pair_prot, blocks_for(P.n, kPBlock), kPBlock, 0, a, c->lbound, c->pbound, ct);
+    }
     return ORBC_OK;
 }
 
@@ -334,7 +355,7 @@ void orbc_destroy(orbc_ctx *c) {
     free_species(c->sp[0]); free_species(c->sp[1]);
     dev_free(c->centroid); dev_free(c->centroid_tmp); dev_free(c->keys); dev_free(c->keys_tmp); dev_free(c->perm); dev_free(c->perm_tmp); dev_free(c->inv);
     dev_free(c->grid.bin_start); dev_free(c->grid.bin_items); dev_free(c->grid.bin_of); dev_free(c->grid.bin_slot);
-    dev_free(c->stencil); dev_free(c->stencil_cnt); dev_free(c->cell_normal); dev_free(c->bonds); dev_free(c->tag2idx);
+    dev_free(c->stencil); dev_free(c->stencil_cnt); dev_free(c->cell_normal); dev_free(c->lbound); dev_free(c->pbound); dev_free(c->bonds); dev_free(c->tag2idx);
     dev_free(c->scan_tmp); dev_free(c->radix_hist); dev_free(c->stage); dev_free(c->d_acc); dev_free(c->d_counters); dev_free(c->d_flags); dev_free(c->d_nh);
     dev_free(c->noise[0]); dev_free(c->noise[1]);
     if (c->h_acc) cudaFreeHost(c->h_acc); if (c->h_flags) cudaFreeHost(c->h_flags); if (c->h_counters) cudaFreeHost(c->h_counters); if (c->h_nh) cudaFreeHost(c->h_nh);
@@ -342,6 +363,12 @@ void orbc_destroy(orbc_ctx *c) {
     for (auto &v : c->prof_ev) for (auto &e : v) cudaEventDestroy(e);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
+}
+
+int orbc_set_option(orbc_ctx *c, const char *name, double value) {
+    if (!c || !name) return fail(ORBC_ERR_ARG, "null argument");
+    if (!strcmp(name, "pair_impl")) { if (value != 1 && value != 2) return fail(ORBC_ERR_ARG, "pair_impl must be 1 or 2"); c->pair_impl = (int)value; return ORBC_OK; }
+    return fail(ORBC_ERR_ARG, "unknown option '%s'", name);
 }
 
 int orbc_synchronize(orbc_ctx *c) { ORBC_CUDA(cudaStreamSynchronize(c->stream)); return check_flags(c); }
@@ -374,6 +401,14 @@ int orbc_upload(orbc_ctx *c, int sp, size_t n, size_t stride, const float *x, co
     ORBC_LAUNCH(c, k_zero4, nb, kBlock, 0, S.t, n, (const int *)nullptr);
     ORBC_LAUNCH(c, k_fill_int, nb, kBlock, 0, S.C(), n, -1);
     ORBC_CUDA(cudaStreamSynchronize(c->stream));   // host arrays are borrowed only for the duration of the call
+    if (sp == ORBC_PROTEIN) {
+        c->type_mask = 0;
+        for (size_t i = 0; i < n; ++i) {
+            const int t = type ? type[i] : 0;
+            if (t < 0 || t >= kNType) return fail(ORBC_ERR_ARG, "protein %zu has type %d outside [0,%d)", i, t, kNType);
+            c->type_mask |= 1u << t;
+        }
+    }
     if (sp == ORBC_PROTEIN && tag) {
         int mx = 0;
         for (size_t i = 0; i < n; ++i) { if (tag[i] < 0) return fail(ORBC_ERR_ARG, "negative protein tag"); mx = std::max(mx, tag[i]); }
@@ -406,7 +441,7 @@ int orbc_voronoi_upload(orbc_ctx *c, int nc, const float *centroids3, const int 
         ORBC_TRY(dev_alloc(&c->keys, nc)); ORBC_TRY(dev_alloc(&c->keys_tmp, nc)); ORBC_TRY(dev_alloc(&c->perm, nc)); ORBC_TRY(dev_alloc(&c->perm_tmp, nc)); ORBC_TRY(dev_alloc(&c->inv, nc));
         ORBC_TRY(dev_alloc(&c->grid.bin_items, nc)); ORBC_TRY(dev_alloc(&c->grid.bin_of, nc)); ORBC_TRY(dev_alloc(&c->grid.bin_slot, nc));
         ORBC_TRY(dev_alloc(&c->stencil, (size_t)nc * kStencilStride)); ORBC_TRY(dev_alloc(&c->stencil_cnt, nc));
-        ORBC_TRY(dev_alloc(&c->cell_normal, nc));
+        ORBC_TRY(dev_alloc(&c->cell_normal, nc)); ORBC_TRY(dev_alloc(&c->lbound, nc)); ORBC_TRY(dev_alloc(&c->pbound, nc));
         for (int s = 0; s < 2; ++s) ORBC_TRY(dev_alloc(&c->sp[s].cell_start, (size_t)nc + 1));
         c->n_cells = nc;
     }

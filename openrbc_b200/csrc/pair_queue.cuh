@@ -1,0 +1,317 @@
+// pair_queue.cuh — the production pair-force kernels.
+//
+// Same candidate sets (cells whose CENTROIDS are closer than 6 / 8 / 9, compute_pairwise_fused.h:260,278,299) and the same
+// per-pair arithmetic as pair.cuh (the simple kernels kept as an independent cross-check), organised for the SIMT machine:
+//
+//   k_cell_bounds  per Voronoi cell, a bounding sphere of its current lipids (centre = centroid of the last rebuild) and of
+//                  its current proteins (centre = their mean).  A particle can only interact with members of a cell whose
+//                  sphere it approaches to within the cutoff, so whole (particle, cell) pairs are skipped by one distance
+//                  test; the skip is conservative (margin kCullEps), results are unchanged.
+//   k_pair_ll      one thread per lipid.  Phase 1 walks the r<6 stencil of the lipid's cell and only TESTS the cutoff
+//                  (r2 < 6.76 && r2 > 1e-5, compute_pairwise_fused.h:109,134); indices that pass go to a per-lane queue in
+//                  shared memory (CPU precedent: the reference's implicit-SIMD "enqueue pairs that pass the cutoff" path,
+//                  pairwise_kernel_implicit_simd.h:25-100).  Phase 2 evaluates the queued pairs, so the ~60-instruction
+//                  force body runs on dense lanes instead of on the ~19 % of lanes that hit in any one iteration.
+//                  One-sided (every lipid gathers its own force), no atomics, fixed summation order.
+//   k_pair_prot    one thread per protein: protein-protein over r<9 (one-sided) and protein-lipid over r<8.  Hits are rare
+//                  (~1 per protein per step on the RBC), so each protein-lipid pair is evaluated ONCE, here, and the lipid
+//                  receives its share through atomicAdd (fp32 RED) instead of re-testing every pair from the lipid side.
+#pragma once
+#include "common.cuh"
+#include "pair.cuh"
+
+namespace orbc {
+
+constexpr int kQCap = 32;          // queue slots per lane
+constexpr int kLLBlock = 128;
+constexpr float kCullEps = 4e-3f;  // slack of the bounding-sphere test (absolute, length units)
+
+struct CullTable {                 // per protein type: largest interaction range against lipids / against the protein types present
+    float cut_l[kNType], cut_p[kNType];
+};
+
+// ---- bounding spheres ------------------------------------------------------------------------------------------------------
+__global__ void k_cell_bounds(const float4 *__restrict__ centroid, int n_cells, const int *__restrict__ cs_l, const float4 *__restrict__ xl,
+                              const int *__restrict__ cs_p, const float4 *__restrict__ xp, float4 *__restrict__ lbound, float4 *__restrict__ pbound) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_cells) return;
+    {
+        const float4 q = centroid[c];
+        const int b = cs_l[c], e = cs_l[c + 1];
+        float r2 = -1.f;                                   // empty cell (or NaN centroid): never passes the test
+        float4 ctr = q;
+        if (!(q.x == q.x)) { ctr = e > b ? xl[b] : make_float4(0, 0, 0, 0); }
+        for (int j = b; j < e; ++j) {
+            const float4 p = xl[j];
+            const float dx = p.x - ctr.x, dy = p.y - ctr.y, dz = p.z - ctr.z;
+            r2 = fmaxf(r2, dx * dx + dy * dy + dz * dz);
+        }
+        lbound[c] = make_float4(ctr.x, ctr.y, ctr.z, r2 < 0.f ? -1.f : sqrtf(r2) * 1.0001f);
+    }
+    if (cs_p) {
+        const int b = cs_p[c], e = cs_p[c + 1];
+        float mx = 0, my = 0, mz = 0;
+        for (int j = b; j < e; ++j) { const float4 p = xp[j]; mx += p.x; my += p.y; mz += p.z; }
+        const float s = e > b ? 1.0f / (float)(e - b) : 0.f;
+        mx *= s; my *= s; mz *= s;
+        float r2 = -1.f;
+        for (int j = b; j < e; ++j) {
+            const float4 p = xp[j];
+            const float dx = p.x - mx, dy = p.y - my, dz = p.z - mz;
+            r2 = fmaxf(r2, dx * dx + dy * dy + dz * dz);
+        }
+        pbound[c] = make_float4(mx, my, mz, r2 < 0.f ? -1.f : sqrtf(r2) * 1.0001f);
+    }
+}
+
+// true when no member of the sphere `b` can be within `cut` of the point (x, y, z)
+__device__ __forceinline__ bool culled(float4 b, float x, float y, float z, float cut) {
+    const float dx = x - b.x, dy = y - b.y, dz = z - b.z;
+    const float lim = b.w + cut + kCullEps;
+    return !(b.w >= 0.f) || (dx * dx + dy * dy + dz * dz > lim * lim);
+}
+
+// ---- lipid-lipid --------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float rsqrt_fast(float x) {      // x is a squared distance in (1e-5, 14.6): never denormal
+    float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y;
+}
+
+__device__ __forceinline__ void sts_i32(unsigned addr, int v) { asm volatile("st.shared.b32 [%0], %1;" :: "r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ int lds_i32(unsigned addr) { int v; asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory"); return v; }
+
+// pairwise_kernel.h:30-68 for particle 1 only (the gathering side): force and torque accumulate straight into the running sums
+struct LLConst { float cut, rep8, att4, alpha, alpha_att, one_m_alpha; };
+__device__ __forceinline__ void ll_eval(const LLConst &k, const float4 *__restrict__ xl, const float4 *__restrict__ nl, F3 xi, F3 mi, int j,
+                                        float &fx, float &fy, float &fz, float &tx, float &ty, float &tz) {
+    const float4 xj = __ldg(xl + j), nj = __ldg(nl + j);
+    const float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
+    const float r2 = dx * dx + dy * dy + dz * dz;
+    const float rinv = rsqrt_fast(r2);
+    const float r = r2 * rinv;
+    const float ux = dx * rinv, uy = dy * rinv, uz = dz * rinv;
+    const float ninj = mi.x * nj.x + mi.y * nj.y + mi.z * nj.z;
+    const float niu = mi.x * ux + mi.y * uy + mi.z * uz;
+    const float nju = nj.x * ux + nj.y * uy + nj.z * uz;
+    const float A = fmaf(k.alpha, ninj - niu * nju, k.one_m_alpha);        // 1 + alpha (a - 1)
+    const float rc = k.cut - r;
+    const float rc2 = rc * rc, rc3 = rc2 * rc, rc4 = rc2 * rc2;
+    const float fra = fmaf(k.rep8, rc3 * rc4, k.att4 * (A * rc3));         // 8 rep rc^7 + 4 A att rc^3
+    const float aua = k.alpha_att * rc4;                                    // alpha * att * rc^4
+    const float auar = aua * rinv;
+    const float pix = mi.x - niu * ux, piy = mi.y - niu * uy, piz = mi.z - niu * uz;
+    const float pjx = nj.x - nju * ux, pjy = nj.y - nju * uy, pjz = nj.z - nju * uz;
+    fx = fmaf(fra, ux, fx); fy = fmaf(fra, uy, fy); fz = fmaf(fra, uz, fz);
+    fx = fmaf(auar, fmaf(nju, pix, niu * pjx), fx); fy = fmaf(auar, fmaf(nju, piy, niu * pjy), fy); fz = fmaf(auar, fmaf(nju, piz, niu * pjz), fz);
+    tx = fmaf(-aua, pjx, tx); ty = fmaf(-aua, pjy, ty); tz = fmaf(-aua, pjz, tz);
+}
+
+// One thread per lipid.  A lane's candidates are the members of the cells in the r<6 stencil of its own cell; the lane walks
+// them as ONE stream, four at a time, independent of what the other lanes of the warp are looking at (lanes of one warp
+// belong to ~3 different cells with different stencils and different cell sizes — aligning them slot by slot would make every
+// lane wait for the largest cell of every slot).  The stream never stalls on the stencil: the range of the next cell and the id
+// of the one after it are prefetched two advances ahead.
+//   phase 1  test the cutoff, push hits on the lane's queue (shared memory, slot-major: conflict-free)
+//   phase 2  drain the queue through the force body on dense lanes; the whole warp drains early if a queue could overflow
+template <bool ACCUM>
+__global__ void __launch_bounds__(kLLBlock) k_pair_ll(PairArgs a) {
+    __shared__ int s_q[kLLBlock / 32][kQCap * 32];
+    const int lane = threadIdx.x & 31;
+    int *const q = s_q[threadIdx.x >> 5] + lane;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i < a.n_l;
+    const float4 *__restrict__ xl = a.xl;
+    const float4 *__restrict__ nl = a.nl;
+    const int *__restrict__ cs = a.cs_l;
+    float fx = 0, fy = 0, fz = 0, tx = 0, ty = 0, tz = 0;
+    F3 xi = {0, 0, 0}, mi = {0, 0, 0};
+    int n6 = 0;
+    const int *st = a.stencil;
+    if (live) {
+        const float4 xi4 = xl[i], ni4 = nl[i];
+        xi = {xi4.x, xi4.y, xi4.z}; mi = {ni4.x, ni4.y, ni4.z};
+        const int c = a.cell_l[i];
+        n6 = a.stencil_cnt[c] & 255;
+        st += (size_t)c * kStencilStride;
+    }
+    const float cutsq = c_ff.cutsqll;
+    const LLConst kc = {c_ff.cutll, 8.0f * c_ff.repll, 4.0f * c_ff.attll, c_ff.alphall, c_ff.alphall * c_ff.attll, 1.0f - c_ff.alphall};
+    // the lane's hit queue, addressed with 32-bit shared-window addresses (slot stride = 32 lanes x 4 B)
+    const unsigned q0 = (unsigned)__cvta_generic_to_shared(q);
+    const unsigned q_full = q0 + (kQCap - 4) * 128;              // a group of four always fits below this mark
+    unsigned qp = q0;
+    // prefetch pipeline: (jb_n, len_n) = range of stencil slot `taken`, c2_nn = cell id of slot `taken + 1`
+    int taken = 0, jb_n = 0, len_n = 0, c2_nn = 0;
+    if (n6 > 0) { const int c2 = __ldg(st); jb_n = __ldg(cs + c2); len_n = __ldg(cs + c2 + 1) - jb_n; }
+    if (n6 > 1) c2_nn = __ldg(st + 1);
+    // cur stays a valid index for idle lanes: loads are unconditional, only the queue push is predicated (the arrays are
+    // allocated with 64 spare elements, so reading up to three elements past a cell's range is always in bounds)
+    int cur = 0, rem = 0;
+    for (;;) {
+        if (rem <= 0 && taken < n6) {                            // advance to the next cell of the stencil
+            cur = jb_n; rem = len_n; ++taken;
+            if (taken < n6) { jb_n = __ldg(cs + c2_nn); len_n = __ldg(cs + c2_nn + 1) - jb_n; }
+            if (taken + 1 < n6) c2_nn = __ldg(st + taken + 1);
+        }
+        if (!__any_sync(0xffffffffu, rem > 0 || taken < n6)) break;
+        if (__any_sync(0xffffffffu, qp > q_full)) {              // make room: every lane drains its queue (dense)
+            for (unsigned e = q0; e < qp; e += 128) ll_eval(kc, xl, nl, xi, mi, lds_i32(e), fx, fy, fz, tx, ty, tz);
+            qp = q0;
+        }
+        const float4 *__restrict__ p = xl + cur;
+        float4 xj[4];
+        #pragma unroll
+        for (int u = 0; u < 4; ++u) xj[u] = __ldg(p + u);
+        #pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float dx = xi.x - xj[u].x, dy = xi.y - xj[u].y, dz = xi.z - xj[u].z;
+            const float r2 = dx * dx + dy * dy + dz * dz;
+            if (u < rem && r2 < cutsq && r2 > 1e-5f) { sts_i32(qp, cur + u); qp += 128; }
+        }
+        if (rem > 0) cur += 4;
+        rem -= 4;
+    }
+    for (unsigned e = q0; e < qp; e += 128) ll_eval(kc, xl, nl, xi, mi, lds_i32(e), fx, fy, fz, tx, ty, tz);
+    if (live) {
+        if (ACCUM) {
+            float4 f = a.fl[i], t = a.tl[i];
+            f.x += fx; f.y += fy; f.z += fz; t.x += tx; t.y += ty; t.z += tz;
+            a.fl[i] = f; a.tl[i] = t;
+        } else {
+            a.fl[i] = make_float4(fx, fy, fz, 0.f); a.tl[i] = make_float4(tx, ty, tz, 0.f);
+        }
+    }
+}
+
+// ---- proteins -------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void atomic_add3(float4 *dst, float x, float y, float z) {
+    atomicAdd(&dst->x, x); atomicAdd(&dst->y, y); atomicAdd(&dst->z, z);
+}
+
+constexpr int kPBlock = 128;
+constexpr int kRangeCap = 16;      // stencil slots handled per round
+
+// One thread per protein.  Phase 0 culls the member lists of the stencil cells against the bounding spheres and COMPACTS the
+// survivors into per-lane range lists in shared memory (a lane-level `if (culled) skip` would save nothing on a SIMT machine;
+// the compaction is what turns skipped cells into skipped warp iterations).  Phase 1 walks the r-th surviving range of every
+// lane together, warp-uniform trip counts, predicated bodies.
+__global__ void __launch_bounds__(kPBlock) k_pair_prot(PairArgs a, const float4 *__restrict__ lbound, const float4 *__restrict__ pbound, CullTable ct) {
+    __shared__ float s_cutsqpp[36], s_ljcutsq[36];
+    __shared__ int s_jb[2][kPBlock / 32][kRangeCap * 32];
+    __shared__ unsigned short s_len[2][kPBlock / 32][kRangeCap * 32];
+    for (int k = threadIdx.x; k < 36; k += blockDim.x) { s_cutsqpp[k] = c_ff.cutsqpp[k]; s_ljcutsq[k] = c_ff.lj_cutsq[k]; }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int *const ljb = s_jb[0][w] + lane, *const pjb = s_jb[1][w] + lane;
+    unsigned short *const llen = s_len[0][w] + lane, *const plen = s_len[1][w] + lane;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i < a.n_p;
+    F3 xi = {0, 0, 0}, mi = {0, 0, 0};
+    int type1 = 0, n8 = 0, n9 = 0;
+    const int *st = a.stencil;
+    if (live) {
+        const float4 xi4 = a.xp[i], ni4 = a.np[i];
+        xi = {xi4.x, xi4.y, xi4.z}; mi = {ni4.x, ni4.y, ni4.z};
+        type1 = __float_as_int(xi4.w);
+        const int c = a.cell_p[i];
+        const int cnt = a.stencil_cnt[c];
+        n8 = (cnt >> 8) & 255; n9 = cnt >> 16;
+        st += (size_t)c * kStencilStride;
+    }
+    // per-type constants in registers (type1 is fixed for the thread)
+    const float cutsq = c_ff.cutsqlp[type1], ljcut = c_ff.lj_cutsq[type1];
+    const float cull_l = type1 == 0 ? ct.cut_l[0] : type1 == 1 ? ct.cut_l[1] : type1 == 2 ? ct.cut_l[2] : type1 == 3 ? ct.cut_l[3] : type1 == 4 ? ct.cut_l[4] : ct.cut_l[5];
+    const float cull_p = type1 == 0 ? ct.cut_p[0] : type1 == 1 ? ct.cut_p[1] : type1 == 2 ? ct.cut_p[2] : type1 == 3 ? ct.cut_p[3] : type1 == 4 ? ct.cut_p[4] : ct.cut_p[5];
+    const float testsq_l = fmaxf(cutsq, ljcut);
+    float fx = 0, fy = 0, fz = 0, tx = 0, ty = 0, tz = 0;
+    const int nmax = __reduce_max_sync(0xffffffffu, n9);
+    for (int kb = 0; kb < nmax; kb += kRangeCap) {
+        // ---- phase 0: cull both member lists of every stencil cell, compact the survivors ------------------------------------------
+        int nl_ = 0, np_ = 0;
+        const int kend = min(kRangeCap, nmax - kb);
+        #pragma unroll 4
+        for (int kk = 0; kk < kend; ++kk) {
+            const int k = kb + kk;
+            const bool in9 = k < n9, in8 = k < n8;
+            int c2 = 0;
+            if (in9) c2 = __ldg(st + k);
+            float4 bp = make_float4(0.f, 0.f, 0.f, -1.f), bl = bp;
+            int pb = 0, pe = 0, lb = 0, le = 0;
+            if (in9) { bp = __ldg(pbound + c2); pb = __ldg(a.cs_p + c2); pe = __ldg(a.cs_p + c2 + 1); }
+            if (in8) { bl = __ldg(lbound + c2); lb = __ldg(a.cs_l + c2); le = __ldg(a.cs_l + c2 + 1); }
+            if (in9 && pe > pb && cull_p > 0.f && !culled(bp, xi.x, xi.y, xi.z, cull_p)) { pjb[np_ * 32] = pb; plen[np_ * 32] = (unsigned short)min(pe - pb, 65535); ++np_; }
+            if (in8 && le > lb && cull_l > 0.f && !culled(bl, xi.x, xi.y, xi.z, cull_l)) { ljb[nl_ * 32] = lb; llen[nl_ * 32] = (unsigned short)min(le - lb, 65535); ++nl_; }
+        }
+        // ---- protein-lipid: evaluated once, here; the lipid gets its share by atomics (compute_pairwise_fused.h:143-179,278-297) ---
+        // every lane streams through ITS surviving ranges four candidates at a time (same scheme as k_pair_ll)
+        {
+            int taken = 0, cur = 0, rem = 0;
+            for (;;) {
+                if (rem <= 0 && taken < nl_) { cur = ljb[taken * 32]; rem = llen[taken * 32]; ++taken; }
+                if (!__any_sync(0xffffffffu, rem > 0 || taken < nl_)) break;
+                const float4 *__restrict__ p = a.xl + cur;
+                float4 xj4[4];
+                #pragma unroll
+                for (int u = 0; u < 4; ++u) xj4[u] = __ldg(p + u);
+                #pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float4 xj = xj4[u];
+                    const F3 d = {xi.x - xj.x, xi.y - xj.y, xi.z - xj.z};          // x_protein - x_lipid (compute_pairwise_fused.h:167)
+                    const float r2 = dot3(d, d);
+                    if (u < rem && r2 < testsq_l && r2 > 1e-5f) {
+                        const int j = cur + u;
+                        if (r2 < cutsq) {
+                            const float4 nj = __ldg(a.nl + j);
+                            F3 f, q1, q2;
+                            poly48(c_ff.cutlp[type1], c_ff.attlp[type1], c_ff.replp[type1], c_ff.alphalp[type1], d, r2, mi, {nj.x, nj.y, nj.z}, f, q1, q2);
+                            fx += f.x; fy += f.y; fz += f.z; tx -= q1.x; ty -= q1.y; tz -= q1.z;
+                            atomic_add3(a.fl + j, -f.x, -f.y, -f.z); atomic_add3(a.tl + j, -q2.x, -q2.y, -q2.z);
+                        } else if (r2 < ljcut) {
+                            const F3 f = lj126(c_ff.lj_lj1[type1], c_ff.lj_lj2[type1], d, r2);
+                            fx += f.x; fy += f.y; fz += f.z;
+                            atomic_add3(a.fl + j, -f.x, -f.y, -f.z);
+                        }
+                    }
+                }
+                if (rem > 0) cur += 4;
+                rem -= 4;
+            }
+        }
+        // ---- protein-protein, one-sided (compute_pairwise_fused.h:182-236, 262-276) ----------------------------------------------------
+        {
+            int taken = 0, cur = 0, rem = 0;
+            for (;;) {
+                if (rem <= 0 && taken < np_) { cur = pjb[taken * 32]; rem = plen[taken * 32]; ++taken; }
+                if (!__any_sync(0xffffffffu, rem > 0 || taken < np_)) break;
+                const float4 *__restrict__ p = a.xp + cur;
+                float4 xj4[2];
+                #pragma unroll
+                for (int u = 0; u < 2; ++u) xj4[u] = __ldg(p + u);
+                #pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const float4 xj = xj4[u];
+                    const F3 d = {xi.x - xj.x, xi.y - xj.y, xi.z - xj.z};
+                    const float r2 = dot3(d, d);
+                    if (u < rem && r2 > 1e-5f && r2 < cull_p * cull_p) {
+                        const int type12 = type1 + __float_as_int(xj.w) * kNType;
+                        if (r2 < s_cutsqpp[type12]) {
+                            const F3 f = rep8(c_ff.cutpp[type12], c_ff.reppp[type12], d, r2);
+                            fx += f.x; fy += f.y; fz += f.z;
+                        } else if (r2 < s_ljcutsq[type12]) {
+                            const F3 f = lj126(c_ff.lj_lj1[type12], c_ff.lj_lj2[type12], d, r2);
+                            fx += f.x; fy += f.y; fz += f.z;
+                        }
+                    }
+                }
+                if (rem > 0) cur += 2;
+                rem -= 2;
+            }
+        }
+    }
+    if (live) {
+        float4 f = a.fp[i], t = a.tp[i];
+        f.x += fx; f.y += fy; f.z += fz; t.x += tx; t.y += ty; t.z += tz;
+        a.fp[i] = f; a.tp[i] = t;
+    }
+}
+
+} // namespace orbc

@@ -28,7 +28,7 @@ EXPORTS = [
     "orbc_cell_update", "orbc_rebuild", "orbc_delete_lipid", "orbc_compute_pairwise_fused", "orbc_compute_bonded",
     "orbc_constrain_volume", "orbc_integrate", "orbc_nh_zeta_update", "orbc_compute_temperature", "orbc_run_langevin",
     "orbc_run_nh", "orbc_download", "orbc_size", "orbc_n_cells", "orbc_debug_dump", "orbc_debug_noise", "orbc_event_record",
-    "orbc_event_elapsed_ms", "orbc_launch_count", "orbc_profile_enable", "orbc_profile_read",
+    "orbc_event_elapsed_ms", "orbc_launch_count", "orbc_profile_enable", "orbc_profile_read", "orbc_set_option",
 ]
 
 
@@ -102,6 +102,7 @@ def load_library():
         lib.orbc_event_record.argtypes = [C.c_void_p, C.c_int]
         lib.orbc_event_elapsed_ms.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         lib.orbc_launch_count.argtypes = [C.c_void_p, C.c_void_p]
+        lib.orbc_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
         lib.orbc_profile_enable.argtypes = [C.c_void_p, C.c_int]
         lib.orbc_profile_read.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         lib.orbc_set_stream.argtypes = [C.c_void_p, C.c_void_p]
@@ -261,6 +262,9 @@ class Simulation:
         out = np.empty((n, 3), np.float32)
         self._ck(self.lib.orbc_debug_noise(self.ctx, self.seed, nstep, species, n, _p(out)))
         return out
+
+    def set_option(self, name, value):
+        self._ck(self.lib.orbc_set_option(self.ctx, name.encode(), float(value)))
 
     def synchronize(self):
         self._ck(self.lib.orbc_synchronize(self.ctx))
