@@ -85,6 +85,8 @@ struct orbc_ctx {
     bool stencil_valid = false;
     float4 *cell_normal = nullptr;                // constrain_volume's persistent scratch
     float4 *lbound = nullptr, *pbound = nullptr;  // per-cell bounding spheres of the current lipids / proteins (pair_queue.cuh)
+    int *porder = nullptr; size_t porder_cap = 0;  // thread -> protein map of the protein pair kernel (heavy types first)
+    bool porder_valid = false;
     unsigned type_mask = 0;                       // protein types present (bit t), from the last protein upload
     // bonds
     size_t n_bonds = 0;

@@ -168,6 +168,35 @@ void langevin_coeffs(IntegArgs &a, const orbc_step_params *p) {
     }
 }
 
+// largest interaction range of every protein type against lipids and against the protein types present
+CullTable cull_table(const orbc_ctx *c) {
+    CullTable ct;
+    for (int t = 0; t < kNType; ++t) {
+        ct.cut_l[t] = std::sqrt(std::max(g_host_ff.cutsqlp[t], g_host_ff.lj_cutsq[t]));
+        float m = 0.f;
+        for (int u = 0; u < kNType; ++u) if (c->type_mask >> u & 1) m = std::max(m, std::max(g_host_ff.cutsqpp[t + kNType * u], g_host_ff.lj_cutsq[t + kNType * u]));
+        ct.cut_p[t] = std::sqrt(m);
+    }
+    return ct;
+}
+
+// thread -> protein map of k_pair_prot (heavy types first); rebuilt whenever the protein storage order changes
+int build_porder(orbc_ctx *c) {
+    Species &P = c->sp[1];
+    if (!P.n) return ORBC_OK;
+    if (c->porder_cap < P.n + 1) { ORBC_TRY(dev_alloc(&c->porder, P.n + 1)); c->porder_cap = P.n + 1; }
+    const CullTable ct = cull_table(c);
+    float lo = 1e30f, hi = 0.f;                                   // heavy = upper half of the ranges present
+    for (int t = 0; t < kNType; ++t) if (c->type_mask >> t & 1) { lo = std::min(lo, ct.cut_l[t]); hi = std::max(hi, ct.cut_l[t]); }
+    const float heavy_cut = hi > 1.5f * lo ? 0.5f * (lo + hi) : 2.f * hi + 1.f;   // homogeneous ranges: nobody is heavy
+    int *flag = P.li;                                             // free between cell updates (n + 1 ints)
+    ORBC_LAUNCH(c, k_porder_flag, blocks_for(P.n, kBlock), kBlock, 0, P.X(), P.n, ct, heavy_cut, flag);
+    ORBC_TRY(scan_exclusive(c, flag, (int)P.n));
+    ORBC_LAUNCH(c, k_porder_scatter, blocks_for(P.n, kBlock), kBlock, 0, flag, P.n, P.X(), ct, heavy_cut, c->porder);
+    c->porder_valid = true;
+    return ORBC_OK;
+}
+
 int launch_pairwise(orbc_ctx *c) {
     Species &L = c->sp[0], &P = c->sp[1];
     if (!c->n_cells || !L.has_partition) return fail(ORBC_ERR_ARG, "compute_pairwise_fused: no Voronoi partition (call orbc_voronoi_upload / orbc_rebuild first)");
@@ -188,16 +217,10 @@ int launch_pairwise(orbc_ctx *c) {
         if (L.n) ORBC_LAUNCH(c, k_pair_ll<true>, blocks_for(L.n, kLLBlock), kLLBlock, 0, a);
     }
     if (P.n) {
-        // largest interaction range of every protein type against lipids and against the protein types present
-        CullTable ct;
-        for (int t = 0; t < kNType; ++t) {
-            ct.cut_l[t] = std::sqrt(std::max(g_host_ff.cutsqlp[t], g_host_ff.lj_cutsq[t]));
-            float m = 0.f;
-            for (int u = 0; u < kNType; ++u) if (c->type_mask >> u & 1) m = std::max(m, std::max(g_host_ff.cutsqpp[t + kNType * u], g_host_ff.lj_cutsq[t + kNType * u]));
-            ct.cut_p[t] = std::sqrt(m);
-        }
+        const CullTable ct = cull_table(c);
+        if (!c->porder_valid) ORBC_TRY(build_porder(c));
         ProfScope ps(c, ORBC_PROF_PAIR_PROTEIN);
-        ORBC_LAUNCH(c, k_pair_prot, blocks_for(P.n, kPBlock), kPBlock, 0, a, c->lbound, c->pbound, ct);
+        ORBC_LAUNCH(c, k_pair_prot, blocks_for(P.n, kPBlock), kPBlock, 0, a, c->lbound, c->pbound, ct, c->porder);
     }
     return ORBC_OK;
 }
@@ -255,7 +278,7 @@ int do_cell_update(orbc_ctx *c, int sp) {
         S.cur = nx;
     }
     S.has_partition = true;
-    if (sp == ORBC_PROTEIN) ORBC_TRY(build_tag2idx(c));
+    if (sp == ORBC_PROTEIN) { ORBC_TRY(build_tag2idx(c)); c->porder_valid = false; }
     return ORBC_OK;
 }
 
@@ -324,6 +347,7 @@ int orbc_set_forcefield(orbc_ctx *c, const orbc_forcefield *ff) {
     ORBC_CUDA(cudaStreamSynchronize(c->stream));
     g_host_ff = *ff;
     c->ff_set = true;
+    c->porder_valid = false;
     return ORBC_OK;
 }
 
@@ -355,7 +379,7 @@ void orbc_destroy(orbc_ctx *c) {
     free_species(c->sp[0]); free_species(c->sp[1]);
     dev_free(c->centroid); dev_free(c->centroid_tmp); dev_free(c->keys); dev_free(c->keys_tmp); dev_free(c->perm); dev_free(c->perm_tmp); dev_free(c->inv);
     dev_free(c->grid.bin_start); dev_free(c->grid.bin_items); dev_free(c->grid.bin_of); dev_free(c->grid.bin_slot);
-    dev_free(c->stencil); dev_free(c->stencil_cnt); dev_free(c->cell_normal); dev_free(c->lbound); dev_free(c->pbound); dev_free(c->bonds); dev_free(c->tag2idx);
+    dev_free(c->stencil); dev_free(c->stencil_cnt); dev_free(c->cell_normal); dev_free(c->lbound); dev_free(c->pbound); dev_free(c->porder); dev_free(c->bonds); dev_free(c->tag2idx);
     dev_free(c->scan_tmp); dev_free(c->radix_hist); dev_free(c->stage); dev_free(c->d_acc); dev_free(c->d_counters); dev_free(c->d_flags); dev_free(c->d_nh);
     dev_free(c->noise[0]); dev_free(c->noise[1]);
     if (c->h_acc) cudaFreeHost(c->h_acc); if (c->h_flags) cudaFreeHost(c->h_flags); if (c->h_counters) cudaFreeHost(c->h_counters); if (c->h_nh) cudaFreeHost(c->h_nh);
@@ -402,6 +426,7 @@ int orbc_upload(orbc_ctx *c, int sp, size_t n, size_t stride, const float *x, co
     ORBC_LAUNCH(c, k_fill_int, nb, kBlock, 0, S.C(), n, -1);
     ORBC_CUDA(cudaStreamSynchronize(c->stream));   // host arrays are borrowed only for the duration of the call
     if (sp == ORBC_PROTEIN) {
+        c->porder_valid = false;
         c->type_mask = 0;
         for (size_t i = 0; i < n; ++i) {
             const int t = type ? type[i] : 0;

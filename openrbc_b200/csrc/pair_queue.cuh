@@ -23,7 +23,7 @@
 namespace orbc {
 
 constexpr int kQCap = 32;          // queue slots per lane
-constexpr int kLLBlock = 128;
+constexpr int kLLBlock = 64;
 constexpr float kCullEps = 4e-3f;  // slack of the bounding-sphere test (absolute, length units)
 
 struct CullTable {                 // per protein type: largest interaction range against lipids / against the protein types present
@@ -184,17 +184,38 @@ __global__ void __launch_bounds__(kLLBlock) k_pair_ll(PairArgs a) {
 
 // ---- proteins -------------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void atomic_add3(float4 *dst, float x, float y, float z) {
-    atomicAdd(&dst->x, x); atomicAdd(&dst->y, y); atomicAdd(&dst->z, z);
+    atomicAdd(dst, make_float4(x, y, z, 0.f));                   // one 16-byte RED (REDG.ADD.F32x4); .w of f and t is unused
 }
 
-constexpr int kPBlock = 128;
-constexpr int kRangeCap = 16;      // stencil slots handled per round
+// Thread -> protein map of k_pair_prot: proteins whose type reaches far into the bilayer (band-3, glycophorin: 2.6) first,
+// the LJ-core-only types (actin, spectrin: 1.1225) after them, each class in storage order.  The work of a protein thread
+// scales with the square of its interaction range, and a warp is as slow as its slowest lane, so mixed warps would run at
+// the pace of the two or three heavy proteins in them.  Built after every protein reorder: flag -> scan -> scatter.
+__global__ void k_porder_flag(const float4 *__restrict__ xp, size_t n, CullTable ct, float heavy_cut, int *__restrict__ flag) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int t = __float_as_int(xp[i].w);
+    flag[i] = (t >= 0 && t < kNType && ct.cut_l[t] >= heavy_cut) ? 1 : 0;
+}
+__global__ void k_porder_scatter(const int *__restrict__ scan /* exclusive, scan[n] = n_heavy */, size_t n, const float4 *__restrict__ xp, CullTable ct, float heavy_cut,
+                                 int *__restrict__ porder) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int t = __float_as_int(xp[i].w);
+    const bool heavy = t >= 0 && t < kNType && ct.cut_l[t] >= heavy_cut;
+    const int before = scan[i];                                   // heavy proteins with a lower index
+    porder[heavy ? before : scan[n] + ((int)i - before)] = (int)i;
+}
+
+constexpr int kPBlock = 64;
+constexpr int kRangeCap = 8;       // stencil slots handled per round
 
 // One thread per protein.  Phase 0 culls the member lists of the stencil cells against the bounding spheres and COMPACTS the
 // survivors into per-lane range lists in shared memory (a lane-level `if (culled) skip` would save nothing on a SIMT machine;
 // the compaction is what turns skipped cells into skipped warp iterations).  Phase 1 walks the r-th surviving range of every
 // lane together, warp-uniform trip counts, predicated bodies.
-__global__ void __launch_bounds__(kPBlock) k_pair_prot(PairArgs a, const float4 *__restrict__ lbound, const float4 *__restrict__ pbound, CullTable ct) {
+__global__ void __launch_bounds__(kPBlock, 16) k_pair_prot(PairArgs a, const float4 *__restrict__ lbound, const float4 *__restrict__ pbound, CullTable ct,
+                                                             const int *__restrict__ porder) {
     __shared__ float s_cutsqpp[36], s_ljcutsq[36];
     __shared__ int s_jb[2][kPBlock / 32][kRangeCap * 32];
     __shared__ unsigned short s_len[2][kPBlock / 32][kRangeCap * 32];
@@ -203,8 +224,9 @@ __global__ void __launch_bounds__(kPBlock) k_pair_prot(PairArgs a, const float4 
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     int *const ljb = s_jb[0][w] + lane, *const pjb = s_jb[1][w] + lane;
     unsigned short *const llen = s_len[0][w] + lane, *const plen = s_len[1][w] + lane;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = i < a.n_p;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = tid < a.n_p;
+    const int i = live ? porder[tid] : 0;
     F3 xi = {0, 0, 0}, mi = {0, 0, 0};
     int type1 = 0, n8 = 0, n9 = 0;
     const int *st = a.stencil;
@@ -307,7 +329,7 @@ __global__ void __launch_bounds__(kPBlock) k_pair_prot(PairArgs a, const float4 
             }
         }
     }
-    if (live) {
+    if (live) {                                                  // the thread owns protein i: plain read-modify-write
         float4 f = a.fp[i], t = a.tp[i];
         f.x += fx; f.y += fy; f.z += fz; t.x += tx; t.y += ty; t.z += tz;
         a.fp[i] = f; a.tp[i] = t;
