@@ -63,6 +63,7 @@ struct Grid {                // uniform grid over the centroids (replaces the k-
     int *bin_items = nullptr;   // n_cells
     int *bin_of = nullptr;      // n_cells
     int *bin_slot = nullptr;    // n_cells
+    float4 *sorted = nullptr;   // n_cells: centroids in bin order, id in .w
     size_t cap_bins = 0;
 };
 

@@ -85,7 +85,7 @@ GridDev grid_dev(const orbc_ctx *c) {
     g.lox = c->grid.lo[0]; g.loy = c->grid.lo[1]; g.loz = c->grid.lo[2];
     g.h = c->grid.h; g.inv_h = 1.0f / c->grid.h;
     g.dx = c->grid.dim[0]; g.dy = c->grid.dim[1]; g.dz = c->grid.dim[2];
-    g.bin_start = c->grid.bin_start; g.bin_items = c->grid.bin_items;
+    g.bin_start = c->grid.bin_start; g.bin_items = c->grid.bin_items; g.sorted = c->grid.sorted;
     return g;
 }
 
@@ -107,7 +107,7 @@ int build_index(orbc_ctx *c) {
     const GridDev gd = grid_dev(c);
     ORBC_LAUNCH(c, k_bin_count, blocks_for(nc, kBlock), kBlock, 0, c->centroid, nc, gd, g.bin_start, g.bin_of, g.bin_slot);
     ORBC_TRY(scan_exclusive(c, g.bin_start, g.nbins));
-    ORBC_LAUNCH(c, k_bin_fill, blocks_for(nc, kBlock), kBlock, 0, nc, g.bin_start, g.bin_of, g.bin_slot, g.bin_items);
+    ORBC_LAUNCH(c, k_bin_fill, blocks_for(nc, kBlock), kBlock, 0, nc, g.bin_start, g.bin_of, g.bin_slot, g.bin_items, c->centroid, g.sorted);
     ORBC_LAUNCH(c, k_stencil_build, blocks_for(nc, kStencilWarps), kStencilWarps * 32, 0, c->centroid, nc, gd, c->stencil, c->stencil_cnt, c->d_flags);
     c->stencil_valid = true;
     return ORBC_OK;
@@ -271,9 +271,8 @@ int do_cell_update(orbc_ctx *c, int sp) {
     ORBC_TRY(scan_exclusive(c, S.cell_start, nc));
     if (S.n) {
         ORBC_LAUNCH(c, k_cell_scatter, blocks_for(S.n, kBlock), kBlock, 0, S.aff, S.li, S.n, S.cell_start, S.cells_tmp);
-        ORBC_LAUNCH(c, k_cell_sort, blocks_for((size_t)nc * 32, kBlock), kBlock, 0, S.cell_start, nc, S.cells_tmp, S.cells);
         const int nx = S.cur ^ 1;
-        ORBC_LAUNCH(c, k_gather_reorder, blocks_for(S.n, kBlock), kBlock, 0, S.cells, S.aff, S.n, S.X(), S.N(), S.V(), S.O(),
+        ORBC_LAUNCH(c, k_rank_and_move, blocks_for(S.n, kBlock), kBlock, 0, S.aff, S.n, S.cell_start, S.cells_tmp, S.cells, S.X(), S.N(), S.V(), S.O(),
                     S.x[nx], S.nn[nx], S.v[nx], S.o[nx], S.cellid[nx]);
         S.cur = nx;
     }
@@ -378,7 +377,7 @@ void orbc_destroy(orbc_ctx *c) {
     cudaStreamSynchronize(c->stream);
     free_species(c->sp[0]); free_species(c->sp[1]);
     dev_free(c->centroid); dev_free(c->centroid_tmp); dev_free(c->keys); dev_free(c->keys_tmp); dev_free(c->perm); dev_free(c->perm_tmp); dev_free(c->inv);
-    dev_free(c->grid.bin_start); dev_free(c->grid.bin_items); dev_free(c->grid.bin_of); dev_free(c->grid.bin_slot);
+    dev_free(c->grid.bin_start); dev_free(c->grid.bin_items); dev_free(c->grid.bin_of); dev_free(c->grid.bin_slot); dev_free(c->grid.sorted);
     dev_free(c->stencil); dev_free(c->stencil_cnt); dev_free(c->cell_normal); dev_free(c->lbound); dev_free(c->pbound); dev_free(c->porder); dev_free(c->bonds); dev_free(c->tag2idx);
     dev_free(c->scan_tmp); dev_free(c->radix_hist); dev_free(c->stage); dev_free(c->d_acc); dev_free(c->d_counters); dev_free(c->d_flags); dev_free(c->d_nh);
     dev_free(c->noise[0]); dev_free(c->noise[1]);
@@ -464,7 +463,7 @@ int orbc_voronoi_upload(orbc_ctx *c, int nc, const float *centroids3, const int 
     if (nc != c->n_cells) {
         ORBC_TRY(dev_alloc(&c->centroid, nc)); ORBC_TRY(dev_alloc(&c->centroid_tmp, nc));
         ORBC_TRY(dev_alloc(&c->keys, nc)); ORBC_TRY(dev_alloc(&c->keys_tmp, nc)); ORBC_TRY(dev_alloc(&c->perm, nc)); ORBC_TRY(dev_alloc(&c->perm_tmp, nc)); ORBC_TRY(dev_alloc(&c->inv, nc));
-        ORBC_TRY(dev_alloc(&c->grid.bin_items, nc)); ORBC_TRY(dev_alloc(&c->grid.bin_of, nc)); ORBC_TRY(dev_alloc(&c->grid.bin_slot, nc));
+        ORBC_TRY(dev_alloc(&c->grid.bin_items, nc)); ORBC_TRY(dev_alloc(&c->grid.bin_of, nc)); ORBC_TRY(dev_alloc(&c->grid.bin_slot, nc)); ORBC_TRY(dev_alloc(&c->grid.sorted, nc));
         ORBC_TRY(dev_alloc(&c->stencil, (size_t)nc * kStencilStride)); ORBC_TRY(dev_alloc(&c->stencil_cnt, nc));
         ORBC_TRY(dev_alloc(&c->cell_normal, nc)); ORBC_TRY(dev_alloc(&c->lbound, nc)); ORBC_TRY(dev_alloc(&c->pbound, nc));
         for (int s = 0; s < 2; ++s) ORBC_TRY(dev_alloc(&c->sp[s].cell_start, (size_t)nc + 1));

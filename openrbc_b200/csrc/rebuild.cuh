@@ -19,6 +19,7 @@ struct GridDev {
     int dx, dy, dz;
     const int *bin_start;
     const int *bin_items;
+    const float4 *sorted;     // centroids in bin order: (x, y, z, cell id as int bits)
 };
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
@@ -97,11 +98,16 @@ __global__ void k_bin_count(const float4 *__restrict__ centroid, int n, GridDev 
     bin_of[i] = b;
     bin_slot[i] = atomicAdd(&bin_cnt[b], 1);
 }
-__global__ void k_bin_fill(int n, const int *__restrict__ bin_start, const int *__restrict__ bin_of, const int *__restrict__ bin_slot, int *__restrict__ bin_items) {
+__global__ void k_bin_fill(int n, const int *__restrict__ bin_start, const int *__restrict__ bin_of, const int *__restrict__ bin_slot, int *__restrict__ bin_items,
+                           const float4 *__restrict__ centroid, float4 *__restrict__ sorted) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int b = bin_of[i];
-    if (b >= 0) bin_items[bin_start[b] + bin_slot[i]] = i;
+    if (b < 0) return;
+    const int k = bin_start[b] + bin_slot[i];
+    bin_items[k] = i;
+    const float4 p = centroid[i];
+    sorted[k] = make_float4(p.x, p.y, p.z, __int_as_float(i));
 }
 
 // ---- per-cell centroid stencils: {c2 : |c2 - c1|^2 < 81}, classed by < 36 / < 64 / < 81, ordered (class, id) -------------
@@ -119,24 +125,39 @@ __global__ void __launch_bounds__(kStencilWarps * 32) k_stencil_build(const floa
     if (q.x == q.x && q.y == q.y && q.z == q.z) {
         int bx, by, bz; grid_bin(g, q, bx, by, bz);
         const int x0 = max(bx - 1, 0), x1 = min(bx + 1, g.dx - 1);
-        for (int zz = max(bz - 1, 0); zz <= min(bz + 1, g.dz - 1); ++zz)
-            for (int yy = max(by - 1, 0); yy <= min(by + 1, g.dy - 1); ++yy) {
+        // lanes 0..8 fetch the nine x-runs together, a warp scan turns them into one flat candidate list
+        int beg = 0, cnt = 0;
+        if (lane < 9) {
+            const int zz = bz - 1 + lane / 3, yy = by - 1 + lane % 3;
+            if (zz >= 0 && zz < g.dz && yy >= 0 && yy < g.dy) {
                 const int row = (zz * g.dy + yy) * g.dx;
-                const int beg = g.bin_start[row + x0], end = g.bin_start[row + x1 + 1];
-                for (int k0 = beg; k0 < end; k0 += 32) {
-                    const int k = k0 + lane;
-                    int key = -1;
-                    if (k < end) {
-                        const int j = g.bin_items[k];
-                        const float d2 = dist2_rn(centroid[j], q);     // normsq(pts_[i] - q), kdtree.h:274
-                        if (d2 < 81.0f) key = ((d2 < 36.0f ? 0 : (d2 < 64.0f ? 1 : 2)) << 28) | j;
-                    }
-                    const unsigned m = __ballot_sync(0xffffffffu, key >= 0);
-                    const int pos = count + __popc(m & ((1u << lane) - 1u));
-                    if (key >= 0 && pos < kStencilStride) s_key[w][pos] = key;
-                    count += __popc(m);
-                }
+                beg = g.bin_start[row + x0];
+                cnt = g.bin_start[row + x1 + 1] - beg;
             }
+        }
+        int incl = cnt;
+        #pragma unroll
+        for (int d = 1; d < 16; d <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += y; }
+        const int total = __shfl_sync(0xffffffffu, incl, 8);
+        int rb[9], re[9];                                         // run r covers flat slots [re[r] - cnt_r, re[r])
+        #pragma unroll
+        for (int r = 0; r < 9; ++r) { rb[r] = __shfl_sync(0xffffffffu, beg, r); re[r] = __shfl_sync(0xffffffffu, incl, r); }
+        for (int s0 = 0; s0 < total; s0 += 32) {
+            const int s = s0 + lane;
+            int key = -1;
+            if (s < total) {
+                int idx = rb[0] + s;
+                #pragma unroll
+                for (int r = 1; r < 9; ++r) if (s >= re[r - 1]) idx = rb[r] + (s - re[r - 1]);
+                const float4 p = g.sorted[idx];
+                const float d2 = dist2_rn(p, q);                  // normsq(pts_[i] - q), kdtree.h:274
+                if (d2 < 81.0f) key = ((d2 < 36.0f ? 0 : (d2 < 64.0f ? 1 : 2)) << 28) | __float_as_int(p.w);
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, key >= 0);
+            const int pos = count + __popc(m & ((1u << lane) - 1u));
+            if (key >= 0 && pos < kStencilStride) s_key[w][pos] = key;
+            count += __popc(m);
+        }
     }
     if (count > kStencilStride) { if (lane == 0) atomicExch(&flags[0], c + 1); count = kStencilStride; }
     __syncwarp();
@@ -197,16 +218,26 @@ __global__ void k_assign_nearest(const float4 *__restrict__ x, const int *__rest
     const int guess = cellid ? cellid[i] : -1;
     float best = INFINITY; int bi = -1; bool ok = false;
     if (guess >= 0 && guess < n_cells) {
-        const int n9 = stencil_cnt[guess] >> 16;
+        // candidates = the r<6 stencil of the previous cell; exact whenever d(best) + d(guess) < 6 (every centroid at least
+        // as close to the particle as `best` is then closer than 6 to the guess, i.e. inside that stencil).  Otherwise the
+        // same argument with the r<9 stencil, then the grid.
+        const int cnt = stencil_cnt[guess];
+        const int n6 = cnt & 255, n9 = cnt >> 16;
         const int *st = stencil + (size_t)guess * kStencilStride;
-        for (int k = 0; k < n9; ++k) {
+        for (int k = 0; k < n6; ++k) {
             const int j = st[k];
             const float d2 = dist2_rn(p, centroid[j]);
             if (d2 < best || (d2 == best && j < bi)) { best = d2; bi = j; }
         }
-        if (bi >= 0) {
-            const float dg = dist2_rn(p, centroid[guess]);
-            ok = sqrtf(best) + sqrtf(dg) < 9.0f - 1e-3f;
+        const float dg = sqrtf(dist2_rn(p, centroid[guess]));
+        if (bi >= 0) ok = sqrtf(best) + dg < 6.0f - 1e-3f;
+        if (!ok) {
+            for (int k = n6; k < n9; ++k) {
+                const int j = st[k];
+                const float d2 = dist2_rn(p, centroid[j]);
+                if (d2 < best || (d2 == best && j < bi)) { best = d2; bi = j; }
+            }
+            if (bi >= 0) ok = sqrtf(best) + dg < 9.0f - 1e-3f;
         }
     }
     if (!ok) {
@@ -236,6 +267,26 @@ __global__ void k_cell_sort(const int *__restrict__ cell_start, int n_cells, con
         for (int k = 0; k < m; ++k) rank += (cells_tmp[b + k] < v);
         cells[b + rank] = v;
     }
+}
+
+// The two steps above and the gather below in one pass, one thread per particle: the slot of particle i inside its new cell is
+// the number of members with a lower index (= arrival order of the reference at one thread, voronoi.h:214-215), found by
+// scanning the cell's arrival list (a few dozen L1-resident ints shared by neighbouring threads); the particle then moves
+// itself: new[cell_start + rank] = old[i]  (reorder.h:73-149 as a scatter instead of a gather; `cells` still records the
+// permutation, VCellList::cells).
+__global__ void k_rank_and_move(const int *__restrict__ aff, size_t n, const int *__restrict__ cell_start, const int *__restrict__ cells_tmp, int *__restrict__ cells,
+                                const float4 *__restrict__ x0, const float4 *__restrict__ n0, const float4 *__restrict__ v0, const float4 *__restrict__ o0,
+                                float4 *__restrict__ x1, float4 *__restrict__ n1, float4 *__restrict__ v1, float4 *__restrict__ o1, int *__restrict__ cellid1) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int c = aff[i];
+    const int b = cell_start[c], e = cell_start[c + 1];
+    int rank = 0;
+    for (int k = b; k < e; ++k) rank += (cells_tmp[k] < (int)i);
+    const int j = b + rank;
+    cells[j] = (int)i;
+    x1[j] = x0[i]; n1[j] = n0[i]; v1[j] = v0[i]; o1[j] = o0[i];
+    cellid1[j] = c;
 }
 
 // reorder.h:73-149: out-of-place gather of x, v, n, o (type and tag ride in x.w / n.w) + the particle's cell

@@ -3,7 +3,8 @@
 output of the previous stage, so integer structures can be required to be EQUAL and fp32 fields compared tightly.
 
 Tolerances: forces / torques 1e-4 * (|f_ref| + f_rms) per particle; integrator outputs 1e-6
-relative; kinetic energy / temperature 1e-6 relative (fp64 accumulation on both sides)."""
+relative (1e-5 for the torque cross product n x t, which cancels); kinetic energy / temperature 1e-6 relative (fp64
+accumulation on both sides)."""
 import os
 
 import numpy as np
@@ -14,7 +15,7 @@ from tests.common import GOLDEN, rel_err
 pytestmark = pytest.mark.gpu
 
 FILES = ["vesicle_ico0", "sphere_r12"]
-F_TOL, X_TOL = 1e-4, 1e-6
+F_TOL, X_TOL, T_TOL = 1e-4, 1e-6, 1e-5
 
 
 def load(name):
@@ -109,7 +110,9 @@ def test_nose_hoover_pair(name):
     for s, p in ((0, "l"), (1, "p")):
         d = sim.download(s, "vot")
         for f in "vot":
-            assert rel_err(d[f], g[f"nhf_{p}{f}"]) < X_TOL, (p, f)
+            # t = n x t is a difference of products: the device contracts it into FMAs, the strict reference build does not,
+            # so the cancellation leaves a few fp32 ulps of the operands rather than of the result
+            assert rel_err(d[f], g[f"nhf_{p}{f}"]) < (T_TOL if f == "t" else X_TOL), (p, f)
     # second kernel from the reference's own intermediate state
     for s, p in ((0, "l"), (1, "p")):
         for f in "vot":
