@@ -88,17 +88,22 @@ def workload_name(workload, st):
 # ---------------------------------------------------------------------------------------------------------------------
 # reference arm: the unmodified reference on the host cores
 # ---------------------------------------------------------------------------------------------------------------------
-def run_reference(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
+def host_threads():
+    """Host threads this process may use (cgroup / affinity aware)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def reference_child(args):
+    """One measurement of the unmodified reference at a fixed OpenMP thread count (its own process: the reference keeps
+    function-local statics sized by omp_get_max_threads()).  Prints the JSON line, then silences stdout so that the
+    reference's at-exit timer report (timer.h:55) cannot follow it."""
     from oracle import ref as refmod
-    if not refmod.available("fast"):
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libref_fast.so is not built (python __graft_entry__.py build where /root/reference exists)"}))
-        return
     st = load_state(args.workload)
     n = len(st["lx"]) + len(st["px"])
-    threads = args.threads or (os.cpu_count() or 1)
+    threads = args.threads
     r = refmod.Ref("fast", threads=threads, args=["-i", "lipid"])   # the state is loaded below; "lipid" only satisfies the CLI check
     r.load_state(st)
     r.set_param("kBT", 0.22)
@@ -121,26 +126,63 @@ def run_reference(args):
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+    sys.stdout.flush()
+    os.dup2(os.open(os.devnull, os.O_WRONLY), 1)
+
+
+def reference_line(args, steps, warmup, budget):
+    """Runs reference_child with all host threads; if that process dies (the reference was written for tens of threads, not
+    hundreds) the thread count is halved until a run completes.  Returns (json dict or None, list of attempts)."""
+    from oracle import ref as refmod
+    if not refmod.available("fast"):
+        return {"impl": "reference", "unavailable": "oracle/_ref/libref_fast.so is not built (python __graft_entry__.py build where /root/reference exists)"}, []
+    ensure_state(args.workload)
+    cand, t = [], args.threads or host_threads()
+    while t >= 1 and len(cand) < 6:
+        cand.append(t)
+        if args.threads:
+            break
+        t //= 2
+    attempts = []
+    for t in cand:
+        env = dict(os.environ)
+        env.setdefault("OMP_PROC_BIND", "close"); env.setdefault("OMP_PLACES", "cores")
+        for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
+            env.pop(k, None)
+        cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference-child", "--workload", args.workload, "--steps", str(steps),
+               "--warmup", str(warmup), "--ref-budget", str(budget), "--threads", str(t), "--gpus", str(args.gpus)]
+        try:
+            out = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=budget * 3 + 300)
+            for ln in reversed(out.stdout.strip().splitlines()):
+                if ln.startswith("{"):
+                    d = json.loads(ln)
+                    d["config"]["thread_attempts"] = attempts + [f"{t}: ok"]
+                    return d, attempts
+            attempts.append(f"{t}: exit {out.returncode} {out.stderr.strip().splitlines()[-1][:120] if out.stderr.strip() else ''}")
+        except Exception as e:  # noqa: BLE001
+            attempts.append(f"{t}: {type(e).__name__}")
+    return None, attempts
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    d, attempts = reference_line(args, args.steps, args.warmup, args.ref_budget)
+    if d is None:
+        d = {"impl": "reference", "unavailable": "the reference process failed at every thread count tried: " + "; ".join(attempts)}
+    print(json.dumps(d), flush=True)
 
 
 def cpu_baseline_subprocess(args):
     """Reference timed on this box's host cores in its own process (one OpenMP runtime, one thread count per process)."""
-    env = dict(os.environ, OMP_PROC_BIND="close", OMP_PLACES="cores")
-    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
-        env.pop(k, None)
-    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", args.workload, "--steps", str(args.cpu_steps),
-           "--warmup", "2", "--ref-budget", "40"]
-    try:
-        out = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=600)
-        for ln in reversed(out.stdout.strip().splitlines()):
-            if ln.startswith("{"):
-                d = json.loads(ln)
-                if "cpu_baseline" in d:
-                    return d["cpu_baseline"]
-                return {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": d.get("unavailable", "no output")}
-    except Exception as e:  # noqa: BLE001
-        return {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"failed: {e}"}
-    return {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "no output"}
+    d, attempts = reference_line(args, args.cpu_steps, 2, 40)
+    if d and "cpu_baseline" in d:
+        cb = d["cpu_baseline"]
+        cb["omp"] = d["config"]["omp_binding"]
+        return cb
+    why = d.get("unavailable") if d else "failed: " + "; ".join(attempts)
+    return {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": why}
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -358,7 +400,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=240)
     ap.add_argument("--warmup", type=int, default=24)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-child"])
     ap.add_argument("--workload", default="rbc")
     ap.add_argument("--threads", type=int, default=0, help="reference arm: OpenMP threads (0 = all host cores)")
     ap.add_argument("--ref-budget", type=float, default=150.0, help="reference arm: wall-clock bound in seconds")
@@ -366,9 +408,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
-        os.environ.setdefault("OMP_PROC_BIND", "close")
-        os.environ.setdefault("OMP_PLACES", "cores")
         run_reference(args)
+    elif args.impl == "reference-child":
+        reference_child(args)
     else:
         run_ours(args)
 
