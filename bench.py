@@ -251,6 +251,9 @@ def hbm_peak():
 
 def run_chunked(sim, n_steps):
     """n_steps of the main loop through the fused entry point, with delete_lipid at multiples of freq_cleanup (openrbc.cpp:201)."""
+    if sim.world > 1:                      # delete_lipid is not decomposed yet (DESIGN.md §multi-GPU): stated in config.multi_gpu
+        sim.run_langevin(n_steps)
+        return
     done = 0
     while done < n_steps:
         if sim.nstep % FREQ_CLEANUP == 0:
@@ -278,9 +281,17 @@ def run_ours(args):
     st = load_state(args.workload)
     n_total = len(st["lx"]) + len(st["px"])
 
+    def connect(s):
+        """Exchange the ranks' connection blobs (CUDA IPC handles) once; the data path never touches torch.distributed again."""
+        blobs = [None] * world
+        dist.all_gather_object(blobs, s.mg_export())
+        s.mg_connect(blobs)
+
     def make_sim(state):
-        s = orbc.Simulation(state, kBT=0.22, device=local)
+        s = orbc.Simulation(state, kBT=0.22, device=local, rank=rank, world=world)
         s.stray_tolerance = 2.5
+        if world > 1:
+            connect(s)
         return s
 
     def barrier():
@@ -310,10 +321,13 @@ def run_ours(args):
         t = torch.tensor([ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    # N>1: independent replicas of the whole cell, one per GPU (spatial decomposition of one cell: see DESIGN.md §multi-GPU)
-    value = world * n_total * args.steps / (ms * 1e-3)
+    # N>1: ONE cell decomposed over the ranks (strong scaling): the job is still n_total particles x steps
+    value = n_total * args.steps / (ms * 1e-3)
     temperature = sim.compute_temperature()
-    sim.close()
+    if world > 1:
+        t = torch.tensor([temperature, float(n_now)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t)                                       # every rank returns its additive share of sum(m v^2) / 3N
+        temperature = float(t[0].item()); n_now = n_total
 
     # ---- end-to-end leg: host buffers through the per-call C ABI ---------------------------------------------------------
     pinned = {}
@@ -325,10 +339,13 @@ def run_ours(args):
     host.update({k: v.numpy() for k, v in pinned.items()})
     out_l = {f: torch.empty((len(st["lx"]), 3), dtype=torch.float32, pin_memory=True) for f in "xn"}
     out_p = {f: torch.empty((len(st["px"]), 3), dtype=torch.float32, pin_memory=True) for f in "xn"}
-    e2e_sim = orbc.Simulation(None, kBT=0.22, device=local)
-    e2e_sim.stray_tolerance = 2.5
-    # warm-up of the e2e path (allocations, first-touch): one upload + W steps, then the timed job starts from a fresh upload
+    # the e2e job re-uses the context (device allocations and, on N>1, the peer mappings are set-up, not per-job work)
+    e2e_sim = sim
+    barrier()
     e2e_sim.upload(host)
+    if world > 1:
+        e2e_sim.mg_export()
+    e2e_sim.nstep = 0
     for _ in range(min(args.warmup, 4)):
         e2e_sim.step_langevin_checked()
     e2e_sim.nstep = 0
@@ -336,10 +353,12 @@ def run_ours(args):
     e2e_sim.event_record(2)
     t_wall = time.perf_counter()
     e2e_sim.upload(host)
+    if world > 1:
+        e2e_sim.mg_export()              # owned ranges + halo masks of the fresh state (device work, no new allocations)
     h2d = sum(host[k].nbytes for k in ("lx", "lv", "ln", "lo", "px", "pv", "pn", "po", "ptype", "ptag", "bonds", "centroids", "cs_l", "cs_p"))
     d2h = 0
     for _ in range(args.steps):
-        if e2e_sim.nstep % FREQ_CLEANUP == 0:
+        if world == 1 and e2e_sim.nstep % FREQ_CLEANUP == 0:
             e2e_sim.delete_lipid(e2e_sim.stray_tolerance); d2h += 8
         e2e_sim.step_langevin_checked(); d2h += 16
         if e2e_sim.nstep % FREQ_DISPLAY == 0:
@@ -356,7 +375,8 @@ def run_ours(args):
         t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item())
-    e2e_value = world * n_total * args.steps / (e2e_ms * 1e-3)
+    e2e_value = n_total * args.steps / (e2e_ms * 1e-3)
+    barrier()
     e2e_sim.close()
 
     if rank != 0:
@@ -366,15 +386,16 @@ def run_ours(args):
 
     peak, peak_src = hbm_peak()
     pl_ms, pl_cnt = prof["pair_lipid"]
-    n_l = len(st["lx"])
+    n_l = len(st["lx"]) / world          # lipids one launch of the kernel covers (this rank's share on N>1)
     achieved = (B_ALG_PAIR * n_l / (pl_ms / pl_cnt * 1e-3) / 1e9) if pl_cnt else None
     shares = {k: round(v[0] / ms, 4) for k, v in prof.items()}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak" if world > 1 else "strong", "vs_baseline": None,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args.workload, st), "l2": "inputs larger than L2 (state %.0f MB resident in HBM, no flush needed)" % (n_total * 6 * 16 / 1e6),
-                   "multi_gpu": "single GPU" if world == 1 else f"{world} independent replicas of the whole cell (no data-path collective)",
+                   "multi_gpu": "single GPU" if world == 1 else (f"one cell decomposed over {world} ranks: contiguous ranges of Morton-ordered Voronoi cells, halo push + migration "
+                                                                "by peer stores over NVLink, epoch-flag barriers; delete_lipid (every 60 steps on 1 GPU) not run"),
                    "integrator": "verlet_langevin kBT=0.22 dt=0.01, rebuild every 2 steps, Morton sort every 24, cleanup every 60",
                    "particles_at_end": n_now, "temperature_at_end": temperature,
                    "hbm_roofline_frac_step": value / world * B_ALG_STEP / 1e9 / peak, "device_time_shares": shares},

@@ -142,6 +142,24 @@ ORBC_API int  orbc_run_langevin(orbc_ctx *ctx, const orbc_step_params *p, int n_
 /* same for the Nose-Hoover build (openrbc.cpp:192-241); zeta/Q are updated on the device and returned */
 ORBC_API int  orbc_run_nh(orbc_ctx *ctx, const orbc_step_params *p, int n_steps, int freq_voronoi, int freq_sort_ctrd, float *zeta_inout, float *Q_inout);
 
+/* ---- one cell over the GPUs of a box (no counterpart in the reference, which is one shared-memory process; the model is
+ * its own thread decomposition: contiguous ranges of Morton-ordered cells per worker, util_numa.h:41-42, cross-range cell
+ * pairs evaluated one-sidedly by both owners, compute_pairwise_fused.h:264-275,287-295,303-314) -------------------------------
+ * Call order on every rank (one process per GPU, or several contexts in one process): orbc_create, orbc_mg_init,
+ * orbc_upload / orbc_upload_bonds / orbc_voronoi_upload with the WHOLE system, orbc_mg_export, exchange the blobs
+ * (any transport: torch.distributed, MPI, a file), orbc_mg_connect with all of them in rank order.  After that
+ * orbc_rebuild / orbc_compute_pairwise_fused / orbc_compute_bonded / orbc_integrate(VERLET_LANGEVIN) / orbc_run_langevin work on
+ * the rank's own cells; halo copies, particle migration and the synchronisation between ranks happen on the device over
+ * NVLink (peer stores and epoch flags), with no host synchronisation and no collective library on the data path.
+ * Every rank must issue the same sequence of calls. */
+ORBC_API int  orbc_mg_init(orbc_ctx *ctx, int rank, int world /* <= 8 */);
+ORBC_API size_t orbc_mg_blob_bytes(void);
+ORBC_API int  orbc_mg_export(orbc_ctx *ctx, void *blob_out, size_t bytes);
+ORBC_API int  orbc_mg_connect(orbc_ctx *ctx, const void *blobs /* world x bytes_each, rank order */, size_t bytes_each);
+/* particle slots [begin, end) of one container this rank owns right now (synchronises); orbc_download returns whole
+ * containers of which only these slots (and the halo) are current */
+ORBC_API int  orbc_mg_range(orbc_ctx *ctx, int species, size_t *begin, size_t *end);
+
 /* ---- download: what save_frame()/display() need (trajectory.h:61-105, openrbc.cpp:248-254) ------------------------ */
 /* any destination may be NULL.  affiliation = VCellList::update_particle_affiliation (voronoi.h:166-175). */
 ORBC_API int  orbc_download(orbc_ctx *ctx, int species, size_t stride_floats,

@@ -26,6 +26,7 @@ inline int fail(int code, const char *fmt, ...) {
 constexpr int kNType = 6;              // forcefield_canonical.h:37
 constexpr int kStencilStride = ORBC_STENCIL_STRIDE;
 constexpr float kBin = 9.0f;           // centroid grid bin = largest centroid stencil radius (compute_pairwise_fused.h:183)
+constexpr int kMaxWorld = 8;           // ranks of one spatially decomposed run (one B200 box)
 
 // device image of the force field + derived Langevin coefficients, in __constant__ memory
 struct DevForceField {
@@ -65,6 +66,39 @@ struct Grid {                // uniform grid over the centroids (replaces the k-
     int *bin_slot = nullptr;    // n_cells
     float4 *sorted = nullptr;   // n_cells: centroids in bin order, id in .w
     size_t cap_bins = 0;
+};
+
+// ---- spatial decomposition over the GPUs of one box (multi.cuh) -----------------------------------------------------------
+// Every rank keeps the containers in the SAME global index space (particles sorted by Voronoi cell, cells in Morton order)
+// and owns a contiguous range of cells [cb, ce) together with the particle slots of those cells; only the owned slots and
+// the halo (members of cells inside the r<9 centroid stencil of an owned cell, and bonded partners) are kept up to date.
+// Peers write into each other's arrays directly over NVLink (peer-mapped pointers); PeerTable holds those pointers.
+struct PeerTable {
+    float4 *x[2][2][kMaxWorld], *nn[2][2][kMaxWorld], *v[2][2][kMaxWorld], *o[2][2][kMaxWorld];   // [species][buffer][rank]
+    int *cellid[2][2][kMaxWorld];
+    float4 *centroid[2][kMaxWorld];       // [parity][rank]
+    int *cnt_all[2][kMaxWorld];           // [species][rank]: world x (n_cells + 1) arrival counts
+    int *tag2idx[kMaxWorld];
+    unsigned *flags[kMaxWorld];           // barrier epochs, one slot per writer
+};
+struct Decomp {
+    bool on = false, connected = false;
+    int rank = 0, world = 1;
+    int cb = 0, ce = 0;                   // owned cells
+    size_t own_cap[2] = {0, 0};           // launch bound of the owned-particle kernels
+    unsigned epoch = 0;                   // barriers issued so far
+    int need_epoch = 0;                   // rebuild counter marking owned + halo cells in `need`
+    int cen_par = 0;                      // which of the two centroid buffers is current (they swap on rebuilds)
+    float4 *cen_buf[2] = {nullptr, nullptr};
+    unsigned *flags = nullptr;            // kMaxWorld epochs written by the peers
+    int *cnt_all[2] = {nullptr, nullptr}; // world rows of arrival counts per species (row r written by rank r)
+    int *off_me[2] = {nullptr, nullptr};  // members of each cell that come from lower ranks
+    int *local_start[2] = {nullptr, nullptr};
+    unsigned char *dest_mask = nullptr;   // per cell: ranks (other than the owner) that own a cell of its r<9 stencil
+    unsigned char *pmask = nullptr;       // per protein slot: ranks that own a bonded partner
+    int *need = nullptr;                  // per cell: == need_epoch for owned and halo cells
+    PeerTable peers;
+    std::vector<void *> opened;           // IPC mappings to close
 };
 
 } // namespace orbc
@@ -107,6 +141,8 @@ struct orbc_ctx {
     unsigned long long launches = 0;
     bool ff_set = false;
     int pair_impl = 2;
+    int *d_range = nullptr;                               // {l0, l1, p0, p1}: particle slots this context computes (all of them on one GPU)
+    orbc::Decomp mg;
     // per-class event-pair profiling (orbc_profile_*)
     bool prof_on = false;
     std::vector<cudaEvent_t> prof_ev[ORBC_PROF_N];   // even = start, odd = stop

@@ -38,9 +38,20 @@ __global__ void k_noise(uint64_t seed, uint32_t step, uint32_t species, size_t n
     out[3 * i] = r.x; out[3 * i + 1] = r.y; out[3 * i + 2] = r.z;
 }
 
+// Halo push of a decomposed run, fused into the integrator: the new position and director of an owned particle are also
+// stored straight into the arrays of the ranks that read it as halo (same global slot, peer memory over NVLink).
+struct PushArgs {
+    const unsigned char *cell_mask;        // per cell: ranks owning a member of its r<9 stencil (rebuild.cuh HaloOut)
+    const unsigned char *pmask;            // per protein slot: ranks owning a bonded partner (null for lipids)
+    const int *cellid;
+    float4 *x[kMaxWorld], *nn[kMaxWorld];
+    int world;
+};
 struct IntegArgs {
     float4 *x, *v, *f, *nn, *o, *t;
     size_t n;
+    const int *range;                      // {begin, end} slots to integrate (verlet_langevin)
+    PushArgs push;
     int species;
     float dt;
     float gamma[kNType], sigma[kNType];   // Langevin: 6 pi eta R, sqrt(2 kBT gamma) sqrt(3/dt)   (integrate_langevin.h:110-114)
@@ -107,8 +118,8 @@ __global__ void k_bounce_back(IntegArgs a) {
 
 // integrate_langevin.h:99-149 — one pass: torque -> omega -> director, noise, friction, kick, drift, clear f and t
 __global__ void __launch_bounds__(256) k_verlet_langevin(IntegArgs a) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.n) return;
+    const size_t i = (size_t)a.range[0] + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)a.range[1]) return;
     float4 x = a.x[i], v = a.v[i], n4 = a.nn[i], o = a.o[i];
     const float4 f = a.f[i], t = a.t[i];
     const int type = __float_as_int(x.w);
@@ -124,8 +135,17 @@ __global__ void __launch_bounds__(256) k_verlet_langevin(IntegArgs a) {
     v.x += fx * k; v.y += fy * k; v.z += fz * k;
     x.x += v.x * a.dt; x.y += v.y * a.dt; x.z += v.z * a.dt;
     a.x[i] = x; a.v[i] = v; a.o[i] = o;
-    a.nn[i] = make_float4(nn.x, nn.y, nn.z, n4.w);
+    const float4 nnew = make_float4(nn.x, nn.y, nn.z, n4.w);
+    a.nn[i] = nnew;
     a.f[i] = make_float4(0, 0, 0, 0); a.t[i] = make_float4(0, 0, 0, 0);
+    if (a.push.world > 1) {
+        unsigned m = a.push.cell_mask[a.push.cellid[i]];
+        if (a.push.pmask) m |= a.push.pmask[i];
+        while (m) {
+            const int r = __ffs(m) - 1; m &= m - 1;
+            a.push.x[r][i] = x; a.push.nn[r][i] = nnew;
+        }
+    }
 }
 
 // integrate_nh.h:178-235 (operator()) — half kick with 1/(1 + dt zeta / 2), drift, bounce-back, KE, omega half kick, director, clear
@@ -188,10 +208,10 @@ __global__ void k_nh_final(IntegArgs a) {
 }
 
 // integrate_nh.h:69-94 (KE only) and compute_temperature.h:23-29 (sum m v^2): acc[0] += scale * m |v|^2
-__global__ void __launch_bounds__(256) k_kinetic(const float4 *__restrict__ x, const float4 *__restrict__ v, size_t n, float scale, double *acc) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) k_kinetic(const float4 *__restrict__ x, const float4 *__restrict__ v, const int *__restrict__ range, float scale, double *acc) {
+    const size_t i = (size_t)range[0] + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     double e = 0.0;
-    if (i < n) {
+    if (i < (size_t)range[1]) {
         const float4 vv = v[i];
         e = scale * c_ff.mass[__float_as_int(x[i].w)] * (vv.x * vv.x + vv.y * vv.y + vv.z * vv.z);
     }

@@ -11,6 +11,7 @@
 #include "pair.cuh"
 #include "pair_queue.cuh"
 #include "integrate.cuh"
+#include "multi.cuh"
 
 using namespace orbc;
 
@@ -70,7 +71,8 @@ int alloc_species(orbc_ctx *c, Species &s, size_t n) {
         s.cap = cap;
     }
     s.n = n; s.cur = 0; s.has_partition = false;
-    (void)c;
+    const int sp = (int)(&s - c->sp);
+    ORBC_LAUNCH(c, k_set_range_const, 1, 1, 0, c->d_range + 2 * sp, 0, (int)n);   // a single GPU computes every slot
     return ORBC_OK;
 }
 
@@ -96,11 +98,13 @@ int check_flags(orbc_ctx *c) {
     if (c->h_flags[0]) return fail(ORBC_ERR_STATE, "centroid stencil of cell %d holds more than %d cells", c->h_flags[0] - 1, kStencilStride);
     if (c->h_flags[1]) return fail(ORBC_ERR_STATE, "particle %d has no nearest centroid (NaN position?)", c->h_flags[1] - 1);
     if (c->h_flags[2]) return fail(ORBC_ERR_STATE, "protein %d carries a tag outside the tag->index map", c->h_flags[2] - 1);
+    if (c->h_flags[3] > 0) return fail(ORBC_ERR_STATE, "decomposed run: rank %d never reached a barrier (rank %d waited 20 s)", c->h_flags[3] - 1, c->mg.rank);
+    if (c->h_flags[3] < 0) return fail(ORBC_ERR_STATE, "decomposed run: rank %d now owns %d particles of one container, more than its launch bound", c->mg.rank, -c->h_flags[3]);
     return ORBC_OK;
 }
 
 // grid + stencils from the current centroids (the part of VoronoiDiagram::update that replaces tree.build, voronoi.h:83)
-int build_index(orbc_ctx *c) {
+int build_index(orbc_ctx *c, bool all_cells = true) {
     const int nc = c->n_cells;
     Grid &g = c->grid;
     ORBC_CUDA(cudaMemsetAsync(g.bin_start, 0, sizeof(int) * ((size_t)g.nbins + 1), c->stream));
@@ -108,7 +112,14 @@ int build_index(orbc_ctx *c) {
     ORBC_LAUNCH(c, k_bin_count, blocks_for(nc, kBlock), kBlock, 0, c->centroid, nc, gd, g.bin_start, g.bin_of, g.bin_slot);
     ORBC_TRY(scan_exclusive(c, g.bin_start, g.nbins));
     ORBC_LAUNCH(c, k_bin_fill, blocks_for(nc, kBlock), kBlock, 0, nc, g.bin_start, g.bin_of, g.bin_slot, g.bin_items, c->centroid, g.sorted);
-    ORBC_LAUNCH(c, k_stencil_build, blocks_for(nc, kStencilWarps), kStencilWarps * 32, 0, c->centroid, nc, gd, c->stencil, c->stencil_cnt, c->d_flags);
+    // decomposed run: only the owned cells' stencils are read (pair kernels, and the nearest-centroid search starts from the
+    // particle's previous cell, which its owner owns) — except right after a Morton renumbering of the cells
+    HaloOut halo;
+    halo.dest_mask = c->mg.dest_mask; halo.need = c->mg.need; halo.need_epoch = ++c->mg.need_epoch; halo.own = cell_owners(c); halo.rank = c->mg.rank;
+    if (!c->mg.need) halo.own.world = 1;                         // before orbc_mg_export: no halo bookkeeping yet
+    const bool part = mg_active(c) && !all_cells;
+    const int c0 = part ? c->mg.cb : 0, c1 = part ? c->mg.ce : nc;
+    if (c1 > c0) ORBC_LAUNCH(c, k_stencil_build, blocks_for(c1 - c0, kStencilWarps), kStencilWarps * 32, 0, c->centroid, c0, c1, gd, c->stencil, c->stencil_cnt, c->d_flags, halo);
     c->stencil_valid = true;
     return ORBC_OK;
 }
@@ -156,6 +167,12 @@ void fill_integ(IntegArgs &a, orbc_ctx *c, int sp, const orbc_step_params *p) {
     a.dr_opt = p->dr_opt; a.dn_opt = p->dn_opt;
     a.seed = p->seed; a.step = (uint32_t)p->nstep;
     a.noise = nullptr; a.acc = c->d_acc; a.zeta_dev = nullptr;
+    a.range = c->d_range + 2 * sp;
+    a.push.world = 1; a.push.cell_mask = nullptr; a.push.pmask = nullptr; a.push.cellid = nullptr;
+    if (mg_active(c)) {
+        a.push.world = c->mg.world; a.push.cell_mask = c->mg.dest_mask; a.push.pmask = sp == ORBC_PROTEIN ? c->mg.pmask : nullptr; a.push.cellid = s.C();
+        for (int r = 0; r < kMaxWorld; ++r) { a.push.x[r] = c->mg.peers.x[sp][s.cur][r]; a.push.nn[r] = c->mg.peers.nn[sp][s.cur][r]; }
+    }
 }
 
 orbc_forcefield g_host_ff;   // host copy of the table last installed (radius feeds the Langevin coefficients)
@@ -184,15 +201,16 @@ CullTable cull_table(const orbc_ctx *c) {
 int build_porder(orbc_ctx *c) {
     Species &P = c->sp[1];
     if (!P.n) return ORBC_OK;
-    if (c->porder_cap < P.n + 1) { ORBC_TRY(dev_alloc(&c->porder, P.n + 1)); c->porder_cap = P.n + 1; }
+    const size_t cap = owned_bound(c, ORBC_PROTEIN);
+    if (c->porder_cap < cap + 1) { ORBC_TRY(dev_alloc(&c->porder, cap + 1)); c->porder_cap = cap + 1; }
     const CullTable ct = cull_table(c);
     float lo = 1e30f, hi = 0.f;                                   // heavy = upper half of the ranges present
     for (int t = 0; t < kNType; ++t) if (c->type_mask >> t & 1) { lo = std::min(lo, ct.cut_l[t]); hi = std::max(hi, ct.cut_l[t]); }
     const float heavy_cut = hi > 1.5f * lo ? 0.5f * (lo + hi) : 2.f * hi + 1.f;   // homogeneous ranges: nobody is heavy
     int *flag = P.li;                                             // free between cell updates (n + 1 ints)
-    ORBC_LAUNCH(c, k_porder_flag, blocks_for(P.n, kBlock), kBlock, 0, P.X(), P.n, ct, heavy_cut, flag);
-    ORBC_TRY(scan_exclusive(c, flag, (int)P.n));
-    ORBC_LAUNCH(c, k_porder_scatter, blocks_for(P.n, kBlock), kBlock, 0, flag, P.n, P.X(), ct, heavy_cut, c->porder);
+    ORBC_LAUNCH(c, k_porder_flag, blocks_for(cap, kBlock), kBlock, 0, P.X(), c->d_range, cap, ct, heavy_cut, flag);
+    ORBC_TRY(scan_exclusive(c, flag, (int)cap));
+    ORBC_LAUNCH(c, k_porder_scatter, blocks_for(cap, kBlock), kBlock, 0, flag, c->d_range, cap, P.X(), ct, heavy_cut, c->porder);
     c->porder_valid = true;
     return ORBC_OK;
 }
@@ -206,21 +224,29 @@ int launch_pairwise(orbc_ctx *c) {
     a.xp = P.X(); a.np = P.N(); a.cs_p = P.cell_start; a.cell_p = P.C(); a.n_p = (int)P.n;
     a.stencil = c->stencil; a.stencil_cnt = c->stencil_cnt;
     a.fl = L.f; a.tl = L.t; a.fp = P.f; a.tp = P.t;
+    a.range = c->d_range;
+    const bool mg = mg_active(c);
+    a.cb = mg ? c->mg.cb : 0; a.ce = mg ? c->mg.ce : c->n_cells; a.world = mg ? c->mg.world : 1;
+    const size_t nl = owned_bound(c, ORBC_LIPID), np = owned_bound(c, ORBC_PROTEIN);
     if (c->pair_impl == 1) {
-        if (L.n) { ProfScope ps(c, ORBC_PROF_PAIR_LIPID); ORBC_LAUNCH(c, k_pair_lipid, blocks_for(L.n, 128), 128, 0, a); }
-        if (P.n) { ProfScope ps(c, ORBC_PROF_PAIR_PROTEIN); ORBC_LAUNCH(c, k_pair_protein, blocks_for(P.n, 128), 128, 0, a); }
+        if (mg) return fail(ORBC_ERR_ARG, "pair_impl 1 is a single-GPU cross-check");
+        if (L.n) { ProfScope ps(c, ORBC_PROF_PAIR_LIPID); ORBC_LAUNCH(c, k_pair_lipid<false>, blocks_for(nl, 128), 128, 0, a, (const unsigned char *)nullptr); }
+        if (P.n) { ProfScope ps(c, ORBC_PROF_PAIR_PROTEIN); ORBC_LAUNCH(c, k_pair_protein, blocks_for(np, 128), 128, 0, a); }
         return ORBC_OK;
     }
     {
         ProfScope ps(c, ORBC_PROF_PAIR_LIPID);
-        ORBC_LAUNCH(c, k_cell_bounds, blocks_for(c->n_cells, 128), 128, 0, c->centroid, c->n_cells, L.cell_start, L.X(), P.n ? P.cell_start : nullptr, P.X(), c->lbound, c->pbound);
-        if (L.n) ORBC_LAUNCH(c, k_pair_ll<true>, blocks_for(L.n, kLLBlock), kLLBlock, 0, a);
+        ORBC_LAUNCH(c, k_cell_bounds, blocks_for(c->n_cells, 128), 128, 0, c->centroid, c->n_cells, L.cell_start, L.X(), P.n ? P.cell_start : nullptr, P.X(), c->lbound, c->pbound,
+                    mg ? c->mg.need : (const int *)nullptr, c->mg.need_epoch);
+        if (L.n) ORBC_LAUNCH(c, k_pair_ll<true>, blocks_for(nl, kLLBlock), kLLBlock, 0, a);
+        // lipid side of the protein-lipid pairs whose protein lives on another rank
+        if (mg && L.n && P.n) ORBC_LAUNCH(c, k_pair_lipid<true>, blocks_for(nl, 128), 128, 0, a, c->mg.dest_mask);
     }
     if (P.n) {
         const CullTable ct = cull_table(c);
         if (!c->porder_valid) ORBC_TRY(build_porder(c));
         ProfScope ps(c, ORBC_PROF_PAIR_PROTEIN);
-        ORBC_LAUNCH(c, k_pair_prot, blocks_for(P.n, kPBlock), kPBlock, 0, a, c->lbound, c->pbound, ct, c->porder);
+        ORBC_LAUNCH(c, k_pair_prot, blocks_for(np, kPBlock), kPBlock, 0, a, c->lbound, c->pbound, ct, c->porder);
     }
     return ORBC_OK;
 }
@@ -229,7 +255,7 @@ int launch_bonded(orbc_ctx *c) {
     Species &P = c->sp[1];
     if (!c->n_bonds) return ORBC_OK;
     ProfScope ps(c, ORBC_PROF_BONDED);
-    ORBC_LAUNCH(c, k_bonded, blocks_for(c->n_bonds, kBlock), kBlock, 0, c->bonds, c->n_bonds, c->tag2idx, P.X(), P.f);
+    ORBC_LAUNCH(c, k_bonded, blocks_for(c->n_bonds, kBlock), kBlock, 0, c->bonds, c->n_bonds, c->tag2idx, P.X(), P.f, c->d_range);
     return ORBC_OK;
 }
 
@@ -244,58 +270,145 @@ int do_voronoi_update(orbc_ctx *c, int nstep, int freq_sort_ctrd) {
     Species &L = c->sp[0];
     if (!c->n_cells || !L.has_partition) return fail(ORBC_ERR_ARG, "voronoi_update: no previous partition (orbc_voronoi_upload with cell_start first)");
     const int nc = c->n_cells;
-    ORBC_LAUNCH(c, k_centroid_update, blocks_for(nc, kBlock), kBlock, 0, L.cell_start, L.X(), nc, c->centroid_tmp);
-    if (freq_sort_ctrd > 0 && nstep % freq_sort_ctrd == 0) {
+    const bool mg = mg_active(c);
+    // centroids of the owned cells, published to every rank (voronoi.h:123-140)
+    CentroidOut out; out.world = mg ? c->mg.world : 1;
+    for (int r = 0; r < kMaxWorld; ++r) out.dst[r] = mg ? c->mg.peers.centroid[c->mg.cen_par ^ 1][r] : c->centroid_tmp;
+    const int cb = mg ? c->mg.cb : 0, ce = mg ? c->mg.ce : nc;
+    if (ce > cb) ORBC_LAUNCH(c, k_centroid_update, blocks_for(ce - cb, kBlock), kBlock, 0, L.cell_start, L.X(), cb, ce, out);
+    ORBC_TRY(mg_barrier(c));
+    const bool morton = freq_sort_ctrd > 0 && nstep % freq_sort_ctrd == 0;
+    if (morton) {
         ORBC_LAUNCH(c, k_morton_keys, blocks_for(nc, kBlock), kBlock, 0, c->centroid_tmp, nc, c->keys, c->perm);
         ORBC_TRY(radix_sort_pairs(c, c->keys, c->perm, c->keys_tmp, c->perm_tmp, nc));
         ORBC_LAUNCH(c, k_permute_centroids, blocks_for(nc, kBlock), kBlock, 0, c->centroid_tmp, c->perm, nc, c->centroid, c->inv);
         // cells were renumbered: carry every particle's previous cell into the new numbering (it is only a search hint)
-        for (int s = 0; s < 2; ++s) if (c->sp[s].n) ORBC_LAUNCH(c, k_remap_cellid, blocks_for(c->sp[s].n, kBlock), kBlock, 0, c->sp[s].C(), c->sp[s].n, c->inv);
+        for (int s = 0; s < 2; ++s) if (c->sp[s].n) ORBC_LAUNCH(c, k_remap_cellid, blocks_for(owned_bound(c, s), kBlock), kBlock, 0, c->sp[s].C(), c->d_range + 2 * s, c->inv);
     } else {
         std::swap(c->centroid, c->centroid_tmp);
+        c->mg.cen_par ^= 1;
     }
-    return build_index(c);
+    return build_index(c, morton);
 }
 
-int do_cell_update(orbc_ctx *c, int sp) {
+// VCellList::update in three phases, so that a decomposed rebuild can run both containers through each phase between two
+// barriers.  Phase A: nearest centroid of every owned particle + arrival counts (voronoi.h:179-216), counts published.
+int cell_update_assign(orbc_ctx *c, int sp) {
     Species &S = c->sp[sp];
     if (!c->n_cells || !c->stencil_valid) return fail(ORBC_ERR_ARG, "cell_update: no Voronoi diagram");
     const int nc = c->n_cells;
+    const bool mg = mg_active(c);
     if (!S.cell_start) ORBC_TRY(dev_alloc(&S.cell_start, (size_t)nc + 1));
-    ORBC_CUDA(cudaMemsetAsync(S.cell_start, 0, sizeof(int) * ((size_t)nc + 1), c->stream));
+    int *cnt = mg ? c->mg.cnt_all[sp] + (size_t)c->mg.rank * (nc + 1) : S.cell_start;
+    ORBC_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int) * ((size_t)nc + 1), c->stream));
     if (S.n) {
         const GridDev gd = grid_dev(c);
-        ORBC_LAUNCH(c, k_assign_nearest, blocks_for(S.n, kBlock), kBlock, 0, S.X(), S.has_partition ? S.C() : nullptr, S.n, c->centroid, nc,
-                    c->stencil, c->stencil_cnt, gd, S.aff, S.li, S.cell_start, c->d_counters, c->d_flags);
+        ORBC_LAUNCH(c, k_assign_nearest, blocks_for(owned_bound(c, sp), kBlock), kBlock, 0, S.X(), S.has_partition ? S.C() : nullptr, c->d_range + 2 * sp, c->centroid, nc,
+                    c->stencil, c->stencil_cnt, gd, S.aff, S.li, cnt, c->d_counters, c->d_flags);
+    }
+    if (mg) {
+        CountRows rows; for (int r = 0; r < kMaxWorld; ++r) rows.dst[r] = c->mg.peers.cnt_all[sp][r];
+        ORBC_LAUNCH(c, k_share_counts, blocks_for((size_t)nc + 1, kBlock), kBlock, 0, cnt, nc + 1, c->mg.rank, c->mg.world, rows);
+    }
+    return ORBC_OK;
+}
+// Phase B: global cell_start (voronoi.h:217-227), then every particle moves to its new slot on its new owner (voronoi.h:228-231
+// + reorder.h:73-149 as one scatter; the migration of a decomposed run is the same store, into a peer's memory)
+int cell_update_move(orbc_ctx *c, int sp) {
+    Species &S = c->sp[sp];
+    const int nc = c->n_cells;
+    const bool mg = mg_active(c);
+    const int *local_start = S.cell_start, *off_me = nullptr;
+    if (mg) {
+        ORBC_LAUNCH(c, k_cell_totals, blocks_for(nc, kBlock), kBlock, 0, c->mg.cnt_all[sp], nc, c->mg.rank, c->mg.world, S.cell_start, c->mg.off_me[sp], c->mg.local_start[sp]);
+        ORBC_TRY(scan_exclusive(c, c->mg.local_start[sp], nc));
+        local_start = c->mg.local_start[sp]; off_me = c->mg.off_me[sp];
     }
     ORBC_TRY(scan_exclusive(c, S.cell_start, nc));
     if (S.n) {
-        ORBC_LAUNCH(c, k_cell_scatter, blocks_for(S.n, kBlock), kBlock, 0, S.aff, S.li, S.n, S.cell_start, S.cells_tmp);
+        const size_t nb = owned_bound(c, sp);
+        ORBC_LAUNCH(c, k_cell_scatter, blocks_for(nb, kBlock), kBlock, 0, S.aff, S.li, c->d_range + 2 * sp, local_start, S.cells_tmp);
         const int nx = S.cur ^ 1;
-        ORBC_LAUNCH(c, k_rank_and_move, blocks_for(S.n, kBlock), kBlock, 0, S.aff, S.n, S.cell_start, S.cells_tmp, S.cells, S.X(), S.N(), S.V(), S.O(),
-                    S.x[nx], S.nn[nx], S.v[nx], S.o[nx], S.cellid[nx]);
+        MoveDst d; d.own = cell_owners(c);
+        for (int r = 0; r < kMaxWorld; ++r) {
+            d.x[r] = mg ? c->mg.peers.x[sp][nx][r] : S.x[nx]; d.nn[r] = mg ? c->mg.peers.nn[sp][nx][r] : S.nn[nx];
+            d.v[r] = mg ? c->mg.peers.v[sp][nx][r] : S.v[nx]; d.o[r] = mg ? c->mg.peers.o[sp][nx][r] : S.o[nx];
+            d.cellid[r] = mg ? c->mg.peers.cellid[sp][nx][r] : S.cellid[nx];
+            d.tag2idx[r] = mg ? c->mg.peers.tag2idx[r] : c->tag2idx;
+        }
+        ORBC_LAUNCH(c, k_rank_and_move, blocks_for(nb, kBlock), kBlock, 0, S.aff, c->d_range + 2 * sp, S.cell_start, local_start, off_me, S.cells_tmp, S.cells,
+                    S.X(), S.N(), S.V(), S.O(), d, (mg && sp == ORBC_PROTEIN) ? 1 : 0);
         S.cur = nx;
     }
     S.has_partition = true;
-    if (sp == ORBC_PROTEIN) { ORBC_TRY(build_tag2idx(c)); c->porder_valid = false; }
+    return ORBC_OK;
+}
+// Phase C: tag -> index map (container.h:39-58); decomposed: new owned range, bonded-partner masks, halo copies of the moved particles
+int cell_update_finish(orbc_ctx *c, int sp) {
+    Species &S = c->sp[sp];
+    const bool mg = mg_active(c);
+    if (sp == ORBC_PROTEIN) c->porder_valid = false;
+    if (!mg) { if (sp == ORBC_PROTEIN) ORBC_TRY(build_tag2idx(c)); return ORBC_OK; }
+    ORBC_LAUNCH(c, k_set_range, 1, 1, 0, S.cell_start, c->mg.cb, c->mg.ce, c->d_range + 2 * sp, (int)c->mg.own_cap[sp], c->d_flags);
+    if (!S.n) return ORBC_OK;
+    if (sp == ORBC_PROTEIN && c->n_bonds) {
+        ORBC_CUDA(cudaMemsetAsync(c->mg.pmask, 0, (S.n + 3) / 4 * 4, c->stream));
+        ORBC_LAUNCH(c, k_bond_mask, blocks_for(c->n_bonds, kBlock), kBlock, 0, c->bonds, c->n_bonds, c->tag2idx, c->d_range, S.cell_start, cell_owners(c), (unsigned *)c->mg.pmask);
+    }
+    HaloDst d; for (int r = 0; r < kMaxWorld; ++r) { d.x[r] = c->mg.peers.x[sp][S.cur][r]; d.nn[r] = c->mg.peers.nn[sp][S.cur][r]; }
+    ORBC_LAUNCH(c, k_halo_push, blocks_for(owned_bound(c, sp), kBlock), kBlock, 0, c->d_range + 2 * sp, c->mg.dest_mask, sp == ORBC_PROTEIN ? c->mg.pmask : (const unsigned char *)nullptr,
+                S.C(), S.X(), S.N(), d);
     return ORBC_OK;
 }
 
+int do_cell_update(orbc_ctx *c, int sp) {
+    ORBC_TRY(cell_update_assign(c, sp)); ORBC_TRY(mg_barrier(c));
+    ORBC_TRY(cell_update_move(c, sp));   ORBC_TRY(mg_barrier(c));
+    ORBC_TRY(cell_update_finish(c, sp)); return mg_barrier(c);
+}
+
 int do_integrate_langevin(orbc_ctx *c, const orbc_step_params *p) {
-    ProfScope ps(c, ORBC_PROF_INTEGRATE);
-    for (int sp = 0; sp < 2; ++sp) {
-        Species &S = c->sp[sp];
-        if (!S.n) continue;
-        IntegArgs a; fill_integ(a, c, sp, p); langevin_coeffs(a, p);
-        const float *hn = sp == 0 ? p->noise_lipid : p->noise_protein;
-        if (hn) {
-            if (c->noise_cap[sp] < 3 * S.n) { ORBC_TRY(dev_alloc(&c->noise[sp], 3 * S.n)); c->noise_cap[sp] = 3 * S.n; }
-            ORBC_CUDA(cudaMemcpyAsync(c->noise[sp], hn, sizeof(float) * 3 * S.n, cudaMemcpyHostToDevice, c->stream));
-            a.noise = c->noise[sp];
+    ORBC_TRY(mg_barrier(c));                                     // every rank has finished reading the halo it is about to overwrite
+    {
+        ProfScope ps(c, ORBC_PROF_INTEGRATE);
+        for (int sp = 0; sp < 2; ++sp) {
+            Species &S = c->sp[sp];
+            if (!S.n) continue;
+            IntegArgs a; fill_integ(a, c, sp, p); langevin_coeffs(a, p);
+            const float *hn = sp == 0 ? p->noise_lipid : p->noise_protein;
+            if (hn) {
+                if (c->noise_cap[sp] < 3 * S.n) { ORBC_TRY(dev_alloc(&c->noise[sp], 3 * S.n)); c->noise_cap[sp] = 3 * S.n; }
+                ORBC_CUDA(cudaMemcpyAsync(c->noise[sp], hn, sizeof(float) * 3 * S.n, cudaMemcpyHostToDevice, c->stream));
+                a.noise = c->noise[sp];
+            }
+            ORBC_LAUNCH(c, k_verlet_langevin, blocks_for(owned_bound(c, sp), 256), 256, 0, a);
         }
-        ORBC_LAUNCH(c, k_verlet_langevin, blocks_for(S.n, 256), 256, 0, a);
     }
+    return mg_barrier(c);                                        // the pushed halo has landed everywhere
+}
+
+// CUDA loads kernels lazily, and loading one may wait for the device to go idle — a rank spinning in k_mg_barrier while its
+// peer loads a kernel for the first time would never be released.  A decomposed context therefore loads every kernel up front.
+int preload_kernels() {
+    cudaFuncAttributes fa;
+#define ORBC_PRELOAD(k) ORBC_CUDA(cudaFuncGetAttributes(&fa, (const void *)(k)))
+    ORBC_PRELOAD(k_assign_nearest); ORBC_PRELOAD(k_bin_count); ORBC_PRELOAD(k_bin_fill); ORBC_PRELOAD(k_bond_mask); ORBC_PRELOAD(k_bonded);
+    ORBC_PRELOAD(k_bounce_back); ORBC_PRELOAD(k_build_tag2idx); ORBC_PRELOAD(k_cell_bounds); ORBC_PRELOAD(k_cell_scatter); ORBC_PRELOAD(k_cell_totals);
+    ORBC_PRELOAD(k_centroid_update); ORBC_PRELOAD(k_clear_force); ORBC_PRELOAD(k_compact); ORBC_PRELOAD(k_cv_apply); ORBC_PRELOAD(k_cv_center);
+    ORBC_PRELOAD(k_cv_normal_volume); ORBC_PRELOAD(k_fill_cellid); ORBC_PRELOAD(k_fill_int); ORBC_PRELOAD(k_halo_push); ORBC_PRELOAD(k_kinetic);
+    ORBC_PRELOAD(k_mg_barrier); ORBC_PRELOAD(k_morton_keys); ORBC_PRELOAD(k_morton_keys_only); ORBC_PRELOAD(k_nh_final); ORBC_PRELOAD(k_nh_final_fused);
+    ORBC_PRELOAD(k_nh_initial_fused); ORBC_PRELOAD(k_nh_zeta_update); ORBC_PRELOAD(k_noise); ORBC_PRELOAD(k_opt_move); ORBC_PRELOAD(k_pack4);
+    ORBC_PRELOAD(k_pair_lipid<true>); ORBC_PRELOAD(k_pair_lipid<false>); ORBC_PRELOAD(k_pair_ll<true>); ORBC_PRELOAD(k_pair_prot); ORBC_PRELOAD(k_pair_protein);
+    ORBC_PRELOAD(k_permute_centroids); ORBC_PRELOAD(k_porder_flag); ORBC_PRELOAD(k_porder_scatter); ORBC_PRELOAD(k_post_torque); ORBC_PRELOAD(k_radix_hist);
+    ORBC_PRELOAD(k_radix_scatter); ORBC_PRELOAD(k_rank_and_move); ORBC_PRELOAD(k_remap_cellid); ORBC_PRELOAD(k_scan_apply); ORBC_PRELOAD(k_scan_sums);
+    ORBC_PRELOAD(k_scan_tile_sums); ORBC_PRELOAD(k_set3); ORBC_PRELOAD(k_set_range); ORBC_PRELOAD(k_set_range_const); ORBC_PRELOAD(k_share_counts);
+    ORBC_PRELOAD(k_stencil_build); ORBC_PRELOAD(k_stray_mask); ORBC_PRELOAD(k_unpack3); ORBC_PRELOAD(k_unpack_w); ORBC_PRELOAD(k_verlet_langevin); ORBC_PRELOAD(k_zero4);
+#undef ORBC_PRELOAD
     return ORBC_OK;
+}
+
+int single_gpu_only(orbc_ctx *c, const char *what) {
+    return mg_active(c) ? fail(ORBC_ERR_ARG, "%s is not available on a decomposed run yet", what) : ORBC_OK;
 }
 
 } // namespace
@@ -340,7 +453,7 @@ int orbc_forcefield_canonical(orbc_forcefield *ff) {
     return ORBC_OK;
 }
 
-int orbc_set_forcefield(orbc_ctx *c, const orbc_forcefield *ff) {
+int orbc_set_forcefield(orbc_ctx *c, const orbc_forcefield *ff) { if (c) cudaSetDevice(c->device);
     if (!c || !ff) return fail(ORBC_ERR_ARG, "null argument");
     ORBC_CUDA(cudaMemcpyToSymbolAsync(c_ff, ff, sizeof(*ff), 0, cudaMemcpyHostToDevice, c->stream));
     ORBC_CUDA(cudaStreamSynchronize(c->stream));
@@ -362,6 +475,7 @@ int orbc_create(orbc_ctx **out, int device) {
     c->stream = c->own_stream;
     for (auto &e : c->ev) ORBC_CUDA(cudaEventCreate(&e));
     ORBC_TRY(dev_alloc(&c->d_acc, 8)); ORBC_TRY(dev_alloc(&c->d_counters, 8)); ORBC_TRY(dev_alloc(&c->d_flags, 4)); ORBC_TRY(dev_alloc(&c->d_nh, 2));
+    ORBC_TRY(dev_alloc(&c->d_range, 4)); ORBC_CUDA(cudaMemset(c->d_range, 0, 4 * sizeof(int)));
     ORBC_CUDA(cudaMemset(c->d_acc, 0, 8 * sizeof(double))); ORBC_CUDA(cudaMemset(c->d_counters, 0, 8 * sizeof(unsigned long long)));
     ORBC_CUDA(cudaMemset(c->d_flags, 0, 4 * sizeof(int))); ORBC_CUDA(cudaMemset(c->d_nh, 0, 2 * sizeof(float)));
     ORBC_CUDA(cudaMallocHost((void **)&c->h_acc, 8 * sizeof(double))); ORBC_CUDA(cudaMallocHost((void **)&c->h_flags, 4 * sizeof(int)));
@@ -371,7 +485,7 @@ int orbc_create(orbc_ctx **out, int device) {
     return orbc_set_forcefield(c, &ff);
 }
 
-void orbc_destroy(orbc_ctx *c) {
+void orbc_destroy(orbc_ctx *c) { if (c) cudaSetDevice(c->device);
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
@@ -380,7 +494,10 @@ void orbc_destroy(orbc_ctx *c) {
     dev_free(c->grid.bin_start); dev_free(c->grid.bin_items); dev_free(c->grid.bin_of); dev_free(c->grid.bin_slot); dev_free(c->grid.sorted);
     dev_free(c->stencil); dev_free(c->stencil_cnt); dev_free(c->cell_normal); dev_free(c->lbound); dev_free(c->pbound); dev_free(c->porder); dev_free(c->bonds); dev_free(c->tag2idx);
     dev_free(c->scan_tmp); dev_free(c->radix_hist); dev_free(c->stage); dev_free(c->d_acc); dev_free(c->d_counters); dev_free(c->d_flags); dev_free(c->d_nh);
-    dev_free(c->noise[0]); dev_free(c->noise[1]);
+    dev_free(c->noise[0]); dev_free(c->noise[1]); dev_free(c->d_range);
+    for (void *m : c->mg.opened) cudaIpcCloseMemHandle(m);
+    dev_free(c->mg.flags); dev_free(c->mg.dest_mask); dev_free(c->mg.pmask); dev_free(c->mg.need);
+    for (int s = 0; s < 2; ++s) { dev_free(c->mg.cnt_all[s]); dev_free(c->mg.off_me[s]); dev_free(c->mg.local_start[s]); }
     if (c->h_acc) cudaFreeHost(c->h_acc); if (c->h_flags) cudaFreeHost(c->h_flags); if (c->h_counters) cudaFreeHost(c->h_counters); if (c->h_nh) cudaFreeHost(c->h_nh);
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
     for (auto &v : c->prof_ev) for (auto &e : v) cudaEventDestroy(e);
@@ -388,16 +505,16 @@ void orbc_destroy(orbc_ctx *c) {
     delete c;
 }
 
-int orbc_set_option(orbc_ctx *c, const char *name, double value) {
+int orbc_set_option(orbc_ctx *c, const char *name, double value) { if (c) cudaSetDevice(c->device);
     if (!c || !name) return fail(ORBC_ERR_ARG, "null argument");
     if (!strcmp(name, "pair_impl")) { if (value != 1 && value != 2) return fail(ORBC_ERR_ARG, "pair_impl must be 1 or 2"); c->pair_impl = (int)value; return ORBC_OK; }
     return fail(ORBC_ERR_ARG, "unknown option '%s'", name);
 }
 
-int orbc_synchronize(orbc_ctx *c) { ORBC_CUDA(cudaStreamSynchronize(c->stream)); return check_flags(c); }
-int orbc_set_stream(orbc_ctx *c, void *s) { ORBC_CUDA(cudaStreamSynchronize(c->stream)); c->stream = s ? (cudaStream_t)s : c->own_stream; return ORBC_OK; }
+int orbc_synchronize(orbc_ctx *c) { if (c) cudaSetDevice(c->device); ORBC_CUDA(cudaStreamSynchronize(c->stream)); return check_flags(c); }
+int orbc_set_stream(orbc_ctx *c, void *s) { if (c) cudaSetDevice(c->device); ORBC_CUDA(cudaStreamSynchronize(c->stream)); c->stream = s ? (cudaStream_t)s : c->own_stream; return ORBC_OK; }
 
-int orbc_upload(orbc_ctx *c, int sp, size_t n, size_t stride, const float *x, const float *v, const float *n_, const float *o, const int *type, const int *tag) {
+int orbc_upload(orbc_ctx *c, int sp, size_t n, size_t stride, const float *x, const float *v, const float *n_, const float *o, const int *type, const int *tag) { if (c) cudaSetDevice(c->device);
     if (!c || sp < 0 || sp > 1 || stride < 3) return fail(ORBC_ERR_ARG, "orbc_upload: bad argument");
     if (n && (!x || !n_)) return fail(ORBC_ERR_ARG, "orbc_upload: x and n are required");
     if (n >= (size_t)1 << 31) return fail(ORBC_ERR_ARG, "orbc_upload: more than 2^31 particles per container");
@@ -443,7 +560,7 @@ int orbc_upload(orbc_ctx *c, int sp, size_t n, size_t stride, const float *x, co
     return ORBC_OK;
 }
 
-int orbc_upload_bonds(orbc_ctx *c, size_t n_bonds, const int *tij) {
+int orbc_upload_bonds(orbc_ctx *c, size_t n_bonds, const int *tij) { if (c) cudaSetDevice(c->device);
     if (!c || (n_bonds && !tij)) return fail(ORBC_ERR_ARG, "orbc_upload_bonds: bad argument");
     for (size_t b = 0; b < n_bonds; ++b) {
         if (tij[3 * b] < 0 || tij[3 * b] >= 4) return fail(ORBC_ERR_ARG, "bond %zu has type %d outside [0,4)", b, tij[3 * b]);
@@ -457,7 +574,7 @@ int orbc_upload_bonds(orbc_ctx *c, size_t n_bonds, const int *tij) {
     return ORBC_OK;
 }
 
-int orbc_voronoi_upload(orbc_ctx *c, int nc, const float *centroids3, const int *csl, const int *csp) {
+int orbc_voronoi_upload(orbc_ctx *c, int nc, const float *centroids3, const int *csl, const int *csp) { if (c) cudaSetDevice(c->device);
     if (!c || nc <= 0 || !centroids3) return fail(ORBC_ERR_ARG, "orbc_voronoi_upload: bad argument");
     if (nc >= (1 << 28)) return fail(ORBC_ERR_ARG, "more than 2^28 Voronoi cells");
     if (nc != c->n_cells) {
@@ -490,7 +607,7 @@ int orbc_voronoi_upload(orbc_ctx *c, int nc, const float *centroids3, const int 
     return ORBC_OK;
 }
 
-int orbc_set_field(orbc_ctx *c, int sp, char field, size_t stride, const float *src) {
+int orbc_set_field(orbc_ctx *c, int sp, char field, size_t stride, const float *src) { if (c) cudaSetDevice(c->device);
     if (!c || sp < 0 || sp > 1 || stride < 3 || !src) return fail(ORBC_ERR_ARG, "orbc_set_field: bad argument");
     Species &S = c->sp[sp];
     float4 *dst = field == 'f' ? S.f : field == 't' ? S.t : field == 'v' ? S.V() : field == 'x' ? S.X() : field == 'n' ? S.N() : field == 'o' ? S.O() : nullptr;
@@ -503,9 +620,9 @@ int orbc_set_field(orbc_ctx *c, int sp, char field, size_t stride, const float *
     return ORBC_OK;
 }
 
-int orbc_voronoi_update(orbc_ctx *c, int nstep, int freq_sort_ctrd) { if (!c) return fail(ORBC_ERR_ARG, "null ctx"); return do_voronoi_update(c, nstep, freq_sort_ctrd); }
+int orbc_voronoi_update(orbc_ctx *c, int nstep, int freq_sort_ctrd) { if (c) cudaSetDevice(c->device); if (!c) return fail(ORBC_ERR_ARG, "null ctx"); return do_voronoi_update(c, nstep, freq_sort_ctrd); }
 
-int orbc_cell_update(orbc_ctx *c, int sp, int nstep, int freq_sort_bond) {
+int orbc_cell_update(orbc_ctx *c, int sp, int nstep, int freq_sort_bond) { if (c) cudaSetDevice(c->device);
     (void)nstep; (void)freq_sort_bond;   // reorder_bond (reorder.h:33-68) only permutes bond storage for CPU cache locality
     if (!c || sp < 0 || sp > 1) return fail(ORBC_ERR_ARG, "orbc_cell_update: bad argument");
     return do_cell_update(c, sp);
@@ -514,19 +631,24 @@ int orbc_cell_update(orbc_ctx *c, int sp, int nstep, int freq_sort_bond) {
 int do_rebuild(orbc_ctx *c, int nstep, int freq_sort_ctrd) {
     ProfScope ps(c, ORBC_PROF_REBUILD);
     ORBC_TRY(do_voronoi_update(c, nstep, freq_sort_ctrd));
-    ORBC_TRY(do_cell_update(c, ORBC_LIPID));
-    return do_cell_update(c, ORBC_PROTEIN);
+    for (int sp = 0; sp < 2; ++sp) ORBC_TRY(cell_update_assign(c, sp));
+    ORBC_TRY(mg_barrier(c));
+    for (int sp = 0; sp < 2; ++sp) ORBC_TRY(cell_update_move(c, sp));
+    ORBC_TRY(mg_barrier(c));
+    for (int sp = 0; sp < 2; ++sp) ORBC_TRY(cell_update_finish(c, sp));
+    return mg_barrier(c);
 }
 
-int orbc_rebuild(orbc_ctx *c, int nstep, int freq_sort_ctrd, int freq_sort_bond) {
+int orbc_rebuild(orbc_ctx *c, int nstep, int freq_sort_ctrd, int freq_sort_bond) { if (c) cudaSetDevice(c->device);
     (void)freq_sort_bond;
     if (!c) return fail(ORBC_ERR_ARG, "null ctx");
     return do_rebuild(c, nstep, freq_sort_ctrd);
 }
 
-int orbc_delete_lipid(orbc_ctx *c, float tol, size_t *n_out) {
+int orbc_delete_lipid(orbc_ctx *c, float tol, size_t *n_out) { if (c) cudaSetDevice(c->device);
     if (!c) return fail(ORBC_ERR_ARG, "null ctx");
     Species &L = c->sp[0];
+    ORBC_TRY(single_gpu_only(c, "delete_lipid"));
     if (!L.has_partition) return fail(ORBC_ERR_ARG, "delete_lipid: lipids are not partitioned");
     const int nc = c->n_cells;
     const size_t n = L.n;
@@ -542,6 +664,7 @@ int orbc_delete_lipid(orbc_ctx *c, float tol, size_t *n_out) {
         ORBC_LAUNCH(c, k_compact, blocks_for(n, kBlock), kBlock, 0, keep, newpos, n, L.X(), L.N(), L.V(), L.O(), L.C(),
                     L.x[nx], L.nn[nx], L.v[nx], L.o[nx], L.cellid[nx]);
         L.cur = nx; L.n = (size_t)total;
+        ORBC_LAUNCH(c, k_set_range_const, 1, 1, 0, c->d_range, 0, total);
         // f and t are zero at this point of the loop (cleared by the integrator); keep them so for the survivors
         ORBC_LAUNCH(c, k_zero4, blocks_for(n, kBlock), kBlock, 0, L.f, n, (const int *)nullptr);
         ORBC_LAUNCH(c, k_zero4, blocks_for(n, kBlock), kBlock, 0, L.t, n, (const int *)nullptr);
@@ -551,12 +674,13 @@ int orbc_delete_lipid(orbc_ctx *c, float tol, size_t *n_out) {
     return ORBC_OK;
 }
 
-int orbc_compute_pairwise_fused(orbc_ctx *c) { if (!c) return fail(ORBC_ERR_ARG, "null ctx"); return launch_pairwise(c); }
-int orbc_compute_bonded(orbc_ctx *c) { if (!c) return fail(ORBC_ERR_ARG, "null ctx"); return launch_bonded(c); }
+int orbc_compute_pairwise_fused(orbc_ctx *c) { if (c) cudaSetDevice(c->device); if (!c) return fail(ORBC_ERR_ARG, "null ctx"); return launch_pairwise(c); }
+int orbc_compute_bonded(orbc_ctx *c) { if (c) cudaSetDevice(c->device); if (!c) return fail(ORBC_ERR_ARG, "null ctx"); return launch_bonded(c); }
 
-int orbc_constrain_volume(orbc_ctx *c, float target, float strength, float *volume_out) {
+int orbc_constrain_volume(orbc_ctx *c, float target, float strength, float *volume_out) { if (c) cudaSetDevice(c->device);
     if (!c) return fail(ORBC_ERR_ARG, "null ctx");
     Species &L = c->sp[0], &P = c->sp[1];
+    ORBC_TRY(single_gpu_only(c, "constrain_volume"));
     if (!L.has_partition) return fail(ORBC_ERR_ARG, "constrain_volume: lipids are not partitioned");
     const int nc = c->n_cells;
     ORBC_CUDA(cudaMemsetAsync(c->d_acc + 1, 0, 4 * sizeof(double), c->stream));
@@ -579,12 +703,13 @@ float orbc_nh_zeta_update(float zeta, float *Q, double dt, float kBT, double ke,
     return zeta;
 }
 
-int orbc_integrate(orbc_ctx *c, int kernel, const orbc_step_params *p, orbc_step_result *res) {
+int orbc_integrate(orbc_ctx *c, int kernel, const orbc_step_params *p, orbc_step_result *res) { if (c) cudaSetDevice(c->device);
     if (!c) return fail(ORBC_ERR_ARG, "null ctx");
     const bool needs_p = kernel != ORBC_CLEAR_FORCE && kernel != ORBC_POST_TORQUE;
     if (needs_p && !p) return fail(ORBC_ERR_ARG, "orbc_integrate: this kernel needs step parameters");
     const bool reduces = kernel == ORBC_NH_INITIAL_FUSED || kernel == ORBC_NH_FINAL_FUSED || kernel == ORBC_NH_UPDATE;
     if (reduces) ORBC_CUDA(cudaMemsetAsync(c->d_acc, 0, sizeof(double), c->stream));
+    if (kernel != ORBC_VERLET_LANGEVIN && kernel != ORBC_CLEAR_FORCE) ORBC_TRY(single_gpu_only(c, "this integrate() kernel"));
     if (kernel == ORBC_VERLET_LANGEVIN) ORBC_TRY(do_integrate_langevin(c, p));
     else for (int sp = 0; sp < 2; ++sp) {
         Species &S = c->sp[sp];
@@ -599,7 +724,7 @@ int orbc_integrate(orbc_ctx *c, int kernel, const orbc_step_params *p, orbc_step
         case ORBC_NH_INITIAL_FUSED: ORBC_LAUNCH(c, k_nh_initial_fused, nb, 256, 0, a); break;
         case ORBC_NH_FINAL_FUSED: ORBC_LAUNCH(c, k_nh_final_fused, nb, 256, 0, a); break;
         case ORBC_NH_FINAL: ORBC_LAUNCH(c, k_nh_final, nb, 256, 0, a); break;
-        case ORBC_NH_UPDATE: ORBC_LAUNCH(c, k_kinetic, nb, 256, 0, S.X(), S.V(), S.n, 0.5f, c->d_acc); break;
+        case ORBC_NH_UPDATE: ORBC_LAUNCH(c, k_kinetic, nb, 256, 0, S.X(), S.V(), c->d_range + 2 * sp, 0.5f, c->d_acc); break;
         case ORBC_OPT_MOVE: ORBC_LAUNCH(c, k_opt_move, nb, 256, 0, a); break;
         default: return fail(ORBC_ERR_ARG, "orbc_integrate: unknown kernel id %d", kernel);
         }
@@ -615,22 +740,22 @@ int orbc_integrate(orbc_ctx *c, int kernel, const orbc_step_params *p, orbc_step
     return ORBC_OK;
 }
 
-int orbc_compute_temperature(orbc_ctx *c, double *T) {
+int orbc_compute_temperature(orbc_ctx *c, double *T) { if (c) cudaSetDevice(c->device);
     if (!c || !T) return fail(ORBC_ERR_ARG, "null argument");
     ORBC_CUDA(cudaMemsetAsync(c->d_acc, 0, sizeof(double), c->stream));
     size_t n = 0;
     for (int sp = 0; sp < 2; ++sp) {
         Species &S = c->sp[sp];
         n += S.n;
-        if (S.n) ORBC_LAUNCH(c, k_kinetic, blocks_for(S.n, 256), 256, 0, S.X(), S.V(), S.n, 1.0f, c->d_acc);
+        if (S.n) ORBC_LAUNCH(c, k_kinetic, blocks_for(owned_bound(c, sp), 256), 256, 0, S.X(), S.V(), c->d_range + 2 * sp, 1.0f, c->d_acc);
     }
     ORBC_CUDA(cudaMemcpyAsync(c->h_acc, c->d_acc, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     ORBC_CUDA(cudaStreamSynchronize(c->stream));
-    *T = c->h_acc[0] / (3.0 * (double)n);
+    *T = c->h_acc[0] / (3.0 * (double)n);     // decomposed run: this rank's share of the sum (the shares of all ranks add up to T)
     return ORBC_OK;
 }
 
-int orbc_run_langevin(orbc_ctx *c, const orbc_step_params *p, int n_steps, int freq_voronoi, int freq_sort_ctrd) {
+int orbc_run_langevin(orbc_ctx *c, const orbc_step_params *p, int n_steps, int freq_voronoi, int freq_sort_ctrd) { if (c) cudaSetDevice(c->device);
     if (!c || !p || freq_voronoi <= 0) return fail(ORBC_ERR_ARG, "orbc_run_langevin: bad argument");
     orbc_step_params q = *p;
     q.noise_lipid = q.noise_protein = nullptr;
@@ -643,8 +768,9 @@ int orbc_run_langevin(orbc_ctx *c, const orbc_step_params *p, int n_steps, int f
     return ORBC_OK;
 }
 
-int orbc_run_nh(orbc_ctx *c, const orbc_step_params *p, int n_steps, int freq_voronoi, int freq_sort_ctrd, float *zeta_io, float *Q_io) {
+int orbc_run_nh(orbc_ctx *c, const orbc_step_params *p, int n_steps, int freq_voronoi, int freq_sort_ctrd, float *zeta_io, float *Q_io) { if (c) cudaSetDevice(c->device);
     if (!c || !p || !zeta_io || !Q_io || freq_voronoi <= 0) return fail(ORBC_ERR_ARG, "orbc_run_nh: bad argument");
+    ORBC_TRY(single_gpu_only(c, "orbc_run_nh"));
     c->h_nh[0] = *zeta_io; c->h_nh[1] = *Q_io;
     ORBC_CUDA(cudaMemcpyAsync(c->d_nh, c->h_nh, 2 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     ORBC_CUDA(cudaMemsetAsync(c->d_acc, 0, sizeof(double), c->stream));
@@ -671,11 +797,110 @@ int orbc_run_nh(orbc_ctx *c, const orbc_step_params *p, int n_steps, int freq_vo
     return check_flags(c);
 }
 
-int orbc_size(orbc_ctx *c, int sp, size_t *n) { if (!c || sp < 0 || sp > 1 || !n) return fail(ORBC_ERR_ARG, "bad argument"); *n = c->sp[sp].n; return ORBC_OK; }
-int orbc_n_cells(orbc_ctx *c, int *n) { if (!c || !n) return fail(ORBC_ERR_ARG, "bad argument"); *n = c->n_cells; return ORBC_OK; }
+// ---- decomposition over the GPUs of one box (multi.cuh) ------------------------------------------------------------------------
+int orbc_mg_init(orbc_ctx *c, int rank, int world) { if (c) cudaSetDevice(c->device);
+    if (!c || world < 1 || world > kMaxWorld || rank < 0 || rank >= world) return fail(ORBC_ERR_ARG, "orbc_mg_init: rank %d of %d (at most %d ranks)", rank, world, kMaxWorld);
+    if (c->mg.connected) return fail(ORBC_ERR_ARG, "orbc_mg_init: already connected");
+    c->mg.on = true; c->mg.rank = rank; c->mg.world = world;
+    return preload_kernels();
+}
+
+size_t orbc_mg_blob_bytes(void) { return sizeof(MgBlob); }
+
+int orbc_mg_export(orbc_ctx *c, void *blob_out, size_t bytes) { if (c) cudaSetDevice(c->device);
+    if (!c || !blob_out || bytes < sizeof(MgBlob)) return fail(ORBC_ERR_ARG, "orbc_mg_export: bad argument");
+    if (!c->mg.on) return fail(ORBC_ERR_ARG, "orbc_mg_export: call orbc_mg_init first");
+    Species &L = c->sp[0], &P = c->sp[1];
+    if (!c->n_cells || !L.has_partition || (P.n && !P.has_partition))
+        return fail(ORBC_ERR_ARG, "orbc_mg_export: upload the whole state and its Voronoi partition on every rank first");
+    const int nc = c->n_cells, w = c->mg.world;
+    Decomp &m = c->mg;
+    const CellOwners own = cell_owners(c);
+    m.cb = own.beg[m.rank]; m.ce = own.beg[m.rank + 1];
+    if (m.flags && c->mg.connected) {
+        // a second call after a fresh upload of the same system: the peer-visible allocations stay where they are
+        for (int sp = 0; sp < 2; ++sp) ORBC_CUDA(cudaMemsetAsync(m.cnt_all[sp], 0, sizeof(int) * (size_t)w * (nc + 1), c->stream));
+        ORBC_CUDA(cudaMemsetAsync(m.pmask, 0, P.n + 4, c->stream));
+        if (m.cen_buf[m.cen_par] != c->centroid) return fail(ORBC_ERR_STATE, "orbc_mg_export: centroid buffers were reallocated after orbc_mg_connect");
+    } else {
+        for (int sp = 0; sp < 2; ++sp) {
+            const size_t n = c->sp[sp].n;
+            m.own_cap[sp] = w == 1 ? n : std::min(n, n / w + n / (4 * (size_t)w) + 8192);
+            ORBC_TRY(dev_alloc(&m.cnt_all[sp], (size_t)w * (nc + 1))); ORBC_TRY(dev_alloc(&m.off_me[sp], (size_t)nc + 1)); ORBC_TRY(dev_alloc(&m.local_start[sp], (size_t)nc + 1));
+            ORBC_CUDA(cudaMemsetAsync(m.cnt_all[sp], 0, sizeof(int) * (size_t)w * (nc + 1), c->stream));
+        }
+        ORBC_TRY(dev_alloc(&m.flags, kMaxWorld)); ORBC_CUDA(cudaMemsetAsync(m.flags, 0, sizeof(unsigned) * kMaxWorld, c->stream));
+        ORBC_TRY(dev_alloc(&m.dest_mask, nc)); ORBC_CUDA(cudaMemsetAsync(m.dest_mask, 0, nc, c->stream));
+        ORBC_TRY(dev_alloc(&m.pmask, P.n + 4)); ORBC_CUDA(cudaMemsetAsync(m.pmask, 0, P.n + 4, c->stream));
+        ORBC_TRY(dev_alloc(&m.need, nc)); ORBC_CUDA(cudaMemsetAsync(m.need, 0, sizeof(int) * nc, c->stream));
+        m.cen_buf[0] = c->centroid; m.cen_buf[1] = c->centroid_tmp; m.cen_par = 0; m.epoch = 0;
+        // scratch that the single-GPU path allocates on first use: allocate it now, no cudaMalloc while peers spin in a barrier
+        if (c->scan_tmp_cap < 65537) { ORBC_TRY(dev_alloc(&c->scan_tmp, 65537)); c->scan_tmp_cap = 65537; }
+        const size_t hist_n = (size_t)256 * ((nc + kRadixTile - 1) / kRadixTile) + 1;
+        if (c->radix_hist_cap < hist_n) { ORBC_TRY(dev_alloc(&c->radix_hist, hist_n)); c->radix_hist_cap = hist_n; }
+        if (c->porder_cap < m.own_cap[1] + 1) { ORBC_TRY(dev_alloc(&c->porder, m.own_cap[1] + 1)); c->porder_cap = m.own_cap[1] + 1; }
+    }
+    // owned ranges, halo masks and the cells this rank reads, from the uploaded (complete, everywhere identical) state
+    if (w > 1) {
+        for (int sp = 0; sp < 2; ++sp) ORBC_LAUNCH(c, k_set_range, 1, 1, 0, c->sp[sp].cell_start, m.cb, m.ce, c->d_range + 2 * sp, (int)m.own_cap[sp], c->d_flags);
+        ORBC_TRY(build_index(c, true));
+        if (P.n && c->n_bonds)
+            ORBC_LAUNCH(c, k_bond_mask, blocks_for(c->n_bonds, kBlock), kBlock, 0, c->bonds, c->n_bonds, c->tag2idx, c->d_range, P.cell_start, own, (unsigned *)m.pmask);
+        c->porder_valid = false;
+    }
+    ORBC_CUDA(cudaStreamSynchronize(c->stream));
+    MgBlob *b = (MgBlob *)blob_out;
+    memset(b, 0, sizeof(*b));
+    b->magic = kMgMagic; b->pid = (int)getpid(); b->device = c->device; b->rank = m.rank; b->world = w; b->n_cells = nc; b->n_l = L.n; b->n_p = P.n;
+    void *list[kMgShared]; mg_shared_list(c, list);
+    for (int k = 0; k < kMgShared; ++k) {
+        b->e[k].raw = (unsigned long long)(uintptr_t)list[k];
+        if (list[k] && w > 1) ORBC_CUDA(cudaIpcGetMemHandle(&b->e[k].handle, list[k]));
+    }
+    return check_flags(c);
+}
+
+int orbc_mg_connect(orbc_ctx *c, const void *blobs, size_t bytes_each) { if (c) cudaSetDevice(c->device);
+    if (!c || !blobs || bytes_each < sizeof(MgBlob)) return fail(ORBC_ERR_ARG, "orbc_mg_connect: bad argument");
+    Decomp &m = c->mg;
+    if (!m.on || !m.flags) return fail(ORBC_ERR_ARG, "orbc_mg_connect: call orbc_mg_init and orbc_mg_export first");
+    ORBC_CUDA(cudaSetDevice(c->device));
+    for (int r = 0; r < m.world; ++r) {
+        const MgBlob *b = (const MgBlob *)((const char *)blobs + (size_t)r * bytes_each);
+        if (b->magic != kMgMagic || b->rank != r || b->world != m.world) return fail(ORBC_ERR_ARG, "orbc_mg_connect: blob %d is not rank %d of %d", r, r, m.world);
+        if (b->n_cells != c->n_cells || b->n_l != c->sp[0].n || b->n_p != c->sp[1].n) return fail(ORBC_ERR_ARG, "orbc_mg_connect: rank %d holds a different system", r);
+        void *ptr[kMgShared];
+        for (int k = 0; k < kMgShared; ++k) {
+            ptr[k] = nullptr;
+            if (!b->e[k].raw) continue;
+            if (b->pid == (int)getpid()) {                       // same process (several ranks driven by one host program): plain pointers
+                ptr[k] = (void *)(uintptr_t)b->e[k].raw;
+                if (b->device != c->device) { cudaError_t e = cudaDeviceEnablePeerAccess(b->device, 0); if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) ORBC_CUDA(e); cudaGetLastError(); }
+            } else {                                             // one process per GPU: CUDA IPC mapping of the peer's allocation
+                ORBC_CUDA(cudaIpcOpenMemHandle(&ptr[k], b->e[k].handle, cudaIpcMemLazyEnablePeerAccess));
+                m.opened.push_back(ptr[k]);
+            }
+        }
+        mg_fill_peers(c, r, ptr);
+    }
+    m.connected = true;
+    return ORBC_OK;
+}
+
+int orbc_mg_range(orbc_ctx *c, int sp, size_t *begin, size_t *end) { if (c) cudaSetDevice(c->device);
+    if (!c || sp < 0 || sp > 1 || !begin || !end) return fail(ORBC_ERR_ARG, "orbc_mg_range: bad argument");
+    int r[2];
+    ORBC_CUDA(cudaMemcpyAsync(r, c->d_range + 2 * sp, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    ORBC_CUDA(cudaStreamSynchronize(c->stream));
+    *begin = (size_t)r[0]; *end = (size_t)r[1];
+    return check_flags(c);
+}
+
+int orbc_size(orbc_ctx *c, int sp, size_t *n) { if (c) cudaSetDevice(c->device); if (!c || sp < 0 || sp > 1 || !n) return fail(ORBC_ERR_ARG, "bad argument"); *n = c->sp[sp].n; return ORBC_OK; }
+int orbc_n_cells(orbc_ctx *c, int *n) { if (c) cudaSetDevice(c->device); if (!c || !n) return fail(ORBC_ERR_ARG, "bad argument"); *n = c->n_cells; return ORBC_OK; }
 
 int orbc_download(orbc_ctx *c, int sp, size_t stride, float *x, float *v, float *n_, float *o, float *f, float *t,
-                  int *affiliation, int *type, int *tag, size_t *n_out) {
+                  int *affiliation, int *type, int *tag, size_t *n_out) { if (c) cudaSetDevice(c->device);
     if (!c || sp < 0 || sp > 1 || stride < 3) return fail(ORBC_ERR_ARG, "orbc_download: bad argument");
     Species &S = c->sp[sp];
     if (n_out) *n_out = S.n;
@@ -705,7 +930,7 @@ int orbc_download(orbc_ctx *c, int sp, size_t stride, float *x, float *v, float 
     return check_flags(c);
 }
 
-int orbc_debug_dump(orbc_ctx *c, int what, void *dst, size_t bytes) {
+int orbc_debug_dump(orbc_ctx *c, int what, void *dst, size_t bytes) { if (c) cudaSetDevice(c->device);
     if (!c || !dst) return fail(ORBC_ERR_ARG, "bad argument");
     const int nc = c->n_cells;
     const void *src = nullptr; size_t need = 0;
@@ -747,7 +972,7 @@ int orbc_debug_dump(orbc_ctx *c, int what, void *dst, size_t bytes) {
     return check_flags(c);
 }
 
-int orbc_debug_noise(orbc_ctx *c, uint64_t seed, int nstep, int species, size_t n, float *dst) {
+int orbc_debug_noise(orbc_ctx *c, uint64_t seed, int nstep, int species, size_t n, float *dst) { if (c) cudaSetDevice(c->device);
     if (!c || !dst) return fail(ORBC_ERR_ARG, "bad argument");
     ORBC_TRY(ensure_stage(c, 3 * n));
     ORBC_LAUNCH(c, k_noise, blocks_for(n, kBlock), kBlock, 0, seed, (uint32_t)nstep, (uint32_t)species, n, c->stage);
@@ -756,25 +981,25 @@ int orbc_debug_noise(orbc_ctx *c, uint64_t seed, int nstep, int species, size_t 
     return ORBC_OK;
 }
 
-int orbc_event_record(orbc_ctx *c, int slot) {
+int orbc_event_record(orbc_ctx *c, int slot) { if (c) cudaSetDevice(c->device);
     if (!c || slot < 0 || slot >= 16) return fail(ORBC_ERR_ARG, "bad event slot");
     ORBC_CUDA(cudaEventRecord(c->ev[slot], c->stream));
     return ORBC_OK;
 }
-int orbc_event_elapsed_ms(orbc_ctx *c, int a, int b, float *ms) {
+int orbc_event_elapsed_ms(orbc_ctx *c, int a, int b, float *ms) { if (c) cudaSetDevice(c->device);
     if (!c || a < 0 || a >= 16 || b < 0 || b >= 16 || !ms) return fail(ORBC_ERR_ARG, "bad event slot");
     ORBC_CUDA(cudaEventSynchronize(c->ev[b]));
     ORBC_CUDA(cudaEventElapsedTime(ms, c->ev[a], c->ev[b]));
     return ORBC_OK;
 }
-int orbc_profile_enable(orbc_ctx *c, int on) {
+int orbc_profile_enable(orbc_ctx *c, int on) { if (c) cudaSetDevice(c->device);
     if (!c) return fail(ORBC_ERR_ARG, "null ctx");
     ORBC_CUDA(cudaStreamSynchronize(c->stream));
     c->prof_on = on != 0;
     for (auto &u : c->prof_used) u = 0;
     return ORBC_OK;
 }
-int orbc_profile_read(orbc_ctx *c, int cls, double *total_ms, unsigned long long *count) {
+int orbc_profile_read(orbc_ctx *c, int cls, double *total_ms, unsigned long long *count) { if (c) cudaSetDevice(c->device);
     if (!c || cls < 0 || cls >= ORBC_PROF_N || !total_ms || !count) return fail(ORBC_ERR_ARG, "orbc_profile_read: bad argument");
     ORBC_CUDA(cudaStreamSynchronize(c->stream));
     double sum = 0.0; const size_t pairs = c->prof_used[cls] / 2;
@@ -783,6 +1008,6 @@ int orbc_profile_read(orbc_ctx *c, int cls, double *total_ms, unsigned long long
     c->prof_used[cls] = 0;
     return ORBC_OK;
 }
-int orbc_launch_count(orbc_ctx *c, unsigned long long *n) { if (!c || !n) return fail(ORBC_ERR_ARG, "bad argument"); *n = c->launches; return ORBC_OK; }
+int orbc_launch_count(orbc_ctx *c, unsigned long long *n) { if (c) cudaSetDevice(c->device); if (!c || !n) return fail(ORBC_ERR_ARG, "bad argument"); *n = c->launches; return ORBC_OK; }
 
 } // extern "C"

@@ -17,6 +17,8 @@ struct PairArgs {
     const float4 *xp, *np; const int *cs_p; const int *cell_p; int n_p;
     const int *stencil, *stencil_cnt;
     float4 *fl, *tl, *fp, *tp;
+    const int *range;      // {l0, l1, p0, p1}: the particle slots this GPU computes (everything on a single GPU)
+    int cb, ce, world;     // owned cells of a decomposed run ([0, n_cells) and 1 otherwise)
 };
 
 struct F3 { float x, y, z; };
@@ -65,9 +67,14 @@ __device__ __forceinline__ F3 rep8(float cut, float rep, F3 d, float r2) {
 // ---- v1: one thread per lipid -------------------------------------------------------------------------------------------------
 // lipid i gathers: LL over the r<6 stencil of its cell (lipid_lipid::rmax, compute_pairwise_fused.h:92), protein-lipid over the
 // r<8 stencil (prote_lipid::rmax, :144) as the lipid side of protein_lipid_omp / lennard_jones_omp.
-__global__ void __launch_bounds__(128) k_pair_lipid(PairArgs a) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.n_l) return;
+// FOREIGN = true (decomposed runs): only the proteins of stencil cells owned by ANOTHER rank are visited — the lipid side of
+// the protein-lipid pairs whose protein side that rank evaluates (the reference's one-sided evaluation across thread
+// ranges, compute_pairwise_fused.h:287-295); lipid-lipid is left to k_pair_ll.
+template <bool FOREIGN>
+__global__ void __launch_bounds__(128) k_pair_lipid(PairArgs a, const unsigned char *__restrict__ dest_mask) {
+    const int i = a.range[0] + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.range[1]) return;
+    if (FOREIGN && !dest_mask[a.cell_l[i]]) return;      // no stencil cell of this lipid's cell lives on another rank
     const float4 xi4 = a.xl[i], ni4 = a.nl[i];
     const F3 xi = {xi4.x, xi4.y, xi4.z}, mi = {ni4.x, ni4.y, ni4.z};
     const int c = a.cell_l[i];
@@ -78,7 +85,8 @@ __global__ void __launch_bounds__(128) k_pair_lipid(PairArgs a) {
     const float cutsqll = c_ff.cutsqll;
     for (int k = 0; k < n8; ++k) {
         const int c2 = st[k];
-        if (k < n6) {
+        if (FOREIGN && c2 >= a.cb && c2 < a.ce) continue;
+        if (!FOREIGN && k < n6) {
             const int jb = a.cs_l[c2], je = a.cs_l[c2 + 1];
             for (int j = jb; j < je; ++j) {
                 const float4 xj = a.xl[j];
@@ -118,8 +126,8 @@ __global__ void __launch_bounds__(128) k_pair_lipid(PairArgs a) {
 
 // ---- v1: one thread per protein: protein-protein over r<9 (prote_prote::rmax, :183), protein side of protein-lipid over r<8 ----
 __global__ void __launch_bounds__(128) k_pair_protein(PairArgs a) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.n_p) return;
+    const int i = a.range[2] + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.range[3]) return;
     const float4 xi4 = a.xp[i], ni4 = a.np[i];
     const F3 xi = {xi4.x, xi4.y, xi4.z}, mi = {ni4.x, ni4.y, ni4.z};
     const int type1 = __float_as_int(xi4.w);
@@ -171,16 +179,22 @@ __global__ void __launch_bounds__(128) k_pair_protein(PairArgs a) {
 }
 
 // ---- compute_bonded.h:89-146: F = K (1 - r0 / |dx|) dx, +F on atom i, -F on atom j ----------------------------------------------
-__global__ void k_bonded(const int *__restrict__ bonds, size_t n_bonds, const int *__restrict__ tag2idx, const float4 *__restrict__ x, float4 *__restrict__ f) {
+// Decomposed runs: every rank walks the whole bond list and applies the force to the atoms it owns (slots [p0, p1)); a bond
+// that straddles two ranks is evaluated by both, one-sidedly, from the halo copy of the partner.
+__global__ void k_bonded(const int *__restrict__ bonds, size_t n_bonds, const int *__restrict__ tag2idx, const float4 *__restrict__ x, float4 *__restrict__ f,
+                         const int *__restrict__ range) {
     const size_t l = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= n_bonds) return;
     const int type = bonds[3 * l], p1 = tag2idx[bonds[3 * l + 1]], p2 = tag2idx[bonds[3 * l + 2]];
+    const int lo = range[2], hi = range[3];
+    const bool own1 = p1 >= lo && p1 < hi, own2 = p2 >= lo && p2 < hi;
+    if (!own1 && !own2) return;
     const float4 a = x[p1], b = x[p2];
     const float dx = b.x - a.x, dy = b.y - a.y, dz = b.z - a.z;
     const float rinv = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);   // K (1 - r0/r) cancels near r0: keep the exact reciprocal root
     const float s = c_ff.K[type] * (1.0f - c_ff.r0[type] * rinv);
-    atomicAdd(&f[p1].x, s * dx); atomicAdd(&f[p1].y, s * dy); atomicAdd(&f[p1].z, s * dz);
-    atomicAdd(&f[p2].x, -s * dx); atomicAdd(&f[p2].y, -s * dy); atomicAdd(&f[p2].z, -s * dz);
+    if (own1) { atomicAdd(&f[p1].x, s * dx); atomicAdd(&f[p1].y, s * dy); atomicAdd(&f[p1].z, s * dz); }
+    if (own2) { atomicAdd(&f[p2].x, -s * dx); atomicAdd(&f[p2].y, -s * dy); atomicAdd(&f[p2].z, -s * dz); }
 }
 
 } // namespace orbc

@@ -32,9 +32,11 @@ struct CullTable {                 // per protein type: largest interaction rang
 
 // ---- bounding spheres ------------------------------------------------------------------------------------------------------
 __global__ void k_cell_bounds(const float4 *__restrict__ centroid, int n_cells, const int *__restrict__ cs_l, const float4 *__restrict__ xl,
-                              const int *__restrict__ cs_p, const float4 *__restrict__ xp, float4 *__restrict__ lbound, float4 *__restrict__ pbound) {
+                              const int *__restrict__ cs_p, const float4 *__restrict__ xp, float4 *__restrict__ lbound, float4 *__restrict__ pbound,
+                              const int *__restrict__ need, int need_epoch) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n_cells) return;
+    if (need && need[c] != need_epoch) return;             // decomposed run: neither owned nor halo, its particles are stale here
     {
         const float4 q = centroid[c];
         const int b = cs_l[c], e = cs_l[c + 1];
@@ -117,8 +119,8 @@ __global__ void __launch_bounds__(kLLBlock) k_pair_ll(PairArgs a) {
     __shared__ int s_q[kLLBlock / 32][kQCap * 32];
     const int lane = threadIdx.x & 31;
     int *const q = s_q[threadIdx.x >> 5] + lane;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = i < a.n_l;
+    const int i = a.range[0] + blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i < a.range[1];
     const float4 *__restrict__ xl = a.xl;
     const float4 *__restrict__ nl = a.nl;
     const int *__restrict__ cs = a.cs_l;
@@ -191,20 +193,24 @@ __device__ __forceinline__ void atomic_add3(float4 *dst, float x, float y, float
 // the LJ-core-only types (actin, spectrin: 1.1225) after them, each class in storage order.  The work of a protein thread
 // scales with the square of its interaction range, and a warp is as slow as its slowest lane, so mixed warps would run at
 // the pace of the two or three heavy proteins in them.  Built after every protein reorder: flag -> scan -> scatter.
-__global__ void k_porder_flag(const float4 *__restrict__ xp, size_t n, CullTable ct, float heavy_cut, int *__restrict__ flag) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int t = __float_as_int(xp[i].w);
-    flag[i] = (t >= 0 && t < kNType && ct.cut_l[t] >= heavy_cut) ? 1 : 0;
+// Both kernels run over `cap` threads (the launch bound of the owned proteins); thread k stands for protein slot p0 + k.
+__global__ void k_porder_flag(const float4 *__restrict__ xp, const int *__restrict__ range, size_t cap, CullTable ct, float heavy_cut, int *__restrict__ flag) {
+    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= cap) return;
+    const int i = range[2] + (int)k;
+    int h = 0;
+    if (i < range[3]) { const int t = __float_as_int(xp[i].w); h = (t >= 0 && t < kNType && ct.cut_l[t] >= heavy_cut) ? 1 : 0; }
+    flag[k] = h;
 }
-__global__ void k_porder_scatter(const int *__restrict__ scan /* exclusive, scan[n] = n_heavy */, size_t n, const float4 *__restrict__ xp, CullTable ct, float heavy_cut,
-                                 int *__restrict__ porder) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+__global__ void k_porder_scatter(const int *__restrict__ scan /* exclusive, scan[cap] = n_heavy */, const int *__restrict__ range, size_t cap, const float4 *__restrict__ xp,
+                                 CullTable ct, float heavy_cut, int *__restrict__ porder) {
+    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = range[2] + (int)k;
+    if (k >= cap || i >= range[3]) return;
     const int t = __float_as_int(xp[i].w);
     const bool heavy = t >= 0 && t < kNType && ct.cut_l[t] >= heavy_cut;
-    const int before = scan[i];                                   // heavy proteins with a lower index
-    porder[heavy ? before : scan[n] + ((int)i - before)] = (int)i;
+    const int before = scan[k];                                   // heavy proteins with a lower index
+    porder[heavy ? before : scan[cap] + ((int)k - before)] = i;
 }
 
 constexpr int kPBlock = 64;
@@ -225,8 +231,9 @@ __global__ void __launch_bounds__(kPBlock, 16) k_pair_prot(PairArgs a, const flo
     int *const ljb = s_jb[0][w] + lane, *const pjb = s_jb[1][w] + lane;
     unsigned short *const llen = s_len[0][w] + lane, *const plen = s_len[1][w] + lane;
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = tid < a.n_p;
+    const bool live = tid < a.range[3] - a.range[2];
     const int i = live ? porder[tid] : 0;
+    const int l0 = a.range[0], l1 = a.range[1];                  // lipids of other ranks get their share from k_pair_lipid<true> over there
     F3 xi = {0, 0, 0}, mi = {0, 0, 0};
     int type1 = 0, n8 = 0, n9 = 0;
     const int *st = a.stencil;
@@ -286,11 +293,11 @@ __global__ void __launch_bounds__(kPBlock, 16) k_pair_prot(PairArgs a, const flo
                             F3 f, q1, q2;
                             poly48(c_ff.cutlp[type1], c_ff.attlp[type1], c_ff.replp[type1], c_ff.alphalp[type1], d, r2, mi, {nj.x, nj.y, nj.z}, f, q1, q2);
                             fx += f.x; fy += f.y; fz += f.z; tx -= q1.x; ty -= q1.y; tz -= q1.z;
-                            atomic_add3(a.fl + j, -f.x, -f.y, -f.z); atomic_add3(a.tl + j, -q2.x, -q2.y, -q2.z);
+                            if (j >= l0 && j < l1) { atomic_add3(a.fl + j, -f.x, -f.y, -f.z); atomic_add3(a.tl + j, -q2.x, -q2.y, -q2.z); }
                         } else if (r2 < ljcut) {
                             const F3 f = lj126(c_ff.lj_lj1[type1], c_ff.lj_lj2[type1], d, r2);
                             fx += f.x; fy += f.y; fz += f.z;
-                            atomic_add3(a.fl + j, -f.x, -f.y, -f.z);
+                            if (j >= l0 && j < l1) atomic_add3(a.fl + j, -f.x, -f.y, -f.z);
                         }
                     }
                 }

@@ -29,10 +29,25 @@ __device__ __forceinline__ void grid_bin(const GridDev &g, float4 p, int &bx, in
     bz = clampi((int)floorf((p.z - g.loz) * g.inv_h), 0, g.dz - 1);
 }
 
+// Static partition of the Voronoi cells over the ranks of a decomposed run: rank g owns cells [beg[g], beg[g + 1]),
+// beg[g] = g * n_cells / world — the reference's own thread partition (util_numa.h:41-42).  world == 1: everything.
+struct CellOwners {
+    int beg[kMaxWorld + 1];
+    int world;
+    __host__ __device__ int owner(int c) const {
+        int g = 0;
+        #pragma unroll
+        for (int r = 1; r < kMaxWorld; ++r) g += (r < world && c >= beg[r]);
+        return g;
+    }
+};
+struct CentroidOut { float4 *dst[kMaxWorld]; int world; };
+
 // ---- voronoi.h:123-140 — centroid = fp32 sequential sum over the cell's slots, times 1/count --------------------------
-__global__ void k_centroid_update(const int *__restrict__ cell_start, const float4 *__restrict__ x, int n_cells, float4 *__restrict__ centroid) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_cells) return;
+// cells [cb, ce) (the owned ones); the result goes to every rank's copy of the centroid array
+__global__ void k_centroid_update(const int *__restrict__ cell_start, const float4 *__restrict__ x, int cb, int ce, CentroidOut out) {
+    const int i = cb + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ce) return;
     const int b = cell_start[i], e = cell_start[i + 1];
     float cx = 0.f, cy = 0.f, cz = 0.f;
     for (int j = b; j < e; ++j) {
@@ -40,7 +55,8 @@ __global__ void k_centroid_update(const int *__restrict__ cell_start, const floa
         cx = __fadd_rn(cx, p.x); cy = __fadd_rn(cy, p.y); cz = __fadd_rn(cz, p.z);
     }
     const float s = __fdiv_rn(1.0f, __int2float_rn(e - b));   // empty cell: inf -> NaN centroid, as in the reference
-    centroid[i] = make_float4(__fmul_rn(cx, s), __fmul_rn(cy, s), __fmul_rn(cz, s), 0.f);
+    const float4 r = make_float4(__fmul_rn(cx, s), __fmul_rn(cy, s), __fmul_rn(cz, s), 0.f);
+    for (int g = 0; g < out.world; ++g) out.dst[g][i] = r;
 }
 
 // ---- reorder_morton.h:25-42 ----------------------------------------------------------------------------------------------
@@ -71,9 +87,9 @@ __global__ void k_permute_centroids(const float4 *__restrict__ src, const int *_
     dst[i] = src[o];
     inv[o] = i;
 }
-__global__ void k_remap_cellid(int *__restrict__ cellid, size_t n, const int *__restrict__ inv) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+__global__ void k_remap_cellid(int *__restrict__ cellid, const int *__restrict__ range, const int *__restrict__ inv) {
+    const int i = range[0] + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= range[1]) return;
     const int c = cellid[i];
     if (c >= 0) cellid[i] = inv[c];
 }
@@ -114,12 +130,15 @@ __global__ void k_bin_fill(int n, const int *__restrict__ bin_start, const int *
 // voronoi.h:105-117 (get_stencil_whole / refine_stencil) and kdtree.h:263-285 (find_within); the sets are identical, the
 // reference's order is tree-traversal order.  One warp per cell; the 27 surrounding bins are 9 x-contiguous runs.
 constexpr int kStencilWarps = 8;
-__global__ void __launch_bounds__(kStencilWarps * 32) k_stencil_build(const float4 *__restrict__ centroid, int n_cells, GridDev g,
-                                                                       int *__restrict__ stencil, int *__restrict__ stencil_cnt, int *__restrict__ flags) {
+// Decomposed runs also derive, per cell, the set of OTHER ranks that own a member of its r<9 stencil (dest_mask: who needs
+// this cell's particles as halo) and mark the cells this rank reads (need[c2] = need_epoch for the stencil members of owned cells).
+struct HaloOut { unsigned char *dest_mask; int *need; int need_epoch; CellOwners own; int rank; };
+__global__ void __launch_bounds__(kStencilWarps * 32) k_stencil_build(const float4 *__restrict__ centroid, int c_beg, int c_end, GridDev g,
+                                                                       int *__restrict__ stencil, int *__restrict__ stencil_cnt, int *__restrict__ flags, HaloOut halo) {
     __shared__ int s_key[kStencilWarps][kStencilStride];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int c = blockIdx.x * kStencilWarps + w;
-    if (c >= n_cells) return;
+    const int c = c_beg + blockIdx.x * kStencilWarps + w;
+    if (c >= c_end) return;
     const float4 q = centroid[c];
     int count = 0;
     if (q.x == q.x && q.y == q.y && q.z == q.z) {
@@ -162,16 +181,26 @@ __global__ void __launch_bounds__(kStencilWarps * 32) k_stencil_build(const floa
     if (count > kStencilStride) { if (lane == 0) atomicExch(&flags[0], c + 1); count = kStencilStride; }
     __syncwarp();
     int n6 = 0, n8 = 0;
+    unsigned owners = 0;
+    const bool mine = halo.own.world > 1 && halo.own.owner(c) == halo.rank;
     for (int e = lane; e < count; e += 32) {
         const int key = s_key[w][e];
         int rank = 0;
         for (int k = 0; k < count; ++k) rank += (s_key[w][k] < key);
         stencil[(size_t)c * kStencilStride + rank] = key & 0x0fffffff;
         n6 += (key >> 28) == 0; n8 += (key >> 28) <= 1;
+        if (halo.own.world > 1) {
+            owners |= 1u << halo.own.owner(key & 0x0fffffff);
+            if (mine) halo.need[key & 0x0fffffff] = halo.need_epoch;
+        }
     }
     #pragma unroll
     for (int d = 16; d > 0; d >>= 1) { n6 += __shfl_xor_sync(0xffffffffu, n6, d); n8 += __shfl_xor_sync(0xffffffffu, n8, d); }
     if (lane == 0) stencil_cnt[c] = n6 | (n8 << 8) | (count << 16);
+    if (halo.own.world > 1) {
+        owners = __reduce_or_sync(0xffffffffu, owners);
+        if (lane == 0) { halo.dest_mask[c] = (unsigned char)(owners & ~(1u << halo.own.owner(c))); if (mine) halo.need[c] = halo.need_epoch; }
+    }
 }
 
 // ---- nearest centroid (voronoi.h:179-216 + kdtree.h:206-236) ------------------------------------------------------------------
@@ -208,12 +237,12 @@ __device__ int nearest_by_grid(float4 p, const GridDev &g, const float4 *__restr
 // One thread per particle.  Fast path: the particle's previous cell g and g's r<9 centroid stencil; it is exact whenever
 // d(best) + d(g) < 9 (every centroid at least that close to the particle is then inside the stencil).  Otherwise the grid
 // search above.  Ties in the squared distance go to the lower cell id.
-__global__ void k_assign_nearest(const float4 *__restrict__ x, const int *__restrict__ cellid, size_t n, const float4 *__restrict__ centroid, int n_cells,
+__global__ void k_assign_nearest(const float4 *__restrict__ x, const int *__restrict__ cellid, const int *__restrict__ range, const float4 *__restrict__ centroid, int n_cells,
                                  const int *__restrict__ stencil, const int *__restrict__ stencil_cnt, GridDev g,
                                  int *__restrict__ aff, int *__restrict__ li, int *__restrict__ cell_cnt,
                                  unsigned long long *__restrict__ counters, int *__restrict__ flags) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    const int i = range[0] + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= range[1]) return;
     const float4 p = x[i];
     const int guess = cellid ? cellid[i] : -1;
     float best = INFINITY; int bi = -1; bool ok = false;
@@ -250,54 +279,45 @@ __global__ void k_assign_nearest(const float4 *__restrict__ x, const int *__rest
 }
 
 // cells_tmp[cell_start[aff] + arrival slot] = i   (voronoi.h:228-231 with an arbitrary arrival order ...)
-__global__ void k_cell_scatter(const int *__restrict__ aff, const int *__restrict__ li, size_t n, const int *__restrict__ cell_start, int *__restrict__ cells_tmp) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    cells_tmp[cell_start[aff[i]] + li[i]] = (int)i;
+__global__ void k_cell_scatter(const int *__restrict__ aff, const int *__restrict__ li, const int *__restrict__ range, const int *__restrict__ local_start, int *__restrict__ cells_tmp) {
+    const int i = range[0] + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= range[1]) return;
+    cells_tmp[local_start[aff[i]] + li[i]] = i;
 }
-// ... then every cell's segment is sorted ascending, which is the arrival order of the reference at one thread
-// (omp atomic capture in index order, voronoi.h:214-215): a stable counting sort.
-__global__ void k_cell_sort(const int *__restrict__ cell_start, int n_cells, const int *__restrict__ cells_tmp, int *__restrict__ cells) {
-    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (c >= n_cells) return;
-    const int b = cell_start[c], m = cell_start[c + 1] - b;
-    for (int e = lane; e < m; e += 32) {
-        const int v = cells_tmp[b + e];
-        int rank = 0;
-        for (int k = 0; k < m; ++k) rank += (cells_tmp[b + k] < v);
-        cells[b + rank] = v;
-    }
-}
-
-// The two steps above and the gather below in one pass, one thread per particle: the slot of particle i inside its new cell is
+// Sorting every cell's arrival list and the gather-reorder in one pass, one thread per particle: the slot of particle i inside its new cell is
 // the number of members with a lower index (= arrival order of the reference at one thread, voronoi.h:214-215), found by
 // scanning the cell's arrival list (a few dozen L1-resident ints shared by neighbouring threads); the particle then moves
 // itself: new[cell_start + rank] = old[i]  (reorder.h:73-149 as a scatter instead of a gather; `cells` still records the
 // permutation, VCellList::cells).
-__global__ void k_rank_and_move(const int *__restrict__ aff, size_t n, const int *__restrict__ cell_start, const int *__restrict__ cells_tmp, int *__restrict__ cells,
+// On a decomposed run the arrival list is this rank's (local_start = scan of its own counts), members that come from lower
+// ranks precede it in the cell (off_me; ranks own ascending slot ranges, so this is still ascending old index), and the
+// destination is the array of whichever rank owns the new cell — a direct store into that GPU's memory over NVLink.  A
+// protein also announces its new slot to every rank's tag -> index map (container.h:39-58).
+struct MoveDst {
+    float4 *x[kMaxWorld], *nn[kMaxWorld], *v[kMaxWorld], *o[kMaxWorld];
+    int *cellid[kMaxWorld], *tag2idx[kMaxWorld];
+    CellOwners own;
+};
+__global__ void k_rank_and_move(const int *__restrict__ aff, const int *__restrict__ range, const int *__restrict__ cell_start, const int *__restrict__ local_start,
+                                const int *__restrict__ off_me, const int *__restrict__ cells_tmp, int *__restrict__ cells,
                                 const float4 *__restrict__ x0, const float4 *__restrict__ n0, const float4 *__restrict__ v0, const float4 *__restrict__ o0,
-                                float4 *__restrict__ x1, float4 *__restrict__ n1, float4 *__restrict__ v1, float4 *__restrict__ o1, int *__restrict__ cellid1) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+                                MoveDst d, int announce_tags) {
+    const int i = range[0] + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= range[1]) return;
     const int c = aff[i];
-    const int b = cell_start[c], e = cell_start[c + 1];
+    const int b = local_start[c], e = local_start[c + 1];
     int rank = 0;
-    for (int k = b; k < e; ++k) rank += (cells_tmp[k] < (int)i);
-    const int j = b + rank;
-    cells[j] = (int)i;
-    x1[j] = x0[i]; n1[j] = n0[i]; v1[j] = v0[i]; o1[j] = o0[i];
-    cellid1[j] = c;
-}
-
-// reorder.h:73-149: out-of-place gather of x, v, n, o (type and tag ride in x.w / n.w) + the particle's cell
-__global__ void k_gather_reorder(const int *__restrict__ cells, const int *__restrict__ aff, size_t n,
-                                 const float4 *__restrict__ x0, const float4 *__restrict__ n0, const float4 *__restrict__ v0, const float4 *__restrict__ o0,
-                                 float4 *__restrict__ x1, float4 *__restrict__ n1, float4 *__restrict__ v1, float4 *__restrict__ o1, int *__restrict__ cellid1) {
-    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
-    const int s = cells[j];
-    x1[j] = x0[s]; n1[j] = n0[s]; v1[j] = v0[s]; o1[j] = o0[s];
-    cellid1[j] = aff[s];
+    for (int k = b; k < e; ++k) rank += (cells_tmp[k] < i);
+    const int j = cell_start[c] + (off_me ? off_me[c] : 0) + rank;
+    const int g = d.own.owner(c);
+    cells[j] = i;
+    const float4 nn = n0[i];
+    d.x[g][j] = x0[i]; d.nn[g][j] = nn; d.v[g][j] = v0[i]; d.o[g][j] = o0[i];
+    d.cellid[g][j] = c;
+    if (announce_tags) {
+        const int tag = __float_as_int(nn.w);
+        for (int r = 0; r < d.own.world; ++r) d.tag2idx[r][tag] = j;
+    }
 }
 
 // container.h:39-58

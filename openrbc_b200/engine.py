@@ -29,6 +29,7 @@ EXPORTS = [
     "orbc_constrain_volume", "orbc_integrate", "orbc_nh_zeta_update", "orbc_compute_temperature", "orbc_run_langevin",
     "orbc_run_nh", "orbc_download", "orbc_size", "orbc_n_cells", "orbc_debug_dump", "orbc_debug_noise", "orbc_event_record",
     "orbc_event_elapsed_ms", "orbc_launch_count", "orbc_profile_enable", "orbc_profile_read", "orbc_set_option",
+    "orbc_mg_init", "orbc_mg_blob_bytes", "orbc_mg_export", "orbc_mg_connect", "orbc_mg_range",
 ]
 
 
@@ -108,6 +109,11 @@ def load_library():
         lib.orbc_set_stream.argtypes = [C.c_void_p, C.c_void_p]
         lib.orbc_destroy.argtypes = [C.c_void_p]
         lib.orbc_destroy.restype = None
+        lib.orbc_mg_init.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        lib.orbc_mg_blob_bytes.restype = C.c_size_t
+        lib.orbc_mg_export.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        lib.orbc_mg_connect.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        lib.orbc_mg_range.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         _lib = lib
     return _lib
 
@@ -134,10 +140,13 @@ class Simulation:
     bonds (B x 3: type, tag_i, tag_j), centroids (C x 3), cs_l, cs_p (C + 1).
     """
 
-    def __init__(self, st, dt=1e-2, kBT=0.22, eta=0.01, seed=0xBAD5EED, device=0, box=(-1000.0, 1000.0)):
+    def __init__(self, st, dt=1e-2, kBT=0.22, eta=0.01, seed=0xBAD5EED, device=0, box=(-1000.0, 1000.0), rank=0, world=1):
         self.lib = load_library()
         self.ctx = C.c_void_p()
         self._ck(self.lib.orbc_create(C.byref(self.ctx), int(device)))
+        self.rank, self.world = rank, world
+        if world > 1:
+            self._ck(self.lib.orbc_mg_init(self.ctx, rank, world))
         self.dt, self.kBT, self.eta, self.seed = dt, kBT, eta, seed
         self.box = box
         self.zeta, self.Q = 0.0, C.c_float(0.0)
@@ -268,6 +277,26 @@ class Simulation:
 
     def synchronize(self):
         self._ck(self.lib.orbc_synchronize(self.ctx))
+
+    # ---- one cell over several GPUs ----------------------------------------------------------------------------
+    def mg_export(self):
+        """This rank's connection blob (bytes): raw pointers + CUDA IPC handles of the arrays its peers write into."""
+        n = self.lib.orbc_mg_blob_bytes()
+        buf = C.create_string_buffer(n)
+        self._ck(self.lib.orbc_mg_export(self.ctx, buf, n))
+        return buf.raw
+
+    def mg_connect(self, blobs):
+        """blobs: the mg_export() of every rank, in rank order."""
+        assert len(blobs) == self.world
+        n = self.lib.orbc_mg_blob_bytes()
+        joined = b"".join(blobs)
+        self._ck(self.lib.orbc_mg_connect(self.ctx, joined, n))
+
+    def owned_range(self, s):
+        b, e = C.c_size_t(), C.c_size_t()
+        self._ck(self.lib.orbc_mg_range(self.ctx, s, C.byref(b), C.byref(e)))
+        return b.value, e.value
 
     # ---- the reference's hot-path calls -------------------------------------------------------------------
     def voronoi_update(self):                                    # voronoi.update(lipid, cell_lipid, param)      openrbc.cpp:202
