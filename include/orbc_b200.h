@@ -154,6 +154,8 @@ ORBC_API int  orbc_run_nh(orbc_ctx *ctx, const orbc_step_params *p, int n_steps,
  * Every rank must issue the same sequence of calls. */
 ORBC_API int  orbc_mg_init(orbc_ctx *ctx, int rank, int world /* <= 8 */);
 ORBC_API size_t orbc_mg_blob_bytes(void);
+/* cells [begin, end) that rank `rank` of `world` owns: the reference's static range partition, util_numa.h:41-42 (host-only helper) */
+ORBC_API int  orbc_mg_cell_range(int n_cells, int rank, int world, int *cell_begin, int *cell_end);
 ORBC_API int  orbc_mg_export(orbc_ctx *ctx, void *blob_out, size_t bytes);
 ORBC_API int  orbc_mg_connect(orbc_ctx *ctx, const void *blobs /* world x bytes_each, rank order */, size_t bytes_each);
 /* particle slots [begin, end) of one container this rank owns right now (synchronises); orbc_download returns whole

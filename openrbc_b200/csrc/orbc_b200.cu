@@ -807,6 +807,14 @@ int orbc_mg_init(orbc_ctx *c, int rank, int world) { if (c) cudaSetDevice(c->dev
 
 size_t orbc_mg_blob_bytes(void) { return sizeof(MgBlob); }
 
+int orbc_mg_cell_range(int n_cells, int rank, int world, int *cell_begin, int *cell_end) {
+    // the reference's own static partition of a range over its workers (util_numa.h:41-42)
+    if (n_cells < 0 || world < 1 || world > kMaxWorld || rank < 0 || rank >= world || !cell_begin || !cell_end) return fail(ORBC_ERR_ARG, "orbc_mg_cell_range: bad argument");
+    *cell_begin = (int)((long long)rank * n_cells / world);
+    *cell_end = rank == world - 1 ? n_cells : (int)((long long)(rank + 1) * n_cells / world);
+    return ORBC_OK;
+}
+
 int orbc_mg_export(orbc_ctx *c, void *blob_out, size_t bytes) { if (c) cudaSetDevice(c->device);
     if (!c || !blob_out || bytes < sizeof(MgBlob)) return fail(ORBC_ERR_ARG, "orbc_mg_export: bad argument");
     if (!c->mg.on) return fail(ORBC_ERR_ARG, "orbc_mg_export: call orbc_mg_init first");

@@ -29,7 +29,7 @@ EXPORTS = [
     "orbc_constrain_volume", "orbc_integrate", "orbc_nh_zeta_update", "orbc_compute_temperature", "orbc_run_langevin",
     "orbc_run_nh", "orbc_download", "orbc_size", "orbc_n_cells", "orbc_debug_dump", "orbc_debug_noise", "orbc_event_record",
     "orbc_event_elapsed_ms", "orbc_launch_count", "orbc_profile_enable", "orbc_profile_read", "orbc_set_option",
-    "orbc_mg_init", "orbc_mg_blob_bytes", "orbc_mg_export", "orbc_mg_connect", "orbc_mg_range",
+    "orbc_mg_init", "orbc_mg_blob_bytes", "orbc_mg_cell_range", "orbc_mg_export", "orbc_mg_connect", "orbc_mg_range",
 ]
 
 
@@ -111,11 +111,21 @@ def load_library():
         lib.orbc_destroy.restype = None
         lib.orbc_mg_init.argtypes = [C.c_void_p, C.c_int, C.c_int]
         lib.orbc_mg_blob_bytes.restype = C.c_size_t
+        lib.orbc_mg_cell_range.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         lib.orbc_mg_export.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
         lib.orbc_mg_connect.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
         lib.orbc_mg_range.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         _lib = lib
     return _lib
+
+
+def cell_range(n_cells, rank, world):
+    """Cells [begin, end) owned by `rank` of `world` (util_numa.h:41-42)."""
+    b, e = C.c_int(), C.c_int()
+    lib = load_library()
+    if lib.orbc_mg_cell_range(n_cells, rank, world, C.byref(b), C.byref(e)) != 0:
+        raise OrbcError(lib.orbc_last_error().decode())
+    return b.value, e.value
 
 
 def forcefield_canonical():

@@ -123,7 +123,7 @@ def test_free_running_loop(name, world):
     for s in (0, 1):
         ref, got = one.download(s, "xvno"), gathered(sims, s, "xvno")
         for f in "xvno":
-            np.testing.assert_allclose(got[f], ref[f], rtol=0, atol=2e-5 * (1 + np.abs(ref[f]).max()), err_msg=f)
+            np.testing.assert_allclose(got[f], ref[f], rtol=0, atol=2e-5 * (1 + np.abs(ref[f]).max(initial=0.0)), err_msg=f)
     t = sum(sim.compute_temperature() for sim in sims)
     assert abs(t - one.compute_temperature()) < 1e-6 * t
     for sim in [one] + sims:
