@@ -64,7 +64,8 @@ def ensure_state(workload):
         np.savez(path, **st)
     else:
         kind = {"rbc": ["rbc", "--opt", "100"], "sphere": ["sphere", "--radius", "100", "--opt", "20"]}[workload]
-        env = dict(os.environ, OMP_PROC_BIND="close", OMP_PLACES="cores")
+        # torchrun exports OMP_NUM_THREADS=1 to its workers; the reference's initialisation should use the whole host
+        env = dict(os.environ, OMP_PROC_BIND="close", OMP_PLACES="cores", OMP_NUM_THREADS=str(host_threads()))
         out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "make_states.py"), *kind, "--out", path],
                              env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         if out.returncode != 0 or not os.path.exists(path):
@@ -145,7 +146,7 @@ def reference_line(args, steps, warmup, budget):
         t //= 2
     attempts = []
     for t in cand:
-        env = dict(os.environ)
+        env = dict(os.environ, OMP_NUM_THREADS=str(t))
         env.setdefault("OMP_PROC_BIND", "close"); env.setdefault("OMP_PLACES", "cores")
         for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
             env.pop(k, None)
@@ -249,11 +250,18 @@ def hbm_peak():
     return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(kernel):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/ncu_traffic.json,
+    written by hand from profiles/*_pair_ncu.txt: dram__bytes_read.sum + dram__bytes_write.sum); None when absent."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[kernel]
+        return float(d["dram_bytes_read"]) + float(d["dram_bytes_write"]), d.get("source")
+    except Exception:  # noqa: BLE001
+        return None, None
+
+
 def run_chunked(sim, n_steps):
     """n_steps of the main loop through the fused entry point, with delete_lipid at multiples of freq_cleanup (openrbc.cpp:201)."""
-    if sim.world > 1:                      # delete_lipid is not decomposed yet (DESIGN.md §multi-GPU): stated in config.multi_gpu
-        sim.run_langevin(n_steps)
-        return
     done = 0
     while done < n_steps:
         if sim.nstep % FREQ_CLEANUP == 0:
@@ -358,7 +366,7 @@ def run_ours(args):
     h2d = sum(host[k].nbytes for k in ("lx", "lv", "ln", "lo", "px", "pv", "pn", "po", "ptype", "ptag", "bonds", "centroids", "cs_l", "cs_p"))
     d2h = 0
     for _ in range(args.steps):
-        if world == 1 and e2e_sim.nstep % FREQ_CLEANUP == 0:
+        if e2e_sim.nstep % FREQ_CLEANUP == 0:
             e2e_sim.delete_lipid(e2e_sim.stray_tolerance); d2h += 8
         e2e_sim.step_langevin_checked(); d2h += 16
         if e2e_sim.nstep % FREQ_DISPLAY == 0:
@@ -395,12 +403,13 @@ def run_ours(args):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args.workload, st), "l2": "inputs larger than L2 (state %.0f MB resident in HBM, no flush needed)" % (n_total * 6 * 16 / 1e6),
                    "multi_gpu": "single GPU" if world == 1 else (f"one cell decomposed over {world} ranks: contiguous ranges of Morton-ordered Voronoi cells, halo push + migration "
-                                                                "by peer stores over NVLink, epoch-flag barriers; delete_lipid (every 60 steps on 1 GPU) not run"),
+                                                                "by peer stores over NVLink, epoch-flag barriers"),
                    "integrator": "verlet_langevin kBT=0.22 dt=0.01, rebuild every 2 steps, Morton sort every 24, cleanup every 60",
                    "particles_at_end": n_now, "temperature_at_end": temperature,
                    "hbm_roofline_frac_step": value / world * B_ALG_STEP / 1e9 / peak, "device_time_shares": shares},
         "roofline": {"bound": "hbm", "kernel": "k_pair_lipid (lipid side of compute_pairwise_fused)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+                     "frac": (achieved / peak) if achieved else None, "traffic": (ncu_traffic("k_pair_ll")[0] if world == 1 else None),
+                     "traffic_source": ncu_traffic("k_pair_ll")[1], "peak_source": peak_src,
                      "launch_ms": pl_ms / pl_cnt if pl_cnt else None, "launches_timed": pl_cnt,
                      "algorithmic_bytes_per_launch": B_ALG_PAIR * n_l,
                      "note": "pair forces are FP32-ALU bound (~1.6-3 kFLOP per 48 B), see DESIGN.md; HBM fraction reported as the contract asks"},

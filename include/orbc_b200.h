@@ -207,6 +207,11 @@ typedef enum {
 } orbc_prof_class;
 ORBC_API int  orbc_profile_enable(orbc_ctx *ctx, int on);
 ORBC_API int  orbc_profile_read(orbc_ctx *ctx, int cls, double *total_ms, unsigned long long *count);
+/* per-kernel launch list: while enabled every launch is bracketed by a CUDA event pair on the context's stream; the report is
+ * one line per kernel, "name launches total_us", sorted by total time, and resets the list (also usable on decomposed runs,
+ * where a replaying profiler cannot be: the ranks wait for each other inside kernels) */
+ORBC_API int  orbc_profile_kernels(orbc_ctx *ctx, int on);
+ORBC_API int  orbc_profile_kernels_report(orbc_ctx *ctx, char *text, size_t bytes);
 /* number of kernels this context has launched since creation */
 ORBC_API int  orbc_launch_count(orbc_ctx *ctx, unsigned long long *n);
 

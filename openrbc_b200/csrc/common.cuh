@@ -39,7 +39,8 @@ struct DevForceField {
 // x, n, v, o are double-buffered for the out-of-place reorder (reorder.h:73-149), like the reference's shadow arrays.
 struct Species {
     size_t n = 0, cap = 0;
-    int cur = 0;
+    int cur = 0;                          // current buffer of v, o, cellid
+    int cur_xn = 0;                       // current buffer of x, n (a decomposed run also flips it at every integration step)
     float4 *x[2] = {nullptr, nullptr}, *nn[2] = {nullptr, nullptr}, *v[2] = {nullptr, nullptr}, *o[2] = {nullptr, nullptr};
     float4 *f = nullptr, *t = nullptr;
     int *cellid[2] = {nullptr, nullptr};  // cell of every particle in storage order (-1: unknown), double-buffered with x
@@ -48,8 +49,8 @@ struct Species {
     int *cells = nullptr, *cells_tmp = nullptr;  // gather permutation (VCellList::cells)
     int *cell_start = nullptr;            // n_cells + 1 (VCellList::cell_start)
     bool has_partition = false;
-    float4 *X() const { return x[cur]; }
-    float4 *N() const { return nn[cur]; }
+    float4 *X() const { return x[cur_xn]; }
+    float4 *N() const { return nn[cur_xn]; }
     float4 *V() const { return v[cur]; }
     float4 *O() const { return o[cur]; }
     int *C() const { return cellid[cur]; }
@@ -80,6 +81,7 @@ struct PeerTable {
     int *cnt_all[2][kMaxWorld];           // [species][rank]: world x (n_cells + 1) arrival counts
     int *tag2idx[kMaxWorld];
     unsigned *flags[kMaxWorld];           // barrier epochs, one slot per writer
+    double *ke_all[kMaxWorld];            // partial kinetic energies, one slot per writer
 };
 struct Decomp {
     bool on = false, connected = false;
@@ -91,12 +93,14 @@ struct Decomp {
     int cen_par = 0;                      // which of the two centroid buffers is current (they swap on rebuilds)
     float4 *cen_buf[2] = {nullptr, nullptr};
     unsigned *flags = nullptr;            // kMaxWorld epochs written by the peers
+    double *ke_all = nullptr;             // kMaxWorld partial kinetic energies written by the peers
     int *cnt_all[2] = {nullptr, nullptr}; // world rows of arrival counts per species (row r written by rank r)
     int *off_me[2] = {nullptr, nullptr};  // members of each cell that come from lower ranks
     int *local_start[2] = {nullptr, nullptr};
     unsigned char *dest_mask = nullptr;   // per cell: ranks (other than the owner) that own a cell of its r<9 stencil
     unsigned char *pmask = nullptr;       // per protein slot: ranks that own a bonded partner
     int *need = nullptr;                  // per cell: == need_epoch for owned and halo cells
+    int *keep = nullptr;                  // per lipid slot: survives delete_lipid
     PeerTable peers;
     std::vector<void *> opened;           // IPC mappings to close
 };
@@ -128,7 +132,7 @@ struct orbc_ctx {
     int *bonds = nullptr;                         // (type, tag_i, tag_j)
     int *tag2idx = nullptr; size_t tag2idx_size = 0;
     // scratch
-    int *scan_tmp = nullptr; size_t scan_tmp_cap = 0;
+    int *scan_tmp = nullptr; size_t scan_tmp_cap = 0; unsigned scan_epoch = 0;   // tile descriptors of the single-pass scan
     int *radix_hist = nullptr; size_t radix_hist_cap = 0;
     float *stage = nullptr; size_t stage_cap = 0;         // device staging for strided host<->device packing
     double *d_acc = nullptr;                              // 8 doubles: reductions
@@ -141,20 +145,32 @@ struct orbc_ctx {
     unsigned long long launches = 0;
     bool ff_set = false;
     int pair_impl = 2;
+    int ll_variant = 1;
+    int prot_lanes = 0;                            // lanes per protein in k_pair_prot (0 = by the number of owned proteins)
     int *d_range = nullptr;                               // {l0, l1, p0, p1}: particle slots this context computes (all of them on one GPU)
     orbc::Decomp mg;
     // per-class event-pair profiling (orbc_profile_*)
     bool prof_on = false;
     std::vector<cudaEvent_t> prof_ev[ORBC_PROF_N];   // even = start, odd = stop
     size_t prof_used[ORBC_PROF_N] = {};
+    bool kprof_on = false;
+    std::vector<cudaEvent_t> kprof_ev;               // even = start, odd = stop
+    std::vector<const char *> kprof_name;            // one per pair
+    size_t kprof_used = 0;
 };
 
 namespace orbc {
 
 // launch helper: counts launches (bench.py reports gpu_launches from this)
 #define ORBC_LAUNCH(ctx, kernel, grid, block, smem, ...) do { \
+        if ((ctx)->kprof_on) ::orbc::kprof_mark((ctx), #kernel, false); \
         kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__); (ctx)->launches++; \
+        if ((ctx)->kprof_on) ::orbc::kprof_mark((ctx), #kernel, true); \
         ORBC_CUDA(cudaGetLastError()); } while (0)
+
+// per-launch event pairs keyed by kernel name (orbc_profile_kernels): an in-process launch list that also works on decomposed
+// runs, where a replaying profiler cannot be used (the ranks wait for each other inside kernels)
+inline void kprof_mark(orbc_ctx *c, const char *name, bool stop);
 
 // event pair around the launches of one kernel class; no-ops unless profiling is on
 inline int prof_mark(orbc_ctx *c, int cls, bool stop) {
@@ -173,6 +189,13 @@ struct ProfScope {
     ProfScope(orbc_ctx *c_, int cls_) : c(c_), cls(cls_) { prof_mark(c, cls, false); }
     ~ProfScope() { prof_mark(c, cls, true); }
 };
+
+inline void kprof_mark(orbc_ctx *c, const char *name, bool stop) {
+    if (c->kprof_used >= ((size_t)1 << 18)) return;
+    if (c->kprof_used >= c->kprof_ev.size()) { cudaEvent_t e; if (cudaEventCreate(&e) != cudaSuccess) return; c->kprof_ev.push_back(e); }
+    if (!stop) { if (c->kprof_name.size() <= c->kprof_used / 2) c->kprof_name.push_back(name); else c->kprof_name[c->kprof_used / 2] = name; }
+    cudaEventRecord(c->kprof_ev[c->kprof_used++], c->stream);
+}
 
 inline unsigned blocks_for(size_t n, unsigned block) { return (unsigned)((n + block - 1) / block); }
 

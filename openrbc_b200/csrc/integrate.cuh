@@ -49,6 +49,7 @@ struct PushArgs {
 };
 struct IntegArgs {
     float4 *x, *v, *f, *nn, *o, *t;
+    float4 *x_out, *nn_out;                // where verlet_langevin stores the new x, n (the same arrays on a single GPU)
     size_t n;
     const int *range;                      // {begin, end} slots to integrate (verlet_langevin)
     PushArgs push;
@@ -134,9 +135,9 @@ __global__ void __launch_bounds__(256) k_verlet_langevin(IntegArgs a) {
     const float k = a.dt / c_ff.mass[type];
     v.x += fx * k; v.y += fy * k; v.z += fz * k;
     x.x += v.x * a.dt; x.y += v.y * a.dt; x.z += v.z * a.dt;
-    a.x[i] = x; a.v[i] = v; a.o[i] = o;
+    a.x_out[i] = x; a.v[i] = v; a.o[i] = o;
     const float4 nnew = make_float4(nn.x, nn.y, nn.z, n4.w);
-    a.nn[i] = nnew;
+    a.nn_out[i] = nnew;
     a.f[i] = make_float4(0, 0, 0, 0); a.t[i] = make_float4(0, 0, 0, 0);
     if (a.push.world > 1) {
         unsigned m = a.push.cell_mask[a.push.cellid[i]];
@@ -150,9 +151,9 @@ __global__ void __launch_bounds__(256) k_verlet_langevin(IntegArgs a) {
 
 // integrate_nh.h:178-235 (operator()) — half kick with 1/(1 + dt zeta / 2), drift, bounce-back, KE, omega half kick, director, clear
 __global__ void __launch_bounds__(256) k_nh_initial_fused(IntegArgs a) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t i = (size_t)a.range[0] + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     double ke = 0.0;
-    if (i < a.n) {
+    if (i < (size_t)a.range[1]) {
         const float zeta = a.zeta_dev ? a.zeta_dev[0] : a.zeta;
         const float gamma = 1.0f / (1.0f + 0.5f * a.dt * zeta);
         float4 x = a.x[i], v = a.v[i], n4 = a.nn[i], o = a.o[i];
@@ -167,18 +168,27 @@ __global__ void __launch_bounds__(256) k_nh_initial_fused(IntegArgs a) {
         const float so = 0.5f * a.dt;
         o.x += so * t.x; o.y += so * t.y; o.z += so * t.z;
         const F3 nn = rotate_director({n4.x, n4.y, n4.z}, {o.x, o.y, o.z}, a.dt);
-        a.x[i] = x; a.v[i] = v; a.o[i] = o;
-        a.nn[i] = make_float4(nn.x, nn.y, nn.z, n4.w);
+        const float4 nnew = make_float4(nn.x, nn.y, nn.z, n4.w);
+        a.x_out[i] = x; a.v[i] = v; a.o[i] = o;
+        a.nn_out[i] = nnew;
         a.f[i] = make_float4(0, 0, 0, 0); a.t[i] = make_float4(0, 0, 0, 0);
+        if (a.push.world > 1) {                                  // halo push, as in k_verlet_langevin
+            unsigned m = a.push.cell_mask[a.push.cellid[i]];
+            if (a.push.pmask) m |= a.push.pmask[i];
+            while (m) {
+                const int r = __ffs(m) - 1; m &= m - 1;
+                a.push.x[r][i] = x; a.push.nn[r][i] = nnew;
+            }
+        }
     }
     block_add_double(ke, a.acc);
 }
 
 // integrate_nh.h:237-273 — t = n x t, second half kick with -zeta v, omega half kick, KE
 __global__ void __launch_bounds__(256) k_nh_final_fused(IntegArgs a) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t i = (size_t)a.range[0] + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     double ke = 0.0;
-    if (i < a.n) {
+    if (i < (size_t)a.range[1]) {
         const float zeta = a.zeta_dev ? a.zeta_dev[0] : a.zeta;
         float4 v = a.v[i], o = a.o[i];
         const float4 x = a.x[i], n4 = a.nn[i], f = a.f[i], t = a.t[i];
@@ -240,13 +250,28 @@ __global__ void k_opt_move(IntegArgs a) {
 
 // Nose-Hoover friction update of the functor destructors (integrate_nh.h:181-185,240-244), on the device for orbc_run_nh:
 // nh[0] = zeta, nh[1] = Q; acc[0] = KE (consumed and reset)
-__global__ void k_nh_zeta_update(float *nh, double *acc, double dt, float kBT, long n) {
+// Decomposed run: ke_all holds one partial kinetic energy per rank (k_share_ke + barrier); they are summed in rank order, so
+// every rank arrives at the same zeta.
+__global__ void k_nh_zeta_update(float *nh, double *acc, double dt, float kBT, long n, const double *ke_all, int world) {
     if (threadIdx.x || blockIdx.x) return;
+    double ke = acc[0];
+    if (ke_all) { ke = 0.0; for (int r = 0; r < world; ++r) ke += ke_all[r]; }
     if (!nh[1]) nh[1] = (float)(n * 0.01);
     float zeta = nh[0];
-    zeta += 0.5 * dt / nh[1] * (acc[0] - 0.5 * 3.0 * n * kBT);
+    zeta += 0.5 * dt / nh[1] * (ke - 0.5 * 3.0 * n * kBT);
     nh[0] = zeta;
     acc[0] = 0.0;
+    acc[5] = ke;                                                 // the summed kinetic energy, for callers that return it
+}
+struct KeDst { double *dst[kMaxWorld]; };
+__global__ void k_share_ke(const double *acc, int rank, int world, KeDst d) {
+    const int r = threadIdx.x;
+    if (r < world) d.dst[r][rank] = acc[0];
+}
+__global__ void k_sum_ke(double *acc, const double *ke_all, int world) {
+    if (threadIdx.x || blockIdx.x) return;
+    double ke = 0.0; for (int r = 0; r < world; ++r) ke += ke_all[r];
+    acc[0] = ke;
 }
 
 // ---- constrain_volume.h:26-83 ------------------------------------------------------------------------------------------------

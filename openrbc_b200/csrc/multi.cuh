@@ -129,6 +129,8 @@ inline CellOwners cell_owners(const orbc_ctx *c) {
 inline bool mg_active(const orbc_ctx *c) { return c->mg.on && c->mg.world > 1; }
 inline size_t owned_bound(const orbc_ctx *c, int sp) { return mg_active(c) ? c->mg.own_cap[sp] : c->sp[sp].n; }
 
+// every rank's partial kinetic energy (d_acc[0]) -> slot `rank` of every rank's ke_all; the caller puts a barrier behind it
+inline int mg_share_ke(orbc_ctx *c);
 inline int mg_barrier(orbc_ctx *c) {
     if (!mg_active(c)) return ORBC_OK;
     if (!c->mg.connected) return fail(ORBC_ERR_ARG, "decomposed run: orbc_mg_connect has not been called");
@@ -139,8 +141,15 @@ inline int mg_barrier(orbc_ctx *c) {
     return ORBC_OK;
 }
 
+inline int mg_share_ke(orbc_ctx *c) {
+    if (!mg_active(c)) return ORBC_OK;
+    KeDst d; for (int r = 0; r < kMaxWorld; ++r) d.dst[r] = c->mg.peers.ke_all[r];
+    ORBC_LAUNCH(c, k_share_ke, 1, 32, 0, c->d_acc, c->mg.rank, c->mg.world, d);
+    return ORBC_OK;
+}
+
 // the pointers peers write through, in a fixed order (identical on every rank)
-constexpr int kMgShared = 26;
+constexpr int kMgShared = 27;
 inline void mg_shared_list(orbc_ctx *c, void *out[kMgShared]) {
     int k = 0;
     for (int s = 0; s < 2; ++s) for (int b = 0; b < 2; ++b) {
@@ -149,7 +158,7 @@ inline void mg_shared_list(orbc_ctx *c, void *out[kMgShared]) {
     }
     out[k++] = c->mg.cen_buf[0]; out[k++] = c->mg.cen_buf[1];
     out[k++] = c->mg.cnt_all[0]; out[k++] = c->mg.cnt_all[1];
-    out[k++] = c->tag2idx; out[k++] = c->mg.flags;
+    out[k++] = c->tag2idx; out[k++] = c->mg.flags; out[k++] = c->mg.ke_all;
 }
 inline void mg_fill_peers(orbc_ctx *c, int r, void *const p[kMgShared]) {
     PeerTable &t = c->mg.peers;
@@ -160,7 +169,7 @@ inline void mg_fill_peers(orbc_ctx *c, int r, void *const p[kMgShared]) {
     }
     t.centroid[0][r] = (float4 *)p[k++]; t.centroid[1][r] = (float4 *)p[k++];
     t.cnt_all[0][r] = (int *)p[k++]; t.cnt_all[1][r] = (int *)p[k++];
-    t.tag2idx[r] = (int *)p[k++]; t.flags[r] = (unsigned *)p[k++];
+    t.tag2idx[r] = (int *)p[k++]; t.flags[r] = (unsigned *)p[k++]; t.ke_all[r] = (double *)p[k++];
 }
 
 struct MgEntry { unsigned long long raw; cudaIpcMemHandle_t handle; };

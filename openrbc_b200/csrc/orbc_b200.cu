@@ -70,7 +70,7 @@ int alloc_species(orbc_ctx *c, Species &s, size_t n) {
         ORBC_TRY(dev_alloc(&s.cells, cap)); ORBC_TRY(dev_alloc(&s.cells_tmp, cap));
         s.cap = cap;
     }
-    s.n = n; s.cur = 0; s.has_partition = false;
+    s.n = n; s.cur = 0; s.cur_xn = 0; s.has_partition = false;
     const int sp = (int)(&s - c->sp);
     ORBC_LAUNCH(c, k_set_range_const, 1, 1, 0, c->d_range + 2 * sp, 0, (int)n);   // a single GPU computes every slot
     return ORBC_OK;
@@ -95,7 +95,7 @@ GridDev grid_dev(const orbc_ctx *c) {
 int check_flags(orbc_ctx *c) {
     ORBC_CUDA(cudaMemcpyAsync(c->h_flags, c->d_flags, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     ORBC_CUDA(cudaStreamSynchronize(c->stream));
-    if (c->h_flags[0]) return fail(ORBC_ERR_STATE, "centroid stencil of cell %d holds more than %d cells", c->h_flags[0] - 1, kStencilStride);
+    if (c->h_flags[0]) return fail(ORBC_ERR_STATE, "centroid stencil of cell %d holds more than %d cells (or more than 32 closer than 6)", c->h_flags[0] - 1, kStencilStride);
     if (c->h_flags[1]) return fail(ORBC_ERR_STATE, "particle %d has no nearest centroid (NaN position?)", c->h_flags[1] - 1);
     if (c->h_flags[2]) return fail(ORBC_ERR_STATE, "protein %d carries a tag outside the tag->index map", c->h_flags[2] - 1);
     if (c->h_flags[3] > 0) return fail(ORBC_ERR_STATE, "decomposed run: rank %d never reached a barrier (rank %d waited 20 s)", c->h_flags[3] - 1, c->mg.rank);
@@ -159,6 +159,7 @@ float ff_att(float cut, float req, float eps) { return (float)(-2.0 * eps / pow_
 void fill_integ(IntegArgs &a, orbc_ctx *c, int sp, const orbc_step_params *p) {
     Species &s = c->sp[sp];
     a.x = s.X(); a.v = s.V(); a.f = s.f; a.nn = s.N(); a.o = s.O(); a.t = s.t;
+    a.x_out = a.x; a.nn_out = a.nn;
     a.n = s.n; a.species = sp;
     a.dt = (float)p->dt; a.dt_d = p->dt;
     for (int i = 0; i < kNType; ++i) a.gamma[i] = a.sigma[i] = 0.f;
@@ -170,8 +171,12 @@ void fill_integ(IntegArgs &a, orbc_ctx *c, int sp, const orbc_step_params *p) {
     a.range = c->d_range + 2 * sp;
     a.push.world = 1; a.push.cell_mask = nullptr; a.push.pmask = nullptr; a.push.cellid = nullptr;
     if (mg_active(c)) {
+        // decomposed: new x, n go to the OTHER buffer, here and on the ranks that read them as halo; peers may still be reading
+        // the current one (their forces of this step), and nobody reads the other one until the barrier after this push
         a.push.world = c->mg.world; a.push.cell_mask = c->mg.dest_mask; a.push.pmask = sp == ORBC_PROTEIN ? c->mg.pmask : nullptr; a.push.cellid = s.C();
-        for (int r = 0; r < kMaxWorld; ++r) { a.push.x[r] = c->mg.peers.x[sp][s.cur][r]; a.push.nn[r] = c->mg.peers.nn[sp][s.cur][r]; }
+        const int nb = s.cur_xn ^ 1;
+        a.x_out = s.x[nb]; a.nn_out = s.nn[nb];
+        for (int r = 0; r < kMaxWorld; ++r) { a.push.x[r] = c->mg.peers.x[sp][nb][r]; a.push.nn[r] = c->mg.peers.nn[sp][nb][r]; }
     }
 }
 
@@ -238,7 +243,14 @@ int launch_pairwise(orbc_ctx *c) {
         ProfScope ps(c, ORBC_PROF_PAIR_LIPID);
         ORBC_LAUNCH(c, k_cell_bounds, blocks_for(c->n_cells, 128), 128, 0, c->centroid, c->n_cells, L.cell_start, L.X(), P.n ? P.cell_start : nullptr, P.X(), c->lbound, c->pbound,
                     mg ? c->mg.need : (const int *)nullptr, c->mg.need_epoch);
-        if (L.n) ORBC_LAUNCH(c, k_pair_ll<true>, blocks_for(nl, kLLBlock), kLLBlock, 0, a);
+        if (L.n) {
+            switch (c->ll_variant) {     // bit 1: per-lane bounding-sphere cull of the stencil cells; bit 0: aim at 20 resident blocks per SM
+            case 0: ORBC_LAUNCH(c, (k_pair_ll<true, false, 1>), blocks_for(nl, kLLBlock), kLLBlock, 0, a, c->lbound); break;
+            case 1: ORBC_LAUNCH(c, (k_pair_ll<true, false, 20>), blocks_for(nl, kLLBlock), kLLBlock, 0, a, c->lbound); break;
+            case 2: ORBC_LAUNCH(c, (k_pair_ll<true, true, 1>), blocks_for(nl, kLLBlock), kLLBlock, 0, a, c->lbound); break;
+            default: ORBC_LAUNCH(c, (k_pair_ll<true, true, 20>), blocks_for(nl, kLLBlock), kLLBlock, 0, a, c->lbound); break;
+            }
+        }
         // lipid side of the protein-lipid pairs whose protein lives on another rank
         if (mg && L.n && P.n) ORBC_LAUNCH(c, k_pair_lipid<true>, blocks_for(nl, 128), 128, 0, a, c->mg.dest_mask);
     }
@@ -246,7 +258,11 @@ int launch_pairwise(orbc_ctx *c) {
         const CullTable ct = cull_table(c);
         if (!c->porder_valid) ORBC_TRY(build_porder(c));
         ProfScope ps(c, ORBC_PROF_PAIR_PROTEIN);
-        ORBC_LAUNCH(c, k_pair_prot, blocks_for(np, kPBlock), kPBlock, 0, a, c->lbound, c->pbound, ct, c->porder);
+        // few owned proteins (a rank of a decomposed run): more lanes per protein, shorter dependent-load chains, more warps
+        const int lanes = c->prot_lanes ? c->prot_lanes : (np <= 400000 ? 4 : 1);
+        if (lanes == 4) ORBC_LAUNCH(c, k_pair_prot<4>, blocks_for(np * 4, kPBlock), kPBlock, 0, a, c->lbound, c->pbound, ct, c->porder);
+        else if (lanes == 2) ORBC_LAUNCH(c, k_pair_prot<2>, blocks_for(np * 2, kPBlock), kPBlock, 0, a, c->lbound, c->pbound, ct, c->porder);
+        else ORBC_LAUNCH(c, k_pair_prot<1>, blocks_for(np, kPBlock), kPBlock, 0, a, c->lbound, c->pbound, ct, c->porder);
     }
     return ORBC_OK;
 }
@@ -293,7 +309,7 @@ int do_voronoi_update(orbc_ctx *c, int nstep, int freq_sort_ctrd) {
 
 // VCellList::update in three phases, so that a decomposed rebuild can run both containers through each phase between two
 // barriers.  Phase A: nearest centroid of every owned particle + arrival counts (voronoi.h:179-216), counts published.
-int cell_update_assign(orbc_ctx *c, int sp) {
+int cell_update_assign(orbc_ctx *c, int sp, const int *keep = nullptr) {
     Species &S = c->sp[sp];
     if (!c->n_cells || !c->stencil_valid) return fail(ORBC_ERR_ARG, "cell_update: no Voronoi diagram");
     const int nc = c->n_cells;
@@ -304,7 +320,7 @@ int cell_update_assign(orbc_ctx *c, int sp) {
     if (S.n) {
         const GridDev gd = grid_dev(c);
         ORBC_LAUNCH(c, k_assign_nearest, blocks_for(owned_bound(c, sp), kBlock), kBlock, 0, S.X(), S.has_partition ? S.C() : nullptr, c->d_range + 2 * sp, c->centroid, nc,
-                    c->stencil, c->stencil_cnt, gd, S.aff, S.li, cnt, c->d_counters, c->d_flags);
+                    c->stencil, c->stencil_cnt, gd, S.aff, S.li, cnt, c->d_counters, c->d_flags, keep);
     }
     if (mg) {
         CountRows rows; for (int r = 0; r < kMaxWorld; ++r) rows.dst[r] = c->mg.peers.cnt_all[sp][r];
@@ -328,17 +344,17 @@ int cell_update_move(orbc_ctx *c, int sp) {
     if (S.n) {
         const size_t nb = owned_bound(c, sp);
         ORBC_LAUNCH(c, k_cell_scatter, blocks_for(nb, kBlock), kBlock, 0, S.aff, S.li, c->d_range + 2 * sp, local_start, S.cells_tmp);
-        const int nx = S.cur ^ 1;
+        const int nx = S.cur ^ 1, nxn = S.cur_xn ^ 1;
         MoveDst d; d.own = cell_owners(c);
         for (int r = 0; r < kMaxWorld; ++r) {
-            d.x[r] = mg ? c->mg.peers.x[sp][nx][r] : S.x[nx]; d.nn[r] = mg ? c->mg.peers.nn[sp][nx][r] : S.nn[nx];
+            d.x[r] = mg ? c->mg.peers.x[sp][nxn][r] : S.x[nxn]; d.nn[r] = mg ? c->mg.peers.nn[sp][nxn][r] : S.nn[nxn];
             d.v[r] = mg ? c->mg.peers.v[sp][nx][r] : S.v[nx]; d.o[r] = mg ? c->mg.peers.o[sp][nx][r] : S.o[nx];
             d.cellid[r] = mg ? c->mg.peers.cellid[sp][nx][r] : S.cellid[nx];
             d.tag2idx[r] = mg ? c->mg.peers.tag2idx[r] : c->tag2idx;
         }
         ORBC_LAUNCH(c, k_rank_and_move, blocks_for(nb, kBlock), kBlock, 0, S.aff, c->d_range + 2 * sp, S.cell_start, local_start, off_me, S.cells_tmp, S.cells,
                     S.X(), S.N(), S.V(), S.O(), d, (mg && sp == ORBC_PROTEIN) ? 1 : 0);
-        S.cur = nx;
+        S.cur = nx; S.cur_xn = nxn;
     }
     S.has_partition = true;
     return ORBC_OK;
@@ -355,7 +371,7 @@ int cell_update_finish(orbc_ctx *c, int sp) {
         ORBC_CUDA(cudaMemsetAsync(c->mg.pmask, 0, (S.n + 3) / 4 * 4, c->stream));
         ORBC_LAUNCH(c, k_bond_mask, blocks_for(c->n_bonds, kBlock), kBlock, 0, c->bonds, c->n_bonds, c->tag2idx, c->d_range, S.cell_start, cell_owners(c), (unsigned *)c->mg.pmask);
     }
-    HaloDst d; for (int r = 0; r < kMaxWorld; ++r) { d.x[r] = c->mg.peers.x[sp][S.cur][r]; d.nn[r] = c->mg.peers.nn[sp][S.cur][r]; }
+    HaloDst d; for (int r = 0; r < kMaxWorld; ++r) { d.x[r] = c->mg.peers.x[sp][S.cur_xn][r]; d.nn[r] = c->mg.peers.nn[sp][S.cur_xn][r]; }
     ORBC_LAUNCH(c, k_halo_push, blocks_for(owned_bound(c, sp), kBlock), kBlock, 0, c->d_range + 2 * sp, c->mg.dest_mask, sp == ORBC_PROTEIN ? c->mg.pmask : (const unsigned char *)nullptr,
                 S.C(), S.X(), S.N(), d);
     return ORBC_OK;
@@ -367,8 +383,9 @@ int do_cell_update(orbc_ctx *c, int sp) {
     ORBC_TRY(cell_update_finish(c, sp)); return mg_barrier(c);
 }
 
-int do_integrate_langevin(orbc_ctx *c, const orbc_step_params *p) {
-    ORBC_TRY(mg_barrier(c));                                     // every rank has finished reading the halo it is about to overwrite
+// `rebuild_follows`: the caller rebuilds next; the first barrier of the rebuild then also covers the arrival of this push
+int do_integrate_langevin(orbc_ctx *c, const orbc_step_params *p, bool rebuild_follows = false) {
+    // decomposed: no barrier before the push — it goes to the x, n buffers nobody is reading (fill_integ)
     {
         ProfScope ps(c, ORBC_PROF_INTEGRATE);
         for (int sp = 0; sp < 2; ++sp) {
@@ -382,9 +399,10 @@ int do_integrate_langevin(orbc_ctx *c, const orbc_step_params *p) {
                 a.noise = c->noise[sp];
             }
             ORBC_LAUNCH(c, k_verlet_langevin, blocks_for(owned_bound(c, sp), 256), 256, 0, a);
+            if (mg_active(c)) S.cur_xn ^= 1;
         }
     }
-    return mg_barrier(c);                                        // the pushed halo has landed everywhere
+    return rebuild_follows ? ORBC_OK : mg_barrier(c);            // the pushed halo has landed everywhere
 }
 
 // CUDA loads kernels lazily, and loading one may wait for the device to go idle — a rank spinning in k_mg_barrier while its
@@ -397,11 +415,10 @@ int preload_kernels() {
     ORBC_PRELOAD(k_centroid_update); ORBC_PRELOAD(k_clear_force); ORBC_PRELOAD(k_compact); ORBC_PRELOAD(k_cv_apply); ORBC_PRELOAD(k_cv_center);
     ORBC_PRELOAD(k_cv_normal_volume); ORBC_PRELOAD(k_fill_cellid); ORBC_PRELOAD(k_fill_int); ORBC_PRELOAD(k_halo_push); ORBC_PRELOAD(k_kinetic);
     ORBC_PRELOAD(k_mg_barrier); ORBC_PRELOAD(k_morton_keys); ORBC_PRELOAD(k_morton_keys_only); ORBC_PRELOAD(k_nh_final); ORBC_PRELOAD(k_nh_final_fused);
-    ORBC_PRELOAD(k_nh_initial_fused); ORBC_PRELOAD(k_nh_zeta_update); ORBC_PRELOAD(k_noise); ORBC_PRELOAD(k_opt_move); ORBC_PRELOAD(k_pack4);
-    ORBC_PRELOAD(k_pair_lipid<true>); ORBC_PRELOAD(k_pair_lipid<false>); ORBC_PRELOAD(k_pair_ll<true>); ORBC_PRELOAD(k_pair_prot); ORBC_PRELOAD(k_pair_protein);
+    ORBC_PRELOAD(k_nh_initial_fused); ORBC_PRELOAD(k_nh_zeta_update); ORBC_PRELOAD(k_share_ke); ORBC_PRELOAD(k_sum_ke); ORBC_PRELOAD(k_noise); ORBC_PRELOAD(k_opt_move); ORBC_PRELOAD(k_pack4);
+    ORBC_PRELOAD(k_pair_lipid<true>); ORBC_PRELOAD(k_pair_lipid<false>); ORBC_PRELOAD((k_pair_ll<true, false, 1>)); ORBC_PRELOAD((k_pair_ll<true, false, 20>)); ORBC_PRELOAD((k_pair_ll<true, true, 1>)); ORBC_PRELOAD((k_pair_ll<true, true, 20>)); ORBC_PRELOAD(k_pair_prot<1>); ORBC_PRELOAD(k_pair_prot<2>); ORBC_PRELOAD(k_pair_prot<4>); ORBC_PRELOAD(k_pair_protein);
     ORBC_PRELOAD(k_permute_centroids); ORBC_PRELOAD(k_porder_flag); ORBC_PRELOAD(k_porder_scatter); ORBC_PRELOAD(k_post_torque); ORBC_PRELOAD(k_radix_hist);
-    ORBC_PRELOAD(k_radix_scatter); ORBC_PRELOAD(k_rank_and_move); ORBC_PRELOAD(k_remap_cellid); ORBC_PRELOAD(k_scan_apply); ORBC_PRELOAD(k_scan_sums);
-    ORBC_PRELOAD(k_scan_tile_sums); ORBC_PRELOAD(k_set3); ORBC_PRELOAD(k_set_range); ORBC_PRELOAD(k_set_range_const); ORBC_PRELOAD(k_share_counts);
+    ORBC_PRELOAD(k_radix_scatter); ORBC_PRELOAD(k_rank_and_move); ORBC_PRELOAD(k_remap_cellid); ORBC_PRELOAD(k_scan_onepass); ORBC_PRELOAD(k_set3); ORBC_PRELOAD(k_set_range); ORBC_PRELOAD(k_set_range_const); ORBC_PRELOAD(k_share_counts);
     ORBC_PRELOAD(k_stencil_build); ORBC_PRELOAD(k_stray_mask); ORBC_PRELOAD(k_unpack3); ORBC_PRELOAD(k_unpack_w); ORBC_PRELOAD(k_verlet_langevin); ORBC_PRELOAD(k_zero4);
 #undef ORBC_PRELOAD
     return ORBC_OK;
@@ -496,11 +513,12 @@ void orbc_destroy(orbc_ctx *c) { if (c) cudaSetDevice(c->device);
     dev_free(c->scan_tmp); dev_free(c->radix_hist); dev_free(c->stage); dev_free(c->d_acc); dev_free(c->d_counters); dev_free(c->d_flags); dev_free(c->d_nh);
     dev_free(c->noise[0]); dev_free(c->noise[1]); dev_free(c->d_range);
     for (void *m : c->mg.opened) cudaIpcCloseMemHandle(m);
-    dev_free(c->mg.flags); dev_free(c->mg.dest_mask); dev_free(c->mg.pmask); dev_free(c->mg.need);
+    dev_free(c->mg.keep); dev_free(c->mg.ke_all); dev_free(c->mg.flags); dev_free(c->mg.dest_mask); dev_free(c->mg.pmask); dev_free(c->mg.need);
     for (int s = 0; s < 2; ++s) { dev_free(c->mg.cnt_all[s]); dev_free(c->mg.off_me[s]); dev_free(c->mg.local_start[s]); }
     if (c->h_acc) cudaFreeHost(c->h_acc); if (c->h_flags) cudaFreeHost(c->h_flags); if (c->h_counters) cudaFreeHost(c->h_counters); if (c->h_nh) cudaFreeHost(c->h_nh);
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
     for (auto &v : c->prof_ev) for (auto &e : v) cudaEventDestroy(e);
+    for (auto &e : c->kprof_ev) cudaEventDestroy(e);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -508,6 +526,16 @@ void orbc_destroy(orbc_ctx *c) { if (c) cudaSetDevice(c->device);
 int orbc_set_option(orbc_ctx *c, const char *name, double value) { if (c) cudaSetDevice(c->device);
     if (!c || !name) return fail(ORBC_ERR_ARG, "null argument");
     if (!strcmp(name, "pair_impl")) { if (value != 1 && value != 2) return fail(ORBC_ERR_ARG, "pair_impl must be 1 or 2"); c->pair_impl = (int)value; return ORBC_OK; }
+    if (!strcmp(name, "prot_lanes")) { if (value != 0 && value != 1 && value != 2 && value != 4) return fail(ORBC_ERR_ARG, "prot_lanes must be 0 (automatic), 1, 2 or 4"); c->prot_lanes = (int)value; return ORBC_OK; }
+    if (!strcmp(name, "ll_variant")) { c->ll_variant = (int)value & 3; return ORBC_OK; }   // tuning variants of k_pair_ll (see launch_pairwise)
+    if (!strcmp(name, "debug_owned_fraction")) {
+        // test / profiling aid: compute only the first `value` of the slots of both containers, as one rank of a decomposed run
+        // would (forces and integration of the other slots are skipped; results are partial by construction)
+        if (!(value > 0.0 && value <= 1.0)) return fail(ORBC_ERR_ARG, "debug_owned_fraction must be in (0, 1]");
+        for (int sp = 0; sp < 2; ++sp) ORBC_LAUNCH(c, k_set_range_const, 1, 1, 0, c->d_range + 2 * sp, 0, (int)(c->sp[sp].n * value));
+        c->porder_valid = false;
+        return ORBC_OK;
+    }
     return fail(ORBC_ERR_ARG, "unknown option '%s'", name);
 }
 
@@ -648,22 +676,37 @@ int orbc_rebuild(orbc_ctx *c, int nstep, int freq_sort_ctrd, int freq_sort_bond)
 int orbc_delete_lipid(orbc_ctx *c, float tol, size_t *n_out) { if (c) cudaSetDevice(c->device);
     if (!c) return fail(ORBC_ERR_ARG, "null ctx");
     Species &L = c->sp[0];
-    ORBC_TRY(single_gpu_only(c, "delete_lipid"));
     if (!L.has_partition) return fail(ORBC_ERR_ARG, "delete_lipid: lipids are not partitioned");
     const int nc = c->n_cells;
     const size_t n = L.n;
+    if (mg_active(c)) {
+        // decomposed: every rank masks the strays of its own cells, then the lipid cell update runs with the mask — a deleted
+        // lipid is not counted and not moved, so the survivors close ranks in the global slot order (order-preserving
+        // compaction + cell_lipid.update of cleanup.h:62-85 in one pass).  All ranks learn the new size from the same cell_start.
+        if (c->mg.ce > c->mg.cb)
+            ORBC_LAUNCH(c, k_stray_mask, blocks_for((size_t)(c->mg.ce - c->mg.cb) * 32, kBlock), kBlock, 0, L.cell_start, c->mg.cb, c->mg.ce, c->centroid, L.X(), tol, c->mg.keep);
+        ORBC_TRY(cell_update_assign(c, ORBC_LIPID, c->mg.keep)); ORBC_TRY(mg_barrier(c));
+        ORBC_TRY(cell_update_move(c, ORBC_LIPID));               ORBC_TRY(mg_barrier(c));
+        ORBC_TRY(cell_update_finish(c, ORBC_LIPID));             ORBC_TRY(mg_barrier(c));
+        int total = 0;
+        ORBC_CUDA(cudaMemcpyAsync(&total, L.cell_start + nc, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        ORBC_CUDA(cudaStreamSynchronize(c->stream));
+        L.n = (size_t)total;
+        if (n_out) *n_out = L.n;
+        return check_flags(c);
+    }
     int *keep = L.aff, *newpos = L.li;
-    ORBC_LAUNCH(c, k_stray_mask, blocks_for((size_t)nc * 32, kBlock), kBlock, 0, L.cell_start, nc, c->centroid, L.X(), tol, keep);
+    ORBC_LAUNCH(c, k_stray_mask, blocks_for((size_t)nc * 32, kBlock), kBlock, 0, L.cell_start, 0, nc, c->centroid, L.X(), tol, keep);
     ORBC_CUDA(cudaMemcpyAsync(newpos, keep, sizeof(int) * n, cudaMemcpyDeviceToDevice, c->stream));
     ORBC_TRY(scan_exclusive(c, newpos, (int)n));
     int total = 0;
     ORBC_CUDA(cudaMemcpyAsync(&total, newpos + n, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     ORBC_CUDA(cudaStreamSynchronize(c->stream));
     if ((size_t)total < n) {
-        const int nx = L.cur ^ 1;
+        const int nx = L.cur ^ 1, nxn = L.cur_xn ^ 1;
         ORBC_LAUNCH(c, k_compact, blocks_for(n, kBlock), kBlock, 0, keep, newpos, n, L.X(), L.N(), L.V(), L.O(), L.C(),
-                    L.x[nx], L.nn[nx], L.v[nx], L.o[nx], L.cellid[nx]);
-        L.cur = nx; L.n = (size_t)total;
+                    L.x[nxn], L.nn[nxn], L.v[nx], L.o[nx], L.cellid[nx]);
+        L.cur = nx; L.cur_xn = nxn; L.n = (size_t)total;
         ORBC_LAUNCH(c, k_set_range_const, 1, 1, 0, c->d_range, 0, total);
         // f and t are zero at this point of the loop (cleared by the integrator); keep them so for the survivors
         ORBC_LAUNCH(c, k_zero4, blocks_for(n, kBlock), kBlock, 0, L.f, n, (const int *)nullptr);
@@ -709,19 +752,20 @@ int orbc_integrate(orbc_ctx *c, int kernel, const orbc_step_params *p, orbc_step
     if (needs_p && !p) return fail(ORBC_ERR_ARG, "orbc_integrate: this kernel needs step parameters");
     const bool reduces = kernel == ORBC_NH_INITIAL_FUSED || kernel == ORBC_NH_FINAL_FUSED || kernel == ORBC_NH_UPDATE;
     if (reduces) ORBC_CUDA(cudaMemsetAsync(c->d_acc, 0, sizeof(double), c->stream));
-    if (kernel != ORBC_VERLET_LANGEVIN && kernel != ORBC_CLEAR_FORCE) ORBC_TRY(single_gpu_only(c, "this integrate() kernel"));
+    const bool mg_ok = kernel == ORBC_VERLET_LANGEVIN || kernel == ORBC_CLEAR_FORCE || kernel == ORBC_NH_INITIAL_FUSED || kernel == ORBC_NH_FINAL_FUSED;
+    if (!mg_ok) ORBC_TRY(single_gpu_only(c, "this integrate() kernel"));
     if (kernel == ORBC_VERLET_LANGEVIN) ORBC_TRY(do_integrate_langevin(c, p));
     else for (int sp = 0; sp < 2; ++sp) {
         Species &S = c->sp[sp];
         if (!S.n) continue;
-        const unsigned nb = blocks_for(S.n, 256);
+        const unsigned nb = blocks_for(owned_bound(c, sp), 256);
         IntegArgs a;
         if (p) fill_integ(a, c, sp, p);
         switch (kernel) {
         case ORBC_CLEAR_FORCE: ORBC_LAUNCH(c, k_clear_force, nb, 256, 0, S.f, S.t, S.n); break;
         case ORBC_POST_TORQUE: ORBC_LAUNCH(c, k_post_torque, nb, 256, 0, S.N(), S.t, S.n); break;
         case ORBC_BOUNCE_BACK: ORBC_LAUNCH(c, k_bounce_back, nb, 256, 0, a); break;
-        case ORBC_NH_INITIAL_FUSED: ORBC_LAUNCH(c, k_nh_initial_fused, nb, 256, 0, a); break;
+        case ORBC_NH_INITIAL_FUSED: ORBC_LAUNCH(c, k_nh_initial_fused, nb, 256, 0, a); if (mg_active(c)) S.cur_xn ^= 1; break;
         case ORBC_NH_FINAL_FUSED: ORBC_LAUNCH(c, k_nh_final_fused, nb, 256, 0, a); break;
         case ORBC_NH_FINAL: ORBC_LAUNCH(c, k_nh_final, nb, 256, 0, a); break;
         case ORBC_NH_UPDATE: ORBC_LAUNCH(c, k_kinetic, nb, 256, 0, S.X(), S.V(), c->d_range + 2 * sp, 0.5f, c->d_acc); break;
@@ -729,6 +773,11 @@ int orbc_integrate(orbc_ctx *c, int kernel, const orbc_step_params *p, orbc_step
         default: return fail(ORBC_ERR_ARG, "orbc_integrate: unknown kernel id %d", kernel);
         }
     }
+    if (mg_active(c) && reduces) {
+        // the partial sums of all ranks, added in rank order on every rank; the barrier is also the one behind the halo push
+        ORBC_TRY(mg_share_ke(c)); ORBC_TRY(mg_barrier(c));
+        ORBC_LAUNCH(c, k_sum_ke, 1, 32, 0, c->d_acc, c->mg.ke_all, c->mg.world);
+    } else if (mg_active(c) && kernel == ORBC_NH_INITIAL_FUSED) ORBC_TRY(mg_barrier(c));
     if (res) {
         res->ke = 0.0; res->n = (long)(c->sp[0].n + c->sp[1].n);
         if (reduces) {
@@ -763,33 +812,39 @@ int orbc_run_langevin(orbc_ctx *c, const orbc_step_params *p, int n_steps, int f
         if (q.nstep % freq_voronoi == 0) ORBC_TRY(do_rebuild(c, q.nstep, freq_sort_ctrd));
         ORBC_TRY(launch_pairwise(c));
         ORBC_TRY(launch_bonded(c));
-        ORBC_TRY(do_integrate_langevin(c, &q));
+        ORBC_TRY(do_integrate_langevin(c, &q, s + 1 < n_steps && (q.nstep + 1) % freq_voronoi == 0));
     }
     return ORBC_OK;
 }
 
 int orbc_run_nh(orbc_ctx *c, const orbc_step_params *p, int n_steps, int freq_voronoi, int freq_sort_ctrd, float *zeta_io, float *Q_io) { if (c) cudaSetDevice(c->device);
     if (!c || !p || !zeta_io || !Q_io || freq_voronoi <= 0) return fail(ORBC_ERR_ARG, "orbc_run_nh: bad argument");
-    ORBC_TRY(single_gpu_only(c, "orbc_run_nh"));
     c->h_nh[0] = *zeta_io; c->h_nh[1] = *Q_io;
     ORBC_CUDA(cudaMemcpyAsync(c->d_nh, c->h_nh, 2 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     ORBC_CUDA(cudaMemsetAsync(c->d_acc, 0, sizeof(double), c->stream));
     orbc_step_params q = *p;
     const long n = (long)(c->sp[0].n + c->sp[1].n);
+    const bool mg = mg_active(c);
+    const double *ke_all = mg ? c->mg.ke_all : nullptr;
+    const int world = mg ? c->mg.world : 1;
     for (int s = 0; s < n_steps; ++s, ++q.nstep) {
         for (int sp = 0; sp < 2; ++sp) if (c->sp[sp].n) {
             IntegArgs a; fill_integ(a, c, sp, &q); a.zeta_dev = c->d_nh;
-            ORBC_LAUNCH(c, k_nh_initial_fused, blocks_for(c->sp[sp].n, 256), 256, 0, a);
+            ORBC_LAUNCH(c, k_nh_initial_fused, blocks_for(owned_bound(c, sp), 256), 256, 0, a);
+            if (mg) c->sp[sp].cur_xn ^= 1;
         }
-        ORBC_LAUNCH(c, k_nh_zeta_update, 1, 32, 0, c->d_nh, c->d_acc, q.dt, q.kBT, n);
+        // decomposed: one barrier stands behind both the halo push of the drift and the exchange of the partial kinetic energies
+        ORBC_TRY(mg_share_ke(c)); ORBC_TRY(mg_barrier(c));
+        ORBC_LAUNCH(c, k_nh_zeta_update, 1, 32, 0, c->d_nh, c->d_acc, q.dt, q.kBT, n, ke_all, world);
         if (q.nstep % freq_voronoi == 0) ORBC_TRY(do_rebuild(c, q.nstep, freq_sort_ctrd));
         ORBC_TRY(launch_pairwise(c));
         ORBC_TRY(launch_bonded(c));
         for (int sp = 0; sp < 2; ++sp) if (c->sp[sp].n) {
             IntegArgs a; fill_integ(a, c, sp, &q); a.zeta_dev = c->d_nh;
-            ORBC_LAUNCH(c, k_nh_final_fused, blocks_for(c->sp[sp].n, 256), 256, 0, a);
+            ORBC_LAUNCH(c, k_nh_final_fused, blocks_for(owned_bound(c, sp), 256), 256, 0, a);
         }
-        ORBC_LAUNCH(c, k_nh_zeta_update, 1, 32, 0, c->d_nh, c->d_acc, q.dt, q.kBT, n);
+        ORBC_TRY(mg_share_ke(c)); ORBC_TRY(mg_barrier(c));
+        ORBC_LAUNCH(c, k_nh_zeta_update, 1, 32, 0, c->d_nh, c->d_acc, q.dt, q.kBT, n, ke_all, world);
     }
     ORBC_CUDA(cudaMemcpyAsync(c->h_nh, c->d_nh, 2 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     ORBC_CUDA(cudaStreamSynchronize(c->stream));
@@ -838,12 +893,15 @@ int orbc_mg_export(orbc_ctx *c, void *blob_out, size_t bytes) { if (c) cudaSetDe
             ORBC_CUDA(cudaMemsetAsync(m.cnt_all[sp], 0, sizeof(int) * (size_t)w * (nc + 1), c->stream));
         }
         ORBC_TRY(dev_alloc(&m.flags, kMaxWorld)); ORBC_CUDA(cudaMemsetAsync(m.flags, 0, sizeof(unsigned) * kMaxWorld, c->stream));
+        ORBC_TRY(dev_alloc(&m.ke_all, kMaxWorld)); ORBC_CUDA(cudaMemsetAsync(m.ke_all, 0, sizeof(double) * kMaxWorld, c->stream));
         ORBC_TRY(dev_alloc(&m.dest_mask, nc)); ORBC_CUDA(cudaMemsetAsync(m.dest_mask, 0, nc, c->stream));
         ORBC_TRY(dev_alloc(&m.pmask, P.n + 4)); ORBC_CUDA(cudaMemsetAsync(m.pmask, 0, P.n + 4, c->stream));
         ORBC_TRY(dev_alloc(&m.need, nc)); ORBC_CUDA(cudaMemsetAsync(m.need, 0, sizeof(int) * nc, c->stream));
+        ORBC_TRY(dev_alloc(&m.keep, L.n + 1));
         m.cen_buf[0] = c->centroid; m.cen_buf[1] = c->centroid_tmp; m.cen_par = 0; m.epoch = 0;
         // scratch that the single-GPU path allocates on first use: allocate it now, no cudaMalloc while peers spin in a barrier
-        if (c->scan_tmp_cap < 65537) { ORBC_TRY(dev_alloc(&c->scan_tmp, 65537)); c->scan_tmp_cap = 65537; }
+        ORBC_CUDA(cudaMemsetAsync(m.off_me[0], 0, 2 * sizeof(int), c->stream));
+        ORBC_TRY(scan_exclusive(c, m.off_me[0], 1));             // allocates the scan's descriptors
         const size_t hist_n = (size_t)256 * ((nc + kRadixTile - 1) / kRadixTile) + 1;
         if (c->radix_hist_cap < hist_n) { ORBC_TRY(dev_alloc(&c->radix_hist, hist_n)); c->radix_hist_cap = hist_n; }
         if (c->porder_cap < m.own_cap[1] + 1) { ORBC_TRY(dev_alloc(&c->porder, m.own_cap[1] + 1)); c->porder_cap = m.own_cap[1] + 1; }
@@ -1014,6 +1072,36 @@ int orbc_profile_read(orbc_ctx *c, int cls, double *total_ms, unsigned long long
     for (size_t k = 0; k < pairs; ++k) { float ms = 0.f; ORBC_CUDA(cudaEventElapsedTime(&ms, c->prof_ev[cls][2 * k], c->prof_ev[cls][2 * k + 1])); sum += ms; }
     *total_ms = sum; *count = pairs;
     c->prof_used[cls] = 0;
+    return ORBC_OK;
+}
+int orbc_profile_kernels(orbc_ctx *c, int on) {
+    if (c) cudaSetDevice(c->device);
+    if (!c) return fail(ORBC_ERR_ARG, "null ctx");
+    ORBC_CUDA(cudaStreamSynchronize(c->stream));
+    c->kprof_on = on != 0; c->kprof_used = 0;
+    return ORBC_OK;
+}
+int orbc_profile_kernels_report(orbc_ctx *c, char *text, size_t bytes) {
+    if (c) cudaSetDevice(c->device);
+    if (!c || !text || !bytes) return fail(ORBC_ERR_ARG, "orbc_profile_kernels_report: bad argument");
+    ORBC_CUDA(cudaStreamSynchronize(c->stream));
+    struct Row { const char *name; double us; unsigned long long n; };
+    std::vector<Row> rows;
+    for (size_t k = 0; k + 1 < c->kprof_used; k += 2) {
+        float ms = 0.f; ORBC_CUDA(cudaEventElapsedTime(&ms, c->kprof_ev[k], c->kprof_ev[k + 1]));
+        const char *nm = c->kprof_name[k / 2];
+        size_t r = 0; while (r < rows.size() && strcmp(rows[r].name, nm)) ++r;
+        if (r == rows.size()) rows.push_back({nm, 0.0, 0});
+        rows[r].us += 1e3 * ms; rows[r].n++;
+    }
+    std::sort(rows.begin(), rows.end(), [](const Row &a, const Row &b) { return a.us > b.us; });
+    size_t off = 0; text[0] = 0;
+    for (const Row &r : rows) {
+        const int w = snprintf(text + off, bytes - off, "%s %llu %.1f\n", r.name, r.n, r.us);
+        if (w < 0 || (size_t)w >= bytes - off) break;
+        off += (size_t)w;
+    }
+    c->kprof_used = 0;
     return ORBC_OK;
 }
 int orbc_launch_count(orbc_ctx *c, unsigned long long *n) { if (c) cudaSetDevice(c->device); if (!c || !n) return fail(ORBC_ERR_ARG, "bad argument"); *n = c->launches; return ORBC_OK; }

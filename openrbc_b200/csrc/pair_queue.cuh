@@ -81,41 +81,45 @@ __device__ __forceinline__ float rsqrt_fast(float x) {      // x is a squared di
 __device__ __forceinline__ void sts_i32(unsigned addr, int v) { asm volatile("st.shared.b32 [%0], %1;" :: "r"(addr), "r"(v) : "memory"); }
 __device__ __forceinline__ int lds_i32(unsigned addr) { int v; asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory"); return v; }
 
-// pairwise_kernel.h:30-68 for particle 1 only (the gathering side): force and torque accumulate straight into the running sums
+// pairwise_kernel.h:30-68 for particle 1 only (the gathering side), in coefficient form.  With u = d / r, p_k = n_k - (n_k.u) u:
+//   f_i  = F_r u + (alpha ua / r) [ (n_j.u) p_i + (n_i.u) p_j ]  =  A1 d + C n_j + B n_i
+//   t_i -= alpha ua p_j                                          =>  t_i += -aua n_j + B d
+// with aua = alpha att rc^4, B = aua (n_j.u) / r, C = aua (n_i.u) / r, A1 = (F_r - 2 aua (n_i.u)(n_j.u) / r) / r.
+// n_i is the lane's own director, so its coefficient is summed as ONE scalar (sB) and applied after the loop.
 struct LLConst { float cut, rep8, att4, alpha, alpha_att, one_m_alpha; };
 __device__ __forceinline__ void ll_eval(const LLConst &k, const float4 *__restrict__ xl, const float4 *__restrict__ nl, F3 xi, F3 mi, int j,
-                                        float &fx, float &fy, float &fz, float &tx, float &ty, float &tz) {
+                                        float &fx, float &fy, float &fz, float &tx, float &ty, float &tz, float &sB) {
     const float4 xj = __ldg(xl + j), nj = __ldg(nl + j);
     const float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
     const float r2 = dx * dx + dy * dy + dz * dz;
     const float rinv = rsqrt_fast(r2);
     const float r = r2 * rinv;
-    const float ux = dx * rinv, uy = dy * rinv, uz = dz * rinv;
     const float ninj = mi.x * nj.x + mi.y * nj.y + mi.z * nj.z;
-    const float niu = mi.x * ux + mi.y * uy + mi.z * uz;
-    const float nju = nj.x * ux + nj.y * uy + nj.z * uz;
-    const float A = fmaf(k.alpha, ninj - niu * nju, k.one_m_alpha);        // 1 + alpha (a - 1)
+    const float niu = (mi.x * dx + mi.y * dy + mi.z * dz) * rinv;
+    const float nju = (nj.x * dx + nj.y * dy + nj.z * dz) * rinv;
+    const float A = fmaf(k.alpha, fmaf(-niu, nju, ninj), k.one_m_alpha);   // 1 + alpha (a - 1)
     const float rc = k.cut - r;
     const float rc2 = rc * rc, rc3 = rc2 * rc, rc4 = rc2 * rc2;
     const float fra = fmaf(k.rep8, rc3 * rc4, k.att4 * (A * rc3));         // 8 rep rc^7 + 4 A att rc^3
     const float aua = k.alpha_att * rc4;                                    // alpha * att * rc^4
     const float auar = aua * rinv;
-    const float pix = mi.x - niu * ux, piy = mi.y - niu * uy, piz = mi.z - niu * uz;
-    const float pjx = nj.x - nju * ux, pjy = nj.y - nju * uy, pjz = nj.z - nju * uz;
-    fx = fmaf(fra, ux, fx); fy = fmaf(fra, uy, fy); fz = fmaf(fra, uz, fz);
-    fx = fmaf(auar, fmaf(nju, pix, niu * pjx), fx); fy = fmaf(auar, fmaf(nju, piy, niu * pjy), fy); fz = fmaf(auar, fmaf(nju, piz, niu * pjz), fz);
-    tx = fmaf(-aua, pjx, tx); ty = fmaf(-aua, pjy, ty); tz = fmaf(-aua, pjz, tz);
+    const float B = auar * nju, C = auar * niu;
+    const float A1 = fmaf(-2.0f * C, nju, fra) * rinv;
+    fx = fmaf(A1, dx, fmaf(C, nj.x, fx)); fy = fmaf(A1, dy, fmaf(C, nj.y, fy)); fz = fmaf(A1, dz, fmaf(C, nj.z, fz));
+    tx = fmaf(B, dx, fmaf(-aua, nj.x, tx)); ty = fmaf(B, dy, fmaf(-aua, nj.y, ty)); tz = fmaf(B, dz, fmaf(-aua, nj.z, tz));
+    sB += B;
 }
 
 // One thread per lipid.  A lane's candidates are the members of the cells in the r<6 stencil of its own cell; the lane walks
 // them as ONE stream, four at a time, independent of what the other lanes of the warp are looking at (lanes of one warp
 // belong to ~3 different cells with different stencils and different cell sizes — aligning them slot by slot would make every
-// lane wait for the largest cell of every slot).  The stream never stalls on the stencil: the range of the next cell and the id
-// of the one after it are prefetched two advances ahead.
+// lane wait for the largest cell of every slot).
+//   phase 0  cull: a stencil cell whose bounding sphere (k_cell_bounds) stays further than the cutoff from THIS lipid cannot
+//            hold a partner; the surviving cells are a bit mask, so culled cells cost no loop iteration
 //   phase 1  test the cutoff, push hits on the lane's queue (shared memory, slot-major: conflict-free)
 //   phase 2  drain the queue through the force body on dense lanes; the whole warp drains early if a queue could overflow
-template <bool ACCUM>
-__global__ void __launch_bounds__(kLLBlock) k_pair_ll(PairArgs a) {
+template <bool ACCUM, bool CULL, int MINB>
+__global__ void __launch_bounds__(kLLBlock, MINB) k_pair_ll(PairArgs a, const float4 *__restrict__ lbound) {
     __shared__ int s_q[kLLBlock / 32][kQCap * 32];
     const int lane = threadIdx.x & 31;
     int *const q = s_q[threadIdx.x >> 5] + lane;
@@ -124,39 +128,52 @@ __global__ void __launch_bounds__(kLLBlock) k_pair_ll(PairArgs a) {
     const float4 *__restrict__ xl = a.xl;
     const float4 *__restrict__ nl = a.nl;
     const int *__restrict__ cs = a.cs_l;
-    float fx = 0, fy = 0, fz = 0, tx = 0, ty = 0, tz = 0;
+    float fx = 0, fy = 0, fz = 0, tx = 0, ty = 0, tz = 0, sB = 0;
     F3 xi = {0, 0, 0}, mi = {0, 0, 0};
-    int n6 = 0;
     const int *st = a.stencil;
+    const float cutsq = c_ff.cutsqll;
+    const LLConst kc = {c_ff.cutll, 8.0f * c_ff.repll, 4.0f * c_ff.attll, c_ff.alphall, c_ff.alphall * c_ff.attll, 1.0f - c_ff.alphall};
+    unsigned keep = 0;                                           // stencil slots (<= 32 of the r<6 class) still to visit
     if (live) {
         const float4 xi4 = xl[i], ni4 = nl[i];
         xi = {xi4.x, xi4.y, xi4.z}; mi = {ni4.x, ni4.y, ni4.z};
         const int c = a.cell_l[i];
-        n6 = a.stencil_cnt[c] & 255;
+        const int n6 = min(a.stencil_cnt[c] & 255, 32);
         st += (size_t)c * kStencilStride;
+        if (CULL) {
+            // four stencil slots at a time, ids first, then their spheres, then the tests: two round trips to memory per four cells
+            for (int k0 = 0; k0 < n6; k0 += 4) {
+                int c2[4]; float4 b[4];
+                #pragma unroll
+                for (int u = 0; u < 4; ++u) c2[u] = __ldg(st + min(k0 + u, n6 - 1));
+                #pragma unroll
+                for (int u = 0; u < 4; ++u) b[u] = __ldg(lbound + c2[u]);
+                #pragma unroll
+                for (int u = 0; u < 4; ++u) if (k0 + u < n6 && !culled(b[u], xi.x, xi.y, xi.z, kc.cut)) keep |= 1u << (k0 + u);
+            }
+        } else keep = n6 >= 32 ? 0xffffffffu : (1u << n6) - 1u;
     }
-    const float cutsq = c_ff.cutsqll;
-    const LLConst kc = {c_ff.cutll, 8.0f * c_ff.repll, 4.0f * c_ff.attll, c_ff.alphall, c_ff.alphall * c_ff.attll, 1.0f - c_ff.alphall};
     // the lane's hit queue, addressed with 32-bit shared-window addresses (slot stride = 32 lanes x 4 B)
     const unsigned q0 = (unsigned)__cvta_generic_to_shared(q);
     const unsigned q_full = q0 + (kQCap - 4) * 128;              // a group of four always fits below this mark
     unsigned qp = q0;
-    // prefetch pipeline: (jb_n, len_n) = range of stencil slot `taken`, c2_nn = cell id of slot `taken + 1`
-    int taken = 0, jb_n = 0, len_n = 0, c2_nn = 0;
-    if (n6 > 0) { const int c2 = __ldg(st); jb_n = __ldg(cs + c2); len_n = __ldg(cs + c2 + 1) - jb_n; }
-    if (n6 > 1) c2_nn = __ldg(st + 1);
+    // two-deep prefetch so that the stream never waits for the stencil: (jb_n, len_n) = member range of the next cell to
+    // visit, c2_nn = id of the one after it; n_next = cells not yet entered
+    int n_next = __popc(keep), jb_n = 0, len_n = 0, c2_nn = 0;
+    if (n_next > 0) { const int c2 = __ldg(st + (__ffs(keep) - 1)); keep &= keep - 1; jb_n = __ldg(cs + c2); len_n = __ldg(cs + c2 + 1) - jb_n; }
+    if (n_next > 1) { c2_nn = __ldg(st + (__ffs(keep) - 1)); keep &= keep - 1; }
     // cur stays a valid index for idle lanes: loads are unconditional, only the queue push is predicated (the arrays are
     // allocated with 64 spare elements, so reading up to three elements past a cell's range is always in bounds)
     int cur = 0, rem = 0;
     for (;;) {
-        if (rem <= 0 && taken < n6) {                            // advance to the next cell of the stencil
-            cur = jb_n; rem = len_n; ++taken;
-            if (taken < n6) { jb_n = __ldg(cs + c2_nn); len_n = __ldg(cs + c2_nn + 1) - jb_n; }
-            if (taken + 1 < n6) c2_nn = __ldg(st + taken + 1);
+        if (rem <= 0 && n_next > 0) {                            // advance to the next cell of the stencil
+            cur = jb_n; rem = len_n; --n_next;
+            if (n_next > 0) { jb_n = __ldg(cs + c2_nn); len_n = __ldg(cs + c2_nn + 1) - jb_n; }
+            if (n_next > 1) { c2_nn = __ldg(st + (__ffs(keep) - 1)); keep &= keep - 1; }
         }
-        if (!__any_sync(0xffffffffu, rem > 0 || taken < n6)) break;
+        if (!__any_sync(0xffffffffu, rem > 0 || n_next > 0)) break;
         if (__any_sync(0xffffffffu, qp > q_full)) {              // make room: every lane drains its queue (dense)
-            for (unsigned e = q0; e < qp; e += 128) ll_eval(kc, xl, nl, xi, mi, lds_i32(e), fx, fy, fz, tx, ty, tz);
+            for (unsigned e = q0; e < qp; e += 128) ll_eval(kc, xl, nl, xi, mi, lds_i32(e), fx, fy, fz, tx, ty, tz, sB);
             qp = q0;
         }
         const float4 *__restrict__ p = xl + cur;
@@ -172,7 +189,8 @@ __global__ void __launch_bounds__(kLLBlock) k_pair_ll(PairArgs a) {
         if (rem > 0) cur += 4;
         rem -= 4;
     }
-    for (unsigned e = q0; e < qp; e += 128) ll_eval(kc, xl, nl, xi, mi, lds_i32(e), fx, fy, fz, tx, ty, tz);
+    for (unsigned e = q0; e < qp; e += 128) ll_eval(kc, xl, nl, xi, mi, lds_i32(e), fx, fy, fz, tx, ty, tz, sB);
+    fx = fmaf(sB, mi.x, fx); fy = fmaf(sB, mi.y, fy); fz = fmaf(sB, mi.z, fz);
     if (live) {
         if (ACCUM) {
             float4 f = a.fl[i], t = a.tl[i];
@@ -216,10 +234,15 @@ __global__ void k_porder_scatter(const int *__restrict__ scan /* exclusive, scan
 constexpr int kPBlock = 64;
 constexpr int kRangeCap = 8;       // stencil slots handled per round
 
-// One thread per protein.  Phase 0 culls the member lists of the stencil cells against the bounding spheres and COMPACTS the
+// LPP lanes per protein (adjacent lanes; each takes every LPP-th cell of the stencil, the partial sums are combined with
+// shuffles at the end).  The kernel is bound by chains of dependent loads (stencil -> bounds / ranges -> members -> directors):
+// with one lane per protein a warp needs ~100 serial round trips to memory and a rank of a decomposed run has too few
+// warps to hide them; four lanes per protein make the chains four times shorter and give four times as many warps.
+// Phase 0 culls the member lists of the stencil cells against the bounding spheres and COMPACTS the
 // survivors into per-lane range lists in shared memory (a lane-level `if (culled) skip` would save nothing on a SIMT machine;
 // the compaction is what turns skipped cells into skipped warp iterations).  Phase 1 walks the r-th surviving range of every
 // lane together, warp-uniform trip counts, predicated bodies.
+template <int LPP>
 __global__ void __launch_bounds__(kPBlock, 16) k_pair_prot(PairArgs a, const float4 *__restrict__ lbound, const float4 *__restrict__ pbound, CullTable ct,
                                                              const int *__restrict__ porder) {
     __shared__ float s_cutsqpp[36], s_ljcutsq[36];
@@ -231,8 +254,9 @@ __global__ void __launch_bounds__(kPBlock, 16) k_pair_prot(PairArgs a, const flo
     int *const ljb = s_jb[0][w] + lane, *const pjb = s_jb[1][w] + lane;
     unsigned short *const llen = s_len[0][w] + lane, *const plen = s_len[1][w] + lane;
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = tid < a.range[3] - a.range[2];
-    const int i = live ? porder[tid] : 0;
+    const int pid = tid / LPP, sub = tid % LPP;
+    const bool live = pid < a.range[3] - a.range[2];
+    const int i = live ? porder[pid] : 0;
     const int l0 = a.range[0], l1 = a.range[1];                  // lipids of other ranks get their share from k_pair_lipid<true> over there
     F3 xi = {0, 0, 0}, mi = {0, 0, 0};
     int type1 = 0, n8 = 0, n9 = 0;
@@ -253,13 +277,13 @@ __global__ void __launch_bounds__(kPBlock, 16) k_pair_prot(PairArgs a, const flo
     const float testsq_l = fmaxf(cutsq, ljcut);
     float fx = 0, fy = 0, fz = 0, tx = 0, ty = 0, tz = 0;
     const int nmax = __reduce_max_sync(0xffffffffu, n9);
-    for (int kb = 0; kb < nmax; kb += kRangeCap) {
+    for (int kb = 0; kb < nmax; kb += kRangeCap * LPP) {
         // ---- phase 0: cull both member lists of every stencil cell, compact the survivors ------------------------------------------
         int nl_ = 0, np_ = 0;
-        const int kend = min(kRangeCap, nmax - kb);
+        const int kend = min(kRangeCap, (nmax - kb + LPP - 1) / LPP);
         #pragma unroll 4
         for (int kk = 0; kk < kend; ++kk) {
-            const int k = kb + kk;
+            const int k = kb + kk * LPP + sub;
             const bool in9 = k < n9, in8 = k < n8;
             int c2 = 0;
             if (in9) c2 = __ldg(st + k);
@@ -336,7 +360,12 @@ __global__ void __launch_bounds__(kPBlock, 16) k_pair_prot(PairArgs a, const flo
             }
         }
     }
-    if (live) {                                                  // the thread owns protein i: plain read-modify-write
+    #pragma unroll
+    for (int o = 1; o < LPP; o <<= 1) {
+        fx += __shfl_xor_sync(0xffffffffu, fx, o); fy += __shfl_xor_sync(0xffffffffu, fy, o); fz += __shfl_xor_sync(0xffffffffu, fz, o);
+        tx += __shfl_xor_sync(0xffffffffu, tx, o); ty += __shfl_xor_sync(0xffffffffu, ty, o); tz += __shfl_xor_sync(0xffffffffu, tz, o);
+    }
+    if (live && sub == 0) {                                      // this lane owns protein i: plain read-modify-write
         float4 f = a.fp[i], t = a.tp[i];
         f.x += fx; f.y += fy; f.z += fz; t.x += tx; t.y += ty; t.z += tz;
         a.fp[i] = f; a.tp[i] = t;

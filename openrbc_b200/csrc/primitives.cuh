@@ -7,7 +7,7 @@
 namespace orbc {
 
 constexpr int kScanThreads = 1024;
-constexpr int kScanItems = 4;
+constexpr int kScanItems = 16;          // 16384 elements per tile: the cell / bin arrays of a whole RBC are 12 - 48 tiles, short look-back chains
 constexpr int kScanTile = kScanThreads * kScanItems;
 
 // exclusive scan of `v` across the block; returns the exclusive prefix for this thread and the block total
@@ -32,48 +32,83 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int &total) {
     return warp_sums[wid] + incl - v;
 }
 
-__global__ void __launch_bounds__(kScanThreads) k_scan_tile_sums(const int *__restrict__ data, int n, int *__restrict__ tile_sums) {
-    const int base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
-    int s = 0;
-    #pragma unroll
-    for (int k = 0; k < kScanItems; ++k) if (base + k < n) s += data[base + k];
-    int total; block_exclusive_scan(s, total);
-    if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+// ---- single-pass scan (decoupled look-back, Merrill & Garland 2016) -------------------------------------------------------------
+// One launch instead of three: a tile publishes its aggregate, looks back over its predecessors' descriptors until it meets an
+// inclusive prefix, then publishes its own.  Tiles take their index from a counter in scheduling order, so a tile only ever
+// waits for tiles that are already resident.  Descriptors carry the scan's epoch, so nothing has to be cleared between scans:
+//   desc = epoch << 34 | state << 32 | value     state 1 = aggregate, 2 = inclusive prefix
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p) {
+    unsigned long long v; asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v;
 }
-
-__global__ void __launch_bounds__(kScanThreads) k_scan_sums(int *__restrict__ tile_sums, int n_tiles) {
-    // single block: up to kScanTile tiles
-    const int base = threadIdx.x * kScanItems;
-    int v[kScanItems], s = 0;
-    #pragma unroll
-    for (int k = 0; k < kScanItems; ++k) { v[k] = base + k < n_tiles ? tile_sums[base + k] : 0; s += v[k]; }
-    int total; int off = block_exclusive_scan(s, total);
-    #pragma unroll
-    for (int k = 0; k < kScanItems; ++k) { if (base + k < n_tiles) tile_sums[base + k] = off; off += v[k]; }
-    if (threadIdx.x == 0) tile_sums[n_tiles] = total;
+__device__ __forceinline__ void st_release_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
 }
-
-// data[0..n) counts -> exclusive offsets in place; data[n] = grand total
-__global__ void __launch_bounds__(kScanThreads) k_scan_apply(int *__restrict__ data, int n, const int *__restrict__ tile_sums) {
-    const int base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
+__global__ void __launch_bounds__(kScanThreads) k_scan_onepass(int *__restrict__ data, int n, int n_tiles, unsigned long long *__restrict__ desc,
+                                                               unsigned *__restrict__ counter, unsigned epoch) {
+    __shared__ int s_tile, s_prefix;
+    if (threadIdx.x == 0) s_tile = (int)atomicAdd(counter, 1u);
+    __syncthreads();
+    const int tile = s_tile;
+    const int base = tile * kScanTile + threadIdx.x * kScanItems;
     int v[kScanItems], s = 0;
     #pragma unroll
     for (int k = 0; k < kScanItems; ++k) { v[k] = base + k < n ? data[base + k] : 0; s += v[k]; }
-    int total; int off = block_exclusive_scan(s, total) + tile_sums[blockIdx.x];
+    int total; int off = block_exclusive_scan(s, total);
+    if (threadIdx.x < 32) {                                      // warp 0: publish, look back 32 predecessors at a time
+        const int lane = threadIdx.x;
+        const unsigned long long tag = (unsigned long long)epoch << 34;
+        int prefix = 0;
+        if (tile == 0) { if (lane == 0) st_release_u64(desc, tag | (2ull << 32) | (unsigned)total); }
+        else {
+            if (lane == 0) st_release_u64(desc + tile, tag | (1ull << 32) | (unsigned)total);
+            for (int t = tile - 1; ; t -= 32) {
+                const int idx = t - lane;                        // lane 0 looks at the nearest predecessor
+                unsigned long long d = tag | (2ull << 32);       // before tile 0: an inclusive prefix of zero
+                bool ready;
+                do {
+                    if (idx >= 0) d = ld_acquire_u64(desc + idx);
+                    ready = (d >> 34) == epoch && ((d >> 32) & 3) != 0;
+                } while (!__all_sync(0xffffffffu, ready));
+                const unsigned has_prefix = __ballot_sync(0xffffffffu, ((d >> 32) & 3) == 2);
+                const int first = has_prefix ? __ffs(has_prefix) - 1 : 31;
+                int part = lane <= first ? (int)(unsigned)d : 0;
+                #pragma unroll
+                for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+                prefix += part;
+                if (has_prefix) break;
+            }
+            if (lane == 0) st_release_u64(desc + tile, tag | (2ull << 32) | (unsigned)(prefix + total));
+        }
+        if (lane == 0) {
+            s_prefix = prefix;
+            if (tile == n_tiles - 1) { data[n] = prefix + total; *counter = 0u; }   // every tile has taken its index by now
+        }
+    }
+    __syncthreads();
+    off += s_prefix;
     #pragma unroll
     for (int k = 0; k < kScanItems; ++k) { if (base + k < n) data[base + k] = off; off += v[k]; }
-    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) data[n] = tile_sums[gridDim.x];
 }
 
-// counts in data[0..n) -> exclusive offsets in data[0..n], data[n] = total.  n <= kScanTile^2 (16.7 M).
+// counts in data[0..n) -> exclusive offsets in data[0..n], data[n] = total.
 inline int scan_exclusive(orbc_ctx *c, int *data, int n) {
     if (n <= 0) return ORBC_OK;
     const int n_tiles = (n + kScanTile - 1) / kScanTile;
-    if (n_tiles > kScanTile) return fail(ORBC_ERR_ARG, "scan_exclusive: %d elements exceed the two-level limit", n);
-    if (c->scan_tmp_cap < (size_t)n_tiles + 1) { ORBC_TRY(dev_alloc(&c->scan_tmp, (size_t)n_tiles + 1)); c->scan_tmp_cap = (size_t)n_tiles + 1; }
-    ORBC_LAUNCH(c, k_scan_tile_sums, n_tiles, kScanThreads, 0, data, n, c->scan_tmp);
-    ORBC_LAUNCH(c, k_scan_sums, 1, kScanThreads, 0, c->scan_tmp, n_tiles);
-    ORBC_LAUNCH(c, k_scan_apply, n_tiles, kScanThreads, 0, data, n, c->scan_tmp);
+    // descriptors (2 ints each) + the tile counter live in scan_tmp; a new buffer starts zeroed (epoch 0 is never used)
+    const size_t need = 2 * (size_t)n_tiles + 4;
+    if (c->scan_tmp_cap < need) {
+        const size_t cap = need < 65540 ? 65540 : need;
+        ORBC_TRY(dev_alloc(&c->scan_tmp, cap)); c->scan_tmp_cap = cap;
+        ORBC_CUDA(cudaMemsetAsync(c->scan_tmp, 0, sizeof(int) * cap, c->stream));
+        c->scan_epoch = 0;
+    }
+    if (++c->scan_epoch >= (1u << 30)) {
+        ORBC_CUDA(cudaMemsetAsync(c->scan_tmp, 0, sizeof(int) * c->scan_tmp_cap, c->stream));
+        c->scan_epoch = 1;
+    }
+    unsigned *counter = (unsigned *)c->scan_tmp;
+    unsigned long long *desc = (unsigned long long *)(c->scan_tmp + 2);
+    ORBC_LAUNCH(c, k_scan_onepass, n_tiles, kScanThreads, 0, data, n, n_tiles, desc, counter, c->scan_epoch);
     return ORBC_OK;
 }
 

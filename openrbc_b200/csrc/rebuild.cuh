@@ -196,7 +196,10 @@ __global__ void __launch_bounds__(kStencilWarps * 32) k_stencil_build(const floa
     }
     #pragma unroll
     for (int d = 16; d > 0; d >>= 1) { n6 += __shfl_xor_sync(0xffffffffu, n6, d); n8 += __shfl_xor_sync(0xffffffffu, n8, d); }
-    if (lane == 0) stencil_cnt[c] = n6 | (n8 << 8) | (count << 16);
+    if (lane == 0) {
+        stencil_cnt[c] = n6 | (n8 << 8) | (count << 16);
+        if (n6 > 32) atomicExch(&flags[0], c + 1);               // k_pair_ll keeps the surviving r<6 cells in a 32-bit mask
+    }
     if (halo.own.world > 1) {
         owners = __reduce_or_sync(0xffffffffu, owners);
         if (lane == 0) { halo.dest_mask[c] = (unsigned char)(owners & ~(1u << halo.own.owner(c))); if (mine) halo.need[c] = halo.need_epoch; }
@@ -240,9 +243,10 @@ __device__ int nearest_by_grid(float4 p, const GridDev &g, const float4 *__restr
 __global__ void k_assign_nearest(const float4 *__restrict__ x, const int *__restrict__ cellid, const int *__restrict__ range, const float4 *__restrict__ centroid, int n_cells,
                                  const int *__restrict__ stencil, const int *__restrict__ stencil_cnt, GridDev g,
                                  int *__restrict__ aff, int *__restrict__ li, int *__restrict__ cell_cnt,
-                                 unsigned long long *__restrict__ counters, int *__restrict__ flags) {
+                                 unsigned long long *__restrict__ counters, int *__restrict__ flags, const int *__restrict__ keep) {
     const int i = range[0] + blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= range[1]) return;
+    if (keep && !keep[i]) { aff[i] = -1; return; }               // stray lipid being deleted (cleanup.h:29-91): it joins no cell
     const float4 p = x[i];
     const int guess = cellid ? cellid[i] : -1;
     float best = INFINITY; int bi = -1; bool ok = false;
@@ -281,7 +285,7 @@ __global__ void k_assign_nearest(const float4 *__restrict__ x, const int *__rest
 // cells_tmp[cell_start[aff] + arrival slot] = i   (voronoi.h:228-231 with an arbitrary arrival order ...)
 __global__ void k_cell_scatter(const int *__restrict__ aff, const int *__restrict__ li, const int *__restrict__ range, const int *__restrict__ local_start, int *__restrict__ cells_tmp) {
     const int i = range[0] + blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= range[1]) return;
+    if (i >= range[1] || aff[i] < 0) return;
     cells_tmp[local_start[aff[i]] + li[i]] = i;
 }
 // Sorting every cell's arrival list and the gather-reorder in one pass, one thread per particle: the slot of particle i inside its new cell is
@@ -305,6 +309,7 @@ __global__ void k_rank_and_move(const int *__restrict__ aff, const int *__restri
     const int i = range[0] + blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= range[1]) return;
     const int c = aff[i];
+    if (c < 0) return;
     const int b = local_start[c], e = local_start[c + 1];
     int rank = 0;
     for (int k = b; k < e; ++k) rank += (cells_tmp[k] < i);
@@ -329,10 +334,10 @@ __global__ void k_build_tag2idx(const float4 *__restrict__ nn, size_t n, int *__
 }
 
 // ---- cleanup.h:29-60: per cell, median squared distance to the centroid; keep = dr2 < median * tol^2 ------------------------
-__global__ void k_stray_mask(const int *__restrict__ cell_start, int n_cells, const float4 *__restrict__ centroid, const float4 *__restrict__ x,
+__global__ void k_stray_mask(const int *__restrict__ cell_start, int c_beg, int c_end, const float4 *__restrict__ centroid, const float4 *__restrict__ x,
                              float tol, int *__restrict__ keep) {
-    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (c >= n_cells) return;
+    const int c = c_beg + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (c >= c_end) return;
     const int b = cell_start[c], m = cell_start[c + 1] - b;
     if (m <= 0) return;
     const float4 q = centroid[c];

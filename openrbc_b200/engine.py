@@ -29,7 +29,7 @@ EXPORTS = [
     "orbc_constrain_volume", "orbc_integrate", "orbc_nh_zeta_update", "orbc_compute_temperature", "orbc_run_langevin",
     "orbc_run_nh", "orbc_download", "orbc_size", "orbc_n_cells", "orbc_debug_dump", "orbc_debug_noise", "orbc_event_record",
     "orbc_event_elapsed_ms", "orbc_launch_count", "orbc_profile_enable", "orbc_profile_read", "orbc_set_option",
-    "orbc_mg_init", "orbc_mg_blob_bytes", "orbc_mg_cell_range", "orbc_mg_export", "orbc_mg_connect", "orbc_mg_range",
+    "orbc_profile_kernels", "orbc_profile_kernels_report", "orbc_mg_init", "orbc_mg_blob_bytes", "orbc_mg_cell_range", "orbc_mg_export", "orbc_mg_connect", "orbc_mg_range",
 ]
 
 
@@ -109,6 +109,8 @@ def load_library():
         lib.orbc_set_stream.argtypes = [C.c_void_p, C.c_void_p]
         lib.orbc_destroy.argtypes = [C.c_void_p]
         lib.orbc_destroy.restype = None
+        lib.orbc_profile_kernels.argtypes = [C.c_void_p, C.c_int]
+        lib.orbc_profile_kernels_report.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
         lib.orbc_mg_init.argtypes = [C.c_void_p, C.c_int, C.c_int]
         lib.orbc_mg_blob_bytes.restype = C.c_size_t
         lib.orbc_mg_cell_range.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
@@ -419,6 +421,16 @@ class Simulation:
         ms, cnt = C.c_double(), C.c_ulonglong()
         self._ck(self.lib.orbc_profile_read(self.ctx, PROF[cls], C.byref(ms), C.byref(cnt)))
         return ms.value, cnt.value
+
+    def profile_kernels(self, on=True):
+        self._ck(self.lib.orbc_profile_kernels(self.ctx, int(on)))
+
+    def kernel_report(self):
+        """[(kernel, launches, total_us)] since profile_kernels(True) / the last report, sorted by total time."""
+        buf = C.create_string_buffer(1 << 16)
+        self._ck(self.lib.orbc_profile_kernels_report(self.ctx, buf, len(buf)))
+        rows = [ln.rsplit(None, 2) for ln in buf.value.decode().splitlines()]
+        return [(r[0], int(r[1]), float(r[2])) for r in rows]
 
     def launch_count(self):
         n = C.c_ulonglong()

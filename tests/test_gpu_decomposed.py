@@ -128,3 +128,61 @@ def test_free_running_loop(name, world):
     assert abs(t - one.compute_temperature()) < 1e-6 * t
     for sim in [one] + sims:
         sim.close()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_delete_lipid(world):
+    """cleanup.h:29-91 on a decomposed run: same survivors, same slots, same partition as on one GPU."""
+    from openrbc_b200 import Simulation
+    st = load_state("vesicle_ico0")
+    one = Simulation(st, kBT=0.22)
+    sims = make_ranks(st, world, kBT=0.22)
+    one.run_langevin(3)
+    on_all(sims, lambda s: s.run_langevin(3))
+    n_one = one.delete_lipid(1.3)
+    out = {}
+    on_all(sims, lambda s: out.__setitem__(s.rank, s.delete_lipid(1.3)))
+    assert 0 < n_one < len(st["lx"]) and all(v == n_one for v in out.values()), (n_one, out)
+    ref = one.dump("cell_start_l")
+    for sim in sims:
+        assert sim.size(0) == n_one
+        np.testing.assert_array_equal(sim.dump("cell_start_l"), ref)
+    ref, got = one.download(0, "xvno"), gathered(sims, 0, "xvno")
+    for f in "xvno":
+        np.testing.assert_allclose(got[f], ref[f], rtol=0, atol=2e-6 * (1 + np.abs(ref[f]).max(initial=0.0)), err_msg=f)
+    # and the loop goes on from there
+    one.run_langevin(3)
+    on_all(sims, lambda s: s.run_langevin(3))
+    ref, got = one.download(0, "xvno"), gathered(sims, 0, "xvno")
+    for f in "xvno":
+        np.testing.assert_allclose(got[f], ref[f], rtol=0, atol=2e-5 * (1 + np.abs(ref[f]).max(initial=0.0)), err_msg=f)
+    for sim in [one] + sims:
+        sim.close()
+
+
+@pytest.mark.parametrize("name,world", [("vesicle_ico0", 2), ("vesicle_ico0", 4)])
+def test_nose_hoover_loop(name, world):
+    """orbc_run_nh (integrate_nh.h fused pair) on a decomposed run: the partial kinetic energies of the ranks are exchanged and
+    summed in rank order, so every rank carries the same friction zeta as the single-GPU run."""
+    from openrbc_b200 import Simulation
+    st = load_state(name)
+    one = Simulation(st, kBT=0.22)
+    sims = make_ranks(st, world, kBT=0.22)
+    for sim in [one] + sims:
+        sim.nstep = 22
+        sim.zeta = 0.01
+    one.run_nh(6)
+    on_all(sims, lambda s: s.run_nh(6))
+    for sim in sims:
+        assert abs(sim.zeta - one.zeta) <= 1e-6 * abs(one.zeta) and sim.Q.value == one.Q.value, (sim.zeta, one.zeta)
+    for s in (0, 1):
+        ref, got = one.download(s, "xvno"), gathered(sims, s, "xvno")
+        for f in "xvno":
+            np.testing.assert_allclose(got[f], ref[f], rtol=0, atol=2e-5 * (1 + np.abs(ref[f]).max(initial=0.0)), err_msg=f)
+    # call by call: the kinetic energy returned on every rank is the global one
+    ke_one = one.nh_initial_fused()
+    out = {}
+    on_all(sims, lambda s: out.__setitem__(s.rank, s.nh_initial_fused()))
+    assert all(abs(v - ke_one) <= 1e-9 * ke_one for v in out.values()), (ke_one, out)
+    for sim in [one] + sims:
+        sim.close()

@@ -1,0 +1,74 @@
+"""The drop-in host program (openrbc_b200/host/openrbc_b200.cpp = OpenRBC's own host code + orbc_shim.h + liborbc_b200.so)
+against the unmodified reference program (oracle/_ref/openrbc), same command line, same seed, one host thread so that the
+reference's initialisation is deterministic.  With -T 0 both runs are deterministic: the progress table (temperature) and
+the trajectory frames (cell.orbc, trajectory.h:61-105) must agree."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OURS = os.path.join(ROOT, "openrbc_b200", "host", "_build", "openrbc_b200")
+REF = os.path.join(ROOT, "oracle", "_ref", "openrbc")
+ARGS = ["-i", "lipid", "-E", "4", "-t", "0.1", "-T", "0", "-D", "5", "-d", "10", "--stray-tolerance", "1e9", "--dump-field", "15"]
+
+
+def read_frames(path):
+    """Minimal reader of the .orbc sections (8-byte NUL-padded titles followed by raw PODs)."""
+    buf = open(path, "rb").read()
+    pos, frames, cur, n = 0, [], None, 0
+    while pos < len(buf):
+        title = buf[pos:pos + 8].rstrip(b"\0").decode(); pos += 8
+        if title == "FRAMEBEG":
+            cur = {"nstep": int(np.frombuffer(buf, np.int32, 1, pos)[0])}; pos += 4
+        elif title == "NATOM":
+            n = int(np.frombuffer(buf, np.uint64, 1, pos)[0]); pos += 8
+        elif title == "IDENTITY":
+            cur["identity"] = np.frombuffer(buf, np.int32, 2 * n, pos).reshape(n, 2); pos += 8 * n
+        elif title in ("POSITION", "VELOCITY", "ROTATION", "FORCE"):
+            cur[title] = np.frombuffer(buf, np.float32, 3 * n, pos).reshape(n, 3); pos += 12 * n
+        elif title == "VORONOI":
+            cur[title] = np.frombuffer(buf, np.int32, n, pos); pos += 4 * n
+        elif title == "FRAMEEND":
+            frames.append(cur)
+        else:
+            raise ValueError(f"unknown section {title!r} at {pos - 8}")
+    return frames
+
+
+def run(binary, cwd):
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    out = subprocess.run([binary] + ARGS, cwd=cwd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-2000:]
+    rows = [tuple(float(v) for v in ln.split()) for ln in out.stdout.splitlines() if re.fullmatch(r"\s*[\d.]+\s+[\d.eE+-]+\s+[\d.]+\s+\d+\s*", ln)]
+    return out.stdout, rows
+
+
+@pytest.mark.skipif(not (os.path.exists(OURS) and os.path.exists(REF)), reason="host programs not built (python __graft_entry__.py build where the reference tree exists)")
+def test_same_command_line_same_trajectory(tmp_path):
+    (tmp_path / "ours").mkdir(); (tmp_path / "ref").mkdir()
+    out_o, rows_o = run(OURS, tmp_path / "ours")
+    out_r, rows_r = run(REF, tmp_path / "ref")
+    assert "kernel launches" in out_o and "particles" in out_r
+    # progress table: time, temperature, wall time, lost lipids (display.h:38-50)
+    assert len(rows_o) == len(rows_r) >= 2, (out_o[-1500:], out_r[-1500:])
+    for a, b in zip(rows_o, rows_r):
+        assert a[0] == b[0] and a[3] == b[3]
+        assert abs(a[1] - b[1]) <= 2e-3 * abs(b[1]) + 1e-9, (a, b)
+    # topology file is written by the reference's own code in both programs
+    assert open(tmp_path / "ours" / "cell.data").read() == open(tmp_path / "ref" / "cell.data").read()
+    fo, fr = read_frames(tmp_path / "ours" / "cell.orbc"), read_frames(tmp_path / "ref" / "cell.orbc")
+    assert [f["nstep"] for f in fo] == [f["nstep"] for f in fr] and len(fo) >= 2
+    np.testing.assert_array_equal(fo[0]["POSITION"], fr[0]["POSITION"])      # frame 0 is written before the device takes over
+    last_o, last_r = fo[-1], fr[-1]
+    assert last_o["POSITION"].shape == last_r["POSITION"].shape
+    same_cell = last_o["VORONOI"] == last_r["VORONOI"]
+    assert same_cell.mean() > 0.999                                          # storage order = (cell, arrival): identical but for ties
+    d = np.abs(last_o["POSITION"] - last_r["POSITION"]).max(axis=1)
+    assert np.quantile(d, 0.999) < 2e-3, float(np.quantile(d, 0.999))
+    dn = np.abs(last_o["ROTATION"] - last_r["ROTATION"]).max(axis=1)
+    assert np.quantile(dn, 0.999) < 2e-3

@@ -63,3 +63,36 @@ timeit("cell_update protein", lambda: sim.cell_update(1))
 timeit("compute_temperature", sim.compute_temperature)
 sim.nstep = 0
 timeit("run_langevin(2)", lambda: sim.run_langevin(2))
+sim.set_option("pair_impl", 2)
+for var in range(4):
+    sim.set_option("ll_variant", var)
+    sim.clear_force(); sim.compute_pairwise_fused(); sim.synchronize()
+    sim.profile_enable(True)
+    for _ in range(reps):
+        sim.compute_pairwise_fused()
+    print(f"ll_variant {var} (cull {var >> 1}, min blocks {20 if var & 1 else 1}): pair_lipid {sim.profile_read('pair_lipid')[0] / reps * 1e3:.1f} us")
+    sim.profile_enable(False)
+sim.set_option("ll_variant", 1)
+for lanes in (1, 2, 4):
+    sim.set_option("prot_lanes", lanes)
+    for frac in (1.0, 0.125):
+        sim.set_option("debug_owned_fraction", frac)
+        sim.clear_force(); sim.compute_pairwise_fused(); sim.synchronize()
+        sim.profile_enable(True)
+        for _ in range(reps):
+            sim.compute_pairwise_fused()
+        print(f"prot_lanes {lanes}, owned fraction {frac}: pair_protein {sim.profile_read('pair_protein')[0] / reps * 1e3:.1f} us")
+        sim.profile_enable(False)
+sim.set_option("debug_owned_fraction", 1.0)
+sim.set_option("prot_lanes", 0)
+# how the pair kernels scale with the number of owned particles (what one rank of a decomposed run sees)
+sim.set_option("pair_impl", 2)
+for frac in (1.0, 0.5, 0.25, 0.125):
+    sim.set_option("debug_owned_fraction", frac)
+    sim.clear_force(); sim.compute_pairwise_fused(); sim.synchronize()
+    sim.profile_enable(True)
+    for _ in range(reps):
+        sim.compute_pairwise_fused()
+    print(f"owned fraction {frac}: " + "  ".join(f"{k} {sim.profile_read(k)[0] / reps * 1e3:.1f} us" for k in ("pair_lipid", "pair_protein")))
+    sim.profile_enable(False)
+sim.set_option("debug_owned_fraction", 1.0)

@@ -23,6 +23,8 @@ st = bench.load_state(workload)
 print(f"{workload}: {len(st['lx'])} lipids, {len(st['px'])} proteins, {len(st['centroids'])} cells; {world} ranks on {ndev} device(s)", flush=True)
 
 one = orbc.Simulation(st, kBT=0.22)
+if len(st["px"]) // world <= 300000:
+    one.set_option("prot_lanes", 4)       # same lanes per protein (= same summation order) as the ranks will choose
 one.run_langevin(steps)
 one.synchronize()
 ref = [one.download(s, "xvno") for s in (0, 1)]
@@ -87,5 +89,14 @@ for rep in range(2):
 sims[0].profile_enable(True)
 on_all(lambda s: timed(s, 20))
 print("rank 0 per class (us/step):", {k: round(sims[0].profile_read(k)[0] / 20 * 1e3, 1) for k in orbc.engine.PROF})
+for s in sims:
+    s.profile_kernels(True)
+on_all(lambda s: timed(s, 24))
+for s in sims[:1] + sims[-1:]:
+    rep = s.kernel_report()
+    tot = sum(r[2] for r in rep)
+    print(f"rank {s.rank}: kernel time {tot / 24:.0f} us/step of {ms[s.rank] / 24 * 1e3:.0f} us/step elapsed")
+    for name, n, us in rep[:22]:
+        print(f"   {name:24s} {n:5d} launches {us / n:8.1f} us mean {us / 24:8.1f} us/step")
 for s in sims:
     s.close()
