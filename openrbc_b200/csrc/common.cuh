@@ -96,11 +96,12 @@ struct Decomp {
     double *ke_all = nullptr;             // kMaxWorld partial kinetic energies written by the peers
     int *cnt_all[2] = {nullptr, nullptr}; // world rows of arrival counts per species (row r written by rank r)
     int *off_me[2] = {nullptr, nullptr};  // members of each cell that come from lower ranks
-    int *local_start[2] = {nullptr, nullptr};
+    int *cnt_prev[2] = {nullptr, nullptr};// this rank's counts at the previous exchange (which entries the peers hold non-zero)
     unsigned char *dest_mask = nullptr;   // per cell: ranks (other than the owner) that own a cell of its r<9 stencil
     unsigned char *pmask = nullptr;       // per protein slot: ranks that own a bonded partner
     int *need = nullptr;                  // per cell: == need_epoch for owned and halo cells
     int *keep = nullptr;                  // per lipid slot: survives delete_lipid
+    int *my_bonds = nullptr; int my_bonds_cap = 0;   // [0] = count, then the bonds with an owned atom
     PeerTable peers;
     std::vector<void *> opened;           // IPC mappings to close
 };

@@ -64,36 +64,42 @@ __global__ void k_set_range(const int *__restrict__ cell_start, int cb, int ce, 
 }
 __global__ void k_set_range_const(int *__restrict__ range2, int b, int e) { range2[0] = b; range2[1] = e; }
 
-// arrival counts of this rank -> row `rank` of every peer's table
+// arrival counts of this rank -> row `rank` of every peer's table.  A rank's particles only ever land in its own cells and
+// their neighbours, so the row is zero almost everywhere: only entries that are non-zero now or were non-zero at the last
+// exchange (prev, so the peers' copies get cleared) cross the link.
 struct CountRows { int *dst[kMaxWorld]; };
-__global__ void k_share_counts(const int *__restrict__ cnt_me, int nc1, int rank, int world, CountRows rows) {
+__global__ void k_share_counts(const int *__restrict__ cnt_me, int *__restrict__ prev, int nc1, int rank, int world, CountRows rows) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nc1) return;
     const int v = cnt_me[c];
+    if (v == 0 && prev[c] == 0) return;
+    prev[c] = v;
     for (int r = 0; r < world; ++r) if (r != rank) rows.dst[r][(size_t)rank * nc1 + c] = v;
 }
-// members of every cell over all ranks (-> global cell_start after the scan), members from lower ranks, own members
-__global__ void k_cell_totals(const int *__restrict__ cnt_all, int nc, int rank, int world, int *__restrict__ cell_start, int *__restrict__ off_me, int *__restrict__ local_start) {
+// members of every cell over all ranks (-> global cell_start after the scan) and members that come from lower ranks
+__global__ void k_cell_totals(const int *__restrict__ cnt_all, int nc, int rank, int world, int *__restrict__ cell_start, int *__restrict__ off_me) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nc) return;
-    int tot = 0, off = 0, me = 0;
+    int tot = 0, off = 0;
     for (int g = 0; g < world; ++g) {
         const int v = cnt_all[(size_t)g * (nc + 1) + c];
         if (g < rank) off += v;
-        if (g == rank) me = v;
         tot += v;
     }
-    cell_start[c] = tot; off_me[c] = off; local_start[c] = me;
+    cell_start[c] = tot; off_me[c] = off;
 }
 
 // ranks that own a bonded partner of an owned protein (its x must reach them even if the cells are not stencil neighbours)
+// Also collects the bonds with at least one owned atom (my_bonds[0] = count, then bond indices): k_bonded walks that list
+// instead of the whole bond array.
 __global__ void k_bond_mask(const int *__restrict__ bonds, size_t n_bonds, const int *__restrict__ tag2idx, const int *__restrict__ range,
-                            const int *__restrict__ cs_p, CellOwners own, unsigned *__restrict__ pmask32) {
+                            const int *__restrict__ cs_p, CellOwners own, unsigned *__restrict__ pmask32, int *__restrict__ my_bonds, int my_cap, int *__restrict__ flags) {
     const size_t l = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= n_bonds) return;
     const int p1 = tag2idx[bonds[3 * l + 1]], p2 = tag2idx[bonds[3 * l + 2]];
     const int lo = range[2], hi = range[3];
     const bool own1 = p1 >= lo && p1 < hi, own2 = p2 >= lo && p2 < hi;
+    if (own1 || own2) { const int k = atomicAdd(my_bonds, 1); if (k < my_cap) my_bonds[1 + k] = (int)l; else atomicExch(flags + 3, -(k + 1)); }
     if (own1 == own2) return;
     const int mine = own1 ? p1 : p2, other = own1 ? p2 : p1;
     int g = 0;

@@ -232,10 +232,11 @@ int launch_pairwise(orbc_ctx *c) {
     a.range = c->d_range;
     const bool mg = mg_active(c);
     a.cb = mg ? c->mg.cb : 0; a.ce = mg ? c->mg.ce : c->n_cells; a.world = mg ? c->mg.world : 1;
+    a.dest_mask = c->mg.dest_mask;
     const size_t nl = owned_bound(c, ORBC_LIPID), np = owned_bound(c, ORBC_PROTEIN);
     if (c->pair_impl == 1) {
         if (mg) return fail(ORBC_ERR_ARG, "pair_impl 1 is a single-GPU cross-check");
-        if (L.n) { ProfScope ps(c, ORBC_PROF_PAIR_LIPID); ORBC_LAUNCH(c, k_pair_lipid<false>, blocks_for(nl, 128), 128, 0, a, (const unsigned char *)nullptr); }
+        if (L.n) { ProfScope ps(c, ORBC_PROF_PAIR_LIPID); ORBC_LAUNCH(c, k_pair_lipid, blocks_for(nl, 128), 128, 0, a); }
         if (P.n) { ProfScope ps(c, ORBC_PROF_PAIR_PROTEIN); ORBC_LAUNCH(c, k_pair_protein, blocks_for(np, 128), 128, 0, a); }
         return ORBC_OK;
     }
@@ -251,8 +252,7 @@ int launch_pairwise(orbc_ctx *c) {
             default: ORBC_LAUNCH(c, (k_pair_ll<true, true, 20>), blocks_for(nl, kLLBlock), kLLBlock, 0, a, c->lbound); break;
             }
         }
-        // lipid side of the protein-lipid pairs whose protein lives on another rank
-        if (mg && L.n && P.n) ORBC_LAUNCH(c, k_pair_lipid<true>, blocks_for(nl, 128), 128, 0, a, c->mg.dest_mask);
+        // (decomposed: the lipid side of the protein-lipid pairs whose protein lives on another rank is the epilogue of k_pair_ll)
     }
     if (P.n) {
         const CullTable ct = cull_table(c);
@@ -271,7 +271,8 @@ int launch_bonded(orbc_ctx *c) {
     Species &P = c->sp[1];
     if (!c->n_bonds) return ORBC_OK;
     ProfScope ps(c, ORBC_PROF_BONDED);
-    ORBC_LAUNCH(c, k_bonded, blocks_for(c->n_bonds, kBlock), kBlock, 0, c->bonds, c->n_bonds, c->tag2idx, P.X(), P.f, c->d_range);
+    if (mg_active(c)) ORBC_LAUNCH(c, k_bonded, blocks_for(c->mg.my_bonds_cap, kBlock), kBlock, 0, c->bonds, c->n_bonds, c->tag2idx, P.X(), P.f, c->d_range, c->mg.my_bonds);
+    else ORBC_LAUNCH(c, k_bonded, blocks_for(c->n_bonds, kBlock), kBlock, 0, c->bonds, c->n_bonds, c->tag2idx, P.X(), P.f, c->d_range, (const int *)nullptr);
     return ORBC_OK;
 }
 
@@ -324,7 +325,7 @@ int cell_update_assign(orbc_ctx *c, int sp, const int *keep = nullptr) {
     }
     if (mg) {
         CountRows rows; for (int r = 0; r < kMaxWorld; ++r) rows.dst[r] = c->mg.peers.cnt_all[sp][r];
-        ORBC_LAUNCH(c, k_share_counts, blocks_for((size_t)nc + 1, kBlock), kBlock, 0, cnt, nc + 1, c->mg.rank, c->mg.world, rows);
+        ORBC_LAUNCH(c, k_share_counts, blocks_for((size_t)nc + 1, kBlock), kBlock, 0, cnt, c->mg.cnt_prev[sp], nc + 1, c->mg.rank, c->mg.world, rows);
     }
     return ORBC_OK;
 }
@@ -334,16 +335,15 @@ int cell_update_move(orbc_ctx *c, int sp) {
     Species &S = c->sp[sp];
     const int nc = c->n_cells;
     const bool mg = mg_active(c);
-    const int *local_start = S.cell_start, *off_me = nullptr;
+    const int *cnt_me = nullptr, *off_me = nullptr;
     if (mg) {
-        ORBC_LAUNCH(c, k_cell_totals, blocks_for(nc, kBlock), kBlock, 0, c->mg.cnt_all[sp], nc, c->mg.rank, c->mg.world, S.cell_start, c->mg.off_me[sp], c->mg.local_start[sp]);
-        ORBC_TRY(scan_exclusive(c, c->mg.local_start[sp], nc));
-        local_start = c->mg.local_start[sp]; off_me = c->mg.off_me[sp];
+        ORBC_LAUNCH(c, k_cell_totals, blocks_for(nc, kBlock), kBlock, 0, c->mg.cnt_all[sp], nc, c->mg.rank, c->mg.world, S.cell_start, c->mg.off_me[sp]);
+        cnt_me = c->mg.cnt_all[sp] + (size_t)c->mg.rank * (nc + 1); off_me = c->mg.off_me[sp];
     }
     ORBC_TRY(scan_exclusive(c, S.cell_start, nc));
     if (S.n) {
         const size_t nb = owned_bound(c, sp);
-        ORBC_LAUNCH(c, k_cell_scatter, blocks_for(nb, kBlock), kBlock, 0, S.aff, S.li, c->d_range + 2 * sp, local_start, S.cells_tmp);
+        ORBC_LAUNCH(c, k_cell_scatter, blocks_for(nb, kBlock), kBlock, 0, S.aff, S.li, c->d_range + 2 * sp, S.cell_start, off_me, S.cells_tmp);
         const int nx = S.cur ^ 1, nxn = S.cur_xn ^ 1;
         MoveDst d; d.own = cell_owners(c);
         for (int r = 0; r < kMaxWorld; ++r) {
@@ -352,7 +352,7 @@ int cell_update_move(orbc_ctx *c, int sp) {
             d.cellid[r] = mg ? c->mg.peers.cellid[sp][nx][r] : S.cellid[nx];
             d.tag2idx[r] = mg ? c->mg.peers.tag2idx[r] : c->tag2idx;
         }
-        ORBC_LAUNCH(c, k_rank_and_move, blocks_for(nb, kBlock), kBlock, 0, S.aff, c->d_range + 2 * sp, S.cell_start, local_start, off_me, S.cells_tmp, S.cells,
+        ORBC_LAUNCH(c, k_rank_and_move, blocks_for(nb, kBlock), kBlock, 0, S.aff, c->d_range + 2 * sp, S.cell_start, cnt_me, off_me, S.cells_tmp, S.cells,
                     S.X(), S.N(), S.V(), S.O(), d, (mg && sp == ORBC_PROTEIN) ? 1 : 0);
         S.cur = nx; S.cur_xn = nxn;
     }
@@ -369,7 +369,9 @@ int cell_update_finish(orbc_ctx *c, int sp) {
     if (!S.n) return ORBC_OK;
     if (sp == ORBC_PROTEIN && c->n_bonds) {
         ORBC_CUDA(cudaMemsetAsync(c->mg.pmask, 0, (S.n + 3) / 4 * 4, c->stream));
-        ORBC_LAUNCH(c, k_bond_mask, blocks_for(c->n_bonds, kBlock), kBlock, 0, c->bonds, c->n_bonds, c->tag2idx, c->d_range, S.cell_start, cell_owners(c), (unsigned *)c->mg.pmask);
+        ORBC_CUDA(cudaMemsetAsync(c->mg.my_bonds, 0, sizeof(int), c->stream));
+        ORBC_LAUNCH(c, k_bond_mask, blocks_for(c->n_bonds, kBlock), kBlock, 0, c->bonds, c->n_bonds, c->tag2idx, c->d_range, S.cell_start, cell_owners(c), (unsigned *)c->mg.pmask,
+                    c->mg.my_bonds, c->mg.my_bonds_cap, c->d_flags);
     }
     HaloDst d; for (int r = 0; r < kMaxWorld; ++r) { d.x[r] = c->mg.peers.x[sp][S.cur_xn][r]; d.nn[r] = c->mg.peers.nn[sp][S.cur_xn][r]; }
     ORBC_LAUNCH(c, k_halo_push, blocks_for(owned_bound(c, sp), kBlock), kBlock, 0, c->d_range + 2 * sp, c->mg.dest_mask, sp == ORBC_PROTEIN ? c->mg.pmask : (const unsigned char *)nullptr,
@@ -416,7 +418,7 @@ int preload_kernels() {
     ORBC_PRELOAD(k_cv_normal_volume); ORBC_PRELOAD(k_fill_cellid); ORBC_PRELOAD(k_fill_int); ORBC_PRELOAD(k_halo_push); ORBC_PRELOAD(k_kinetic);
     ORBC_PRELOAD(k_mg_barrier); ORBC_PRELOAD(k_morton_keys); ORBC_PRELOAD(k_morton_keys_only); ORBC_PRELOAD(k_nh_final); ORBC_PRELOAD(k_nh_final_fused);
     ORBC_PRELOAD(k_nh_initial_fused); ORBC_PRELOAD(k_nh_zeta_update); ORBC_PRELOAD(k_share_ke); ORBC_PRELOAD(k_sum_ke); ORBC_PRELOAD(k_noise); ORBC_PRELOAD(k_opt_move); ORBC_PRELOAD(k_pack4);
-    ORBC_PRELOAD(k_pair_lipid<true>); ORBC_PRELOAD(k_pair_lipid<false>); ORBC_PRELOAD((k_pair_ll<true, false, 1>)); ORBC_PRELOAD((k_pair_ll<true, false, 20>)); ORBC_PRELOAD((k_pair_ll<true, true, 1>)); ORBC_PRELOAD((k_pair_ll<true, true, 20>)); ORBC_PRELOAD(k_pair_prot<1>); ORBC_PRELOAD(k_pair_prot<2>); ORBC_PRELOAD(k_pair_prot<4>); ORBC_PRELOAD(k_pair_protein);
+    ORBC_PRELOAD(k_pair_lipid); ORBC_PRELOAD((k_pair_ll<true, false, 1>)); ORBC_PRELOAD((k_pair_ll<true, false, 20>)); ORBC_PRELOAD((k_pair_ll<true, true, 1>)); ORBC_PRELOAD((k_pair_ll<true, true, 20>)); ORBC_PRELOAD(k_pair_prot<1>); ORBC_PRELOAD(k_pair_prot<2>); ORBC_PRELOAD(k_pair_prot<4>); ORBC_PRELOAD(k_pair_protein);
     ORBC_PRELOAD(k_permute_centroids); ORBC_PRELOAD(k_porder_flag); ORBC_PRELOAD(k_porder_scatter); ORBC_PRELOAD(k_post_torque); ORBC_PRELOAD(k_radix_hist);
     ORBC_PRELOAD(k_radix_scatter); ORBC_PRELOAD(k_rank_and_move); ORBC_PRELOAD(k_remap_cellid); ORBC_PRELOAD(k_scan_onepass); ORBC_PRELOAD(k_set3); ORBC_PRELOAD(k_set_range); ORBC_PRELOAD(k_set_range_const); ORBC_PRELOAD(k_share_counts);
     ORBC_PRELOAD(k_stencil_build); ORBC_PRELOAD(k_stray_mask); ORBC_PRELOAD(k_unpack3); ORBC_PRELOAD(k_unpack_w); ORBC_PRELOAD(k_verlet_langevin); ORBC_PRELOAD(k_zero4);
@@ -513,8 +515,8 @@ void orbc_destroy(orbc_ctx *c) { if (c) cudaSetDevice(c->device);
     dev_free(c->scan_tmp); dev_free(c->radix_hist); dev_free(c->stage); dev_free(c->d_acc); dev_free(c->d_counters); dev_free(c->d_flags); dev_free(c->d_nh);
     dev_free(c->noise[0]); dev_free(c->noise[1]); dev_free(c->d_range);
     for (void *m : c->mg.opened) cudaIpcCloseMemHandle(m);
-    dev_free(c->mg.keep); dev_free(c->mg.ke_all); dev_free(c->mg.flags); dev_free(c->mg.dest_mask); dev_free(c->mg.pmask); dev_free(c->mg.need);
-    for (int s = 0; s < 2; ++s) { dev_free(c->mg.cnt_all[s]); dev_free(c->mg.off_me[s]); dev_free(c->mg.local_start[s]); }
+    dev_free(c->mg.my_bonds); dev_free(c->mg.keep); dev_free(c->mg.ke_all); dev_free(c->mg.flags); dev_free(c->mg.dest_mask); dev_free(c->mg.pmask); dev_free(c->mg.need);
+    for (int s = 0; s < 2; ++s) { dev_free(c->mg.cnt_all[s]); dev_free(c->mg.off_me[s]); dev_free(c->mg.cnt_prev[s]); }
     if (c->h_acc) cudaFreeHost(c->h_acc); if (c->h_flags) cudaFreeHost(c->h_flags); if (c->h_counters) cudaFreeHost(c->h_counters); if (c->h_nh) cudaFreeHost(c->h_nh);
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
     for (auto &v : c->prof_ev) for (auto &e : v) cudaEventDestroy(e);
@@ -882,14 +884,18 @@ int orbc_mg_export(orbc_ctx *c, void *blob_out, size_t bytes) { if (c) cudaSetDe
     m.cb = own.beg[m.rank]; m.ce = own.beg[m.rank + 1];
     if (m.flags && c->mg.connected) {
         // a second call after a fresh upload of the same system: the peer-visible allocations stay where they are
-        for (int sp = 0; sp < 2; ++sp) ORBC_CUDA(cudaMemsetAsync(m.cnt_all[sp], 0, sizeof(int) * (size_t)w * (nc + 1), c->stream));
+        for (int sp = 0; sp < 2; ++sp) {
+            ORBC_CUDA(cudaMemsetAsync(m.cnt_all[sp], 0, sizeof(int) * (size_t)w * (nc + 1), c->stream));
+            ORBC_CUDA(cudaMemsetAsync(m.cnt_prev[sp], 0, sizeof(int) * ((size_t)nc + 1), c->stream));
+        }
         ORBC_CUDA(cudaMemsetAsync(m.pmask, 0, P.n + 4, c->stream));
         if (m.cen_buf[m.cen_par] != c->centroid) return fail(ORBC_ERR_STATE, "orbc_mg_export: centroid buffers were reallocated after orbc_mg_connect");
     } else {
         for (int sp = 0; sp < 2; ++sp) {
             const size_t n = c->sp[sp].n;
             m.own_cap[sp] = w == 1 ? n : std::min(n, n / w + n / (4 * (size_t)w) + 8192);
-            ORBC_TRY(dev_alloc(&m.cnt_all[sp], (size_t)w * (nc + 1))); ORBC_TRY(dev_alloc(&m.off_me[sp], (size_t)nc + 1)); ORBC_TRY(dev_alloc(&m.local_start[sp], (size_t)nc + 1));
+            ORBC_TRY(dev_alloc(&m.cnt_all[sp], (size_t)w * (nc + 1))); ORBC_TRY(dev_alloc(&m.off_me[sp], (size_t)nc + 1)); ORBC_TRY(dev_alloc(&m.cnt_prev[sp], (size_t)nc + 1));
+            ORBC_CUDA(cudaMemsetAsync(m.cnt_prev[sp], 0, sizeof(int) * ((size_t)nc + 1), c->stream));
             ORBC_CUDA(cudaMemsetAsync(m.cnt_all[sp], 0, sizeof(int) * (size_t)w * (nc + 1), c->stream));
         }
         ORBC_TRY(dev_alloc(&m.flags, kMaxWorld)); ORBC_CUDA(cudaMemsetAsync(m.flags, 0, sizeof(unsigned) * kMaxWorld, c->stream));
@@ -898,6 +904,9 @@ int orbc_mg_export(orbc_ctx *c, void *blob_out, size_t bytes) { if (c) cudaSetDe
         ORBC_TRY(dev_alloc(&m.pmask, P.n + 4)); ORBC_CUDA(cudaMemsetAsync(m.pmask, 0, P.n + 4, c->stream));
         ORBC_TRY(dev_alloc(&m.need, nc)); ORBC_CUDA(cudaMemsetAsync(m.need, 0, sizeof(int) * nc, c->stream));
         ORBC_TRY(dev_alloc(&m.keep, L.n + 1));
+        // work list of the bonds with an owned atom (clipped and flagged at the capacity)
+        m.my_bonds_cap = (int)std::min(c->n_bonds, c->n_bonds / w + c->n_bonds / (2 * (size_t)w) + 8192);
+        ORBC_TRY(dev_alloc(&m.my_bonds, (size_t)m.my_bonds_cap + 1));
         m.cen_buf[0] = c->centroid; m.cen_buf[1] = c->centroid_tmp; m.cen_par = 0; m.epoch = 0;
         // scratch that the single-GPU path allocates on first use: allocate it now, no cudaMalloc while peers spin in a barrier
         ORBC_CUDA(cudaMemsetAsync(m.off_me[0], 0, 2 * sizeof(int), c->stream));
@@ -910,8 +919,10 @@ int orbc_mg_export(orbc_ctx *c, void *blob_out, size_t bytes) { if (c) cudaSetDe
     if (w > 1) {
         for (int sp = 0; sp < 2; ++sp) ORBC_LAUNCH(c, k_set_range, 1, 1, 0, c->sp[sp].cell_start, m.cb, m.ce, c->d_range + 2 * sp, (int)m.own_cap[sp], c->d_flags);
         ORBC_TRY(build_index(c, true));
+        ORBC_CUDA(cudaMemsetAsync(m.my_bonds, 0, sizeof(int), c->stream));
         if (P.n && c->n_bonds)
-            ORBC_LAUNCH(c, k_bond_mask, blocks_for(c->n_bonds, kBlock), kBlock, 0, c->bonds, c->n_bonds, c->tag2idx, c->d_range, P.cell_start, own, (unsigned *)m.pmask);
+            ORBC_LAUNCH(c, k_bond_mask, blocks_for(c->n_bonds, kBlock), kBlock, 0, c->bonds, c->n_bonds, c->tag2idx, c->d_range, P.cell_start, own, (unsigned *)m.pmask,
+                        m.my_bonds, m.my_bonds_cap, c->d_flags);
         c->porder_valid = false;
     }
     ORBC_CUDA(cudaStreamSynchronize(c->stream));

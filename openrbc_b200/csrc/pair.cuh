@@ -19,6 +19,7 @@ struct PairArgs {
     float4 *fl, *tl, *fp, *tp;
     const int *range;      // {l0, l1, p0, p1}: the particle slots this GPU computes (everything on a single GPU)
     int cb, ce, world;     // owned cells of a decomposed run ([0, n_cells) and 1 otherwise)
+    const unsigned char *dest_mask;   // decomposed: per cell, the other ranks that own a cell of its r<9 stencil
 };
 
 struct F3 { float x, y, z; };
@@ -67,14 +68,9 @@ __device__ __forceinline__ F3 rep8(float cut, float rep, F3 d, float r2) {
 // ---- v1: one thread per lipid -------------------------------------------------------------------------------------------------
 // lipid i gathers: LL over the r<6 stencil of its cell (lipid_lipid::rmax, compute_pairwise_fused.h:92), protein-lipid over the
 // r<8 stencil (prote_lipid::rmax, :144) as the lipid side of protein_lipid_omp / lennard_jones_omp.
-// FOREIGN = true (decomposed runs): only the proteins of stencil cells owned by ANOTHER rank are visited — the lipid side of
-// the protein-lipid pairs whose protein side that rank evaluates (the reference's one-sided evaluation across thread
-// ranges, compute_pairwise_fused.h:287-295); lipid-lipid is left to k_pair_ll.
-template <bool FOREIGN>
-__global__ void __launch_bounds__(128) k_pair_lipid(PairArgs a, const unsigned char *__restrict__ dest_mask) {
+__global__ void __launch_bounds__(128) k_pair_lipid(PairArgs a) {
     const int i = a.range[0] + blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.range[1]) return;
-    if (FOREIGN && !dest_mask[a.cell_l[i]]) return;      // no stencil cell of this lipid's cell lives on another rank
     const float4 xi4 = a.xl[i], ni4 = a.nl[i];
     const F3 xi = {xi4.x, xi4.y, xi4.z}, mi = {ni4.x, ni4.y, ni4.z};
     const int c = a.cell_l[i];
@@ -85,8 +81,7 @@ __global__ void __launch_bounds__(128) k_pair_lipid(PairArgs a, const unsigned c
     const float cutsqll = c_ff.cutsqll;
     for (int k = 0; k < n8; ++k) {
         const int c2 = st[k];
-        if (FOREIGN && c2 >= a.cb && c2 < a.ce) continue;
-        if (!FOREIGN && k < n6) {
+        if (k < n6) {
             const int jb = a.cs_l[c2], je = a.cs_l[c2 + 1];
             for (int j = jb; j < je; ++j) {
                 const float4 xj = a.xl[j];
@@ -181,10 +176,12 @@ __global__ void __launch_bounds__(128) k_pair_protein(PairArgs a) {
 // ---- compute_bonded.h:89-146: F = K (1 - r0 / |dx|) dx, +F on atom i, -F on atom j ----------------------------------------------
 // Decomposed runs: every rank walks the whole bond list and applies the force to the atoms it owns (slots [p0, p1)); a bond
 // that straddles two ranks is evaluated by both, one-sidedly, from the halo copy of the partner.
+// `my_bonds` (decomposed): [0] = count, then the indices of the bonds with an owned atom (multi.cuh k_bond_mask).
 __global__ void k_bonded(const int *__restrict__ bonds, size_t n_bonds, const int *__restrict__ tag2idx, const float4 *__restrict__ x, float4 *__restrict__ f,
-                         const int *__restrict__ range) {
-    const size_t l = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (l >= n_bonds) return;
+                         const int *__restrict__ range, const int *__restrict__ my_bonds) {
+    size_t l = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (my_bonds) { if (l >= (size_t)my_bonds[0]) return; l = (size_t)my_bonds[1 + l]; }
+    else if (l >= n_bonds) return;
     const int type = bonds[3 * l], p1 = tag2idx[bonds[3 * l + 1]], p2 = tag2idx[bonds[3 * l + 2]];
     const int lo = range[2], hi = range[3];
     const bool own1 = p1 >= lo && p1 < hi, own2 = p2 >= lo && p2 < hi;

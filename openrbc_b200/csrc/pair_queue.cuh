@@ -191,6 +191,34 @@ __global__ void __launch_bounds__(kLLBlock, MINB) k_pair_ll(PairArgs a, const fl
     }
     for (unsigned e = q0; e < qp; e += 128) ll_eval(kc, xl, nl, xi, mi, lds_i32(e), fx, fy, fz, tx, ty, tz, sB);
     fx = fmaf(sB, mi.x, fx); fy = fmaf(sB, mi.y, fy); fz = fmaf(sB, mi.z, fz);
+    if (a.world > 1 && live && a.n_p) {
+        // decomposed run: the lipid side of the protein-lipid pairs whose protein lives on another rank (that rank evaluates the
+        // protein side) — the reference's one-sided evaluation across thread ranges, compute_pairwise_fused.h:287-295
+        const int c = a.cell_l[i];
+        if (a.dest_mask[c]) {
+            const int n8 = (a.stencil_cnt[c] >> 8) & 255;
+            for (int k = 0; k < n8; ++k) {
+                const int c2 = __ldg(st + k);
+                if (c2 >= a.cb && c2 < a.ce) continue;
+                const int jb = __ldg(a.cs_p + c2), je = __ldg(a.cs_p + c2 + 1);
+                for (int j = jb; j < je; ++j) {
+                    const float4 xj = __ldg(a.xp + j);
+                    const int type = __float_as_int(xj.w);
+                    const F3 d = {xj.x - xi.x, xj.y - xi.y, xj.z - xi.z};      // x_protein - x_lipid (compute_pairwise_fused.h:167)
+                    const float r2 = dot3(d, d);
+                    if (r2 < c_ff.cutsqlp[type] && r2 > 1e-5f) {
+                        const float4 nj = __ldg(a.np + j);
+                        F3 f, q1, q2;
+                        poly48(c_ff.cutlp[type], c_ff.attlp[type], c_ff.replp[type], c_ff.alphalp[type], d, r2, {nj.x, nj.y, nj.z}, mi, f, q1, q2);
+                        fx -= f.x; fy -= f.y; fz -= f.z; tx -= q2.x; ty -= q2.y; tz -= q2.z;
+                    } else if (r2 < c_ff.lj_cutsq[type] && r2 > 1e-5f) {
+                        const F3 f = lj126(c_ff.lj_lj1[type], c_ff.lj_lj2[type], d, r2);
+                        fx -= f.x; fy -= f.y; fz -= f.z;
+                    }
+                }
+            }
+        }
+    }
     if (live) {
         if (ACCUM) {
             float4 f = a.fl[i], t = a.tl[i];

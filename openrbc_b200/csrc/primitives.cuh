@@ -6,8 +6,8 @@
 
 namespace orbc {
 
-constexpr int kScanThreads = 1024;
-constexpr int kScanItems = 16;          // 16384 elements per tile: the cell / bin arrays of a whole RBC are 12 - 48 tiles, short look-back chains
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 8;           // two 16-byte loads per thread; small tiles: the latency of ONE tile bounds the whole scan
 constexpr int kScanTile = kScanThreads * kScanItems;
 
 // exclusive scan of `v` across the block; returns the exclusive prefix for this thread and the block total
@@ -51,8 +51,16 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_onepass(int *__restrict__
     const int tile = s_tile;
     const int base = tile * kScanTile + threadIdx.x * kScanItems;
     int v[kScanItems], s = 0;
+    const bool whole = base + kScanItems <= n;                   // `data` is a cudaMalloc base pointer: 16-byte aligned groups
+    if (whole) {
+        const int4 a = *reinterpret_cast<const int4 *>(data + base), b = *reinterpret_cast<const int4 *>(data + base + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+        #pragma unroll
+        for (int k = 0; k < kScanItems; ++k) v[k] = base + k < n ? data[base + k] : 0;
+    }
     #pragma unroll
-    for (int k = 0; k < kScanItems; ++k) { v[k] = base + k < n ? data[base + k] : 0; s += v[k]; }
+    for (int k = 0; k < kScanItems; ++k) s += v[k];
     int total; int off = block_exclusive_scan(s, total);
     if (threadIdx.x < 32) {                                      // warp 0: publish, look back 32 predecessors at a time
         const int lane = threadIdx.x;
@@ -86,8 +94,16 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_onepass(int *__restrict__
     }
     __syncthreads();
     off += s_prefix;
+    int o[kScanItems];
     #pragma unroll
-    for (int k = 0; k < kScanItems; ++k) { if (base + k < n) data[base + k] = off; off += v[k]; }
+    for (int k = 0; k < kScanItems; ++k) { o[k] = off; off += v[k]; }
+    if (whole) {
+        *reinterpret_cast<int4 *>(data + base) = make_int4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<int4 *>(data + base + 4) = make_int4(o[4], o[5], o[6], o[7]);
+    } else {
+        #pragma unroll
+        for (int k = 0; k < kScanItems; ++k) if (base + k < n) data[base + k] = o[k];
+    }
 }
 
 // counts in data[0..n) -> exclusive offsets in data[0..n], data[n] = total.

@@ -283,18 +283,22 @@ __global__ void k_assign_nearest(const float4 *__restrict__ x, const int *__rest
 }
 
 // cells_tmp[cell_start[aff] + arrival slot] = i   (voronoi.h:228-231 with an arbitrary arrival order ...)
-__global__ void k_cell_scatter(const int *__restrict__ aff, const int *__restrict__ li, const int *__restrict__ range, const int *__restrict__ local_start, int *__restrict__ cells_tmp) {
+// (decomposed: this rank's members of cell c take the slots [cell_start[c] + off_me[c], + cnt_me[c]) of the arrival list)
+__global__ void k_cell_scatter(const int *__restrict__ aff, const int *__restrict__ li, const int *__restrict__ range, const int *__restrict__ cell_start,
+                               const int *__restrict__ off_me, int *__restrict__ cells_tmp) {
     const int i = range[0] + blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= range[1] || aff[i] < 0) return;
-    cells_tmp[local_start[aff[i]] + li[i]] = i;
+    if (i >= range[1]) return;
+    const int c = aff[i];
+    if (c < 0) return;
+    cells_tmp[cell_start[c] + (off_me ? off_me[c] : 0) + li[i]] = i;
 }
 // Sorting every cell's arrival list and the gather-reorder in one pass, one thread per particle: the slot of particle i inside its new cell is
 // the number of members with a lower index (= arrival order of the reference at one thread, voronoi.h:214-215), found by
 // scanning the cell's arrival list (a few dozen L1-resident ints shared by neighbouring threads); the particle then moves
 // itself: new[cell_start + rank] = old[i]  (reorder.h:73-149 as a scatter instead of a gather; `cells` still records the
 // permutation, VCellList::cells).
-// On a decomposed run the arrival list is this rank's (local_start = scan of its own counts), members that come from lower
-// ranks precede it in the cell (off_me; ranks own ascending slot ranges, so this is still ascending old index), and the
+// On a decomposed run the arrival list holds this rank's members only (cnt_me of them per cell), members that come from lower
+// ranks precede them in the cell (off_me; ranks own ascending slot ranges, so this is still ascending old index), and the
 // destination is the array of whichever rank owns the new cell — a direct store into that GPU's memory over NVLink.  A
 // protein also announces its new slot to every rank's tag -> index map (container.h:39-58).
 struct MoveDst {
@@ -302,7 +306,7 @@ struct MoveDst {
     int *cellid[kMaxWorld], *tag2idx[kMaxWorld];
     CellOwners own;
 };
-__global__ void k_rank_and_move(const int *__restrict__ aff, const int *__restrict__ range, const int *__restrict__ cell_start, const int *__restrict__ local_start,
+__global__ void k_rank_and_move(const int *__restrict__ aff, const int *__restrict__ range, const int *__restrict__ cell_start, const int *__restrict__ cnt_me,
                                 const int *__restrict__ off_me, const int *__restrict__ cells_tmp, int *__restrict__ cells,
                                 const float4 *__restrict__ x0, const float4 *__restrict__ n0, const float4 *__restrict__ v0, const float4 *__restrict__ o0,
                                 MoveDst d, int announce_tags) {
@@ -310,10 +314,10 @@ __global__ void k_rank_and_move(const int *__restrict__ aff, const int *__restri
     if (i >= range[1]) return;
     const int c = aff[i];
     if (c < 0) return;
-    const int b = local_start[c], e = local_start[c + 1];
+    const int b = cell_start[c] + (off_me ? off_me[c] : 0), e = cnt_me ? b + cnt_me[c] : cell_start[c + 1];
     int rank = 0;
     for (int k = b; k < e; ++k) rank += (cells_tmp[k] < i);
-    const int j = cell_start[c] + (off_me ? off_me[c] : 0) + rank;
+    const int j = b + rank;
     const int g = d.own.owner(c);
     cells[j] = i;
     const float4 nn = n0[i];
