@@ -125,6 +125,9 @@ struct orbc_ctx {
     bool stencil_valid = false;
     float4 *cell_normal = nullptr;                // constrain_volume's persistent scratch
     float4 *lbound = nullptr, *pbound = nullptr;  // per-cell bounding spheres of the current lipids / proteins (pair_queue.cuh)
+    uint4 *rel16 = nullptr; size_t rel16_cap = 0;  // half-precision cell-relative lipid positions, two per record (k_pair_ll_h)
+    int *rel_flag = nullptr;                      // raised by k_cell_bounds when a lipid does not fit the half-precision prefilter
+    int ll_half = 0;                              // experimental packed-half prefilter kernel k_pair_ll_h (0 off; 1, 2 = register targets)
     int *porder = nullptr; size_t porder_cap = 0;  // thread -> protein map of the protein pair kernel (heavy types first)
     bool porder_valid = false;
     unsigned type_mask = 0;                       // protein types present (bit t), from the last protein upload

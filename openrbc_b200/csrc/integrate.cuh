@@ -52,6 +52,7 @@ struct IntegArgs {
     float4 *x_out, *nn_out;                // where verlet_langevin stores the new x, n (the same arrays on a single GPU)
     size_t n;
     const int *range;                      // {begin, end} slots to integrate (verlet_langevin)
+    int clear;                             // verlet_langevin: zero f and t (the reference's semantics) or leave them dead
     PushArgs push;
     int species;
     float dt;
@@ -138,7 +139,7 @@ __global__ void __launch_bounds__(256) k_verlet_langevin(IntegArgs a) {
     a.x_out[i] = x; a.v[i] = v; a.o[i] = o;
     const float4 nnew = make_float4(nn.x, nn.y, nn.z, n4.w);
     a.nn_out[i] = nnew;
-    a.f[i] = make_float4(0, 0, 0, 0); a.t[i] = make_float4(0, 0, 0, 0);
+    if (a.clear) { a.f[i] = make_float4(0, 0, 0, 0); a.t[i] = make_float4(0, 0, 0, 0); }
     if (a.push.world > 1) {
         unsigned m = a.push.cell_mask[a.push.cellid[i]];
         if (a.push.pmask) m |= a.push.pmask[i];

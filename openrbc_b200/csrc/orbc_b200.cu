@@ -169,6 +169,7 @@ void fill_integ(IntegArgs &a, orbc_ctx *c, int sp, const orbc_step_params *p) {
     a.seed = p->seed; a.step = (uint32_t)p->nstep;
     a.noise = nullptr; a.acc = c->d_acc; a.zeta_dev = nullptr;
     a.range = c->d_range + 2 * sp;
+    a.clear = 1;
     a.push.world = 1; a.push.cell_mask = nullptr; a.push.pmask = nullptr; a.push.cellid = nullptr;
     if (mg_active(c)) {
         // decomposed: new x, n go to the OTHER buffer, here and on the ranks that read them as halo; peers may still be reading
@@ -220,7 +221,7 @@ int build_porder(orbc_ctx *c) {
     return ORBC_OK;
 }
 
-int launch_pairwise(orbc_ctx *c) {
+int launch_pairwise(orbc_ctx *c, bool accumulate = true) {
     Species &L = c->sp[0], &P = c->sp[1];
     if (!c->n_cells || !L.has_partition) return fail(ORBC_ERR_ARG, "compute_pairwise_fused: no Voronoi partition (call orbc_voronoi_upload / orbc_rebuild first)");
     if (P.n && !P.has_partition) return fail(ORBC_ERR_ARG, "compute_pairwise_fused: proteins are not partitioned");
@@ -233,6 +234,7 @@ int launch_pairwise(orbc_ctx *c) {
     const bool mg = mg_active(c);
     a.cb = mg ? c->mg.cb : 0; a.ce = mg ? c->mg.ce : c->n_cells; a.world = mg ? c->mg.world : 1;
     a.dest_mask = c->mg.dest_mask;
+    a.accumulate = accumulate ? 1 : 0;
     const size_t nl = owned_bound(c, ORBC_LIPID), np = owned_bound(c, ORBC_PROTEIN);
     if (c->pair_impl == 1) {
         if (mg) return fail(ORBC_ERR_ARG, "pair_impl 1 is a single-GPU cross-check");
@@ -242,14 +244,22 @@ int launch_pairwise(orbc_ctx *c) {
     }
     {
         ProfScope ps(c, ORBC_PROF_PAIR_LIPID);
+        const size_t rel_need = (L.cap + 64) / 2 + 8;
+        if (c->ll_half && c->rel16_cap < rel_need) { ORBC_TRY(dev_alloc(&c->rel16, rel_need)); c->rel16_cap = rel_need; ORBC_CUDA(cudaMemsetAsync(c->rel16, 0, sizeof(uint4) * rel_need, c->stream)); }
+        if (c->ll_half) ORBC_CUDA(cudaMemsetAsync(c->rel_flag, 0, sizeof(int), c->stream));
         ORBC_LAUNCH(c, k_cell_bounds, blocks_for(c->n_cells, 128), 128, 0, c->centroid, c->n_cells, L.cell_start, L.X(), P.n ? P.cell_start : nullptr, P.X(), c->lbound, c->pbound,
-                    mg ? c->mg.need : (const int *)nullptr, c->mg.need_epoch);
+                    mg ? c->mg.need : (const int *)nullptr, c->mg.need_epoch, c->ll_half ? c->rel16 : (uint4 *)nullptr, c->rel_flag);
         if (L.n) {
+            // packed half-precision prefilter when every lipid fits its error budget (rel_flag == 0), the fp32 kernel otherwise:
+            // both are launched, the one that is not needed returns at once
+            const int *gate = c->ll_half ? c->rel_flag : nullptr;
+            if (c->ll_half == 1) ORBC_LAUNCH(c, (k_pair_ll_h<20>), blocks_for(nl, kLLBlock), kLLBlock, 0, a, c->lbound, c->rel16, gate, 0);
+            else if (c->ll_half) ORBC_LAUNCH(c, (k_pair_ll_h<18>), blocks_for(nl, kLLBlock), kLLBlock, 0, a, c->lbound, c->rel16, gate, 0);
             switch (c->ll_variant) {     // bit 1: per-lane bounding-sphere cull of the stencil cells; bit 0: aim at 20 resident blocks per SM
-            case 0: ORBC_LAUNCH(c, (k_pair_ll<true, false, 1>), blocks_for(nl, kLLBlock), kLLBlock, 0, a, c->lbound); break;
-            case 1: ORBC_LAUNCH(c, (k_pair_ll<true, false, 20>), blocks_for(nl, kLLBlock), kLLBlock, 0, a, c->lbound); break;
-            case 2: ORBC_LAUNCH(c, (k_pair_ll<true, true, 1>), blocks_for(nl, kLLBlock), kLLBlock, 0, a, c->lbound); break;
-            default: ORBC_LAUNCH(c, (k_pair_ll<true, true, 20>), blocks_for(nl, kLLBlock), kLLBlock, 0, a, c->lbound); break;
+            case 0: ORBC_LAUNCH(c, (k_pair_ll<false, 1>), blocks_for(nl, kLLBlock), kLLBlock, 0, a, c->lbound, gate, 1); break;
+            case 1: ORBC_LAUNCH(c, (k_pair_ll<false, 20>), blocks_for(nl, kLLBlock), kLLBlock, 0, a, c->lbound, gate, 1); break;
+            case 2: ORBC_LAUNCH(c, (k_pair_ll<true, 1>), blocks_for(nl, kLLBlock), kLLBlock, 0, a, c->lbound, gate, 1); break;
+            default: ORBC_LAUNCH(c, (k_pair_ll<true, 20>), blocks_for(nl, kLLBlock), kLLBlock, 0, a, c->lbound, gate, 1); break;
             }
         }
         // (decomposed: the lipid side of the protein-lipid pairs whose protein lives on another rank is the epilogue of k_pair_ll)
@@ -386,7 +396,7 @@ int do_cell_update(orbc_ctx *c, int sp) {
 }
 
 // `rebuild_follows`: the caller rebuilds next; the first barrier of the rebuild then also covers the arrival of this push
-int do_integrate_langevin(orbc_ctx *c, const orbc_step_params *p, bool rebuild_follows = false) {
+int do_integrate_langevin(orbc_ctx *c, const orbc_step_params *p, bool rebuild_follows = false, bool clear = true) {
     // decomposed: no barrier before the push — it goes to the x, n buffers nobody is reading (fill_integ)
     {
         ProfScope ps(c, ORBC_PROF_INTEGRATE);
@@ -394,6 +404,7 @@ int do_integrate_langevin(orbc_ctx *c, const orbc_step_params *p, bool rebuild_f
             Species &S = c->sp[sp];
             if (!S.n) continue;
             IntegArgs a; fill_integ(a, c, sp, p); langevin_coeffs(a, p);
+            a.clear = clear ? 1 : 0;
             const float *hn = sp == 0 ? p->noise_lipid : p->noise_protein;
             if (hn) {
                 if (c->noise_cap[sp] < 3 * S.n) { ORBC_TRY(dev_alloc(&c->noise[sp], 3 * S.n)); c->noise_cap[sp] = 3 * S.n; }
@@ -418,7 +429,7 @@ int preload_kernels() {
     ORBC_PRELOAD(k_cv_normal_volume); ORBC_PRELOAD(k_fill_cellid); ORBC_PRELOAD(k_fill_int); ORBC_PRELOAD(k_halo_push); ORBC_PRELOAD(k_kinetic);
     ORBC_PRELOAD(k_mg_barrier); ORBC_PRELOAD(k_morton_keys); ORBC_PRELOAD(k_morton_keys_only); ORBC_PRELOAD(k_nh_final); ORBC_PRELOAD(k_nh_final_fused);
     ORBC_PRELOAD(k_nh_initial_fused); ORBC_PRELOAD(k_nh_zeta_update); ORBC_PRELOAD(k_share_ke); ORBC_PRELOAD(k_sum_ke); ORBC_PRELOAD(k_noise); ORBC_PRELOAD(k_opt_move); ORBC_PRELOAD(k_pack4);
-    ORBC_PRELOAD(k_pair_lipid); ORBC_PRELOAD((k_pair_ll<true, false, 1>)); ORBC_PRELOAD((k_pair_ll<true, false, 20>)); ORBC_PRELOAD((k_pair_ll<true, true, 1>)); ORBC_PRELOAD((k_pair_ll<true, true, 20>)); ORBC_PRELOAD(k_pair_prot<1>); ORBC_PRELOAD(k_pair_prot<2>); ORBC_PRELOAD(k_pair_prot<4>); ORBC_PRELOAD(k_pair_protein);
+    ORBC_PRELOAD(k_pair_lipid); ORBC_PRELOAD((k_pair_ll_h<20>)); ORBC_PRELOAD((k_pair_ll_h<18>)); ORBC_PRELOAD((k_pair_ll<false, 1>)); ORBC_PRELOAD((k_pair_ll<false, 20>)); ORBC_PRELOAD((k_pair_ll<true, 1>)); ORBC_PRELOAD((k_pair_ll<true, 20>)); ORBC_PRELOAD(k_pair_prot<1>); ORBC_PRELOAD(k_pair_prot<2>); ORBC_PRELOAD(k_pair_prot<4>); ORBC_PRELOAD(k_pair_protein);
     ORBC_PRELOAD(k_permute_centroids); ORBC_PRELOAD(k_porder_flag); ORBC_PRELOAD(k_porder_scatter); ORBC_PRELOAD(k_post_torque); ORBC_PRELOAD(k_radix_hist);
     ORBC_PRELOAD(k_radix_scatter); ORBC_PRELOAD(k_rank_and_move); ORBC_PRELOAD(k_remap_cellid); ORBC_PRELOAD(k_scan_onepass); ORBC_PRELOAD(k_set3); ORBC_PRELOAD(k_set_range); ORBC_PRELOAD(k_set_range_const); ORBC_PRELOAD(k_share_counts);
     ORBC_PRELOAD(k_stencil_build); ORBC_PRELOAD(k_stray_mask); ORBC_PRELOAD(k_unpack3); ORBC_PRELOAD(k_unpack_w); ORBC_PRELOAD(k_verlet_langevin); ORBC_PRELOAD(k_zero4);
@@ -495,6 +506,7 @@ int orbc_create(orbc_ctx **out, int device) {
     for (auto &e : c->ev) ORBC_CUDA(cudaEventCreate(&e));
     ORBC_TRY(dev_alloc(&c->d_acc, 8)); ORBC_TRY(dev_alloc(&c->d_counters, 8)); ORBC_TRY(dev_alloc(&c->d_flags, 4)); ORBC_TRY(dev_alloc(&c->d_nh, 2));
     ORBC_TRY(dev_alloc(&c->d_range, 4)); ORBC_CUDA(cudaMemset(c->d_range, 0, 4 * sizeof(int)));
+    ORBC_TRY(dev_alloc(&c->rel_flag, 1)); ORBC_CUDA(cudaMemset(c->rel_flag, 0, sizeof(int)));
     ORBC_CUDA(cudaMemset(c->d_acc, 0, 8 * sizeof(double))); ORBC_CUDA(cudaMemset(c->d_counters, 0, 8 * sizeof(unsigned long long)));
     ORBC_CUDA(cudaMemset(c->d_flags, 0, 4 * sizeof(int))); ORBC_CUDA(cudaMemset(c->d_nh, 0, 2 * sizeof(float)));
     ORBC_CUDA(cudaMallocHost((void **)&c->h_acc, 8 * sizeof(double))); ORBC_CUDA(cudaMallocHost((void **)&c->h_flags, 4 * sizeof(int)));
@@ -513,7 +525,7 @@ void orbc_destroy(orbc_ctx *c) { if (c) cudaSetDevice(c->device);
     dev_free(c->grid.bin_start); dev_free(c->grid.bin_items); dev_free(c->grid.bin_of); dev_free(c->grid.bin_slot); dev_free(c->grid.sorted);
     dev_free(c->stencil); dev_free(c->stencil_cnt); dev_free(c->cell_normal); dev_free(c->lbound); dev_free(c->pbound); dev_free(c->porder); dev_free(c->bonds); dev_free(c->tag2idx);
     dev_free(c->scan_tmp); dev_free(c->radix_hist); dev_free(c->stage); dev_free(c->d_acc); dev_free(c->d_counters); dev_free(c->d_flags); dev_free(c->d_nh);
-    dev_free(c->noise[0]); dev_free(c->noise[1]); dev_free(c->d_range);
+    dev_free(c->noise[0]); dev_free(c->noise[1]); dev_free(c->d_range); dev_free(c->rel16); dev_free(c->rel_flag);
     for (void *m : c->mg.opened) cudaIpcCloseMemHandle(m);
     dev_free(c->mg.my_bonds); dev_free(c->mg.keep); dev_free(c->mg.ke_all); dev_free(c->mg.flags); dev_free(c->mg.dest_mask); dev_free(c->mg.pmask); dev_free(c->mg.need);
     for (int s = 0; s < 2; ++s) { dev_free(c->mg.cnt_all[s]); dev_free(c->mg.off_me[s]); dev_free(c->mg.cnt_prev[s]); }
@@ -529,7 +541,12 @@ int orbc_set_option(orbc_ctx *c, const char *name, double value) { if (c) cudaSe
     if (!c || !name) return fail(ORBC_ERR_ARG, "null argument");
     if (!strcmp(name, "pair_impl")) { if (value != 1 && value != 2) return fail(ORBC_ERR_ARG, "pair_impl must be 1 or 2"); c->pair_impl = (int)value; return ORBC_OK; }
     if (!strcmp(name, "prot_lanes")) { if (value != 0 && value != 1 && value != 2 && value != 4) return fail(ORBC_ERR_ARG, "prot_lanes must be 0 (automatic), 1, 2 or 4"); c->prot_lanes = (int)value; return ORBC_OK; }
+    if (!strcmp(name, "ll_half")) { c->ll_half = (int)value; return ORBC_OK; }   // 0 off, 1 / 2: register targets of 20 / 18 resident blocks   // packed half-precision prefilter in the lipid-lipid kernel
     if (!strcmp(name, "ll_variant")) { c->ll_variant = (int)value & 3; return ORBC_OK; }   // tuning variants of k_pair_ll (see launch_pairwise)
+    if (!strcmp(name, "debug_barriers")) {                       // profiling aid: `value` back-to-back barriers of a decomposed run
+        for (int k = 0; k < (int)value; ++k) ORBC_TRY(mg_barrier(c));
+        return ORBC_OK;
+    }
     if (!strcmp(name, "debug_owned_fraction")) {
         // test / profiling aid: compute only the first `value` of the slots of both containers, as one rank of a decomposed run
         // would (forces and integration of the other slots are skipped; results are partial by construction)
@@ -812,10 +829,19 @@ int orbc_run_langevin(orbc_ctx *c, const orbc_step_params *p, int n_steps, int f
     q.noise_lipid = q.noise_protein = nullptr;
     for (int s = 0; s < n_steps; ++s, ++q.nstep) {
         if (q.nstep % freq_voronoi == 0) ORBC_TRY(do_rebuild(c, q.nstep, freq_sort_ctrd));
-        ORBC_TRY(launch_pairwise(c));
+        // f and t are accumulators in the reference (cleared by the integrator, integrate_langevin.h:144).  Inside this loop they are
+        // dead between the integrator and the next force evaluation, so only the first evaluation accumulates (onto whatever the
+        // caller left there) and only the last integration clears: 64 B per particle and step less traffic.
+        const bool first = s == 0 || c->pair_impl != 2, last = s + 1 == n_steps || c->pair_impl != 2;   // (the cross-check kernels always accumulate)
+        ORBC_TRY(launch_pairwise(c, first));
         ORBC_TRY(launch_bonded(c));
-        ORBC_TRY(do_integrate_langevin(c, &q, s + 1 < n_steps && (q.nstep + 1) % freq_voronoi == 0));
+        ORBC_TRY(do_integrate_langevin(c, &q, !last && (q.nstep + 1) % freq_voronoi == 0, last));
     }
+    if (mg_active(c) && n_steps > 1)     // slots this rank owned at some step but not at the last one still hold dead values: clear everything
+        for (int sp = 0; sp < 2; ++sp) if (c->sp[sp].n) {
+            ORBC_LAUNCH(c, k_zero4, blocks_for(c->sp[sp].n, kBlock), kBlock, 0, c->sp[sp].f, c->sp[sp].n, (const int *)nullptr);
+            ORBC_LAUNCH(c, k_zero4, blocks_for(c->sp[sp].n, kBlock), kBlock, 0, c->sp[sp].t, c->sp[sp].n, (const int *)nullptr);
+        }
     return ORBC_OK;
 }
 
@@ -904,6 +930,8 @@ int orbc_mg_export(orbc_ctx *c, void *blob_out, size_t bytes) { if (c) cudaSetDe
         ORBC_TRY(dev_alloc(&m.pmask, P.n + 4)); ORBC_CUDA(cudaMemsetAsync(m.pmask, 0, P.n + 4, c->stream));
         ORBC_TRY(dev_alloc(&m.need, nc)); ORBC_CUDA(cudaMemsetAsync(m.need, 0, sizeof(int) * nc, c->stream));
         ORBC_TRY(dev_alloc(&m.keep, L.n + 1));
+        { const size_t rel_need = (L.cap + 64) / 2 + 8;
+          if (c->ll_half && c->rel16_cap < rel_need) { ORBC_TRY(dev_alloc(&c->rel16, rel_need)); c->rel16_cap = rel_need; ORBC_CUDA(cudaMemsetAsync(c->rel16, 0, sizeof(uint4) * rel_need, c->stream)); } }
         // work list of the bonds with an owned atom (clipped and flagged at the capacity)
         m.my_bonds_cap = (int)std::min(c->n_bonds, c->n_bonds / w + c->n_bonds / (2 * (size_t)w) + 8192);
         ORBC_TRY(dev_alloc(&m.my_bonds, (size_t)m.my_bonds_cap + 1));

@@ -20,6 +20,7 @@ struct PairArgs {
     const int *range;      // {l0, l1, p0, p1}: the particle slots this GPU computes (everything on a single GPU)
     int cb, ce, world;     // owned cells of a decomposed run ([0, n_cells) and 1 otherwise)
     const unsigned char *dest_mask;   // decomposed: per cell, the other ranks that own a cell of its r<9 stencil
+    int accumulate;        // 1: f, t += (the reference's semantics); 0: f, t = (orbc_run_langevin, where they are known to be dead)
 };
 
 struct F3 { float x, y, z; };

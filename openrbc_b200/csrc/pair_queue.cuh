@@ -17,6 +17,8 @@
 //                  (~1 per protein per step on the RBC), so each protein-lipid pair is evaluated ONCE, here, and the lipid
 //                  receives its share through atomicAdd (fp32 RED) instead of re-testing every pair from the lipid side.
 #pragma once
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "pair.cuh"
 
@@ -31,9 +33,13 @@ struct CullTable {                 // per protein type: largest interaction rang
 };
 
 // ---- bounding spheres ------------------------------------------------------------------------------------------------------
+// It also writes every lipid's position relative to the centre of its cell's sphere in HALF precision, two lipids per 16-byte
+// record (slots 2p and 2p+1: x pair, y pair, z pair, pad) — the operands of k_pair_ll_h's packed cutoff prefilter — and raises
+// rel_flag when a component does not fit the prefilter's error budget (|rel| >= 8), which sends that step to k_pair_ll.
+constexpr float kRelMax = 8.0f;
 __global__ void k_cell_bounds(const float4 *__restrict__ centroid, int n_cells, const int *__restrict__ cs_l, const float4 *__restrict__ xl,
                               const int *__restrict__ cs_p, const float4 *__restrict__ xp, float4 *__restrict__ lbound, float4 *__restrict__ pbound,
-                              const int *__restrict__ need, int need_epoch) {
+                              const int *__restrict__ need, int need_epoch, uint4 *__restrict__ rel16, int *__restrict__ rel_flag) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n_cells) return;
     if (need && need[c] != need_epoch) return;             // decomposed run: neither owned nor halo, its particles are stale here
@@ -43,11 +49,18 @@ __global__ void k_cell_bounds(const float4 *__restrict__ centroid, int n_cells, 
         float r2 = -1.f;                                   // empty cell (or NaN centroid): never passes the test
         float4 ctr = q;
         if (!(q.x == q.x)) { ctr = e > b ? xl[b] : make_float4(0, 0, 0, 0); }
+        bool fits = true;
         for (int j = b; j < e; ++j) {
             const float4 p = xl[j];
             const float dx = p.x - ctr.x, dy = p.y - ctr.y, dz = p.z - ctr.z;
             r2 = fmaxf(r2, dx * dx + dy * dy + dz * dz);
+            if (rel16) {
+                __half *h = reinterpret_cast<__half *>(rel16 + (j >> 1)) + (j & 1);      // x pair at halves 0-1, y at 2-3, z at 4-5
+                h[0] = __float2half_rn(dx); h[2] = __float2half_rn(dy); h[4] = __float2half_rn(dz);
+                fits = fits && fabsf(dx) < kRelMax && fabsf(dy) < kRelMax && fabsf(dz) < kRelMax;
+            }
         }
+        if (!fits) atomicExch(rel_flag, 1);
         lbound[c] = make_float4(ctr.x, ctr.y, ctr.z, r2 < 0.f ? -1.f : sqrtf(r2) * 1.0001f);
     }
     if (cs_p) {
@@ -86,12 +99,16 @@ __device__ __forceinline__ int lds_i32(unsigned addr) { int v; asm volatile("ld.
 //   t_i -= alpha ua p_j                                          =>  t_i += -aua n_j + B d
 // with aua = alpha att rc^4, B = aua (n_j.u) / r, C = aua (n_i.u) / r, A1 = (F_r - 2 aua (n_i.u)(n_j.u) / r) / r.
 // n_i is the lane's own director, so its coefficient is summed as ONE scalar (sB) and applied after the loop.
-struct LLConst { float cut, rep8, att4, alpha, alpha_att, one_m_alpha; };
+struct LLConst { float cut, rep8, att4, alpha, alpha_att, one_m_alpha, cutsq; };
+// RECHECK: the queue was filled by the half-precision prefilter, which admits a few pairs just outside the cutoff (never the
+// reverse); the exact fp32 test of the reference (compute_pairwise_fused.h:109,134) decides here.
+template <bool RECHECK>
 __device__ __forceinline__ void ll_eval(const LLConst &k, const float4 *__restrict__ xl, const float4 *__restrict__ nl, F3 xi, F3 mi, int j,
                                         float &fx, float &fy, float &fz, float &tx, float &ty, float &tz, float &sB) {
     const float4 xj = __ldg(xl + j), nj = __ldg(nl + j);
     const float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
     const float r2 = dx * dx + dy * dy + dz * dz;
+    if (RECHECK && !(r2 < k.cutsq && r2 > 1e-5f)) return;
     const float rinv = rsqrt_fast(r2);
     const float r = r2 * rinv;
     const float ninj = mi.x * nj.x + mi.y * nj.y + mi.z * nj.z;
@@ -110,6 +127,50 @@ __device__ __forceinline__ void ll_eval(const LLConst &k, const float4 *__restri
     sB += B;
 }
 
+// Common tail of the lipid kernels: the n_i component of the force, (decomposed runs) the lipid side of the protein-lipid pairs
+// whose protein lives on another rank, and the store.
+__device__ __forceinline__ void ll_finish(const PairArgs &a, int i, bool live, const int *st, F3 xi, F3 mi,
+                                          float fx, float fy, float fz, float tx, float ty, float tz, float sB) {
+    fx = fmaf(sB, mi.x, fx); fy = fmaf(sB, mi.y, fy); fz = fmaf(sB, mi.z, fz);
+    if (a.world > 1 && live && a.n_p) {
+        // decomposed run: the lipid side of the protein-lipid pairs whose protein lives on another rank (that rank evaluates the
+        // protein side) — the reference's one-sided evaluation across thread ranges, compute_pairwise_fused.h:287-295
+        const int c = a.cell_l[i];
+        if (a.dest_mask[c]) {
+            const int n8 = (a.stencil_cnt[c] >> 8) & 255;
+            for (int k = 0; k < n8; ++k) {
+                const int c2 = __ldg(st + k);
+                if (c2 >= a.cb && c2 < a.ce) continue;
+                const int jb = __ldg(a.cs_p + c2), je = __ldg(a.cs_p + c2 + 1);
+                for (int j = jb; j < je; ++j) {
+                    const float4 xj = __ldg(a.xp + j);
+                    const int type = __float_as_int(xj.w);
+                    const F3 d = {xj.x - xi.x, xj.y - xi.y, xj.z - xi.z};      // x_protein - x_lipid (compute_pairwise_fused.h:167)
+                    const float r2 = dot3(d, d);
+                    if (r2 < c_ff.cutsqlp[type] && r2 > 1e-5f) {
+                        const float4 nj = __ldg(a.np + j);
+                        F3 f, q1, q2;
+                        poly48(c_ff.cutlp[type], c_ff.attlp[type], c_ff.replp[type], c_ff.alphalp[type], d, r2, {nj.x, nj.y, nj.z}, mi, f, q1, q2);
+                        fx -= f.x; fy -= f.y; fz -= f.z; tx -= q2.x; ty -= q2.y; tz -= q2.z;
+                    } else if (r2 < c_ff.lj_cutsq[type] && r2 > 1e-5f) {
+                        const F3 f = lj126(c_ff.lj_lj1[type], c_ff.lj_lj2[type], d, r2);
+                        fx -= f.x; fy -= f.y; fz -= f.z;
+                    }
+                }
+            }
+        }
+    }
+    if (live) {
+        if (a.accumulate) {
+            float4 f = a.fl[i], t = a.tl[i];
+            f.x += fx; f.y += fy; f.z += fz; t.x += tx; t.y += ty; t.z += tz;
+            a.fl[i] = f; a.tl[i] = t;
+        } else {
+            a.fl[i] = make_float4(fx, fy, fz, 0.f); a.tl[i] = make_float4(tx, ty, tz, 0.f);
+        }
+    }
+}
+
 // One thread per lipid.  A lane's candidates are the members of the cells in the r<6 stencil of its own cell; the lane walks
 // them as ONE stream, four at a time, independent of what the other lanes of the warp are looking at (lanes of one warp
 // belong to ~3 different cells with different stencils and different cell sizes — aligning them slot by slot would make every
@@ -118,8 +179,9 @@ __device__ __forceinline__ void ll_eval(const LLConst &k, const float4 *__restri
 //            hold a partner; the surviving cells are a bit mask, so culled cells cost no loop iteration
 //   phase 1  test the cutoff, push hits on the lane's queue (shared memory, slot-major: conflict-free)
 //   phase 2  drain the queue through the force body on dense lanes; the whole warp drains early if a queue could overflow
-template <bool ACCUM, bool CULL, int MINB>
-__global__ void __launch_bounds__(kLLBlock, MINB) k_pair_ll(PairArgs a, const float4 *__restrict__ lbound) {
+template <bool CULL, int MINB>
+__global__ void __launch_bounds__(kLLBlock, MINB) k_pair_ll(PairArgs a, const float4 *__restrict__ lbound, const int *__restrict__ run_if, int run_value) {
+    if (run_if && *run_if != run_value) return;                  // the packed-prefilter kernel handles this step (or the other way round)
     __shared__ int s_q[kLLBlock / 32][kQCap * 32];
     const int lane = threadIdx.x & 31;
     int *const q = s_q[threadIdx.x >> 5] + lane;
@@ -132,7 +194,7 @@ __global__ void __launch_bounds__(kLLBlock, MINB) k_pair_ll(PairArgs a, const fl
     F3 xi = {0, 0, 0}, mi = {0, 0, 0};
     const int *st = a.stencil;
     const float cutsq = c_ff.cutsqll;
-    const LLConst kc = {c_ff.cutll, 8.0f * c_ff.repll, 4.0f * c_ff.attll, c_ff.alphall, c_ff.alphall * c_ff.attll, 1.0f - c_ff.alphall};
+    const LLConst kc = {c_ff.cutll, 8.0f * c_ff.repll, 4.0f * c_ff.attll, c_ff.alphall, c_ff.alphall * c_ff.attll, 1.0f - c_ff.alphall, c_ff.cutsqll};
     unsigned keep = 0;                                           // stencil slots (<= 32 of the r<6 class) still to visit
     if (live) {
         const float4 xi4 = xl[i], ni4 = nl[i];
@@ -173,7 +235,7 @@ __global__ void __launch_bounds__(kLLBlock, MINB) k_pair_ll(PairArgs a, const fl
         }
         if (!__any_sync(0xffffffffu, rem > 0 || n_next > 0)) break;
         if (__any_sync(0xffffffffu, qp > q_full)) {              // make room: every lane drains its queue (dense)
-            for (unsigned e = q0; e < qp; e += 128) ll_eval(kc, xl, nl, xi, mi, lds_i32(e), fx, fy, fz, tx, ty, tz, sB);
+            for (unsigned e = q0; e < qp; e += 128) ll_eval<false>(kc, xl, nl, xi, mi, lds_i32(e), fx, fy, fz, tx, ty, tz, sB);
             qp = q0;
         }
         const float4 *__restrict__ p = xl + cur;
@@ -189,46 +251,122 @@ __global__ void __launch_bounds__(kLLBlock, MINB) k_pair_ll(PairArgs a, const fl
         if (rem > 0) cur += 4;
         rem -= 4;
     }
-    for (unsigned e = q0; e < qp; e += 128) ll_eval(kc, xl, nl, xi, mi, lds_i32(e), fx, fy, fz, tx, ty, tz, sB);
-    fx = fmaf(sB, mi.x, fx); fy = fmaf(sB, mi.y, fy); fz = fmaf(sB, mi.z, fz);
-    if (a.world > 1 && live && a.n_p) {
-        // decomposed run: the lipid side of the protein-lipid pairs whose protein lives on another rank (that rank evaluates the
-        // protein side) — the reference's one-sided evaluation across thread ranges, compute_pairwise_fused.h:287-295
-        const int c = a.cell_l[i];
-        if (a.dest_mask[c]) {
-            const int n8 = (a.stencil_cnt[c] >> 8) & 255;
-            for (int k = 0; k < n8; ++k) {
-                const int c2 = __ldg(st + k);
-                if (c2 >= a.cb && c2 < a.ce) continue;
-                const int jb = __ldg(a.cs_p + c2), je = __ldg(a.cs_p + c2 + 1);
-                for (int j = jb; j < je; ++j) {
-                    const float4 xj = __ldg(a.xp + j);
-                    const int type = __float_as_int(xj.w);
-                    const F3 d = {xj.x - xi.x, xj.y - xi.y, xj.z - xi.z};      // x_protein - x_lipid (compute_pairwise_fused.h:167)
-                    const float r2 = dot3(d, d);
-                    if (r2 < c_ff.cutsqlp[type] && r2 > 1e-5f) {
-                        const float4 nj = __ldg(a.np + j);
-                        F3 f, q1, q2;
-                        poly48(c_ff.cutlp[type], c_ff.attlp[type], c_ff.replp[type], c_ff.alphalp[type], d, r2, {nj.x, nj.y, nj.z}, mi, f, q1, q2);
-                        fx -= f.x; fy -= f.y; fz -= f.z; tx -= q2.x; ty -= q2.y; tz -= q2.z;
-                    } else if (r2 < c_ff.lj_cutsq[type] && r2 > 1e-5f) {
-                        const F3 f = lj126(c_ff.lj_lj1[type], c_ff.lj_lj2[type], d, r2);
-                        fx -= f.x; fy -= f.y; fz -= f.z;
-                    }
-                }
-            }
-        }
-    }
-    if (live) {
-        if (ACCUM) {
-            float4 f = a.fl[i], t = a.tl[i];
-            f.x += fx; f.y += fy; f.z += fz; t.x += tx; t.y += ty; t.z += tz;
-            a.fl[i] = f; a.tl[i] = t;
-        } else {
-            a.fl[i] = make_float4(fx, fy, fz, 0.f); a.tl[i] = make_float4(tx, ty, tz, 0.f);
-        }
-    }
+    for (unsigned e = q0; e < qp; e += 128) ll_eval<false>(kc, xl, nl, xi, mi, lds_i32(e), fx, fy, fz, tx, ty, tz, sB);
+    ll_finish(a, i, live, st, xi, mi, fx, fy, fz, tx, ty, tz, sB);
 }
+
+// ---- k_pair_ll_h (EXPERIMENTAL, off by default: option "ll_half"): the cutoff test of phase 1 in packed half precision ---------
+// Measured on the full RBC (profiles/r01_half_prefilter.txt): exact (hits, order and forces bit-identical to k_pair_ll), the
+// packed test is 25 % cheaper than the fp32 one (16 instructions per two partners), but the kernel as a whole is SLOWER (540-590
+// vs 487 us): queues fill 3 % fuller and drain less densely, the re-test and the per-cell frame shift cost instructions, and the
+// 2-byte scattered stores that produce the records add 70 us to k_cell_bounds.  Kept as a measured negative result.
+// Phase 1 is two thirds of k_pair_ll's instructions and 81 % of the pairs it tests are beyond the cutoff.  Here it runs on the
+// cell-relative half-precision records written by k_cell_bounds, two partners per instruction (sub / mul / fma.f16x2, one
+// setp.lt.f16x2 for both): 6.5 instead of 11 instructions per candidate and half the bytes.  It is a PREFILTER: the limit is
+// cutsq + kHalfMargin, so that no pair the reference's fp32 test (r2 < 6.76) admits can be missed — with |rel| < 8 the
+// partner's record is off by <= 2^-8, the lane's own position (fp32, shifted into the partner cell's frame, rounded once) by
+// <= 2^-8, the difference by <= 2^-10 where it matters (|d| < 4), i.e. <= 0.009 per component and <= 0.09 in r2, plus three
+// half-precision roundings of r2 (<= 0.012).  Phase 2 re-tests every queued pair exactly (ll_eval<true>), so the hits, their
+// order and the forces are bit-identical to k_pair_ll's.  k_cell_bounds raises rel_flag when a lipid strays further than 8
+// from its cell's origin; that step then runs through k_pair_ll instead (both kernels are launched, one returns at once).
+constexpr float kHalfMargin = 0.2f;
+__device__ __forceinline__ unsigned h2_bcast(float v) { const __half2 h = __float2half2_rn(v); return *reinterpret_cast<const unsigned *>(&h); }
+
+// one record (two partners, slots j0 and j0 + 1 = positions s0, s0 + 1 of the lane's current run): test both, queue the hits
+#define ORBC_LL_PAIR(REC, S0, FIRST)                                                                                            \
+    asm volatile("{\n"                                                                                                          \
+                 ".reg .b32 dx, dy, dz, r2;\n"                                                                                  \
+                 ".reg .pred p, q;\n"                                                                                           \
+                 "sub.f16x2 dx, %1, %4;\n"                                                                                      \
+                 "sub.f16x2 dy, %2, %5;\n"                                                                                      \
+                 "sub.f16x2 dz, %3, %6;\n"                                                                                      \
+                 "mul.f16x2 r2, dx, dx;\n"                                                                                      \
+                 "fma.rn.f16x2 r2, dy, dy, r2;\n"                                                                               \
+                 "fma.rn.f16x2 r2, dz, dz, r2;\n"                                                                               \
+                 "setp.lt.f16x2 p|q, r2, %7;\n"                                                                                 \
+                 "setp.gt.and.s32 p, %8, %9, p;\n"                                                                              \
+                 "setp.gt.and.s32 q, %8, %10, q;\n"                                                                             \
+                 "setp.eq.and.s32 p, %13, 0, p;\n"                                                                              \
+                 "@p st.shared.b32 [%0], %11;\n"                                                                                \
+                 "@p add.u32 %0, %0, 128;\n"                                                                                    \
+                 "@q st.shared.b32 [%0], %12;\n"                                                                                \
+                 "@q add.u32 %0, %0, 128;\n"                                                                                    \
+                 "}"                                                                                                            \
+                 : "+r"(qp)                                                                                                     \
+                 : "r"(xh), "r"(yh), "r"(zh), "r"((REC).x), "r"((REC).y), "r"((REC).z), "r"(lim), "r"(rem), "n"(S0), "n"((S0) + 1),      \
+                   "r"(cur + (S0)), "r"(cur + (S0) + 1), "r"((FIRST) ? skip : 0)                                                  \
+                 : "memory")
+
+template <int MINB>
+__global__ void __launch_bounds__(kLLBlock, MINB) k_pair_ll_h(PairArgs a, const float4 *__restrict__ lbound, const uint4 *__restrict__ rel16,
+                                                               const int *__restrict__ run_if, int run_value) {
+    if (run_if && *run_if != run_value) return;
+    __shared__ int s_q[kLLBlock / 32][kQCap * 32];
+    const int lane = threadIdx.x & 31;
+    int *const q = s_q[threadIdx.x >> 5] + lane;
+    const int i = a.range[0] + blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i < a.range[1];
+    const float4 *__restrict__ xl = a.xl;
+    const float4 *__restrict__ nl = a.nl;
+    const int *__restrict__ cs = a.cs_l;
+    float fx = 0, fy = 0, fz = 0, tx = 0, ty = 0, tz = 0, sB = 0;
+    F3 xi = {0, 0, 0}, mi = {0, 0, 0};
+    const int *st = a.stencil;
+    const LLConst kc = {c_ff.cutll, 8.0f * c_ff.repll, 4.0f * c_ff.attll, c_ff.alphall, c_ff.alphall * c_ff.attll, 1.0f - c_ff.alphall, c_ff.cutsqll};
+    const unsigned lim = h2_bcast(c_ff.cutsqll + kHalfMargin);
+    unsigned keep = 0;                                           // stencil slots (<= 32 of the r<6 class) still to visit
+    if (live) {
+        const float4 xi4 = xl[i], ni4 = nl[i];
+        xi = {xi4.x, xi4.y, xi4.z}; mi = {ni4.x, ni4.y, ni4.z};
+        const int c = a.cell_l[i];
+        const int n6 = min(a.stencil_cnt[c] & 255, 32);
+        st += (size_t)c * kStencilStride;
+        keep = n6 >= 32 ? 0xffffffffu : (1u << n6) - 1u;
+    }
+    const unsigned q0 = (unsigned)__cvta_generic_to_shared(q);
+    const unsigned q_full = q0 + (kQCap - 8) * 128;              // a group of eight always fits below this mark
+    unsigned qp = q0;
+    // two-deep prefetch: (c2_n, jb_n, len_n) = id and member range of the next cell, c2_nn = id of the one after it; the sphere
+    // record of a cell (its frame origin) is pulled into L1 one advance before it is read
+    int n_next = __popc(keep), c2_n = 0, jb_n = 0, len_n = 0, c2_nn = 0;
+    if (n_next > 0) { c2_n = __ldg(st + (__ffs(keep) - 1)); keep &= keep - 1; jb_n = __ldg(cs + c2_n); len_n = __ldg(cs + c2_n + 1) - jb_n; }
+    if (n_next > 1) { c2_nn = __ldg(st + (__ffs(keep) - 1)); keep &= keep - 1; }
+    // cur = even slot the current run is read from, rem = slots of the run still to test counted from cur, skip = 1 when the run
+    // starts on an odd slot (the first half of its first record belongs to the previous cell)
+    int cur = 0, rem = 0, skip = 0;
+    unsigned xh = 0, yh = 0, zh = 0;                             // the lane's position in the current cell's frame, half2-broadcast
+    for (;;) {
+        if (rem <= 0 && n_next > 0) {                            // advance to the next cell of the stencil
+            const float4 o = __ldg(lbound + c2_n);
+            xh = h2_bcast(xi.x - o.x); yh = h2_bcast(xi.y - o.y); zh = h2_bcast(xi.z - o.z);
+            skip = jb_n & 1; cur = jb_n - skip; rem = len_n + skip; --n_next;
+            if (n_next > 0) {
+                c2_n = c2_nn; jb_n = __ldg(cs + c2_n); len_n = __ldg(cs + c2_n + 1) - jb_n;
+                asm volatile("prefetch.global.L1 [%0];" :: "l"(lbound + c2_n));
+            }
+            if (n_next > 1) { c2_nn = __ldg(st + (__ffs(keep) - 1)); keep &= keep - 1; }
+        }
+        if (!__any_sync(0xffffffffu, rem > 0 || n_next > 0)) break;
+        if (__any_sync(0xffffffffu, qp > q_full)) {              // make room: every lane drains its queue (dense)
+            for (unsigned e = q0; e < qp; e += 128) ll_eval<true>(kc, xl, nl, xi, mi, lds_i32(e), fx, fy, fz, tx, ty, tz, sB);
+            qp = q0;
+        }
+        const uint4 *__restrict__ p = rel16 + (cur >> 1);
+        uint4 rec[4];
+        #pragma unroll
+        for (int u = 0; u < 4; ++u) rec[u] = __ldg(p + u);
+        ORBC_LL_PAIR(rec[0], 0, true);
+        ORBC_LL_PAIR(rec[1], 2, false);
+        ORBC_LL_PAIR(rec[2], 4, false);
+        ORBC_LL_PAIR(rec[3], 6, false);
+        skip = 0;
+        if (rem > 0) cur += 8;
+        rem -= 8;
+    }
+    for (unsigned e = q0; e < qp; e += 128) ll_eval<true>(kc, xl, nl, xi, mi, lds_i32(e), fx, fy, fz, tx, ty, tz, sB);
+    ll_finish(a, i, live, st, xi, mi, fx, fy, fz, tx, ty, tz, sB);
+}
+#undef ORBC_LL_PAIR
 
 // ---- proteins -------------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void atomic_add3(float4 *dst, float x, float y, float z) {
@@ -393,8 +531,9 @@ __global__ void __launch_bounds__(kPBlock, 16) k_pair_prot(PairArgs a, const flo
         fx += __shfl_xor_sync(0xffffffffu, fx, o); fy += __shfl_xor_sync(0xffffffffu, fy, o); fz += __shfl_xor_sync(0xffffffffu, fz, o);
         tx += __shfl_xor_sync(0xffffffffu, tx, o); ty += __shfl_xor_sync(0xffffffffu, ty, o); tz += __shfl_xor_sync(0xffffffffu, tz, o);
     }
-    if (live && sub == 0) {                                      // this lane owns protein i: plain read-modify-write
-        float4 f = a.fp[i], t = a.tp[i];
+    if (live && sub == 0) {                                      // this lane owns protein i: plain read-modify-write, or plain write
+        float4 f = make_float4(0.f, 0.f, 0.f, 0.f), t = f;
+        if (a.accumulate) { f = a.fp[i]; t = a.tp[i]; }
         f.x += fx; f.y += fy; f.z += fz; t.x += tx; t.y += ty; t.z += tz;
         a.fp[i] = f; a.tp[i] = t;
     }

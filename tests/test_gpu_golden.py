@@ -141,3 +141,41 @@ def test_counter_based_rng_matches_port_and_law():
     assert z.min() >= -1.0 and z.max() <= 1.0
     assert abs(z.mean()) < 1e-2 and abs(z.var() - 1 / 3) < 1e-2
     sim.close()
+
+
+@pytest.mark.parametrize("name", FILES)
+def test_half_precision_prefilter_is_exact(name):
+    """k_pair_ll_h tests the cutoff in packed half precision as a PREFILTER (limit cutsq + margin) and re-tests the queued pairs in
+    fp32: hits, their order and therefore the forces must be bit-identical to the fp32 kernel's.  A lipid further than 8 from
+    its cell's origin exceeds the prefilter's error budget: k_cell_bounds raises the flag and the step runs on the fp32 kernel."""
+    from openrbc_b200 import Simulation
+    g = load(name)
+    st = state_of(g, "in")
+    out = {}
+    for mode in (0, 1, 2):
+        sim = Simulation(st, kBT=0.0)
+        sim.set_option("ll_half", mode)
+        sim.compute_pairwise_fused()
+        out[mode] = sim.download(0, "ft")
+        sim.close()
+    exact = len(st["px"]) == 0            # protein -> lipid reactions arrive by atomics: their order is not fixed
+    for mode in (1, 2):
+        for k in "ft":
+            if exact:
+                np.testing.assert_array_equal(out[mode][k], out[0][k])
+            else:
+                assert rel_err(out[mode][k], out[0][k]) < 1e-6
+    # a stray lipid: 9.5 away from where its cell's origin expects it
+    st2 = dict(st); st2["lx"] = st["lx"].copy(); st2["lx"][7] += np.float32(9.5) * st["ln"][7] / np.linalg.norm(st["ln"][7])
+    res = []
+    for mode in (0, 1):
+        sim = Simulation(st2, kBT=0.0)
+        sim.set_option("ll_half", mode)
+        sim.compute_pairwise_fused()
+        res.append(sim.download(0, "ft"))
+        sim.close()
+    for k in "ft":
+        if exact:
+            np.testing.assert_array_equal(res[1][k], res[0][k])
+        else:
+            assert rel_err(res[1][k], res[0][k]) < 1e-6

@@ -86,6 +86,17 @@ for rep in range(2):
     wall = time.perf_counter() - t0
     n = len(st["lx"]) + len(st["px"])
     print(f"40 steps: max over ranks {max(ms) / 40 * 1e3:.0f} us/step -> {n * 40 / (max(ms) * 1e-3) / 1e9:.3f} G particle-steps/s (wall {wall * 1e3 / 40:.3f} ms/step)", flush=True)
+def barriers(s, n):
+    s.event_record(0)
+    s.set_option("debug_barriers", n)
+    s.event_record(1)
+    s.synchronize()
+    ms[s.rank] = s.event_elapsed_ms(0, 1)
+
+
+on_all(lambda s: barriers(s, 200))
+on_all(lambda s: barriers(s, 200))
+print(f"200 back-to-back barriers: {max(ms) / 200 * 1e3:.2f} us each")
 sims[0].profile_enable(True)
 on_all(lambda s: timed(s, 20))
 print("rank 0 per class (us/step):", {k: round(sims[0].profile_read(k)[0] / 20 * 1e3, 1) for k in orbc.engine.PROF})
