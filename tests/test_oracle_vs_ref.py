@@ -2,6 +2,8 @@
 headers of /root/reference/src compiled behind oracle/ref_harness.cpp (strict IEEE flags, one thread).
 Integer structures must be equal; single-call fp32 outputs are bit-exact where the summation order
 is the same and within 2e-5 where only the stencil visiting order differs."""
+import ctypes
+
 import numpy as np
 import pytest
 
@@ -212,8 +214,16 @@ def test_constrain_volume():
     cs = r.cell_array(0, "cell_start")
     assert (np.diff(cs) > 0).all()
     r.integrate(refmod.CLEAR_FORCE)
-    r.constrain_volume(3.15, 0.05)
+    # the scratch comes from malloc uninitialised: garbage (NaN included) would stick for ever.  glibc's M_PERTURB (-6)
+    # with 255 makes every fresh allocation come back as zeros for the duration of the first call.
+    libc = ctypes.CDLL(None)
+    libc.mallopt(-6, 255)
+    try:
+        r.constrain_volume(3.15, 0.05)
+    finally:
+        libc.mallopt(-6, 0)
     fl = r.get(0, "f")
+    assert np.isfinite(fl).all()
     c = r.centroids()
     nrm = fl[cs[:-1]] / np.linalg.norm(fl[cs[:-1]], axis=1, keepdims=True)
     outward = ((c - c.mean(0)) * nrm).sum(1)
