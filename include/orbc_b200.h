@@ -61,7 +61,8 @@ typedef enum {
     ORBC_NH_FINAL_FUSED = 5,     /* post_toque_final_update                   integrate_nh.h:237-273 */
     ORBC_NH_FINAL = 6,           /* verlet_nh_final                           integrate_nh.h:156-176 */
     ORBC_NH_UPDATE = 7,          /* verlet_nh_update (KE only)                integrate_nh.h:69-94   */
-    ORBC_OPT_MOVE = 9            /* steepest-descent mover                    openrbc.cpp:114-131    */
+    ORBC_OPT_MOVE = 9,           /* steepest-descent mover                    openrbc.cpp:114-131    */
+    ORBC_OPT_FUSED = 10          /* post_torque + mover + bounce_back in one pass: openrbc.cpp:110-133 (f is kept, t becomes n x t) */
 } orbc_integrator;
 
 /* The RTParameter fields the kernels read (runtime_parameter.h:38-80). */
@@ -127,6 +128,9 @@ ORBC_API int  orbc_delete_lipid(orbc_ctx *ctx, float stray_tolerance, size_t *n_
 ORBC_API int  orbc_compute_pairwise_fused(orbc_ctx *ctx);   /* compute_pairwise_fused.h:238-320; accumulates into f, t */
 ORBC_API int  orbc_compute_bonded(orbc_ctx *ctx);           /* compute_bonded.h:89-146; accumulates into protein f */
 ORBC_API int  orbc_constrain_volume(orbc_ctx *ctx, float target_volume, float strength, float *volume_out); /* constrain_volume.h:26-83 */
+/* switch for the (commented-out) call of openrbc.cpp:229: when on, orbc_run_langevin / orbc_run_nh apply constrain_volume(target,
+ * strength) between compute_bonded and the integrator of every step (BASELINE configs[2]: 3.15, 0.05) */
+ORBC_API int  orbc_set_volume_constraint(orbc_ctx *ctx, int on, float target_volume, float strength);
 
 /* ---- integrators ------------------------------------------------------------------------------------------- */
 /* integrate(KERNEL&&, lipid, protein) — integrate_nh.h:29-37.  The Nose-Hoover kernels return (ke, n); the zeta update
@@ -139,6 +143,10 @@ ORBC_API int  orbc_compute_temperature(orbc_ctx *ctx, double *temperature);   /*
 /* n_steps of: [rebuild if nstep % freq_voronoi == 0] -> pair forces -> bonded -> verlet_langevin, with no host
  * synchronisation inside.  p->nstep is the first step's index. */
 ORBC_API int  orbc_run_langevin(orbc_ctx *ctx, const orbc_step_params *p, int n_steps, int freq_voronoi, int freq_sort_ctrd);
+/* the energy-minimisation loop, openrbc.cpp:88-133: n_steps of rebuild (Morton sort included: param.nstep stays 0 there) ->
+ * clear_force -> pair forces -> bonded -> post_torque -> capped steepest-descent move -> bounce_back, the last three as one
+ * kernel.  Uses p->dt, dr_opt, dn_opt, box.  On return f holds the last forces and t the last n x t, as in the reference. */
+ORBC_API int  orbc_run_minimize(orbc_ctx *ctx, const orbc_step_params *p, int n_steps, int freq_sort_ctrd);
 /* same for the Nose-Hoover build (openrbc.cpp:192-241); zeta/Q are updated on the device and returned */
 ORBC_API int  orbc_run_nh(orbc_ctx *ctx, const orbc_step_params *p, int n_steps, int freq_voronoi, int freq_sort_ctrd, float *zeta_inout, float *Q_inout);
 
@@ -151,7 +159,8 @@ ORBC_API int  orbc_run_nh(orbc_ctx *ctx, const orbc_step_params *p, int n_steps,
  * orbc_rebuild / orbc_compute_pairwise_fused / orbc_compute_bonded / orbc_integrate(VERLET_LANGEVIN) / orbc_run_langevin work on
  * the rank's own cells; halo copies, particle migration and the synchronisation between ranks happen on the device over
  * NVLink (peer stores and epoch flags), with no host synchronisation and no collective library on the data path.
- * Every rank must issue the same sequence of calls. */
+ * orbc_constrain_volume, orbc_integrate(NH_*_FUSED / OPT_FUSED), orbc_run_nh, orbc_run_minimize and orbc_delete_lipid are decomposed
+ * the same way.  Every rank must issue the same sequence of calls. */
 ORBC_API int  orbc_mg_init(orbc_ctx *ctx, int rank, int world /* <= 8 */);
 ORBC_API size_t orbc_mg_blob_bytes(void);
 /* cells [begin, end) that rank `rank` of `world` owns: the reference's static range partition, util_numa.h:41-42 (host-only helper) */
@@ -167,6 +176,19 @@ ORBC_API int  orbc_mg_range(orbc_ctx *ctx, int species, size_t *begin, size_t *e
 ORBC_API int  orbc_download(orbc_ctx *ctx, int species, size_t stride_floats,
                             float *x, float *v, float *n_, float *o, float *f, float *t,
                             int *affiliation, int *type, int *tag, size_t *n);
+/* save_frame (trajectory.h:61-105) with update_particle_affiliation (voronoi.h:166-175) folded in: the frame is assembled on
+ * the device in the .orbc byte layout (FRAMEBEG nstep NATOM n IDENTITY ... FRAMEEND, lipids before proteins, the sections that
+ * dump_field selects: DumpField bits of runtime_parameter.h:30-36) and leaves the GPU as ONE copy; the host appends the bytes
+ * to its trajectory stream.  lipid_tag_base = LipidContainer::tag.base (container.h:122-126, default 1).
+ *   orbc_save_frame        synchronous, into the caller's buffer (orbc_frame_bytes tells its size)
+ *   orbc_save_frame_begin  packs on the context's stream and starts the copy into a pinned buffer of the library on a second
+ *                          stream; the run continues meanwhile.  At most two frames in flight.
+ *   orbc_save_frame_end    waits for the oldest frame in flight; *data stays valid until the next-but-one _begin.
+ * Decomposed run: a rank's image holds the titles and the slots it owns, zeros elsewhere (OR the images of all ranks). */
+ORBC_API int  orbc_frame_bytes(orbc_ctx *ctx, int dump_field, size_t *bytes);
+ORBC_API int  orbc_save_frame(orbc_ctx *ctx, int nstep, int dump_field, int lipid_tag_base, void *dst, size_t cap, size_t *bytes);
+ORBC_API int  orbc_save_frame_begin(orbc_ctx *ctx, int nstep, int dump_field, int lipid_tag_base);
+ORBC_API int  orbc_save_frame_end(orbc_ctx *ctx, const void **data, size_t *bytes);
 ORBC_API int  orbc_size(orbc_ctx *ctx, int species, size_t *n);
 ORBC_API int  orbc_n_cells(orbc_ctx *ctx, int *n_cells);
 

@@ -82,6 +82,8 @@ struct PeerTable {
     int *tag2idx[kMaxWorld];
     unsigned *flags[kMaxWorld];           // barrier epochs, one slot per writer
     double *ke_all[kMaxWorld];            // partial kinetic energies, one slot per writer
+    double *vol_all[kMaxWorld];           // partial volumes of constrain_volume, one slot per writer
+    int *cv_ptype[kMaxWorld];             // type of the protein in slot c, c < n_cells (constrain_volume.h:73 indexes it by CELL)
 };
 struct Decomp {
     bool on = false, connected = false;
@@ -93,7 +95,11 @@ struct Decomp {
     int cen_par = 0;                      // which of the two centroid buffers is current (they swap on rebuilds)
     float4 *cen_buf[2] = {nullptr, nullptr};
     unsigned *flags = nullptr;            // kMaxWorld epochs written by the peers
-    double *ke_all = nullptr;             // kMaxWorld partial kinetic energies written by the peers
+    double *ke_all = nullptr;             // 2 x kMaxWorld partial kinetic energies written by the peers, halves used alternately
+    int ke_par = 0;
+    double *vol_all = nullptr;            // 2 x kMaxWorld partial volumes written by the peers (constrain_volume), halves used alternately
+    int cv_par = 0;
+    int *cv_ptype = nullptr;              // n_cells protein types by slot, written by the slots' owners (constrain_volume)
     int *cnt_all[2] = {nullptr, nullptr}; // world rows of arrival counts per species (row r written by rank r)
     int *off_me[2] = {nullptr, nullptr};  // members of each cell that come from lower ranks
     int *cnt_prev[2] = {nullptr, nullptr};// this rank's counts at the previous exchange (which entries the peers hold non-zero)
@@ -152,6 +158,15 @@ struct orbc_ctx {
     int ll_variant = 1;
     int prot_lanes = 0;                            // lanes per protein in k_pair_prot (0 = by the number of owned proteins)
     int *d_range = nullptr;                               // {l0, l1, p0, p1}: particle slots this context computes (all of them on one GPU)
+    // volume constraint inside the whole-loop entry points (openrbc.cpp:229)
+    bool cv_on = false; float cv_target = 0.f, cv_strength = 0.f;
+    // save_frame: frame image assembled on the device, copied out on a second stream into two pinned buffers
+    unsigned char *frame_dev[2] = {nullptr, nullptr}; size_t frame_dev_cap[2] = {0, 0};
+    unsigned char *frame_host[2] = {nullptr, nullptr}; size_t frame_host_cap[2] = {0, 0};
+    size_t frame_bytes[2] = {0, 0};
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t frame_packed[2] = {}, frame_copied[2] = {};
+    int frame_head = 0, frame_pending = 0;                // ring of two frames in flight
     orbc::Decomp mg;
     // per-class event-pair profiling (orbc_profile_*)
     bool prof_on = false;

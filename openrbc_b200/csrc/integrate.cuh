@@ -249,6 +249,45 @@ __global__ void k_opt_move(IntegArgs a) {
     a.nn[i] = make_float4(gx * s, gy * s, gz * s, n4.w);
 }
 
+// One iteration of the energy-minimisation loop behind the forces (openrbc.cpp:110-133) as ONE pass: post_torque
+// (integrate_nh.h:146-154), the capped steepest-descent mover (openrbc.cpp:114-131, same arithmetic as k_opt_move) and
+// bounce_back (integrate_nh.h:124-144); `clear` also does the clear_force of the next iteration (openrbc.cpp:94).  Range-based
+// and out of place like k_verlet_langevin, so it also serves a decomposed run (halo push fused in).
+__global__ void __launch_bounds__(256) k_opt_fused(IntegArgs a) {
+    const size_t i = (size_t)a.range[0] + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)a.range[1]) return;
+    float4 x = a.x[i], n4 = a.nn[i];
+    const float4 f = a.f[i], t0 = a.t[i];
+    const F3 t = cross3({n4.x, n4.y, n4.z}, {t0.x, t0.y, t0.z});                 // post_torque
+    const float m = c_ff.mass[__float_as_int(x.w)];
+    const float dxn = sqrtf((f.x / m) * (f.x / m) + (f.y / m) * (f.y / m) + (f.z / m) * (f.z / m));
+    const F3 dn = cross3(t, {n4.x, n4.y, n4.z});
+    const float dnn = sqrtf(dn.x * dn.x + dn.y * dn.y + dn.z * dn.z);
+    double dt = a.dt_d;
+    if (dxn > a.dr_opt || dnn > a.dn_opt) dt = fmin(a.dr_opt / dxn, a.dn_opt / dnn);
+    const float sx = (float)(dt / m), sn = (float)dt;
+    x.x += f.x * sx; x.y += f.y * sx; x.z += f.z * sx;
+    const float gx = n4.x + dn.x * sn, gy = n4.y + dn.y * sn, gz = n4.z + dn.z * sn;
+    const float s = 1.0f / sqrtf(gx * gx + gy * gy + gz * gz);
+    const float4 nnew = make_float4(gx * s, gy * s, gz * s, n4.w);
+    if (x.x < a.dlo || x.x > a.dhi || x.y < a.dlo || x.y > a.dhi || x.z < a.dlo || x.z > a.dhi) {   // bounce_back (rare)
+        float4 v = a.v[i];
+        bounce(x.x, v.x, a.dlo, a.dhi); bounce(x.y, v.y, a.dlo, a.dhi); bounce(x.z, v.z, a.dlo, a.dhi);
+        a.v[i] = v;
+    }
+    a.x_out[i] = x; a.nn_out[i] = nnew;
+    if (a.clear) { a.f[i] = make_float4(0, 0, 0, 0); a.t[i] = make_float4(0, 0, 0, 0); }
+    else a.t[i] = make_float4(t.x, t.y, t.z, 0);
+    if (a.push.world > 1) {
+        unsigned msk = a.push.cell_mask[a.push.cellid[i]];
+        if (a.push.pmask) msk |= a.push.pmask[i];
+        while (msk) {
+            const int r = __ffs(msk) - 1; msk &= msk - 1;
+            a.push.x[r][i] = x; a.push.nn[r][i] = nnew;
+        }
+    }
+}
+
 // Nose-Hoover friction update of the functor destructors (integrate_nh.h:181-185,240-244), on the device for orbc_run_nh:
 // nh[0] = zeta, nh[1] = Q; acc[0] = KE (consumed and reset)
 // Decomposed run: ke_all holds one partial kinetic energy per rank (k_share_ke + barrier); they are summed in rank order, so
@@ -276,21 +315,27 @@ __global__ void k_sum_ke(double *acc, const double *ke_all, int world) {
 }
 
 // ---- constrain_volume.h:26-83 ------------------------------------------------------------------------------------------------
-// pass 1: acc[1..3] += centroid sum
-__global__ void __launch_bounds__(256) k_cv_center(const float4 *__restrict__ centroid, int n_cells, double *acc) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+// pass 1: acc[1..3] = centroid sum.  One block, fixed summation order: every rank of a decomposed run holds all the centroids
+// and must arrive at the same centre.
+__global__ void __launch_bounds__(1024) k_cv_center(const float4 *__restrict__ centroid, int n_cells, double *acc) {
+    __shared__ double s[3][1024];
     double x = 0, y = 0, z = 0;
-    if (i < n_cells) { const float4 c = centroid[i]; x = c.x; y = c.y; z = c.z; }
-    block_add_double(x, acc + 1); __syncthreads();
-    block_add_double(y, acc + 2); __syncthreads();
-    block_add_double(z, acc + 3);
+    for (int i = threadIdx.x; i < n_cells; i += 1024) { const float4 c = centroid[i]; x += c.x; y += c.y; z += c.z; }
+    s[0][threadIdx.x] = x; s[1][threadIdx.x] = y; s[2][threadIdx.x] = z;
+    __syncthreads();
+    for (int d = 512; d > 0; d >>= 1) {
+        if (threadIdx.x < d) { s[0][threadIdx.x] += s[0][threadIdx.x + d]; s[1][threadIdx.x] += s[1][threadIdx.x + d]; s[2][threadIdx.x] += s[2][threadIdx.x + d]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { acc[1] = s[0][0]; acc[2] = s[1][0]; acc[3] = s[2][0]; }
 }
-// pass 2: per cell outward normal (persistent scratch, never cleared — constrain_volume.h:34,55) and volume, acc[4] += volume
-__global__ void __launch_bounds__(256) k_cv_normal_volume(const float4 *__restrict__ centroid, int n_cells, const int *__restrict__ cs_l, const float4 *__restrict__ nl,
+// pass 2, cells [cb, ce): per cell outward normal (persistent scratch, never cleared — constrain_volume.h:34,55) and volume,
+// acc[4] += volume of these cells
+__global__ void __launch_bounds__(256) k_cv_normal_volume(const float4 *__restrict__ centroid, int n_cells, int cb, int ce, const int *__restrict__ cs_l, const float4 *__restrict__ nl,
                                                            float4 *__restrict__ cell_normal, double *acc) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = cb + blockIdx.x * blockDim.x + threadIdx.x;
     double vol = 0.0;
-    if (i < n_cells) {
+    if (i < ce) {
         const float cx = (float)acc[1] / n_cells, cy = (float)acc[2] / n_cells, cz = (float)acc[3] / n_cells;
         float4 cn = cell_normal[i];
         const int b = cs_l[i], e = cs_l[i + 1];
@@ -306,17 +351,43 @@ __global__ void __launch_bounds__(256) k_cv_normal_volume(const float4 *__restri
     }
     block_add_double(vol, acc + 4);
 }
+// decomposed run: this rank's partial volume -> slot `rank` of every rank's vol_all, and the types of the owned protein slots
+// below n_cells -> every rank's cv_ptype (pass 3 indexes the protein mass by the CELL index); a barrier follows
+struct CvShare { double *vol[kMaxWorld]; int *ptype[kMaxWorld]; };
+__global__ void k_cv_share(const double *__restrict__ acc, const float4 *__restrict__ xp, const int *__restrict__ range, int n_cells, int rank, int world, CvShare d) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < world) d.vol[k][rank] = acc[4];
+    const int i = range[2] + k;
+    if (i < range[3] && i < n_cells) {
+        const int t = __float_as_int(xp[i].w);
+        for (int r = 0; r < world; ++r) d.ptype[r][i] = t;
+    }
+}
+__global__ void k_sum_partials(double *dst, const double *all, int world) {
+    if (threadIdx.x || blockIdx.x) return;
+    double s = 0.0; for (int r = 0; r < world; ++r) s += all[r];
+    *dst = s;
+}
 // pass 3: f += strength (V0 - V) / V0 * normal * mass[type[CELL index]] — the reference indexes the mass by the cell index
 // (constrain_volume.h:70,73): lipid.type[i] is always 0, prote.type[i] is the type of protein number i.
-__global__ void k_cv_apply(const int *__restrict__ cellid, size_t n, const float4 *__restrict__ cell_normal, const float4 *__restrict__ type_src, size_t n_type_src,
-                           float target, float strength, const double *acc, float4 *__restrict__ f) {
-    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
+// slots [range[0], range[1]); the protein type comes from the container (type_src, one GPU) or from cv_ptype (decomposed);
+// the volume is acc[4] (one GPU) or the sum of the ranks' partial volumes in rank order (vol_all)
+__global__ void k_cv_apply(const int *__restrict__ cellid, const int *__restrict__ range, const float4 *__restrict__ cell_normal, const float4 *__restrict__ type_src, size_t n_type_src,
+                           const int *__restrict__ ptype, int is_protein, float target, float strength, const double *acc, const double *vol_all, int world, float4 *__restrict__ f) {
+    const size_t j = (size_t)range[0] + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= (size_t)range[1]) return;
     const int c = cellid[j];
-    const float volume = (float)acc[4];
+    double vsum = acc[4];
+    if (vol_all) { vsum = 0.0; for (int r = 0; r < world; ++r) vsum += vol_all[r]; }
+    const float volume = (float)vsum;
     const float fs = strength * (target - volume) / target;
     float m = c_ff.mass[0];
-    if (type_src) m = c_ff.mass[(size_t)c < n_type_src ? __float_as_int(type_src[c].w) : 0];
+    if (is_protein) {
+        int t = 0;
+        if (ptype) t = ptype[c];
+        else if ((size_t)c < n_type_src) t = __float_as_int(type_src[c].w);
+        m = c_ff.mass[t];
+    }
     const float4 cn = cell_normal[c];
     float4 ff = f[j];
     ff.x += fs * cn.x * m; ff.y += fs * cn.y * m; ff.z += fs * cn.z * m;

@@ -147,15 +147,18 @@ inline int mg_barrier(orbc_ctx *c) {
     return ORBC_OK;
 }
 
+// two sets of slots used alternately: a fast rank may publish its next partial sum while a slow one still reads this set
+inline const double *mg_ke_slots(const orbc_ctx *c) { return c->mg.ke_all + c->mg.ke_par * kMaxWorld; }
 inline int mg_share_ke(orbc_ctx *c) {
     if (!mg_active(c)) return ORBC_OK;
-    KeDst d; for (int r = 0; r < kMaxWorld; ++r) d.dst[r] = c->mg.peers.ke_all[r];
+    c->mg.ke_par ^= 1;
+    KeDst d; for (int r = 0; r < kMaxWorld; ++r) d.dst[r] = c->mg.peers.ke_all[r] + c->mg.ke_par * kMaxWorld;
     ORBC_LAUNCH(c, k_share_ke, 1, 32, 0, c->d_acc, c->mg.rank, c->mg.world, d);
     return ORBC_OK;
 }
 
 // the pointers peers write through, in a fixed order (identical on every rank)
-constexpr int kMgShared = 27;
+constexpr int kMgShared = 29;
 inline void mg_shared_list(orbc_ctx *c, void *out[kMgShared]) {
     int k = 0;
     for (int s = 0; s < 2; ++s) for (int b = 0; b < 2; ++b) {
@@ -165,6 +168,7 @@ inline void mg_shared_list(orbc_ctx *c, void *out[kMgShared]) {
     out[k++] = c->mg.cen_buf[0]; out[k++] = c->mg.cen_buf[1];
     out[k++] = c->mg.cnt_all[0]; out[k++] = c->mg.cnt_all[1];
     out[k++] = c->tag2idx; out[k++] = c->mg.flags; out[k++] = c->mg.ke_all;
+    out[k++] = c->mg.vol_all; out[k++] = c->mg.cv_ptype;
 }
 inline void mg_fill_peers(orbc_ctx *c, int r, void *const p[kMgShared]) {
     PeerTable &t = c->mg.peers;
@@ -176,6 +180,7 @@ inline void mg_fill_peers(orbc_ctx *c, int r, void *const p[kMgShared]) {
     t.centroid[0][r] = (float4 *)p[k++]; t.centroid[1][r] = (float4 *)p[k++];
     t.cnt_all[0][r] = (int *)p[k++]; t.cnt_all[1][r] = (int *)p[k++];
     t.tag2idx[r] = (int *)p[k++]; t.flags[r] = (unsigned *)p[k++]; t.ke_all[r] = (double *)p[k++];
+    t.vol_all[r] = (double *)p[k++]; t.cv_ptype[r] = (int *)p[k++];
 }
 
 struct MgEntry { unsigned long long raw; cudaIpcMemHandle_t handle; };

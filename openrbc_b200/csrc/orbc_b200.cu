@@ -53,6 +53,57 @@ __global__ void k_morton_keys_only(const float4 *__restrict__ pts, int n, uint32
     if (i < n) keys[i] = morton_encode(pts[i]);
 }
 
+// ---- save_frame (trajectory.h:61-105): the frame in the .orbc byte layout, assembled on the device -------------------------------------
+// FRAMEBEG nstep(int) NATOM n(size_t) IDENTITY (tag,type)* [POSITION xyz*] [VELOCITY xyz*] [ROTATION xyz*] [VORONOI cell*] [FORCE xyz*]
+// FRAMEEND, titles NUL-padded to 8 bytes, lipids before proteins.  Section payloads start at 4-byte aligned offsets.
+struct FrameLayout {
+    size_t off_id, off_x, off_v, off_n, off_aff, off_f, off_end;   // payload offsets (0 = section absent); off_end = offset of "FRAMEEND"
+    size_t n_l, n_p;
+    int nstep, tag_base;
+    int l0, l1, p0, p1;                                            // slots to write (all of them on one GPU, the owned ones on a rank)
+};
+__device__ __forceinline__ void put_title(unsigned char *dst, const char *t) {
+    int k = 0;
+    for (; k < 8 && t[k]; ++k) dst[k] = (unsigned char)t[k];
+    for (; k < 8; ++k) dst[k] = 0;
+}
+__device__ __forceinline__ void put3(unsigned char *base, size_t off, size_t i, float4 v) {
+    float *p = reinterpret_cast<float *>(base + off) + 3 * i;
+    p[0] = v.x; p[1] = v.y; p[2] = v.z;
+}
+__global__ void __launch_bounds__(256) k_frame_pack(FrameLayout L, unsigned char *__restrict__ out,
+                                                     const float4 *__restrict__ xl, const float4 *__restrict__ vl, const float4 *__restrict__ nl, const float4 *__restrict__ fl, const int *__restrict__ cl,
+                                                     const float4 *__restrict__ xp, const float4 *__restrict__ vp, const float4 *__restrict__ np, const float4 *__restrict__ fp, const int *__restrict__ cp) {
+    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k == 0) {
+        put_title(out, "FRAMEBEG");
+        for (int b = 0; b < 4; ++b) out[8 + b] = (unsigned char)((unsigned)L.nstep >> (8 * b));
+        put_title(out + 12, "NATOM");
+        const unsigned long long n = L.n_l + L.n_p;
+        for (int b = 0; b < 8; ++b) out[20 + b] = (unsigned char)(n >> (8 * b));
+        put_title(out + 28, "IDENTITY");
+        if (L.off_x) put_title(out + L.off_x - 8, "POSITION");
+        if (L.off_v) put_title(out + L.off_v - 8, "VELOCITY");
+        if (L.off_n) put_title(out + L.off_n - 8, "ROTATION");
+        if (L.off_aff) put_title(out + L.off_aff - 8, "VORONOI");
+        if (L.off_f) put_title(out + L.off_f - 8, "FORCE");
+        put_title(out + L.off_end, "FRAMEEND");
+    }
+    if (k >= L.n_l + L.n_p) return;
+    const bool prot = k >= L.n_l;
+    const size_t i = prot ? k - L.n_l : k;
+    if (prot ? ((int)i < L.p0 || (int)i >= L.p1) : ((int)i < L.l0 || (int)i >= L.l1)) return;
+    const float4 x = prot ? xp[i] : xl[i], n = prot ? np[i] : nl[i];
+    int *id = reinterpret_cast<int *>(out + L.off_id) + 2 * k;
+    id[0] = prot ? __float_as_int(n.w) : L.tag_base + (int)i;      // container.h:122-130: lipid tag = base + i, type = 0
+    id[1] = prot ? __float_as_int(x.w) : 0;
+    if (L.off_x) put3(out, L.off_x, k, x);
+    if (L.off_v) put3(out, L.off_v, k, prot ? vp[i] : vl[i]);
+    if (L.off_n) put3(out, L.off_n, k, n);
+    if (L.off_aff) reinterpret_cast<int *>(out + L.off_aff)[k] = prot ? cp[i] : cl[i];
+    if (L.off_f) put3(out, L.off_f, k, prot ? fp[i] : fl[i]);
+}
+
 int ensure_stage(orbc_ctx *c, size_t floats) {
     if (c->stage_cap < floats) { ORBC_TRY(dev_alloc(&c->stage, floats)); c->stage_cap = floats; }
     return ORBC_OK;
@@ -425,7 +476,7 @@ int preload_kernels() {
 #define ORBC_PRELOAD(k) ORBC_CUDA(cudaFuncGetAttributes(&fa, (const void *)(k)))
     ORBC_PRELOAD(k_assign_nearest); ORBC_PRELOAD(k_bin_count); ORBC_PRELOAD(k_bin_fill); ORBC_PRELOAD(k_bond_mask); ORBC_PRELOAD(k_bonded);
     ORBC_PRELOAD(k_bounce_back); ORBC_PRELOAD(k_build_tag2idx); ORBC_PRELOAD(k_cell_bounds); ORBC_PRELOAD(k_cell_scatter); ORBC_PRELOAD(k_cell_totals);
-    ORBC_PRELOAD(k_centroid_update); ORBC_PRELOAD(k_clear_force); ORBC_PRELOAD(k_compact); ORBC_PRELOAD(k_cv_apply); ORBC_PRELOAD(k_cv_center);
+    ORBC_PRELOAD(k_centroid_update); ORBC_PRELOAD(k_clear_force); ORBC_PRELOAD(k_compact); ORBC_PRELOAD(k_cv_apply); ORBC_PRELOAD(k_cv_center); ORBC_PRELOAD(k_cv_share); ORBC_PRELOAD(k_sum_partials); ORBC_PRELOAD(k_opt_fused); ORBC_PRELOAD(k_frame_pack);
     ORBC_PRELOAD(k_cv_normal_volume); ORBC_PRELOAD(k_fill_cellid); ORBC_PRELOAD(k_fill_int); ORBC_PRELOAD(k_halo_push); ORBC_PRELOAD(k_kinetic);
     ORBC_PRELOAD(k_mg_barrier); ORBC_PRELOAD(k_morton_keys); ORBC_PRELOAD(k_morton_keys_only); ORBC_PRELOAD(k_nh_final); ORBC_PRELOAD(k_nh_final_fused);
     ORBC_PRELOAD(k_nh_initial_fused); ORBC_PRELOAD(k_nh_zeta_update); ORBC_PRELOAD(k_share_ke); ORBC_PRELOAD(k_sum_ke); ORBC_PRELOAD(k_noise); ORBC_PRELOAD(k_opt_move); ORBC_PRELOAD(k_pack4);
@@ -434,6 +485,36 @@ int preload_kernels() {
     ORBC_PRELOAD(k_radix_scatter); ORBC_PRELOAD(k_rank_and_move); ORBC_PRELOAD(k_remap_cellid); ORBC_PRELOAD(k_scan_onepass); ORBC_PRELOAD(k_set3); ORBC_PRELOAD(k_set_range); ORBC_PRELOAD(k_set_range_const); ORBC_PRELOAD(k_share_counts);
     ORBC_PRELOAD(k_stencil_build); ORBC_PRELOAD(k_stray_mask); ORBC_PRELOAD(k_unpack3); ORBC_PRELOAD(k_unpack_w); ORBC_PRELOAD(k_verlet_langevin); ORBC_PRELOAD(k_zero4);
 #undef ORBC_PRELOAD
+    return ORBC_OK;
+}
+
+// constrain_volume.h:26-83.  Decomposed: every rank holds all centroids (same centre everywhere), computes the normals and the
+// volume share of its own cells, the shares are exchanged (peer stores + one barrier) and summed in rank order.
+int do_constrain_volume(orbc_ctx *c, float target, float strength) {
+    Species &L = c->sp[0], &P = c->sp[1];
+    if (!L.has_partition) return fail(ORBC_ERR_ARG, "constrain_volume: lipids are not partitioned");
+    const int nc = c->n_cells;
+    const bool mg = mg_active(c);
+    const int cb = mg ? c->mg.cb : 0, ce = mg ? c->mg.ce : nc;
+    ORBC_CUDA(cudaMemsetAsync(c->d_acc + 4, 0, sizeof(double), c->stream));
+    ORBC_LAUNCH(c, k_cv_center, 1, 1024, 0, c->centroid, nc, c->d_acc);
+    if (ce > cb) ORBC_LAUNCH(c, k_cv_normal_volume, blocks_for(ce - cb, 256), 256, 0, c->centroid, nc, cb, ce, L.cell_start, L.N(), c->cell_normal, c->d_acc);
+    const double *vol_all = nullptr; const int *ptype = nullptr;
+    if (mg) {
+        // two sets of slots used alternately: a fast rank may publish its next share while a slow one still reads this one
+        const int half = (c->mg.cv_par ^= 1) * kMaxWorld;
+        CvShare d; for (int r = 0; r < kMaxWorld; ++r) { d.vol[r] = c->mg.peers.vol_all[r] + half; d.ptype[r] = c->mg.peers.cv_ptype[r]; }
+        const size_t work = std::max<size_t>(kMaxWorld, std::min<size_t>(owned_bound(c, ORBC_PROTEIN), (size_t)nc));
+        ORBC_LAUNCH(c, k_cv_share, blocks_for(work, kBlock), kBlock, 0, c->d_acc, P.X(), c->d_range, nc, c->mg.rank, c->mg.world, d);
+        ORBC_TRY(mg_barrier(c));
+        vol_all = c->mg.vol_all + half; ptype = c->mg.cv_ptype;
+        ORBC_LAUNCH(c, k_sum_partials, 1, 32, 0, c->d_acc + 4, vol_all, c->mg.world);   // acc[4] = the whole volume, for the caller
+    }
+    const int world = mg ? c->mg.world : 1;
+    if (L.n) ORBC_LAUNCH(c, k_cv_apply, blocks_for(owned_bound(c, ORBC_LIPID), kBlock), kBlock, 0, L.C(), c->d_range, c->cell_normal, (const float4 *)nullptr, (size_t)0,
+                         (const int *)nullptr, 0, target, strength, c->d_acc, vol_all, world, L.f);
+    if (P.n && P.has_partition) ORBC_LAUNCH(c, k_cv_apply, blocks_for(owned_bound(c, ORBC_PROTEIN), kBlock), kBlock, 0, P.C(), c->d_range + 2, c->cell_normal, P.X(), P.n,
+                                            ptype, 1, target, strength, c->d_acc, vol_all, world, P.f);
     return ORBC_OK;
 }
 
@@ -527,12 +608,17 @@ void orbc_destroy(orbc_ctx *c) { if (c) cudaSetDevice(c->device);
     dev_free(c->scan_tmp); dev_free(c->radix_hist); dev_free(c->stage); dev_free(c->d_acc); dev_free(c->d_counters); dev_free(c->d_flags); dev_free(c->d_nh);
     dev_free(c->noise[0]); dev_free(c->noise[1]); dev_free(c->d_range); dev_free(c->rel16); dev_free(c->rel_flag);
     for (void *m : c->mg.opened) cudaIpcCloseMemHandle(m);
-    dev_free(c->mg.my_bonds); dev_free(c->mg.keep); dev_free(c->mg.ke_all); dev_free(c->mg.flags); dev_free(c->mg.dest_mask); dev_free(c->mg.pmask); dev_free(c->mg.need);
+    dev_free(c->mg.my_bonds); dev_free(c->mg.keep); dev_free(c->mg.ke_all); dev_free(c->mg.vol_all); dev_free(c->mg.cv_ptype); dev_free(c->mg.flags); dev_free(c->mg.dest_mask); dev_free(c->mg.pmask); dev_free(c->mg.need);
     for (int s = 0; s < 2; ++s) { dev_free(c->mg.cnt_all[s]); dev_free(c->mg.off_me[s]); dev_free(c->mg.cnt_prev[s]); }
     if (c->h_acc) cudaFreeHost(c->h_acc); if (c->h_flags) cudaFreeHost(c->h_flags); if (c->h_counters) cudaFreeHost(c->h_counters); if (c->h_nh) cudaFreeHost(c->h_nh);
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
     for (auto &v : c->prof_ev) for (auto &e : v) cudaEventDestroy(e);
     for (auto &e : c->kprof_ev) cudaEventDestroy(e);
+    for (int k = 0; k < 2; ++k) {
+        dev_free(c->frame_dev[k]); if (c->frame_host[k]) cudaFreeHost(c->frame_host[k]);
+        if (c->frame_packed[k]) cudaEventDestroy(c->frame_packed[k]); if (c->frame_copied[k]) cudaEventDestroy(c->frame_copied[k]);
+    }
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -741,20 +827,19 @@ int orbc_compute_bonded(orbc_ctx *c) { if (c) cudaSetDevice(c->device); if (!c) 
 
 int orbc_constrain_volume(orbc_ctx *c, float target, float strength, float *volume_out) { if (c) cudaSetDevice(c->device);
     if (!c) return fail(ORBC_ERR_ARG, "null ctx");
-    Species &L = c->sp[0], &P = c->sp[1];
-    ORBC_TRY(single_gpu_only(c, "constrain_volume"));
-    if (!L.has_partition) return fail(ORBC_ERR_ARG, "constrain_volume: lipids are not partitioned");
-    const int nc = c->n_cells;
-    ORBC_CUDA(cudaMemsetAsync(c->d_acc + 1, 0, 4 * sizeof(double), c->stream));
-    ORBC_LAUNCH(c, k_cv_center, blocks_for(nc, 256), 256, 0, c->centroid, nc, c->d_acc);
-    ORBC_LAUNCH(c, k_cv_normal_volume, blocks_for(nc, 256), 256, 0, c->centroid, nc, L.cell_start, L.N(), c->cell_normal, c->d_acc);
-    if (L.n) ORBC_LAUNCH(c, k_cv_apply, blocks_for(L.n, kBlock), kBlock, 0, L.C(), L.n, c->cell_normal, (const float4 *)nullptr, (size_t)0, target, strength, c->d_acc, L.f);
-    if (P.n && P.has_partition) ORBC_LAUNCH(c, k_cv_apply, blocks_for(P.n, kBlock), kBlock, 0, P.C(), P.n, c->cell_normal, P.X(), P.n, target, strength, c->d_acc, P.f);
+    ORBC_TRY(do_constrain_volume(c, target, strength));
     if (volume_out) {
         ORBC_CUDA(cudaMemcpyAsync(c->h_acc, c->d_acc, 8 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         ORBC_CUDA(cudaStreamSynchronize(c->stream));
         *volume_out = (float)c->h_acc[4];
     }
+    return ORBC_OK;
+}
+
+int orbc_set_volume_constraint(orbc_ctx *c, int on, float target, float strength) {
+    if (!c) return fail(ORBC_ERR_ARG, "null ctx");
+    if (on && !(target != 0.f)) return fail(ORBC_ERR_ARG, "orbc_set_volume_constraint: target volume must not be zero");
+    c->cv_on = on != 0; c->cv_target = target; c->cv_strength = strength;
     return ORBC_OK;
 }
 
@@ -771,7 +856,7 @@ int orbc_integrate(orbc_ctx *c, int kernel, const orbc_step_params *p, orbc_step
     if (needs_p && !p) return fail(ORBC_ERR_ARG, "orbc_integrate: this kernel needs step parameters");
     const bool reduces = kernel == ORBC_NH_INITIAL_FUSED || kernel == ORBC_NH_FINAL_FUSED || kernel == ORBC_NH_UPDATE;
     if (reduces) ORBC_CUDA(cudaMemsetAsync(c->d_acc, 0, sizeof(double), c->stream));
-    const bool mg_ok = kernel == ORBC_VERLET_LANGEVIN || kernel == ORBC_CLEAR_FORCE || kernel == ORBC_NH_INITIAL_FUSED || kernel == ORBC_NH_FINAL_FUSED;
+    const bool mg_ok = kernel == ORBC_VERLET_LANGEVIN || kernel == ORBC_CLEAR_FORCE || kernel == ORBC_NH_INITIAL_FUSED || kernel == ORBC_NH_FINAL_FUSED || kernel == ORBC_OPT_FUSED;
     if (!mg_ok) ORBC_TRY(single_gpu_only(c, "this integrate() kernel"));
     if (kernel == ORBC_VERLET_LANGEVIN) ORBC_TRY(do_integrate_langevin(c, p));
     else for (int sp = 0; sp < 2; ++sp) {
@@ -789,14 +874,15 @@ int orbc_integrate(orbc_ctx *c, int kernel, const orbc_step_params *p, orbc_step
         case ORBC_NH_FINAL: ORBC_LAUNCH(c, k_nh_final, nb, 256, 0, a); break;
         case ORBC_NH_UPDATE: ORBC_LAUNCH(c, k_kinetic, nb, 256, 0, S.X(), S.V(), c->d_range + 2 * sp, 0.5f, c->d_acc); break;
         case ORBC_OPT_MOVE: ORBC_LAUNCH(c, k_opt_move, nb, 256, 0, a); break;
+        case ORBC_OPT_FUSED: a.clear = 0; ORBC_LAUNCH(c, k_opt_fused, nb, 256, 0, a); if (mg_active(c)) S.cur_xn ^= 1; break;
         default: return fail(ORBC_ERR_ARG, "orbc_integrate: unknown kernel id %d", kernel);
         }
     }
     if (mg_active(c) && reduces) {
         // the partial sums of all ranks, added in rank order on every rank; the barrier is also the one behind the halo push
         ORBC_TRY(mg_share_ke(c)); ORBC_TRY(mg_barrier(c));
-        ORBC_LAUNCH(c, k_sum_ke, 1, 32, 0, c->d_acc, c->mg.ke_all, c->mg.world);
-    } else if (mg_active(c) && kernel == ORBC_NH_INITIAL_FUSED) ORBC_TRY(mg_barrier(c));
+        ORBC_LAUNCH(c, k_sum_ke, 1, 32, 0, c->d_acc, mg_ke_slots(c), c->mg.world);
+    } else if (mg_active(c) && (kernel == ORBC_NH_INITIAL_FUSED || kernel == ORBC_OPT_FUSED)) ORBC_TRY(mg_barrier(c));
     if (res) {
         res->ke = 0.0; res->n = (long)(c->sp[0].n + c->sp[1].n);
         if (reduces) {
@@ -835,6 +921,7 @@ int orbc_run_langevin(orbc_ctx *c, const orbc_step_params *p, int n_steps, int f
         const bool first = s == 0 || c->pair_impl != 2, last = s + 1 == n_steps || c->pair_impl != 2;   // (the cross-check kernels always accumulate)
         ORBC_TRY(launch_pairwise(c, first));
         ORBC_TRY(launch_bonded(c));
+        if (c->cv_on) ORBC_TRY(do_constrain_volume(c, c->cv_target, c->cv_strength));   // openrbc.cpp:229
         ORBC_TRY(do_integrate_langevin(c, &q, !last && (q.nstep + 1) % freq_voronoi == 0, last));
     }
     if (mg_active(c) && n_steps > 1)     // slots this rank owned at some step but not at the last one still hold dead values: clear everything
@@ -842,6 +929,33 @@ int orbc_run_langevin(orbc_ctx *c, const orbc_step_params *p, int n_steps, int f
             ORBC_LAUNCH(c, k_zero4, blocks_for(c->sp[sp].n, kBlock), kBlock, 0, c->sp[sp].f, c->sp[sp].n, (const int *)nullptr);
             ORBC_LAUNCH(c, k_zero4, blocks_for(c->sp[sp].n, kBlock), kBlock, 0, c->sp[sp].t, c->sp[sp].n, (const int *)nullptr);
         }
+    return ORBC_OK;
+}
+
+int orbc_run_minimize(orbc_ctx *c, const orbc_step_params *p, int n_steps, int freq_sort_ctrd) { if (c) cudaSetDevice(c->device);
+    if (!c || !p) return fail(ORBC_ERR_ARG, "orbc_run_minimize: bad argument");
+    // openrbc.cpp:88-133.  param.nstep stays 0 for the whole minimisation (it is only incremented in the main loop, :244), so every
+    // iteration Morton-sorts the centroids (voronoi.h:82: nstep % freq_sort_ctrd == 0).  clear_force is folded into the first force
+    // kernel (plain stores instead of accumulation); post_torque + mover + bounce_back are one pass (k_opt_fused).
+    orbc_step_params q = *p; q.nstep = 0;
+    for (int s = 0; s < n_steps; ++s) {
+        ORBC_TRY(do_rebuild(c, 0, freq_sort_ctrd));
+        if (c->pair_impl != 2)                                   // the cross-check kernels always accumulate
+            for (int sp = 0; sp < 2; ++sp) if (c->sp[sp].n) ORBC_LAUNCH(c, k_clear_force, blocks_for(c->sp[sp].n, 256), 256, 0, c->sp[sp].f, c->sp[sp].t, c->sp[sp].n);
+        ORBC_TRY(launch_pairwise(c, false));
+        ORBC_TRY(launch_bonded(c));
+        {
+            ProfScope ps(c, ORBC_PROF_INTEGRATE);
+            for (int sp = 0; sp < 2; ++sp) {
+                Species &S = c->sp[sp];
+                if (!S.n) continue;
+                IntegArgs a; fill_integ(a, c, sp, &q); a.clear = 0;
+                ORBC_LAUNCH(c, k_opt_fused, blocks_for(owned_bound(c, sp), 256), 256, 0, a);
+                if (mg_active(c)) S.cur_xn ^= 1;
+            }
+        }
+        if (s + 1 == n_steps) ORBC_TRY(mg_barrier(c));           // otherwise the first barrier of the next rebuild covers the push
+    }
     return ORBC_OK;
 }
 
@@ -853,7 +967,6 @@ int orbc_run_nh(orbc_ctx *c, const orbc_step_params *p, int n_steps, int freq_vo
     orbc_step_params q = *p;
     const long n = (long)(c->sp[0].n + c->sp[1].n);
     const bool mg = mg_active(c);
-    const double *ke_all = mg ? c->mg.ke_all : nullptr;
     const int world = mg ? c->mg.world : 1;
     for (int s = 0; s < n_steps; ++s, ++q.nstep) {
         for (int sp = 0; sp < 2; ++sp) if (c->sp[sp].n) {
@@ -863,16 +976,17 @@ int orbc_run_nh(orbc_ctx *c, const orbc_step_params *p, int n_steps, int freq_vo
         }
         // decomposed: one barrier stands behind both the halo push of the drift and the exchange of the partial kinetic energies
         ORBC_TRY(mg_share_ke(c)); ORBC_TRY(mg_barrier(c));
-        ORBC_LAUNCH(c, k_nh_zeta_update, 1, 32, 0, c->d_nh, c->d_acc, q.dt, q.kBT, n, ke_all, world);
+        ORBC_LAUNCH(c, k_nh_zeta_update, 1, 32, 0, c->d_nh, c->d_acc, q.dt, q.kBT, n, mg ? mg_ke_slots(c) : (const double *)nullptr, world);
         if (q.nstep % freq_voronoi == 0) ORBC_TRY(do_rebuild(c, q.nstep, freq_sort_ctrd));
         ORBC_TRY(launch_pairwise(c));
         ORBC_TRY(launch_bonded(c));
+        if (c->cv_on) ORBC_TRY(do_constrain_volume(c, c->cv_target, c->cv_strength));   // openrbc.cpp:229
         for (int sp = 0; sp < 2; ++sp) if (c->sp[sp].n) {
             IntegArgs a; fill_integ(a, c, sp, &q); a.zeta_dev = c->d_nh;
             ORBC_LAUNCH(c, k_nh_final_fused, blocks_for(owned_bound(c, sp), 256), 256, 0, a);
         }
         ORBC_TRY(mg_share_ke(c)); ORBC_TRY(mg_barrier(c));
-        ORBC_LAUNCH(c, k_nh_zeta_update, 1, 32, 0, c->d_nh, c->d_acc, q.dt, q.kBT, n, ke_all, world);
+        ORBC_LAUNCH(c, k_nh_zeta_update, 1, 32, 0, c->d_nh, c->d_acc, q.dt, q.kBT, n, mg ? mg_ke_slots(c) : (const double *)nullptr, world);
     }
     ORBC_CUDA(cudaMemcpyAsync(c->h_nh, c->d_nh, 2 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     ORBC_CUDA(cudaStreamSynchronize(c->stream));
@@ -925,7 +1039,9 @@ int orbc_mg_export(orbc_ctx *c, void *blob_out, size_t bytes) { if (c) cudaSetDe
             ORBC_CUDA(cudaMemsetAsync(m.cnt_all[sp], 0, sizeof(int) * (size_t)w * (nc + 1), c->stream));
         }
         ORBC_TRY(dev_alloc(&m.flags, kMaxWorld)); ORBC_CUDA(cudaMemsetAsync(m.flags, 0, sizeof(unsigned) * kMaxWorld, c->stream));
-        ORBC_TRY(dev_alloc(&m.ke_all, kMaxWorld)); ORBC_CUDA(cudaMemsetAsync(m.ke_all, 0, sizeof(double) * kMaxWorld, c->stream));
+        ORBC_TRY(dev_alloc(&m.ke_all, 2 * kMaxWorld)); ORBC_CUDA(cudaMemsetAsync(m.ke_all, 0, sizeof(double) * 2 * kMaxWorld, c->stream));
+        ORBC_TRY(dev_alloc(&m.vol_all, 2 * kMaxWorld)); ORBC_CUDA(cudaMemsetAsync(m.vol_all, 0, sizeof(double) * 2 * kMaxWorld, c->stream));
+        ORBC_TRY(dev_alloc(&m.cv_ptype, nc)); ORBC_CUDA(cudaMemsetAsync(m.cv_ptype, 0, sizeof(int) * nc, c->stream));
         ORBC_TRY(dev_alloc(&m.dest_mask, nc)); ORBC_CUDA(cudaMemsetAsync(m.dest_mask, 0, nc, c->stream));
         ORBC_TRY(dev_alloc(&m.pmask, P.n + 4)); ORBC_CUDA(cudaMemsetAsync(m.pmask, 0, P.n + 4, c->stream));
         ORBC_TRY(dev_alloc(&m.need, nc)); ORBC_CUDA(cudaMemsetAsync(m.need, 0, sizeof(int) * nc, c->stream));
@@ -1033,6 +1149,97 @@ int orbc_download(orbc_ctx *c, int sp, size_t stride, float *x, float *v, float 
         ORBC_CUDA(cudaStreamSynchronize(c->stream));
     }
     return check_flags(c);
+}
+
+// ---- save_frame -----------------------------------------------------------------------------------------------------------------------
+static FrameLayout frame_layout(const orbc_ctx *c, int nstep, int dump_field, int tag_base, size_t *total) {
+    FrameLayout L; memset(&L, 0, sizeof(L));
+    L.n_l = c->sp[0].n; L.n_p = c->sp[1].n; L.nstep = nstep; L.tag_base = tag_base;
+    const size_t n = L.n_l + L.n_p;
+    size_t off = 8 + 4 + 8 + 8 + 8;                              // FRAMEBEG nstep NATOM n IDENTITY
+    L.off_id = off; off += 8 * n;
+    auto section = [&](bool on, size_t bytes_each) -> size_t { if (!on) return 0; off += 8; const size_t o = off; off += bytes_each * n; return o; };
+    L.off_x = section(dump_field & 1, 12);                       // DumpField::position  (runtime_parameter.h:30-36; order of trajectory.h:77-101)
+    L.off_v = section(dump_field & 8, 12);                       // velocity
+    L.off_n = section(dump_field & 2, 12);                       // rotation
+    L.off_aff = section(dump_field & 4, 4);                      // voronoi
+    L.off_f = section(dump_field & 16, 12);                      // force
+    L.off_end = off; off += 8;
+    *total = off;
+    return L;
+}
+
+int orbc_frame_bytes(orbc_ctx *c, int dump_field, size_t *bytes) {
+    if (!c || !bytes) return fail(ORBC_ERR_ARG, "orbc_frame_bytes: bad argument");
+    frame_layout(c, 0, dump_field, 1, bytes);
+    return ORBC_OK;
+}
+
+// pack the frame into device buffer `slot` on the context's stream
+static int frame_pack(orbc_ctx *c, int slot, int nstep, int dump_field, int tag_base, size_t *total) {
+    FrameLayout L = frame_layout(c, nstep, dump_field, tag_base, total);
+    Species &S0 = c->sp[0], &S1 = c->sp[1];
+    if ((dump_field & 4) && ((S0.n && !S0.has_partition) || (S1.n && !S1.has_partition))) return fail(ORBC_ERR_ARG, "save_frame: the VORONOI section needs a partition");
+    if (c->frame_dev_cap[slot] < *total) { ORBC_TRY(dev_alloc(&c->frame_dev[slot], *total + (*total >> 4))); c->frame_dev_cap[slot] = *total + (*total >> 4); }
+    L.l0 = 0; L.l1 = (int)S0.n; L.p0 = 0; L.p1 = (int)S1.n;
+    if (mg_active(c)) {
+        // a rank's image holds the titles and the slots it owns; the other slots are zero (the images of all ranks OR together)
+        int r[4];
+        ORBC_CUDA(cudaMemcpyAsync(r, c->d_range, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        ORBC_CUDA(cudaStreamSynchronize(c->stream));
+        L.l0 = r[0]; L.l1 = r[1]; L.p0 = r[2]; L.p1 = r[3];
+        ORBC_CUDA(cudaMemsetAsync(c->frame_dev[slot], 0, *total, c->stream));
+    }
+    ORBC_LAUNCH(c, k_frame_pack, blocks_for(std::max<size_t>(1, L.n_l + L.n_p), 256), 256, 0, L, c->frame_dev[slot],
+                S0.X(), S0.V(), S0.N(), S0.f, S0.C(), S1.X(), S1.V(), S1.N(), S1.f, S1.C());
+    return ORBC_OK;
+}
+
+int orbc_save_frame(orbc_ctx *c, int nstep, int dump_field, int lipid_tag_base, void *dst, size_t cap, size_t *bytes) { if (c) cudaSetDevice(c->device);
+    if (!c || !dst) return fail(ORBC_ERR_ARG, "orbc_save_frame: bad argument");
+    size_t total = 0;
+    frame_layout(c, nstep, dump_field, lipid_tag_base, &total);
+    if (bytes) *bytes = total;
+    if (cap < total) return fail(ORBC_ERR_ARG, "orbc_save_frame: the frame needs %zu bytes, the buffer holds %zu", total, cap);
+    ORBC_TRY(frame_pack(c, 0, nstep, dump_field, lipid_tag_base, &total));
+    ORBC_CUDA(cudaMemcpyAsync(dst, c->frame_dev[0], total, cudaMemcpyDeviceToHost, c->stream));
+    ORBC_CUDA(cudaStreamSynchronize(c->stream));
+    return check_flags(c);
+}
+
+int orbc_save_frame_begin(orbc_ctx *c, int nstep, int dump_field, int lipid_tag_base) { if (c) cudaSetDevice(c->device);
+    if (!c) return fail(ORBC_ERR_ARG, "null ctx");
+    if (c->frame_pending >= 2) return fail(ORBC_ERR_ARG, "orbc_save_frame_begin: two frames are already in flight (call orbc_save_frame_end)");
+    if (!c->copy_stream) {
+        ORBC_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        for (int k = 0; k < 2; ++k) { ORBC_CUDA(cudaEventCreateWithFlags(&c->frame_packed[k], cudaEventDisableTiming)); ORBC_CUDA(cudaEventCreateWithFlags(&c->frame_copied[k], cudaEventDisableTiming)); }
+    }
+    const int slot = (c->frame_head + c->frame_pending) & 1;
+    size_t total = 0;
+    ORBC_TRY(frame_pack(c, slot, nstep, dump_field, lipid_tag_base, &total));
+    if (c->frame_host_cap[slot] < total) {
+        if (c->frame_host[slot]) { ORBC_CUDA(cudaFreeHost(c->frame_host[slot])); c->frame_host[slot] = nullptr; }
+        ORBC_CUDA(cudaMallocHost((void **)&c->frame_host[slot], total + (total >> 4)));
+        c->frame_host_cap[slot] = total + (total >> 4);
+    }
+    // the copy runs on its own stream behind the pack; the next kernels of the run do not wait for it
+    ORBC_CUDA(cudaEventRecord(c->frame_packed[slot], c->stream));
+    ORBC_CUDA(cudaStreamWaitEvent(c->copy_stream, c->frame_packed[slot], 0));
+    ORBC_CUDA(cudaMemcpyAsync(c->frame_host[slot], c->frame_dev[slot], total, cudaMemcpyDeviceToHost, c->copy_stream));
+    ORBC_CUDA(cudaEventRecord(c->frame_copied[slot], c->copy_stream));
+    c->frame_bytes[slot] = total;
+    ++c->frame_pending;
+    return ORBC_OK;
+}
+
+int orbc_save_frame_end(orbc_ctx *c, const void **data, size_t *bytes) { if (c) cudaSetDevice(c->device);
+    if (!c || !data || !bytes) return fail(ORBC_ERR_ARG, "orbc_save_frame_end: bad argument");
+    if (!c->frame_pending) return fail(ORBC_ERR_ARG, "orbc_save_frame_end: no frame in flight");
+    const int slot = c->frame_head;
+    ORBC_CUDA(cudaEventSynchronize(c->frame_copied[slot]));
+    *data = c->frame_host[slot]; *bytes = c->frame_bytes[slot];
+    c->frame_head ^= 1; --c->frame_pending;
+    return ORBC_OK;
 }
 
 int orbc_debug_dump(orbc_ctx *c, int what, void *dst, size_t bytes) { if (c) cudaSetDevice(c->device);

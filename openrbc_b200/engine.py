@@ -15,7 +15,7 @@ _SO = os.path.join(_HERE, "liborbc_b200.so")
 
 LIPID, PROTEIN = 0, 1
 CLEAR_FORCE, POST_TORQUE, BOUNCE_BACK, VERLET_LANGEVIN, NH_INITIAL_FUSED, NH_FINAL_FUSED, NH_FINAL, NH_UPDATE = range(8)
-OPT_MOVE = 9
+OPT_MOVE, OPT_FUSED = 9, 10
 STENCIL_STRIDE = 64
 DUMP = dict(centroids=0, cell_start_l=1, cell_start_p=2, cells_l=3, cells_p=4, aff_l=5, aff_p=6, morton_keys=7, morton_perm=8,
             stencil_counts=9, stencil=10, tag2idx=11, counters=12)
@@ -29,6 +29,7 @@ EXPORTS = [
     "orbc_constrain_volume", "orbc_integrate", "orbc_nh_zeta_update", "orbc_compute_temperature", "orbc_run_langevin",
     "orbc_run_nh", "orbc_download", "orbc_size", "orbc_n_cells", "orbc_debug_dump", "orbc_debug_noise", "orbc_event_record",
     "orbc_event_elapsed_ms", "orbc_launch_count", "orbc_profile_enable", "orbc_profile_read", "orbc_set_option",
+    "orbc_set_volume_constraint", "orbc_run_minimize", "orbc_frame_bytes", "orbc_save_frame", "orbc_save_frame_begin", "orbc_save_frame_end",
     "orbc_profile_kernels", "orbc_profile_kernels_report", "orbc_mg_init", "orbc_mg_blob_bytes", "orbc_mg_cell_range", "orbc_mg_export", "orbc_mg_connect", "orbc_mg_range",
 ]
 
@@ -111,6 +112,12 @@ def load_library():
         lib.orbc_destroy.restype = None
         lib.orbc_profile_kernels.argtypes = [C.c_void_p, C.c_int]
         lib.orbc_profile_kernels_report.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        lib.orbc_set_volume_constraint.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float]
+        lib.orbc_run_minimize.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        lib.orbc_frame_bytes.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        lib.orbc_save_frame.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]
+        lib.orbc_save_frame_begin.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        lib.orbc_save_frame_end.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         lib.orbc_mg_init.argtypes = [C.c_void_p, C.c_int, C.c_int]
         lib.orbc_mg_blob_bytes.restype = C.c_size_t
         lib.orbc_mg_cell_range.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
@@ -361,6 +368,9 @@ class Simulation:
     def opt_move(self):                                          # :114-131
         self.integrate(OPT_MOVE)
 
+    def opt_fused(self):                                         # :110-133 in one pass (post_torque + mover + bounce_back)
+        self.integrate(OPT_FUSED)
+
     def compute_temperature(self):                               # :253
         t = C.c_double()
         self._ck(self.lib.orbc_compute_temperature(self.ctx, C.byref(t)))
@@ -370,6 +380,33 @@ class Simulation:
         v = C.c_float()
         self._ck(self.lib.orbc_constrain_volume(self.ctx, target, strength, C.byref(v)))
         return v.value
+
+    def set_volume_constraint(self, on, target=3.15, strength=0.05):
+        """Apply constrain_volume inside run_langevin / run_nh at the place of openrbc.cpp:229."""
+        self._ck(self.lib.orbc_set_volume_constraint(self.ctx, int(on), target, strength))
+
+    # ---- save_frame (trajectory.h:61-105) ---------------------------------------------------------------------
+    def frame_bytes(self, dump_field=7):
+        n = C.c_size_t()
+        self._ck(self.lib.orbc_frame_bytes(self.ctx, dump_field, C.byref(n)))
+        return n.value
+
+    def save_frame(self, dump_field=7, tag_base=1, out=None):
+        """One frame in the .orbc byte layout (np.uint8 array); `out` may be a caller-owned (pinned) buffer."""
+        n = self.frame_bytes(dump_field)
+        buf = out if out is not None else np.empty(n, np.uint8)
+        got = C.c_size_t()
+        self._ck(self.lib.orbc_save_frame(self.ctx, self.nstep, dump_field, tag_base, _p(buf), buf.nbytes, C.byref(got)))
+        return buf[:got.value]
+
+    def save_frame_begin(self, dump_field=7, tag_base=1):
+        self._ck(self.lib.orbc_save_frame_begin(self.ctx, self.nstep, dump_field, tag_base))
+
+    def save_frame_end(self):
+        """View (np.uint8) of the oldest frame in flight, inside the library's pinned buffer: valid until the next-but-one begin."""
+        ptr, n = C.c_void_p(), C.c_size_t()
+        self._ck(self.lib.orbc_save_frame_end(self.ctx, C.byref(ptr), C.byref(n)))
+        return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_ubyte)), shape=(n.value,))
 
     def delete_lipid(self, stray_tolerance):                     # :201
         n = C.c_size_t()
@@ -381,6 +418,10 @@ class Simulation:
         p = self.params()
         self._ck(self.lib.orbc_run_langevin(self.ctx, C.byref(p), n_steps, self.freq_voronoi, self.freq_sort_ctrd))
         self.nstep += n_steps
+
+    def run_minimize(self, n_steps):                             # openrbc.cpp:88-133
+        p = self.params()
+        self._ck(self.lib.orbc_run_minimize(self.ctx, C.byref(p), n_steps, self.freq_sort_ctrd))
 
     def run_nh(self, n_steps):
         p = self.params()

@@ -298,3 +298,26 @@ class World:
         self.compute_bonded()
         self.nh_final_fused()
         self.nstep += 1
+
+
+def frame_bytes(nstep, dump_field, tag_base, lx, lv, ln, lf, aff_l, px, pv, pn, pf, aff_p, ptype, ptag):
+    """Restatement of save_frame (trajectory.h:61-105): FRAMEBEG nstep(int32) NATOM n(size_t) IDENTITY (tag, type)*
+    [POSITION] [VELOCITY] [ROTATION] [VORONOI] [FORCE] FRAMEEND; titles NUL-padded to 8 bytes (:29-33); lipids first;
+    lipid tag = base + i, type 0 (container.h:122-130); DumpField bits runtime_parameter.h:30-36."""
+    def title(t):
+        return t.encode().ljust(8, b"\0")
+    nl, npr = len(lx), len(px)
+    out = [title("FRAMEBEG"), np.int32(nstep).tobytes(), title("NATOM"), np.uint64(nl + npr).tobytes(), title("IDENTITY")]
+    ident = np.empty((nl + npr, 2), np.int32)
+    ident[:nl, 0] = tag_base + np.arange(nl); ident[:nl, 1] = 0
+    ident[nl:, 0] = ptag; ident[nl:, 1] = ptype
+    out.append(ident.tobytes())
+    def sec(name, a, b, dt=np.float32):
+        out.append(title(name)); out.append(np.ascontiguousarray(a, dt).tobytes()); out.append(np.ascontiguousarray(b, dt).tobytes())
+    if dump_field & 1: sec("POSITION", lx, px)
+    if dump_field & 8: sec("VELOCITY", lv, pv)
+    if dump_field & 2: sec("ROTATION", ln, pn)
+    if dump_field & 4: sec("VORONOI", aff_l, aff_p, np.int32)
+    if dump_field & 16: sec("FORCE", lf, pf)
+    out.append(title("FRAMEEND"))
+    return b"".join(out)

@@ -189,6 +189,18 @@ class Ref:
     def opt_move(self):
         self.lib.ref_opt_move()
 
+    def save_frame(self, dump_field=7):
+        """Bytes of one frame as the reference's save_frame writes it (trajectory.h:61-105)."""
+        import tempfile
+        fd, path = tempfile.mkstemp(suffix=".orbc")
+        os.close(fd)
+        try:
+            assert self.lib.ref_save_frame(path.encode(), int(dump_field)) == 0
+            with open(path, "rb") as f:
+                return f.read()
+        finally:
+            os.unlink(path)
+
     def stencil(self, cell, rmax, cap=256):
         out = np.empty(cap, np.int32)
         n = self.lib.ref_get_stencil(int(cell), C.c_float(rmax), out.ctypes.data_as(C.c_void_p), cap)

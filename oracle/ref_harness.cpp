@@ -376,6 +376,18 @@ double ref_run_opt( int n_steps ) {
     return omp_get_wtime() - t0;
 }
 
+// openrbc.cpp:247-250: update_particle_affiliation of both cell lists, then save_frame (trajectory.h:61-105) into `path`
+int ref_save_frame( const char * path, int dump_field ) {
+    W->cell_lipid.update_particle_affiliation( W->lipid );
+    W->cell_protein.update_particle_affiliation( W->protein );
+    const int keep = W->param.dump_field;
+    W->param.dump_field = dump_field;
+    std::ofstream f( path, std::ios::binary );
+    save_frame( f, W->lipid, W->protein, W->cell_lipid, W->cell_protein, W->param );
+    W->param.dump_field = keep;
+    return f.good() ? 0 : -1;
+}
+
 double ref_timer( const char * name ) { return Service<Timers>::call()[ name ].read(); }
 void ref_timers_report() { Service<Timers>::call().report( false ); }
 

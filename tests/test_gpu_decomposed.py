@@ -186,3 +186,90 @@ def test_nose_hoover_loop(name, world):
     assert all(abs(v - ke_one) <= 1e-9 * ke_one for v in out.values()), (ke_one, out)
     for sim in [one] + sims:
         sim.close()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_volume_constraint(world):
+    """constrain_volume.h:26-83 on a decomposed run (BASELINE configs[2]): every rank computes the normals and the volume share of
+    its own cells, the shares are exchanged and summed in rank order — same volume and same forces as on one GPU, call by
+    call (twice: the scratch normals persist) and inside the free-running loop."""
+    from openrbc_b200 import Simulation
+    st = load_state("vesicle_ico0")
+    one = Simulation(st, kBT=0.22)
+    sims = make_ranks(st, world, kBT=0.22)
+    for k in range(2):
+        v_one = one.constrain_volume(3.15, 0.05)
+        out = {}
+        on_all(sims, lambda s: out.__setitem__(s.rank, s.constrain_volume(3.15, 0.05)))
+        assert all(abs(v - v_one) <= 1e-6 * abs(v_one) for v in out.values()), (v_one, out)
+        for s in (0, 1):
+            ref, got = one.download(s, "f"), gathered(sims, s, "f")
+            assert rel_err(got["f"], ref["f"]) < 1e-6, (k, s)
+    for sim in [one] + sims:
+        sim.clear_force()
+        sim.set_volume_constraint(True, 3.15, 0.05)
+        sim.nstep = 22
+    one.run_langevin(6)
+    on_all(sims, lambda s: s.run_langevin(6))
+    for s in (0, 1):
+        ref, got = one.download(s, "xvno"), gathered(sims, s, "xvno")
+        for f in "xvno":
+            np.testing.assert_allclose(got[f], ref[f], rtol=0, atol=2e-5 * (1 + np.abs(ref[f]).max(initial=0.0)), err_msg=f)
+    for sim in [one] + sims:
+        sim.close()
+
+
+@pytest.mark.parametrize("name,world", [("vesicle_ico0", 2), ("vesicle_ico0", 3), ("sphere_r12", 4)])
+def test_minimisation_loop(name, world):
+    """orbc_run_minimize (openrbc.cpp:88-133) decomposed: a rebuild with Morton renumbering on every iteration."""
+    from openrbc_b200 import Simulation
+    st = load_state(name)
+    one = Simulation(st, kBT=0.0)
+    sims = make_ranks(st, world, kBT=0.0)
+    one.run_minimize(3)
+    on_all(sims, lambda s: s.run_minimize(3))
+    for what in ("cell_start_l", "cell_start_p", "centroids"):
+        ref = one.dump(what)
+        for sim in sims:
+            np.testing.assert_array_equal(sim.dump(what), ref, err_msg=f"{what} rank {sim.rank}")
+    for s in (0, 1):
+        ref, got = one.download(s, "xnft"), gathered(sims, s, "xnft")
+        for f in "xn":
+            np.testing.assert_allclose(got[f], ref[f], rtol=0, atol=2e-6 * (1 + np.abs(ref[f]).max(initial=0.0)), err_msg=f)
+        assert rel_err(got["f"], ref["f"]) < 1e-5 and rel_err(got["t"], ref["t"]) < 1e-5
+    for sim in [one] + sims:
+        sim.close()
+
+
+def test_frames_of_the_ranks_combine():
+    """save_frame on a decomposed run: each rank's image holds the titles and its own slots, zeros elsewhere; OR-ed together
+    they are the single-GPU frame."""
+    from openrbc_b200 import Simulation
+    st = load_state("vesicle_ico0")
+    one = Simulation(st, kBT=0.22)
+    sims = make_ranks(st, 3, kBT=0.22)
+    for sim in [one] + sims:
+        sim.nstep = 22
+    one.run_langevin(4)
+    on_all(sims, lambda s: s.run_langevin(4))
+    want = one.save_frame(15)
+    out = {}
+    on_all(sims, lambda s: out.__setitem__(s.rank, s.save_frame(15).copy()))
+    merged = np.zeros_like(want)
+    for r in sorted(out):
+        merged |= out[r]
+    # positions / velocities follow the single-GPU trajectory to rounding, everything else is equal: compare section by section
+    n = one.size(0) + one.size(1)
+    off = 36 + 8 * n
+    np.testing.assert_array_equal(merged[:off], want[:off])                      # titles, nstep, NATOM, IDENTITY
+    for width in (12, 12, 12, 4):                                                # POSITION VELOCITY ROTATION VORONOI
+        np.testing.assert_array_equal(merged[off:off + 8], want[off:off + 8])
+        a = merged[off + 8:off + 8 + width * n]; b = want[off + 8:off + 8 + width * n]
+        if width == 4:
+            np.testing.assert_array_equal(a, b)
+        else:
+            np.testing.assert_allclose(a.view(np.float32), b.view(np.float32), rtol=0, atol=2e-5 * (1 + np.abs(b.view(np.float32)).max()))
+        off += 8 + width * n
+    np.testing.assert_array_equal(merged[off:], want[off:])
+    for sim in [one] + sims:
+        sim.close()

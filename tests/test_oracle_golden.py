@@ -94,3 +94,57 @@ def test_philox_noise_statistics():
     assert abs(z.mean()) < 5e-3 and abs(z.var() - 1.0 / 3.0) < 5e-3
     z2 = port.philox_noise(1234, 8, 0, 200000)
     assert abs(np.corrcoef(z[:, 0], z2[:, 0])[0, 1]) < 1e-2
+
+
+# ---- second set: frames, minimisation loop, volume constraint (tests/golden/make_golden_ext.py) ------------------------------------
+def load_ext(name):
+    return dict(np.load(os.path.join(GOLDEN, "ext_" + name + ".npz")))
+
+
+def ext_state(g):
+    return {k[3:]: v for k, v in g.items() if k.startswith("in_")}
+
+
+@pytest.mark.parametrize("name", FILES)
+def test_frame_bytes(name):
+    """save_frame's byte layout restated (oracle/port.py frame_bytes) == the reference's own file, byte for byte."""
+    g = load_ext(name)
+    st = ext_state(g)
+    aff = [np.repeat(np.arange(len(cs) - 1, dtype=np.int32), np.diff(cs)) for cs in (st["cs_l"], st["cs_p"])]
+    for df in (7, 31, 1):
+        mine = port.frame_bytes(int(g["frame_nstep"]), df, int(g["tag_base"]), st["lx"], st["lv"], st["ln"], g["frc_lf"], aff[0],
+                                st["px"], st["pv"], st["pn"], g["frc_pf"], aff[1], st["ptype"], st["ptag"])
+        assert mine == g[f"frame_{df}"].tobytes(), df
+
+
+@pytest.mark.parametrize("name", FILES)
+def test_constrain_volume_golden(name):
+    """Two consecutive calls (the scratch normals persist between them, constrain_volume.h:34,55) from a zeroed scratch."""
+    g = load_ext(name)
+    w = port.World(ext_state(g), kBT=0.0)
+    for k in (1, 2):
+        w.clear_force()
+        vol = w.constrain_volume(3.15, 0.05)
+        assert np.isfinite(vol)
+        assert rel_err(w.lf, g[f"cv{k}_lf"]) < 1e-5, k
+        assert rel_err(w.pf, g[f"cv{k}_pf"]) < 1e-5, k
+
+
+@pytest.mark.parametrize("name", FILES)
+def test_minimisation_loop_golden(name):
+    """Two iterations of openrbc.cpp:88-133 (rebuild with Morton sort, clear, forces, post_torque, mover, bounce_back)."""
+    g = load_ext(name)
+    w = port.World(ext_state(g), kBT=0.0)
+    for _ in range(2):
+        w.nstep = 0
+        w.rebuild()
+        w.clear_force(); w.compute_pairwise_fused(); w.compute_bonded()
+        w.post_torque(); w.opt_move(); w.bounce_back()
+    np.testing.assert_array_equal(w.cs_l, g["opt_cs_l"])
+    np.testing.assert_array_equal(w.cs_p, g["opt_cs_p"])
+    # positions carry the summation-order ulps of the pair forces (stencil visiting order), so do their per-cell means
+    assert rel_err(w.centroids, g["opt_centroids"]) < 1e-6
+    for p in "lp":
+        for f in "xn":
+            assert rel_err(getattr(w, p + f), g[f"opt_{p}{f}"]) < 1e-6, (p, f)
+        assert rel_err(getattr(w, p + "f"), g[f"opt_{p}f"]) < 2e-5
