@@ -363,20 +363,46 @@ def run_ours(args):
     e2e_sim.upload(host)
     if world > 1:
         e2e_sim.mg_export()              # owned ranges + halo masks of the fresh state (device work, no new allocations)
+    t_up = time.perf_counter()
+    trace = bool(os.environ.get("ORBC_BENCH_TRACE"))
+    if trace:
+        print(f"[bench rank {rank}] e2e upload + export took {(t_up - t_wall) * 1e3:.1f} ms", file=sys.stderr, flush=True)
+    slow = []                            # (ms, what) of the slowest host-side calls, for the phase breakdown
     h2d = sum(host[k].nbytes for k in ("lx", "lv", "ln", "lo", "px", "pv", "pn", "po", "ptype", "ptag", "bonds", "centroids", "cs_l", "cs_p"))
     d2h = 0
     for _ in range(args.steps):
+        t0 = time.perf_counter()
         if e2e_sim.nstep % FREQ_CLEANUP == 0:
             e2e_sim.delete_lipid(e2e_sim.stray_tolerance); d2h += 8
+            slow.append(((time.perf_counter() - t0) * 1e3, "delete_lipid@%d" % e2e_sim.nstep)); t0 = time.perf_counter()
         e2e_sim.step_langevin_checked(); d2h += 16
+        slow.append(((time.perf_counter() - t0) * 1e3, "step@%d" % (e2e_sim.nstep - 1)))
+        if trace and slow[-1][0] > 20.0:
+            print(f"[bench rank {rank}] slow call {slow[-1]}", file=sys.stderr, flush=True)
         if e2e_sim.nstep % FREQ_DISPLAY == 0:
             e2e_sim.compute_temperature(); d2h += 8
+    t_steps = time.perf_counter()
     fl = e2e_sim.download_into(0, x=out_l["x"].numpy(), n=out_l["n"].numpy(), affiliation=True)
     fp = e2e_sim.download_into(1, x=out_p["x"].numpy(), n=out_p["n"].numpy(), affiliation=True)
     d2h += fl + fp
     e2e_sim.event_record(3)
     e2e_sim.synchronize()
     wall_ms = (time.perf_counter() - t_wall) * 1e3
+    slow.sort(reverse=True)
+    phases = {"upload_ms": (t_up - t_wall) * 1e3, "steps_ms": (t_steps - t_up) * 1e3, "download_ms": wall_ms - (t_steps - t_wall) * 1e3,
+              "slowest_calls": [[round(a, 2), b] for a, b in slow[:4]], "median_step_ms": round(slow[len(slow) // 2][0], 3)}
+    if os.environ.get("ORBC_BENCH_TRACE"):
+        print(f"[bench rank {rank}] e2e phases {phases}", file=sys.stderr, flush=True)
+        # a few more (untimed) steps with a host synchronisation behind every call: which call is the slow one?
+        acc = {}
+        for _ in range(8):
+            calls = [("rebuild", e2e_sim.rebuild)] if e2e_sim.nstep % e2e_sim.freq_voronoi == 0 else []
+            calls += [("pairwise", e2e_sim.compute_pairwise_fused), ("bonded", e2e_sim.compute_bonded), ("langevin", e2e_sim.verlet_langevin)]
+            for name, fn in calls:
+                t0 = time.perf_counter(); fn(); t1 = time.perf_counter(); e2e_sim.synchronize(); t2 = time.perf_counter()
+                a = acc.setdefault(name, [0.0, 0.0, 0]); a[0] += (t1 - t0) * 1e3; a[1] += (t2 - t1) * 1e3; a[2] += 1
+            e2e_sim.nstep += 1
+        print(f"[bench rank {rank}] per call (issue ms, wait ms): " + ", ".join(f"{k} {v[0] / v[2]:.3f}/{v[1] / v[2]:.3f}" for k, v in acc.items()), file=sys.stderr, flush=True)
     barrier()
     e2e_ms = max(e2e_sim.event_elapsed_ms(2, 3), wall_ms)
     if world > 1:
@@ -414,7 +440,7 @@ def run_ours(args):
                      "algorithmic_bytes_per_launch": B_ALG_PAIR * n_l,
                      "note": "pair forces are FP32-ALU bound (~1.6-3 kFLOP per 48 B), see DESIGN.md; HBM fraction reported as the contract asks"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d / args.steps, "d2h_bytes_per_step": d2h / args.steps,
-                "ms_per_step": e2e_ms / args.steps, "what": "upload from pinned host containers + K per-call steps with status read-back + frame download, all timed"},
+                "ms_per_step": e2e_ms / args.steps, "phases": phases, "what": "upload from pinned host containers + K per-call steps with status read-back + frame download, all timed"},
         "gpu_launches": int(launches),
         "clocks": clk.summary(),
     }

@@ -159,6 +159,8 @@ ORBC_API int  orbc_run_nh(orbc_ctx *ctx, const orbc_step_params *p, int n_steps,
  * orbc_rebuild / orbc_compute_pairwise_fused / orbc_compute_bonded / orbc_integrate(VERLET_LANGEVIN) / orbc_run_langevin work on
  * the rank's own cells; halo copies, particle migration and the synchronisation between ranks happen on the device over
  * NVLink (peer stores and epoch flags), with no host synchronisation and no collective library on the data path.
+ * A fresh orbc_upload of the same system on connected ranks is followed by orbc_mg_export again (no second connect); that call
+ * is collective: it returns when every rank has exported.
  * orbc_constrain_volume, orbc_integrate(NH_*_FUSED / OPT_FUSED), orbc_run_nh, orbc_run_minimize and orbc_delete_lipid are decomposed
  * the same way.  Every rank must issue the same sequence of calls. */
 ORBC_API int  orbc_mg_init(orbc_ctx *ctx, int rank, int world /* <= 8 */);

@@ -172,6 +172,7 @@ int build_index(orbc_ctx *c, bool all_cells = true) {
     const int c0 = part ? c->mg.cb : 0, c1 = part ? c->mg.ce : nc;
     if (c1 > c0) ORBC_LAUNCH(c, k_stencil_build, blocks_for(c1 - c0, kStencilWarps), kStencilWarps * 32, 0, c->centroid, c0, c1, gd, c->stencil, c->stencil_cnt, c->d_flags, halo);
     c->stencil_valid = true;
+    c->lruns_valid = false;
     return ORBC_OK;
 }
 
@@ -306,7 +307,14 @@ int launch_pairwise(orbc_ctx *c, bool accumulate = true) {
             const int *gate = c->ll_half ? c->rel_flag : nullptr;
             if (c->ll_half == 1) ORBC_LAUNCH(c, (k_pair_ll_h<20>), blocks_for(nl, kLLBlock), kLLBlock, 0, a, c->lbound, c->rel16, gate, 0);
             else if (c->ll_half) ORBC_LAUNCH(c, (k_pair_ll_h<18>), blocks_for(nl, kLLBlock), kLLBlock, 0, a, c->lbound, c->rel16, gate, 0);
-            switch (c->ll_variant) {     // bit 1: per-lane bounding-sphere cull of the stencil cells; bit 0: aim at 20 resident blocks per SM
+            if ((c->ll_variant & 4) && !c->ll_half) {     // candidate runs merged over Morton-adjacent stencil cells, rebuilt after every rebuild
+                if (!c->lruns_valid) {
+                    if (a.ce > a.cb) ORBC_LAUNCH(c, k_lipid_runs, blocks_for(a.ce - a.cb, 128), 128, 0, a.cb, a.ce, c->stencil, c->stencil_cnt, L.cell_start, c->lruns, c->lrun_cnt);
+                    c->lruns_valid = true;
+                }
+                ORBC_LAUNCH(c, (k_pair_ll_r<20, 4>), blocks_for(nl, kLLBlock), kLLBlock, 0, a, c->lruns, c->lrun_cnt);
+            } else
+            switch (c->ll_variant & 3) { // bit 1: per-lane bounding-sphere cull of the stencil cells; bit 0: aim at 20 resident blocks per SM
             case 0: ORBC_LAUNCH(c, (k_pair_ll<false, 1>), blocks_for(nl, kLLBlock), kLLBlock, 0, a, c->lbound, gate, 1); break;
             case 1: ORBC_LAUNCH(c, (k_pair_ll<false, 20>), blocks_for(nl, kLLBlock), kLLBlock, 0, a, c->lbound, gate, 1); break;
             case 2: ORBC_LAUNCH(c, (k_pair_ll<true, 1>), blocks_for(nl, kLLBlock), kLLBlock, 0, a, c->lbound, gate, 1); break;
@@ -418,6 +426,7 @@ int cell_update_move(orbc_ctx *c, int sp) {
         S.cur = nx; S.cur_xn = nxn;
     }
     S.has_partition = true;
+    if (sp == ORBC_LIPID) c->lruns_valid = false;
     return ORBC_OK;
 }
 // Phase C: tag -> index map (container.h:39-58); decomposed: new owned range, bonded-partner masks, halo copies of the moved particles
@@ -480,7 +489,7 @@ int preload_kernels() {
     ORBC_PRELOAD(k_cv_normal_volume); ORBC_PRELOAD(k_fill_cellid); ORBC_PRELOAD(k_fill_int); ORBC_PRELOAD(k_halo_push); ORBC_PRELOAD(k_kinetic);
     ORBC_PRELOAD(k_mg_barrier); ORBC_PRELOAD(k_morton_keys); ORBC_PRELOAD(k_morton_keys_only); ORBC_PRELOAD(k_nh_final); ORBC_PRELOAD(k_nh_final_fused);
     ORBC_PRELOAD(k_nh_initial_fused); ORBC_PRELOAD(k_nh_zeta_update); ORBC_PRELOAD(k_share_ke); ORBC_PRELOAD(k_sum_ke); ORBC_PRELOAD(k_noise); ORBC_PRELOAD(k_opt_move); ORBC_PRELOAD(k_pack4);
-    ORBC_PRELOAD(k_pair_lipid); ORBC_PRELOAD((k_pair_ll_h<20>)); ORBC_PRELOAD((k_pair_ll_h<18>)); ORBC_PRELOAD((k_pair_ll<false, 1>)); ORBC_PRELOAD((k_pair_ll<false, 20>)); ORBC_PRELOAD((k_pair_ll<true, 1>)); ORBC_PRELOAD((k_pair_ll<true, 20>)); ORBC_PRELOAD(k_pair_prot<1>); ORBC_PRELOAD(k_pair_prot<2>); ORBC_PRELOAD(k_pair_prot<4>); ORBC_PRELOAD(k_pair_protein);
+    ORBC_PRELOAD(k_pair_lipid); ORBC_PRELOAD(k_lipid_runs); ORBC_PRELOAD((k_pair_ll_r<20, 4>)); ORBC_PRELOAD((k_pair_ll_h<20>)); ORBC_PRELOAD((k_pair_ll_h<18>)); ORBC_PRELOAD((k_pair_ll<false, 1>)); ORBC_PRELOAD((k_pair_ll<false, 20>)); ORBC_PRELOAD((k_pair_ll<true, 1>)); ORBC_PRELOAD((k_pair_ll<true, 20>)); ORBC_PRELOAD(k_pair_prot<1>); ORBC_PRELOAD(k_pair_prot<2>); ORBC_PRELOAD(k_pair_prot<4>); ORBC_PRELOAD(k_pair_protein);
     ORBC_PRELOAD(k_permute_centroids); ORBC_PRELOAD(k_porder_flag); ORBC_PRELOAD(k_porder_scatter); ORBC_PRELOAD(k_post_torque); ORBC_PRELOAD(k_radix_hist);
     ORBC_PRELOAD(k_radix_scatter); ORBC_PRELOAD(k_rank_and_move); ORBC_PRELOAD(k_remap_cellid); ORBC_PRELOAD(k_scan_onepass); ORBC_PRELOAD(k_set3); ORBC_PRELOAD(k_set_range); ORBC_PRELOAD(k_set_range_const); ORBC_PRELOAD(k_share_counts);
     ORBC_PRELOAD(k_stencil_build); ORBC_PRELOAD(k_stray_mask); ORBC_PRELOAD(k_unpack3); ORBC_PRELOAD(k_unpack_w); ORBC_PRELOAD(k_verlet_langevin); ORBC_PRELOAD(k_zero4);
@@ -604,7 +613,7 @@ void orbc_destroy(orbc_ctx *c) { if (c) cudaSetDevice(c->device);
     free_species(c->sp[0]); free_species(c->sp[1]);
     dev_free(c->centroid); dev_free(c->centroid_tmp); dev_free(c->keys); dev_free(c->keys_tmp); dev_free(c->perm); dev_free(c->perm_tmp); dev_free(c->inv);
     dev_free(c->grid.bin_start); dev_free(c->grid.bin_items); dev_free(c->grid.bin_of); dev_free(c->grid.bin_slot); dev_free(c->grid.sorted);
-    dev_free(c->stencil); dev_free(c->stencil_cnt); dev_free(c->cell_normal); dev_free(c->lbound); dev_free(c->pbound); dev_free(c->porder); dev_free(c->bonds); dev_free(c->tag2idx);
+    dev_free(c->stencil); dev_free(c->stencil_cnt); dev_free(c->cell_normal); dev_free(c->lbound); dev_free(c->pbound); dev_free(c->porder); dev_free(c->lruns); dev_free(c->lrun_cnt); dev_free(c->bonds); dev_free(c->tag2idx);
     dev_free(c->scan_tmp); dev_free(c->radix_hist); dev_free(c->stage); dev_free(c->d_acc); dev_free(c->d_counters); dev_free(c->d_flags); dev_free(c->d_nh);
     dev_free(c->noise[0]); dev_free(c->noise[1]); dev_free(c->d_range); dev_free(c->rel16); dev_free(c->rel_flag);
     for (void *m : c->mg.opened) cudaIpcCloseMemHandle(m);
@@ -628,7 +637,7 @@ int orbc_set_option(orbc_ctx *c, const char *name, double value) { if (c) cudaSe
     if (!strcmp(name, "pair_impl")) { if (value != 1 && value != 2) return fail(ORBC_ERR_ARG, "pair_impl must be 1 or 2"); c->pair_impl = (int)value; return ORBC_OK; }
     if (!strcmp(name, "prot_lanes")) { if (value != 0 && value != 1 && value != 2 && value != 4) return fail(ORBC_ERR_ARG, "prot_lanes must be 0 (automatic), 1, 2 or 4"); c->prot_lanes = (int)value; return ORBC_OK; }
     if (!strcmp(name, "ll_half")) { c->ll_half = (int)value; return ORBC_OK; }   // 0 off, 1 / 2: register targets of 20 / 18 resident blocks   // packed half-precision prefilter in the lipid-lipid kernel
-    if (!strcmp(name, "ll_variant")) { c->ll_variant = (int)value & 3; return ORBC_OK; }   // tuning variants of k_pair_ll (see launch_pairwise)
+    if (!strcmp(name, "ll_variant")) { c->ll_variant = (int)value & 7; return ORBC_OK; }   // tuning variants of k_pair_ll (see launch_pairwise)
     if (!strcmp(name, "debug_barriers")) {                       // profiling aid: `value` back-to-back barriers of a decomposed run
         for (int k = 0; k < (int)value; ++k) ORBC_TRY(mg_barrier(c));
         return ORBC_OK;
@@ -716,6 +725,7 @@ int orbc_voronoi_upload(orbc_ctx *c, int nc, const float *centroids3, const int 
         ORBC_TRY(dev_alloc(&c->grid.bin_items, nc)); ORBC_TRY(dev_alloc(&c->grid.bin_of, nc)); ORBC_TRY(dev_alloc(&c->grid.bin_slot, nc)); ORBC_TRY(dev_alloc(&c->grid.sorted, nc));
         ORBC_TRY(dev_alloc(&c->stencil, (size_t)nc * kStencilStride)); ORBC_TRY(dev_alloc(&c->stencil_cnt, nc));
         ORBC_TRY(dev_alloc(&c->cell_normal, nc)); ORBC_TRY(dev_alloc(&c->lbound, nc)); ORBC_TRY(dev_alloc(&c->pbound, nc));
+        ORBC_TRY(dev_alloc(&c->lruns, (size_t)nc * kRunStride)); ORBC_TRY(dev_alloc(&c->lrun_cnt, (size_t)nc)); c->lruns_cells = (size_t)nc;
         for (int s = 0; s < 2; ++s) ORBC_TRY(dev_alloc(&c->sp[s].cell_start, (size_t)nc + 1));
         c->n_cells = nc;
     }
@@ -1069,6 +1079,9 @@ int orbc_mg_export(orbc_ctx *c, void *blob_out, size_t bytes) { if (c) cudaSetDe
                         m.my_bonds, m.my_bonds_cap, c->d_flags);
         c->porder_valid = false;
     }
+    // a repeated export (fresh upload of the same system on connected ranks) is a collective call: no rank may start storing
+    // counts, halo copies or migrating particles into a peer that is still uploading or clearing its tables
+    if (m.connected) ORBC_TRY(mg_barrier(c));
     ORBC_CUDA(cudaStreamSynchronize(c->stream));
     MgBlob *b = (MgBlob *)blob_out;
     memset(b, 0, sizeof(*b));

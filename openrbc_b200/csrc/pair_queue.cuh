@@ -255,6 +255,93 @@ __global__ void __launch_bounds__(kLLBlock, MINB) k_pair_ll(PairArgs a, const fl
     ll_finish(a, i, live, st, xi, mi, fx, fy, fz, tx, ty, tz, sB);
 }
 
+// ---- k_pair_ll_r: the same kernel over precomputed candidate RUNS ---------------------------------------------------------------------
+// The candidates of a lipid are the members of the r<6 stencil cells of its cell, visited in ascending cell id.  Cells are
+// numbered in Morton order and particles are stored sorted by cell, so neighbouring stencil cells usually hold neighbouring
+// slot ranges: k_lipid_runs merges them, once per rebuild, into a few (first slot, length) runs per cell.  The stream then
+// advances by one 8-byte load per run instead of three dependent loads per cell (stencil id -> cell_start pair), wastes fewer
+// lanes on the partial group at the end of every cell, and the loop control shrinks accordingly.  Same candidates, same order,
+// same hits as k_pair_ll: results are bit-identical.
+constexpr int kRunStride = 32;     // a cell has at most 32 stencil cells of the r<6 class (k_stencil_build raises a flag otherwise)
+__global__ void k_lipid_runs(int cb, int ce, const int *__restrict__ stencil, const int *__restrict__ stencil_cnt, const int *__restrict__ cs_l,
+                             int2 *__restrict__ lruns, int *__restrict__ lrun_cnt) {
+    const int c = cb + blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ce) return;
+    const int n6 = min(stencil_cnt[c] & 255, 32);
+    const int *st = stencil + (size_t)c * kStencilStride;
+    int2 *out = lruns + (size_t)c * kRunStride;
+    int nr = 0, rb = 0, re = -1;
+    for (int k = 0; k < n6; ++k) {
+        const int c2 = st[k];
+        const int b = cs_l[c2], e = cs_l[c2 + 1];
+        if (e <= b) continue;
+        if (b == re) { re = e; continue; }
+        if (re > rb) out[nr++] = make_int2(rb, re - rb);
+        rb = b; re = e;
+    }
+    if (re > rb) out[nr++] = make_int2(rb, re - rb);
+    lrun_cnt[c] = nr;
+}
+
+// W = candidates per lane and iteration.  Measured on the full RBC (B200): W = 4 with 20 resident blocks 470 us (k_pair_ll: 508);
+// W = 8 505-515 us (longer partial groups, 64 registers); 24 resident blocks at 40 registers 538 us (spills); an L1 prefetch 4-16
+// candidates ahead of the stream changes nothing.
+template <int MINB, int W>
+__global__ void __launch_bounds__(kLLBlock, MINB) k_pair_ll_r(PairArgs a, const int2 *__restrict__ lruns, const int *__restrict__ lrun_cnt) {
+    __shared__ int s_q[kLLBlock / 32][kQCap * 32];
+    const int lane = threadIdx.x & 31;
+    int *const q = s_q[threadIdx.x >> 5] + lane;
+    const int i = a.range[0] + blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i < a.range[1];
+    const float4 *__restrict__ xl = a.xl;
+    const float4 *__restrict__ nl = a.nl;
+    float fx = 0, fy = 0, fz = 0, tx = 0, ty = 0, tz = 0, sB = 0;
+    F3 xi = {0, 0, 0}, mi = {0, 0, 0};
+    const int *st = a.stencil;
+    const LLConst kc = {c_ff.cutll, 8.0f * c_ff.repll, 4.0f * c_ff.attll, c_ff.alphall, c_ff.alphall * c_ff.attll, 1.0f - c_ff.alphall, c_ff.cutsqll};
+    // r2 > 1e-5 && r2 < cutsq (compute_pairwise_fused.h:109,134) as ONE unsigned comparison of the bit patterns: r2 is a sum of
+    // squares (never negative), and non-negative floats order like their bits; a NaN lies above every finite pattern
+    const unsigned lo_bits = __float_as_uint(1e-5f) + 1u, span = __float_as_uint(c_ff.cutsqll) - lo_bits;
+    const int2 *rp = lruns;
+    int nr = 0;
+    if (live) {
+        const float4 xi4 = xl[i], ni4 = nl[i];
+        xi = {xi4.x, xi4.y, xi4.z}; mi = {ni4.x, ni4.y, ni4.z};
+        const int c = a.cell_l[i];
+        st += (size_t)c * kStencilStride;
+        rp += (size_t)c * kRunStride;
+        nr = __ldg(lrun_cnt + c);
+    }
+    const unsigned q0 = (unsigned)__cvta_generic_to_shared(q);
+    const unsigned q_full = q0 + (kQCap - W) * 128;              // a group of W always fits below this mark
+    unsigned qp = q0;
+    int2 nx = make_int2(0, 0);                                   // the next run, loaded one advance ahead
+    if (nr > 0) nx = __ldg(rp);
+    int k = 0, cur = 0, rem = 0;
+    for (;;) {
+        if (rem <= 0 && k < nr) { cur = nx.x; rem = nx.y; ++k; if (k < nr) nx = __ldg(rp + k); }
+        if (!__any_sync(0xffffffffu, rem > 0)) break;
+        if (__any_sync(0xffffffffu, qp > q_full)) {              // make room: every lane drains its queue (dense)
+            for (unsigned e = q0; e < qp; e += 128) ll_eval<false>(kc, xl, nl, xi, mi, lds_i32(e), fx, fy, fz, tx, ty, tz, sB);
+            qp = q0;
+        }
+        const float4 *__restrict__ p = xl + cur;
+        float4 xj[W];
+        #pragma unroll
+        for (int u = 0; u < W; ++u) xj[u] = __ldg(p + u);
+        #pragma unroll
+        for (int u = 0; u < W; ++u) {
+            const float dx = xi.x - xj[u].x, dy = xi.y - xj[u].y, dz = xi.z - xj[u].z;
+            const float r2 = dx * dx + dy * dy + dz * dz;
+            if (u < rem && __float_as_uint(r2) - lo_bits < span) { sts_i32(qp, cur + u); qp += 128; }
+        }
+        if (rem > 0) cur += W;
+        rem -= W;
+    }
+    for (unsigned e = q0; e < qp; e += 128) ll_eval<false>(kc, xl, nl, xi, mi, lds_i32(e), fx, fy, fz, tx, ty, tz, sB);
+    ll_finish(a, i, live, st, xi, mi, fx, fy, fz, tx, ty, tz, sB);
+}
+
 // ---- k_pair_ll_h (EXPERIMENTAL, off by default: option "ll_half"): the cutoff test of phase 1 in packed half precision ---------
 // Measured on the full RBC (profiles/r01_half_prefilter.txt): exact (hits, order and forces bit-identical to k_pair_ll), the
 // packed test is 25 % cheaper than the fp32 one (16 instructions per two partners), but the kernel as a whole is SLOWER (540-590

@@ -85,10 +85,7 @@ int main( int argc, char ** argv ) {
         b200::compute_pairwise_fused( dev );
         b200::compute_bonded( dev );
     };
-    auto dump = [&]() {
-        dev.download( lipid, protein, cell_lipid, cell_protein, param.dump_field );
-        save_frame( traj, lipid, protein, cell_lipid, cell_protein, param );
-    };
+    auto dump = [&]() { b200::save_frame( dev, traj, lipid, param ); };
 
     // ---- energy minimisation (openrbc.cpp:88-146) ---------------------------------------------------------------------------
     std::cout << "Opt..." << std::endl;
@@ -105,6 +102,7 @@ int main( int argc, char ** argv ) {
             display( std::cout, nopt + 1, b200::compute_temperature( dev ), omp_get_wtime() - Service<Timers>::call()["+optimization"].get_start_time() );
     }
     orbc_synchronize( dev.ctx );
+    b200::flush_frames( dev, traj );
     Service<Timers>::call()["+optimization"].stop();
     Service<Timers>::call().report( true );
 
@@ -137,6 +135,7 @@ int main( int argc, char ** argv ) {
             display( std::cout, param.nstep * param.dt, b200::compute_temperature( dev ), omp_get_wtime() - Service<Timers>::call()["+main-loop"].get_start_time() );
     }
     orbc_synchronize( dev.ctx );
+    b200::flush_frames( dev, traj );
 
     std::size_t nl = 0, np = 0;
     orbc_size( dev.ctx, ORBC_LIPID, &nl ); orbc_size( dev.ctx, ORBC_PROTEIN, &np );

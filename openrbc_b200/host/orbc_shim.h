@@ -15,7 +15,9 @@
 //   compute_bonded(protein)                                  :106,173,225  compute_bonded(dev)
 //   integrate(KERNEL(param), lipid, protein)                 :94,110,...   integrate(dev, b200::KERNEL(param))  (same functor names)
 //   compute_temperature(lipid, protein, param)               :143,253      compute_temperature(dev)
-//   update_particle_affiliation + save_frame                 :138-140,248  download(dev, lipid, protein, cl, cp) then the reference's save_frame
+//   update_particle_affiliation + save_frame                 :138-140,248  save_frame(dev, traj, lipid, param): the frame is assembled on the
+//                                                                          device in the .orbc layout and copied out while the run goes on
+//                                                                          (or: download(dev, ...) then the reference's own save_frame)
 #ifndef ORBC_SHIM_H_
 #define ORBC_SHIM_H_
 
@@ -77,6 +79,19 @@ struct Device {
                               frc ? (float *) protein.f.data() : nullptr, nullptr, cell_protein.affiliation.data(), protein.type.data(), protein.tag.data(), nullptr ), "orbc_download(protein)" );
     }
 };
+
+// save_frame( traj, lipid, protein, cell_lipid, cell_protein, param ) (trajectory.h:61-105) with update_particle_affiliation folded in.
+// The bytes of frame k are appended to the stream when frame k + 1 is requested (or by flush_frames), so the device-to-host
+// copy overlaps the steps in between.
+inline void flush_frames( Device & dev, std::ostream & traj ) {
+    const void * data = nullptr; std::size_t bytes = 0;
+    while ( orbc_save_frame_end( dev.ctx, &data, &bytes ) == ORBC_OK ) traj.write( (const char *) data, (std::streamsize) bytes );
+    traj << std::flush;
+}
+inline void save_frame( Device & dev, std::ostream & traj, LipidContainer const & lipid, RTParameter const & param ) {
+    flush_frames( dev, traj );
+    check( orbc_save_frame_begin( dev.ctx, param.nstep, param.dump_field, lipid.tag[0] ), "save_frame" );
+}
 
 // brackets one device call with the reference's timer of the same name (timer.h:26-69)
 struct TimedCall {

@@ -26,7 +26,7 @@ for row in csv.reader(out):
         continue
     key = (fname, int(row[0]))
     a = agg.setdefault(key, [0, 0, row[1].strip()])
-    a[0] += int(ie); a[1] += int(sm or 0)
+    a[0] += int(ie); a[1] += int(sm) if sm.isdigit() else 0
 ti = sum(a[0] for a in agg.values()); ts = sum(a[1] for a in agg.values())
 print(f"total warp instructions {ti}, samples {ts}")
 for (f, ln), a in sorted(agg.items()):
