@@ -361,12 +361,13 @@ def run_ours(args):
     e2e_sim.event_record(2)
     t_wall = time.perf_counter()
     e2e_sim.upload(host)
+    t_up0 = time.perf_counter()
     if world > 1:
-        e2e_sim.mg_export()              # owned ranges + halo masks of the fresh state (device work, no new allocations)
+        e2e_sim.mg_export()              # owned ranges + halo masks of the fresh state (device work, no new allocations); collective
     t_up = time.perf_counter()
     trace = bool(os.environ.get("ORBC_BENCH_TRACE"))
     if trace:
-        print(f"[bench rank {rank}] e2e upload + export took {(t_up - t_wall) * 1e3:.1f} ms", file=sys.stderr, flush=True)
+        print(f"[bench rank {rank}] e2e upload {(t_up0 - t_wall) * 1e3:.1f} ms + export {(t_up - t_up0) * 1e3:.1f} ms", file=sys.stderr, flush=True)
     slow = []                            # (ms, what) of the slowest host-side calls, for the phase breakdown
     h2d = sum(host[k].nbytes for k in ("lx", "lv", "ln", "lo", "px", "pv", "pn", "po", "ptype", "ptag", "bonds", "centroids", "cs_l", "cs_p"))
     d2h = 0

@@ -109,6 +109,10 @@ ORBC_API int  orbc_upload_bonds(orbc_ctx *ctx, size_t n_bonds, const int *type_i
 /* VoronoiDiagram::centroids + VCellList::cell_start of both containers after voronoi.init() (openrbc.cpp:69-74).
  * Particles must already be stored sorted by cell.  cell_start_* may be NULL (no previous partition known). */
 ORBC_API int  orbc_voronoi_upload(orbc_ctx *ctx, int n_cells, const float *centroids3, const int *cell_start_l, const int *cell_start_p);
+/* VoronoiDiagram::init(lipid, cell_lipid, param, n_iterate) (voronoi.h:54-75, openrbc.cpp:71) on the device, for hosts that do
+ * not want to spend the reference's seconds of k-means on the CPU: needs the lipids uploaded (any order), leaves them sorted by
+ * cell with centroids, cell_start and the index in place; follow with orbc_cell_update(ORBC_PROTEIN).  Single GPU. */
+ORBC_API int  orbc_voronoi_init(orbc_ctx *ctx, int n_cells, int n_iterate);
 /* overwrite f / t / v of one container (tests, and hosts that compute extra forces on the CPU); field: 'f','t','v','x','n','o' */
 ORBC_API int  orbc_set_field(orbc_ctx *ctx, int species, char field, size_t stride_floats, const float *src);
 

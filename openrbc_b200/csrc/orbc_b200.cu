@@ -178,12 +178,16 @@ int build_index(orbc_ctx *c, bool all_cells = true) {
 
 // fit the uniform grid to the centroids' bounding box (host side, at upload); centroids that later drift outside are
 // clamped into the boundary bins, which keeps every search exact
+int fit_grid_box(orbc_ctx *c, float lo[3], float hi[3]);
 int fit_grid(orbc_ctx *c, const float *centroids3, int nc) {
     float lo[3] = {1e30f, 1e30f, 1e30f}, hi[3] = {-1e30f, -1e30f, -1e30f};
     for (int i = 0; i < nc; ++i) for (int d = 0; d < 3; ++d) {
         const float v = centroids3[3 * i + d];
         if (v == v) { lo[d] = std::min(lo[d], v); hi[d] = std::max(hi[d], v); }
     }
+    return fit_grid_box(c, lo, hi);
+}
+int fit_grid_box(orbc_ctx *c, float lo[3], float hi[3]) {
     for (int d = 0; d < 3; ++d) if (lo[d] > hi[d]) { lo[d] = 0; hi[d] = 0; }
     Grid &g = c->grid;
     float h = kBin;
@@ -361,7 +365,7 @@ int do_voronoi_update(orbc_ctx *c, int nstep, int freq_sort_ctrd) {
     CentroidOut out; out.world = mg ? c->mg.world : 1;
     for (int r = 0; r < kMaxWorld; ++r) out.dst[r] = mg ? c->mg.peers.centroid[c->mg.cen_par ^ 1][r] : c->centroid_tmp;
     const int cb = mg ? c->mg.cb : 0, ce = mg ? c->mg.ce : nc;
-    if (ce > cb) ORBC_LAUNCH(c, k_centroid_update, blocks_for(ce - cb, kBlock), kBlock, 0, L.cell_start, L.X(), cb, ce, out);
+    if (ce > cb) ORBC_LAUNCH(c, k_centroid_update, blocks_for(ce - cb, kBlock), kBlock, 0, L.cell_start, L.X(), cb, ce, out, (const int *)nullptr);
     ORBC_TRY(mg_barrier(c));
     const bool morton = freq_sort_ctrd > 0 && nstep % freq_sort_ctrd == 0;
     if (morton) {
@@ -489,7 +493,7 @@ int preload_kernels() {
     ORBC_PRELOAD(k_cv_normal_volume); ORBC_PRELOAD(k_fill_cellid); ORBC_PRELOAD(k_fill_int); ORBC_PRELOAD(k_halo_push); ORBC_PRELOAD(k_kinetic);
     ORBC_PRELOAD(k_mg_barrier); ORBC_PRELOAD(k_morton_keys); ORBC_PRELOAD(k_morton_keys_only); ORBC_PRELOAD(k_nh_final); ORBC_PRELOAD(k_nh_final_fused);
     ORBC_PRELOAD(k_nh_initial_fused); ORBC_PRELOAD(k_nh_zeta_update); ORBC_PRELOAD(k_share_ke); ORBC_PRELOAD(k_sum_ke); ORBC_PRELOAD(k_noise); ORBC_PRELOAD(k_opt_move); ORBC_PRELOAD(k_pack4);
-    ORBC_PRELOAD(k_pair_lipid); ORBC_PRELOAD(k_lipid_runs); ORBC_PRELOAD((k_pair_ll_r<20, 4>)); ORBC_PRELOAD((k_pair_ll_h<20>)); ORBC_PRELOAD((k_pair_ll_h<18>)); ORBC_PRELOAD((k_pair_ll<false, 1>)); ORBC_PRELOAD((k_pair_ll<false, 20>)); ORBC_PRELOAD((k_pair_ll<true, 1>)); ORBC_PRELOAD((k_pair_ll<true, 20>)); ORBC_PRELOAD(k_pair_prot<1>); ORBC_PRELOAD(k_pair_prot<2>); ORBC_PRELOAD(k_pair_prot<4>); ORBC_PRELOAD(k_pair_protein);
+    ORBC_PRELOAD(k_pair_lipid); ORBC_PRELOAD(k_lipid_runs); ORBC_PRELOAD(k_rank_only); ORBC_PRELOAD(k_init_centroids); ORBC_PRELOAD(k_bbox); ORBC_PRELOAD((k_pair_ll_r<20, 4>)); ORBC_PRELOAD((k_pair_ll_h<20>)); ORBC_PRELOAD((k_pair_ll_h<18>)); ORBC_PRELOAD((k_pair_ll<false, 1>)); ORBC_PRELOAD((k_pair_ll<false, 20>)); ORBC_PRELOAD((k_pair_ll<true, 1>)); ORBC_PRELOAD((k_pair_ll<true, 20>)); ORBC_PRELOAD(k_pair_prot<1>); ORBC_PRELOAD(k_pair_prot<2>); ORBC_PRELOAD(k_pair_prot<4>); ORBC_PRELOAD(k_pair_protein);
     ORBC_PRELOAD(k_permute_centroids); ORBC_PRELOAD(k_porder_flag); ORBC_PRELOAD(k_porder_scatter); ORBC_PRELOAD(k_post_torque); ORBC_PRELOAD(k_radix_hist);
     ORBC_PRELOAD(k_radix_scatter); ORBC_PRELOAD(k_rank_and_move); ORBC_PRELOAD(k_remap_cellid); ORBC_PRELOAD(k_scan_onepass); ORBC_PRELOAD(k_set3); ORBC_PRELOAD(k_set_range); ORBC_PRELOAD(k_set_range_const); ORBC_PRELOAD(k_share_counts);
     ORBC_PRELOAD(k_stencil_build); ORBC_PRELOAD(k_stray_mask); ORBC_PRELOAD(k_unpack3); ORBC_PRELOAD(k_unpack_w); ORBC_PRELOAD(k_verlet_langevin); ORBC_PRELOAD(k_zero4);
@@ -524,6 +528,19 @@ int do_constrain_volume(orbc_ctx *c, float target, float strength) {
                          (const int *)nullptr, 0, target, strength, c->d_acc, vol_all, world, L.f);
     if (P.n && P.has_partition) ORBC_LAUNCH(c, k_cv_apply, blocks_for(owned_bound(c, ORBC_PROTEIN), kBlock), kBlock, 0, P.C(), c->d_range + 2, c->cell_normal, P.X(), P.n,
                                             ptype, 1, target, strength, c->d_acc, vol_all, world, P.f);
+    return ORBC_OK;
+}
+
+int alloc_voronoi(orbc_ctx *c, int nc) {
+    if (nc == c->n_cells) return ORBC_OK;
+    ORBC_TRY(dev_alloc(&c->centroid, nc)); ORBC_TRY(dev_alloc(&c->centroid_tmp, nc));
+    ORBC_TRY(dev_alloc(&c->keys, nc)); ORBC_TRY(dev_alloc(&c->keys_tmp, nc)); ORBC_TRY(dev_alloc(&c->perm, nc)); ORBC_TRY(dev_alloc(&c->perm_tmp, nc)); ORBC_TRY(dev_alloc(&c->inv, nc));
+    ORBC_TRY(dev_alloc(&c->grid.bin_items, nc)); ORBC_TRY(dev_alloc(&c->grid.bin_of, nc)); ORBC_TRY(dev_alloc(&c->grid.bin_slot, nc)); ORBC_TRY(dev_alloc(&c->grid.sorted, nc));
+    ORBC_TRY(dev_alloc(&c->stencil, (size_t)nc * kStencilStride)); ORBC_TRY(dev_alloc(&c->stencil_cnt, nc));
+    ORBC_TRY(dev_alloc(&c->cell_normal, nc)); ORBC_TRY(dev_alloc(&c->lbound, nc)); ORBC_TRY(dev_alloc(&c->pbound, nc));
+    ORBC_TRY(dev_alloc(&c->lruns, (size_t)nc * kRunStride)); ORBC_TRY(dev_alloc(&c->lrun_cnt, (size_t)nc)); c->lruns_cells = (size_t)nc;
+    for (int s = 0; s < 2; ++s) ORBC_TRY(dev_alloc(&c->sp[s].cell_start, (size_t)nc + 1));
+    c->n_cells = nc;
     return ORBC_OK;
 }
 
@@ -719,16 +736,7 @@ int orbc_upload_bonds(orbc_ctx *c, size_t n_bonds, const int *tij) { if (c) cuda
 int orbc_voronoi_upload(orbc_ctx *c, int nc, const float *centroids3, const int *csl, const int *csp) { if (c) cudaSetDevice(c->device);
     if (!c || nc <= 0 || !centroids3) return fail(ORBC_ERR_ARG, "orbc_voronoi_upload: bad argument");
     if (nc >= (1 << 28)) return fail(ORBC_ERR_ARG, "more than 2^28 Voronoi cells");
-    if (nc != c->n_cells) {
-        ORBC_TRY(dev_alloc(&c->centroid, nc)); ORBC_TRY(dev_alloc(&c->centroid_tmp, nc));
-        ORBC_TRY(dev_alloc(&c->keys, nc)); ORBC_TRY(dev_alloc(&c->keys_tmp, nc)); ORBC_TRY(dev_alloc(&c->perm, nc)); ORBC_TRY(dev_alloc(&c->perm_tmp, nc)); ORBC_TRY(dev_alloc(&c->inv, nc));
-        ORBC_TRY(dev_alloc(&c->grid.bin_items, nc)); ORBC_TRY(dev_alloc(&c->grid.bin_of, nc)); ORBC_TRY(dev_alloc(&c->grid.bin_slot, nc)); ORBC_TRY(dev_alloc(&c->grid.sorted, nc));
-        ORBC_TRY(dev_alloc(&c->stencil, (size_t)nc * kStencilStride)); ORBC_TRY(dev_alloc(&c->stencil_cnt, nc));
-        ORBC_TRY(dev_alloc(&c->cell_normal, nc)); ORBC_TRY(dev_alloc(&c->lbound, nc)); ORBC_TRY(dev_alloc(&c->pbound, nc));
-        ORBC_TRY(dev_alloc(&c->lruns, (size_t)nc * kRunStride)); ORBC_TRY(dev_alloc(&c->lrun_cnt, (size_t)nc)); c->lruns_cells = (size_t)nc;
-        for (int s = 0; s < 2; ++s) ORBC_TRY(dev_alloc(&c->sp[s].cell_start, (size_t)nc + 1));
-        c->n_cells = nc;
-    }
+    ORBC_TRY(alloc_voronoi(c, nc));
     ORBC_CUDA(cudaMemsetAsync(c->cell_normal, 0, sizeof(float4) * nc, c->stream));
     ORBC_TRY(ensure_stage(c, (size_t)3 * nc));
     ORBC_CUDA(cudaMemcpyAsync(c->stage, centroids3, sizeof(float) * 3 * nc, cudaMemcpyHostToDevice, c->stream));
@@ -748,6 +756,73 @@ int orbc_voronoi_upload(orbc_ctx *c, int nc, const float *centroids3, const int 
     ORBC_TRY(build_index(c));
     ORBC_CUDA(cudaStreamSynchronize(c->stream));   // host arrays are borrowed only for the duration of the call
     return ORBC_OK;
+}
+
+int orbc_voronoi_init(orbc_ctx *c, int nc, int n_iterate) { if (c) cudaSetDevice(c->device);
+    // VoronoiDiagram::init (voronoi.h:54-75): initial guess = every delta-th lipid; n_iterate rounds of { Morton sort of the centroids,
+    // index rebuild (tree.build), partition, centroid update through VCellList::cells }, the container being reordered only at
+    // the rounds k = 0, 1, 2, 4, 8, ... and once more at the end.
+    if (!c || nc <= 0 || n_iterate <= 0) return fail(ORBC_ERR_ARG, "orbc_voronoi_init: bad argument");
+    ORBC_TRY(single_gpu_only(c, "orbc_voronoi_init"));
+    Species &L = c->sp[0];
+    if (!L.n) return fail(ORBC_ERR_ARG, "orbc_voronoi_init: upload the lipids first");
+    if (nc >= (1 << 28)) return fail(ORBC_ERR_ARG, "more than 2^28 Voronoi cells");
+    const int last = n_iterate - 1;
+    if ((last & (~last + 1)) == last)
+        return fail(ORBC_ERR_ARG, "orbc_voronoi_init: with n_iterate - 1 = %d a power of two (or zero) the reference applies its last permutation twice (voronoi.h:70,74) and leaves the "
+                    "container unsorted; use another count (the driver uses 64)", last);
+    ORBC_TRY(alloc_voronoi(c, nc));
+    ORBC_CUDA(cudaMemsetAsync(c->cell_normal, 0, sizeof(float4) * nc, c->stream));
+    // grid over the bounding box of the lipids: every centroid is a mean of lipid positions and stays inside it
+    int *bb_dev = nullptr; ORBC_TRY(dev_alloc(&bb_dev, 6));
+    const int init_bb[6] = {0x7fffffff, 0x7fffffff, 0x7fffffff, (int)0x80000000, (int)0x80000000, (int)0x80000000};
+    ORBC_CUDA(cudaMemcpyAsync(bb_dev, init_bb, sizeof(init_bb), cudaMemcpyHostToDevice, c->stream));
+    ORBC_LAUNCH(c, k_bbox, blocks_for(L.n, kBlock), kBlock, 0, L.X(), L.n, bb_dev);
+    int hb[6];
+    ORBC_CUDA(cudaMemcpyAsync(hb, bb_dev, sizeof(hb), cudaMemcpyDeviceToHost, c->stream));
+    ORBC_CUDA(cudaStreamSynchronize(c->stream));
+    dev_free(bb_dev);
+    float lo[3], hi[3];
+    for (int d = 0; d < 6; ++d) {
+        const int k = hb[d], bits = k >= 0 ? k : k ^ 0x7fffffff;
+        float v; memcpy(&v, &bits, sizeof(v));
+        (d < 3 ? lo[d] : hi[d - 3]) = v;
+    }
+    ORBC_TRY(fit_grid_box(c, lo, hi));
+    ORBC_LAUNCH(c, k_init_centroids, blocks_for(nc, kBlock), kBlock, 0, L.X(), L.n, nc, L.n / (size_t)nc, c->centroid);
+    ORBC_LAUNCH(c, k_fill_int, blocks_for(L.n, kBlock), kBlock, 0, L.C(), L.n, -1);
+    L.has_partition = false;
+    CentroidOut out; out.world = 1;
+    for (int k = 0; k < n_iterate; ++k) {
+        // reorder_morton(centroids, param); tree.build(centroids)
+        ORBC_LAUNCH(c, k_morton_keys, blocks_for(nc, kBlock), kBlock, 0, c->centroid, nc, c->keys, c->perm);
+        ORBC_TRY(radix_sort_pairs(c, c->keys, c->perm, c->keys_tmp, c->perm_tmp, nc));
+        ORBC_LAUNCH(c, k_permute_centroids, blocks_for(nc, kBlock), kBlock, 0, c->centroid, c->perm, nc, c->centroid_tmp, c->inv);
+        std::swap(c->centroid, c->centroid_tmp);
+        if (k > 0) ORBC_LAUNCH(c, k_remap_cellid, blocks_for(L.n, kBlock), kBlock, 0, L.C(), c->d_range, c->inv);   // last round's cell = this round's search hint
+        ORBC_TRY(build_index(c));
+        // cell_list.partition(cont, *this)
+        ORBC_TRY(cell_update_assign(c, ORBC_LIPID));
+        const bool reorder = (k & (~k + 1)) == k || k == last;
+        if (reorder) {
+            ORBC_TRY(cell_update_move(c, ORBC_LIPID));            // scan, arrival lists, rank + move (reorder.h:73-149)
+            for (int r = 0; r < kMaxWorld; ++r) out.dst[r] = c->centroid;
+            ORBC_LAUNCH(c, k_centroid_update, blocks_for(nc, kBlock), kBlock, 0, L.cell_start, L.X(), 0, nc, out, (const int *)nullptr);
+        } else {
+            ORBC_TRY(scan_exclusive(c, L.cell_start, nc));
+            ORBC_LAUNCH(c, k_cell_scatter, blocks_for(L.n, kBlock), kBlock, 0, L.aff, L.li, c->d_range, L.cell_start, (const int *)nullptr, L.cells_tmp);
+            ORBC_LAUNCH(c, k_rank_only, blocks_for(L.n, kBlock), kBlock, 0, L.aff, c->d_range, L.cell_start, L.cells_tmp, L.cells);
+            for (int r = 0; r < kMaxWorld; ++r) out.dst[r] = c->centroid;
+            ORBC_LAUNCH(c, k_centroid_update, blocks_for(nc, kBlock), kBlock, 0, L.cell_start, L.X(), 0, nc, out, L.cells);
+            ORBC_CUDA(cudaMemcpyAsync(L.C(), L.aff, sizeof(int) * L.n, cudaMemcpyDeviceToDevice, c->stream));
+            L.has_partition = true;                              // (as a search hint only: the container is not sorted by cell here)
+        }
+    }
+    // the centroids moved once more after the last partition: the index follows them (the reference leaves its tree one update behind)
+    ORBC_TRY(build_index(c));
+    c->sp[1].has_partition = false;
+    ORBC_CUDA(cudaStreamSynchronize(c->stream));
+    return check_flags(c);
 }
 
 int orbc_set_field(orbc_ctx *c, int sp, char field, size_t stride, const float *src) { if (c) cudaSetDevice(c->device);

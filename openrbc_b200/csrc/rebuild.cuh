@@ -45,13 +45,14 @@ struct CentroidOut { float4 *dst[kMaxWorld]; int world; };
 
 // ---- voronoi.h:123-140 — centroid = fp32 sequential sum over the cell's slots, times 1/count --------------------------
 // cells [cb, ce) (the owned ones); the result goes to every rank's copy of the centroid array
-__global__ void k_centroid_update(const int *__restrict__ cell_start, const float4 *__restrict__ x, int cb, int ce, CentroidOut out) {
+// `map` (VoronoiDiagram::init, voronoi.h:69: the members of a cell through VCellList::cells while the container is not reordered) or null
+__global__ void k_centroid_update(const int *__restrict__ cell_start, const float4 *__restrict__ x, int cb, int ce, CentroidOut out, const int *__restrict__ map) {
     const int i = cb + blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= ce) return;
     const int b = cell_start[i], e = cell_start[i + 1];
     float cx = 0.f, cy = 0.f, cz = 0.f;
     for (int j = b; j < e; ++j) {
-        const float4 p = x[j];
+        const float4 p = x[map ? map[j] : j];
         cx = __fadd_rn(cx, p.x); cy = __fadd_rn(cy, p.y); cz = __fadd_rn(cz, p.z);
     }
     const float s = __fdiv_rn(1.0f, __int2float_rn(e - b));   // empty cell: inf -> NaN centroid, as in the reference
@@ -326,6 +327,42 @@ __global__ void k_rank_and_move(const int *__restrict__ aff, const int *__restri
     if (announce_tags) {
         const int tag = __float_as_int(nn.w);
         for (int r = 0; r < d.own.world; ++r) d.tag2idx[r][tag] = j;
+    }
+}
+
+// the sorting half of k_rank_and_move alone: cells[] = the members of every cell in ascending index (VCellList::cells after
+// partition(), voronoi.h:228-231), the container stays where it is (VoronoiDiagram::init reorders only at some iterations)
+__global__ void k_rank_only(const int *__restrict__ aff, const int *__restrict__ range, const int *__restrict__ cell_start, const int *__restrict__ cells_tmp, int *__restrict__ cells) {
+    const int i = range[0] + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= range[1]) return;
+    const int c = aff[i];
+    if (c < 0) return;
+    const int b = cell_start[c], e = cell_start[c + 1];
+    int rank = 0;
+    for (int k = b; k < e; ++k) rank += (cells_tmp[k] < i);
+    cells[b + rank] = i;
+}
+
+// VoronoiDiagram::init, voronoi.h:57-62: the initial guess is every delta-th particle, starting at delta / 2, wrapping around
+__global__ void k_init_centroids(const float4 *__restrict__ x, size_t n, int n_cells, size_t delta, float4 *__restrict__ centroid) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_cells) return;
+    const float4 p = x[(delta / 2 + (size_t)i * delta) % n];
+    centroid[i] = make_float4(p.x, p.y, p.z, 0.f);
+}
+// bounding box of the positions as order-preserving integer keys: bb[0..2] = min, bb[3..5] = max
+__device__ __forceinline__ int float_key(float f) { const int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
+__global__ void k_bbox(const float4 *__restrict__ x, size_t n, int *__restrict__ bb) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int lo[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff}, hi[3] = {(int)0x80000000, (int)0x80000000, (int)0x80000000};
+    if (i < n) {
+        const float4 p = x[i];
+        if (p.x == p.x && p.y == p.y && p.z == p.z) { lo[0] = hi[0] = float_key(p.x); lo[1] = hi[1] = float_key(p.y); lo[2] = hi[2] = float_key(p.z); }
+    }
+    #pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        const int l = __reduce_min_sync(0xffffffffu, lo[d]), h = __reduce_max_sync(0xffffffffu, hi[d]);
+        if ((threadIdx.x & 31) == 0) { atomicMin(bb + d, l); atomicMax(bb + 3 + d, h); }
     }
 }
 

@@ -29,7 +29,7 @@ EXPORTS = [
     "orbc_constrain_volume", "orbc_integrate", "orbc_nh_zeta_update", "orbc_compute_temperature", "orbc_run_langevin",
     "orbc_run_nh", "orbc_download", "orbc_size", "orbc_n_cells", "orbc_debug_dump", "orbc_debug_noise", "orbc_event_record",
     "orbc_event_elapsed_ms", "orbc_launch_count", "orbc_profile_enable", "orbc_profile_read", "orbc_set_option",
-    "orbc_set_volume_constraint", "orbc_run_minimize", "orbc_frame_bytes", "orbc_save_frame", "orbc_save_frame_begin", "orbc_save_frame_end",
+    "orbc_voronoi_init", "orbc_set_volume_constraint", "orbc_run_minimize", "orbc_frame_bytes", "orbc_save_frame", "orbc_save_frame_begin", "orbc_save_frame_end",
     "orbc_profile_kernels", "orbc_profile_kernels_report", "orbc_mg_init", "orbc_mg_blob_bytes", "orbc_mg_cell_range", "orbc_mg_export", "orbc_mg_connect", "orbc_mg_range",
 ]
 
@@ -112,6 +112,7 @@ def load_library():
         lib.orbc_destroy.restype = None
         lib.orbc_profile_kernels.argtypes = [C.c_void_p, C.c_int]
         lib.orbc_profile_kernels_report.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        lib.orbc_voronoi_init.argtypes = [C.c_void_p, C.c_int, C.c_int]
         lib.orbc_set_volume_constraint.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float]
         lib.orbc_run_minimize.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         lib.orbc_frame_bytes.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
@@ -316,6 +317,9 @@ class Simulation:
         b, e = C.c_size_t(), C.c_size_t()
         self._ck(self.lib.orbc_mg_range(self.ctx, s, C.byref(b), C.byref(e)))
         return b.value, e.value
+
+    def voronoi_init(self, n_cells, n_iterate=64):               # voronoi.init(lipid, cell_lipid, param, 64)     openrbc.cpp:71
+        self._ck(self.lib.orbc_voronoi_init(self.ctx, int(n_cells), int(n_iterate)))
 
     # ---- the reference's hot-path calls -------------------------------------------------------------------
     def voronoi_update(self):                                    # voronoi.update(lipid, cell_lipid, param)      openrbc.cpp:202

@@ -112,6 +112,31 @@ def partition(aff, n_cells):
     return cs, cells, li
 
 
+def voronoi_init(x, n_cells, n_iterate=64, others=()):
+    """Restatement of VoronoiDiagram::init (voronoi.h:54-75): initial guess = every delta-th particle from delta / 2 (wrapping),
+    then n_iterate rounds of Morton sort of the centroids, partition, centroid update through `cells`; the container (x and the
+    arrays in `others`) is reordered at the rounds k = 0, 1, 2, 4, 8, ... and once more at the end (:70,74).
+    Returns (centroids, cell_start, x, others, ties)."""
+    x = f3(x).copy()
+    others = [np.ascontiguousarray(a).copy() for a in others]
+    n = len(x)
+    delta = n // n_cells
+    idx = (delta // 2 + np.arange(n_cells, dtype=np.int64) * delta) % n
+    c = np.ascontiguousarray(x[idx])
+    ties = 0
+    for k in range(n_iterate):
+        perm, _ = morton_perm(c)
+        c = np.ascontiguousarray(c[perm])
+        aff, _, nt = assign_nearest(x, c)
+        ties += nt
+        cs, cells, _ = partition(aff, n_cells)
+        c = update_centroid(cs, np.ascontiguousarray(x[cells]))      # the sum runs over cells[j] in ascending j (:131-134)
+        if (k & (~k + 1)) == k:
+            x = np.ascontiguousarray(x[cells]); others = [np.ascontiguousarray(a[cells]) for a in others]
+    x = np.ascontiguousarray(x[cells]); others = [np.ascontiguousarray(a[cells]) for a in others]
+    return c, cs, x, others, ties
+
+
 def stencil(centroids, cell, rmax, cap=4096):
     c = f3(centroids)
     out = np.empty(cap, np.int32)

@@ -57,11 +57,25 @@ def chain(r, name):
     print(name, os.path.getsize(path) // 1024, "KiB")
 
 
+def init_chain(name, radius, n_iter):
+    """VoronoiDiagram::init (voronoi.h:54-75) on a random lipid sphere: the container before, the Voronoi state and the container after."""
+    r = refmod.Ref("strict", threads=1, args=["-i", "lipid"])
+    r.init_lipid_sphere(radius)
+    g = {"x0": r.get(0, "x"), "n0": r.get(0, "n"), "n_iter": np.int32(n_iter)}
+    g["n_cells"] = np.int32(r.voronoi_init(n_iter))
+    g["centroids"] = r.centroids(); g["cs_l"] = r.cell_array(0, "cell_start"); g["x"] = r.get(0, "x"); g["n"] = r.get(0, "n")
+    path = os.path.join(OUT, "init_" + name + ".npz")
+    np.savez_compressed(path, **g)
+    print(name, len(g["x0"]), "lipids", int(g["n_cells"]), "cells", os.path.getsize(path) // 1024, "KiB")
+
+
 if __name__ == "__main__":
     # one process per chain: constrain_volume's scratch is a function-static that would carry over from one world to the next
     import subprocess
-    if len(sys.argv) > 1:
+    if len(sys.argv) > 1 and sys.argv[1].startswith("init_"):
+        init_chain(sys.argv[1][5:], {"sphere_r12": 12.0, "sphere_r16": 16.0}[sys.argv[1][5:]], {"sphere_r12": 64, "sphere_r16": 11}[sys.argv[1][5:]])
+    elif len(sys.argv) > 1:
         chain({"vesicle_ico0": lambda: ref_vesicle(0), "sphere_r12": lambda: ref_sphere(12.0)}[sys.argv[1]](), sys.argv[1])
     else:
-        for name in ("vesicle_ico0", "sphere_r12"):
+        for name in ("vesicle_ico0", "sphere_r12", "init_sphere_r12", "init_sphere_r16"):
             subprocess.check_call([sys.executable, os.path.abspath(__file__), name])

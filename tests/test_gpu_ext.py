@@ -103,3 +103,29 @@ def test_volume_constraint_inside_run_langevin():
         assert rel_err(da["v"], dc["v"]) > 1e-6            # and the constraint does act
     for sim in (a, b, c):
         sim.close()
+
+
+@pytest.mark.parametrize("name", ["sphere_r12", "sphere_r16"])
+def test_voronoi_init(name):
+    """orbc_voronoi_init == VoronoiDiagram::init of the reference (voronoi.h:54-75): centroids, cell_start and the storage order
+    of the container, bit for bit (the summation order of every centroid update is the reference's)."""
+    from openrbc_b200 import Simulation
+    g = dict(np.load(os.path.join(GOLDEN, "init_" + name + ".npz")))
+    n = len(g["x0"])
+    z = np.zeros((n, 3), np.float32)
+    e = np.zeros((0, 3), np.float32)
+    st = dict(lx=g["x0"], lv=z, ln=g["n0"], lo=z, px=e, pv=e, pn=e, po=e, ptype=np.zeros(0, np.int32), ptag=np.zeros(0, np.int32), bonds=np.zeros((0, 3), np.int32))
+    sim = Simulation(st, kBT=0.0)
+    sim.voronoi_init(int(g["n_cells"]), int(g["n_iter"]))
+    np.testing.assert_array_equal(sim.dump("centroids"), g["centroids"])
+    np.testing.assert_array_equal(sim.dump("cell_start_l"), g["cs_l"])
+    d = sim.download(0, "xn", affiliation=True)
+    np.testing.assert_array_equal(d["x"], g["x"])
+    np.testing.assert_array_equal(d["n"], g["n"])
+    np.testing.assert_array_equal(d["affiliation"], np.repeat(np.arange(len(g["cs_l"]) - 1), np.diff(g["cs_l"])))
+    # the state is ready for the loop: forces can be computed straight away
+    sim.compute_pairwise_fused()
+    assert np.isfinite(sim.get(0, "f")).all()
+    with pytest.raises(Exception):
+        sim.voronoi_init(int(g["n_cells"]), 5)             # n_iterate - 1 a power of two: the reference's double reorder
+    sim.close()

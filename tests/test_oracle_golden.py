@@ -148,3 +148,15 @@ def test_minimisation_loop_golden(name):
         for f in "xn":
             assert rel_err(getattr(w, p + f), g[f"opt_{p}{f}"]) < 1e-6, (p, f)
         assert rel_err(getattr(w, p + "f"), g[f"opt_{p}f"]) < 2e-5
+
+
+@pytest.mark.parametrize("name", ["sphere_r12", "sphere_r16"])
+def test_voronoi_init_golden(name):
+    """VoronoiDiagram::init (voronoi.h:54-75) restated == the reference's own result, bit for bit."""
+    g = dict(np.load(os.path.join(GOLDEN, "init_" + name + ".npz")))
+    c, cs, x, (n,), ties = port.voronoi_init(g["x0"], int(g["n_cells"]), int(g["n_iter"]), others=(g["n0"],))
+    assert ties == 0
+    np.testing.assert_array_equal(c, g["centroids"])
+    np.testing.assert_array_equal(cs, g["cs_l"])
+    np.testing.assert_array_equal(x, g["x"])
+    np.testing.assert_array_equal(n, g["n"])

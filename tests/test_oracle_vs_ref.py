@@ -236,3 +236,18 @@ def test_constrain_volume():
     assert np.isfinite(vol)
     assert rel_err(w.lf, r.get(0, "f")) < 1e-5
     assert rel_err(w.pf, r.get(1, "f")) < 1e-5
+
+
+@pytest.mark.parametrize("radius,n_iter", [(20.0, 64), (14.0, 6)])
+def test_voronoi_init(radius, n_iter):
+    """VoronoiDiagram::init (voronoi.h:54-75) restated: same centroids, same partition, same storage order, bit for bit."""
+    r = refmod.Ref("strict", threads=1, args=["-i", "lipid"])
+    r.init_lipid_sphere(radius)
+    x0, n0 = r.get(0, "x"), r.get(0, "n")
+    nc = r.voronoi_init(n_iter)
+    c, cs, x, (n,), ties = port.voronoi_init(x0, nc, n_iter, others=(n0,))
+    if ties == 0:
+        np.testing.assert_array_equal(c, r.centroids())
+        np.testing.assert_array_equal(cs, r.cell_array(0, "cell_start"))
+        np.testing.assert_array_equal(x, r.get(0, "x"))
+        np.testing.assert_array_equal(n, r.get(0, "n"))
