@@ -367,7 +367,7 @@ def run_ours(args):
     t_up = time.perf_counter()
     trace = bool(os.environ.get("ORBC_BENCH_TRACE"))
     if trace:
-        print(f"[bench rank {rank}] e2e upload {(t_up0 - t_wall) * 1e3:.1f} ms + export {(t_up - t_up0) * 1e3:.1f} ms", file=sys.stderr, flush=True)
+        print(f"[bench rank {rank}] e2e upload {(t_up0 - t_wall) * 1e3:.1f} ms {e2e_sim.last_upload_ms} (lipids, proteins, bonds, voronoi) + export {(t_up - t_up0) * 1e3:.1f} ms", file=sys.stderr, flush=True)
     slow = []                            # (ms, what) of the slowest host-side calls, for the phase breakdown
     h2d = sum(host[k].nbytes for k in ("lx", "lv", "ln", "lo", "px", "pv", "pn", "po", "ptype", "ptag", "bonds", "centroids", "cs_l", "cs_p"))
     d2h = 0

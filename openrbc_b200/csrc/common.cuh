@@ -141,7 +141,7 @@ struct orbc_ctx {
     unsigned type_mask = 0;                       // protein types present (bit t), from the last protein upload
     // bonds
     size_t n_bonds = 0;
-    int *bonds = nullptr;                         // (type, tag_i, tag_j)
+    int *bonds = nullptr; size_t bonds_cap = 0;   // (type, tag_i, tag_j)
     int *tag2idx = nullptr; size_t tag2idx_size = 0;
     // scratch
     int *scan_tmp = nullptr; size_t scan_tmp_cap = 0; unsigned scan_epoch = 0;   // tile descriptors of the single-pass scan

@@ -726,7 +726,7 @@ int orbc_upload_bonds(orbc_ctx *c, size_t n_bonds, const int *tij) { if (c) cuda
         if ((size_t)tij[3 * b + 1] >= c->tag2idx_size || (size_t)tij[3 * b + 2] >= c->tag2idx_size || tij[3 * b + 1] < 0 || tij[3 * b + 2] < 0)
             return fail(ORBC_ERR_ARG, "bond %zu refers to a tag that no uploaded protein carries (upload proteins first)", b);
     }
-    ORBC_TRY(dev_alloc(&c->bonds, 3 * n_bonds));
+    if (!c->bonds || c->bonds_cap < 3 * n_bonds) { ORBC_TRY(dev_alloc(&c->bonds, 3 * n_bonds)); c->bonds_cap = 3 * n_bonds; }   // a re-upload keeps the allocation
     if (n_bonds) ORBC_CUDA(cudaMemcpyAsync(c->bonds, tij, sizeof(int) * 3 * n_bonds, cudaMemcpyHostToDevice, c->stream));
     ORBC_CUDA(cudaStreamSynchronize(c->stream));
     c->n_bonds = n_bonds;

@@ -206,19 +206,23 @@ class Simulation:
 
     # ---- upload / download ------------------------------------------------------------------------------
     def upload(self, st):
+        import time
+        t = [time.perf_counter()]
         lx, lv, ln, lo = (_f3(st["l" + f]) for f in "xvno")
-        self._ck(self.lib.orbc_upload(self.ctx, LIPID, len(lx), 3, _p(lx), _p(lv), _p(ln), _p(lo), None, None))
+        self._ck(self.lib.orbc_upload(self.ctx, LIPID, len(lx), 3, _p(lx), _p(lv), _p(ln), _p(lo), None, None)); t.append(time.perf_counter())
         px, pv, pn, po = (_f3(st["p" + f]) for f in "xvno")
         ty = np.ascontiguousarray(st["ptype"], np.int32)
         tg = np.ascontiguousarray(st["ptag"], np.int32)
-        self._ck(self.lib.orbc_upload(self.ctx, PROTEIN, len(px), 3, _p(px), _p(pv), _p(pn), _p(po), _p(ty), _p(tg)))
+        self._ck(self.lib.orbc_upload(self.ctx, PROTEIN, len(px), 3, _p(px), _p(pv), _p(pn), _p(po), _p(ty), _p(tg))); t.append(time.perf_counter())
         bd = np.ascontiguousarray(st["bonds"], np.int32).reshape(-1, 3)
-        self._ck(self.lib.orbc_upload_bonds(self.ctx, len(bd), _p(bd)))
+        self._ck(self.lib.orbc_upload_bonds(self.ctx, len(bd), _p(bd))); t.append(time.perf_counter())
         if "centroids" in st:
             c = _f3(st["centroids"])
             csl = np.ascontiguousarray(st["cs_l"], np.int32)
             csp = np.ascontiguousarray(st["cs_p"], np.int32)
-            self._ck(self.lib.orbc_voronoi_upload(self.ctx, len(c), _p(c), _p(csl), _p(csp)))
+            self._ck(self.lib.orbc_voronoi_upload(self.ctx, len(c), _p(c), _p(csl), _p(csp))); t.append(time.perf_counter())
+        # wall time of the four calls (lipids, proteins, bonds, Voronoi state), for the phase breakdown of bench.py
+        self.last_upload_ms = [round((b - a) * 1e3, 2) for a, b in zip(t[:-1], t[1:])]
 
     def size(self, s):
         n = C.c_size_t()

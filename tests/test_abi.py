@@ -31,7 +31,8 @@ def test_header_and_library_agree(lib):
 def test_every_entry_point_cites_the_reference():
     header = open(os.path.join(ROOT, "include", "orbc_b200.h")).read()
     for needle in ("compute_pairwise_fused.h:238-320", "compute_bonded.h:89-146", "integrate_nh.h:29-37", "voronoi.h:77-86",
-                   "voronoi.h:153-163", "cleanup.h:29-91", "compute_temperature.h:23-29", "constrain_volume.h:26-83", "trajectory.h:61-105"):
+                   "voronoi.h:153-163", "cleanup.h:29-91", "compute_temperature.h:23-29", "constrain_volume.h:26-83", "trajectory.h:61-105",
+                   "voronoi.h:54-75", "openrbc.cpp:88-133", "openrbc.cpp:229", "openrbc.cpp:189-256", "integrate_langevin.h:99-149"):
         assert needle in header, needle
 
 
