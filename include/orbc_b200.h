@@ -141,6 +141,8 @@ ORBC_API int  orbc_set_volume_constraint(orbc_ctx *ctx, int on, float target_vol
  * of their destructors (integrate_nh.h:181-185) stays on the host, see orbc_nh_zeta_update(). */
 ORBC_API int  orbc_integrate(orbc_ctx *ctx, int kernel, const orbc_step_params *p, orbc_step_result *res);
 ORBC_API float orbc_nh_zeta_update(float zeta, float *Q, double dt, float kBT, double ke, long n);
+/* same for the unfused verlet_nh_update (integrate_nh.h:72-76), whose target kinetic energy 1.5 n kBT is a product of floats */
+ORBC_API float orbc_nh_zeta_update_unfused(float zeta, float *Q, double dt, float kBT, double ke, long n);
 ORBC_API int  orbc_compute_temperature(orbc_ctx *ctx, double *temperature);   /* compute_temperature.h:23-29 */
 
 /* ---- whole-loop entry points (what the GPU build of openrbc.cpp's while-loop calls; openrbc.cpp:189-256) ------- */

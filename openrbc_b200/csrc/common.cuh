@@ -156,6 +156,7 @@ struct orbc_ctx {
     cudaEvent_t ev[16] = {};
     unsigned long long launches = 0;
     bool ff_set = false;
+    orbc_forcefield host_ff;                       // host copy of this context's force field (Langevin coefficients, cull radii)
     int pair_impl = 2;
     int ll_variant = 5;                            // bit 2: run-list kernel k_pair_ll_r; bit 1: sphere cull; bit 0: 20 resident blocks per SM
     int prot_lanes = 0;                            // lanes per protein in k_pair_prot (0 = by the number of owned proteins)

@@ -110,8 +110,8 @@ int ensure_stage(orbc_ctx *c, size_t floats) {
 }
 
 int alloc_species(orbc_ctx *c, Species &s, size_t n) {
-    if (n > s.cap) {
-        const size_t cap = n + 64;
+    if (n + 64 > s.cap) {                                        // the pair kernels read up to 3 elements past a cell's last slot: keep 64 spare
+        const size_t cap = n + 64 + n / 16;
         for (int b = 0; b < 2; ++b) {
             ORBC_TRY(dev_alloc(&s.x[b], cap)); ORBC_TRY(dev_alloc(&s.nn[b], cap)); ORBC_TRY(dev_alloc(&s.v[b], cap)); ORBC_TRY(dev_alloc(&s.o[b], cap));
             ORBC_TRY(dev_alloc(&s.cellid[b], cap));
@@ -237,12 +237,11 @@ void fill_integ(IntegArgs &a, orbc_ctx *c, int sp, const orbc_step_params *p) {
     }
 }
 
-orbc_forcefield g_host_ff;   // host copy of the table last installed (radius feeds the Langevin coefficients)
 
 // integrate_langevin.h:110-114: gamma = 6 pi eta R (fp64 -> fp32), sigma = sqrtf(2 kBT gamma) * sqrt(3 / dt)
-void langevin_coeffs(IntegArgs &a, const orbc_step_params *p) {
+void langevin_coeffs(const orbc_ctx *c, IntegArgs &a, const orbc_step_params *p) {
     for (int i = 0; i < kNType; ++i) {
-        a.gamma[i] = (float)(6.0 * M_PI * p->eta * g_host_ff.radius[i]);
+        a.gamma[i] = (float)(6.0 * M_PI * p->eta * c->host_ff.radius[i]);
         a.sigma[i] = (float)(std::sqrt((float)(2 * p->kBT * a.gamma[i])) * std::sqrt(3.0 / p->dt));
     }
 }
@@ -251,9 +250,9 @@ void langevin_coeffs(IntegArgs &a, const orbc_step_params *p) {
 CullTable cull_table(const orbc_ctx *c) {
     CullTable ct;
     for (int t = 0; t < kNType; ++t) {
-        ct.cut_l[t] = std::sqrt(std::max(g_host_ff.cutsqlp[t], g_host_ff.lj_cutsq[t]));
+        ct.cut_l[t] = std::sqrt(std::max(c->host_ff.cutsqlp[t], c->host_ff.lj_cutsq[t]));
         float m = 0.f;
-        for (int u = 0; u < kNType; ++u) if (c->type_mask >> u & 1) m = std::max(m, std::max(g_host_ff.cutsqpp[t + kNType * u], g_host_ff.lj_cutsq[t + kNType * u]));
+        for (int u = 0; u < kNType; ++u) if (c->type_mask >> u & 1) m = std::max(m, std::max(c->host_ff.cutsqpp[t + kNType * u], c->host_ff.lj_cutsq[t + kNType * u]));
         ct.cut_p[t] = std::sqrt(m);
     }
     return ct;
@@ -467,7 +466,7 @@ int do_integrate_langevin(orbc_ctx *c, const orbc_step_params *p, bool rebuild_f
         for (int sp = 0; sp < 2; ++sp) {
             Species &S = c->sp[sp];
             if (!S.n) continue;
-            IntegArgs a; fill_integ(a, c, sp, p); langevin_coeffs(a, p);
+            IntegArgs a; fill_integ(a, c, sp, p); langevin_coeffs(c, a, p);
             a.clear = clear ? 1 : 0;
             const float *hn = sp == 0 ? p->noise_lipid : p->noise_protein;
             if (hn) {
@@ -594,7 +593,7 @@ int orbc_set_forcefield(orbc_ctx *c, const orbc_forcefield *ff) { if (c) cudaSet
     if (!c || !ff) return fail(ORBC_ERR_ARG, "null argument");
     ORBC_CUDA(cudaMemcpyToSymbolAsync(c_ff, ff, sizeof(*ff), 0, cudaMemcpyHostToDevice, c->stream));
     ORBC_CUDA(cudaStreamSynchronize(c->stream));
-    g_host_ff = *ff;
+    c->host_ff = *ff;
     c->ff_set = true;
     c->porder_valid = false;
     return ORBC_OK;
@@ -935,6 +934,15 @@ float orbc_nh_zeta_update(float zeta, float *Q, double dt, float kBT, double ke,
     return zeta;
 }
 
+float orbc_nh_zeta_update_unfused(float zeta, float *Q, double dt, float kBT, double ke, long n) {
+    // destructor of the unfused verlet_nh_update (integrate_nh.h:72-76): the target kinetic energy is a product of floats there
+    // (constant::onehalf * n * parameter.kBT with real kBT), not the fused kernels' double expression
+    if (!*Q) *Q = (float)(n * 0.01);
+    const float target = 1.5f * (float)n * kBT;
+    zeta += 0.5f * dt / *Q * (ke - target);
+    return zeta;
+}
+
 int orbc_integrate(orbc_ctx *c, int kernel, const orbc_step_params *p, orbc_step_result *res) { if (c) cudaSetDevice(c->device);
     if (!c) return fail(ORBC_ERR_ARG, "null ctx");
     const bool needs_p = kernel != ORBC_CLEAR_FORCE && kernel != ORBC_POST_TORQUE;
@@ -951,7 +959,8 @@ int orbc_integrate(orbc_ctx *c, int kernel, const orbc_step_params *p, orbc_step
         IntegArgs a;
         if (p) fill_integ(a, c, sp, p);
         switch (kernel) {
-        case ORBC_CLEAR_FORCE: ORBC_LAUNCH(c, k_clear_force, nb, 256, 0, S.f, S.t, S.n); break;
+        // the whole array, not the owned range: slots a rank stops owning must not keep stale sums for the accumulating force kernels
+        case ORBC_CLEAR_FORCE: ORBC_LAUNCH(c, k_clear_force, blocks_for(S.n, 256), 256, 0, S.f, S.t, S.n); break;
         case ORBC_POST_TORQUE: ORBC_LAUNCH(c, k_post_torque, nb, 256, 0, S.N(), S.t, S.n); break;
         case ORBC_BOUNCE_BACK: ORBC_LAUNCH(c, k_bounce_back, nb, 256, 0, a); break;
         case ORBC_NH_INITIAL_FUSED: ORBC_LAUNCH(c, k_nh_initial_fused, nb, 256, 0, a); if (mg_active(c)) S.cur_xn ^= 1; break;

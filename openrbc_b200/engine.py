@@ -26,7 +26,7 @@ EXPORTS = [
     "orbc_create", "orbc_destroy", "orbc_last_error", "orbc_synchronize", "orbc_set_stream", "orbc_forcefield_canonical",
     "orbc_set_forcefield", "orbc_upload", "orbc_upload_bonds", "orbc_voronoi_upload", "orbc_set_field", "orbc_voronoi_update",
     "orbc_cell_update", "orbc_rebuild", "orbc_delete_lipid", "orbc_compute_pairwise_fused", "orbc_compute_bonded",
-    "orbc_constrain_volume", "orbc_integrate", "orbc_nh_zeta_update", "orbc_compute_temperature", "orbc_run_langevin",
+    "orbc_constrain_volume", "orbc_integrate", "orbc_nh_zeta_update", "orbc_nh_zeta_update_unfused", "orbc_compute_temperature", "orbc_run_langevin",
     "orbc_run_nh", "orbc_download", "orbc_size", "orbc_n_cells", "orbc_debug_dump", "orbc_debug_noise", "orbc_event_record",
     "orbc_event_elapsed_ms", "orbc_launch_count", "orbc_profile_enable", "orbc_profile_read", "orbc_set_option",
     "orbc_voronoi_init", "orbc_set_volume_constraint", "orbc_run_minimize", "orbc_frame_bytes", "orbc_save_frame", "orbc_save_frame_begin", "orbc_save_frame_end",
@@ -83,6 +83,8 @@ def load_library():
         lib.orbc_last_error.restype = C.c_char_p
         lib.orbc_nh_zeta_update.restype = C.c_float
         lib.orbc_nh_zeta_update.argtypes = [C.c_float, C.POINTER(C.c_float), C.c_double, C.c_float, C.c_double, C.c_long]
+        lib.orbc_nh_zeta_update_unfused.restype = C.c_float
+        lib.orbc_nh_zeta_update_unfused.argtypes = [C.c_float, C.POINTER(C.c_float), C.c_double, C.c_float, C.c_double, C.c_long]
         lib.orbc_constrain_volume.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_void_p]
         lib.orbc_delete_lipid.argtypes = [C.c_void_p, C.c_float, C.c_void_p]
         lib.orbc_debug_noise.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_size_t, C.c_void_p]
@@ -371,6 +373,15 @@ class Simulation:
     def nh_final_fused(self):                                    # :236
         res = self.integrate(NH_FINAL_FUSED, want_result=True)
         self._zeta(res)
+        return res.ke
+
+    def nh_final(self):                                          # verlet_nh_final (unfused), integrate_nh.h:155-176
+        self.integrate(NH_FINAL)
+
+    def nh_update(self):                                         # verlet_nh_update + its destructor, integrate_nh.h:66-94
+        res = self.integrate(NH_UPDATE, want_result=True)
+        self.last_ke = res.ke
+        self.zeta = self.lib.orbc_nh_zeta_update_unfused(self.zeta, C.byref(self.Q), self.dt, self.kBT, res.ke, res.n)
         return res.ke
 
     def opt_move(self):                                          # :114-131

@@ -109,8 +109,10 @@ int main( int argc, char ** argv ) {
     // ---- main loop (openrbc.cpp:151-256) --------------------------------------------------------------------------------
     std::cout << "Run ... " << std::endl;
     Service<Timers>::call()["+main-loop"].start();
-    // Maxwell velocities from the reference's generator (assign_temperature.h:26-44), drawn on the host for the particles in
-    // their uploaded order and carried along by the rebuild (the reference draws them after its rebuild: same law)
+    // Maxwell velocities from the reference's generator (assign_temperature.h:26-44), drawn on the host.  The minimisation has
+    // reordered the device's containers at every rebuild, and the velocity spread depends on mass[type]: bring the host's type /
+    // tag arrays into the device's current slot order first, so that slot i receives a velocity drawn for ITS type
+    dev.download_ids( protein );
     integrate( assign_temperature( param ), lipid, protein );
     dev.upload_velocities( lipid, protein );
     rebuild();

@@ -60,6 +60,12 @@ struct Device {
         check( orbc_voronoi_upload( ctx, voronoi.n_cells, (const float *) voronoi.centroids.data(), cell_lipid.cell_start.data(),
                                     protein.size() ? cell_protein.cell_start.data() : nullptr ), "orbc_voronoi_upload" );
     }
+    // type and tag of every protein slot in the device's CURRENT storage order (every rebuild reorders the containers): needed
+    // before any host-side per-particle work that depends on the type, e.g. assign_temperature's sigma ~ 1 / sqrt(mass[type])
+    void download_ids( ProteContainer & protein ) {
+        if ( protein.size() ) check( orbc_download( ctx, ORBC_PROTEIN, vect_floats, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                                    protein.type.data(), protein.tag.data(), nullptr ), "orbc_download(protein ids)" );
+    }
     void upload_velocities( LipidContainer const & lipid, ProteContainer const & protein ) {
         if ( lipid.size() ) check( orbc_set_field( ctx, ORBC_LIPID, 'v', vect_floats, (const float *) lipid.v.data() ), "orbc_set_field" );
         if ( protein.size() ) check( orbc_set_field( ctx, ORBC_PROTEIN, 'v', vect_floats, (const float *) protein.v.data() ), "orbc_set_field" );
@@ -150,7 +156,8 @@ inline void integrate_id( Device & dev, int kernel, const char * name, RTParamet
     check( orbc_integrate( dev.ctx, kernel, param ? &p : nullptr, reduces ? &res : nullptr ), name );
     if ( reduces ) {
         float Q = param->Q;
-        param->zeta = orbc_nh_zeta_update( param->zeta, &Q, param->dt, param->kBT, res.ke, res.n );
+        param->zeta = kernel == ORBC_NH_UPDATE ? orbc_nh_zeta_update_unfused( param->zeta, &Q, param->dt, param->kBT, res.ke, res.n )
+                                               : orbc_nh_zeta_update( param->zeta, &Q, param->dt, param->kBT, res.ke, res.n );
         param->Q = Q;
     }
 }
@@ -164,6 +171,7 @@ struct verlet_langevin { RTParameter & parameter; explicit verlet_langevin( RTPa
 struct verlet_initial_bounce_clearforce_update { RTParameter & parameter; explicit verlet_initial_bounce_clearforce_update( RTParameter & p ) : parameter( p ) {} };
 struct post_toque_final_update { RTParameter & parameter; explicit post_toque_final_update( RTParameter & p ) : parameter( p ) {} };
 struct verlet_nh_final { RTParameter & parameter; explicit verlet_nh_final( RTParameter & p ) : parameter( p ) {} };
+struct verlet_nh_update { RTParameter & parameter; explicit verlet_nh_update( RTParameter & p ) : parameter( p ) {} };
 
 inline void integrate( Device & dev, clear_force const & ) { integrate_id( dev, ORBC_CLEAR_FORCE, "clear_force", nullptr ); }
 inline void integrate( Device & dev, post_torque const & ) { integrate_id( dev, ORBC_POST_TORQUE, "post_torque", nullptr ); }
@@ -172,6 +180,7 @@ inline void integrate( Device & dev, verlet_langevin const & k ) { integrate_id(
 inline void integrate( Device & dev, verlet_initial_bounce_clearforce_update const & k ) { integrate_id( dev, ORBC_NH_INITIAL_FUSED, "verlet_initial_bounce_clearforce", &k.parameter ); }
 inline void integrate( Device & dev, post_toque_final_update const & k ) { integrate_id( dev, ORBC_NH_FINAL_FUSED, "post_toque_final_update", &k.parameter ); }
 inline void integrate( Device & dev, verlet_nh_final const & k ) { integrate_id( dev, ORBC_NH_FINAL, "verlet_nh_final", &k.parameter ); }
+inline void integrate( Device & dev, verlet_nh_update const & k ) { integrate_id( dev, ORBC_NH_UPDATE, "verlet_nh_update", &k.parameter ); }
 // the minimiser's capped steepest-descent move (openrbc.cpp:114-131), a plain loop in the reference
 inline void opt_move( Device & dev, RTParameter & param ) { integrate_id( dev, ORBC_OPT_MOVE, "OptIntegration", &param ); }
 

@@ -561,11 +561,43 @@ void orc_nh_final_fused(const orc_forcefield *ff, long n, float *v, const float 
     *ke += ke_local;
 }
 
+/* verlet_nh_final, integrate_nh.h:155-176 (the unfused second half-kick; post_torque has run before it) */
+void orc_nh_final(const orc_forcefield *ff, long n, float *v, const float *f, float *o, const float *t, const int *type, double dt_, float zeta)
+{
+    const float dt = (float)dt_;
+    const float inertia = 1.0f;
+    for (long i = 0; i < n; ++i) {
+        float *V = v + 3 * i, *O = o + 3 * i;
+        const float *F = f + 3 * i, *T = t + 3 * i;
+        const int ty = type ? type[i] : 0;
+        for (int d = 0; d < 3; ++d) V[d] += 0.5f * (F[d] / ff->mass[ty] - zeta * V[d]) * dt;
+        for (int d = 0; d < 3; ++d) O[d] += 0.5f * T[d] / inertia * dt;
+    }
+}
+
+/* verlet_nh_update::operator(), integrate_nh.h:78-89: the kinetic energy of one container (its destructor is orc_nh_zeta_update) */
+void orc_nh_update(const orc_forcefield *ff, long n, const float *v, const int *type, double *ke)
+{
+    double ke_local = 0;
+    for (long i = 0; i < n; ++i) ke_local += 0.5f * ff->mass[type ? type[i] : 0] * normsq3(v + 3 * i);
+    *ke += ke_local;
+}
+
 /* destructor of the fused NH kernels, integrate_nh.h:181-185 / 240-244; Q defaults to 0.01 n (runtime_parameter.h:76) */
 float orc_nh_zeta_update(float zeta, float *Q, double dt, float kBT, double ke, int n)
 {
     if (!*Q) *Q = (float)(n * 0.01);
     zeta += 0.5 * dt / *Q * (ke - 0.5 * 3.0 * n * kBT);
+    return zeta;
+}
+
+/* destructor of the UNFUSED verlet_nh_update, integrate_nh.h:72-76: `constant::onehalf * n * parameter.kBT` is a product of
+ * floats there (real kBT, runtime_parameter.h:49), where the fused kernels spell 0.5 * 3.0 * n * kBT in double */
+float orc_nh_zeta_update_unfused(float zeta, float *Q, double dt, float kBT, double ke, int n)
+{
+    if (!*Q) *Q = (float)(n * 0.01);
+    const float target = 1.5f * n * kBT;
+    zeta += 0.5f * dt / *Q * (ke - target);
     return zeta;
 }
 

@@ -65,6 +65,9 @@ void orc_nh_initial_fused(const orc_forcefield *ff, long n, float *x, float *v, 
                           const int *type, double dt, float zeta, double lo, double hi, double *ke); /* integrate_nh.h:178-235 */
 void orc_nh_final_fused(const orc_forcefield *ff, long n, float *v, const float *f, const float *nn, float *o, float *t,
                         const int *type, double dt, float zeta, double *ke);                         /* :237-273 */
+void orc_nh_final(const orc_forcefield *ff, long n, float *v, const float *f, float *o, const float *t, const int *type, double dt, float zeta); /* :155-176 */
+void orc_nh_update(const orc_forcefield *ff, long n, const float *v, const int *type, double *ke);  /* :78-89 */
+float orc_nh_zeta_update_unfused(float zeta, float *Q, double dt, float kBT, double ke, int n);      /* :72-76 */
 float orc_nh_zeta_update(float zeta, float *Q, double dt, float kBT, double ke, int n);              /* :72-76,181-185 */
 void orc_opt_move(const orc_forcefield *ff, long n, float *x, float *nn, const float *f, const float *t, const int *type,
                   double dt, double dr_opt, double dn_opt);                                          /* openrbc.cpp:114-131 */

@@ -49,6 +49,7 @@ def lib():
         L.orc_constrain_volume.restype = C.c_float
         L.orc_delete_lipid_mask.restype = C.c_long
         L.orc_nh_zeta_update.restype = C.c_float
+        L.orc_nh_zeta_update_unfused.restype = C.c_float
         L.orc_mt_uint.restype = C.c_uint32
         L.orc_mt_u01.restype = C.c_float
         L.orc_uint2u11.restype = C.c_float
@@ -192,6 +193,7 @@ class World:
         self.n_cells = len(self.centroids)
         self.dt, self.kBT, self.eta = dt, kBT, eta
         self.zeta, self.Q = 0.0, C.c_float(0.0)
+        self.box = (BOX_LO, BOX_HI)
         self.nstep = 0
         self.freq_sort_ctrd = 24
         self.cell_normal = np.zeros((self.n_cells, 3), np.float32)
@@ -253,7 +255,7 @@ class World:
 
     def bounce_back(self):
         for x, v, f, n, o, t, ty in self._each():
-            lib().orc_bounce_back(C.c_long(len(x)), _p(x), _p(v), C.c_double(BOX_LO), C.c_double(BOX_HI))
+            lib().orc_bounce_back(C.c_long(len(x)), _p(x), _p(v), C.c_double(self.box[0]), C.c_double(self.box[1]))
 
     def verlet_langevin(self, noise_l=None, noise_p=None):
         for (x, v, f, n, o, t, ty), nz in zip(self._each(), (noise_l, noise_p)):
@@ -265,7 +267,7 @@ class World:
         ke = C.c_double(0.0); n = 0
         for x, v, f, nn, o, t, ty in self._each():
             lib().orc_nh_initial_fused(C.byref(self.ff), C.c_long(len(x)), _p(x), _p(v), _p(f), _p(nn), _p(o), _p(t), _p(ty),
-                                       C.c_double(self.dt), C.c_float(self.zeta), C.c_double(BOX_LO), C.c_double(BOX_HI), C.byref(ke))
+                                       C.c_double(self.dt), C.c_float(self.zeta), C.c_double(self.box[0]), C.c_double(self.box[1]), C.byref(ke))
             n += len(x)
         self.last_ke = ke.value
         self.zeta = lib().orc_nh_zeta_update(C.c_float(self.zeta), C.byref(self.Q), C.c_double(self.dt), C.c_float(self.kBT), ke, n)
@@ -279,6 +281,19 @@ class World:
             n += len(x)
         self.last_ke = ke.value
         self.zeta = lib().orc_nh_zeta_update(C.c_float(self.zeta), C.byref(self.Q), C.c_double(self.dt), C.c_float(self.kBT), ke, n)
+        return ke.value
+
+    def nh_final(self):                                          # verlet_nh_final (unfused), integrate_nh.h:155-176
+        for x, v, f, nn, o, t, ty in self._each():
+            lib().orc_nh_final(C.byref(self.ff), C.c_long(len(x)), _p(v), _p(f), _p(o), _p(t), _p(ty), C.c_double(self.dt), C.c_float(self.zeta))
+
+    def nh_update(self):                                         # verlet_nh_update + its destructor, integrate_nh.h:66-94
+        ke = C.c_double(0.0); n = 0
+        for x, v, f, nn, o, t, ty in self._each():
+            lib().orc_nh_update(C.byref(self.ff), C.c_long(len(x)), _p(v), _p(ty), C.byref(ke))
+            n += len(x)
+        self.last_ke = ke.value
+        self.zeta = lib().orc_nh_zeta_update_unfused(C.c_float(self.zeta), C.byref(self.Q), C.c_double(self.dt), C.c_float(self.kBT), ke, n)
         return ke.value
 
     def opt_move(self, dr_opt=5e-2, dn_opt=5e-2):

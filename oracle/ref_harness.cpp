@@ -145,6 +145,9 @@ int ref_set_param( const char * name, double v ) {
     else if ( n == "dn_opt" ) p.dn_opt = v;
     else if ( n == "rho" ) p.rho = v;
     else if ( n == "voronoi_cell_size" ) p.voronoi_cell_size = (int)v;
+    // the reflecting walls (runtime_parameter.h:45,111-115); bsize (the Morton quantisation) is left alone
+    else if ( n == "box_lo" ) { for ( int d = 0; d < 3; ++d ) p.box[d][0] = v; }
+    else if ( n == "box_hi" ) { for ( int d = 0; d < 3; ++d ) p.box[d][1] = v; }
     else return -1;
     return 0;
 }
