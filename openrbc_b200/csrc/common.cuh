@@ -131,10 +131,9 @@ struct orbc_ctx {
     bool stencil_valid = false;
     float4 *cell_normal = nullptr;                // constrain_volume's persistent scratch
     float4 *lbound = nullptr, *pbound = nullptr;  // per-cell bounding spheres of the current lipids / proteins (pair_queue.cuh)
-    uint4 *rel16 = nullptr; size_t rel16_cap = 0;  // half-precision cell-relative lipid positions, two per record (k_pair_ll_h)
-    int *rel_flag = nullptr;                      // raised by k_cell_bounds when a lipid does not fit the half-precision prefilter
-    int ll_half = 0;                              // experimental packed-half prefilter kernel k_pair_ll_h (0 off; 1, 2 = register targets)
-    int2 *lruns = nullptr; int *lrun_cnt = nullptr; size_t lruns_cells = 0;   // merged candidate runs of every cell's r<6 stencil (k_lipid_runs)
+    int2 *lruns = nullptr; int *lrun_cnt = nullptr; size_t lruns_cells = 0;   // merged candidate runs of every cell's r<6 stencil + packed per-cell info (k_lipid_runs)
+    int tile_cap = 256;                           // candidates a tile holds (kTileCap; smaller only under the test option debug_tile_cap)
+    int *tile_overflow = nullptr;                 // raised by k_lipid_runs when a cell's candidates do not fit the tile of k_pair_ll_t
     bool lruns_valid = false;
     int *porder = nullptr; size_t porder_cap = 0;  // thread -> protein map of the protein pair kernel (heavy types first)
     bool porder_valid = false;
@@ -158,7 +157,7 @@ struct orbc_ctx {
     bool ff_set = false;
     orbc_forcefield host_ff;                       // host copy of this context's force field (Langevin coefficients, cull radii)
     int pair_impl = 2;
-    int ll_variant = 5;                            // bit 2: run-list kernel k_pair_ll_r; bit 1: sphere cull; bit 0: 20 resident blocks per SM
+    int ll_variant = 0;                            // 0: tile kernel k_pair_ll_t (k_pair_ll_r when a cell overflows the tile); 1: always k_pair_ll_r
     int prot_lanes = 0;                            // lanes per protein in k_pair_prot (0 = by the number of owned proteins)
     int *d_range = nullptr;                               // {l0, l1, p0, p1}: particle slots this context computes (all of them on one GPU)
     // volume constraint inside the whole-loop entry points (openrbc.cpp:229)

@@ -10,6 +10,7 @@
 #include "rebuild.cuh"
 #include "pair.cuh"
 #include "pair_queue.cuh"
+#include "pair_tile.cuh"
 #include "integrate.cuh"
 #include "multi.cuh"
 
@@ -299,32 +300,27 @@ int launch_pairwise(orbc_ctx *c, bool accumulate = true) {
     }
     {
         ProfScope ps(c, ORBC_PROF_PAIR_LIPID);
-        const size_t rel_need = (L.cap + 64) / 2 + 8;
-        if (c->ll_half && c->rel16_cap < rel_need) { ORBC_TRY(dev_alloc(&c->rel16, rel_need)); c->rel16_cap = rel_need; ORBC_CUDA(cudaMemsetAsync(c->rel16, 0, sizeof(uint4) * rel_need, c->stream)); }
-        if (c->ll_half) ORBC_CUDA(cudaMemsetAsync(c->rel_flag, 0, sizeof(int), c->stream));
         ORBC_LAUNCH(c, k_cell_bounds, blocks_for(c->n_cells, 128), 128, 0, c->centroid, c->n_cells, L.cell_start, L.X(), P.n ? P.cell_start : nullptr, P.X(), c->lbound, c->pbound,
-                    mg ? c->mg.need : (const int *)nullptr, c->mg.need_epoch, c->ll_half ? c->rel16 : (uint4 *)nullptr, c->rel_flag);
-        if (L.n) {
-            // packed half-precision prefilter when every lipid fits its error budget (rel_flag == 0), the fp32 kernel otherwise:
-            // both are launched, the one that is not needed returns at once
-            const int *gate = c->ll_half ? c->rel_flag : nullptr;
-            if (c->ll_half == 1) ORBC_LAUNCH(c, (k_pair_ll_h<20>), blocks_for(nl, kLLBlock), kLLBlock, 0, a, c->lbound, c->rel16, gate, 0);
-            else if (c->ll_half) ORBC_LAUNCH(c, (k_pair_ll_h<18>), blocks_for(nl, kLLBlock), kLLBlock, 0, a, c->lbound, c->rel16, gate, 0);
-            if ((c->ll_variant & 4) && !c->ll_half) {     // candidate runs merged over Morton-adjacent stencil cells, rebuilt after every rebuild
-                if (!c->lruns_valid) {
-                    if (a.ce > a.cb) ORBC_LAUNCH(c, k_lipid_runs, blocks_for(a.ce - a.cb, 128), 128, 0, a.cb, a.ce, c->stencil, c->stencil_cnt, L.cell_start, c->lruns, c->lrun_cnt);
-                    c->lruns_valid = true;
-                }
-                ORBC_LAUNCH(c, (k_pair_ll_r<20, 4>), blocks_for(nl, kLLBlock), kLLBlock, 0, a, c->lruns, c->lrun_cnt);
-            } else
-            switch (c->ll_variant & 3) { // bit 1: per-lane bounding-sphere cull of the stencil cells; bit 0: aim at 20 resident blocks per SM
-            case 0: ORBC_LAUNCH(c, (k_pair_ll<false, 1>), blocks_for(nl, kLLBlock), kLLBlock, 0, a, c->lbound, gate, 1); break;
-            case 1: ORBC_LAUNCH(c, (k_pair_ll<false, 20>), blocks_for(nl, kLLBlock), kLLBlock, 0, a, c->lbound, gate, 1); break;
-            case 2: ORBC_LAUNCH(c, (k_pair_ll<true, 1>), blocks_for(nl, kLLBlock), kLLBlock, 0, a, c->lbound, gate, 1); break;
-            default: ORBC_LAUNCH(c, (k_pair_ll<true, 20>), blocks_for(nl, kLLBlock), kLLBlock, 0, a, c->lbound, gate, 1); break;
+                    mg ? c->mg.need : (const int *)nullptr, c->mg.need_epoch);
+        if (L.n && a.ce > a.cb) {
+            // candidate runs merged over Morton-adjacent stencil cells, rebuilt after every rebuild of the partition
+            if (!c->lruns_valid) {
+                ORBC_CUDA(cudaMemsetAsync(c->tile_overflow, 0, sizeof(int), c->stream));
+                ORBC_LAUNCH(c, k_lipid_runs, blocks_for(a.ce - a.cb, 128), 128, 0, a.cb, a.ce, c->stencil, c->stencil_cnt, L.cell_start, c->lruns, c->lrun_cnt, c->tile_cap, c->tile_overflow);
+                c->lruns_valid = true;
             }
+            // warp-per-cell tile kernel; the thread-per-lipid kernel takes the step when a cell does not fit the tile (device flag),
+            // or when asked for ("ll_variant" 1)
+            if (c->ll_variant == 0) {
+                const unsigned warps = blocks_for((size_t)(a.ce - a.cb), kTileCells);
+                const orbc_forcefield &ff = c->host_ff;
+                const LLConst kc = {ff.cutll, 8.0f * ff.repll, 4.0f * ff.attll, ff.alphall, ff.alphall * ff.attll, 1.0f - ff.alphall, ff.cutsqll};
+                ORBC_LAUNCH(c, k_pair_ll_t, blocks_for(warps, kTileWarps), kTileWarps * 32, kTileWarps * kTileBytes, a, kc, c->lruns, c->lrun_cnt, c->tile_overflow);
+                ORBC_LAUNCH(c, (k_pair_ll_r<20, 4>), blocks_for(nl, kLLBlock), kLLBlock, 0, a, c->lruns, c->lrun_cnt, c->tile_overflow);
+            } else
+                ORBC_LAUNCH(c, (k_pair_ll_r<20, 4>), blocks_for(nl, kLLBlock), kLLBlock, 0, a, c->lruns, c->lrun_cnt, (const int *)nullptr);
         }
-        // (decomposed: the lipid side of the protein-lipid pairs whose protein lives on another rank is the epilogue of k_pair_ll)
+        // (decomposed: the lipid side of the protein-lipid pairs whose protein lives on another rank is the epilogue of the lipid kernels)
     }
     if (P.n) {
         const CullTable ct = cull_table(c);
@@ -492,7 +488,7 @@ int preload_kernels() {
     ORBC_PRELOAD(k_cv_normal_volume); ORBC_PRELOAD(k_fill_cellid); ORBC_PRELOAD(k_fill_int); ORBC_PRELOAD(k_halo_push); ORBC_PRELOAD(k_kinetic);
     ORBC_PRELOAD(k_mg_barrier); ORBC_PRELOAD(k_morton_keys); ORBC_PRELOAD(k_morton_keys_only); ORBC_PRELOAD(k_nh_final); ORBC_PRELOAD(k_nh_final_fused);
     ORBC_PRELOAD(k_nh_initial_fused); ORBC_PRELOAD(k_nh_zeta_update); ORBC_PRELOAD(k_share_ke); ORBC_PRELOAD(k_sum_ke); ORBC_PRELOAD(k_noise); ORBC_PRELOAD(k_opt_move); ORBC_PRELOAD(k_pack4);
-    ORBC_PRELOAD(k_pair_lipid); ORBC_PRELOAD(k_lipid_runs); ORBC_PRELOAD(k_rank_only); ORBC_PRELOAD(k_init_centroids); ORBC_PRELOAD(k_bbox); ORBC_PRELOAD((k_pair_ll_r<20, 4>)); ORBC_PRELOAD((k_pair_ll_h<20>)); ORBC_PRELOAD((k_pair_ll_h<18>)); ORBC_PRELOAD((k_pair_ll<false, 1>)); ORBC_PRELOAD((k_pair_ll<false, 20>)); ORBC_PRELOAD((k_pair_ll<true, 1>)); ORBC_PRELOAD((k_pair_ll<true, 20>)); ORBC_PRELOAD(k_pair_prot<1>); ORBC_PRELOAD(k_pair_prot<2>); ORBC_PRELOAD(k_pair_prot<4>); ORBC_PRELOAD(k_pair_protein);
+    ORBC_PRELOAD(k_pair_lipid); ORBC_PRELOAD(k_lipid_runs); ORBC_PRELOAD(k_rank_only); ORBC_PRELOAD(k_init_centroids); ORBC_PRELOAD(k_bbox); ORBC_PRELOAD((k_pair_ll_r<20, 4>)); ORBC_PRELOAD(k_pair_ll_t); ORBC_PRELOAD(k_pair_prot<1>); ORBC_PRELOAD(k_pair_prot<2>); ORBC_PRELOAD(k_pair_prot<4>); ORBC_PRELOAD(k_pair_protein);
     ORBC_PRELOAD(k_permute_centroids); ORBC_PRELOAD(k_porder_flag); ORBC_PRELOAD(k_porder_scatter); ORBC_PRELOAD(k_post_torque); ORBC_PRELOAD(k_radix_hist);
     ORBC_PRELOAD(k_radix_scatter); ORBC_PRELOAD(k_rank_and_move); ORBC_PRELOAD(k_remap_cellid); ORBC_PRELOAD(k_scan_onepass); ORBC_PRELOAD(k_set3); ORBC_PRELOAD(k_set_range); ORBC_PRELOAD(k_set_range_const); ORBC_PRELOAD(k_share_counts);
     ORBC_PRELOAD(k_stencil_build); ORBC_PRELOAD(k_stray_mask); ORBC_PRELOAD(k_unpack3); ORBC_PRELOAD(k_unpack_w); ORBC_PRELOAD(k_verlet_langevin); ORBC_PRELOAD(k_zero4);
@@ -612,7 +608,9 @@ int orbc_create(orbc_ctx **out, int device) {
     for (auto &e : c->ev) ORBC_CUDA(cudaEventCreate(&e));
     ORBC_TRY(dev_alloc(&c->d_acc, 8)); ORBC_TRY(dev_alloc(&c->d_counters, 8)); ORBC_TRY(dev_alloc(&c->d_flags, 4)); ORBC_TRY(dev_alloc(&c->d_nh, 2));
     ORBC_TRY(dev_alloc(&c->d_range, 4)); ORBC_CUDA(cudaMemset(c->d_range, 0, 4 * sizeof(int)));
-    ORBC_TRY(dev_alloc(&c->rel_flag, 1)); ORBC_CUDA(cudaMemset(c->rel_flag, 0, sizeof(int)));
+    ORBC_TRY(dev_alloc(&c->tile_overflow, 1)); ORBC_CUDA(cudaMemset(c->tile_overflow, 0, sizeof(int)));
+    // the tile kernel wants the whole shared-memory carve-out: five blocks of four 11 KB warp tiles per SM
+    ORBC_CUDA(cudaFuncSetAttribute((const void *)k_pair_ll_t, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     ORBC_CUDA(cudaMemset(c->d_acc, 0, 8 * sizeof(double))); ORBC_CUDA(cudaMemset(c->d_counters, 0, 8 * sizeof(unsigned long long)));
     ORBC_CUDA(cudaMemset(c->d_flags, 0, 4 * sizeof(int))); ORBC_CUDA(cudaMemset(c->d_nh, 0, 2 * sizeof(float)));
     ORBC_CUDA(cudaMallocHost((void **)&c->h_acc, 8 * sizeof(double))); ORBC_CUDA(cudaMallocHost((void **)&c->h_flags, 4 * sizeof(int)));
@@ -631,7 +629,7 @@ void orbc_destroy(orbc_ctx *c) { if (c) cudaSetDevice(c->device);
     dev_free(c->grid.bin_start); dev_free(c->grid.bin_items); dev_free(c->grid.bin_of); dev_free(c->grid.bin_slot); dev_free(c->grid.sorted);
     dev_free(c->stencil); dev_free(c->stencil_cnt); dev_free(c->cell_normal); dev_free(c->lbound); dev_free(c->pbound); dev_free(c->porder); dev_free(c->lruns); dev_free(c->lrun_cnt); dev_free(c->bonds); dev_free(c->tag2idx);
     dev_free(c->scan_tmp); dev_free(c->radix_hist); dev_free(c->stage); dev_free(c->d_acc); dev_free(c->d_counters); dev_free(c->d_flags); dev_free(c->d_nh);
-    dev_free(c->noise[0]); dev_free(c->noise[1]); dev_free(c->d_range); dev_free(c->rel16); dev_free(c->rel_flag);
+    dev_free(c->noise[0]); dev_free(c->noise[1]); dev_free(c->d_range); dev_free(c->tile_overflow);
     for (void *m : c->mg.opened) cudaIpcCloseMemHandle(m);
     dev_free(c->mg.my_bonds); dev_free(c->mg.keep); dev_free(c->mg.ke_all); dev_free(c->mg.vol_all); dev_free(c->mg.cv_ptype); dev_free(c->mg.flags); dev_free(c->mg.dest_mask); dev_free(c->mg.pmask); dev_free(c->mg.need);
     for (int s = 0; s < 2; ++s) { dev_free(c->mg.cnt_all[s]); dev_free(c->mg.off_me[s]); dev_free(c->mg.cnt_prev[s]); }
@@ -652,8 +650,14 @@ int orbc_set_option(orbc_ctx *c, const char *name, double value) { if (c) cudaSe
     if (!c || !name) return fail(ORBC_ERR_ARG, "null argument");
     if (!strcmp(name, "pair_impl")) { if (value != 1 && value != 2) return fail(ORBC_ERR_ARG, "pair_impl must be 1 or 2"); c->pair_impl = (int)value; return ORBC_OK; }
     if (!strcmp(name, "prot_lanes")) { if (value != 0 && value != 1 && value != 2 && value != 4) return fail(ORBC_ERR_ARG, "prot_lanes must be 0 (automatic), 1, 2 or 4"); c->prot_lanes = (int)value; return ORBC_OK; }
-    if (!strcmp(name, "ll_half")) { c->ll_half = (int)value; return ORBC_OK; }   // 0 off, 1 / 2: register targets of 20 / 18 resident blocks   // packed half-precision prefilter in the lipid-lipid kernel
-    if (!strcmp(name, "ll_variant")) { c->ll_variant = (int)value & 7; return ORBC_OK; }   // tuning variants of k_pair_ll (see launch_pairwise)
+    if (!strcmp(name, "ll_variant")) {                           // 0: warp-per-cell tile kernel k_pair_ll_t (default); 1: thread-per-lipid run-list kernel k_pair_ll_r
+        if (value != 0 && value != 1) return fail(ORBC_ERR_ARG, "ll_variant must be 0 (tile kernel) or 1 (run-list kernel)");
+        c->ll_variant = (int)value; return ORBC_OK;
+    }
+    if (!strcmp(name, "debug_tile_cap")) {                       // test aid: a smaller tile capacity, so that small systems reach the overflow path
+        if (!(value >= 1 && value <= kTileCap)) return fail(ORBC_ERR_ARG, "debug_tile_cap must be in [1, %d]", kTileCap);
+        c->tile_cap = (int)value; c->lruns_valid = false; return ORBC_OK;
+    }
     if (!strcmp(name, "debug_barriers")) {                       // profiling aid: `value` back-to-back barriers of a decomposed run
         for (int k = 0; k < (int)value; ++k) ORBC_TRY(mg_barrier(c));
         return ORBC_OK;
@@ -1140,8 +1144,6 @@ int orbc_mg_export(orbc_ctx *c, void *blob_out, size_t bytes) { if (c) cudaSetDe
         ORBC_TRY(dev_alloc(&m.pmask, P.n + 4)); ORBC_CUDA(cudaMemsetAsync(m.pmask, 0, P.n + 4, c->stream));
         ORBC_TRY(dev_alloc(&m.need, nc)); ORBC_CUDA(cudaMemsetAsync(m.need, 0, sizeof(int) * nc, c->stream));
         ORBC_TRY(dev_alloc(&m.keep, L.n + 1));
-        { const size_t rel_need = (L.cap + 64) / 2 + 8;
-          if (c->ll_half && c->rel16_cap < rel_need) { ORBC_TRY(dev_alloc(&c->rel16, rel_need)); c->rel16_cap = rel_need; ORBC_CUDA(cudaMemsetAsync(c->rel16, 0, sizeof(uint4) * rel_need, c->stream)); } }
         // work list of the bonds with an owned atom (clipped and flagged at the capacity)
         m.my_bonds_cap = (int)std::min(c->n_bonds, c->n_bonds / w + c->n_bonds / (2 * (size_t)w) + 8192);
         ORBC_TRY(dev_alloc(&m.my_bonds, (size_t)m.my_bonds_cap + 1));

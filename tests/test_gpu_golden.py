@@ -144,38 +144,35 @@ def test_counter_based_rng_matches_port_and_law():
 
 
 @pytest.mark.parametrize("name", FILES)
-def test_half_precision_prefilter_is_exact(name):
-    """k_pair_ll_h tests the cutoff in packed half precision as a PREFILTER (limit cutsq + margin) and re-tests the queued pairs in
-    fp32: hits, their order and therefore the forces must be bit-identical to the fp32 kernel's.  A lipid further than 8 from
-    its cell's origin exceeds the prefilter's error budget: k_cell_bounds raises the flag and the step runs on the fp32 kernel."""
+def test_tile_kernel_against_the_run_list_kernel(name):
+    """k_pair_ll_t (warp per cell, shared-memory tile, prefilter + exact re-test) finds exactly the hits of k_pair_ll_r (thread per
+    lipid): the forces differ only by the order of the per-lipid sums.  A cell whose candidates do not fit the tile sends the step
+    to k_pair_ll_r (device flag): with the capacity shrunk by the test option the results are then bit-identical to that kernel's."""
     from openrbc_b200 import Simulation
     g = load(name)
     st = state_of(g, "in")
     out = {}
-    for mode in (0, 1, 2):
+    for key, opts in (("tile", {}), ("runs", {"ll_variant": 1}), ("overflow", {"debug_tile_cap": 48})):
         sim = Simulation(st, kBT=0.0)
-        sim.set_option("ll_half", mode)
+        for k, v in opts.items():
+            sim.set_option(k, v)
         sim.compute_pairwise_fused()
-        out[mode] = sim.download(0, "ft")
+        out[key] = sim.download(0, "ft")
+        # a second evaluation accumulates (reference semantics: f, t +=): exactly twice the first for a deterministic kernel
+        if len(st["px"]) == 0:
+            sim.compute_pairwise_fused()
+            again = sim.download(0, "ft")
+            np.testing.assert_array_equal(again["f"], 2 * out[key]["f"])
         sim.close()
     exact = len(st["px"]) == 0            # protein -> lipid reactions arrive by atomics: their order is not fixed
-    for mode in (1, 2):
-        for k in "ft":
-            if exact:
-                np.testing.assert_array_equal(out[mode][k], out[0][k])
-            else:
-                assert rel_err(out[mode][k], out[0][k]) < 1e-6
-    # a stray lipid: 9.5 away from where its cell's origin expects it
-    st2 = dict(st); st2["lx"] = st["lx"].copy(); st2["lx"][7] += np.float32(9.5) * st["ln"][7] / np.linalg.norm(st["ln"][7])
-    res = []
-    for mode in (0, 1):
-        sim = Simulation(st2, kBT=0.0)
-        sim.set_option("ll_half", mode)
-        sim.compute_pairwise_fused()
-        res.append(sim.download(0, "ft"))
-        sim.close()
     for k in "ft":
+        assert rel_err(out["tile"][k], out["runs"][k]) < 2e-6
         if exact:
-            np.testing.assert_array_equal(res[1][k], res[0][k])
+            np.testing.assert_array_equal(out["overflow"][k], out["runs"][k])
         else:
-            assert rel_err(res[1][k], res[0][k]) < 1e-6
+            assert rel_err(out["overflow"][k], out["runs"][k]) < 1e-6
+    # the tile kernel is deterministic: two fresh contexts give the same bits
+    if exact:
+        sim = Simulation(st, kBT=0.0); sim.compute_pairwise_fused()
+        np.testing.assert_array_equal(sim.get(0, "f"), out["tile"]["f"])
+        sim.close()

@@ -64,30 +64,14 @@ timeit("compute_temperature", sim.compute_temperature)
 sim.nstep = 0
 timeit("run_langevin(2)", lambda: sim.run_langevin(2))
 sim.set_option("pair_impl", 2)
-base = None
-for half in (0, 1, 2):
-    sim.set_option("ll_half", half)
-    sim.clear_force(); sim.compute_pairwise_fused(); sim.synchronize()
-    f = sim.download(0, "ft")
-    if base is None:
-        base = f
-    same = bool((f["f"] == base["f"]).all() and (f["t"] == base["t"]).all())
-    sim.profile_enable(True)
-    for _ in range(reps):
-        sim.compute_pairwise_fused()
-    print(f"ll_half {half}: pair_lipid {sim.profile_read('pair_lipid')[0] / reps * 1e3:.1f} us   forces bit-identical to the fp32 kernel: {same}")
-    sim.profile_enable(False)
-sim.set_option("ll_half", 0)
-for var in range(4):
+for var in (1, 0):
     sim.set_option("ll_variant", var)
     sim.clear_force(); sim.compute_pairwise_fused(); sim.synchronize()
     sim.profile_enable(True)
     for _ in range(reps):
         sim.compute_pairwise_fused()
-    print(f"ll_variant {var} (cull {var >> 1}, min blocks {20 if var & 1 else 1}): pair_lipid {sim.profile_read('pair_lipid')[0] / reps * 1e3:.1f} us")
+    print(f"ll_variant {var} ({'run-list, thread per lipid' if var else 'tile, warp per cell'}): pair_lipid {sim.profile_read('pair_lipid')[0] / reps * 1e3:.1f} us")
     sim.profile_enable(False)
-sim.set_option("ll_variant", 1)
-sim.set_option("ll_half", 1)
 for lanes in (1, 2, 4):
     sim.set_option("prot_lanes", lanes)
     for frac in (1.0, 0.125):
@@ -112,14 +96,13 @@ for frac in (1.0, 0.5, 0.25, 0.125):
     sim.profile_enable(False)
 sim.set_option("debug_owned_fraction", 1.0)
 # per-kernel event timings of the production loop (in-process launch list)
-for half in (0, 1, 2):
-    sim.set_option("ll_half", half)
+for var in (1, 0):
+    sim.set_option("ll_variant", var)
     sim.run_langevin(4); sim.synchronize()
     sim.profile_kernels(True)
     sim.run_langevin(8)
     rep = sim.kernel_report()
     sim.profile_kernels(False)
-    print(f"ll_half {half}: kernel time {sum(r[2] for r in rep) / 8:.0f} us/step")
-    for name, n, us in rep[:8]:
+    print(f"ll_variant {var}: kernel time {sum(r[2] for r in rep) / 8:.0f} us/step")
+    for name, n, us in rep[:12]:
         print(f"   {name:34s} {n:4d} launches {us / n:8.1f} us mean")
-sim.set_option("ll_half", 1)
