@@ -92,8 +92,14 @@ ORBC_API int  orbc_synchronize(orbc_ctx *ctx);
 /* adopt an existing CUDA stream (cudaStream_t passed as void*); NULL = the context's own stream */
 ORBC_API int  orbc_set_stream(orbc_ctx *ctx, void *cuda_stream);
 
-/* tuning / test switches, by name.  "pair_impl": 2 = queued lipid kernel + warp-per-cell protein kernel (default),
- * 1 = the simple thread-per-particle kernels kept as an independent cross-check. */
+/* tuning / test switches, by name.
+ *   "pair_impl"   2 = production kernels (default), 1 = the simple thread-per-particle kernels kept as an independent cross-check
+ *   "ll_variant"  lipid-lipid kernel: 1 = thread per lipid over candidate runs, with hit lists (default); 0 = warp-per-cell tile kernel
+ *   "nl_reuse"    1 (default) = the force evaluation after a rebuild records per-particle hit lists with a skin and the evaluations up
+ *                 to the next rebuild walk them (exact re-test of every entry, a displacement bound guards the skin: same hits, same
+ *                 forces); 0 = every evaluation searches the stencils.  Single GPU only; ignored on a decomposed context.
+ *   "nl_skin"     the skin of those lists, default 0.1
+ *   "prot_lanes"  lanes per protein of the protein kernel (0 = automatic); debug_*: test aids */
 ORBC_API int  orbc_set_option(orbc_ctx *ctx, const char *name, double value);
 
 /* ---- force field (forcefield_canonical.h) ------------------------------------------------------------------ */
@@ -214,7 +220,8 @@ typedef enum {
     ORBC_DUMP_STENCIL_COUNTS = 9,/* n_cells x 3 int: entries with centroid distance < 6, < 8, < 9 */
     ORBC_DUMP_STENCIL = 10,      /* n_cells x ORBC_STENCIL_STRIDE int, ordered (class, id) */
     ORBC_DUMP_TAG2IDX = 11,      /* protein tag -> index, (max_tag + 1) int */
-    ORBC_DUMP_COUNTERS = 12      /* 8 x uint64 device counters (fallback searches, ...) */
+    ORBC_DUMP_COUNTERS = 12,     /* 8 x uint64 device counters (fallback searches, ...) */
+    ORBC_DUMP_NL_STATS = 13      /* 4 x uint32: force evaluations that built the hit lists, that walked them, overflow flag, last decision */
 } orbc_dump;
 #define ORBC_STENCIL_STRIDE 64
 ORBC_API int  orbc_debug_dump(orbc_ctx *ctx, int what, void *dst, size_t bytes);

@@ -64,6 +64,7 @@ struct IntegArgs {
     const float *noise;                    // optional injected noise (n x 3), device pointer
     double *acc;                           // acc[0] += kinetic energy
     const float *zeta_dev;                 // if non-null, zeta is read from the device (orbc_run_nh)
+    unsigned *disp;                        // if non-null: largest squared displacement of this step, for the hit lists (NlState::disp)
 };
 
 __device__ __forceinline__ F3 cross3(F3 u, F3 v) { return {u.y * v.z - u.z * v.y, u.z * v.x - u.x * v.z, u.x * v.y - u.y * v.x}; }
@@ -136,6 +137,7 @@ __global__ void __launch_bounds__(256) k_verlet_langevin(IntegArgs a) {
     const float k = a.dt / c_ff.mass[type];
     v.x += fx * k; v.y += fy * k; v.z += fz * k;
     x.x += v.x * a.dt; x.y += v.y * a.dt; x.z += v.z * a.dt;
+    nl_track(a.disp, (v.x * v.x + v.y * v.y + v.z * v.z) * (a.dt * a.dt));
     a.x_out[i] = x; a.v[i] = v; a.o[i] = o;
     const float4 nnew = make_float4(nn.x, nn.y, nn.z, n4.w);
     a.nn_out[i] = nnew;
@@ -164,7 +166,8 @@ __global__ void __launch_bounds__(256) k_nh_initial_fused(IntegArgs a) {
         const float s = 0.5f / m * a.dt;
         v.x = (v.x + s * f.x) * gamma; v.y = (v.y + s * f.y) * gamma; v.z = (v.z + s * f.z) * gamma;
         x.x += v.x * a.dt; x.y += v.y * a.dt; x.z += v.z * a.dt;
-        bounce(x.x, v.x, a.dlo, a.dhi); bounce(x.y, v.y, a.dlo, a.dhi); bounce(x.z, v.z, a.dlo, a.dhi);
+        bounce(x.x, v.x, a.dlo, a.dhi); bounce(x.y, v.y, a.dlo, a.dhi); bounce(x.z, v.z, a.dlo, a.dhi);   // a reflection never lengthens the step
+        nl_track(a.disp, (v.x * v.x + v.y * v.y + v.z * v.z) * (a.dt * a.dt));
         ke = 0.5f * m * (v.x * v.x + v.y * v.y + v.z * v.z);
         const float so = 0.5f * a.dt;
         o.x += so * t.x; o.y += so * t.y; o.z += so * t.z;

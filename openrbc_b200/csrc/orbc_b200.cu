@@ -123,6 +123,7 @@ int alloc_species(orbc_ctx *c, Species &s, size_t n) {
         s.cap = cap;
     }
     s.n = n; s.cur = 0; s.cur_xn = 0; s.has_partition = false;
+    c->nl_valid = false;
     const int sp = (int)(&s - c->sp);
     ORBC_LAUNCH(c, k_set_range_const, 1, 1, 0, c->d_range + 2 * sp, 0, (int)n);   // a single GPU computes every slot
     return ORBC_OK;
@@ -213,6 +214,25 @@ float pow_chain(float base, int expo) { return expo != 0 ? base * pow_chain(base
 float ff_rep(float cut, float req, float eps) { return eps / pow_chain(cut - req, 8); }
 float ff_att(float cut, float req, float eps) { return (float)(-2.0 * eps / pow_chain(cut - req, 4)); }
 
+// hit lists are used by the default single-GPU kernels only (a decomposed run would have to exchange the displacement bound)
+bool nl_active(const orbc_ctx *c) { return c->nl_on && !mg_active(c) && c->pair_impl == 2 && c->ll_variant == 1; }
+int nl_ensure(orbc_ctx *c) {
+    Species &L = c->sp[0], &P = c->sp[1];
+    if (!c->nl_state) { NlState *st = nullptr; ORBC_TRY(dev_alloc(&st, 1)); c->nl_state = st; ORBC_CUDA(cudaMemsetAsync(st, 0, sizeof(NlState), c->stream)); c->nl_valid = false; }
+    if (c->ll_list_lipids < L.cap) {
+        const size_t groups = (L.cap + 63) / 64;
+        ORBC_TRY(dev_alloc(&c->ll_list, groups * 64 * (size_t)c->nl_cap_ll)); ORBC_TRY(dev_alloc(&c->ll_cnt, groups * 64));
+        c->ll_list_lipids = L.cap; c->nl_valid = false;
+    }
+    if (P.n && c->pl_list_proteins < P.cap) {
+        const size_t groups = (P.cap + 63) / 64;
+        ORBC_TRY(dev_alloc(&c->pl_list, groups * 64 * (size_t)c->nl_cap_pl)); ORBC_TRY(dev_alloc(&c->pl_cnt, groups * 64));
+        ORBC_TRY(dev_alloc(&c->pp_list, groups * 64 * (size_t)c->nl_cap_pp)); ORBC_TRY(dev_alloc(&c->pp_cnt, groups * 64));
+        c->pl_list_proteins = P.cap; c->nl_valid = false;
+    }
+    return ORBC_OK;
+}
+
 void fill_integ(IntegArgs &a, orbc_ctx *c, int sp, const orbc_step_params *p) {
     Species &s = c->sp[sp];
     a.x = s.X(); a.v = s.V(); a.f = s.f; a.nn = s.N(); a.o = s.O(); a.t = s.t;
@@ -225,6 +245,7 @@ void fill_integ(IntegArgs &a, orbc_ctx *c, int sp, const orbc_step_params *p) {
     a.dr_opt = p->dr_opt; a.dn_opt = p->dn_opt;
     a.seed = p->seed; a.step = (uint32_t)p->nstep;
     a.noise = nullptr; a.acc = c->d_acc; a.zeta_dev = nullptr;
+    a.disp = nl_active(c) && c->nl_state ? ((NlState *)c->nl_state)->disp : nullptr;
     a.range = c->d_range + 2 * sp;
     a.clear = 1;
     a.push.world = 1; a.push.cell_mask = nullptr; a.push.pmask = nullptr; a.push.cellid = nullptr;
@@ -254,7 +275,7 @@ CullTable cull_table(const orbc_ctx *c) {
         ct.cut_l[t] = std::sqrt(std::max(c->host_ff.cutsqlp[t], c->host_ff.lj_cutsq[t]));
         float m = 0.f;
         for (int u = 0; u < kNType; ++u) if (c->type_mask >> u & 1) m = std::max(m, std::max(c->host_ff.cutsqpp[t + kNType * u], c->host_ff.lj_cutsq[t + kNType * u]));
-        ct.cut_p[t] = std::sqrt(m);
+        ct.cut_p[t] = std::sqrt(m); ct.cutsq_p[t] = m;
     }
     return ct;
 }
@@ -291,17 +312,30 @@ int launch_pairwise(orbc_ctx *c, bool accumulate = true) {
     a.cb = mg ? c->mg.cb : 0; a.ce = mg ? c->mg.ce : c->n_cells; a.world = mg ? c->mg.world : 1;
     a.dest_mask = c->mg.dest_mask;
     a.accumulate = accumulate ? 1 : 0;
-    const size_t nl = owned_bound(c, ORBC_LIPID), np = owned_bound(c, ORBC_PROTEIN);
+    const size_t nl_count = owned_bound(c, ORBC_LIPID), np = owned_bound(c, ORBC_PROTEIN);
+    constexpr unsigned kSmallGrid = 148 * 16;                   // a gated launch that usually returns at once: grid-stride over few blocks
     if (c->pair_impl == 1) {
         if (mg) return fail(ORBC_ERR_ARG, "pair_impl 1 is a single-GPU cross-check");
-        if (L.n) { ProfScope ps(c, ORBC_PROF_PAIR_LIPID); ORBC_LAUNCH(c, k_pair_lipid, blocks_for(nl, 128), 128, 0, a); }
+        if (L.n) { ProfScope ps(c, ORBC_PROF_PAIR_LIPID); ORBC_LAUNCH(c, k_pair_lipid, blocks_for(nl_count, 128), 128, 0, a); }
         if (P.n) { ProfScope ps(c, ORBC_PROF_PAIR_PROTEIN); ORBC_LAUNCH(c, k_pair_protein, blocks_for(np, 128), 128, 0, a); }
         return ORBC_OK;
     }
+    // hit lists: the evaluation after a rebuild records them, the following ones walk them (pair_queue.cuh)
+    const bool nl = nl_active(c);
+    bool host_build = true;
+    NlState *nls = nullptr;
+    if (nl) {
+        ORBC_TRY(nl_ensure(c));
+        nls = (NlState *)c->nl_state;
+        host_build = !c->nl_valid;
+        ORBC_LAUNCH(c, k_nl_gate, 1, 32, 0, nls, host_build ? 1 : 0, c->nl_moves, c->nl_skin);
+        c->nl_moves = 0; c->nl_valid = true;
+    }
     {
         ProfScope ps(c, ORBC_PROF_PAIR_LIPID);
+        // bounding spheres of the cells' current members: the protein kernel culls with them (on a list-walking step only the gated rebuild of the lists would)
         ORBC_LAUNCH(c, k_cell_bounds, blocks_for(c->n_cells, 128), 128, 0, c->centroid, c->n_cells, L.cell_start, L.X(), P.n ? P.cell_start : nullptr, P.X(), c->lbound, c->pbound,
-                    mg ? c->mg.need : (const int *)nullptr, c->mg.need_epoch);
+                    mg ? c->mg.need : (const int *)nullptr, c->mg.need_epoch, (nl && !host_build) ? &nls->need : (const int *)nullptr);
         if (L.n && a.ce > a.cb) {
             // candidate runs merged over Morton-adjacent stencil cells, rebuilt after every rebuild of the partition
             if (!c->lruns_valid) {
@@ -309,16 +343,24 @@ int launch_pairwise(orbc_ctx *c, bool accumulate = true) {
                 ORBC_LAUNCH(c, k_lipid_runs, blocks_for(a.ce - a.cb, 128), 128, 0, a.cb, a.ce, c->stencil, c->stencil_cnt, L.cell_start, c->lruns, c->lrun_cnt, c->tile_cap, c->tile_overflow);
                 c->lruns_valid = true;
             }
-            // warp-per-cell tile kernel; the thread-per-lipid kernel takes the step when a cell does not fit the tile (device flag),
-            // or when asked for ("ll_variant" 1)
             if (c->ll_variant == 0) {
+                // warp-per-cell tile kernel; the thread-per-lipid kernel takes the step when a cell does not fit the tile (device flag)
                 const unsigned warps = blocks_for((size_t)(a.ce - a.cb), kTileCells);
                 const orbc_forcefield &ff = c->host_ff;
                 const LLConst kc = {ff.cutll, 8.0f * ff.repll, 4.0f * ff.attll, ff.alphall, ff.alphall * ff.attll, 1.0f - ff.alphall, ff.cutsqll};
                 ORBC_LAUNCH(c, k_pair_ll_t, blocks_for(warps, kTileWarps), kTileWarps * 32, kTileWarps * kTileBytes, a, kc, c->lruns, c->lrun_cnt, c->tile_overflow);
-                ORBC_LAUNCH(c, (k_pair_ll_r<20, 4>), blocks_for(nl, kLLBlock), kLLBlock, 0, a, c->lruns, c->lrun_cnt, c->tile_overflow);
-            } else
-                ORBC_LAUNCH(c, (k_pair_ll_r<20, 4>), blocks_for(nl, kLLBlock), kLLBlock, 0, a, c->lruns, c->lrun_cnt, (const int *)nullptr);
+                ORBC_LAUNCH(c, (k_pair_ll_r<20, 4, false>), kSmallGrid, kLLBlock, 0, a, c->lruns, c->lrun_cnt, c->tile_overflow, 1, LLList{}, 0.f);
+            } else if (!nl) {
+                ORBC_LAUNCH(c, (k_pair_ll_r<20, 4, false>), blocks_for(nl_count, kLLBlock), kLLBlock, 0, a, c->lruns, c->lrun_cnt, (const int *)nullptr, 0, LLList{}, 0.f);
+            } else {
+                const LLList ll = {c->ll_list, c->ll_cnt, c->nl_cap_ll, nls};
+                if (host_build)                                  // right after a rebuild: record the lists while evaluating
+                    ORBC_LAUNCH(c, (k_pair_ll_r<20, 4, true>), blocks_for(nl_count, kLLBlock), kLLBlock, 0, a, c->lruns, c->lrun_cnt, (const int *)nullptr, 0, ll, c->nl_skin);
+                else {                                           // walk the lists; the gate orders a fresh build only if a particle outran the skin
+                    ORBC_LAUNCH(c, (k_pair_ll_list<20>), blocks_for(nl_count, kLLBlock), kLLBlock, 0, a, &nls->need, 0, ll);
+                    ORBC_LAUNCH(c, (k_pair_ll_r<20, 4, true>), kSmallGrid, kLLBlock, 0, a, c->lruns, c->lrun_cnt, &nls->need, 1, ll, c->nl_skin);
+                }
+            }
         }
         // (decomposed: the lipid side of the protein-lipid pairs whose protein lives on another rank is the epilogue of the lipid kernels)
     }
@@ -327,10 +369,18 @@ int launch_pairwise(orbc_ctx *c, bool accumulate = true) {
         if (!c->porder_valid) ORBC_TRY(build_porder(c));
         ProfScope ps(c, ORBC_PROF_PAIR_PROTEIN);
         // few owned proteins (a rank of a decomposed run): more lanes per protein, shorter dependent-load chains, more warps
-        const int lanes = c->prot_lanes ? c->prot_lanes : (np <= 400000 ? 4 : 1);
-        if (lanes == 4) ORBC_LAUNCH(c, k_pair_prot<4>, blocks_for(np * 4, kPBlock), kPBlock, 0, a, c->lbound, c->pbound, ct, c->porder);
-        else if (lanes == 2) ORBC_LAUNCH(c, k_pair_prot<2>, blocks_for(np * 2, kPBlock), kPBlock, 0, a, c->lbound, c->pbound, ct, c->porder);
-        else ORBC_LAUNCH(c, k_pair_prot<1>, blocks_for(np, kPBlock), kPBlock, 0, a, c->lbound, c->pbound, ct, c->porder);
+        const PLists pls = {c->pl_list, c->pl_cnt, c->pp_list, c->pp_cnt, c->nl_cap_pl, c->nl_cap_pp, nls};
+        if (nl && host_build)
+            ORBC_LAUNCH(c, (k_pair_prot<1, true>), blocks_for(np, kPBlock), kPBlock, 0, a, c->lbound, c->pbound, ct, c->porder, (const int *)nullptr, 0, pls, c->nl_skin);
+        else if (nl) {
+            ORBC_LAUNCH(c, k_pair_prot_list, blocks_for(np, kPBlock), kPBlock, 0, a, c->porder, &nls->need, 0, pls);
+            ORBC_LAUNCH(c, (k_pair_prot<1, true>), kSmallGrid, kPBlock, 0, a, c->lbound, c->pbound, ct, c->porder, &nls->need, 1, pls, c->nl_skin);
+        } else {
+            const int lanes = c->prot_lanes ? c->prot_lanes : (np <= 400000 ? 4 : 1);
+            if (lanes == 4) ORBC_LAUNCH(c, (k_pair_prot<4, false>), blocks_for(np * 4, kPBlock), kPBlock, 0, a, c->lbound, c->pbound, ct, c->porder, (const int *)nullptr, 0, pls, 0.f);
+            else if (lanes == 2) ORBC_LAUNCH(c, (k_pair_prot<2, false>), blocks_for(np * 2, kPBlock), kPBlock, 0, a, c->lbound, c->pbound, ct, c->porder, (const int *)nullptr, 0, pls, 0.f);
+            else ORBC_LAUNCH(c, (k_pair_prot<1, false>), blocks_for(np, kPBlock), kPBlock, 0, a, c->lbound, c->pbound, ct, c->porder, (const int *)nullptr, 0, pls, 0.f);
+        }
     }
     return ORBC_OK;
 }
@@ -356,6 +406,7 @@ int do_voronoi_update(orbc_ctx *c, int nstep, int freq_sort_ctrd) {
     if (!c->n_cells || !L.has_partition) return fail(ORBC_ERR_ARG, "voronoi_update: no previous partition (orbc_voronoi_upload with cell_start first)");
     const int nc = c->n_cells;
     const bool mg = mg_active(c);
+    c->nl_valid = false;                                         // cells are about to be renumbered / repartitioned: the hit lists die with the old slots
     // centroids of the owned cells, published to every rank (voronoi.h:123-140)
     CentroidOut out; out.world = mg ? c->mg.world : 1;
     for (int r = 0; r < kMaxWorld; ++r) out.dst[r] = mg ? c->mg.peers.centroid[c->mg.cen_par ^ 1][r] : c->centroid_tmp;
@@ -425,6 +476,7 @@ int cell_update_move(orbc_ctx *c, int sp) {
         S.cur = nx; S.cur_xn = nxn;
     }
     S.has_partition = true;
+    c->nl_valid = false;
     if (sp == ORBC_LIPID) c->lruns_valid = false;
     return ORBC_OK;
 }
@@ -457,6 +509,7 @@ int do_cell_update(orbc_ctx *c, int sp) {
 // `rebuild_follows`: the caller rebuilds next; the first barrier of the rebuild then also covers the arrival of this push
 int do_integrate_langevin(orbc_ctx *c, const orbc_step_params *p, bool rebuild_follows = false, bool clear = true) {
     // decomposed: no barrier before the push — it goes to the x, n buffers nobody is reading (fill_integ)
+    ++c->nl_moves;                                               // one tracked integration step (hit lists: displacement bound)
     {
         ProfScope ps(c, ORBC_PROF_INTEGRATE);
         for (int sp = 0; sp < 2; ++sp) {
@@ -488,7 +541,7 @@ int preload_kernels() {
     ORBC_PRELOAD(k_cv_normal_volume); ORBC_PRELOAD(k_fill_cellid); ORBC_PRELOAD(k_fill_int); ORBC_PRELOAD(k_halo_push); ORBC_PRELOAD(k_kinetic);
     ORBC_PRELOAD(k_mg_barrier); ORBC_PRELOAD(k_morton_keys); ORBC_PRELOAD(k_morton_keys_only); ORBC_PRELOAD(k_nh_final); ORBC_PRELOAD(k_nh_final_fused);
     ORBC_PRELOAD(k_nh_initial_fused); ORBC_PRELOAD(k_nh_zeta_update); ORBC_PRELOAD(k_share_ke); ORBC_PRELOAD(k_sum_ke); ORBC_PRELOAD(k_noise); ORBC_PRELOAD(k_opt_move); ORBC_PRELOAD(k_pack4);
-    ORBC_PRELOAD(k_pair_lipid); ORBC_PRELOAD(k_lipid_runs); ORBC_PRELOAD(k_rank_only); ORBC_PRELOAD(k_init_centroids); ORBC_PRELOAD(k_bbox); ORBC_PRELOAD((k_pair_ll_r<20, 4>)); ORBC_PRELOAD(k_pair_ll_t); ORBC_PRELOAD(k_pair_prot<1>); ORBC_PRELOAD(k_pair_prot<2>); ORBC_PRELOAD(k_pair_prot<4>); ORBC_PRELOAD(k_pair_protein);
+    ORBC_PRELOAD(k_pair_lipid); ORBC_PRELOAD(k_lipid_runs); ORBC_PRELOAD(k_rank_only); ORBC_PRELOAD(k_init_centroids); ORBC_PRELOAD(k_bbox); ORBC_PRELOAD((k_pair_ll_r<20, 4, false>)); ORBC_PRELOAD(k_pair_ll_t); ORBC_PRELOAD((k_pair_prot<1, false>)); ORBC_PRELOAD((k_pair_prot<2, false>)); ORBC_PRELOAD((k_pair_prot<4, false>)); ORBC_PRELOAD(k_pair_protein);
     ORBC_PRELOAD(k_permute_centroids); ORBC_PRELOAD(k_porder_flag); ORBC_PRELOAD(k_porder_scatter); ORBC_PRELOAD(k_post_torque); ORBC_PRELOAD(k_radix_hist);
     ORBC_PRELOAD(k_radix_scatter); ORBC_PRELOAD(k_rank_and_move); ORBC_PRELOAD(k_remap_cellid); ORBC_PRELOAD(k_scan_onepass); ORBC_PRELOAD(k_set3); ORBC_PRELOAD(k_set_range); ORBC_PRELOAD(k_set_range_const); ORBC_PRELOAD(k_share_counts);
     ORBC_PRELOAD(k_stencil_build); ORBC_PRELOAD(k_stray_mask); ORBC_PRELOAD(k_unpack3); ORBC_PRELOAD(k_unpack_w); ORBC_PRELOAD(k_verlet_langevin); ORBC_PRELOAD(k_zero4);
@@ -630,6 +683,7 @@ void orbc_destroy(orbc_ctx *c) { if (c) cudaSetDevice(c->device);
     dev_free(c->stencil); dev_free(c->stencil_cnt); dev_free(c->cell_normal); dev_free(c->lbound); dev_free(c->pbound); dev_free(c->porder); dev_free(c->lruns); dev_free(c->lrun_cnt); dev_free(c->bonds); dev_free(c->tag2idx);
     dev_free(c->scan_tmp); dev_free(c->radix_hist); dev_free(c->stage); dev_free(c->d_acc); dev_free(c->d_counters); dev_free(c->d_flags); dev_free(c->d_nh);
     dev_free(c->noise[0]); dev_free(c->noise[1]); dev_free(c->d_range); dev_free(c->tile_overflow);
+    { NlState *st = (NlState *)c->nl_state; dev_free(st); } dev_free(c->ll_list); dev_free(c->ll_cnt); dev_free(c->pl_list); dev_free(c->pl_cnt); dev_free(c->pp_list); dev_free(c->pp_cnt);
     for (void *m : c->mg.opened) cudaIpcCloseMemHandle(m);
     dev_free(c->mg.my_bonds); dev_free(c->mg.keep); dev_free(c->mg.ke_all); dev_free(c->mg.vol_all); dev_free(c->mg.cv_ptype); dev_free(c->mg.flags); dev_free(c->mg.dest_mask); dev_free(c->mg.pmask); dev_free(c->mg.need);
     for (int s = 0; s < 2; ++s) { dev_free(c->mg.cnt_all[s]); dev_free(c->mg.off_me[s]); dev_free(c->mg.cnt_prev[s]); }
@@ -648,11 +702,16 @@ void orbc_destroy(orbc_ctx *c) { if (c) cudaSetDevice(c->device);
 
 int orbc_set_option(orbc_ctx *c, const char *name, double value) { if (c) cudaSetDevice(c->device);
     if (!c || !name) return fail(ORBC_ERR_ARG, "null argument");
-    if (!strcmp(name, "pair_impl")) { if (value != 1 && value != 2) return fail(ORBC_ERR_ARG, "pair_impl must be 1 or 2"); c->pair_impl = (int)value; return ORBC_OK; }
+    if (!strcmp(name, "pair_impl")) { if (value != 1 && value != 2) return fail(ORBC_ERR_ARG, "pair_impl must be 1 or 2"); c->pair_impl = (int)value; c->nl_valid = false; return ORBC_OK; }
     if (!strcmp(name, "prot_lanes")) { if (value != 0 && value != 1 && value != 2 && value != 4) return fail(ORBC_ERR_ARG, "prot_lanes must be 0 (automatic), 1, 2 or 4"); c->prot_lanes = (int)value; return ORBC_OK; }
     if (!strcmp(name, "ll_variant")) {                           // 0: warp-per-cell tile kernel k_pair_ll_t (default); 1: thread-per-lipid run-list kernel k_pair_ll_r
-        if (value != 0 && value != 1) return fail(ORBC_ERR_ARG, "ll_variant must be 0 (tile kernel) or 1 (run-list kernel)");
-        c->ll_variant = (int)value; return ORBC_OK;
+        if (value != 0 && value != 1) return fail(ORBC_ERR_ARG, "ll_variant must be 1 (run-list kernel + hit lists) or 0 (tile kernel)");
+        c->ll_variant = (int)value; c->nl_valid = false; return ORBC_OK;
+    }
+    if (!strcmp(name, "nl_reuse")) { c->nl_on = value != 0; c->nl_valid = false; return ORBC_OK; }   // hit lists between rebuilds on / off
+    if (!strcmp(name, "nl_skin")) {
+        if (!(value >= 0.0 && value <= 1.0)) return fail(ORBC_ERR_ARG, "nl_skin must be in [0, 1]");
+        c->nl_skin = (float)value; c->nl_valid = false; return ORBC_OK;
     }
     if (!strcmp(name, "debug_tile_cap")) {                       // test aid: a smaller tile capacity, so that small systems reach the overflow path
         if (!(value >= 1 && value <= kTileCap)) return fail(ORBC_ERR_ARG, "debug_tile_cap must be in [1, %d]", kTileCap);
@@ -667,7 +726,7 @@ int orbc_set_option(orbc_ctx *c, const char *name, double value) { if (c) cudaSe
         // would (forces and integration of the other slots are skipped; results are partial by construction)
         if (!(value > 0.0 && value <= 1.0)) return fail(ORBC_ERR_ARG, "debug_owned_fraction must be in (0, 1]");
         for (int sp = 0; sp < 2; ++sp) ORBC_LAUNCH(c, k_set_range_const, 1, 1, 0, c->d_range + 2 * sp, 0, (int)(c->sp[sp].n * value));
-        c->porder_valid = false;
+        c->porder_valid = false; c->nl_valid = false;
         return ORBC_OK;
     }
     return fail(ORBC_ERR_ARG, "unknown option '%s'", name);
@@ -740,6 +799,7 @@ int orbc_voronoi_upload(orbc_ctx *c, int nc, const float *centroids3, const int 
     if (!c || nc <= 0 || !centroids3) return fail(ORBC_ERR_ARG, "orbc_voronoi_upload: bad argument");
     if (nc >= (1 << 28)) return fail(ORBC_ERR_ARG, "more than 2^28 Voronoi cells");
     ORBC_TRY(alloc_voronoi(c, nc));
+    c->nl_valid = false;
     ORBC_CUDA(cudaMemsetAsync(c->cell_normal, 0, sizeof(float4) * nc, c->stream));
     ORBC_TRY(ensure_stage(c, (size_t)3 * nc));
     ORBC_CUDA(cudaMemcpyAsync(c->stage, centroids3, sizeof(float) * 3 * nc, cudaMemcpyHostToDevice, c->stream));
@@ -834,6 +894,7 @@ int orbc_set_field(orbc_ctx *c, int sp, char field, size_t stride, const float *
     float4 *dst = field == 'f' ? S.f : field == 't' ? S.t : field == 'v' ? S.V() : field == 'x' ? S.X() : field == 'n' ? S.N() : field == 'o' ? S.O() : nullptr;
     if (!strchr("ftvxno", field)) return fail(ORBC_ERR_ARG, "orbc_set_field: unknown field '%c'", field);
     if (!S.n) return ORBC_OK;
+    if (field == 'x') c->nl_valid = false;
     ORBC_TRY(ensure_stage(c, S.n * stride));
     ORBC_CUDA(cudaMemcpyAsync(c->stage, src, sizeof(float) * S.n * stride, cudaMemcpyHostToDevice, c->stream));
     ORBC_LAUNCH(c, k_set3, blocks_for(S.n, kBlock), kBlock, 0, c->stage, stride, S.n, dst);
@@ -955,6 +1016,8 @@ int orbc_integrate(orbc_ctx *c, int kernel, const orbc_step_params *p, orbc_step
     if (reduces) ORBC_CUDA(cudaMemsetAsync(c->d_acc, 0, sizeof(double), c->stream));
     const bool mg_ok = kernel == ORBC_VERLET_LANGEVIN || kernel == ORBC_CLEAR_FORCE || kernel == ORBC_NH_INITIAL_FUSED || kernel == ORBC_NH_FINAL_FUSED || kernel == ORBC_OPT_FUSED;
     if (!mg_ok) ORBC_TRY(single_gpu_only(c, "this integrate() kernel"));
+    if (kernel == ORBC_NH_INITIAL_FUSED) ++c->nl_moves;          // tracked by the kernel (hit lists)
+    if (kernel == ORBC_BOUNCE_BACK || kernel == ORBC_OPT_MOVE || kernel == ORBC_OPT_FUSED) c->nl_valid = false;   // untracked moves
     if (kernel == ORBC_VERLET_LANGEVIN) ORBC_TRY(do_integrate_langevin(c, p));
     else for (int sp = 0; sp < 2; ++sp) {
         Species &S = c->sp[sp];
@@ -1048,6 +1111,7 @@ int orbc_run_minimize(orbc_ctx *c, const orbc_step_params *p, int n_steps, int f
                 Species &S = c->sp[sp];
                 if (!S.n) continue;
                 IntegArgs a; fill_integ(a, c, sp, &q); a.clear = 0;
+                c->nl_valid = false;
                 ORBC_LAUNCH(c, k_opt_fused, blocks_for(owned_bound(c, sp), 256), 256, 0, a);
                 if (mg_active(c)) S.cur_xn ^= 1;
             }
@@ -1067,6 +1131,7 @@ int orbc_run_nh(orbc_ctx *c, const orbc_step_params *p, int n_steps, int freq_vo
     const bool mg = mg_active(c);
     const int world = mg ? c->mg.world : 1;
     for (int s = 0; s < n_steps; ++s, ++q.nstep) {
+        ++c->nl_moves;
         for (int sp = 0; sp < 2; ++sp) if (c->sp[sp].n) {
             IntegArgs a; fill_integ(a, c, sp, &q); a.zeta_dev = c->d_nh;
             ORBC_LAUNCH(c, k_nh_initial_fused, blocks_for(owned_bound(c, sp), 256), 256, 0, a);
@@ -1375,6 +1440,18 @@ int orbc_debug_dump(orbc_ctx *c, int what, void *dst, size_t bytes) { if (c) cud
     case ORBC_DUMP_STENCIL: src = c->stencil; need = sizeof(int) * (size_t)nc * kStencilStride; break;
     case ORBC_DUMP_TAG2IDX: src = c->tag2idx; need = sizeof(int) * c->tag2idx_size; break;
     case ORBC_DUMP_COUNTERS: src = c->d_counters; need = 8 * sizeof(unsigned long long); break;
+    case ORBC_DUMP_NL_STATS: {
+        need = 4 * sizeof(unsigned);
+        if (bytes < need) return fail(ORBC_ERR_ARG, "dump buffer too small");
+        unsigned out[4] = {0, 0, 0, 0};
+        if (c->nl_state) {
+            NlState h;
+            ORBC_CUDA(cudaMemcpyAsync(&h, c->nl_state, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+            ORBC_CUDA(cudaStreamSynchronize(c->stream));
+            out[0] = h.builds; out[1] = h.reuses; out[2] = (unsigned)h.overflow; out[3] = (unsigned)h.need;
+        }
+        memcpy(dst, out, need);
+        return check_flags(c); }
     default: return fail(ORBC_ERR_ARG, "unknown dump id %d", what);
     }
     if (bytes < need) return fail(ORBC_ERR_ARG, "dump buffer too small: %zu < %zu", bytes, need);

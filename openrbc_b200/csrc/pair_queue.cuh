@@ -28,12 +28,14 @@ constexpr float kCullEps = 4e-3f;  // slack of the bounding-sphere test (absolut
 
 struct CullTable {                 // per protein type: largest interaction range against lipids / against the protein types present
     float cut_l[kNType], cut_p[kNType];
+    float cutsq_p[kNType];         // the largest SQUARED protein-protein cutoff itself (the pair test must not square a rounded root)
 };
 
 // ---- bounding spheres ------------------------------------------------------------------------------------------------------
 __global__ void k_cell_bounds(const float4 *__restrict__ centroid, int n_cells, const int *__restrict__ cs_l, const float4 *__restrict__ xl,
                               const int *__restrict__ cs_p, const float4 *__restrict__ xp, float4 *__restrict__ lbound, float4 *__restrict__ pbound,
-                              const int *__restrict__ need, int need_epoch) {
+                              const int *__restrict__ need, int need_epoch, const int *__restrict__ gate) {
+    if (gate && *gate == 0) return;                          // a list-walking step: nobody culls
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n_cells) return;
     if (need && need[c] != need_epoch) return;             // decomposed run: neither owned nor halo, its particles are stale here
@@ -87,11 +89,15 @@ __device__ __forceinline__ int lds_i32(unsigned addr) { int v; asm volatile("ld.
 // with aua = alpha att rc^4, B = aua (n_j.u) / r, C = aua (n_i.u) / r, A1 = (F_r - 2 aua (n_i.u)(n_j.u) / r) / r.
 // n_i is the lane's own director, so its coefficient is summed as ONE scalar (sB) and applied after the loop.
 struct LLConst { float cut, rep8, att4, alpha, alpha_att, one_m_alpha, cutsq; };
+// RECHECK: the entry comes from a hit list built with a skin (or is padding): the reference's own guards decide here
+// (r2 < cutsq && r2 > 1e-5, compute_pairwise_fused.h:109,134), on the current positions.
+template <bool RECHECK>
 __device__ __forceinline__ void ll_eval(const LLConst &k, const float4 *__restrict__ xl, const float4 *__restrict__ nl, F3 xi, F3 mi, int j,
                                         float &fx, float &fy, float &fz, float &tx, float &ty, float &tz, float &sB) {
     const float4 xj = __ldg(xl + j), nj = __ldg(nl + j);
     const float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
     const float r2 = dx * dx + dy * dy + dz * dz;
+    if (RECHECK && !(__float_as_uint(r2) - (__float_as_uint(1e-5f) + 1u) < __float_as_uint(k.cutsq) - (__float_as_uint(1e-5f) + 1u))) return;
     const float rinv = rsqrt_fast(r2);
     const float r = r2 * rinv;
     const float ninj = mi.x * nj.x + mi.y * nj.y + mi.z * nj.z;
@@ -186,65 +192,162 @@ __global__ void k_lipid_runs(int cb, int ce, const int *__restrict__ stencil, co
     lrun_info[c] = nr | done << 6 | own << 19;
 }
 
-// W = candidates per lane and iteration.  Measured on the full RBC (B200): W = 4 with 20 resident blocks 470 us (k_pair_ll: 508);
-// W = 8 505-515 us (longer partial groups, 64 registers); 24 resident blocks at 40 registers 538 us (spills); an L1 prefetch 4-16
-// candidates ahead of the stream changes nothing.
-template <int MINB, int W>
+// ---- hit lists (Verlet lists with a skin) ---------------------------------------------------------------------------------------------------
+// Between two rebuilds the partition, the stencils and the storage order do not change; only the particles move, by ~0.005 per
+// step.  A force evaluation right after a rebuild therefore records, per lipid, every candidate closer than cut + skin (BUILD), and
+// the evaluations up to the next rebuild walk those lists instead of the ~118 candidates per lipid (k_pair_ll_list), re-testing every
+// entry with the reference's exact guards on the current positions.  The lists are a superset of the reference's hits as long as
+// no particle has moved further than skin / 2 since they were built: the integrators record the largest displacement of every
+// step (NlState::disp), k_nl_gate adds them up and orders a fresh build when 2 x (sum of maxima) exceeds the skin.  Same hits,
+// same order of evaluation per lipid: the forces are bit-identical to an evaluation without lists.
+// Layout: groups of 64 consecutive lipid slots, [group][entry][64] (coalesced for the thread-per-lipid readers), `cap` entries.
+struct NlState {                    // one per context, in device memory
+    unsigned disp[64];              // largest squared displacement of a particle in the integration steps since the last gate (float bits)
+    float accum;                    // sum of the per-step maxima since the lists were built
+    int need;                       // 1: this evaluation (re)builds the lists; 0: it walks them
+    int overflow;                   // a list did not fit its row: the next evaluation builds again (and again: no reuse)
+    unsigned builds, reuses;        // statistics
+};
+__global__ void k_nl_gate(NlState *st, int force, int moves, float skin) {
+    const int lane = threadIdx.x;
+    unsigned m = max(st->disp[lane], st->disp[lane + 32]);
+    st->disp[lane] = 0u; st->disp[lane + 32] = 0u;
+    m = __reduce_max_sync(0xffffffffu, m);
+    if (lane == 0) {
+        const float acc = st->accum + (float)moves * (sqrtf(__uint_as_float(m)) * 1.0001f + 1e-4f);   // + the rounding of x + v dt at |x| ~ 1000
+        const int need = (force || st->overflow || !(2.0f * acc <= skin)) ? 1 : 0;
+        st->accum = need ? 0.f : acc;
+        if (need) { st->overflow = 0; st->builds++; } else st->reuses++;
+        st->need = need;
+    }
+}
+// what the integrators call: the largest squared displacement of the step, one RED per warp into 64 slots
+__device__ __forceinline__ void nl_track(unsigned *disp, float d2) {
+    if (!disp) return;
+    const unsigned act = __activemask();
+    const unsigned m = __reduce_max_sync(act, __float_as_uint(d2));
+    if ((threadIdx.x & 31) == __ffs(act) - 1) atomicMax(disp + (blockIdx.x & 63), m);
+}
+
+struct LLList { int *list; int *cnt; int cap; NlState *st; };
+__device__ __forceinline__ size_t ll_row(int i, int cap) { return ((size_t)(i >> 6) * cap) * 64 + (i & 63); }
+
+// W = candidates per lane and iteration.  Measured on the full RBC (B200): W = 4 with 20 resident blocks 470 us; W = 8 505-515 us
+// (longer partial groups, 64 registers); 24 resident blocks at 40 registers 538 us (spills); an L1 prefetch 4-16 candidates ahead
+// of the stream changes nothing.  Round 2 (profiles/r02_*): partners gathered as interleaved 32-byte (x, n) records with one
+// 256-bit load 454 us (no gain: the stalls are load LATENCY in phase 1, 31 % of the samples, not L1 wavefronts); the warp-per-cell
+// tile kernel (pair_tile.cuh) 713 us.
+// BUILD: also record the hit lists (window 0 <= r2 < (cut + skin)^2, exact guards at evaluation).  `gate`/`want`: run only if
+// *gate == want (the list walker and this kernel are launched together on steps without a rebuild; one of them returns at once).
+// The grid may be smaller than the number of 64-lipid groups (grid-stride), so that a gated launch that returns costs nothing.
+template <int MINB, int W, bool BUILD>
 __global__ void __launch_bounds__(kLLBlock, MINB) k_pair_ll_r(PairArgs a, const int2 *__restrict__ lruns, const int *__restrict__ lrun_info,
-                                                               const int *__restrict__ run_if) {
-    if (run_if && *run_if == 0) return;                          // every cell fits the tile: k_pair_ll_t has done this step
+                                                               const int *__restrict__ gate, int want, LLList nl, float skin) {
+    if (gate && *gate != want) return;
     __shared__ int s_q[kLLBlock / 32][kQCap * 32];
     const int lane = threadIdx.x & 31;
     int *const q = s_q[threadIdx.x >> 5] + lane;
-    const int i = a.range[0] + blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = i < a.range[1];
     const float4 *__restrict__ xl = a.xl;
-    const float4 *__restrict__ nl = a.nl;
-    float fx = 0, fy = 0, fz = 0, tx = 0, ty = 0, tz = 0, sB = 0;
-    F3 xi = {0, 0, 0}, mi = {0, 0, 0};
-    const int *st = a.stencil;
+    const float4 *__restrict__ nl_ = a.nl;
     const LLConst kc = {c_ff.cutll, 8.0f * c_ff.repll, 4.0f * c_ff.attll, c_ff.alphall, c_ff.alphall * c_ff.attll, 1.0f - c_ff.alphall, c_ff.cutsqll};
     // r2 > 1e-5 && r2 < cutsq (compute_pairwise_fused.h:109,134) as ONE unsigned comparison of the bit patterns: r2 is a sum of
     // squares (never negative), and non-negative floats order like their bits; a NaN lies above every finite pattern
-    const unsigned lo_bits = __float_as_uint(1e-5f) + 1u, span = __float_as_uint(c_ff.cutsqll) - lo_bits;
-    const int2 *rp = lruns;
-    int nr = 0;
-    if (live) {
-        const float4 xi4 = xl[i], ni4 = nl[i];
-        xi = {xi4.x, xi4.y, xi4.z}; mi = {ni4.x, ni4.y, ni4.z};
-        const int c = a.cell_l[i];
-        st += (size_t)c * kStencilStride;
-        rp += (size_t)c * kRunStride;
-        nr = __ldg(lrun_info + c) & 63;
-    }
+    const float lim = BUILD ? (c_ff.cutll + skin) * (c_ff.cutll + skin) : c_ff.cutsqll;
+    const unsigned lo_bits = BUILD ? 0u : __float_as_uint(1e-5f) + 1u, span = __float_as_uint(lim) - lo_bits;
     const unsigned q0 = (unsigned)__cvta_generic_to_shared(q);
     const unsigned q_full = q0 + (kQCap - W) * 128;              // a group of W always fits below this mark
-    unsigned qp = q0;
-    int2 nx = make_int2(0, 0);                                   // the next run, loaded one advance ahead
-    if (nr > 0) nx = __ldg(rp);
-    int k = 0, cur = 0, rem = 0;
-    for (;;) {
-        if (rem <= 0 && k < nr) { cur = nx.x; rem = nx.y; ++k; if (k < nr) nx = __ldg(rp + k); }
-        if (!__any_sync(0xffffffffu, rem > 0)) break;
-        if (__any_sync(0xffffffffu, qp > q_full)) {              // make room: every lane drains its queue (dense)
-            for (unsigned e = q0; e < qp; e += 128) ll_eval(kc, xl, nl, xi, mi, lds_i32(e), fx, fy, fz, tx, ty, tz, sB);
-            qp = q0;
+    const int l0 = a.range[0], l1 = a.range[1];
+    for (int base = l0 + blockIdx.x * kLLBlock; base < l1; base += gridDim.x * kLLBlock) {
+        const int i = base + threadIdx.x;
+        const bool live = i < l1;
+        float fx = 0, fy = 0, fz = 0, tx = 0, ty = 0, tz = 0, sB = 0;
+        F3 xi = {0, 0, 0}, mi = {0, 0, 0};
+        const int *st = a.stencil;
+        const int2 *rp = lruns;
+        int nr = 0;
+        if (live) {
+            const float4 xi4 = xl[i], ni4 = nl_[i];
+            xi = {xi4.x, xi4.y, xi4.z}; mi = {ni4.x, ni4.y, ni4.z};
+            const int c = a.cell_l[i];
+            st += (size_t)c * kStencilStride;
+            rp += (size_t)c * kRunStride;
+            nr = __ldg(lrun_info + c) & 63;
         }
-        const float4 *__restrict__ p = xl + cur;
-        float4 xj[W];
-        #pragma unroll
-        for (int u = 0; u < W; ++u) xj[u] = __ldg(p + u);
-        #pragma unroll
-        for (int u = 0; u < W; ++u) {
-            const float dx = xi.x - xj[u].x, dy = xi.y - xj[u].y, dz = xi.z - xj[u].z;
-            const float r2 = dx * dx + dy * dy + dz * dz;
-            if (u < rem && __float_as_uint(r2) - lo_bits < span) { sts_i32(qp, cur + u); qp += 128; }
+        int *row = BUILD ? nl.list + ll_row(live ? i : l0, nl.cap) : nullptr;
+        int total = 0;                                           // entries recorded so far (BUILD)
+        unsigned qp = q0;
+        int2 nx = make_int2(0, 0);                               // the next run, loaded one advance ahead
+        if (nr > 0) nx = __ldg(rp);
+        int k = 0, cur = 0, rem = 0;
+        for (;;) {
+            if (rem <= 0 && k < nr) { cur = nx.x; rem = nx.y; ++k; if (k < nr) nx = __ldg(rp + k); }
+            if (!__any_sync(0xffffffffu, rem > 0)) break;
+            if (__any_sync(0xffffffffu, qp > q_full)) {          // make room: every lane drains its queue (dense)
+                for (unsigned e = q0; e < qp; e += 128) {
+                    const int j = lds_i32(e);
+                    if (BUILD) { if (total < nl.cap) row[(size_t)total * 64] = j; ++total; }
+                    ll_eval<BUILD>(kc, xl, nl_, xi, mi, j, fx, fy, fz, tx, ty, tz, sB);
+                }
+                qp = q0;
+            }
+            const float4 *__restrict__ p = xl + cur;
+            float4 xj[W];
+            #pragma unroll
+            for (int u = 0; u < W; ++u) xj[u] = __ldg(p + u);
+            #pragma unroll
+            for (int u = 0; u < W; ++u) {
+                const float dx = xi.x - xj[u].x, dy = xi.y - xj[u].y, dz = xi.z - xj[u].z;
+                const float r2 = dx * dx + dy * dy + dz * dz;
+                if (u < rem && __float_as_uint(r2) - lo_bits < span) { sts_i32(qp, cur + u); qp += 128; }
+            }
+            if (rem > 0) cur += W;
+            rem -= W;
         }
-        if (rem > 0) cur += W;
-        rem -= W;
+        for (unsigned e = q0; e < qp; e += 128) {
+            const int j = lds_i32(e);
+            if (BUILD) { if (total < nl.cap) row[(size_t)total * 64] = j; ++total; }
+            ll_eval<BUILD>(kc, xl, nl_, xi, mi, j, fx, fy, fz, tx, ty, tz, sB);
+        }
+        if (BUILD && live) {
+            nl.cnt[i] = min(total, nl.cap);
+            if (total > nl.cap) atomicExch(&nl.st->overflow, 1);
+        }
+        ll_finish(a, i, live, st, xi, mi, fx, fy, fz, tx, ty, tz, sB);
+        __syncwarp();
     }
-    for (unsigned e = q0; e < qp; e += 128) ll_eval(kc, xl, nl, xi, mi, lds_i32(e), fx, fy, fz, tx, ty, tz, sB);
-    ll_finish(a, i, live, st, xi, mi, fx, fy, fz, tx, ty, tz, sB);
+}
+
+// The list walker: one thread per lipid, entries read coalesced, two partners in flight per lane.  An entry beyond the lane's
+// count is replaced by the lane's own slot (r2 = 0 fails the guards), which keeps the loop free of branches around the loads.
+template <int MINB>
+__global__ void __launch_bounds__(kLLBlock, MINB) k_pair_ll_list(PairArgs a, const int *__restrict__ gate, int want, LLList nl) {
+    if (gate && *gate != want) return;
+    const float4 *__restrict__ xl = a.xl;
+    const float4 *__restrict__ nl_ = a.nl;
+    const LLConst kc = {c_ff.cutll, 8.0f * c_ff.repll, 4.0f * c_ff.attll, c_ff.alphall, c_ff.alphall * c_ff.attll, 1.0f - c_ff.alphall, c_ff.cutsqll};
+    const int l0 = a.range[0], l1 = a.range[1];
+    for (int base = l0 + blockIdx.x * kLLBlock; base < l1; base += gridDim.x * kLLBlock) {
+        const int i = base + threadIdx.x;
+        const bool live = i < l1;
+        float fx = 0, fy = 0, fz = 0, tx = 0, ty = 0, tz = 0, sB = 0;
+        F3 xi = {0, 0, 0}, mi = {0, 0, 0};
+        int cnt = 0;
+        const int self = live ? i : l0;
+        if (live) {
+            const float4 xi4 = xl[i], ni4 = nl_[i];
+            xi = {xi4.x, xi4.y, xi4.z}; mi = {ni4.x, ni4.y, ni4.z};
+            cnt = __ldg(nl.cnt + i);
+        }
+        const int *row = nl.list + ll_row(self, nl.cap);
+        const int maxc = __reduce_max_sync(0xffffffffu, cnt);
+        for (int s = 0; s < maxc; s += 2) {
+            const int j0 = s < cnt ? __ldg(row + (size_t)s * 64) : self;
+            const int j1 = s + 1 < cnt ? __ldg(row + (size_t)(s + 1) * 64) : self;
+            ll_eval<true>(kc, xl, nl_, xi, mi, j0, fx, fy, fz, tx, ty, tz, sB);
+            ll_eval<true>(kc, xl, nl_, xi, mi, j1, fx, fy, fz, tx, ty, tz, sB);
+        }
+        ll_finish(a, i, live, a.stencil + (live ? (size_t)a.cell_l[i] * kStencilStride : 0), xi, mi, fx, fy, fz, tx, ty, tz, sB);
+    }
 }
 
 // ---- proteins -------------------------------------------------------------------------------------------------------------------
@@ -287,9 +390,49 @@ constexpr int kRangeCap = 8;       // stencil slots handled per round
 // survivors into per-lane range lists in shared memory (a lane-level `if (culled) skip` would save nothing on a SIMT machine;
 // the compaction is what turns skipped cells into skipped warp iterations).  Phase 1 walks the r-th surviving range of every
 // lane together, warp-uniform trip counts, predicated bodies.
-template <int LPP>
+struct PLists { int *pl, *pl_cnt, *pp, *pp_cnt; int cap_pl, cap_pp; NlState *st; };   // rows indexed by the THREAD id (porder position), [group of 64][entry][64]
+
+// one protein-lipid pair from the protein's side with the reference's branch structure (compute_pairwise_fused.h:167-176): the
+// protein accumulates in registers, the lipid (if this rank owns it) gets its share by a 16-byte RED
+__device__ __forceinline__ void pl_pair(const PairArgs &a, int type1, float cutsq, float ljcut, F3 xi, F3 mi, int j, float4 xj, int l0, int l1,
+                                        float &fx, float &fy, float &fz, float &tx, float &ty, float &tz) {
+    const F3 d = {xi.x - xj.x, xi.y - xj.y, xi.z - xj.z};          // x_protein - x_lipid (compute_pairwise_fused.h:167)
+    const float r2 = dot3(d, d);
+    if (!(r2 > 1e-5f)) return;
+    if (r2 < cutsq) {
+        const float4 nj = __ldg(a.nl + j);
+        F3 f, q1, q2;
+        poly48(c_ff.cutlp[type1], c_ff.attlp[type1], c_ff.replp[type1], c_ff.alphalp[type1], d, r2, mi, {nj.x, nj.y, nj.z}, f, q1, q2);
+        fx += f.x; fy += f.y; fz += f.z; tx -= q1.x; ty -= q1.y; tz -= q1.z;
+        if (j >= l0 && j < l1) { atomic_add3(a.fl + j, -f.x, -f.y, -f.z); atomic_add3(a.tl + j, -q2.x, -q2.y, -q2.z); }
+    } else if (r2 < ljcut) {
+        const F3 f = lj126(c_ff.lj_lj1[type1], c_ff.lj_lj2[type1], d, r2);
+        fx += f.x; fy += f.y; fz += f.z;
+        if (j >= l0 && j < l1) atomic_add3(a.fl + j, -f.x, -f.y, -f.z);
+    }
+}
+// one protein-protein pair, gathering side only (compute_pairwise_fused.h:196-208)
+__device__ __forceinline__ void pp_pair(int type1, F3 xi, float4 xj, const float *s_cutsqpp, const float *s_ljcutsq, float &fx, float &fy, float &fz) {
+    const F3 d = {xi.x - xj.x, xi.y - xj.y, xi.z - xj.z};
+    const float r2 = dot3(d, d);
+    if (!(r2 > 1e-5f)) return;
+    const int type12 = type1 + __float_as_int(xj.w) * kNType;
+    if (r2 < s_cutsqpp[type12]) {
+        const F3 f = rep8(c_ff.cutpp[type12], c_ff.reppp[type12], d, r2);
+        fx += f.x; fy += f.y; fz += f.z;
+    } else if (r2 < s_ljcutsq[type12]) {
+        const F3 f = lj126(c_ff.lj_lj1[type12], c_ff.lj_lj2[type12], d, r2);
+        fx += f.x; fy += f.y; fz += f.z;
+    }
+}
+
+// BUILD (LPP = 1 only): also record, per protein, every lipid closer than its range + skin and every protein closer than its
+// protein-protein range + skin (the hit lists of k_pair_prot_list, see the lipid kernels above).
+template <int LPP, bool BUILD>
 __global__ void __launch_bounds__(kPBlock, 16) k_pair_prot(PairArgs a, const float4 *__restrict__ lbound, const float4 *__restrict__ pbound, CullTable ct,
-                                                             const int *__restrict__ porder) {
+                                                             const int *__restrict__ porder, const int *__restrict__ gate, int want, PLists nl, float skin) {
+    if (gate && *gate != want) return;
+    static_assert(!BUILD || LPP == 1, "hit lists are recorded by the one-lane-per-protein kernel");
     __shared__ float s_cutsqpp[36], s_ljcutsq[36];
     __shared__ int s_jb[2][kPBlock / 32][kRangeCap * 32];
     __shared__ unsigned short s_len[2][kPBlock / 32][kRangeCap * 32];
@@ -298,11 +441,13 @@ __global__ void __launch_bounds__(kPBlock, 16) k_pair_prot(PairArgs a, const flo
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     int *const ljb = s_jb[0][w] + lane, *const pjb = s_jb[1][w] + lane;
     unsigned short *const llen = s_len[0][w] + lane, *const plen = s_len[1][w] + lane;
-    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n_own = a.range[3] - a.range[2];
+    const int l0 = a.range[0], l1 = a.range[1];                  // lipids of other ranks get their share from the lipid kernel's epilogue over there
+    for (int tid0 = blockIdx.x * kPBlock; tid0 / LPP < n_own; tid0 += gridDim.x * kPBlock) {
+    const int tid = tid0 + threadIdx.x;
     const int pid = tid / LPP, sub = tid % LPP;
-    const bool live = pid < a.range[3] - a.range[2];
+    const bool live = pid < n_own;
     const int i = live ? porder[pid] : 0;
-    const int l0 = a.range[0], l1 = a.range[1];                  // lipids of other ranks get their share from k_pair_lipid<true> over there
     F3 xi = {0, 0, 0}, mi = {0, 0, 0};
     int type1 = 0, n8 = 0, n9 = 0;
     const int *st = a.stencil;
@@ -317,9 +462,15 @@ __global__ void __launch_bounds__(kPBlock, 16) k_pair_prot(PairArgs a, const flo
     }
     // per-type constants in registers (type1 is fixed for the thread)
     const float cutsq = c_ff.cutsqlp[type1], ljcut = c_ff.lj_cutsq[type1];
-    const float cull_l = type1 == 0 ? ct.cut_l[0] : type1 == 1 ? ct.cut_l[1] : type1 == 2 ? ct.cut_l[2] : type1 == 3 ? ct.cut_l[3] : type1 == 4 ? ct.cut_l[4] : ct.cut_l[5];
-    const float cull_p = type1 == 0 ? ct.cut_p[0] : type1 == 1 ? ct.cut_p[1] : type1 == 2 ? ct.cut_p[2] : type1 == 3 ? ct.cut_p[3] : type1 == 4 ? ct.cut_p[4] : ct.cut_p[5];
-    const float testsq_l = fmaxf(cutsq, ljcut);
+    float cull_l = type1 == 0 ? ct.cut_l[0] : type1 == 1 ? ct.cut_l[1] : type1 == 2 ? ct.cut_l[2] : type1 == 3 ? ct.cut_l[3] : type1 == 4 ? ct.cut_l[4] : ct.cut_l[5];
+    float cull_p = type1 == 0 ? ct.cut_p[0] : type1 == 1 ? ct.cut_p[1] : type1 == 2 ? ct.cut_p[2] : type1 == 3 ? ct.cut_p[3] : type1 == 4 ? ct.cut_p[4] : ct.cut_p[5];
+    const bool any_l = cull_l > 0.f, any_p = cull_p > 0.f;       // a type with no interaction at all against lipids / the proteins present
+    // squared test radii: the largest squared cutoff of the type (exactly the table's values), widened by the skin when recording
+    float testsq_l = fmaxf(cutsq, ljcut);
+    float testsq_p = type1 == 0 ? ct.cutsq_p[0] : type1 == 1 ? ct.cutsq_p[1] : type1 == 2 ? ct.cutsq_p[2] : type1 == 3 ? ct.cutsq_p[3] : type1 == 4 ? ct.cutsq_p[4] : ct.cutsq_p[5];
+    if (BUILD) { cull_l += skin; cull_p += skin; testsq_l = cull_l * cull_l * 1.00001f; testsq_p = cull_p * cull_p * 1.00001f; }
+    int *row_l = nullptr, *row_p = nullptr; int rec_l = 0, rec_p = 0;
+    if (BUILD) { row_l = nl.pl + ll_row(tid, nl.cap_pl); row_p = nl.pp + ll_row(tid, nl.cap_pp); }
     float fx = 0, fy = 0, fz = 0, tx = 0, ty = 0, tz = 0;
     const int nmax = __reduce_max_sync(0xffffffffu, n9);
     for (int kb = 0; kb < nmax; kb += kRangeCap * LPP) {
@@ -336,11 +487,11 @@ __global__ void __launch_bounds__(kPBlock, 16) k_pair_prot(PairArgs a, const flo
             int pb = 0, pe = 0, lb = 0, le = 0;
             if (in9) { bp = __ldg(pbound + c2); pb = __ldg(a.cs_p + c2); pe = __ldg(a.cs_p + c2 + 1); }
             if (in8) { bl = __ldg(lbound + c2); lb = __ldg(a.cs_l + c2); le = __ldg(a.cs_l + c2 + 1); }
-            if (in9 && pe > pb && cull_p > 0.f && !culled(bp, xi.x, xi.y, xi.z, cull_p)) { pjb[np_ * 32] = pb; plen[np_ * 32] = (unsigned short)min(pe - pb, 65535); ++np_; }
-            if (in8 && le > lb && cull_l > 0.f && !culled(bl, xi.x, xi.y, xi.z, cull_l)) { ljb[nl_ * 32] = lb; llen[nl_ * 32] = (unsigned short)min(le - lb, 65535); ++nl_; }
+            if (in9 && pe > pb && any_p && !culled(bp, xi.x, xi.y, xi.z, cull_p)) { pjb[np_ * 32] = pb; plen[np_ * 32] = (unsigned short)min(pe - pb, 65535); ++np_; }
+            if (in8 && le > lb && any_l && !culled(bl, xi.x, xi.y, xi.z, cull_l)) { ljb[nl_ * 32] = lb; llen[nl_ * 32] = (unsigned short)min(le - lb, 65535); ++nl_; }
         }
         // ---- protein-lipid: evaluated once, here; the lipid gets its share by atomics (compute_pairwise_fused.h:143-179,278-297) ---
-        // every lane streams through ITS surviving ranges four candidates at a time (same scheme as k_pair_ll)
+        // every lane streams through ITS surviving ranges four candidates at a time (same scheme as k_pair_ll_r)
         {
             int taken = 0, cur = 0, rem = 0;
             for (;;) {
@@ -353,21 +504,11 @@ __global__ void __launch_bounds__(kPBlock, 16) k_pair_prot(PairArgs a, const flo
                 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const float4 xj = xj4[u];
-                    const F3 d = {xi.x - xj.x, xi.y - xj.y, xi.z - xj.z};          // x_protein - x_lipid (compute_pairwise_fused.h:167)
-                    const float r2 = dot3(d, d);
-                    if (u < rem && r2 < testsq_l && r2 > 1e-5f) {
-                        const int j = cur + u;
-                        if (r2 < cutsq) {
-                            const float4 nj = __ldg(a.nl + j);
-                            F3 f, q1, q2;
-                            poly48(c_ff.cutlp[type1], c_ff.attlp[type1], c_ff.replp[type1], c_ff.alphalp[type1], d, r2, mi, {nj.x, nj.y, nj.z}, f, q1, q2);
-                            fx += f.x; fy += f.y; fz += f.z; tx -= q1.x; ty -= q1.y; tz -= q1.z;
-                            if (j >= l0 && j < l1) { atomic_add3(a.fl + j, -f.x, -f.y, -f.z); atomic_add3(a.tl + j, -q2.x, -q2.y, -q2.z); }
-                        } else if (r2 < ljcut) {
-                            const F3 f = lj126(c_ff.lj_lj1[type1], c_ff.lj_lj2[type1], d, r2);
-                            fx += f.x; fy += f.y; fz += f.z;
-                            if (j >= l0 && j < l1) atomic_add3(a.fl + j, -f.x, -f.y, -f.z);
-                        }
+                    const float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
+                    const float r2 = dx * dx + dy * dy + dz * dz;
+                    if (u < rem && r2 < testsq_l) {
+                        if (BUILD) { if (rec_l < nl.cap_pl) row_l[(size_t)rec_l * 64] = cur + u; ++rec_l; }
+                        pl_pair(a, type1, cutsq, ljcut, xi, mi, cur + u, xj, l0, l1, fx, fy, fz, tx, ty, tz);
                     }
                 }
                 if (rem > 0) cur += 4;
@@ -387,17 +528,11 @@ __global__ void __launch_bounds__(kPBlock, 16) k_pair_prot(PairArgs a, const flo
                 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
                     const float4 xj = xj4[u];
-                    const F3 d = {xi.x - xj.x, xi.y - xj.y, xi.z - xj.z};
-                    const float r2 = dot3(d, d);
-                    if (u < rem && r2 > 1e-5f && r2 < cull_p * cull_p) {
-                        const int type12 = type1 + __float_as_int(xj.w) * kNType;
-                        if (r2 < s_cutsqpp[type12]) {
-                            const F3 f = rep8(c_ff.cutpp[type12], c_ff.reppp[type12], d, r2);
-                            fx += f.x; fy += f.y; fz += f.z;
-                        } else if (r2 < s_ljcutsq[type12]) {
-                            const F3 f = lj126(c_ff.lj_lj1[type12], c_ff.lj_lj2[type12], d, r2);
-                            fx += f.x; fy += f.y; fz += f.z;
-                        }
+                    const float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
+                    const float r2 = dx * dx + dy * dy + dz * dz;
+                    if (u < rem && r2 < testsq_p) {
+                        if (BUILD) { if (rec_p < nl.cap_pp) row_p[(size_t)rec_p * 64] = cur + u; ++rec_p; }
+                        pp_pair(type1, xi, xj, s_cutsqpp, s_ljcutsq, fx, fy, fz);
                     }
                 }
                 if (rem > 0) cur += 2;
@@ -405,12 +540,51 @@ __global__ void __launch_bounds__(kPBlock, 16) k_pair_prot(PairArgs a, const flo
             }
         }
     }
+    if (BUILD && live) {
+        nl.pl_cnt[tid] = min(rec_l, nl.cap_pl); nl.pp_cnt[tid] = min(rec_p, nl.cap_pp);
+        if (rec_l > nl.cap_pl || rec_p > nl.cap_pp) atomicExch(&nl.st->overflow, 1);
+    }
     #pragma unroll
     for (int o = 1; o < LPP; o <<= 1) {
         fx += __shfl_xor_sync(0xffffffffu, fx, o); fy += __shfl_xor_sync(0xffffffffu, fy, o); fz += __shfl_xor_sync(0xffffffffu, fz, o);
         tx += __shfl_xor_sync(0xffffffffu, tx, o); ty += __shfl_xor_sync(0xffffffffu, ty, o); tz += __shfl_xor_sync(0xffffffffu, tz, o);
     }
     if (live && sub == 0) {                                      // this lane owns protein i: plain read-modify-write, or plain write
+        float4 f = make_float4(0.f, 0.f, 0.f, 0.f), t = f;
+        if (a.accumulate) { f = a.fp[i]; t = a.tp[i]; }
+        f.x += fx; f.y += fy; f.z += fz; t.x += tx; t.y += ty; t.z += tz;
+        a.fp[i] = f; a.tp[i] = t;
+    }
+    __syncwarp();
+    }
+}
+
+// The list walker of the proteins: one thread per protein (same thread -> protein map), its recorded partners re-tested with the
+// reference's guards on the current positions.  ~1 protein-lipid hit per protein and step on the RBC: a few microseconds.
+__global__ void __launch_bounds__(kPBlock) k_pair_prot_list(PairArgs a, const int *__restrict__ porder, const int *__restrict__ gate, int want, PLists nl) {
+    if (gate && *gate != want) return;
+    __shared__ float s_cutsqpp[36], s_ljcutsq[36];
+    for (int k = threadIdx.x; k < 36; k += blockDim.x) { s_cutsqpp[k] = c_ff.cutsqpp[k]; s_ljcutsq[k] = c_ff.lj_cutsq[k]; }
+    __syncthreads();
+    const int n_own = a.range[3] - a.range[2];
+    const int l0 = a.range[0], l1 = a.range[1];
+    for (int tid = blockIdx.x * kPBlock + threadIdx.x; tid < n_own; tid += gridDim.x * kPBlock) {
+        const int i = porder[tid];
+        const float4 xi4 = a.xp[i], ni4 = a.np[i];
+        const F3 xi = {xi4.x, xi4.y, xi4.z}, mi = {ni4.x, ni4.y, ni4.z};
+        const int type1 = __float_as_int(xi4.w);
+        const float cutsq = c_ff.cutsqlp[type1], ljcut = c_ff.lj_cutsq[type1];
+        float fx = 0, fy = 0, fz = 0, tx = 0, ty = 0, tz = 0;
+        const int nl_ = __ldg(nl.pl_cnt + tid), np_ = __ldg(nl.pp_cnt + tid);
+        const int *row_l = nl.pl + ll_row(tid, nl.cap_pl), *row_p = nl.pp + ll_row(tid, nl.cap_pp);
+        for (int s = 0; s < nl_; ++s) {
+            const int j = __ldg(row_l + (size_t)s * 64);
+            pl_pair(a, type1, cutsq, ljcut, xi, mi, j, __ldg(a.xl + j), l0, l1, fx, fy, fz, tx, ty, tz);
+        }
+        for (int s = 0; s < np_; ++s) {
+            const int j = __ldg(row_p + (size_t)s * 64);
+            pp_pair(type1, xi, __ldg(a.xp + j), s_cutsqpp, s_ljcutsq, fx, fy, fz);
+        }
         float4 f = make_float4(0.f, 0.f, 0.f, 0.f), t = f;
         if (a.accumulate) { f = a.fp[i]; t = a.tp[i]; }
         f.x += fx; f.y += fy; f.z += fz; t.x += tx; t.y += ty; t.z += tz;

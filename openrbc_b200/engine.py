@@ -18,7 +18,7 @@ CLEAR_FORCE, POST_TORQUE, BOUNCE_BACK, VERLET_LANGEVIN, NH_INITIAL_FUSED, NH_FIN
 OPT_MOVE, OPT_FUSED = 9, 10
 STENCIL_STRIDE = 64
 DUMP = dict(centroids=0, cell_start_l=1, cell_start_p=2, cells_l=3, cells_p=4, aff_l=5, aff_p=6, morton_keys=7, morton_perm=8,
-            stencil_counts=9, stencil=10, tag2idx=11, counters=12)
+            stencil_counts=9, stencil=10, tag2idx=11, counters=12, nl_stats=13)
 
 PROF = dict(pair_lipid=0, pair_protein=1, bonded=2, integrate=3, rebuild=4)
 
@@ -278,7 +278,7 @@ class Simulation:
             "cells_l": ((self.size(0),), np.int32), "cells_p": ((self.size(1),), np.int32),
             "aff_l": ((self.size(0),), np.int32), "aff_p": ((self.size(1),), np.int32),
             "morton_keys": ((nc,), np.uint32), "morton_perm": ((nc,), np.int32), "stencil_counts": ((nc, 3), np.int32),
-            "stencil": ((nc, STENCIL_STRIDE), np.int32), "counters": ((8,), np.uint64),
+            "stencil": ((nc, STENCIL_STRIDE), np.int32), "counters": ((8,), np.uint64), "nl_stats": ((4,), np.uint32),
         }[what]
         out = np.empty(shape, dt)
         self._ck(self.lib.orbc_debug_dump(self.ctx, DUMP[what], _p(out), out.nbytes))

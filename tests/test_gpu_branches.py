@@ -120,16 +120,19 @@ def test_unfused_nose_hoover_and_walls():
     sim.box = (-float(g["nhi_box"]), float(g["nhi_box"]))
     sim.nh_initial_fused()
     assert abs(sim.zeta - float(g["nhi_zeta"])) <= 1e-6 * abs(float(g["nhi_zeta"]))
+    reflected = 0
     for s, p in ((0, "l"), (1, "p")):
         d = sim.download(s, "xvnoft")
         for f in "xvno":
             assert rel_err(d[f], g[f"nhi_{p}{f}"]) < X_TOL, (p, f)
         assert not d["f"].any() and not d["t"].any()
-        # the reflected components themselves
+        # the reflected components themselves (lipids of the six caps; the proteins were all folded inside by the first box)
         out = np.abs(g[f"bb_{p}x"]) > float(g["nhi_box"]) + 0.01
-        assert out.sum() > 5
-        assert np.abs(d["x"][out] - g[f"nhi_{p}x"][out]).max() < 2e-5 and (np.abs(d["x"][out]) <= float(g["nhi_box"])).all()
-        assert (np.sign(d["v"][out]) == np.sign(g[f"nhi_{p}v"][out])).all()
+        reflected += int(out.sum())
+        if out.any():
+            assert np.abs(d["x"][out] - g[f"nhi_{p}x"][out]).max() < 2e-5 and (np.abs(d["x"][out]) <= float(g["nhi_box"])).all()
+            assert (np.sign(d["v"][out]) == np.sign(g[f"nhi_{p}v"][out])).all()
+    assert reflected > 20
     sim.close()
 
 

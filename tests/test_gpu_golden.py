@@ -152,7 +152,7 @@ def test_tile_kernel_against_the_run_list_kernel(name):
     g = load(name)
     st = state_of(g, "in")
     out = {}
-    for key, opts in (("tile", {}), ("runs", {"ll_variant": 1}), ("overflow", {"debug_tile_cap": 48})):
+    for key, opts in (("tile", {"ll_variant": 0}), ("runs", {"ll_variant": 1}), ("records", {"ll_variant": 2}), ("overflow", {"ll_variant": 0, "debug_tile_cap": 48})):
         sim = Simulation(st, kBT=0.0)
         for k, v in opts.items():
             sim.set_option(k, v)
@@ -167,12 +167,13 @@ def test_tile_kernel_against_the_run_list_kernel(name):
     exact = len(st["px"]) == 0            # protein -> lipid reactions arrive by atomics: their order is not fixed
     for k in "ft":
         assert rel_err(out["tile"][k], out["runs"][k]) < 2e-6
-        if exact:
-            np.testing.assert_array_equal(out["overflow"][k], out["runs"][k])
-        else:
-            assert rel_err(out["overflow"][k], out["runs"][k]) < 1e-6
+        for other in ("overflow", "records"):                # same kernel structure, same order of the sums
+            if exact:
+                np.testing.assert_array_equal(out[other][k], out["runs"][k])
+            else:
+                assert rel_err(out[other][k], out["runs"][k]) < 1e-6
     # the tile kernel is deterministic: two fresh contexts give the same bits
     if exact:
-        sim = Simulation(st, kBT=0.0); sim.compute_pairwise_fused()
+        sim = Simulation(st, kBT=0.0); sim.set_option("ll_variant", 0); sim.compute_pairwise_fused()
         np.testing.assert_array_equal(sim.get(0, "f"), out["tile"]["f"])
         sim.close()

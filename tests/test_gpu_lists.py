@@ -1,0 +1,82 @@
+"""Hit lists with a skin (openrbc_b200/csrc/pair_queue.cuh): the force evaluation after a rebuild records, per particle, every candidate
+closer than cut + skin; the evaluations up to the next rebuild walk those lists and re-test every entry with the reference's exact
+guards.  The reference has no such lists (it searches the centroid stencils at every step, compute_pairwise_fused.h:238-320): the
+lists must not change a single hit.  Checked here: trajectories with and without lists are equal (bit for bit where no atomics are
+involved), the lists are really used, and a skin that is too thin for the step is caught by the displacement bound."""
+import os
+
+import numpy as np
+import pytest
+
+from tests.common import GOLDEN, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def load(name):
+    g = dict(np.load(os.path.join(GOLDEN, name + ".npz")))
+    return {k[3:]: v for k, v in g.items() if k.startswith("in_")}
+
+
+def run(st, steps, **opts):
+    from openrbc_b200 import Simulation
+    sim = Simulation(st, kBT=0.22, seed=4242)
+    for k, v in opts.items():
+        sim.set_option(k, v)
+    sim.run_langevin(steps)
+    out = [sim.download(s, "xvno") for s in (0, 1)]
+    stats = sim.dump("nl_stats")
+    sim.close()
+    return out, stats
+
+
+@pytest.mark.parametrize("name", ["sphere_r12", "vesicle_ico0", "branches_vesicle_ico0"])
+def test_lists_do_not_change_the_trajectory(name):
+    st = load(name)
+    exact = len(st["px"]) == 0                 # protein -> lipid reactions arrive by atomics: their order is not fixed
+    steps = 10                                 # rebuild every 2nd step: five builds, five walks
+    ref, s0 = run(st, steps, nl_reuse=0)
+    assert s0[0] == 0 and s0[1] == 0
+    got, s1 = run(st, steps, nl_reuse=1)
+    if name != "branches_vesicle_ico0":       # (that fixture's hand-placed proteins are shot away fast enough to outrun the skin)
+        assert s1[0] == steps // 2 and s1[1] == steps // 2 and s1[2] == 0, s1
+    assert s1[0] + s1[1] == steps and s1[1] > 0
+    for s in (0, 1):
+        for f in "xvno":
+            if exact:
+                np.testing.assert_array_equal(got[s][f], ref[s][f], err_msg=f)
+            else:
+                assert rel_err(got[s][f], ref[s][f]) < 1e-5, (s, f)
+    # a skin thinner than twice the largest step: the gate must order a build at every evaluation, and nothing changes
+    thin, s2 = run(st, steps, nl_reuse=1, nl_skin=1e-4)
+    assert s2[0] == steps and s2[1] == 0, s2
+    for s in (0, 1):
+        for f in "xvno":
+            if exact:
+                np.testing.assert_array_equal(thin[s][f], ref[s][f], err_msg=f)
+            else:
+                assert rel_err(thin[s][f], ref[s][f]) < 1e-5, (s, f)
+
+
+def test_lists_call_by_call_and_forces():
+    """The call-by-call API: rebuild -> forces (build) -> integrate -> forces (walk); the walked forces equal a fresh search's."""
+    from openrbc_b200 import Simulation
+    st = load("vesicle_ico0")
+    a, b = Simulation(st, kBT=0.0), Simulation(st, kBT=0.0)
+    b.set_option("nl_reuse", 0)
+    for sim in (a, b):
+        sim.nstep = 24
+        sim.rebuild(); sim.compute_pairwise_fused(); sim.compute_bonded(); sim.verlet_langevin()
+        sim.compute_pairwise_fused()
+    assert list(a.dump("nl_stats")[:2]) == [1, 1]
+    for s in (0, 1):
+        da, db = a.download(s, "ft"), b.download(s, "ft")
+        assert rel_err(da["f"], db["f"]) < 1e-6 and rel_err(da["t"], db["t"]) < 1e-6
+    # a position overwritten by the host invalidates the lists
+    x = a.get(0, "x"); x[5] += 0.3
+    a.set_field(0, "x", x); b.set_field(0, "x", x)
+    for sim in (a, b):
+        sim.clear_force(); sim.compute_pairwise_fused()
+    assert list(a.dump("nl_stats")[:2]) == [2, 1]
+    assert rel_err(a.get(0, "f"), b.get(0, "f")) < 1e-6
+    a.close(); b.close()

@@ -15,6 +15,7 @@ workload = sys.argv[1] if len(sys.argv) > 1 else "rbc"
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
 st = bench.load_state(workload)
 sim = orbc.Simulation(st, kBT=0.22)
+sim.set_option("nl_reuse", 0)       # per-call timings of the searching kernels (tools/ll_bench.py times the hit lists)
 sim.run_langevin(4)
 
 
@@ -64,14 +65,6 @@ timeit("compute_temperature", sim.compute_temperature)
 sim.nstep = 0
 timeit("run_langevin(2)", lambda: sim.run_langevin(2))
 sim.set_option("pair_impl", 2)
-for var in (1, 0):
-    sim.set_option("ll_variant", var)
-    sim.clear_force(); sim.compute_pairwise_fused(); sim.synchronize()
-    sim.profile_enable(True)
-    for _ in range(reps):
-        sim.compute_pairwise_fused()
-    print(f"ll_variant {var} ({'run-list, thread per lipid' if var else 'tile, warp per cell'}): pair_lipid {sim.profile_read('pair_lipid')[0] / reps * 1e3:.1f} us")
-    sim.profile_enable(False)
 for lanes in (1, 2, 4):
     sim.set_option("prot_lanes", lanes)
     for frac in (1.0, 0.125):
@@ -95,14 +88,3 @@ for frac in (1.0, 0.5, 0.25, 0.125):
     print(f"owned fraction {frac}: " + "  ".join(f"{k} {sim.profile_read(k)[0] / reps * 1e3:.1f} us" for k in ("pair_lipid", "pair_protein")))
     sim.profile_enable(False)
 sim.set_option("debug_owned_fraction", 1.0)
-# per-kernel event timings of the production loop (in-process launch list)
-for var in (1, 0):
-    sim.set_option("ll_variant", var)
-    sim.run_langevin(4); sim.synchronize()
-    sim.profile_kernels(True)
-    sim.run_langevin(8)
-    rep = sim.kernel_report()
-    sim.profile_kernels(False)
-    print(f"ll_variant {var}: kernel time {sum(r[2] for r in rep) / 8:.0f} us/step")
-    for name, n, us in rep[:12]:
-        print(f"   {name:34s} {n:4d} launches {us / n:8.1f} us mean")

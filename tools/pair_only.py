@@ -1,5 +1,5 @@
 """Minimal driver for ncu captures: load a state, advance a few steps, then N force evaluations.
-    python tools/pair_only.py [workload] [n] [pair_impl]"""
+    python tools/pair_only.py [workload] [n] [pair_impl] [ll_variant]"""
 import os
 import sys
 
@@ -13,6 +13,8 @@ n = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 sim = orbc.Simulation(bench.load_state(workload), kBT=0.22)
 if len(sys.argv) > 3:
     sim.set_option("pair_impl", int(sys.argv[3]))
+if len(sys.argv) > 4:
+    sim.set_option("ll_variant", int(sys.argv[4]))
 sim.run_langevin(4)
 for _ in range(n):
     sim.compute_pairwise_fused()
