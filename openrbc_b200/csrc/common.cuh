@@ -161,11 +161,12 @@ struct orbc_ctx {
     // hit lists with a skin (pair_queue.cuh): recorded by the force evaluation after a rebuild, walked until the next one
     bool nl_on = true, nl_valid = false;           // option "nl_reuse"; lists match the current partition and were built (host's view)
     float nl_skin = 0.1f;                          // option "nl_skin"
+    int ll_list_blocks = 16;                       // resident blocks per SM the list walker is compiled for (register budget)
     int nl_moves = 0;                              // tracked integration steps since the last gate
     void *nl_state = nullptr;                      // orbc::NlState on the device
     int *ll_list = nullptr, *ll_cnt = nullptr; size_t ll_list_lipids = 0;
     int *pl_list = nullptr, *pl_cnt = nullptr, *pp_list = nullptr, *pp_cnt = nullptr; size_t pl_list_proteins = 0;
-    int nl_cap_ll = 64, nl_cap_pl = 48, nl_cap_pp = 16;   // entries per lipid / per protein (lipid partners, protein partners)
+    int nl_cap_ll = 96, nl_cap_pl = 64, nl_cap_pp = 32;   // entries per lipid / per protein (lipid partners, protein partners)
     int prot_lanes = 0;                            // lanes per protein in k_pair_prot (0 = by the number of owned proteins)
     int *d_range = nullptr;                               // {l0, l1, p0, p1}: particle slots this context computes (all of them on one GPU)
     // volume constraint inside the whole-loop entry points (openrbc.cpp:229)

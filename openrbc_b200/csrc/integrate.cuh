@@ -122,40 +122,44 @@ __global__ void k_bounce_back(IntegArgs a) {
 // integrate_langevin.h:99-149 — one pass: torque -> omega -> director, noise, friction, kick, drift, clear f and t
 __global__ void __launch_bounds__(256) k_verlet_langevin(IntegArgs a) {
     const size_t i = (size_t)a.range[0] + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (size_t)a.range[1]) return;
-    float4 x = a.x[i], v = a.v[i], n4 = a.nn[i], o = a.o[i];
-    const float4 f = a.f[i], t = a.t[i];
-    const int type = __float_as_int(x.w);
-    const F3 tq = cross3({n4.x, n4.y, n4.z}, {t.x, t.y, t.z});
-    o.x += a.dt * tq.x; o.y += a.dt * tq.y; o.z += a.dt * tq.z;
-    const F3 nn = rotate_director({n4.x, n4.y, n4.z}, {o.x, o.y, o.z}, a.dt);
-    F3 r = {0.f, 0.f, 0.f};
-    if (a.noise) r = {a.noise[3 * i], a.noise[3 * i + 1], a.noise[3 * i + 2]};
-    else if (a.sigma[type] != 0.f) r = noise3(a.seed, a.step, a.species, (uint32_t)i);
-    const float g = a.gamma[type], s = a.sigma[type];
-    const float fx = f.x - (g * v.x + s * r.x), fy = f.y - (g * v.y + s * r.y), fz = f.z - (g * v.z + s * r.z);
-    const float k = a.dt / c_ff.mass[type];
-    v.x += fx * k; v.y += fy * k; v.z += fz * k;
-    x.x += v.x * a.dt; x.y += v.y * a.dt; x.z += v.z * a.dt;
-    nl_track(a.disp, (v.x * v.x + v.y * v.y + v.z * v.z) * (a.dt * a.dt));
-    a.x_out[i] = x; a.v[i] = v; a.o[i] = o;
-    const float4 nnew = make_float4(nn.x, nn.y, nn.z, n4.w);
-    a.nn_out[i] = nnew;
-    if (a.clear) { a.f[i] = make_float4(0, 0, 0, 0); a.t[i] = make_float4(0, 0, 0, 0); }
-    if (a.push.world > 1) {
-        unsigned m = a.push.cell_mask[a.push.cellid[i]];
-        if (a.push.pmask) m |= a.push.pmask[i];
-        while (m) {
-            const int r = __ffs(m) - 1; m &= m - 1;
-            a.push.x[r][i] = x; a.push.nn[r][i] = nnew;
+    float d2 = 0.f;
+    if (i < (size_t)a.range[1]) {
+        float4 x = a.x[i], v = a.v[i], n4 = a.nn[i], o = a.o[i];
+        const float4 f = a.f[i], t = a.t[i];
+        const int type = __float_as_int(x.w);
+        const F3 tq = cross3({n4.x, n4.y, n4.z}, {t.x, t.y, t.z});
+        o.x += a.dt * tq.x; o.y += a.dt * tq.y; o.z += a.dt * tq.z;
+        const F3 nn = rotate_director({n4.x, n4.y, n4.z}, {o.x, o.y, o.z}, a.dt);
+        F3 r = {0.f, 0.f, 0.f};
+        if (a.noise) r = {a.noise[3 * i], a.noise[3 * i + 1], a.noise[3 * i + 2]};
+        else if (a.sigma[type] != 0.f) r = noise3(a.seed, a.step, a.species, (uint32_t)i);
+        const float g = a.gamma[type], s = a.sigma[type];
+        const float fx = f.x - (g * v.x + s * r.x), fy = f.y - (g * v.y + s * r.y), fz = f.z - (g * v.z + s * r.z);
+        const float k = a.dt / c_ff.mass[type];
+        v.x += fx * k; v.y += fy * k; v.z += fz * k;
+        x.x += v.x * a.dt; x.y += v.y * a.dt; x.z += v.z * a.dt;
+        d2 = (v.x * v.x + v.y * v.y + v.z * v.z) * (a.dt * a.dt);
+        a.x_out[i] = x; a.v[i] = v; a.o[i] = o;
+        const float4 nnew = make_float4(nn.x, nn.y, nn.z, n4.w);
+        a.nn_out[i] = nnew;
+        if (a.clear) { a.f[i] = make_float4(0, 0, 0, 0); a.t[i] = make_float4(0, 0, 0, 0); }
+        if (a.push.world > 1) {
+            unsigned m = a.push.cell_mask[a.push.cellid[i]];
+            if (a.push.pmask) m |= a.push.pmask[i];
+            while (m) {
+                const int r = __ffs(m) - 1; m &= m - 1;
+                a.push.x[r][i] = x; a.push.nn[r][i] = nnew;
+            }
         }
     }
+    nl_track(a.disp, d2);
 }
 
 // integrate_nh.h:178-235 (operator()) — half kick with 1/(1 + dt zeta / 2), drift, bounce-back, KE, omega half kick, director, clear
 __global__ void __launch_bounds__(256) k_nh_initial_fused(IntegArgs a) {
     const size_t i = (size_t)a.range[0] + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     double ke = 0.0;
+    float d2 = 0.f;
     if (i < (size_t)a.range[1]) {
         const float zeta = a.zeta_dev ? a.zeta_dev[0] : a.zeta;
         const float gamma = 1.0f / (1.0f + 0.5f * a.dt * zeta);
@@ -167,7 +171,7 @@ __global__ void __launch_bounds__(256) k_nh_initial_fused(IntegArgs a) {
         v.x = (v.x + s * f.x) * gamma; v.y = (v.y + s * f.y) * gamma; v.z = (v.z + s * f.z) * gamma;
         x.x += v.x * a.dt; x.y += v.y * a.dt; x.z += v.z * a.dt;
         bounce(x.x, v.x, a.dlo, a.dhi); bounce(x.y, v.y, a.dlo, a.dhi); bounce(x.z, v.z, a.dlo, a.dhi);   // a reflection never lengthens the step
-        nl_track(a.disp, (v.x * v.x + v.y * v.y + v.z * v.z) * (a.dt * a.dt));
+        d2 = (v.x * v.x + v.y * v.y + v.z * v.z) * (a.dt * a.dt);
         ke = 0.5f * m * (v.x * v.x + v.y * v.y + v.z * v.z);
         const float so = 0.5f * a.dt;
         o.x += so * t.x; o.y += so * t.y; o.z += so * t.z;
@@ -185,6 +189,7 @@ __global__ void __launch_bounds__(256) k_nh_initial_fused(IntegArgs a) {
             }
         }
     }
+    nl_track(a.disp, d2);
     block_add_double(ke, a.acc);
 }
 

@@ -357,7 +357,9 @@ int launch_pairwise(orbc_ctx *c, bool accumulate = true) {
                 if (host_build)                                  // right after a rebuild: record the lists while evaluating
                     ORBC_LAUNCH(c, (k_pair_ll_r<20, 4, true>), blocks_for(nl_count, kLLBlock), kLLBlock, 0, a, c->lruns, c->lrun_cnt, (const int *)nullptr, 0, ll, c->nl_skin);
                 else {                                           // walk the lists; the gate orders a fresh build only if a particle outran the skin
-                    ORBC_LAUNCH(c, (k_pair_ll_list<20>), blocks_for(nl_count, kLLBlock), kLLBlock, 0, a, &nls->need, 0, ll);
+                    if (c->ll_list_blocks == 12) ORBC_LAUNCH(c, (k_pair_ll_list<12>), blocks_for(nl_count, kLLBlock), kLLBlock, 0, a, &nls->need, 0, ll);
+                    else if (c->ll_list_blocks == 20) ORBC_LAUNCH(c, (k_pair_ll_list<20>), blocks_for(nl_count, kLLBlock), kLLBlock, 0, a, &nls->need, 0, ll);
+                    else ORBC_LAUNCH(c, (k_pair_ll_list<16>), blocks_for(nl_count, kLLBlock), kLLBlock, 0, a, &nls->need, 0, ll);
                     ORBC_LAUNCH(c, (k_pair_ll_r<20, 4, true>), kSmallGrid, kLLBlock, 0, a, c->lruns, c->lrun_cnt, &nls->need, 1, ll, c->nl_skin);
                 }
             }
@@ -708,6 +710,7 @@ int orbc_set_option(orbc_ctx *c, const char *name, double value) { if (c) cudaSe
         if (value != 0 && value != 1) return fail(ORBC_ERR_ARG, "ll_variant must be 1 (run-list kernel + hit lists) or 0 (tile kernel)");
         c->ll_variant = (int)value; c->nl_valid = false; return ORBC_OK;
     }
+    if (!strcmp(name, "ll_list_blocks")) { c->ll_list_blocks = (int)value; return ORBC_OK; }   // tuning: resident blocks per SM of the list walker (12, 16, 20)
     if (!strcmp(name, "nl_reuse")) { c->nl_on = value != 0; c->nl_valid = false; return ORBC_OK; }   // hit lists between rebuilds on / off
     if (!strcmp(name, "nl_skin")) {
         if (!(value >= 0.0 && value <= 1.0)) return fail(ORBC_ERR_ARG, "nl_skin must be in [0, 1]");

@@ -92,28 +92,34 @@ struct LLConst { float cut, rep8, att4, alpha, alpha_att, one_m_alpha, cutsq; };
 // RECHECK: the entry comes from a hit list built with a skin (or is padding): the reference's own guards decide here
 // (r2 < cutsq && r2 > 1e-5, compute_pairwise_fused.h:109,134), on the current positions.
 template <bool RECHECK>
-__device__ __forceinline__ void ll_eval(const LLConst &k, const float4 *__restrict__ xl, const float4 *__restrict__ nl, F3 xi, F3 mi, int j,
+__device__ __forceinline__ void ll_pair(const LLConst &k, F3 xi, F3 mi, float4 xj, float4 nj,
                                         float &fx, float &fy, float &fz, float &tx, float &ty, float &tz, float &sB) {
-    const float4 xj = __ldg(xl + j), nj = __ldg(nl + j);
+    // (explicit fmaf / __fmul_rn everywhere: the searching kernel, the recording kernel and the list walker must round alike, so
+    //  that walking a list gives the very bits a search would)
     const float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
-    const float r2 = dx * dx + dy * dy + dz * dz;
+    const float r2 = fmaf(dz, dz, fmaf(dy, dy, __fmul_rn(dx, dx)));
     if (RECHECK && !(__float_as_uint(r2) - (__float_as_uint(1e-5f) + 1u) < __float_as_uint(k.cutsq) - (__float_as_uint(1e-5f) + 1u))) return;
     const float rinv = rsqrt_fast(r2);
-    const float r = r2 * rinv;
-    const float ninj = mi.x * nj.x + mi.y * nj.y + mi.z * nj.z;
-    const float niu = (mi.x * dx + mi.y * dy + mi.z * dz) * rinv;
-    const float nju = (nj.x * dx + nj.y * dy + nj.z * dz) * rinv;
+    const float r = __fmul_rn(r2, rinv);
+    const float ninj = fmaf(mi.z, nj.z, fmaf(mi.y, nj.y, __fmul_rn(mi.x, nj.x)));
+    const float niu = __fmul_rn(fmaf(mi.z, dz, fmaf(mi.y, dy, __fmul_rn(mi.x, dx))), rinv);
+    const float nju = __fmul_rn(fmaf(nj.z, dz, fmaf(nj.y, dy, __fmul_rn(nj.x, dx))), rinv);
     const float A = fmaf(k.alpha, fmaf(-niu, nju, ninj), k.one_m_alpha);   // 1 + alpha (a - 1)
-    const float rc = k.cut - r;
-    const float rc2 = rc * rc, rc3 = rc2 * rc, rc4 = rc2 * rc2;
-    const float fra = fmaf(k.rep8, rc3 * rc4, k.att4 * (A * rc3));         // 8 rep rc^7 + 4 A att rc^3
-    const float aua = k.alpha_att * rc4;                                    // alpha * att * rc^4
-    const float auar = aua * rinv;
-    const float B = auar * nju, C = auar * niu;
-    const float A1 = fmaf(-2.0f * C, nju, fra) * rinv;
+    const float rc = __fsub_rn(k.cut, r);
+    const float rc2 = __fmul_rn(rc, rc), rc3 = __fmul_rn(rc2, rc), rc4 = __fmul_rn(rc2, rc2);
+    const float fra = fmaf(k.rep8, __fmul_rn(rc3, rc4), __fmul_rn(k.att4, __fmul_rn(A, rc3)));   // 8 rep rc^7 + 4 A att rc^3
+    const float aua = __fmul_rn(k.alpha_att, rc4);                          // alpha * att * rc^4
+    const float auar = __fmul_rn(aua, rinv);
+    const float B = __fmul_rn(auar, nju), C = __fmul_rn(auar, niu);
+    const float A1 = __fmul_rn(fmaf(__fmul_rn(-2.0f, C), nju, fra), rinv);
     fx = fmaf(A1, dx, fmaf(C, nj.x, fx)); fy = fmaf(A1, dy, fmaf(C, nj.y, fy)); fz = fmaf(A1, dz, fmaf(C, nj.z, fz));
     tx = fmaf(B, dx, fmaf(-aua, nj.x, tx)); ty = fmaf(B, dy, fmaf(-aua, nj.y, ty)); tz = fmaf(B, dz, fmaf(-aua, nj.z, tz));
-    sB += B;
+    sB = __fadd_rn(sB, B);
+}
+template <bool RECHECK>
+__device__ __forceinline__ void ll_eval(const LLConst &k, const float4 *__restrict__ xl, const float4 *__restrict__ nl, F3 xi, F3 mi, int j,
+                                        float &fx, float &fy, float &fz, float &tx, float &ty, float &tz, float &sB) {
+    ll_pair<RECHECK>(k, xi, mi, __ldg(xl + j), __ldg(nl + j), fx, fy, fz, tx, ty, tz, sB);
 }
 
 // Common tail of the lipid kernels: the n_i component of the force, (decomposed runs) the lipid side of the protein-lipid pairs
@@ -221,12 +227,17 @@ __global__ void k_nl_gate(NlState *st, int force, int moves, float skin) {
         st->need = need;
     }
 }
-// what the integrators call: the largest squared displacement of the step, one RED per warp into 64 slots
+// what the integrators call, with EVERY thread of the block (d2 = 0 for idle ones): the largest squared displacement of the step,
+// one RED per block into 64 slots (one per warp cost 11 us per launch on the RBC)
 __device__ __forceinline__ void nl_track(unsigned *disp, float d2) {
-    if (!disp) return;
-    const unsigned act = __activemask();
-    const unsigned m = __reduce_max_sync(act, __float_as_uint(d2));
-    if ((threadIdx.x & 31) == __ffs(act) - 1) atomicMax(disp + (blockIdx.x & 63), m);
+    if (!disp) return;                                           // (uniform: a kernel argument)
+    __shared__ unsigned s_max;
+    if (threadIdx.x == 0) s_max = 0u;
+    __syncthreads();
+    const unsigned m = __reduce_max_sync(0xffffffffu, __float_as_uint(d2));
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(&s_max, m);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_max) atomicMax(disp + (blockIdx.x & 63), s_max);
 }
 
 struct LLList { int *list; int *cnt; int cap; NlState *st; };
@@ -273,8 +284,9 @@ __global__ void __launch_bounds__(kLLBlock, MINB) k_pair_ll_r(PairArgs a, const 
             rp += (size_t)c * kRunStride;
             nr = __ldg(lrun_info + c) & 63;
         }
-        int *row = BUILD ? nl.list + ll_row(live ? i : l0, nl.cap) : nullptr;
-        int total = 0;                                           // entries recorded so far (BUILD)
+        const int self = live ? i : l0;
+        int *row = BUILD ? nl.list + ll_row(self, nl.cap) : nullptr;
+        int total = 0;                                           // entries recorded so far (BUILD): the same number in every lane of the warp
         unsigned qp = q0;
         int2 nx = make_int2(0, 0);                               // the next run, loaded one advance ahead
         if (nr > 0) nx = __ldg(rp);
@@ -283,11 +295,18 @@ __global__ void __launch_bounds__(kLLBlock, MINB) k_pair_ll_r(PairArgs a, const 
             if (rem <= 0 && k < nr) { cur = nx.x; rem = nx.y; ++k; if (k < nr) nx = __ldg(rp + k); }
             if (!__any_sync(0xffffffffu, rem > 0)) break;
             if (__any_sync(0xffffffffu, qp > q_full)) {          // make room: every lane drains its queue (dense)
-                for (unsigned e = q0; e < qp; e += 128) {
-                    const int j = lds_i32(e);
-                    if (BUILD) { if (total < nl.cap) row[(size_t)total * 64] = j; ++total; }
-                    ll_eval<BUILD>(kc, xl, nl_, xi, mi, j, fx, fy, fz, tx, ty, tz, sB);
-                }
+                if (BUILD) {
+                    // recording: the warp's lanes write the same row index (the longest queue decides, shorter ones are padded with
+                    // the lane's own slot, which fails the guards): one coalesced 128-byte store per entry instead of 32 sectors
+                    const unsigned len = __reduce_max_sync(0xffffffffu, qp - q0);
+                    for (unsigned off = 0; off < len; off += 128) {
+                        const int j = off < qp - q0 ? lds_i32(q0 + off) : self;
+                        if (live && total < nl.cap) row[(size_t)total * 64] = j;
+                        ++total;
+                        ll_eval<true>(kc, xl, nl_, xi, mi, j, fx, fy, fz, tx, ty, tz, sB);
+                    }
+                } else
+                    for (unsigned e = q0; e < qp; e += 128) ll_eval<false>(kc, xl, nl_, xi, mi, lds_i32(e), fx, fy, fz, tx, ty, tz, sB);
                 qp = q0;
             }
             const float4 *__restrict__ p = xl + cur;
@@ -303,11 +322,16 @@ __global__ void __launch_bounds__(kLLBlock, MINB) k_pair_ll_r(PairArgs a, const 
             if (rem > 0) cur += W;
             rem -= W;
         }
-        for (unsigned e = q0; e < qp; e += 128) {
-            const int j = lds_i32(e);
-            if (BUILD) { if (total < nl.cap) row[(size_t)total * 64] = j; ++total; }
-            ll_eval<BUILD>(kc, xl, nl_, xi, mi, j, fx, fy, fz, tx, ty, tz, sB);
-        }
+        if (BUILD) {
+            const unsigned len = __reduce_max_sync(0xffffffffu, qp - q0);
+            for (unsigned off = 0; off < len; off += 128) {
+                const int j = off < qp - q0 ? lds_i32(q0 + off) : self;
+                if (live && total < nl.cap) row[(size_t)total * 64] = j;
+                ++total;
+                ll_eval<true>(kc, xl, nl_, xi, mi, j, fx, fy, fz, tx, ty, tz, sB);
+            }
+        } else
+            for (unsigned e = q0; e < qp; e += 128) ll_eval<false>(kc, xl, nl_, xi, mi, lds_i32(e), fx, fy, fz, tx, ty, tz, sB);
         if (BUILD && live) {
             nl.cnt[i] = min(total, nl.cap);
             if (total > nl.cap) atomicExch(&nl.st->overflow, 1);
@@ -340,11 +364,14 @@ __global__ void __launch_bounds__(kLLBlock, MINB) k_pair_ll_list(PairArgs a, con
         }
         const int *row = nl.list + ll_row(self, nl.cap);
         const int maxc = __reduce_max_sync(0xffffffffu, cnt);
-        for (int s = 0; s < maxc; s += 2) {
-            const int j0 = s < cnt ? __ldg(row + (size_t)s * 64) : self;
-            const int j1 = s + 1 < cnt ? __ldg(row + (size_t)(s + 1) * 64) : self;
-            ll_eval<true>(kc, xl, nl_, xi, mi, j0, fx, fy, fz, tx, ty, tz, sB);
-            ll_eval<true>(kc, xl, nl_, xi, mi, j1, fx, fy, fz, tx, ty, tz, sB);
+        for (int s = 0; s < maxc; s += 4) {
+            int j[4]; float4 xj[4], nj[4];
+            #pragma unroll
+            for (int u = 0; u < 4; ++u) j[u] = s + u < cnt ? __ldg(row + (size_t)(s + u) * 64) : self;
+            #pragma unroll
+            for (int u = 0; u < 4; ++u) { xj[u] = __ldg(xl + j[u]); nj[u] = __ldg(nl_ + j[u]); }   // eight gathers in flight per lane
+            #pragma unroll
+            for (int u = 0; u < 4; ++u) ll_pair<true>(kc, xi, mi, xj[u], nj[u], fx, fy, fz, tx, ty, tz, sB);
         }
         ll_finish(a, i, live, a.stencil + (live ? (size_t)a.cell_l[i] * kStencilStride : 0), xi, mi, fx, fy, fz, tx, ty, tz, sB);
     }
@@ -433,10 +460,14 @@ __global__ void __launch_bounds__(kPBlock, 16) k_pair_prot(PairArgs a, const flo
                                                              const int *__restrict__ porder, const int *__restrict__ gate, int want, PLists nl, float skin) {
     if (gate && *gate != want) return;
     static_assert(!BUILD || LPP == 1, "hit lists are recorded by the one-lane-per-protein kernel");
-    __shared__ float s_cutsqpp[36], s_ljcutsq[36];
+    __shared__ float s_cutsqpp[36], s_ljcutsq[36], s_recsq[36];
     __shared__ int s_jb[2][kPBlock / 32][kRangeCap * 32];
     __shared__ unsigned short s_len[2][kPBlock / 32][kRangeCap * 32];
-    for (int k = threadIdx.x; k < 36; k += blockDim.x) { s_cutsqpp[k] = c_ff.cutsqpp[k]; s_ljcutsq[k] = c_ff.lj_cutsq[k]; }
+    for (int k = threadIdx.x; k < 36; k += blockDim.x) {
+        s_cutsqpp[k] = c_ff.cutsqpp[k]; s_ljcutsq[k] = c_ff.lj_cutsq[k];
+        const float r = sqrtf(fmaxf(c_ff.cutsqpp[k], c_ff.lj_cutsq[k]));                 // range of this pair of types; recorded up to range + skin
+        s_recsq[k] = r > 0.f ? (r + skin) * (r + skin) * 1.00001f : 0.f;
+    }
     __syncthreads();
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     int *const ljb = s_jb[0][w] + lane, *const pjb = s_jb[1][w] + lane;
@@ -531,7 +562,7 @@ __global__ void __launch_bounds__(kPBlock, 16) k_pair_prot(PairArgs a, const flo
                     const float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
                     const float r2 = dx * dx + dy * dy + dz * dz;
                     if (u < rem && r2 < testsq_p) {
-                        if (BUILD) { if (rec_p < nl.cap_pp) row_p[(size_t)rec_p * 64] = cur + u; ++rec_p; }
+                        if (BUILD && r2 < s_recsq[type1 + __float_as_int(xj.w) * kNType]) { if (rec_p < nl.cap_pp) row_p[(size_t)rec_p * 64] = cur + u; ++rec_p; }
                         pp_pair(type1, xi, xj, s_cutsqpp, s_ljcutsq, fx, fy, fz);
                     }
                 }
@@ -577,9 +608,14 @@ __global__ void __launch_bounds__(kPBlock) k_pair_prot_list(PairArgs a, const in
         float fx = 0, fy = 0, fz = 0, tx = 0, ty = 0, tz = 0;
         const int nl_ = __ldg(nl.pl_cnt + tid), np_ = __ldg(nl.pp_cnt + tid);
         const int *row_l = nl.pl + ll_row(tid, nl.cap_pl), *row_p = nl.pp + ll_row(tid, nl.cap_pp);
-        for (int s = 0; s < nl_; ++s) {
-            const int j = __ldg(row_l + (size_t)s * 64);
-            pl_pair(a, type1, cutsq, ljcut, xi, mi, j, __ldg(a.xl + j), l0, l1, fx, fy, fz, tx, ty, tz);
+        for (int s = 0; s < nl_; s += 4) {                       // four partners at a time: the chain list -> position -> director is all latency
+            int j[4]; float4 xj[4];
+            #pragma unroll
+            for (int u = 0; u < 4; ++u) j[u] = s + u < nl_ ? __ldg(row_l + (size_t)(s + u) * 64) : -1;
+            #pragma unroll
+            for (int u = 0; u < 4; ++u) xj[u] = j[u] >= 0 ? __ldg(a.xl + j[u]) : make_float4(xi.x, xi.y, xi.z, 0.f);   // padding: r2 = 0 fails the guard
+            #pragma unroll
+            for (int u = 0; u < 4; ++u) pl_pair(a, type1, cutsq, ljcut, xi, mi, max(j[u], 0), xj[u], l0, l1, fx, fy, fz, tx, ty, tz);
         }
         for (int s = 0; s < np_; ++s) {
             const int j = __ldg(row_p + (size_t)s * 64);

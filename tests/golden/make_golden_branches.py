@@ -150,6 +150,8 @@ def integrator_chain(r, g):
     prng0 = port.mt_init(port.lib().orc_mt_uint(port.C.byref(mt0)))
     for s in (0, 1):                                             # the noise-free Langevin step of forces_chain drew from the same stream
         port.langevin_noise(prng0, r.size(s))
+    r.load_state(st)                                             # back to the state before the walls folded particles onto each other
+    r.set_param("box_lo", -1000.0); r.set_param("box_hi", 1000.0)
     r.integrate(refmod.CLEAR_FORCE); r.compute_pairwise_fused(); r.compute_bonded()
     for k, v in r.state().items():
         g["ln_in_" + k] = v

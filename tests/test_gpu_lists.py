@@ -18,9 +18,9 @@ def load(name):
     return {k[3:]: v for k, v in g.items() if k.startswith("in_")}
 
 
-def run(st, steps, **opts):
+def run(st, steps, dt=1e-2, **opts):
     from openrbc_b200 import Simulation
-    sim = Simulation(st, kBT=0.22, seed=4242)
+    sim = Simulation(st, dt=dt, kBT=0.22, seed=4242)
     for k, v in opts.items():
         sim.set_option(k, v)
     sim.run_langevin(steps)
@@ -35,12 +35,13 @@ def test_lists_do_not_change_the_trajectory(name):
     st = load(name)
     exact = len(st["px"]) == 0                 # protein -> lipid reactions arrive by atomics: their order is not fixed
     steps = 10                                 # rebuild every 2nd step: five builds, five walks
-    ref, s0 = run(st, steps, nl_reuse=0)
+    # the fixtures are freshly initialised membranes, far from equilibrium (forces of 1e2 .. 1e4): with the production time step
+    # their fastest particles outrun the skin and the gate (rightly) orders builds; a short step keeps the walk legal
+    dt = 1e-3 if name != "branches_vesicle_ico0" else 1e-5
+    ref, s0 = run(st, steps, dt, nl_reuse=0)
     assert s0[0] == 0 and s0[1] == 0
-    got, s1 = run(st, steps, nl_reuse=1)
-    if name != "branches_vesicle_ico0":       # (that fixture's hand-placed proteins are shot away fast enough to outrun the skin)
-        assert s1[0] == steps // 2 and s1[1] == steps // 2 and s1[2] == 0, s1
-    assert s1[0] + s1[1] == steps and s1[1] > 0
+    got, s1 = run(st, steps, dt, nl_reuse=1)
+    assert s1[0] == steps // 2 and s1[1] == steps // 2 and s1[2] == 0, s1
     for s in (0, 1):
         for f in "xvno":
             if exact:
@@ -48,7 +49,7 @@ def test_lists_do_not_change_the_trajectory(name):
             else:
                 assert rel_err(got[s][f], ref[s][f]) < 1e-5, (s, f)
     # a skin thinner than twice the largest step: the gate must order a build at every evaluation, and nothing changes
-    thin, s2 = run(st, steps, nl_reuse=1, nl_skin=1e-4)
+    thin, s2 = run(st, steps, dt, nl_reuse=1, nl_skin=1e-7)
     assert s2[0] == steps and s2[1] == 0, s2
     for s in (0, 1):
         for f in "xvno":
@@ -62,7 +63,7 @@ def test_lists_call_by_call_and_forces():
     """The call-by-call API: rebuild -> forces (build) -> integrate -> forces (walk); the walked forces equal a fresh search's."""
     from openrbc_b200 import Simulation
     st = load("vesicle_ico0")
-    a, b = Simulation(st, kBT=0.0), Simulation(st, kBT=0.0)
+    a, b = Simulation(st, dt=1e-3, kBT=0.0), Simulation(st, dt=1e-3, kBT=0.0)
     b.set_option("nl_reuse", 0)
     for sim in (a, b):
         sim.nstep = 24
