@@ -79,6 +79,14 @@ def load_state(workload):
     return dict(np.load(ensure_state(workload)))
 
 
+def data_label(workload):
+    if workload == "rbc":
+        return "real mesh: example-large/rbc.*.txt shipped with the reference, membrane and cytoskeleton placed by the reference's own init_rbc (seed 0xBAD5EED), 100 minimisation steps; no external dataset"
+    if workload == "sphere":
+        return "synthetic: the reference's own random lipid sphere (init_random_sphere, R = 100)"
+    return "synthetic: flat bilayer patch (openrbc_b200/synthetic.py, SURVEY.md 8d config 4)"
+
+
 def workload_name(workload, st):
     n = len(st["lx"]) + len(st["px"])
     base = {"rbc": "full RBC, -i trimesh -m rbc (example-large), Langevin", "sphere": "lipid sphere R=100, -i lipid, Langevin"}.get(
@@ -118,8 +126,9 @@ def reference_child(args):
     sample = f"{steps} MD steps of the whole system after {args.warmup} warm-up steps ({sec:.2f} s)"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * sec / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args.workload, st), "impl": "unmodified reference headers, g++ -O3 -ffast-math -mrecip -fopenmp (oracle/Makefile FAST), compute_pairwise_fused path",
+        "ms_per_step": 1e3 * sec / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": data_label(args.workload),
+        "config": {"workload": workload_name(args.workload, st), "impl": "unmodified reference headers, g++ -O3 -march=x86-64-v3 -mtune=generic -ffast-math -mrecip -fopenmp (oracle/Makefile FAST: AVX2/FMA ISA level instead of the "
+                                                                       "as-shipped -march=native, because the library is built on another machine than it runs on), compute_pairwise_fused path",
                    "omp_threads": threads, "omp_binding": "OMP_PROC_BIND=%s OMP_PLACES=%s" % (os.environ.get("OMP_PROC_BIND", "unset"), os.environ.get("OMP_PLACES", "unset")),
                    "pair_timer_s_per_step": r.timer("compute_pairwise_fused") / max(steps + args.warmup, 1)},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample},
@@ -260,6 +269,34 @@ def ncu_traffic(kernel):
         return None, None
 
 
+def alu_roofline(prof, counts, world):
+    """FP32 roofline of the pair kernels (SURVEY.md 8d 'Algorithmic flops'): flops per force evaluation / mean device time of the
+    two pair kernels (CUDA events, live) against the FFMA peak measured on this pool's B200 (tools/microbench/fp32_peak.cu ->
+    profiles/r02_fp32_peak.json).  executed = what the one-sided GPU evaluation does (every in-cutoff pair from both sides);
+    algorithmic = the reference's Newton-on count (each pair once).  98 flop per evaluated pair + 8 per distance test."""
+    try:
+        pk = json.load(open(os.path.join(ROOT, "profiles", "r02_fp32_peak.json")))
+    except Exception:  # noqa: BLE001
+        pk = {}
+    peak = pk.get("ffma_tflops")
+    if not counts or world != 1:
+        return {"bound": "fp32", "peak": peak, "unit": "TFLOP/s", "note": "pair statistics are taken on the single-GPU run only"}
+    t_ll, h_ll, t_pl, h_pl, t_pp, h_pp = counts                      # one-sided tests / hits of LL and PP; PL from the protein side
+    (ms_l, n_l), (ms_p, n_p) = prof["pair_lipid"], prof["pair_protein"]
+    sec = (ms_l / max(n_l, 1) + ms_p / max(n_p, 1)) * 1e-3          # one evaluation of both kernels, averaged over building and list-walking steps
+    executed = (h_ll + 2 * h_pl + h_pp) * 98.0 + (t_ll + t_pl + t_pp) * 8.0
+    algorithmic = (h_ll / 2 + h_pl + h_pp / 2) * 106.0 + (t_ll / 2 + t_pl + t_pp / 2) * 8.0
+    out = {"bound": "fp32", "unit": "TFLOP/s", "peak": peak, "peak_source": "measured: tools/microbench/fp32_peak.cu on this pool's B200 (profiles/r02_fp32_peak.json); issue ceiling %.3g warp instructions/s" % pk.get("mixed_warp_inst_per_s", float("nan")),
+           "kernels": "lipid + protein pair kernels of one force evaluation", "seconds_per_evaluation": sec,
+           "pairs": {"ll_tests": t_ll, "ll_hits_one_sided": h_ll, "pl_tests": t_pl, "pl_hits": h_pl, "pp_tests": t_pp, "pp_hits_one_sided": h_pp},
+           "gflop_executed": executed / 1e9, "gflop_algorithmic": algorithmic / 1e9,
+           "achieved_executed": executed / sec / 1e12 if sec else None, "achieved_algorithmic": algorithmic / sec / 1e12 if sec else None,
+           "ncu": "profiles/r02_runlist_kernel_ncu.txt (k_pair_ll_r: sm__throughput 63 %, fma pipe 34 %, alu pipe 38 %, issue active 64 %), profiles/r02_list_walker_ncu.txt, profiles/r01_v4_pair_ncu.txt (k_pair_prot)"}
+    if peak and sec:
+        out["frac_executed"] = out["achieved_executed"] / peak; out["frac_algorithmic"] = out["achieved_algorithmic"] / peak
+    return out
+
+
 def run_chunked(sim, n_steps):
     """n_steps of the main loop through the fused entry point, with delete_lipid at multiples of freq_cleanup (openrbc.cpp:201)."""
     done = 0
@@ -337,20 +374,34 @@ def run_ours(args):
         dist.all_reduce(t)                                       # every rank returns its additive share of sum(m v^2) / 3N
         temperature = float(t[0].item()); n_now = n_total
 
+    # ---- pair statistics of the current state for the ALU roofline (untimed): the cross-check kernels count tests and hits ------
+    pair_counts = None
+    if world == 1:
+        c0 = sim.dump("counters").astype(np.int64)
+        sim.set_option("pair_impl", 1); sim.clear_force(); sim.compute_pairwise_fused(); sim.synchronize()
+        pair_counts = (sim.dump("counters").astype(np.int64) - c0)[1:7].tolist()
+        sim.set_option("pair_impl", 2); sim.clear_force()
+
     # ---- end-to-end leg: host buffers through the per-call C ABI ---------------------------------------------------------
+    # the host's containers in pinned memory: the eight vector arrays and the index arrays (ids, bonds, Voronoi state) alike —
+    # 15 MB of pageable index arrays cost as much PCIe time as the 154 MB of pinned vectors
     pinned = {}
-    for k in ("lx", "lv", "ln", "lo", "px", "pv", "pn", "po"):
-        tns = torch.empty(st[k].shape, dtype=torch.float32, pin_memory=True)
-        tns.numpy()[...] = st[k]
+    for k in ("lx", "lv", "ln", "lo", "px", "pv", "pn", "po", "ptype", "ptag", "bonds", "centroids", "cs_l", "cs_p"):
+        a = np.ascontiguousarray(st[k], np.float32 if st[k].dtype.kind == "f" else np.int32)
+        tns = torch.empty(a.shape, dtype=torch.float32 if a.dtype == np.float32 else torch.int32, pin_memory=True)
+        tns.numpy()[...] = a
         pinned[k] = tns
     host = dict(st)
     host.update({k: v.numpy() for k, v in pinned.items()})
     out_l = {f: torch.empty((len(st["lx"]), 3), dtype=torch.float32, pin_memory=True) for f in "xn"}
     out_p = {f: torch.empty((len(st["px"]), 3), dtype=torch.float32, pin_memory=True) for f in "xn"}
+    aff_l = torch.empty(len(st["lx"]), dtype=torch.int32, pin_memory=True)
+    aff_p = torch.empty(len(st["px"]), dtype=torch.int32, pin_memory=True)
     # the e2e job re-uses the context (device allocations and, on N>1, the peer mappings are set-up, not per-job work)
     e2e_sim = sim
     barrier()
-    e2e_sim.upload(host)
+    # N>1: every rank uploads the rows of its own cells only (orbc_upload_range); the halo copies come from their owners over NVLink
+    e2e_sim.upload(host, owned_only=world > 1)
     if world > 1:
         e2e_sim.mg_export()
     e2e_sim.nstep = 0
@@ -360,7 +411,7 @@ def run_ours(args):
     barrier()
     e2e_sim.event_record(2)
     t_wall = time.perf_counter()
-    e2e_sim.upload(host)
+    e2e_sim.upload(host, owned_only=world > 1)
     t_up0 = time.perf_counter()
     if world > 1:
         e2e_sim.mg_export()              # owned ranges + halo masks of the fresh state (device work, no new allocations); collective
@@ -369,7 +420,7 @@ def run_ours(args):
     if trace:
         print(f"[bench rank {rank}] e2e upload {(t_up0 - t_wall) * 1e3:.1f} ms {e2e_sim.last_upload_ms} (lipids, proteins, bonds, voronoi) + export {(t_up - t_up0) * 1e3:.1f} ms", file=sys.stderr, flush=True)
     slow = []                            # (ms, what) of the slowest host-side calls, for the phase breakdown
-    h2d = sum(host[k].nbytes for k in ("lx", "lv", "ln", "lo", "px", "pv", "pn", "po", "ptype", "ptag", "bonds", "centroids", "cs_l", "cs_p"))
+    h2d = e2e_sim.last_upload_bytes      # this rank's rows of x, v, n, o + ids, bonds and the Voronoi state (the job total is the sum over ranks)
     d2h = 0
     for _ in range(args.steps):
         t0 = time.perf_counter()
@@ -383,8 +434,8 @@ def run_ours(args):
         if e2e_sim.nstep % FREQ_DISPLAY == 0:
             e2e_sim.compute_temperature(); d2h += 8
     t_steps = time.perf_counter()
-    fl = e2e_sim.download_into(0, x=out_l["x"].numpy(), n=out_l["n"].numpy(), affiliation=True)
-    fp = e2e_sim.download_into(1, x=out_p["x"].numpy(), n=out_p["n"].numpy(), affiliation=True)
+    fl = e2e_sim.download_into(0, x=out_l["x"].numpy(), n=out_l["n"].numpy(), affiliation=aff_l.numpy())
+    fp = e2e_sim.download_into(1, x=out_p["x"].numpy(), n=out_p["n"].numpy(), affiliation=aff_p.numpy())
     d2h += fl + fp
     e2e_sim.event_record(3)
     e2e_sim.synchronize()
@@ -420,6 +471,7 @@ def run_ours(args):
         return
 
     peak, peak_src = hbm_peak()
+    alu = alu_roofline(prof, pair_counts, world)
     pl_ms, pl_cnt = prof["pair_lipid"]
     n_l = len(st["lx"]) / world          # lipids one launch of the kernel covers (this rank's share on N>1)
     achieved = (B_ALG_PAIR * n_l / (pl_ms / pl_cnt * 1e-3) / 1e9) if pl_cnt else None
@@ -427,7 +479,7 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
+        "dtype": "f32", "data": data_label(args.workload),
         "config": {"workload": workload_name(args.workload, st), "l2": "inputs larger than L2 (state %.0f MB resident in HBM, no flush needed)" % (n_total * 6 * 16 / 1e6),
                    "multi_gpu": "single GPU" if world == 1 else (f"one cell decomposed over {world} ranks: contiguous ranges of Morton-ordered Voronoi cells, halo push + migration "
                                                                 "by peer stores over NVLink, epoch-flag barriers"),
@@ -440,6 +492,7 @@ def run_ours(args):
                      "launch_ms": pl_ms / pl_cnt if pl_cnt else None, "launches_timed": pl_cnt,
                      "algorithmic_bytes_per_launch": B_ALG_PAIR * n_l,
                      "note": "pair forces are FP32-ALU bound (~1.6-3 kFLOP per 48 B), see DESIGN.md; HBM fraction reported as the contract asks"},
+        "roofline_alu": alu,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d / args.steps, "d2h_bytes_per_step": d2h / args.steps,
                 "ms_per_step": e2e_ms / args.steps, "phases": phases, "what": "upload from pinned host containers + K per-call steps with status read-back + frame download, all timed"},
         "gpu_launches": int(launches),

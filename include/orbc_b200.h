@@ -110,6 +110,13 @@ ORBC_API int  orbc_set_forcefield(orbc_ctx *ctx, const orbc_forcefield *ff);
 /* type/tag are NULL for lipids (implicit 0 and base+i, container.h:122-130). f and t start at zero. */
 ORBC_API int  orbc_upload(orbc_ctx *ctx, int species, size_t n, size_t stride_floats,
                           const float *x, const float *v, const float *n_, const float *o, const int *type, const int *tag);
+/* the same for a rank of a CONNECTED decomposed run that re-uploads the system it already holds (a restart, the next job of a
+ * sweep): only rows [first, first + count) of the vector arrays travel over PCIe — the slots this rank owns, cell_start[cell_begin] ..
+ * cell_start[cell_end] of orbc_mg_cell_range — while type / tag are taken for every slot.  The halo copies are then fetched
+ * from their owners over NVLink by the orbc_mg_export that must follow on every rank.  The array pointers are those of the
+ * whole containers (row 0). */
+ORBC_API int  orbc_upload_range(orbc_ctx *ctx, int species, size_t n, size_t first, size_t count, size_t stride_floats,
+                                const float *x, const float *v, const float *n_, const float *o, const int *type, const int *tag);
 /* Bond[] as (type, tag_i, tag_j) triples, container.h:30-34 */
 ORBC_API int  orbc_upload_bonds(orbc_ctx *ctx, size_t n_bonds, const int *type_i_j);
 /* VoronoiDiagram::centroids + VCellList::cell_start of both containers after voronoi.init() (openrbc.cpp:69-74).

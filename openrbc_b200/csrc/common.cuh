@@ -87,6 +87,7 @@ struct PeerTable {
 };
 struct Decomp {
     bool on = false, connected = false;
+    bool partial[2] = {false, false};     // the last upload of the container held only this rank's own rows (orbc_upload_range)
     int rank = 0, world = 1;
     int cb = 0, ce = 0;                   // owned cells
     size_t own_cap[2] = {0, 0};           // launch bound of the owned-particle kernels
@@ -97,6 +98,7 @@ struct Decomp {
     unsigned *flags = nullptr;            // kMaxWorld epochs written by the peers
     double *ke_all = nullptr;             // 2 x kMaxWorld partial kinetic energies written by the peers, halves used alternately
     int ke_par = 0;
+    int disp_par = 0;                     // which of the two sets of displacement bounds (behind the barrier epochs in `flags`) is current
     double *vol_all = nullptr;            // 2 x kMaxWorld partial volumes written by the peers (constrain_volume), halves used alternately
     int cv_par = 0;
     int *cv_ptype = nullptr;              // n_cells protein types by slot, written by the slots' owners (constrain_volume)
@@ -176,9 +178,11 @@ struct orbc_ctx {
     unsigned char *frame_host[2] = {nullptr, nullptr}; size_t frame_host_cap[2] = {0, 0};
     size_t frame_bytes[2] = {0, 0};
     cudaStream_t copy_stream = nullptr;
+    cudaEvent_t xfer_ev[8] = {};                          // upload / download pipeline (copies on copy_stream, packing on stream)
     cudaEvent_t frame_packed[2] = {}, frame_copied[2] = {};
     int frame_head = 0, frame_pending = 0;                // ring of two frames in flight
     orbc::Decomp mg;
+    int mg_own_slack = 8192;                              // slack of the owned-particle launch bounds (test option debug_own_slack)
     // per-class event-pair profiling (orbc_profile_*)
     bool prof_on = false;
     std::vector<cudaEvent_t> prof_ev[ORBC_PROF_N];   // even = start, odd = stop

@@ -214,8 +214,10 @@ float pow_chain(float base, int expo) { return expo != 0 ? base * pow_chain(base
 float ff_rep(float cut, float req, float eps) { return eps / pow_chain(cut - req, 8); }
 float ff_att(float cut, float req, float eps) { return (float)(-2.0 * eps / pow_chain(cut - req, 4)); }
 
-// hit lists are used by the default single-GPU kernels only (a decomposed run would have to exchange the displacement bound)
-bool nl_active(const orbc_ctx *c) { return c->nl_on && !mg_active(c) && c->pair_impl == 2 && c->ll_variant == 1; }
+// hit lists go with the default kernels; on a decomposed run the ranks exchange their displacement bounds (k_nl_share)
+bool nl_active(const orbc_ctx *c) { return c->nl_on && (!mg_active(c) || c->mg.connected) && c->pair_impl == 2 && c->ll_variant == 1; }
+int nl_share(orbc_ctx *c);
+int prot_lanes(const orbc_ctx *c, size_t np) { return c->prot_lanes ? c->prot_lanes : (np <= 400000 ? 4 : 1); }
 int nl_ensure(orbc_ctx *c) {
     Species &L = c->sp[0], &P = c->sp[1];
     if (!c->nl_state) { NlState *st = nullptr; ORBC_TRY(dev_alloc(&st, 1)); c->nl_state = st; ORBC_CUDA(cudaMemsetAsync(st, 0, sizeof(NlState), c->stream)); c->nl_valid = false; }
@@ -224,11 +226,12 @@ int nl_ensure(orbc_ctx *c) {
         ORBC_TRY(dev_alloc(&c->ll_list, groups * 64 * (size_t)c->nl_cap_ll)); ORBC_TRY(dev_alloc(&c->ll_cnt, groups * 64));
         c->ll_list_lipids = L.cap; c->nl_valid = false;
     }
-    if (P.n && c->pl_list_proteins < P.cap) {
-        const size_t groups = (P.cap + 63) / 64;
+    const size_t prot_rows = mg_active(c) ? owned_bound(c, ORBC_PROTEIN) * 4 + 64 : P.cap;   // one row per thread of the protein kernel (up to 4 lanes per protein on a rank)
+    if (P.n && c->pl_list_proteins < prot_rows) {
+        const size_t groups = (prot_rows + 63) / 64;
         ORBC_TRY(dev_alloc(&c->pl_list, groups * 64 * (size_t)c->nl_cap_pl)); ORBC_TRY(dev_alloc(&c->pl_cnt, groups * 64));
         ORBC_TRY(dev_alloc(&c->pp_list, groups * 64 * (size_t)c->nl_cap_pp)); ORBC_TRY(dev_alloc(&c->pp_cnt, groups * 64));
-        c->pl_list_proteins = P.cap; c->nl_valid = false;
+        c->pl_list_proteins = prot_rows; c->nl_valid = false;
     }
     return ORBC_OK;
 }
@@ -312,6 +315,7 @@ int launch_pairwise(orbc_ctx *c, bool accumulate = true) {
     a.cb = mg ? c->mg.cb : 0; a.ce = mg ? c->mg.ce : c->n_cells; a.world = mg ? c->mg.world : 1;
     a.dest_mask = c->mg.dest_mask;
     a.accumulate = accumulate ? 1 : 0;
+    a.counters = c->d_counters;
     const size_t nl_count = owned_bound(c, ORBC_LIPID), np = owned_bound(c, ORBC_PROTEIN);
     constexpr unsigned kSmallGrid = 148 * 16;                   // a gated launch that usually returns at once: grid-stride over few blocks
     if (c->pair_impl == 1) {
@@ -328,7 +332,9 @@ int launch_pairwise(orbc_ctx *c, bool accumulate = true) {
         ORBC_TRY(nl_ensure(c));
         nls = (NlState *)c->nl_state;
         host_build = !c->nl_valid;
-        ORBC_LAUNCH(c, k_nl_gate, 1, 32, 0, nls, host_build ? 1 : 0, c->nl_moves, c->nl_skin);
+        if (mg && c->nl_moves > 1) host_build = true;             // (the ranks exchange the bound of ONE step)
+        ORBC_LAUNCH(c, k_nl_gate, 1, 32, 0, nls, host_build ? 1 : 0, c->nl_moves, c->nl_skin,
+                    mg ? (const unsigned *)(c->mg.flags + kMaxWorld * (1 + c->mg.disp_par)) : (const unsigned *)nullptr, mg ? c->mg.world : 1);
         c->nl_moves = 0; c->nl_valid = true;
     }
     {
@@ -372,16 +378,23 @@ int launch_pairwise(orbc_ctx *c, bool accumulate = true) {
         ProfScope ps(c, ORBC_PROF_PAIR_PROTEIN);
         // few owned proteins (a rank of a decomposed run): more lanes per protein, shorter dependent-load chains, more warps
         const PLists pls = {c->pl_list, c->pl_cnt, c->pp_list, c->pp_cnt, c->nl_cap_pl, c->nl_cap_pp, nls};
-        if (nl && host_build)
-            ORBC_LAUNCH(c, (k_pair_prot<1, true>), blocks_for(np, kPBlock), kPBlock, 0, a, c->lbound, c->pbound, ct, c->porder, (const int *)nullptr, 0, pls, c->nl_skin);
-        else if (nl) {
-            ORBC_LAUNCH(c, k_pair_prot_list, blocks_for(np, kPBlock), kPBlock, 0, a, c->porder, &nls->need, 0, pls);
-            ORBC_LAUNCH(c, (k_pair_prot<1, true>), kSmallGrid, kPBlock, 0, a, c->lbound, c->pbound, ct, c->porder, &nls->need, 1, pls, c->nl_skin);
+        const int lanes = prot_lanes(c, np);
+        const int *gate_b = (nl && !host_build) ? &nls->need : (const int *)nullptr;     // the build kernel is gated only on a list-walking step
+        const float skin = nl ? c->nl_skin : 0.f;
+        if (nl && !host_build) {
+            if (lanes == 4) ORBC_LAUNCH(c, k_pair_prot_list<4>, blocks_for(np * 4, kPBlock), kPBlock, 0, a, c->porder, &nls->need, 0, pls);
+            else if (lanes == 2) ORBC_LAUNCH(c, k_pair_prot_list<2>, blocks_for(np * 2, kPBlock), kPBlock, 0, a, c->porder, &nls->need, 0, pls);
+            else ORBC_LAUNCH(c, k_pair_prot_list<1>, blocks_for(np, kPBlock), kPBlock, 0, a, c->porder, &nls->need, 0, pls);
+        }
+        const unsigned grid = (nl && !host_build) ? kSmallGrid : blocks_for(np * lanes, kPBlock);
+        if (nl) {
+            if (lanes == 4) ORBC_LAUNCH(c, (k_pair_prot<4, true>), grid, kPBlock, 0, a, c->lbound, c->pbound, ct, c->porder, gate_b, 1, pls, skin);
+            else if (lanes == 2) ORBC_LAUNCH(c, (k_pair_prot<2, true>), grid, kPBlock, 0, a, c->lbound, c->pbound, ct, c->porder, gate_b, 1, pls, skin);
+            else ORBC_LAUNCH(c, (k_pair_prot<1, true>), grid, kPBlock, 0, a, c->lbound, c->pbound, ct, c->porder, gate_b, 1, pls, skin);
         } else {
-            const int lanes = c->prot_lanes ? c->prot_lanes : (np <= 400000 ? 4 : 1);
-            if (lanes == 4) ORBC_LAUNCH(c, (k_pair_prot<4, false>), blocks_for(np * 4, kPBlock), kPBlock, 0, a, c->lbound, c->pbound, ct, c->porder, (const int *)nullptr, 0, pls, 0.f);
-            else if (lanes == 2) ORBC_LAUNCH(c, (k_pair_prot<2, false>), blocks_for(np * 2, kPBlock), kPBlock, 0, a, c->lbound, c->pbound, ct, c->porder, (const int *)nullptr, 0, pls, 0.f);
-            else ORBC_LAUNCH(c, (k_pair_prot<1, false>), blocks_for(np, kPBlock), kPBlock, 0, a, c->lbound, c->pbound, ct, c->porder, (const int *)nullptr, 0, pls, 0.f);
+            if (lanes == 4) ORBC_LAUNCH(c, (k_pair_prot<4, false>), grid, kPBlock, 0, a, c->lbound, c->pbound, ct, c->porder, (const int *)nullptr, 0, pls, 0.f);
+            else if (lanes == 2) ORBC_LAUNCH(c, (k_pair_prot<2, false>), grid, kPBlock, 0, a, c->lbound, c->pbound, ct, c->porder, (const int *)nullptr, 0, pls, 0.f);
+            else ORBC_LAUNCH(c, (k_pair_prot<1, false>), grid, kPBlock, 0, a, c->lbound, c->pbound, ct, c->porder, (const int *)nullptr, 0, pls, 0.f);
         }
     }
     return ORBC_OK;
@@ -528,12 +541,22 @@ int do_integrate_langevin(orbc_ctx *c, const orbc_step_params *p, bool rebuild_f
             ORBC_LAUNCH(c, k_verlet_langevin, blocks_for(owned_bound(c, sp), 256), 256, 0, a);
             if (mg_active(c)) S.cur_xn ^= 1;
         }
+        ORBC_TRY(nl_share(c));
     }
     return rebuild_follows ? ORBC_OK : mg_barrier(c);            // the pushed halo has landed everywhere
 }
 
 // CUDA loads kernels lazily, and loading one may wait for the device to go idle — a rank spinning in k_mg_barrier while its
 // peer loads a kernel for the first time would never be released.  A decomposed context therefore loads every kernel up front.
+// decomposed run: publish this rank's displacement bound of the step (the barrier behind the halo push covers it)
+int nl_share(orbc_ctx *c) {
+    if (!mg_active(c) || !nl_active(c) || !c->nl_state) return ORBC_OK;
+    c->mg.disp_par ^= 1;
+    NlShare d; for (int r = 0; r < kMaxWorld; ++r) d.dst[r] = c->mg.peers.flags[r] ? c->mg.peers.flags[r] + kMaxWorld * (1 + c->mg.disp_par) : nullptr;
+    ORBC_LAUNCH(c, k_nl_share, 1, 32, 0, (NlState *)c->nl_state, c->mg.rank, c->mg.world, d);
+    return ORBC_OK;
+}
+
 int preload_kernels() {
     cudaFuncAttributes fa;
 #define ORBC_PRELOAD(k) ORBC_CUDA(cudaFuncGetAttributes(&fa, (const void *)(k)))
@@ -543,7 +566,7 @@ int preload_kernels() {
     ORBC_PRELOAD(k_cv_normal_volume); ORBC_PRELOAD(k_fill_cellid); ORBC_PRELOAD(k_fill_int); ORBC_PRELOAD(k_halo_push); ORBC_PRELOAD(k_kinetic);
     ORBC_PRELOAD(k_mg_barrier); ORBC_PRELOAD(k_morton_keys); ORBC_PRELOAD(k_morton_keys_only); ORBC_PRELOAD(k_nh_final); ORBC_PRELOAD(k_nh_final_fused);
     ORBC_PRELOAD(k_nh_initial_fused); ORBC_PRELOAD(k_nh_zeta_update); ORBC_PRELOAD(k_share_ke); ORBC_PRELOAD(k_sum_ke); ORBC_PRELOAD(k_noise); ORBC_PRELOAD(k_opt_move); ORBC_PRELOAD(k_pack4);
-    ORBC_PRELOAD(k_pair_lipid); ORBC_PRELOAD(k_lipid_runs); ORBC_PRELOAD(k_rank_only); ORBC_PRELOAD(k_init_centroids); ORBC_PRELOAD(k_bbox); ORBC_PRELOAD((k_pair_ll_r<20, 4, false>)); ORBC_PRELOAD(k_pair_ll_t); ORBC_PRELOAD((k_pair_prot<1, false>)); ORBC_PRELOAD((k_pair_prot<2, false>)); ORBC_PRELOAD((k_pair_prot<4, false>)); ORBC_PRELOAD(k_pair_protein);
+    ORBC_PRELOAD(k_pair_lipid); ORBC_PRELOAD(k_lipid_runs); ORBC_PRELOAD(k_rank_only); ORBC_PRELOAD(k_init_centroids); ORBC_PRELOAD(k_bbox); ORBC_PRELOAD((k_pair_ll_r<20, 4, false>)); ORBC_PRELOAD(k_pair_ll_t); ORBC_PRELOAD((k_pair_prot<1, false>)); ORBC_PRELOAD((k_pair_prot<2, false>)); ORBC_PRELOAD((k_pair_prot<4, false>)); ORBC_PRELOAD((k_pair_prot<1, true>)); ORBC_PRELOAD((k_pair_prot<2, true>)); ORBC_PRELOAD((k_pair_prot<4, true>)); ORBC_PRELOAD(k_pair_prot_list<1>); ORBC_PRELOAD(k_pair_prot_list<2>); ORBC_PRELOAD(k_pair_prot_list<4>); ORBC_PRELOAD((k_pair_ll_r<20, 4, true>)); ORBC_PRELOAD((k_pair_ll_list<12>)); ORBC_PRELOAD((k_pair_ll_list<16>)); ORBC_PRELOAD((k_pair_ll_list<20>)); ORBC_PRELOAD(k_nl_gate); ORBC_PRELOAD(k_nl_share); ORBC_PRELOAD(k_pair_protein);
     ORBC_PRELOAD(k_permute_centroids); ORBC_PRELOAD(k_porder_flag); ORBC_PRELOAD(k_porder_scatter); ORBC_PRELOAD(k_post_torque); ORBC_PRELOAD(k_radix_hist);
     ORBC_PRELOAD(k_radix_scatter); ORBC_PRELOAD(k_rank_and_move); ORBC_PRELOAD(k_remap_cellid); ORBC_PRELOAD(k_scan_onepass); ORBC_PRELOAD(k_set3); ORBC_PRELOAD(k_set_range); ORBC_PRELOAD(k_set_range_const); ORBC_PRELOAD(k_share_counts);
     ORBC_PRELOAD(k_stencil_build); ORBC_PRELOAD(k_stray_mask); ORBC_PRELOAD(k_unpack3); ORBC_PRELOAD(k_unpack_w); ORBC_PRELOAD(k_verlet_langevin); ORBC_PRELOAD(k_zero4);
@@ -693,6 +716,7 @@ void orbc_destroy(orbc_ctx *c) { if (c) cudaSetDevice(c->device);
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
     for (auto &v : c->prof_ev) for (auto &e : v) cudaEventDestroy(e);
     for (auto &e : c->kprof_ev) cudaEventDestroy(e);
+    for (auto &e : c->xfer_ev) if (e) cudaEventDestroy(e);
     for (int k = 0; k < 2; ++k) {
         dev_free(c->frame_dev[k]); if (c->frame_host[k]) cudaFreeHost(c->frame_host[k]);
         if (c->frame_packed[k]) cudaEventDestroy(c->frame_packed[k]); if (c->frame_copied[k]) cudaEventDestroy(c->frame_copied[k]);
@@ -705,7 +729,7 @@ void orbc_destroy(orbc_ctx *c) { if (c) cudaSetDevice(c->device);
 int orbc_set_option(orbc_ctx *c, const char *name, double value) { if (c) cudaSetDevice(c->device);
     if (!c || !name) return fail(ORBC_ERR_ARG, "null argument");
     if (!strcmp(name, "pair_impl")) { if (value != 1 && value != 2) return fail(ORBC_ERR_ARG, "pair_impl must be 1 or 2"); c->pair_impl = (int)value; c->nl_valid = false; return ORBC_OK; }
-    if (!strcmp(name, "prot_lanes")) { if (value != 0 && value != 1 && value != 2 && value != 4) return fail(ORBC_ERR_ARG, "prot_lanes must be 0 (automatic), 1, 2 or 4"); c->prot_lanes = (int)value; return ORBC_OK; }
+    if (!strcmp(name, "prot_lanes")) { if (value != 0 && value != 1 && value != 2 && value != 4) return fail(ORBC_ERR_ARG, "prot_lanes must be 0 (automatic), 1, 2 or 4"); c->prot_lanes = (int)value; c->nl_valid = false; return ORBC_OK; }
     if (!strcmp(name, "ll_variant")) {                           // 0: warp-per-cell tile kernel k_pair_ll_t (default); 1: thread-per-lipid run-list kernel k_pair_ll_r
         if (value != 0 && value != 1) return fail(ORBC_ERR_ARG, "ll_variant must be 1 (run-list kernel + hit lists) or 0 (tile kernel)");
         c->ll_variant = (int)value; c->nl_valid = false; return ORBC_OK;
@@ -719,6 +743,10 @@ int orbc_set_option(orbc_ctx *c, const char *name, double value) { if (c) cudaSe
     if (!strcmp(name, "debug_tile_cap")) {                       // test aid: a smaller tile capacity, so that small systems reach the overflow path
         if (!(value >= 1 && value <= kTileCap)) return fail(ORBC_ERR_ARG, "debug_tile_cap must be in [1, %d]", kTileCap);
         c->tile_cap = (int)value; c->lruns_valid = false; return ORBC_OK;
+    }
+    if (!strcmp(name, "debug_own_slack")) {                      // test aid: slack of the owned-particle launch bounds (before orbc_mg_export), so that
+        if (!(value >= 0)) return fail(ORBC_ERR_ARG, "debug_own_slack must be >= 0");   // small systems get launch bounds below their size
+        c->mg_own_slack = (int)value; return ORBC_OK;
     }
     if (!strcmp(name, "debug_barriers")) {                       // profiling aid: `value` back-to-back barriers of a decomposed run
         for (int k = 0; k < (int)value; ++k) ORBC_TRY(mg_barrier(c));
@@ -738,29 +766,50 @@ int orbc_set_option(orbc_ctx *c, const char *name, double value) { if (c) cudaSe
 int orbc_synchronize(orbc_ctx *c) { if (c) cudaSetDevice(c->device); ORBC_CUDA(cudaStreamSynchronize(c->stream)); return check_flags(c); }
 int orbc_set_stream(orbc_ctx *c, void *s) { if (c) cudaSetDevice(c->device); ORBC_CUDA(cudaStreamSynchronize(c->stream)); c->stream = s ? (cudaStream_t)s : c->own_stream; return ORBC_OK; }
 
-int orbc_upload(orbc_ctx *c, int sp, size_t n, size_t stride, const float *x, const float *v, const float *n_, const float *o, const int *type, const int *tag) { if (c) cudaSetDevice(c->device);
-    if (!c || sp < 0 || sp > 1 || stride < 3) return fail(ORBC_ERR_ARG, "orbc_upload: bad argument");
-    if (n && (!x || !n_)) return fail(ORBC_ERR_ARG, "orbc_upload: x and n are required");
-    if (n >= (size_t)1 << 31) return fail(ORBC_ERR_ARG, "orbc_upload: more than 2^31 particles per container");
+// second stream for host <-> device copies that overlap the packing kernels (also used by the asynchronous frames)
+static int ensure_copy_stream(orbc_ctx *c) {
+    if (!c->copy_stream) {
+        ORBC_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        for (int k = 0; k < 2; ++k) { ORBC_CUDA(cudaEventCreateWithFlags(&c->frame_packed[k], cudaEventDisableTiming)); ORBC_CUDA(cudaEventCreateWithFlags(&c->frame_copied[k], cudaEventDisableTiming)); }
+        for (auto &e : c->xfer_ev) ORBC_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    return ORBC_OK;
+}
+
+// the upload proper: rows [first, first + count) of the host's strided arrays, type / tag of EVERY slot.  All host-to-device
+// copies are queued back to back on the copy stream into one staging area (the link never idles); the packing kernels follow
+// each copy on the compute stream.
+static int upload_rows(orbc_ctx *c, int sp, size_t n, size_t first, size_t count, size_t stride,
+                       const float *x, const float *v, const float *n_, const float *o, const int *type, const int *tag) {
     Species &S = c->sp[sp];
     ORBC_TRY(alloc_species(c, S, n));
     if (!n) return ORBC_OK;
-    ORBC_TRY(ensure_stage(c, n * stride + 2 * n));
-    int *w = (int *)(c->stage + n * stride);
-    const unsigned nb = blocks_for(n, kBlock);
-    auto put = [&](const float *src, float4 *dst, const int *wsrc) -> int {
-        const int *wd = nullptr;
-        if (wsrc) { ORBC_CUDA(cudaMemcpyAsync(w, wsrc, sizeof(int) * n, cudaMemcpyHostToDevice, c->stream)); wd = w; }
-        if (src) {
-            ORBC_CUDA(cudaMemcpyAsync(c->stage, src, sizeof(float) * n * stride, cudaMemcpyHostToDevice, c->stream));
-            ORBC_LAUNCH(c, k_pack4, nb, kBlock, 0, c->stage, stride, n, dst, wd);
-        } else ORBC_LAUNCH(c, k_zero4, nb, kBlock, 0, dst, n, wd);
-        return ORBC_OK;
-    };
-    ORBC_TRY(put(x, S.X(), type));
-    ORBC_TRY(put(n_, S.N(), tag));
-    ORBC_TRY(put(v, S.V(), nullptr));
-    ORBC_TRY(put(o, S.O(), nullptr));
+    ORBC_TRY(ensure_copy_stream(c));
+    const size_t rows = count * stride;
+    ORBC_TRY(ensure_stage(c, 4 * rows + 2 * n + 16));
+    float *stage[4] = {c->stage, c->stage + rows, c->stage + 2 * rows, c->stage + 3 * rows};
+    int *w_type = (int *)(c->stage + 4 * rows), *w_tag = w_type + n;
+    const float *src[4] = {x, n_, v, o};
+    float4 *dst[4] = {S.X(), S.N(), S.V(), S.O()};
+    const int *wsrc[4] = {type, tag, nullptr, nullptr};
+    int *wdev[4] = {w_type, w_tag, nullptr, nullptr};
+    ORBC_CUDA(cudaEventRecord(c->xfer_ev[6], c->stream));
+    ORBC_CUDA(cudaStreamWaitEvent(c->copy_stream, c->xfer_ev[6], 0));   // the staging area may still be read by earlier kernels
+    for (int k = 0; k < 4; ++k) {
+        if (wsrc[k]) ORBC_CUDA(cudaMemcpyAsync(wdev[k], wsrc[k], sizeof(int) * n, cudaMemcpyHostToDevice, c->copy_stream));
+        if (src[k] && count) ORBC_CUDA(cudaMemcpyAsync(stage[k], src[k] + first * stride, sizeof(float) * rows, cudaMemcpyHostToDevice, c->copy_stream));
+        ORBC_CUDA(cudaEventRecord(c->xfer_ev[k], c->copy_stream));
+    }
+    const unsigned nb = blocks_for(n, kBlock), nbr = blocks_for(std::max<size_t>(count, 1), kBlock);
+    for (int k = 0; k < 4; ++k) {
+        ORBC_CUDA(cudaStreamWaitEvent(c->stream, c->xfer_ev[k], 0));
+        // type / tag go into .w of every slot; the vectors into the uploaded rows (zeros when the host passes no array)
+        if (k < 2 && count < n) ORBC_LAUNCH(c, k_zero4, nb, kBlock, 0, dst[k], n, (const int *)(wsrc[k] ? wdev[k] : nullptr));
+        if (count) {
+            if (src[k]) ORBC_LAUNCH(c, k_pack4, nbr, kBlock, 0, stage[k], stride, count, dst[k] + first, (const int *)(wsrc[k] ? wdev[k] + first : nullptr));
+            else ORBC_LAUNCH(c, k_zero4, nbr, kBlock, 0, dst[k] + first, count, (const int *)(wsrc[k] ? wdev[k] + first : nullptr));
+        }
+    }
     ORBC_LAUNCH(c, k_zero4, nb, kBlock, 0, S.f, n, (const int *)nullptr);
     ORBC_LAUNCH(c, k_zero4, nb, kBlock, 0, S.t, n, (const int *)nullptr);
     ORBC_LAUNCH(c, k_fill_int, nb, kBlock, 0, S.C(), n, -1);
@@ -782,6 +831,25 @@ int orbc_upload(orbc_ctx *c, int sp, size_t n, size_t stride, const float *x, co
         ORBC_TRY(build_tag2idx(c));
     }
     return ORBC_OK;
+}
+
+int orbc_upload(orbc_ctx *c, int sp, size_t n, size_t stride, const float *x, const float *v, const float *n_, const float *o, const int *type, const int *tag) { if (c) cudaSetDevice(c->device);
+    if (!c || sp < 0 || sp > 1 || stride < 3) return fail(ORBC_ERR_ARG, "orbc_upload: bad argument");
+    if (n && (!x || !n_)) return fail(ORBC_ERR_ARG, "orbc_upload: x and n are required");
+    if (n >= (size_t)1 << 31) return fail(ORBC_ERR_ARG, "orbc_upload: more than 2^31 particles per container");
+    c->mg.partial[sp] = false;
+    return upload_rows(c, sp, n, 0, n, stride, x, v, n_, o, type, tag);
+}
+
+int orbc_upload_range(orbc_ctx *c, int sp, size_t n, size_t first, size_t count, size_t stride,
+                      const float *x, const float *v, const float *n_, const float *o, const int *type, const int *tag) { if (c) cudaSetDevice(c->device);
+    if (!c || sp < 0 || sp > 1 || stride < 3 || first + count > n) return fail(ORBC_ERR_ARG, "orbc_upload_range: bad argument");
+    if (count && (!x || !n_)) return fail(ORBC_ERR_ARG, "orbc_upload_range: x and n are required");
+    if (n >= (size_t)1 << 31) return fail(ORBC_ERR_ARG, "orbc_upload_range: more than 2^31 particles per container");
+    if (!c->mg.connected) return fail(ORBC_ERR_ARG, "orbc_upload_range: only on the connected ranks of a decomposed run (the first upload is a whole one)");
+    if (!c->sp[sp].cap || n + 64 > c->sp[sp].cap) return fail(ORBC_ERR_ARG, "orbc_upload_range: the container would have to grow (peer mappings are fixed): upload the whole system once first");
+    c->mg.partial[sp] = count < n;
+    return upload_rows(c, sp, n, first, count, stride, x, v, n_, o, type, tag);
 }
 
 int orbc_upload_bonds(orbc_ctx *c, size_t n_bonds, const int *tij) { if (c) cudaSetDevice(c->device);
@@ -1033,7 +1101,7 @@ int orbc_integrate(orbc_ctx *c, int kernel, const orbc_step_params *p, orbc_step
         case ORBC_CLEAR_FORCE: ORBC_LAUNCH(c, k_clear_force, blocks_for(S.n, 256), 256, 0, S.f, S.t, S.n); break;
         case ORBC_POST_TORQUE: ORBC_LAUNCH(c, k_post_torque, nb, 256, 0, S.N(), S.t, S.n); break;
         case ORBC_BOUNCE_BACK: ORBC_LAUNCH(c, k_bounce_back, nb, 256, 0, a); break;
-        case ORBC_NH_INITIAL_FUSED: ORBC_LAUNCH(c, k_nh_initial_fused, nb, 256, 0, a); if (mg_active(c)) S.cur_xn ^= 1; break;
+        case ORBC_NH_INITIAL_FUSED: ORBC_LAUNCH(c, k_nh_initial_fused, nb, 256, 0, a); if (mg_active(c)) S.cur_xn ^= 1; if (sp == 1 || !c->sp[1].n) ORBC_TRY(nl_share(c)); break;
         case ORBC_NH_FINAL_FUSED: ORBC_LAUNCH(c, k_nh_final_fused, nb, 256, 0, a); break;
         case ORBC_NH_FINAL: ORBC_LAUNCH(c, k_nh_final, nb, 256, 0, a); break;
         case ORBC_NH_UPDATE: ORBC_LAUNCH(c, k_kinetic, nb, 256, 0, S.X(), S.V(), c->d_range + 2 * sp, 0.5f, c->d_acc); break;
@@ -1140,6 +1208,7 @@ int orbc_run_nh(orbc_ctx *c, const orbc_step_params *p, int n_steps, int freq_vo
             ORBC_LAUNCH(c, k_nh_initial_fused, blocks_for(owned_bound(c, sp), 256), 256, 0, a);
             if (mg) c->sp[sp].cur_xn ^= 1;
         }
+        ORBC_TRY(nl_share(c));
         // decomposed: one barrier stands behind both the halo push of the drift and the exchange of the partial kinetic energies
         ORBC_TRY(mg_share_ke(c)); ORBC_TRY(mg_barrier(c));
         ORBC_LAUNCH(c, k_nh_zeta_update, 1, 32, 0, c->d_nh, c->d_acc, q.dt, q.kBT, n, mg ? mg_ke_slots(c) : (const double *)nullptr, world);
@@ -1199,12 +1268,13 @@ int orbc_mg_export(orbc_ctx *c, void *blob_out, size_t bytes) { if (c) cudaSetDe
     } else {
         for (int sp = 0; sp < 2; ++sp) {
             const size_t n = c->sp[sp].n;
-            m.own_cap[sp] = w == 1 ? n : std::min(n, n / w + n / (4 * (size_t)w) + 8192);
+            m.own_cap[sp] = w == 1 ? n : std::min(n, n / w + n / (4 * (size_t)w) + (size_t)c->mg_own_slack);
             ORBC_TRY(dev_alloc(&m.cnt_all[sp], (size_t)w * (nc + 1))); ORBC_TRY(dev_alloc(&m.off_me[sp], (size_t)nc + 1)); ORBC_TRY(dev_alloc(&m.cnt_prev[sp], (size_t)nc + 1));
             ORBC_CUDA(cudaMemsetAsync(m.cnt_prev[sp], 0, sizeof(int) * ((size_t)nc + 1), c->stream));
             ORBC_CUDA(cudaMemsetAsync(m.cnt_all[sp], 0, sizeof(int) * (size_t)w * (nc + 1), c->stream));
         }
-        ORBC_TRY(dev_alloc(&m.flags, kMaxWorld)); ORBC_CUDA(cudaMemsetAsync(m.flags, 0, sizeof(unsigned) * kMaxWorld, c->stream));
+        // barrier epochs [0, 8) and two sets of per-rank displacement bounds [8, 16), [16, 24) (hit lists, k_nl_share)
+        ORBC_TRY(dev_alloc(&m.flags, 3 * kMaxWorld)); ORBC_CUDA(cudaMemsetAsync(m.flags, 0, sizeof(unsigned) * 3 * kMaxWorld, c->stream));
         ORBC_TRY(dev_alloc(&m.ke_all, 2 * kMaxWorld)); ORBC_CUDA(cudaMemsetAsync(m.ke_all, 0, sizeof(double) * 2 * kMaxWorld, c->stream));
         ORBC_TRY(dev_alloc(&m.vol_all, 2 * kMaxWorld)); ORBC_CUDA(cudaMemsetAsync(m.vol_all, 0, sizeof(double) * 2 * kMaxWorld, c->stream));
         ORBC_TRY(dev_alloc(&m.cv_ptype, nc)); ORBC_CUDA(cudaMemsetAsync(m.cv_ptype, 0, sizeof(int) * nc, c->stream));
@@ -1212,8 +1282,9 @@ int orbc_mg_export(orbc_ctx *c, void *blob_out, size_t bytes) { if (c) cudaSetDe
         ORBC_TRY(dev_alloc(&m.pmask, P.n + 4)); ORBC_CUDA(cudaMemsetAsync(m.pmask, 0, P.n + 4, c->stream));
         ORBC_TRY(dev_alloc(&m.need, nc)); ORBC_CUDA(cudaMemsetAsync(m.need, 0, sizeof(int) * nc, c->stream));
         ORBC_TRY(dev_alloc(&m.keep, L.n + 1));
+        if (c->nl_on) ORBC_TRY(nl_ensure(c));                    // the hit lists: allocated now, never while peers wait in a barrier
         // work list of the bonds with an owned atom (clipped and flagged at the capacity)
-        m.my_bonds_cap = (int)std::min(c->n_bonds, c->n_bonds / w + c->n_bonds / (2 * (size_t)w) + 8192);
+        m.my_bonds_cap = (int)std::min(c->n_bonds, c->n_bonds / w + c->n_bonds / (2 * (size_t)w) + (size_t)c->mg_own_slack);
         ORBC_TRY(dev_alloc(&m.my_bonds, (size_t)m.my_bonds_cap + 1));
         m.cen_buf[0] = c->centroid; m.cen_buf[1] = c->centroid_tmp; m.cen_par = 0; m.epoch = 0;
         // scratch that the single-GPU path allocates on first use: allocate it now, no cudaMalloc while peers spin in a barrier
@@ -1236,6 +1307,17 @@ int orbc_mg_export(orbc_ctx *c, void *blob_out, size_t bytes) { if (c) cudaSetDe
     // a repeated export (fresh upload of the same system on connected ranks) is a collective call: no rank may start storing
     // counts, halo copies or migrating particles into a peer that is still uploading or clearing its tables
     if (m.connected) ORBC_TRY(mg_barrier(c));
+    if (m.connected && w > 1 && (m.partial[0] || m.partial[1])) {
+        // every rank uploaded only its own rows (orbc_upload_range): the halo copies come from their owners, over NVLink
+        for (int sp = 0; sp < 2; ++sp) {
+            Species &S = c->sp[sp];
+            if (!S.n) continue;
+            HaloDst d; for (int r = 0; r < kMaxWorld; ++r) { d.x[r] = m.peers.x[sp][S.cur_xn][r]; d.nn[r] = m.peers.nn[sp][S.cur_xn][r]; }
+            ORBC_LAUNCH(c, k_halo_push, blocks_for(owned_bound(c, sp), kBlock), kBlock, 0, c->d_range + 2 * sp, m.dest_mask, sp == ORBC_PROTEIN ? m.pmask : (const unsigned char *)nullptr,
+                        S.C(), S.X(), S.N(), d);
+        }
+        ORBC_TRY(mg_barrier(c));
+    }
     ORBC_CUDA(cudaStreamSynchronize(c->stream));
     MgBlob *b = (MgBlob *)blob_out;
     memset(b, 0, sizeof(*b));
@@ -1293,28 +1375,50 @@ int orbc_download(orbc_ctx *c, int sp, size_t stride, float *x, float *v, float 
     Species &S = c->sp[sp];
     if (n_out) *n_out = S.n;
     if (!S.n) return check_flags(c);
-    ORBC_TRY(ensure_stage(c, S.n * stride));
-    const unsigned nb = blocks_for(S.n, kBlock);
-    auto get3 = [&](const float4 *src, float *dst) -> int {
-        if (!dst) return ORBC_OK;
-        ORBC_LAUNCH(c, k_unpack3, nb, kBlock, 0, src, S.n, stride, c->stage);
-        ORBC_CUDA(cudaMemcpyAsync(dst, c->stage, sizeof(float) * S.n * stride, cudaMemcpyDeviceToHost, c->stream));
+    // a rank of a decomposed run holds current values only in the slots it owns: it fills exactly those rows of the host arrays
+    // (the ranks of one host program write disjoint rows of the same containers)
+    size_t first = 0, count = S.n;
+    if (mg_active(c)) {
+        int r[2];
+        ORBC_CUDA(cudaMemcpyAsync(r, c->d_range + 2 * sp, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         ORBC_CUDA(cudaStreamSynchronize(c->stream));
-        return ORBC_OK;
-    };
-    auto getw = [&](const float4 *src, int *dst) -> int {
-        if (!dst) return ORBC_OK;
-        ORBC_LAUNCH(c, k_unpack_w, nb, kBlock, 0, src, S.n, (int *)c->stage);
-        ORBC_CUDA(cudaMemcpyAsync(dst, c->stage, sizeof(int) * S.n, cudaMemcpyDeviceToHost, c->stream));
-        ORBC_CUDA(cudaStreamSynchronize(c->stream));
-        return ORBC_OK;
-    };
-    ORBC_TRY(get3(S.X(), x)); ORBC_TRY(get3(S.V(), v)); ORBC_TRY(get3(S.N(), n_)); ORBC_TRY(get3(S.O(), o)); ORBC_TRY(get3(S.f, f)); ORBC_TRY(get3(S.t, t));
-    ORBC_TRY(getw(S.X(), type)); ORBC_TRY(getw(S.N(), tag));
-    if (affiliation) {
-        ORBC_CUDA(cudaMemcpyAsync(affiliation, S.C(), sizeof(int) * S.n, cudaMemcpyDeviceToHost, c->stream));
-        ORBC_CUDA(cudaStreamSynchronize(c->stream));
+        first = (size_t)r[0]; count = (size_t)(r[1] - r[0]);
     }
+    if (!count) return check_flags(c);
+    ORBC_TRY(ensure_copy_stream(c));
+    const float4 *src3[6] = {S.X(), S.V(), S.N(), S.O(), S.f, S.t};
+    float *dst3[6] = {x, v, n_, o, f, t};
+    const float4 *srcw[2] = {S.X(), S.N()};
+    int *dstw[2] = {type, tag};
+    size_t need = 0;
+    for (int k = 0; k < 6; ++k) if (dst3[k]) need += count * stride;
+    for (int k = 0; k < 2; ++k) if (dstw[k]) need += count;
+    ORBC_TRY(ensure_stage(c, need + 16));
+    const unsigned nb = blocks_for(count, kBlock);
+    float *p = c->stage;
+    int ev = 0;
+    // unpack on the compute stream, copy out on the copy stream as soon as each array is ready; one wait at the end
+    for (int k = 0; k < 6; ++k) if (dst3[k]) {
+        ORBC_LAUNCH(c, k_unpack3, nb, kBlock, 0, src3[k] + first, count, stride, p);
+        ORBC_CUDA(cudaEventRecord(c->xfer_ev[ev], c->stream));
+        ORBC_CUDA(cudaStreamWaitEvent(c->copy_stream, c->xfer_ev[ev], 0));
+        ORBC_CUDA(cudaMemcpyAsync(dst3[k] + first * stride, p, sizeof(float) * count * stride, cudaMemcpyDeviceToHost, c->copy_stream));
+        p += count * stride; ev = (ev + 1) & 7;
+    }
+    for (int k = 0; k < 2; ++k) if (dstw[k]) {
+        ORBC_LAUNCH(c, k_unpack_w, nb, kBlock, 0, srcw[k] + first, count, (int *)p);
+        ORBC_CUDA(cudaEventRecord(c->xfer_ev[ev], c->stream));
+        ORBC_CUDA(cudaStreamWaitEvent(c->copy_stream, c->xfer_ev[ev], 0));
+        ORBC_CUDA(cudaMemcpyAsync(dstw[k] + first, p, sizeof(int) * count, cudaMemcpyDeviceToHost, c->copy_stream));
+        p += count; ev = (ev + 1) & 7;
+    }
+    if (affiliation) {
+        ORBC_CUDA(cudaEventRecord(c->xfer_ev[ev], c->stream));
+        ORBC_CUDA(cudaStreamWaitEvent(c->copy_stream, c->xfer_ev[ev], 0));
+        ORBC_CUDA(cudaMemcpyAsync(affiliation + first, S.C() + first, sizeof(int) * count, cudaMemcpyDeviceToHost, c->copy_stream));
+    }
+    ORBC_CUDA(cudaStreamSynchronize(c->copy_stream));
+    // the staging area must not be reused by the compute stream before the copies have left it: they have (synchronised above)
     return check_flags(c);
 }
 
@@ -1377,10 +1481,7 @@ int orbc_save_frame(orbc_ctx *c, int nstep, int dump_field, int lipid_tag_base, 
 int orbc_save_frame_begin(orbc_ctx *c, int nstep, int dump_field, int lipid_tag_base) { if (c) cudaSetDevice(c->device);
     if (!c) return fail(ORBC_ERR_ARG, "null ctx");
     if (c->frame_pending >= 2) return fail(ORBC_ERR_ARG, "orbc_save_frame_begin: two frames are already in flight (call orbc_save_frame_end)");
-    if (!c->copy_stream) {
-        ORBC_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-        for (int k = 0; k < 2; ++k) { ORBC_CUDA(cudaEventCreateWithFlags(&c->frame_packed[k], cudaEventDisableTiming)); ORBC_CUDA(cudaEventCreateWithFlags(&c->frame_copied[k], cudaEventDisableTiming)); }
-    }
+    ORBC_TRY(ensure_copy_stream(c));
     const int slot = (c->frame_head + c->frame_pending) & 1;
     size_t total = 0;
     ORBC_TRY(frame_pack(c, slot, nstep, dump_field, lipid_tag_base, &total));

@@ -21,6 +21,7 @@ struct PairArgs {
     int cb, ce, world;     // owned cells of a decomposed run ([0, n_cells) and 1 otherwise)
     const unsigned char *dest_mask;   // decomposed: per cell, the other ranks that own a cell of its r<9 stencil
     int accumulate;        // 1: f, t += (the reference's semantics); 0: f, t = (orbc_run_langevin, where they are known to be dead)
+    unsigned long long *counters;   // k_pair_lipid / k_pair_protein (the cross-check kernels) count their tests and hits here: [1..6] = LL, PL, PP tests / hits
 };
 
 struct F3 { float x, y, z; };
@@ -80,15 +81,18 @@ __global__ void __launch_bounds__(128) k_pair_lipid(PairArgs a) {
     const int *st = a.stencil + (size_t)c * kStencilStride;
     float fx = 0, fy = 0, fz = 0, tx = 0, ty = 0, tz = 0;
     const float cutsqll = c_ff.cutsqll;
+    unsigned tests = 0, hits = 0;
     for (int k = 0; k < n8; ++k) {
         const int c2 = st[k];
         if (k < n6) {
             const int jb = a.cs_l[c2], je = a.cs_l[c2 + 1];
+            tests += je - jb;
             for (int j = jb; j < je; ++j) {
                 const float4 xj = a.xl[j];
                 const F3 d = {xi.x - xj.x, xi.y - xj.y, xi.z - xj.z};
                 const float r2 = dot3(d, d);
                 if (r2 < cutsqll && r2 > 1e-5f) {
+                    ++hits;
                     const float4 nj = a.nl[j];
                     F3 f, q1, q2;
                     poly48(c_ff.cutll, c_ff.attll, c_ff.repll, c_ff.alphall, d, r2, mi, {nj.x, nj.y, nj.z}, f, q1, q2);
@@ -118,6 +122,7 @@ __global__ void __launch_bounds__(128) k_pair_lipid(PairArgs a) {
     float4 f = a.fl[i], t = a.tl[i];
     f.x += fx; f.y += fy; f.z += fz; t.x += tx; t.y += ty; t.z += tz;
     a.fl[i] = f; a.tl[i] = t;
+    if (a.counters) { atomicAdd(a.counters + 1, (unsigned long long)tests); atomicAdd(a.counters + 2, (unsigned long long)hits); }   // one-sided counts
 }
 
 // ---- v1: one thread per protein: protein-protein over r<9 (prote_prote::rmax, :183), protein side of protein-lipid over r<8 ----
@@ -133,10 +138,12 @@ __global__ void __launch_bounds__(128) k_pair_protein(PairArgs a) {
     const int *st = a.stencil + (size_t)c * kStencilStride;
     float fx = 0, fy = 0, fz = 0, tx = 0, ty = 0, tz = 0;
     const float cutsq = c_ff.cutsqlp[type1], ljcut = c_ff.lj_cutsq[type1];
+    unsigned t_pl = 0, h_pl = 0, t_pp = 0, h_pp = 0;
     for (int k = 0; k < n9; ++k) {
         const int c2 = st[k];
         {
             const int jb = a.cs_p[c2], je = a.cs_p[c2 + 1];
+            t_pp += je - jb;
             for (int j = jb; j < je; ++j) {
                 const float4 xj = a.xp[j];
                 const F3 d = {xi.x - xj.x, xi.y - xj.y, xi.z - xj.z};
@@ -144,15 +151,16 @@ __global__ void __launch_bounds__(128) k_pair_protein(PairArgs a) {
                 const int type12 = type1 + __float_as_int(xj.w) * kNType;
                 if (r2 < c_ff.cutsqpp[type12] && r2 > 1e-5f) {
                     const F3 f = rep8(c_ff.cutpp[type12], c_ff.reppp[type12], d, r2);
-                    fx += f.x; fy += f.y; fz += f.z;
+                    fx += f.x; fy += f.y; fz += f.z; ++h_pp;
                 } else if (r2 < c_ff.lj_cutsq[type12] && r2 > 1e-5f) {
                     const F3 f = lj126(c_ff.lj_lj1[type12], c_ff.lj_lj2[type12], d, r2);
-                    fx += f.x; fy += f.y; fz += f.z;
+                    fx += f.x; fy += f.y; fz += f.z; ++h_pp;
                 }
             }
         }
         if (k < n8) {
             const int jb = a.cs_l[c2], je = a.cs_l[c2 + 1];
+            t_pl += je - jb;
             for (int j = jb; j < je; ++j) {
                 const float4 xj = a.xl[j];
                 const F3 d = {xi.x - xj.x, xi.y - xj.y, xi.z - xj.z};
@@ -161,10 +169,10 @@ __global__ void __launch_bounds__(128) k_pair_protein(PairArgs a) {
                     const float4 nj = a.nl[j];
                     F3 f, q1, q2;
                     poly48(c_ff.cutlp[type1], c_ff.attlp[type1], c_ff.replp[type1], c_ff.alphalp[type1], d, r2, mi, {nj.x, nj.y, nj.z}, f, q1, q2);
-                    fx += f.x; fy += f.y; fz += f.z; tx -= q1.x; ty -= q1.y; tz -= q1.z;
+                    fx += f.x; fy += f.y; fz += f.z; tx -= q1.x; ty -= q1.y; tz -= q1.z; ++h_pl;
                 } else if (r2 < ljcut && r2 > 1e-5f) {
                     const F3 f = lj126(c_ff.lj_lj1[type1], c_ff.lj_lj2[type1], d, r2);
-                    fx += f.x; fy += f.y; fz += f.z;
+                    fx += f.x; fy += f.y; fz += f.z; ++h_pl;
                 }
             }
         }
@@ -172,6 +180,10 @@ __global__ void __launch_bounds__(128) k_pair_protein(PairArgs a) {
     float4 f = a.fp[i], t = a.tp[i];
     f.x += fx; f.y += fy; f.z += fz; t.x += tx; t.y += ty; t.z += tz;
     a.fp[i] = f; a.tp[i] = t;
+    if (a.counters) {
+        atomicAdd(a.counters + 3, (unsigned long long)t_pl); atomicAdd(a.counters + 4, (unsigned long long)h_pl);
+        atomicAdd(a.counters + 5, (unsigned long long)t_pp); atomicAdd(a.counters + 6, (unsigned long long)h_pp);   // PP one-sided
+    }
 }
 
 // ---- compute_bonded.h:89-146: F = K (1 - r0 / |dx|) dx, +F on atom i, -F on atom j ----------------------------------------------

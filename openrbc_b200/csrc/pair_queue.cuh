@@ -214,10 +214,13 @@ struct NlState {                    // one per context, in device memory
     int overflow;                   // a list did not fit its row: the next evaluation builds again (and again: no reuse)
     unsigned builds, reuses;        // statistics
 };
-__global__ void k_nl_gate(NlState *st, int force, int moves, float skin) {
+// `shared` (decomposed run): the per-rank maxima of the last integration step, published by k_nl_share into every rank's table
+// (the barrier behind the halo push stands between the two kernels): every rank takes the same maximum and decides alike.
+__global__ void k_nl_gate(NlState *st, int force, int moves, float skin, const unsigned *__restrict__ shared, int world) {
     const int lane = threadIdx.x;
-    unsigned m = max(st->disp[lane], st->disp[lane + 32]);
-    st->disp[lane] = 0u; st->disp[lane + 32] = 0u;
+    unsigned m;
+    if (shared) m = lane < world ? shared[lane] : 0u;
+    else { m = max(st->disp[lane], st->disp[lane + 32]); st->disp[lane] = 0u; st->disp[lane + 32] = 0u; }
     m = __reduce_max_sync(0xffffffffu, m);
     if (lane == 0) {
         const float acc = st->accum + (float)moves * (sqrtf(__uint_as_float(m)) * 1.0001f + 1e-4f);   // + the rounding of x + v dt at |x| ~ 1000
@@ -226,6 +229,15 @@ __global__ void k_nl_gate(NlState *st, int force, int moves, float skin) {
         if (need) { st->overflow = 0; st->builds++; } else st->reuses++;
         st->need = need;
     }
+}
+// decomposed run, after the integrator kernels of a step: this rank's largest squared displacement -> slot `rank` of every rank
+struct NlShare { unsigned *dst[kMaxWorld]; };
+__global__ void k_nl_share(NlState *st, int rank, int world, NlShare d) {
+    const int lane = threadIdx.x;
+    unsigned m = max(st->disp[lane], st->disp[lane + 32]);
+    st->disp[lane] = 0u; st->disp[lane + 32] = 0u;
+    m = __reduce_max_sync(0xffffffffu, m);
+    if (lane < world) d.dst[lane][rank] = m;
 }
 // what the integrators call, with EVERY thread of the block (d2 = 0 for idle ones): the largest squared displacement of the step,
 // one RED per block into 64 slots (one per warp cost 11 us per launch on the RBC)
@@ -453,13 +465,12 @@ __device__ __forceinline__ void pp_pair(int type1, F3 xi, float4 xj, const float
     }
 }
 
-// BUILD (LPP = 1 only): also record, per protein, every lipid closer than its range + skin and every protein closer than its
-// protein-protein range + skin (the hit lists of k_pair_prot_list, see the lipid kernels above).
+// BUILD: also record, per THREAD (LPP threads share a protein, each with its own row), every lipid closer than the protein's range
+// + skin and every protein closer than the pair's range + skin (the hit lists of k_pair_prot_list, see the lipid kernels above).
 template <int LPP, bool BUILD>
 __global__ void __launch_bounds__(kPBlock, 16) k_pair_prot(PairArgs a, const float4 *__restrict__ lbound, const float4 *__restrict__ pbound, CullTable ct,
                                                              const int *__restrict__ porder, const int *__restrict__ gate, int want, PLists nl, float skin) {
     if (gate && *gate != want) return;
-    static_assert(!BUILD || LPP == 1, "hit lists are recorded by the one-lane-per-protein kernel");
     __shared__ float s_cutsqpp[36], s_ljcutsq[36], s_recsq[36];
     __shared__ int s_jb[2][kPBlock / 32][kRangeCap * 32];
     __shared__ unsigned short s_len[2][kPBlock / 32][kRangeCap * 32];
@@ -590,8 +601,9 @@ __global__ void __launch_bounds__(kPBlock, 16) k_pair_prot(PairArgs a, const flo
     }
 }
 
-// The list walker of the proteins: one thread per protein (same thread -> protein map), its recorded partners re-tested with the
-// reference's guards on the current positions.  ~1 protein-lipid hit per protein and step on the RBC: a few microseconds.
+// The list walker of the proteins: the same thread -> (protein, lane) map as the kernel that recorded, every recorded partner
+// re-tested with the reference's guards on the current positions.  ~1 protein-lipid hit per protein and step on the RBC.
+template <int LPP>
 __global__ void __launch_bounds__(kPBlock) k_pair_prot_list(PairArgs a, const int *__restrict__ porder, const int *__restrict__ gate, int want, PLists nl) {
     if (gate && *gate != want) return;
     __shared__ float s_cutsqpp[36], s_ljcutsq[36];
@@ -599,32 +611,44 @@ __global__ void __launch_bounds__(kPBlock) k_pair_prot_list(PairArgs a, const in
     __syncthreads();
     const int n_own = a.range[3] - a.range[2];
     const int l0 = a.range[0], l1 = a.range[1];
-    for (int tid = blockIdx.x * kPBlock + threadIdx.x; tid < n_own; tid += gridDim.x * kPBlock) {
-        const int i = porder[tid];
-        const float4 xi4 = a.xp[i], ni4 = a.np[i];
-        const F3 xi = {xi4.x, xi4.y, xi4.z}, mi = {ni4.x, ni4.y, ni4.z};
-        const int type1 = __float_as_int(xi4.w);
-        const float cutsq = c_ff.cutsqlp[type1], ljcut = c_ff.lj_cutsq[type1];
+    for (int tid0 = blockIdx.x * kPBlock; tid0 / LPP < n_own; tid0 += gridDim.x * kPBlock) {
+        const int tid = tid0 + threadIdx.x;
+        const int pid = tid / LPP, sub = tid % LPP;
+        const bool live = pid < n_own;
+        const int i = live ? porder[pid] : 0;
         float fx = 0, fy = 0, fz = 0, tx = 0, ty = 0, tz = 0;
-        const int nl_ = __ldg(nl.pl_cnt + tid), np_ = __ldg(nl.pp_cnt + tid);
-        const int *row_l = nl.pl + ll_row(tid, nl.cap_pl), *row_p = nl.pp + ll_row(tid, nl.cap_pp);
-        for (int s = 0; s < nl_; s += 4) {                       // four partners at a time: the chain list -> position -> director is all latency
-            int j[4]; float4 xj[4];
-            #pragma unroll
-            for (int u = 0; u < 4; ++u) j[u] = s + u < nl_ ? __ldg(row_l + (size_t)(s + u) * 64) : -1;
-            #pragma unroll
-            for (int u = 0; u < 4; ++u) xj[u] = j[u] >= 0 ? __ldg(a.xl + j[u]) : make_float4(xi.x, xi.y, xi.z, 0.f);   // padding: r2 = 0 fails the guard
-            #pragma unroll
-            for (int u = 0; u < 4; ++u) pl_pair(a, type1, cutsq, ljcut, xi, mi, max(j[u], 0), xj[u], l0, l1, fx, fy, fz, tx, ty, tz);
+        if (live) {
+            const float4 xi4 = a.xp[i], ni4 = a.np[i];
+            const F3 xi = {xi4.x, xi4.y, xi4.z}, mi = {ni4.x, ni4.y, ni4.z};
+            const int type1 = __float_as_int(xi4.w);
+            const float cutsq = c_ff.cutsqlp[type1], ljcut = c_ff.lj_cutsq[type1];
+            const int nl_ = __ldg(nl.pl_cnt + tid), np_ = __ldg(nl.pp_cnt + tid);
+            const int *row_l = nl.pl + ll_row(tid, nl.cap_pl), *row_p = nl.pp + ll_row(tid, nl.cap_pp);
+            for (int s = 0; s < nl_; s += 4) {                   // four partners at a time: the chain list -> position -> director is all latency
+                int j[4]; float4 xj[4];
+                #pragma unroll
+                for (int u = 0; u < 4; ++u) j[u] = s + u < nl_ ? __ldg(row_l + (size_t)(s + u) * 64) : -1;
+                #pragma unroll
+                for (int u = 0; u < 4; ++u) xj[u] = j[u] >= 0 ? __ldg(a.xl + j[u]) : make_float4(xi.x, xi.y, xi.z, 0.f);   // padding: r2 = 0 fails the guard
+                #pragma unroll
+                for (int u = 0; u < 4; ++u) pl_pair(a, type1, cutsq, ljcut, xi, mi, max(j[u], 0), xj[u], l0, l1, fx, fy, fz, tx, ty, tz);
+            }
+            for (int s = 0; s < np_; ++s) {
+                const int j = __ldg(row_p + (size_t)s * 64);
+                pp_pair(type1, xi, __ldg(a.xp + j), s_cutsqpp, s_ljcutsq, fx, fy, fz);
+            }
         }
-        for (int s = 0; s < np_; ++s) {
-            const int j = __ldg(row_p + (size_t)s * 64);
-            pp_pair(type1, xi, __ldg(a.xp + j), s_cutsqpp, s_ljcutsq, fx, fy, fz);
+        #pragma unroll
+        for (int o = 1; o < LPP; o <<= 1) {
+            fx += __shfl_xor_sync(0xffffffffu, fx, o); fy += __shfl_xor_sync(0xffffffffu, fy, o); fz += __shfl_xor_sync(0xffffffffu, fz, o);
+            tx += __shfl_xor_sync(0xffffffffu, tx, o); ty += __shfl_xor_sync(0xffffffffu, ty, o); tz += __shfl_xor_sync(0xffffffffu, tz, o);
         }
-        float4 f = make_float4(0.f, 0.f, 0.f, 0.f), t = f;
-        if (a.accumulate) { f = a.fp[i]; t = a.tp[i]; }
-        f.x += fx; f.y += fy; f.z += fz; t.x += tx; t.y += ty; t.z += tz;
-        a.fp[i] = f; a.tp[i] = t;
+        if (live && sub == 0) {
+            float4 f = make_float4(0.f, 0.f, 0.f, 0.f), t = f;
+            if (a.accumulate) { f = a.fp[i]; t = a.tp[i]; }
+            f.x += fx; f.y += fy; f.z += fz; t.x += tx; t.y += ty; t.z += tz;
+            a.fp[i] = f; a.tp[i] = t;
+        }
     }
 }
 

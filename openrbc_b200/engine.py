@@ -24,7 +24,7 @@ PROF = dict(pair_lipid=0, pair_protein=1, bonded=2, integrate=3, rebuild=4)
 
 EXPORTS = [
     "orbc_create", "orbc_destroy", "orbc_last_error", "orbc_synchronize", "orbc_set_stream", "orbc_forcefield_canonical",
-    "orbc_set_forcefield", "orbc_upload", "orbc_upload_bonds", "orbc_voronoi_upload", "orbc_set_field", "orbc_voronoi_update",
+    "orbc_set_forcefield", "orbc_upload", "orbc_upload_range", "orbc_upload_bonds", "orbc_voronoi_upload", "orbc_set_field", "orbc_voronoi_update",
     "orbc_cell_update", "orbc_rebuild", "orbc_delete_lipid", "orbc_compute_pairwise_fused", "orbc_compute_bonded",
     "orbc_constrain_volume", "orbc_integrate", "orbc_nh_zeta_update", "orbc_nh_zeta_update_unfused", "orbc_compute_temperature", "orbc_run_langevin",
     "orbc_run_nh", "orbc_download", "orbc_size", "orbc_n_cells", "orbc_debug_dump", "orbc_debug_noise", "orbc_event_record",
@@ -99,6 +99,7 @@ def load_library():
         lib.orbc_run_nh.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         for name in ("orbc_synchronize", "orbc_compute_pairwise_fused", "orbc_compute_bonded"):
             getattr(lib, name).argtypes = [C.c_void_p]
+        lib.orbc_upload_range.argtypes = [C.c_void_p, C.c_int, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t] + [C.c_void_p] * 6
         lib.orbc_voronoi_update.argtypes = [C.c_void_p, C.c_int, C.c_int]
         lib.orbc_cell_update.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
         lib.orbc_rebuild.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
@@ -207,15 +208,23 @@ class Simulation:
         return p
 
     # ---- upload / download ------------------------------------------------------------------------------
-    def upload(self, st):
+    def upload(self, st, owned_only=False):
+        """Hand the host's containers to the device.  owned_only (a connected rank of a decomposed run re-uploading its system):
+        only the rows of this rank's own cells travel, mg_export() then fetches the halo from the owners."""
         import time
         t = [time.perf_counter()]
         lx, lv, ln, lo = (_f3(st["l" + f]) for f in "xvno")
-        self._ck(self.lib.orbc_upload(self.ctx, LIPID, len(lx), 3, _p(lx), _p(lv), _p(ln), _p(lo), None, None)); t.append(time.perf_counter())
         px, pv, pn, po = (_f3(st["p" + f]) for f in "xvno")
         ty = np.ascontiguousarray(st["ptype"], np.int32)
         tg = np.ascontiguousarray(st["ptag"], np.int32)
-        self._ck(self.lib.orbc_upload(self.ctx, PROTEIN, len(px), 3, _p(px), _p(pv), _p(pn), _p(po), _p(ty), _p(tg))); t.append(time.perf_counter())
+        if owned_only and self.world > 1:
+            cb, ce = cell_range(len(st["centroids"]), self.rank, self.world)
+            bl, el = int(st["cs_l"][cb]), int(st["cs_l"][ce]); bp, ep = int(st["cs_p"][cb]), int(st["cs_p"][ce])
+            self._ck(self.lib.orbc_upload_range(self.ctx, LIPID, len(lx), bl, el - bl, 3, _p(lx), _p(lv), _p(ln), _p(lo), None, None)); t.append(time.perf_counter())
+            self._ck(self.lib.orbc_upload_range(self.ctx, PROTEIN, len(px), bp, ep - bp, 3, _p(px), _p(pv), _p(pn), _p(po), _p(ty), _p(tg))); t.append(time.perf_counter())
+        else:
+            self._ck(self.lib.orbc_upload(self.ctx, LIPID, len(lx), 3, _p(lx), _p(lv), _p(ln), _p(lo), None, None)); t.append(time.perf_counter())
+            self._ck(self.lib.orbc_upload(self.ctx, PROTEIN, len(px), 3, _p(px), _p(pv), _p(pn), _p(po), _p(ty), _p(tg))); t.append(time.perf_counter())
         bd = np.ascontiguousarray(st["bonds"], np.int32).reshape(-1, 3)
         self._ck(self.lib.orbc_upload_bonds(self.ctx, len(bd), _p(bd))); t.append(time.perf_counter())
         if "centroids" in st:
@@ -225,6 +234,9 @@ class Simulation:
             self._ck(self.lib.orbc_voronoi_upload(self.ctx, len(c), _p(c), _p(csl), _p(csp))); t.append(time.perf_counter())
         # wall time of the four calls (lipids, proteins, bonds, Voronoi state), for the phase breakdown of bench.py
         self.last_upload_ms = [round((b - a) * 1e3, 2) for a, b in zip(t[:-1], t[1:])]
+        rows_l, rows_p = (el - bl, ep - bp) if (owned_only and self.world > 1) else (len(lx), len(px))
+        self.last_upload_bytes = 48 * (rows_l + rows_p) + ty.nbytes + tg.nbytes + bd.nbytes + sum(
+            np.asarray(st[k]).nbytes for k in ("centroids", "cs_l", "cs_p") if k in st)
 
     def size(self, s):
         n = C.c_size_t()
@@ -255,13 +267,16 @@ class Simulation:
     def download_into(self, s, x=None, v=None, n=None, o=None, f=None, t=None, affiliation=False):
         """Download selected fields into caller-owned (e.g. pinned) N x 3 float32 arrays; returns the bytes copied."""
         cnt = self.size(s)
-        aff = np.empty(cnt, np.int32) if affiliation else None
+        aff = affiliation if isinstance(affiliation, np.ndarray) else (np.empty(cnt, np.int32) if affiliation else None)   # a caller-owned (pinned) int32 array, or True
         arrs = [x, v, n, o, f, t]
         for a in arrs:
             assert a is None or (a.dtype == np.float32 and a.flags.c_contiguous and len(a) >= cnt)
         nn = C.c_size_t()
         self._ck(self.lib.orbc_download(self.ctx, s, 3, *[_p(a) for a in arrs], _p(aff), None, None, C.byref(nn)))
-        return sum(12 * cnt for a in arrs if a is not None) + (4 * cnt if affiliation else 0)
+        if self.world > 1:                 # a rank fills (and moves) only the rows it owns
+            b, e = self.owned_range(s)
+            cnt = e - b
+        return sum(12 * cnt for a in arrs if a is not None) + (4 * cnt if aff is not None else 0)
 
     def get(self, s, field):
         return self.download(s, field)[field]

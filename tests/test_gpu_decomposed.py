@@ -21,11 +21,14 @@ def load_state(name):
     return {k[3:]: v for k, v in g.items() if k.startswith("in_")}
 
 
-def make_ranks(st, world, **kw):
+def make_ranks(st, world, opts=None, **kw):
     import torch
     from openrbc_b200 import Simulation
     ndev = torch.cuda.device_count()
     sims = [Simulation(st, rank=r, world=world, device=r % ndev, **kw) for r in range(world)]
+    for s in sims:
+        for k, v in (opts or {}).items():
+            s.set_option(k, v)
     blobs = [s.mg_export() for s in sims]
     for s in sims:
         s.mg_connect(blobs)
@@ -271,5 +274,81 @@ def test_frames_of_the_ranks_combine():
             np.testing.assert_allclose(a.view(np.float32), b.view(np.float32), rtol=0, atol=2e-5 * (1 + np.abs(b.view(np.float32)).max()))
         off += 8 + width * n
     np.testing.assert_array_equal(merged[off:], want[off:])
+    for sim in [one] + sims:
+        sim.close()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_reupload_of_owned_rows_only(world):
+    """orbc_upload_range: connected ranks re-upload only their own rows; orbc_mg_export fetches the halo copies from their owners
+    over the peer mappings.  The run that follows must equal the run after whole uploads (and the single-GPU run)."""
+    from openrbc_b200 import Simulation
+    st = load_state("vesicle_ico0")
+    one = Simulation(st, kBT=0.0)
+    sims = make_ranks(st, world, kBT=0.0)
+    on_all(sims, lambda s: s.run_langevin(3))                 # leave the first state behind: slots, ranges and halos have moved
+    garbage = dict(st)
+    for k in ("lx", "ln", "px", "pn"):
+        garbage[k] = st[k] + np.float32(3.0)                  # what the other ranks' rows must NOT be taken from
+    def reload(s):
+        mine = dict(garbage)
+        cb, ce = __import__("openrbc_b200").engine.cell_range(len(st["centroids"]), s.rank, world)
+        for p, cs in (("l", st["cs_l"]), ("p", st["cs_p"])):
+            b, e = int(cs[cb]), int(cs[ce])
+            for f in "xvno":
+                a = np.array(mine[p + f], copy=True); a[b:e] = st[p + f][b:e]; mine[p + f] = a
+        s.upload(mine, owned_only=True)
+        s.mg_export()
+        s.nstep = 0
+    on_all(sims, reload)
+    one.run_langevin(4)
+    on_all(sims, lambda s: s.run_langevin(4))
+    for s in (0, 1):
+        ref, got = one.download(s, "xvno"), gathered(sims, s, "xvno")
+        for f in "xvno":
+            np.testing.assert_allclose(got[f], ref[f], rtol=0, atol=2e-6 * (1 + np.abs(ref[f]).max(initial=0.0)), err_msg=f)
+    for sim in [one] + sims:
+        sim.close()
+
+
+@pytest.mark.parametrize("name", ["vesicle_ico0", "sphere_r12"])
+def test_launch_bounds_below_the_container_size(name):
+    """With the production slack (8192) the launch bound of the owned-particle kernels equals the container size on these small
+    systems, which hides any kernel that is launched over the bound but indexed from slot 0.  A small slack makes rank 1 own
+    slots BEYOND its launch bound: clear_force, the call-by-call Nose-Hoover kernels and the fused minimiser must still cover them."""
+    from openrbc_b200 import Simulation
+    st = load_state(name)
+    one = Simulation(st, kBT=0.22)
+    sims = make_ranks(st, 2, opts={"debug_own_slack": 32}, kBT=0.22)
+    n_l = len(st["lx"])
+    assert sims[1].owned_range(0)[1] == n_l and n_l // 2 + n_l // 8 + 32 < n_l           # rank 1 owns the tail, the bound stops short of it
+    # dirty forces everywhere, then clear_force: every slot of every rank must be clean afterwards
+    for sim in [one] + sims:
+        for s in (0, 1):
+            if sim.size(s):
+                sim.set_field(s, "f", np.full((sim.size(s), 3), 7.0, np.float32)); sim.set_field(s, "t", np.full((sim.size(s), 3), -3.0, np.float32))
+    one.clear_force()
+    on_all(sims, lambda s: s.clear_force())
+    for sim in sims:
+        for s in (0, 1):
+            d = sim.download(s, "ft")
+            b, e = sim.owned_range(s)
+            assert not d["f"][b:e].any() and not d["t"][b:e].any()
+    # one Nose-Hoover step call by call, then two minimiser iterations
+    def nh_step(s):
+        s.nh_initial_fused(); s.rebuild(); s.compute_pairwise_fused(); s.compute_bonded(); s.nh_final_fused(); s.nstep += 1
+    nh_step(one)
+    on_all(sims, nh_step)
+    for s in (0, 1):
+        ref, got = one.download(s, "xvno"), gathered(sims, s, "xvno")
+        for f in "xvno":
+            np.testing.assert_allclose(got[f], ref[f], rtol=0, atol=2e-6 * (1 + np.abs(ref[f]).max(initial=0.0)), err_msg=f)
+    assert all(abs(s.zeta - one.zeta) <= 1e-6 * abs(one.zeta) for s in sims)
+    one.run_minimize(2)
+    on_all(sims, lambda s: s.run_minimize(2))
+    for s in (0, 1):
+        ref, got = one.download(s, "xn"), gathered(sims, s, "xn")
+        for f in "xn":
+            np.testing.assert_allclose(got[f], ref[f], rtol=0, atol=2e-6 * (1 + np.abs(ref[f]).max(initial=0.0)), err_msg=f)
     for sim in [one] + sims:
         sim.close()
