@@ -226,7 +226,7 @@ int nl_ensure(orbc_ctx *c) {
         ORBC_TRY(dev_alloc(&c->ll_list, groups * 64 * (size_t)c->nl_cap_ll)); ORBC_TRY(dev_alloc(&c->ll_cnt, groups * 64));
         c->ll_list_lipids = L.cap; c->nl_valid = false;
     }
-    const size_t prot_rows = mg_active(c) ? owned_bound(c, ORBC_PROTEIN) * 4 + 64 : P.cap;   // one row per thread of the protein kernel (up to 4 lanes per protein on a rank)
+    const size_t prot_rows = (mg_active(c) ? owned_bound(c, ORBC_PROTEIN) : P.cap) * 4 + 64;   // one row per thread of the protein kernel: up to 4 lanes per protein
     if (P.n && c->pl_list_proteins < prot_rows) {
         const size_t groups = (prot_rows + 63) / 64;
         ORBC_TRY(dev_alloc(&c->pl_list, groups * 64 * (size_t)c->nl_cap_pl)); ORBC_TRY(dev_alloc(&c->pl_cnt, groups * 64));
@@ -349,24 +349,24 @@ int launch_pairwise(orbc_ctx *c, bool accumulate = true) {
                 ORBC_LAUNCH(c, k_lipid_runs, blocks_for(a.ce - a.cb, 128), 128, 0, a.cb, a.ce, c->stencil, c->stencil_cnt, L.cell_start, c->lruns, c->lrun_cnt, c->tile_cap, c->tile_overflow);
                 c->lruns_valid = true;
             }
+            const orbc_forcefield &ff = c->host_ff;
+            const LLConst kc = {ff.cutll, 8.0f * ff.repll, 4.0f * ff.attll, ff.alphall, ff.alphall * ff.attll, 1.0f - ff.alphall, ff.cutsqll};
             if (c->ll_variant == 0) {
                 // warp-per-cell tile kernel; the thread-per-lipid kernel takes the step when a cell does not fit the tile (device flag)
                 const unsigned warps = blocks_for((size_t)(a.ce - a.cb), kTileCells);
-                const orbc_forcefield &ff = c->host_ff;
-                const LLConst kc = {ff.cutll, 8.0f * ff.repll, 4.0f * ff.attll, ff.alphall, ff.alphall * ff.attll, 1.0f - ff.alphall, ff.cutsqll};
                 ORBC_LAUNCH(c, k_pair_ll_t, blocks_for(warps, kTileWarps), kTileWarps * 32, kTileWarps * kTileBytes, a, kc, c->lruns, c->lrun_cnt, c->tile_overflow);
-                ORBC_LAUNCH(c, (k_pair_ll_r<20, 4, false>), kSmallGrid, kLLBlock, 0, a, c->lruns, c->lrun_cnt, c->tile_overflow, 1, LLList{}, 0.f);
+                ORBC_LAUNCH(c, (k_pair_ll_r<20, 4, false>), kSmallGrid, kLLBlock, 0, a, kc, c->lruns, c->lrun_cnt, c->tile_overflow, 1, LLList{}, 0.f);
             } else if (!nl) {
-                ORBC_LAUNCH(c, (k_pair_ll_r<20, 4, false>), blocks_for(nl_count, kLLBlock), kLLBlock, 0, a, c->lruns, c->lrun_cnt, (const int *)nullptr, 0, LLList{}, 0.f);
+                ORBC_LAUNCH(c, (k_pair_ll_r<20, 4, false>), blocks_for(nl_count, kLLBlock), kLLBlock, 0, a, kc, c->lruns, c->lrun_cnt, (const int *)nullptr, 0, LLList{}, 0.f);
             } else {
                 const LLList ll = {c->ll_list, c->ll_cnt, c->nl_cap_ll, nls};
                 if (host_build)                                  // right after a rebuild: record the lists while evaluating
-                    ORBC_LAUNCH(c, (k_pair_ll_r<20, 4, true>), blocks_for(nl_count, kLLBlock), kLLBlock, 0, a, c->lruns, c->lrun_cnt, (const int *)nullptr, 0, ll, c->nl_skin);
+                    ORBC_LAUNCH(c, (k_pair_ll_r<16, 4, true>), blocks_for(nl_count, kLLBlock), kLLBlock, 0, a, kc, c->lruns, c->lrun_cnt, (const int *)nullptr, 0, ll, c->nl_skin);
                 else {                                           // walk the lists; the gate orders a fresh build only if a particle outran the skin
-                    if (c->ll_list_blocks == 12) ORBC_LAUNCH(c, (k_pair_ll_list<12>), blocks_for(nl_count, kLLBlock), kLLBlock, 0, a, &nls->need, 0, ll);
-                    else if (c->ll_list_blocks == 20) ORBC_LAUNCH(c, (k_pair_ll_list<20>), blocks_for(nl_count, kLLBlock), kLLBlock, 0, a, &nls->need, 0, ll);
-                    else ORBC_LAUNCH(c, (k_pair_ll_list<16>), blocks_for(nl_count, kLLBlock), kLLBlock, 0, a, &nls->need, 0, ll);
-                    ORBC_LAUNCH(c, (k_pair_ll_r<20, 4, true>), kSmallGrid, kLLBlock, 0, a, c->lruns, c->lrun_cnt, &nls->need, 1, ll, c->nl_skin);
+                    if (c->ll_list_blocks == 12) ORBC_LAUNCH(c, (k_pair_ll_list<12>), blocks_for(nl_count, kLLBlock), kLLBlock, 0, a, kc, &nls->need, 0, ll);
+                    else if (c->ll_list_blocks == 20) ORBC_LAUNCH(c, (k_pair_ll_list<20>), blocks_for(nl_count, kLLBlock), kLLBlock, 0, a, kc, &nls->need, 0, ll);
+                    else ORBC_LAUNCH(c, (k_pair_ll_list<16>), blocks_for(nl_count, kLLBlock), kLLBlock, 0, a, kc, &nls->need, 0, ll);
+                    ORBC_LAUNCH(c, (k_pair_ll_r<16, 4, true>), kSmallGrid, kLLBlock, 0, a, kc, c->lruns, c->lrun_cnt, &nls->need, 1, ll, c->nl_skin);
                 }
             }
         }
@@ -566,7 +566,7 @@ int preload_kernels() {
     ORBC_PRELOAD(k_cv_normal_volume); ORBC_PRELOAD(k_fill_cellid); ORBC_PRELOAD(k_fill_int); ORBC_PRELOAD(k_halo_push); ORBC_PRELOAD(k_kinetic);
     ORBC_PRELOAD(k_mg_barrier); ORBC_PRELOAD(k_morton_keys); ORBC_PRELOAD(k_morton_keys_only); ORBC_PRELOAD(k_nh_final); ORBC_PRELOAD(k_nh_final_fused);
     ORBC_PRELOAD(k_nh_initial_fused); ORBC_PRELOAD(k_nh_zeta_update); ORBC_PRELOAD(k_share_ke); ORBC_PRELOAD(k_sum_ke); ORBC_PRELOAD(k_noise); ORBC_PRELOAD(k_opt_move); ORBC_PRELOAD(k_pack4);
-    ORBC_PRELOAD(k_pair_lipid); ORBC_PRELOAD(k_lipid_runs); ORBC_PRELOAD(k_rank_only); ORBC_PRELOAD(k_init_centroids); ORBC_PRELOAD(k_bbox); ORBC_PRELOAD((k_pair_ll_r<20, 4, false>)); ORBC_PRELOAD(k_pair_ll_t); ORBC_PRELOAD((k_pair_prot<1, false>)); ORBC_PRELOAD((k_pair_prot<2, false>)); ORBC_PRELOAD((k_pair_prot<4, false>)); ORBC_PRELOAD((k_pair_prot<1, true>)); ORBC_PRELOAD((k_pair_prot<2, true>)); ORBC_PRELOAD((k_pair_prot<4, true>)); ORBC_PRELOAD(k_pair_prot_list<1>); ORBC_PRELOAD(k_pair_prot_list<2>); ORBC_PRELOAD(k_pair_prot_list<4>); ORBC_PRELOAD((k_pair_ll_r<20, 4, true>)); ORBC_PRELOAD((k_pair_ll_list<12>)); ORBC_PRELOAD((k_pair_ll_list<16>)); ORBC_PRELOAD((k_pair_ll_list<20>)); ORBC_PRELOAD(k_nl_gate); ORBC_PRELOAD(k_nl_share); ORBC_PRELOAD(k_pair_protein);
+    ORBC_PRELOAD(k_pair_lipid); ORBC_PRELOAD(k_lipid_runs); ORBC_PRELOAD(k_rank_only); ORBC_PRELOAD(k_init_centroids); ORBC_PRELOAD(k_bbox); ORBC_PRELOAD((k_pair_ll_r<20, 4, false>)); ORBC_PRELOAD(k_pair_ll_t); ORBC_PRELOAD((k_pair_prot<1, false>)); ORBC_PRELOAD((k_pair_prot<2, false>)); ORBC_PRELOAD((k_pair_prot<4, false>)); ORBC_PRELOAD((k_pair_prot<1, true>)); ORBC_PRELOAD((k_pair_prot<2, true>)); ORBC_PRELOAD((k_pair_prot<4, true>)); ORBC_PRELOAD(k_pair_prot_list<1>); ORBC_PRELOAD(k_pair_prot_list<2>); ORBC_PRELOAD(k_pair_prot_list<4>); ORBC_PRELOAD((k_pair_ll_r<16, 4, true>)); ORBC_PRELOAD((k_pair_ll_list<12>)); ORBC_PRELOAD((k_pair_ll_list<16>)); ORBC_PRELOAD((k_pair_ll_list<20>)); ORBC_PRELOAD(k_nl_gate); ORBC_PRELOAD(k_nl_share); ORBC_PRELOAD(k_pair_protein);
     ORBC_PRELOAD(k_permute_centroids); ORBC_PRELOAD(k_porder_flag); ORBC_PRELOAD(k_porder_scatter); ORBC_PRELOAD(k_post_torque); ORBC_PRELOAD(k_radix_hist);
     ORBC_PRELOAD(k_radix_scatter); ORBC_PRELOAD(k_rank_and_move); ORBC_PRELOAD(k_remap_cellid); ORBC_PRELOAD(k_scan_onepass); ORBC_PRELOAD(k_set3); ORBC_PRELOAD(k_set_range); ORBC_PRELOAD(k_set_range_const); ORBC_PRELOAD(k_share_counts);
     ORBC_PRELOAD(k_stencil_build); ORBC_PRELOAD(k_stray_mask); ORBC_PRELOAD(k_unpack3); ORBC_PRELOAD(k_unpack_w); ORBC_PRELOAD(k_verlet_langevin); ORBC_PRELOAD(k_zero4);

@@ -264,7 +264,7 @@ __device__ __forceinline__ size_t ll_row(int i, int cap) { return ((size_t)(i >>
 // *gate == want (the list walker and this kernel are launched together on steps without a rebuild; one of them returns at once).
 // The grid may be smaller than the number of 64-lipid groups (grid-stride), so that a gated launch that returns costs nothing.
 template <int MINB, int W, bool BUILD>
-__global__ void __launch_bounds__(kLLBlock, MINB) k_pair_ll_r(PairArgs a, const int2 *__restrict__ lruns, const int *__restrict__ lrun_info,
+__global__ void __launch_bounds__(kLLBlock, MINB) k_pair_ll_r(PairArgs a, const LLConst kc, const int2 *__restrict__ lruns, const int *__restrict__ lrun_info,
                                                                const int *__restrict__ gate, int want, LLList nl, float skin) {
     if (gate && *gate != want) return;
     __shared__ int s_q[kLLBlock / 32][kQCap * 32];
@@ -272,10 +272,10 @@ __global__ void __launch_bounds__(kLLBlock, MINB) k_pair_ll_r(PairArgs a, const 
     int *const q = s_q[threadIdx.x >> 5] + lane;
     const float4 *__restrict__ xl = a.xl;
     const float4 *__restrict__ nl_ = a.nl;
-    const LLConst kc = {c_ff.cutll, 8.0f * c_ff.repll, 4.0f * c_ff.attll, c_ff.alphall, c_ff.alphall * c_ff.attll, 1.0f - c_ff.alphall, c_ff.cutsqll};
+    // (kc: the lipid-lipid constants as a kernel parameter — read from c_ff they were rematerialised inside the loops)
     // r2 > 1e-5 && r2 < cutsq (compute_pairwise_fused.h:109,134) as ONE unsigned comparison of the bit patterns: r2 is a sum of
     // squares (never negative), and non-negative floats order like their bits; a NaN lies above every finite pattern
-    const float lim = BUILD ? (c_ff.cutll + skin) * (c_ff.cutll + skin) : c_ff.cutsqll;
+    const float lim = BUILD ? (kc.cut + skin) * (kc.cut + skin) : kc.cutsq;
     const unsigned lo_bits = BUILD ? 0u : __float_as_uint(1e-5f) + 1u, span = __float_as_uint(lim) - lo_bits;
     const unsigned q0 = (unsigned)__cvta_generic_to_shared(q);
     const unsigned q_full = q0 + (kQCap - W) * 128;              // a group of W always fits below this mark
@@ -356,11 +356,10 @@ __global__ void __launch_bounds__(kLLBlock, MINB) k_pair_ll_r(PairArgs a, const 
 // The list walker: one thread per lipid, entries read coalesced, two partners in flight per lane.  An entry beyond the lane's
 // count is replaced by the lane's own slot (r2 = 0 fails the guards), which keeps the loop free of branches around the loads.
 template <int MINB>
-__global__ void __launch_bounds__(kLLBlock, MINB) k_pair_ll_list(PairArgs a, const int *__restrict__ gate, int want, LLList nl) {
+__global__ void __launch_bounds__(kLLBlock, MINB) k_pair_ll_list(PairArgs a, const LLConst kc, const int *__restrict__ gate, int want, LLList nl) {
     if (gate && *gate != want) return;
     const float4 *__restrict__ xl = a.xl;
     const float4 *__restrict__ nl_ = a.nl;
-    const LLConst kc = {c_ff.cutll, 8.0f * c_ff.repll, 4.0f * c_ff.attll, c_ff.alphall, c_ff.alphall * c_ff.attll, 1.0f - c_ff.alphall, c_ff.cutsqll};
     const int l0 = a.range[0], l1 = a.range[1];
     for (int base = l0 + blockIdx.x * kLLBlock; base < l1; base += gridDim.x * kLLBlock) {
         const int i = base + threadIdx.x;

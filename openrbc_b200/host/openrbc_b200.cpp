@@ -8,7 +8,8 @@
 // (LANGEVIN + FUSED_PAIRWISE, config_static.h:30-32); ORBC_INTEGRATOR=nh selects the Nose-Hoover pair (FUSED_INTEGRATOR) at run time.
 //
 // Same command line as the reference (`./openrbc_b200 -i trimesh -m <mesh> -E 100 -t 10 ...`), same outputs (cell.data, cell.orbc,
-// the 4-column progress table, the final "T s on K steps * N particles" line).  Extra environment: ORBC_DEVICE (default 0),
+// the 4-column progress table, the final "T s on K steps * N particles" line).  Extra environment: ORBC_DEVICE (default 0) or
+// ORBC_DEVICES=0,1,... (one cell split over several GPUs of the box),
 // ORBC_TIMERS=1 (per-call timers with a stream sync, like the reference's Timers report).
 #include <limits>
 #include <fstream>
@@ -72,7 +73,15 @@ int main( int argc, char ** argv ) {
     Service<Timers>::call().report( true );
 
     // ---- hand the containers to the device --------------------------------------------------------------------------------
-    b200::Device dev( env_dev ? std::atoi( env_dev ) : 0 );
+    // ORBC_DEVICES=0,1,2,3: the cell is split over these GPUs (contiguous ranges of the Morton-ordered Voronoi cells per GPU, the
+    // reference's own partition over its workers, util_numa.h:30-45); ORBC_DEVICE=k or nothing: one GPU
+    std::vector<int> devices;
+    if ( const char * env_devs = std::getenv( "ORBC_DEVICES" ) ) {
+        std::stringstream ss( env_devs );
+        for ( std::string tok; std::getline( ss, tok, ',' ); ) if ( tok.size() ) devices.push_back( std::atoi( tok.c_str() ) );
+    }
+    if ( devices.empty() ) devices.push_back( env_dev ? std::atoi( env_dev ) : 0 );
+    b200::Device dev( devices );
     dev.time_calls = std::getenv( "ORBC_TIMERS" ) != nullptr;
     dev.upload( lipid, protein, voronoi, cell_lipid, cell_protein );
 
@@ -85,7 +94,7 @@ int main( int argc, char ** argv ) {
         b200::compute_pairwise_fused( dev );
         b200::compute_bonded( dev );
     };
-    auto dump = [&]() { b200::save_frame( dev, traj, lipid, param ); };
+    auto dump = [&]() { b200::save_frame( dev, traj, lipid, protein, cell_lipid, cell_protein, param ); };
 
     // ---- energy minimisation (openrbc.cpp:88-146) ---------------------------------------------------------------------------
     std::cout << "Opt..." << std::endl;
@@ -101,7 +110,7 @@ int main( int argc, char ** argv ) {
         if ( ( nopt + 1 ) % param.freq_display == 0 )
             display( std::cout, nopt + 1, b200::compute_temperature( dev ), omp_get_wtime() - Service<Timers>::call()["+optimization"].get_start_time() );
     }
-    orbc_synchronize( dev.ctx );
+    dev.synchronize();
     b200::flush_frames( dev, traj );
     Service<Timers>::call()["+optimization"].stop();
     Service<Timers>::call().report( true );
@@ -136,15 +145,15 @@ int main( int argc, char ** argv ) {
         if ( param.nstep % param.freq_display == 0 )
             display( std::cout, param.nstep * param.dt, b200::compute_temperature( dev ), omp_get_wtime() - Service<Timers>::call()["+main-loop"].get_start_time() );
     }
-    orbc_synchronize( dev.ctx );
+    dev.synchronize();
     b200::flush_frames( dev, traj );
 
     std::size_t nl = 0, np = 0;
     orbc_size( dev.ctx, ORBC_LIPID, &nl ); orbc_size( dev.ctx, ORBC_PROTEIN, &np );
     unsigned long long launches = 0;
-    orbc_launch_count( dev.ctx, &launches );
+    for ( auto c : dev.ranks ) { unsigned long long l = 0; orbc_launch_count( c, &l ); launches += l; }
     std::stringstream msg;
-    msg << param.nstep << " steps * " << nl + np << " particles on 1 B200 (" << launches << " kernel launches).";
+    msg << param.nstep << " steps * " << nl + np << " particles on " << dev.world() << " B200 (" << launches << " kernel launches).";
     display_timing( std::cout, Service<Timers>::call()["+main-loop"].stop(), msg.str().c_str() );
     return 0;
 }

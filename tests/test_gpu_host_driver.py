@@ -72,3 +72,29 @@ def test_same_command_line_same_trajectory(tmp_path):
     assert np.quantile(d, 0.999) < 2e-3, float(np.quantile(d, 0.999))
     dn = np.abs(last_o["ROTATION"] - last_r["ROTATION"]).max(axis=1)
     assert np.quantile(dn, 0.999) < 2e-3
+
+
+@pytest.mark.skipif(not os.path.exists(OURS), reason="host program not built (python __graft_entry__.py build where the reference tree exists)")
+def test_one_cell_over_several_contexts_from_the_cpp_host(tmp_path):
+    """ORBC_DEVICES=a,b: the C++ host program splits the cell over several device contexts of ONE process (b200::Device with N
+    ranks, peer pointers instead of IPC handles; the reference's own partition of the cells over its workers, util_numa.h:30-45).
+    Same command line, same trajectory as on one context.  On a one-GPU box both ranks share the device."""
+    import torch
+    ndev = torch.cuda.device_count()
+    devs = "0,1" if ndev >= 2 else "0,0"
+    env1 = dict(os.environ, OMP_NUM_THREADS="1")
+    env2 = dict(os.environ, OMP_NUM_THREADS="1", ORBC_DEVICES=devs)
+    outs = {}
+    for name, env in (("one", env1), ("two", env2)):
+        d = tmp_path / name; d.mkdir()
+        r = subprocess.run([OURS] + ARGS, cwd=d, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+        assert r.returncode == 0 and "Error" not in r.stdout, r.stdout[-2000:]
+        outs[name] = (r.stdout, read_frames(d / "cell.orbc"))
+    assert "on 2 B200" in outs["two"][0] and "on 1 B200" in outs["one"][0]
+    f1, f2 = outs["one"][1], outs["two"][1]
+    assert [f["nstep"] for f in f1] == [f["nstep"] for f in f2] and len(f1) >= 2
+    for a, b in zip(f1, f2):
+        np.testing.assert_array_equal(a["identity"], b["identity"])
+        np.testing.assert_array_equal(a["VORONOI"], b["VORONOI"])
+        for k in ("POSITION", "VELOCITY", "ROTATION"):
+            assert np.abs(a[k] - b[k]).max() <= 2e-5 * (1 + np.abs(a[k]).max()), k
