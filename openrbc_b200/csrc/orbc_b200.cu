@@ -562,7 +562,7 @@ int preload_kernels() {
 #define ORBC_PRELOAD(k) ORBC_CUDA(cudaFuncGetAttributes(&fa, (const void *)(k)))
     ORBC_PRELOAD(k_assign_nearest); ORBC_PRELOAD(k_bin_count); ORBC_PRELOAD(k_bin_fill); ORBC_PRELOAD(k_bond_mask); ORBC_PRELOAD(k_bonded);
     ORBC_PRELOAD(k_bounce_back); ORBC_PRELOAD(k_build_tag2idx); ORBC_PRELOAD(k_cell_bounds); ORBC_PRELOAD(k_cell_scatter); ORBC_PRELOAD(k_cell_totals);
-    ORBC_PRELOAD(k_centroid_update); ORBC_PRELOAD(k_clear_force); ORBC_PRELOAD(k_compact); ORBC_PRELOAD(k_cv_apply); ORBC_PRELOAD(k_cv_center); ORBC_PRELOAD(k_cv_share); ORBC_PRELOAD(k_sum_partials); ORBC_PRELOAD(k_opt_fused); ORBC_PRELOAD(k_frame_pack);
+    ORBC_PRELOAD(k_centroid_update); ORBC_PRELOAD(k_clear_force); ORBC_PRELOAD(k_compact); ORBC_PRELOAD(k_count_strays); ORBC_PRELOAD(k_cv_apply); ORBC_PRELOAD(k_cv_center); ORBC_PRELOAD(k_cv_share); ORBC_PRELOAD(k_sum_partials); ORBC_PRELOAD(k_opt_fused); ORBC_PRELOAD(k_frame_pack);
     ORBC_PRELOAD(k_cv_normal_volume); ORBC_PRELOAD(k_fill_cellid); ORBC_PRELOAD(k_fill_int); ORBC_PRELOAD(k_halo_push); ORBC_PRELOAD(k_kinetic);
     ORBC_PRELOAD(k_mg_barrier); ORBC_PRELOAD(k_morton_keys); ORBC_PRELOAD(k_morton_keys_only); ORBC_PRELOAD(k_nh_final); ORBC_PRELOAD(k_nh_final_fused);
     ORBC_PRELOAD(k_nh_initial_fused); ORBC_PRELOAD(k_nh_zeta_update); ORBC_PRELOAD(k_share_ke); ORBC_PRELOAD(k_sum_ke); ORBC_PRELOAD(k_noise); ORBC_PRELOAD(k_opt_move); ORBC_PRELOAD(k_pack4);
@@ -1010,6 +1010,15 @@ int orbc_delete_lipid(orbc_ctx *c, float tol, size_t *n_out) { if (c) cudaSetDev
         // compaction + cell_lipid.update of cleanup.h:62-85 in one pass).  All ranks learn the new size from the same cell_start.
         if (c->mg.ce > c->mg.cb)
             ORBC_LAUNCH(c, k_stray_mask, blocks_for((size_t)(c->mg.ce - c->mg.cb) * 32, kBlock), kBlock, 0, L.cell_start, c->mg.cb, c->mg.ce, c->centroid, L.X(), tol, c->mg.keep);
+        // nothing to delete anywhere: the reference leaves the partition alone (cleanup.h:62 `if ( size_new < n )`), so must every rank —
+        // a re-partition here would change the membership the next voronoi.update averages over.  The ranks add up their counts.
+        ORBC_CUDA(cudaMemsetAsync(c->d_acc, 0, sizeof(double), c->stream));
+        ORBC_LAUNCH(c, k_count_strays, blocks_for(owned_bound(c, ORBC_LIPID), kBlock), kBlock, 0, c->mg.keep, c->d_range, c->d_acc);
+        ORBC_TRY(mg_share_ke(c)); ORBC_TRY(mg_barrier(c));
+        ORBC_LAUNCH(c, k_sum_ke, 1, 32, 0, c->d_acc, mg_ke_slots(c), c->mg.world);
+        ORBC_CUDA(cudaMemcpyAsync(c->h_acc, c->d_acc, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        ORBC_CUDA(cudaStreamSynchronize(c->stream));
+        if (c->h_acc[0] == 0.0) { if (n_out) *n_out = L.n; return check_flags(c); }
         ORBC_TRY(cell_update_assign(c, ORBC_LIPID, c->mg.keep)); ORBC_TRY(mg_barrier(c));
         ORBC_TRY(cell_update_move(c, ORBC_LIPID));               ORBC_TRY(mg_barrier(c));
         ORBC_TRY(cell_update_finish(c, ORBC_LIPID));             ORBC_TRY(mg_barrier(c));

@@ -395,6 +395,14 @@ __global__ void k_stray_mask(const int *__restrict__ cell_start, int c_beg, int 
     const float threshold = __fmul_rn(__fmul_rn(med, tol), tol);
     for (int e = lane; e < m; e += 32) keep[b + e] = dist2_rn(x[b + e], q) < threshold ? 1 : 0;
 }
+// decomposed delete_lipid: lipids of the owned slots that do NOT survive (acc[0] += count); integrate.cuh's block_add_double is not
+// visible here, a warp reduction + one atomic per warp does
+__global__ void k_count_strays(const int *__restrict__ keep, const int *__restrict__ range, double *acc) {
+    const int i = range[0] + blockIdx.x * blockDim.x + threadIdx.x;
+    int gone = (i < range[1] && !keep[i]) ? 1 : 0;
+    gone = __reduce_add_sync(0xffffffffu, gone);
+    if ((threadIdx.x & 31) == 0 && gone) atomicAdd(acc, (double)gone);
+}
 __global__ void k_compact(const int *__restrict__ keep, const int *__restrict__ newpos, size_t n,
                           const float4 *__restrict__ x0, const float4 *__restrict__ n0, const float4 *__restrict__ v0, const float4 *__restrict__ o0, const int *__restrict__ c0,
                           float4 *__restrict__ x1, float4 *__restrict__ n1, float4 *__restrict__ v1, float4 *__restrict__ o1, int *__restrict__ c1) {

@@ -43,6 +43,7 @@ int main( int argc, char ** argv ) {
     const char * env_dev = std::getenv( "ORBC_DEVICE" );
     const char * env_int = std::getenv( "ORBC_INTEGRATOR" );
     const bool nose_hoover = env_int && std::string( env_int ) == "nh";
+    const bool fused_opt = std::getenv( "ORBC_OPT_FUSED" ) != nullptr;   // one pass per minimisation step also on a single GPU
 
     // ---- host initialisation: the reference's code, unchanged (openrbc.cpp:51-79) --------------------------------------------
     std::cout << "Initializing system ..." << std::flush;
@@ -103,9 +104,11 @@ int main( int argc, char ** argv ) {
         rebuild();
         b200::integrate( dev, b200::clear_force() );
         forces();
-        b200::integrate( dev, b200::post_torque() );
-        b200::opt_move( dev, param );
-        b200::integrate( dev, b200::bounce_back( param ) );
+        if ( dev.world() == 1 && !fused_opt ) {
+            b200::integrate( dev, b200::post_torque() );
+            b200::opt_move( dev, param );
+            b200::integrate( dev, b200::bounce_back( param ) );
+        } else b200::opt_fused( dev, param );                     // the same three operations in one pass, with the halo push
         if ( ( nopt + 1 ) % param.freq_dump == 0 ) dump();
         if ( ( nopt + 1 ) % param.freq_display == 0 )
             display( std::cout, nopt + 1, b200::compute_temperature( dev ), omp_get_wtime() - Service<Timers>::call()["+optimization"].get_start_time() );

@@ -236,6 +236,9 @@ inline void integrate( Device & dev, verlet_nh_final const & k ) { integrate_id(
 inline void integrate( Device & dev, verlet_nh_update const & k ) { integrate_id( dev, ORBC_NH_UPDATE, "verlet_nh_update", &k.parameter ); }
 // the minimiser's capped steepest-descent move (openrbc.cpp:114-131), a plain loop in the reference
 inline void opt_move( Device & dev, RTParameter & param ) { integrate_id( dev, ORBC_OPT_MOVE, "OptIntegration", &param ); }
+// post_torque + mover + bounce_back of one minimisation step (openrbc.cpp:110-133) as one pass; the form a decomposed run uses
+// (the new positions are pushed to the neighbouring ranks from the same kernel)
+inline void opt_fused( Device & dev, RTParameter & param ) { integrate_id( dev, ORBC_OPT_FUSED, "OptIntegration", &param ); }
 
 }  // namespace b200
 }  // namespace openrbc

@@ -352,3 +352,29 @@ def test_launch_bounds_below_the_container_size(name):
             np.testing.assert_allclose(got[f], ref[f], rtol=0, atol=2e-6 * (1 + np.abs(ref[f]).max(initial=0.0)), err_msg=f)
     for sim in [one] + sims:
         sim.close()
+
+
+def test_delete_lipid_that_deletes_nothing_leaves_the_partition_alone():
+    """cleanup.h:62: `if ( size_new < n )` — without a stray the reference neither compacts nor re-partitions, and the next
+    voronoi.update averages over the OLD membership.  A decomposed run must not re-partition either (it used to)."""
+    from openrbc_b200 import Simulation
+    st = load_state("vesicle_ico0")
+    one = Simulation(st, kBT=0.22)
+    sims = make_ranks(st, 2, kBT=0.22)
+    one.run_langevin(1)                                       # one step: the partition is now stale (rebuild at step 0 only)
+    on_all(sims, lambda s: s.run_langevin(1))
+    before = one.dump("cell_start_l").copy()
+    assert one.delete_lipid(1e9) == len(st["lx"])
+    out = {}
+    on_all(sims, lambda s: out.__setitem__(s.rank, s.delete_lipid(1e9)))
+    assert all(v == len(st["lx"]) for v in out.values())
+    for sim in [one] + sims:
+        np.testing.assert_array_equal(sim.dump("cell_start_l"), before)
+    one.run_langevin(3)
+    on_all(sims, lambda s: s.run_langevin(3))
+    np.testing.assert_array_equal(sims[0].dump("cell_start_l"), one.dump("cell_start_l"))
+    ref, got = one.download(0, "xvno"), gathered(sims, 0, "xvno")
+    for f in "xvno":
+        np.testing.assert_allclose(got[f], ref[f], rtol=0, atol=2e-5 * (1 + np.abs(ref[f]).max(initial=0.0)), err_msg=f)
+    for sim in [one] + sims:
+        sim.close()
