@@ -25,7 +25,7 @@ inline int fail(int code, const char *fmt, ...) {
 
 constexpr int kNType = 6;              // forcefield_canonical.h:37
 constexpr int kStencilStride = ORBC_STENCIL_STRIDE;
-constexpr float kBin = 9.0f;           // centroid grid bin = largest centroid stencil radius (compute_pairwise_fused.h:183)
+constexpr float kBin = 10.0f;          // centroid grid bin = largest centroid stencil radius (9, compute_pairwise_fused.h:183) + the margin of the wide stencils (rebuild.cuh)
 constexpr int kMaxWorld = 8;           // ranks of one spatially decomposed run (one B200 box)
 
 // device image of the force field + derived Langevin coefficients, in __constant__ memory
@@ -131,6 +131,9 @@ struct orbc_ctx {
     int *stencil = nullptr;                       // n_cells x kStencilStride
     int *stencil_cnt = nullptr;                   // n_cells, packed n6 | n8 << 8 | n9 << 16
     bool stencil_valid = false;
+    int *wide = nullptr, *wide_cnt = nullptr; float4 *cen_ref = nullptr;   // wide stencils (r < 9 + margin) and the centroids they were recorded at (rebuild.cuh)
+    int *wide_ok = nullptr;                       // device flag: no centroid has outrun the margin since
+    bool wide_valid = false;                      // the wide stencils match the current numbering of the cells (host's view)
     float4 *cell_normal = nullptr;                // constrain_volume's persistent scratch
     float4 *lbound = nullptr, *pbound = nullptr;  // per-cell bounding spheres of the current lipids / proteins (pair_queue.cuh)
     int2 *lruns = nullptr; int *lrun_cnt = nullptr; size_t lruns_cells = 0;   // merged candidate runs of every cell's r<6 stencil + packed per-cell info (k_lipid_runs)

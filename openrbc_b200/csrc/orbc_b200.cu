@@ -157,7 +157,7 @@ int check_flags(orbc_ctx *c) {
 }
 
 // grid + stencils from the current centroids (the part of VoronoiDiagram::update that replaces tree.build, voronoi.h:83)
-int build_index(orbc_ctx *c, bool all_cells = true) {
+int build_index(orbc_ctx *c, bool all_cells = true, bool renumbered = true) {
     const int nc = c->n_cells;
     Grid &g = c->grid;
     ORBC_CUDA(cudaMemsetAsync(g.bin_start, 0, sizeof(int) * ((size_t)g.nbins + 1), c->stream));
@@ -172,7 +172,20 @@ int build_index(orbc_ctx *c, bool all_cells = true) {
     if (!c->mg.need) halo.own.world = 1;                         // before orbc_mg_export: no halo bookkeeping yet
     const bool part = mg_active(c) && !all_cells;
     const int c0 = part ? c->mg.cb : 0, c1 = part ? c->mg.ce : nc;
-    if (c1 > c0) ORBC_LAUNCH(c, k_stencil_build, blocks_for(c1 - c0, kStencilWarps), kStencilWarps * 32, 0, c->centroid, c0, c1, gd, c->stencil, c->stencil_cnt, c->d_flags, halo);
+    const WideOut wide = {c->wide, c->wide_cnt, c->cen_ref};
+    if (c1 > c0) {
+        if (c->wide_valid && !renumbered) {
+            // the cells kept their numbers since the last full search: re-classify the recorded neighbours (k_stencil_refresh); the full
+            // search stands by behind a device flag in case a centroid has outrun the margin
+            ORBC_CUDA(cudaMemsetAsync(c->wide_ok, 0xff, sizeof(int), c->stream));
+            ORBC_LAUNCH(c, k_centroid_disp, blocks_for(nc, kBlock), kBlock, 0, c->centroid, c->cen_ref, nc, c->wide_ok);
+            ORBC_LAUNCH(c, k_stencil_refresh, blocks_for(c1 - c0, kStencilWarps), kStencilWarps * 32, 0, c->centroid, c0, c1, c->wide, c->wide_cnt, c->stencil, c->stencil_cnt, c->d_flags, halo, c->wide_ok);
+            ORBC_LAUNCH(c, k_stencil_build, 148 * 4, kStencilWarps * 32, 0, c->centroid, c0, c1, gd, c->stencil, c->stencil_cnt, c->d_flags, halo, wide, c->wide_ok);
+        } else {
+            ORBC_LAUNCH(c, k_stencil_build, blocks_for(c1 - c0, kStencilWarps), kStencilWarps * 32, 0, c->centroid, c0, c1, gd, c->stencil, c->stencil_cnt, c->d_flags, halo, wide, (const int *)nullptr);
+            c->wide_valid = true;                                // (a rank's partial search records its own cells: all its refreshes need)
+        }
+    }
     c->stencil_valid = true;
     c->lruns_valid = false;
     return ORBC_OK;
@@ -439,7 +452,7 @@ int do_voronoi_update(orbc_ctx *c, int nstep, int freq_sort_ctrd) {
         std::swap(c->centroid, c->centroid_tmp);
         c->mg.cen_par ^= 1;
     }
-    return build_index(c, morton);
+    return build_index(c, morton, morton);
 }
 
 // VCellList::update in three phases, so that a decomposed rebuild can run both containers through each phase between two
@@ -569,7 +582,7 @@ int preload_kernels() {
     ORBC_PRELOAD(k_pair_lipid); ORBC_PRELOAD(k_lipid_runs); ORBC_PRELOAD(k_rank_only); ORBC_PRELOAD(k_init_centroids); ORBC_PRELOAD(k_bbox); ORBC_PRELOAD((k_pair_ll_r<20, 4, false>)); ORBC_PRELOAD(k_pair_ll_t); ORBC_PRELOAD((k_pair_prot<1, false>)); ORBC_PRELOAD((k_pair_prot<2, false>)); ORBC_PRELOAD((k_pair_prot<4, false>)); ORBC_PRELOAD((k_pair_prot<1, true>)); ORBC_PRELOAD((k_pair_prot<2, true>)); ORBC_PRELOAD((k_pair_prot<4, true>)); ORBC_PRELOAD(k_pair_prot_list<1>); ORBC_PRELOAD(k_pair_prot_list<2>); ORBC_PRELOAD(k_pair_prot_list<4>); ORBC_PRELOAD((k_pair_ll_r<16, 4, true>)); ORBC_PRELOAD((k_pair_ll_list<12>)); ORBC_PRELOAD((k_pair_ll_list<16>)); ORBC_PRELOAD((k_pair_ll_list<20>)); ORBC_PRELOAD(k_nl_gate); ORBC_PRELOAD(k_nl_share); ORBC_PRELOAD(k_pair_protein);
     ORBC_PRELOAD(k_permute_centroids); ORBC_PRELOAD(k_porder_flag); ORBC_PRELOAD(k_porder_scatter); ORBC_PRELOAD(k_post_torque); ORBC_PRELOAD(k_radix_hist);
     ORBC_PRELOAD(k_radix_scatter); ORBC_PRELOAD(k_rank_and_move); ORBC_PRELOAD(k_remap_cellid); ORBC_PRELOAD(k_scan_onepass); ORBC_PRELOAD(k_set3); ORBC_PRELOAD(k_set_range); ORBC_PRELOAD(k_set_range_const); ORBC_PRELOAD(k_share_counts);
-    ORBC_PRELOAD(k_stencil_build); ORBC_PRELOAD(k_stray_mask); ORBC_PRELOAD(k_unpack3); ORBC_PRELOAD(k_unpack_w); ORBC_PRELOAD(k_verlet_langevin); ORBC_PRELOAD(k_zero4);
+    ORBC_PRELOAD(k_stencil_build); ORBC_PRELOAD(k_stencil_refresh); ORBC_PRELOAD(k_centroid_disp); ORBC_PRELOAD(k_stray_mask); ORBC_PRELOAD(k_unpack3); ORBC_PRELOAD(k_unpack_w); ORBC_PRELOAD(k_verlet_langevin); ORBC_PRELOAD(k_zero4);
 #undef ORBC_PRELOAD
     return ORBC_OK;
 }
@@ -610,6 +623,8 @@ int alloc_voronoi(orbc_ctx *c, int nc) {
     ORBC_TRY(dev_alloc(&c->keys, nc)); ORBC_TRY(dev_alloc(&c->keys_tmp, nc)); ORBC_TRY(dev_alloc(&c->perm, nc)); ORBC_TRY(dev_alloc(&c->perm_tmp, nc)); ORBC_TRY(dev_alloc(&c->inv, nc));
     ORBC_TRY(dev_alloc(&c->grid.bin_items, nc)); ORBC_TRY(dev_alloc(&c->grid.bin_of, nc)); ORBC_TRY(dev_alloc(&c->grid.bin_slot, nc)); ORBC_TRY(dev_alloc(&c->grid.sorted, nc));
     ORBC_TRY(dev_alloc(&c->stencil, (size_t)nc * kStencilStride)); ORBC_TRY(dev_alloc(&c->stencil_cnt, nc));
+    ORBC_TRY(dev_alloc(&c->wide, (size_t)nc * kStencilStride)); ORBC_TRY(dev_alloc(&c->wide_cnt, nc)); ORBC_TRY(dev_alloc(&c->cen_ref, nc)); ORBC_TRY(dev_alloc(&c->wide_ok, 1));
+    c->wide_valid = false;
     ORBC_TRY(dev_alloc(&c->cell_normal, nc)); ORBC_TRY(dev_alloc(&c->lbound, nc)); ORBC_TRY(dev_alloc(&c->pbound, nc));
     ORBC_TRY(dev_alloc(&c->lruns, (size_t)nc * kRunStride)); ORBC_TRY(dev_alloc(&c->lrun_cnt, (size_t)nc)); c->lruns_cells = (size_t)nc;
     for (int s = 0; s < 2; ++s) ORBC_TRY(dev_alloc(&c->sp[s].cell_start, (size_t)nc + 1));
@@ -705,7 +720,7 @@ void orbc_destroy(orbc_ctx *c) { if (c) cudaSetDevice(c->device);
     free_species(c->sp[0]); free_species(c->sp[1]);
     dev_free(c->centroid); dev_free(c->centroid_tmp); dev_free(c->keys); dev_free(c->keys_tmp); dev_free(c->perm); dev_free(c->perm_tmp); dev_free(c->inv);
     dev_free(c->grid.bin_start); dev_free(c->grid.bin_items); dev_free(c->grid.bin_of); dev_free(c->grid.bin_slot); dev_free(c->grid.sorted);
-    dev_free(c->stencil); dev_free(c->stencil_cnt); dev_free(c->cell_normal); dev_free(c->lbound); dev_free(c->pbound); dev_free(c->porder); dev_free(c->lruns); dev_free(c->lrun_cnt); dev_free(c->bonds); dev_free(c->tag2idx);
+    dev_free(c->stencil); dev_free(c->stencil_cnt); dev_free(c->wide); dev_free(c->wide_cnt); dev_free(c->cen_ref); dev_free(c->wide_ok); dev_free(c->cell_normal); dev_free(c->lbound); dev_free(c->pbound); dev_free(c->porder); dev_free(c->lruns); dev_free(c->lrun_cnt); dev_free(c->bonds); dev_free(c->tag2idx);
     dev_free(c->scan_tmp); dev_free(c->radix_hist); dev_free(c->stage); dev_free(c->d_acc); dev_free(c->d_counters); dev_free(c->d_flags); dev_free(c->d_nh);
     dev_free(c->noise[0]); dev_free(c->noise[1]); dev_free(c->d_range); dev_free(c->tile_overflow);
     { NlState *st = (NlState *)c->nl_state; dev_free(st); } dev_free(c->ll_list); dev_free(c->ll_cnt); dev_free(c->pl_list); dev_free(c->pl_cnt); dev_free(c->pp_list); dev_free(c->pp_cnt);
@@ -816,16 +831,16 @@ static int upload_rows(orbc_ctx *c, int sp, size_t n, size_t first, size_t count
     ORBC_CUDA(cudaStreamSynchronize(c->stream));   // host arrays are borrowed only for the duration of the call
     if (sp == ORBC_PROTEIN) {
         c->porder_valid = false;
-        c->type_mask = 0;
-        for (size_t i = 0; i < n; ++i) {
-            const int t = type ? type[i] : 0;
-            if (t < 0 || t >= kNType) return fail(ORBC_ERR_ARG, "protein %zu has type %d outside [0,%d)", i, t, kNType);
-            c->type_mask |= 1u << t;
-        }
+        c->type_mask = type ? 0u : 1u;
+        unsigned bad = 0, mask = 0;
+        if (type) for (size_t i = 0; i < n; ++i) { const unsigned t = (unsigned)type[i]; bad |= t >= (unsigned)kNType; mask |= 1u << (t & 31u); }
+        if (bad) for (size_t i = 0; i < n; ++i) if (type[i] < 0 || type[i] >= kNType) return fail(ORBC_ERR_ARG, "protein %zu has type %d outside [0,%d)", i, type[i], kNType);
+        c->type_mask |= mask;
     }
     if (sp == ORBC_PROTEIN && tag) {
-        int mx = 0;
-        for (size_t i = 0; i < n; ++i) { if (tag[i] < 0) return fail(ORBC_ERR_ARG, "negative protein tag"); mx = std::max(mx, tag[i]); }
+        int mx = 0, mn = 0;
+        for (size_t i = 0; i < n; ++i) { mn = std::min(mn, tag[i]); mx = std::max(mx, tag[i]); }
+        if (mn < 0) return fail(ORBC_ERR_ARG, "negative protein tag");
         if (c->tag2idx_size < (size_t)mx + 1) { ORBC_TRY(dev_alloc(&c->tag2idx, (size_t)mx + 1)); c->tag2idx_size = (size_t)mx + 1; }
         ORBC_CUDA(cudaMemsetAsync(c->tag2idx, 0xff, sizeof(int) * c->tag2idx_size, c->stream));
         ORBC_TRY(build_tag2idx(c));
@@ -854,11 +869,20 @@ int orbc_upload_range(orbc_ctx *c, int sp, size_t n, size_t first, size_t count,
 
 int orbc_upload_bonds(orbc_ctx *c, size_t n_bonds, const int *tij) { if (c) cudaSetDevice(c->device);
     if (!c || (n_bonds && !tij)) return fail(ORBC_ERR_ARG, "orbc_upload_bonds: bad argument");
+    // validation in two passes: a branch-free min / max sweep (vectorised by the compiler: the sweep sits inside the timed upload of
+    // every job), and the search for the offending bond only when the sweep found one
+    int tmin = 0, tmax = 0, gmin = 0, gmax = 0;
     for (size_t b = 0; b < n_bonds; ++b) {
-        if (tij[3 * b] < 0 || tij[3 * b] >= 4) return fail(ORBC_ERR_ARG, "bond %zu has type %d outside [0,4)", b, tij[3 * b]);
-        if ((size_t)tij[3 * b + 1] >= c->tag2idx_size || (size_t)tij[3 * b + 2] >= c->tag2idx_size || tij[3 * b + 1] < 0 || tij[3 * b + 2] < 0)
-            return fail(ORBC_ERR_ARG, "bond %zu refers to a tag that no uploaded protein carries (upload proteins first)", b);
+        const int t = tij[3 * b], i = tij[3 * b + 1], j = tij[3 * b + 2];
+        tmin = std::min(tmin, t); tmax = std::max(tmax, t);
+        gmin = std::min(gmin, std::min(i, j)); gmax = std::max(gmax, std::max(i, j));
     }
+    if (tmin < 0 || tmax >= 4 || gmin < 0 || (size_t)gmax >= c->tag2idx_size)
+        for (size_t b = 0; b < n_bonds; ++b) {
+            if (tij[3 * b] < 0 || tij[3 * b] >= 4) return fail(ORBC_ERR_ARG, "bond %zu has type %d outside [0,4)", b, tij[3 * b]);
+            if ((size_t)tij[3 * b + 1] >= c->tag2idx_size || (size_t)tij[3 * b + 2] >= c->tag2idx_size || tij[3 * b + 1] < 0 || tij[3 * b + 2] < 0)
+                return fail(ORBC_ERR_ARG, "bond %zu refers to a tag that no uploaded protein carries (upload proteins first)", b);
+        }
     if (!c->bonds || c->bonds_cap < 3 * n_bonds) { ORBC_TRY(dev_alloc(&c->bonds, 3 * n_bonds)); c->bonds_cap = 3 * n_bonds; }   // a re-upload keeps the allocation
     if (n_bonds) ORBC_CUDA(cudaMemcpyAsync(c->bonds, tij, sizeof(int) * 3 * n_bonds, cudaMemcpyHostToDevice, c->stream));
     ORBC_CUDA(cudaStreamSynchronize(c->stream));

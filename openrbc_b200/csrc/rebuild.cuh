@@ -134,77 +134,148 @@ constexpr int kStencilWarps = 8;
 // Decomposed runs also derive, per cell, the set of OTHER ranks that own a member of its r<9 stencil (dest_mask: who needs
 // this cell's particles as halo) and mark the cells this rank reads (need[c2] = need_epoch for the stencil members of owned cells).
 struct HaloOut { unsigned char *dest_mask; int *need; int need_epoch; CellOwners own; int rank; };
-__global__ void __launch_bounds__(kStencilWarps * 32) k_stencil_build(const float4 *__restrict__ centroid, int c_beg, int c_end, GridDev g,
-                                                                       int *__restrict__ stencil, int *__restrict__ stencil_cnt, int *__restrict__ flags, HaloOut halo) {
-    __shared__ int s_key[kStencilWarps][kStencilStride];
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int c = c_beg + blockIdx.x * kStencilWarps + w;
-    if (c >= c_end) return;
-    const float4 q = centroid[c];
-    int count = 0;
-    if (q.x == q.x && q.y == q.y && q.z == q.z) {
-        int bx, by, bz; grid_bin(g, q, bx, by, bz);
-        const int x0 = max(bx - 1, 0), x1 = min(bx + 1, g.dx - 1);
-        // lanes 0..8 fetch the nine x-runs together, a warp scan turns them into one flat candidate list
-        int beg = 0, cnt = 0;
-        if (lane < 9) {
-            const int zz = bz - 1 + lane / 3, yy = by - 1 + lane % 3;
-            if (zz >= 0 && zz < g.dz && yy >= 0 && yy < g.dy) {
-                const int row = (zz * g.dy + yy) * g.dx;
-                beg = g.bin_start[row + x0];
-                cnt = g.bin_start[row + x1 + 1] - beg;
-            }
-        }
-        int incl = cnt;
-        #pragma unroll
-        for (int d = 1; d < 16; d <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += y; }
-        const int total = __shfl_sync(0xffffffffu, incl, 8);
-        int rb[9], re[9];                                         // run r covers flat slots [re[r] - cnt_r, re[r])
-        #pragma unroll
-        for (int r = 0; r < 9; ++r) { rb[r] = __shfl_sync(0xffffffffu, beg, r); re[r] = __shfl_sync(0xffffffffu, incl, r); }
-        for (int s0 = 0; s0 < total; s0 += 32) {
-            const int s = s0 + lane;
-            int key = -1;
-            if (s < total) {
-                int idx = rb[0] + s;
-                #pragma unroll
-                for (int r = 1; r < 9; ++r) if (s >= re[r - 1]) idx = rb[r] + (s - re[r - 1]);
-                const float4 p = g.sorted[idx];
-                const float d2 = dist2_rn(p, q);                  // normsq(pts_[i] - q), kdtree.h:274
-                if (d2 < 81.0f) key = ((d2 < 36.0f ? 0 : (d2 < 64.0f ? 1 : 2)) << 28) | __float_as_int(p.w);
-            }
-            const unsigned m = __ballot_sync(0xffffffffu, key >= 0);
-            const int pos = count + __popc(m & ((1u << lane) - 1u));
-            if (key >= 0 && pos < kStencilStride) s_key[w][pos] = key;
-            count += __popc(m);
-        }
-    }
-    if (count > kStencilStride) { if (lane == 0) atomicExch(&flags[0], c + 1); count = kStencilStride; }
-    __syncwarp();
-    int n6 = 0, n8 = 0;
+
+// WIDE stencils.  Centroids creep (~0.003 per rebuild), so the r<9 stencil of a cell hardly ever changes — but it must be exact at
+// every rebuild.  The full search (27 grid bins, ~80 candidates per cell) therefore also records every cell closer than 9 + kWideMargin
+// together with the centroids it saw (cen_ref); the rebuilds that follow re-classify only those ~25 recorded neighbours with
+// the exact squared distances (k_stencil_refresh) — the same test on the same operands, so the same sets — as long as no centroid
+// has moved further than kWideMargin / 2 from its recorded position (k_centroid_disp raises the flag otherwise and the full
+// search runs again).  A Morton renumbering of the cells always forces the full search.
+constexpr float kWideMargin = 1.0f;
+struct WideOut { int *wide; int *wide_cnt; float4 *cen_ref; };    // wide == nullptr: not recorded
+
+// classification key of a candidate: class << 28 | id, class 0: d2 < 36, 1: < 64, 2: < 81, 3: only inside the wide radius
+__device__ __forceinline__ int stencil_key(float d2, int id) { return ((d2 < 36.0f ? 0 : (d2 < 64.0f ? 1 : (d2 < 81.0f ? 2 : 3))) << 28) | id; }
+
+// common tail: the keys of one cell (in shared memory, `count` of them, any order) -> ordered (class, id) stencil row, counts,
+// halo bookkeeping, and (full search only) the wide row
+__device__ __forceinline__ void stencil_emit(const int *s_key, int count, int c, int lane, int *__restrict__ stencil, int *__restrict__ stencil_cnt,
+                                             int *__restrict__ flags, const HaloOut &halo, const WideOut &wide) {
+    int n6 = 0, n8 = 0, n9 = 0;
     unsigned owners = 0;
     const bool mine = halo.own.world > 1 && halo.own.owner(c) == halo.rank;
     for (int e = lane; e < count; e += 32) {
-        const int key = s_key[w][e];
+        const int key = s_key[e];
         int rank = 0;
-        for (int k = 0; k < count; ++k) rank += (s_key[w][k] < key);
-        stencil[(size_t)c * kStencilStride + rank] = key & 0x0fffffff;
-        n6 += (key >> 28) == 0; n8 += (key >> 28) <= 1;
-        if (halo.own.world > 1) {
-            owners |= 1u << halo.own.owner(key & 0x0fffffff);
-            if (mine) halo.need[key & 0x0fffffff] = halo.need_epoch;
+        for (int k = 0; k < count; ++k) rank += (s_key[k] < key);
+        const int cls = key >> 28, id = key & 0x0fffffff;
+        if (wide.wide) wide.wide[(size_t)c * kStencilStride + rank] = id;          // (class 3 sorts last: the first n9 entries are the stencil)
+        if (cls <= 2) {
+            stencil[(size_t)c * kStencilStride + rank] = id;
+            n6 += cls == 0; n8 += cls <= 1; ++n9;
+            if (halo.own.world > 1) {
+                owners |= 1u << halo.own.owner(id);
+                if (mine) halo.need[id] = halo.need_epoch;
+            }
         }
     }
     #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) { n6 += __shfl_xor_sync(0xffffffffu, n6, d); n8 += __shfl_xor_sync(0xffffffffu, n8, d); }
+    for (int d = 16; d > 0; d >>= 1) { n6 += __shfl_xor_sync(0xffffffffu, n6, d); n8 += __shfl_xor_sync(0xffffffffu, n8, d); n9 += __shfl_xor_sync(0xffffffffu, n9, d); }
     if (lane == 0) {
-        stencil_cnt[c] = n6 | (n8 << 8) | (count << 16);
-        if (n6 > 32) atomicExch(&flags[0], c + 1);               // k_pair_ll keeps the surviving r<6 cells in a 32-bit mask
+        stencil_cnt[c] = n6 | (n8 << 8) | (n9 << 16);
+        if (wide.wide) wide.wide_cnt[c] = count;
+        if (n6 > 32) atomicExch(&flags[0], c + 1);               // the lipid kernels keep the r<6 cells of a cell in 32 slots
     }
     if (halo.own.world > 1) {
         owners = __reduce_or_sync(0xffffffffu, owners);
         if (lane == 0) { halo.dest_mask[c] = (unsigned char)(owners & ~(1u << halo.own.owner(c))); if (mine) halo.need[c] = halo.need_epoch; }
     }
+}
+
+// the full search.  `gate`: run only if *gate == 0 (the refresh could not be trusted); grid-stride, so that a gated launch is cheap.
+__global__ void __launch_bounds__(kStencilWarps * 32) k_stencil_build(const float4 *__restrict__ centroid, int c_beg, int c_end, GridDev g,
+                                                                       int *__restrict__ stencil, int *__restrict__ stencil_cnt, int *__restrict__ flags, HaloOut halo,
+                                                                       WideOut wide, const int *__restrict__ gate) {
+    if (gate && *gate != 0) return;
+    __shared__ int s_key[kStencilWarps][kStencilStride];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float lim = wide.wide ? (9.0f + kWideMargin) * (9.0f + kWideMargin) : 81.0f;
+    for (int c = c_beg + blockIdx.x * kStencilWarps + w; c < c_end; c += gridDim.x * kStencilWarps) {
+        const float4 q = centroid[c];
+        int count = 0;
+        if (q.x == q.x && q.y == q.y && q.z == q.z) {
+            int bx, by, bz; grid_bin(g, q, bx, by, bz);
+            const int x0 = max(bx - 1, 0), x1 = min(bx + 1, g.dx - 1);
+            // lanes 0..8 fetch the nine x-runs together, a warp scan turns them into one flat candidate list
+            int beg = 0, cnt = 0;
+            if (lane < 9) {
+                const int zz = bz - 1 + lane / 3, yy = by - 1 + lane % 3;
+                if (zz >= 0 && zz < g.dz && yy >= 0 && yy < g.dy) {
+                    const int row = (zz * g.dy + yy) * g.dx;
+                    beg = g.bin_start[row + x0];
+                    cnt = g.bin_start[row + x1 + 1] - beg;
+                }
+            }
+            int incl = cnt;
+            #pragma unroll
+            for (int d = 1; d < 16; d <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += y; }
+            const int total = __shfl_sync(0xffffffffu, incl, 8);
+            int rb[9], re[9];                                     // run r covers flat slots [re[r] - cnt_r, re[r])
+            #pragma unroll
+            for (int r = 0; r < 9; ++r) { rb[r] = __shfl_sync(0xffffffffu, beg, r); re[r] = __shfl_sync(0xffffffffu, incl, r); }
+            for (int s0 = 0; s0 < total; s0 += 32) {
+                const int s = s0 + lane;
+                int key = -1;
+                if (s < total) {
+                    int idx = rb[0] + s;
+                    #pragma unroll
+                    for (int r = 1; r < 9; ++r) if (s >= re[r - 1]) idx = rb[r] + (s - re[r - 1]);
+                    const float4 p = g.sorted[idx];
+                    const float d2 = dist2_rn(p, q);              // normsq(pts_[i] - q), kdtree.h:274
+                    if (d2 < lim) key = stencil_key(d2, __float_as_int(p.w));
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, key >= 0);
+                const int pos = count + __popc(m & ((1u << lane) - 1u));
+                if (key >= 0 && pos < kStencilStride) s_key[w][pos] = key;
+                count += __popc(m);
+            }
+        }
+        if (count > kStencilStride) { if (lane == 0) atomicExch(&flags[0], c + 1); count = kStencilStride; }
+        __syncwarp();
+        if (wide.wide && lane == 0) wide.cen_ref[c] = q;
+        stencil_emit(s_key[w], count, c, lane, stencil, stencil_cnt, flags, halo, wide);
+        __syncwarp();
+    }
+}
+
+// largest displacement of a centroid since the wide stencils were recorded: *ok = 0 when 2 x displacement can exceed the margin
+__global__ void k_centroid_disp(const float4 *__restrict__ centroid, const float4 *__restrict__ cen_ref, int n, int *__restrict__ ok) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 a = centroid[i], b = cen_ref[i];
+    const float dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z;
+    const float lim = 0.5f * kWideMargin - 1e-3f;
+    const bool fine = (dx * dx + dy * dy + dz * dz <= lim * lim) || (!(a.x == a.x) && !(b.x == b.x));   // (an empty cell stays a NaN on both sides)
+    if (!fine) atomicExch(ok, 0);
+}
+
+// the refresh: the recorded neighbours of every cell re-classified with the exact squared distances.  `gate`: run only if *gate != 0.
+__global__ void __launch_bounds__(kStencilWarps * 32) k_stencil_refresh(const float4 *__restrict__ centroid, int c_beg, int c_end, const int *__restrict__ wide_rows,
+                                                                         const int *__restrict__ wide_cnt, int *__restrict__ stencil, int *__restrict__ stencil_cnt,
+                                                                         int *__restrict__ flags, HaloOut halo, const int *__restrict__ gate) {
+    if (gate && *gate == 0) return;
+    __shared__ int s_key[kStencilWarps][kStencilStride];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c = c_beg + blockIdx.x * kStencilWarps + w;
+    if (c >= c_end) return;
+    const float4 q = centroid[c];
+    const int n = wide_cnt[c];
+    int count = 0;
+    for (int e0 = 0; e0 < n; e0 += 32) {
+        const int e = e0 + lane;
+        int key = -1;
+        if (e < n) {
+            const int id = wide_rows[(size_t)c * kStencilStride + e];
+            const float d2 = dist2_rn(centroid[id], q);
+            if (d2 < 81.0f) key = stencil_key(d2, id);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, key >= 0);
+        const int pos = count + __popc(m & ((1u << lane) - 1u));
+        if (key >= 0) s_key[w][pos] = key;
+        count += __popc(m);
+    }
+    __syncwarp();
+    stencil_emit(s_key[w], count, c, lane, stencil, stencil_cnt, flags, halo, WideOut{nullptr, nullptr, nullptr});
 }
 
 // ---- nearest centroid (voronoi.h:179-216 + kdtree.h:206-236) ------------------------------------------------------------------

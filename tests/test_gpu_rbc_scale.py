@@ -109,6 +109,30 @@ def test_full_rbc_rebuild_and_forces_match_the_reference():
             e = rel_err(d[f], r.get(s, f))
             log[f"rel_err_{p}{f}"] = e
             assert e < 1e-4, (p, f, e)
+    # ---- a second rebuild two steps later, without renumbering: the device re-classifies the recorded wide stencils (k_stencil_refresh)
+    #      instead of searching the grid; sets and partition must still be the reference's
+    for s, p in ((0, "l"), (1, "p")):                              # the same (reference) forces on both sides, then one noise-free step
+        sim.set_field(s, "f", r.get(s, "f")); sim.set_field(s, "t", r.get(s, "t"))
+    r.integrate(refmod.VERLET_LANGEVIN); sim.verlet_langevin()
+    for s, p in ((0, "l"), (1, "p")):                              # teacher-force the reference's positions (the integrators agree to 1e-6 only)
+        for f in "xvno":
+            sim.set_field(s, f, r.get(s, f))
+    r.set_param("nstep", 26); sim.nstep = 26
+    r.voronoi_update(); r.cell_update(0); r.cell_update(1)
+    sim.rebuild(); sim.synchronize()
+    np.testing.assert_array_equal(sim.dump("centroids"), r.centroids())
+    for s, p in ((0, "l"), (1, "p")):
+        np.testing.assert_array_equal(sim.dump("cell_start_" + p), r.cell_array(s, "cell_start"), err_msg="second rebuild cell_start " + p)
+        np.testing.assert_array_equal(sim.dump("aff_" + p), r.cell_array(s, "affiliation"), err_msg="second rebuild affiliation " + p)
+    tab, cnt = ref_stencil_table(r, nc)
+    np.testing.assert_array_equal(sim.dump("stencil_counts")[:, ::-1], cnt)
+    dst = sim.dump("stencil")
+    changed = 0
+    for k, name in ((0, 9), (1, 8), (2, 6)):
+        mine = np.where(col < cnt[:, k][:, None], dst, big)
+        mine.sort(axis=1)
+        np.testing.assert_array_equal(mine, tab[:, k, :], err_msg=f"second rebuild stencil r<{name}")
+    log["second_rebuild"] = "refresh path (k_stencil_refresh): stencil sets, affiliation and cell_start equal to the reference"
     log["t_total_s"] = round(time.time() - t0, 1)
     out = os.path.join(ROOT, "gpurun_out")
     os.makedirs(out, exist_ok=True)
