@@ -335,6 +335,8 @@ def run_ours(args):
     def make_sim(state):
         s = orbc.Simulation(state, kBT=0.22, device=local, rank=rank, world=world)
         s.stray_tolerance = 2.5
+        if args.cv:
+            s.set_volume_constraint(True, 3.15, 0.05)              # inside orbc_run_langevin; the per-call e2e loop calls constrain_volume itself
         if world > 1:
             connect(s)
         return s
@@ -427,7 +429,10 @@ def run_ours(args):
         if e2e_sim.nstep % FREQ_CLEANUP == 0:
             e2e_sim.delete_lipid(e2e_sim.stray_tolerance); d2h += 8
             slow.append(((time.perf_counter() - t0) * 1e3, "delete_lipid@%d" % e2e_sim.nstep)); t0 = time.perf_counter()
-        e2e_sim.step_langevin_checked(); d2h += 16
+        if args.cv:
+            e2e_sim.step_langevin_cv_checked(3.15, 0.05); d2h += 20
+        else:
+            e2e_sim.step_langevin_checked(); d2h += 16
         slow.append(((time.perf_counter() - t0) * 1e3, "step@%d" % (e2e_sim.nstep - 1)))
         if trace and slow[-1][0] > 20.0:
             print(f"[bench rank {rank}] slow call {slow[-1]}", file=sys.stderr, flush=True)
@@ -478,12 +483,12 @@ def run_ours(args):
     shares = {k: round(v[0] / ms, 4) for k, v in prof.items()}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f32", "data": data_label(args.workload),
         "config": {"workload": workload_name(args.workload, st), "l2": "inputs larger than L2 (state %.0f MB resident in HBM, no flush needed)" % (n_total * 6 * 16 / 1e6),
                    "multi_gpu": "single GPU" if world == 1 else (f"one cell decomposed over {world} ranks: contiguous ranges of Morton-ordered Voronoi cells, halo push + migration "
                                                                 "by peer stores over NVLink, epoch-flag barriers"),
-                   "integrator": "verlet_langevin kBT=0.22 dt=0.01, rebuild every 2 steps, Morton sort every 24, cleanup every 60",
+                   "integrator": "verlet_langevin kBT=0.22 dt=0.01, rebuild every 2 steps, Morton sort every 24, cleanup every 60" + (", constrain_volume(3.15, 0.05) every step" if args.cv else ""),
                    "particles_at_end": n_now, "temperature_at_end": temperature,
                    "hbm_roofline_frac_step": value / world * B_ALG_STEP / 1e9 / peak, "device_time_shares": shares},
         "roofline": {"bound": "hbm", "kernel": "k_pair_lipid (lipid side of compute_pairwise_fused)", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -516,6 +521,8 @@ def main():
     ap.add_argument("--ref-budget", type=float, default=150.0, help="reference arm: wall-clock bound in seconds")
     ap.add_argument("--cpu-steps", type=int, default=40, help="steps of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cv", action="store_true", help="BASELINE.json configs[2]: constrain_volume(3.15, 0.05) at the place of openrbc.cpp:229 in every step")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"], help="label of the run (weak: the workload was sized with the number of GPUs, e.g. patch:<N x 1.05e6>)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -156,10 +156,10 @@ __device__ __forceinline__ void stencil_emit(const int *s_key, int count, int c,
     const bool mine = halo.own.world > 1 && halo.own.owner(c) == halo.rank;
     for (int e = lane; e < count; e += 32) {
         const int key = s_key[e];
-        int rank = 0;
-        for (int k = 0; k < count; ++k) rank += (s_key[k] < key);
         const int cls = key >> 28, id = key & 0x0fffffff;
-        if (wide.wide) wide.wide[(size_t)c * kStencilStride + rank] = id;          // (class 3 sorts last: the first n9 entries are the stencil)
+        int rank = 0, rank_id = 0;
+        for (int k = 0; k < count; ++k) { const int o = s_key[k]; rank += (o < key); rank_id += ((o & 0x0fffffff) < id); }
+        if (wide.wide) wide.wide[(size_t)c * kStencilStride + rank_id] = id;       // the wide row in ascending id (k_stencil_refresh ranks by lane order)
         if (cls <= 2) {
             stencil[(size_t)c * kStencilStride + rank] = id;
             n6 += cls == 0; n8 += cls <= 1; ++n9;
@@ -250,32 +250,59 @@ __global__ void k_centroid_disp(const float4 *__restrict__ centroid, const float
 }
 
 // the refresh: the recorded neighbours of every cell re-classified with the exact squared distances.  `gate`: run only if *gate != 0.
+// The wide row is stored in ascending id, so inside one class lane order IS id order: the slot of an entry in the (class, id) ordered
+// stencil row is (entries of lower classes) + (entries of its class in lower lanes) — a few ballots instead of a sort.
 __global__ void __launch_bounds__(kStencilWarps * 32) k_stencil_refresh(const float4 *__restrict__ centroid, int c_beg, int c_end, const int *__restrict__ wide_rows,
                                                                          const int *__restrict__ wide_cnt, int *__restrict__ stencil, int *__restrict__ stencil_cnt,
                                                                          int *__restrict__ flags, HaloOut halo, const int *__restrict__ gate) {
     if (gate && *gate == 0) return;
-    __shared__ int s_key[kStencilWarps][kStencilStride];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int c = c_beg + blockIdx.x * kStencilWarps + w;
     if (c >= c_end) return;
     const float4 q = centroid[c];
-    const int n = wide_cnt[c];
-    int count = 0;
-    for (int e0 = 0; e0 < n; e0 += 32) {
-        const int e = e0 + lane;
-        int key = -1;
+    const int n = min(wide_cnt[c], kStencilStride);
+    // two entries per lane (rows hold at most 64): e = lane and e = lane + 32
+    int id[2], cls[2];
+    #pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int e = lane + 32 * h;
+        id[h] = 0; cls[h] = 3;
         if (e < n) {
-            const int id = wide_rows[(size_t)c * kStencilStride + e];
-            const float d2 = dist2_rn(centroid[id], q);
-            if (d2 < 81.0f) key = stencil_key(d2, id);
+            id[h] = wide_rows[(size_t)c * kStencilStride + e];
+            const float d2 = dist2_rn(centroid[id[h]], q);
+            cls[h] = d2 < 36.0f ? 0 : (d2 < 64.0f ? 1 : (d2 < 81.0f ? 2 : 3));    // (a NaN distance: class 3, not a member)
         }
-        const unsigned m = __ballot_sync(0xffffffffu, key >= 0);
-        const int pos = count + __popc(m & ((1u << lane) - 1u));
-        if (key >= 0) s_key[w][pos] = key;
-        count += __popc(m);
     }
-    __syncwarp();
-    stencil_emit(s_key[w], count, c, lane, stencil, stencil_cnt, flags, halo, WideOut{nullptr, nullptr, nullptr});
+    unsigned m[2][3];
+    #pragma unroll
+    for (int h = 0; h < 2; ++h)
+        #pragma unroll
+        for (int k = 0; k < 3; ++k) m[h][k] = __ballot_sync(0xffffffffu, cls[h] == k);
+    const int n0 = __popc(m[0][0]) + __popc(m[1][0]), n1 = __popc(m[0][1]) + __popc(m[1][1]), n2 = __popc(m[0][2]) + __popc(m[1][2]);
+    const unsigned lt = (1u << lane) - 1u;
+    unsigned owners = 0;
+    const bool mine = halo.own.world > 1 && halo.own.owner(c) == halo.rank;
+    #pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        if (cls[h] > 2) continue;
+        const int k = cls[h];
+        const int below = k == 0 ? 0 : (k == 1 ? n0 : n0 + n1);
+        const unsigned same0 = k == 0 ? m[0][0] : (k == 1 ? m[0][1] : m[0][2]), same1 = k == 0 ? m[1][0] : (k == 1 ? m[1][1] : m[1][2]);
+        const int slot = below + (h == 0 ? __popc(same0 & lt) : __popc(same0) + __popc(same1 & lt));
+        stencil[(size_t)c * kStencilStride + slot] = id[h];
+        if (halo.own.world > 1) {
+            owners |= 1u << halo.own.owner(id[h]);
+            if (mine) halo.need[id[h]] = halo.need_epoch;
+        }
+    }
+    if (lane == 0) {
+        stencil_cnt[c] = n0 | ((n0 + n1) << 8) | ((n0 + n1 + n2) << 16);
+        if (n0 > 32) atomicExch(&flags[0], c + 1);
+    }
+    if (halo.own.world > 1) {
+        owners = __reduce_or_sync(0xffffffffu, owners);
+        if (lane == 0) { halo.dest_mask[c] = (unsigned char)(owners & ~(1u << halo.own.owner(c))); if (mine) halo.need[c] = halo.need_epoch; }
+    }
 }
 
 // ---- nearest centroid (voronoi.h:179-216 + kdtree.h:206-236) ------------------------------------------------------------------
@@ -317,11 +344,13 @@ __global__ void k_assign_nearest(const float4 *__restrict__ x, const int *__rest
                                  int *__restrict__ aff, int *__restrict__ li, int *__restrict__ cell_cnt,
                                  unsigned long long *__restrict__ counters, int *__restrict__ flags, const int *__restrict__ keep) {
     const int i = range[0] + blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= range[1]) return;
-    if (keep && !keep[i]) { aff[i] = -1; return; }               // stray lipid being deleted (cleanup.h:29-91): it joins no cell
+    const bool live = i < range[1];
+    const bool gone = live && keep && !keep[i];                  // stray lipid being deleted (cleanup.h:29-91): it joins no cell
+    int bi = -1;
+    if (live && !gone) {
     const float4 p = x[i];
     const int guess = cellid ? cellid[i] : -1;
-    float best = INFINITY; int bi = -1; bool ok = false;
+    float best = INFINITY; bool ok = false;
     if (guess >= 0 && guess < n_cells) {
         // candidates = the r<6 stencil of the previous cell; exact whenever d(best) + d(guess) < 6 (every centroid at least
         // as close to the particle as `best` is then closer than 6 to the guess, i.e. inside that stencil).  Otherwise the
@@ -350,8 +379,19 @@ __global__ void k_assign_nearest(const float4 *__restrict__ x, const int *__rest
         atomicAdd(&counters[0], 1ULL);
     }
     if (bi < 0) { atomicExch(&flags[1], (int)(i & 0x7fffffff) + 1); bi = 0; }   // NaN position: keep the structure consistent, report
-    aff[i] = bi;
-    li[i] = atomicAdd(&cell_cnt[bi], 1);
+    }
+    if (gone) aff[i] = -1;
+    // arrival slots: the lanes of a warp that chose the same cell (neighbours in storage order mostly do) take ONE atomic between
+    // them — the arrival order is arbitrary anyway, k_rank_and_move sorts every cell's list by old index
+    const unsigned peers = __match_any_sync(0xffffffffu, bi);
+    if (bi >= 0) {
+        const int leader = __ffs(peers) - 1, lane = threadIdx.x & 31;
+        int base = 0;
+        if (lane == leader) base = atomicAdd(&cell_cnt[bi], __popc(peers));
+        base = __shfl_sync(peers, base, leader);
+        aff[i] = bi;
+        li[i] = base + __popc(peers & ((1u << lane) - 1u));
+    }
 }
 
 // cells_tmp[cell_start[aff] + arrival slot] = i   (voronoi.h:228-231 with an arbitrary arrival order ...)

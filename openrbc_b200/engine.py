@@ -474,6 +474,17 @@ class Simulation:
         self.verlet_langevin(nl, npr)
         self.nstep += 1
 
+    def step_langevin_cv_checked(self, target, strength):
+        """The same iteration with constrain_volume at the place of openrbc.cpp:229 (BASELINE.json configs[2])."""
+        if self.nstep % self.freq_voronoi == 0:
+            self.rebuild()
+        self.compute_pairwise_fused()
+        self.compute_bonded()
+        self.constrain_volume(target, strength)
+        self.verlet_langevin()
+        self.nstep += 1
+        self.synchronize()
+
     def step_langevin_checked(self):
         """One loop iteration call by call, then wait for it and read the device status back (16 B D2H)."""
         self.step_langevin()
