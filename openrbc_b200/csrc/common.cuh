@@ -166,7 +166,8 @@ struct orbc_ctx {
     // hit lists with a skin (pair_queue.cuh): recorded by the force evaluation after a rebuild, walked until the next one
     bool nl_on = true, nl_valid = false;           // option "nl_reuse"; lists match the current partition and were built (host's view)
     float nl_skin = 0.1f;                          // option "nl_skin"
-    int ll_list_blocks = 16;                       // resident blocks per SM the list walker is compiled for (register budget)
+    bool ll_xn = false;                            // list walker gathers interleaved (x, n) records (k_pack_xn); measured: no gain (243 vs 238 us), off
+    float *xn = nullptr; size_t xn_cap = 0;        // those records, 32 B per lipid
     int nl_moves = 0;                              // tracked integration steps since the last gate
     void *nl_state = nullptr;                      // orbc::NlState on the device
     int *ll_list = nullptr, *ll_cnt = nullptr; size_t ll_list_lipids = 0;
