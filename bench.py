@@ -335,6 +335,9 @@ def run_ours(args):
     def make_sim(state):
         s = orbc.Simulation(state, kBT=0.22, device=local, rank=rank, world=world)
         s.stray_tolerance = 2.5
+        for kv in args.opt:
+            k, v = kv.split("=")
+            s.set_option(k, float(v))
         if args.cv:
             s.set_volume_constraint(True, 3.15, 0.05)              # inside orbc_run_langevin; the per-call e2e loop calls constrain_volume itself
         if world > 1:
@@ -364,6 +367,7 @@ def run_ours(args):
     prof = {k: sim.profile_read(k) for k in orbc.engine.PROF}
     sim.profile_enable(False)
     n_now = sim.size(0) + sim.size(1)
+    nl_stats = sim.dump("nl_stats").tolist()
     if world > 1:
         t = torch.tensor([ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -489,7 +493,8 @@ def run_ours(args):
                    "multi_gpu": "single GPU" if world == 1 else (f"one cell decomposed over {world} ranks: contiguous ranges of Morton-ordered Voronoi cells, halo push + migration "
                                                                 "by peer stores over NVLink, epoch-flag barriers"),
                    "integrator": "verlet_langevin kBT=0.22 dt=0.01, rebuild every 2 steps, Morton sort every 24, cleanup every 60" + (", constrain_volume(3.15, 0.05) every step" if args.cv else ""),
-                   "particles_at_end": n_now, "temperature_at_end": temperature,
+                   "particles_at_end": n_now, "temperature_at_end": temperature, "options": args.opt,
+                   "hit_lists": {"evaluations_that_recorded": nl_stats[0], "evaluations_that_walked": nl_stats[1], "evaluations_that_searched": nl_stats[3], "overflow": nl_stats[2]},
                    "hbm_roofline_frac_step": value / world * B_ALG_STEP / 1e9 / peak, "device_time_shares": shares},
         "roofline": {"bound": "hbm", "kernel": "k_pair_lipid (lipid side of compute_pairwise_fused)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": (achieved / peak) if achieved else None, "traffic": (ncu_traffic("k_pair_ll")[0] if world == 1 else None),
@@ -521,6 +526,7 @@ def main():
     ap.add_argument("--ref-budget", type=float, default=150.0, help="reference arm: wall-clock bound in seconds")
     ap.add_argument("--cpu-steps", type=int, default=40, help="steps of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], help="library option name=value (orbc_set_option), e.g. --opt nl_skin=0.2")
     ap.add_argument("--cv", action="store_true", help="BASELINE.json configs[2]: constrain_volume(3.15, 0.05) at the place of openrbc.cpp:229 in every step")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"], help="label of the run (weak: the workload was sized with the number of GPUs, e.g. patch:<N x 1.05e6>)")
     args = ap.parse_args()

@@ -228,7 +228,7 @@ typedef enum {
     ORBC_DUMP_STENCIL = 10,      /* n_cells x ORBC_STENCIL_STRIDE int, ordered (class, id) */
     ORBC_DUMP_TAG2IDX = 11,      /* protein tag -> index, (max_tag + 1) int */
     ORBC_DUMP_COUNTERS = 12,     /* 8 x uint64 device counters (fallback searches, ...) */
-    ORBC_DUMP_NL_STATS = 13      /* 4 x uint32: force evaluations that built the hit lists, that walked them, overflow flag, last decision */
+    ORBC_DUMP_NL_STATS = 13      /* 4 x uint32: force evaluations that recorded the hit lists, that walked them, overflow flag, that searched without recording */
 } orbc_dump;
 #define ORBC_STENCIL_STRIDE 64
 ORBC_API int  orbc_debug_dump(orbc_ctx *ctx, int what, void *dst, size_t bytes);

@@ -186,6 +186,7 @@ struct orbc_ctx {
     cudaEvent_t frame_packed[2] = {}, frame_copied[2] = {};
     int frame_head = 0, frame_pending = 0;                // ring of two frames in flight
     orbc::Decomp mg;
+    int nl_debug_mode = -1;                               // measurement aid (option debug_nl_mode): 1 / 2 = every evaluation records / searches
     int mg_own_slack = 8192;                              // slack of the owned-particle launch bounds (test option debug_own_slack)
     // per-class event-pair profiling (orbc_profile_*)
     bool prof_on = false;

@@ -346,7 +346,8 @@ int launch_pairwise(orbc_ctx *c, bool accumulate = true) {
         nls = (NlState *)c->nl_state;
         host_build = !c->nl_valid;
         if (mg && c->nl_moves > 1) host_build = true;             // (the ranks exchange the bound of ONE step)
-        ORBC_LAUNCH(c, k_nl_gate, 1, 32, 0, nls, host_build ? 1 : 0, c->nl_moves, c->nl_skin,
+        if (c->nl_debug_mode > 0) host_build = true;
+        ORBC_LAUNCH(c, k_nl_gate, 1, 32, 0, nls, host_build ? 1 : 0, c->nl_debug_mode, c->nl_moves, c->nl_skin,
                     mg ? (const unsigned *)(c->mg.flags + kMaxWorld * (1 + c->mg.disp_par)) : (const unsigned *)nullptr, mg ? c->mg.world : 1);
         c->nl_moves = 0; c->nl_valid = true;
     }
@@ -354,7 +355,7 @@ int launch_pairwise(orbc_ctx *c, bool accumulate = true) {
         ProfScope ps(c, ORBC_PROF_PAIR_LIPID);
         // bounding spheres of the cells' current members: the protein kernel culls with them (on a list-walking step only the gated rebuild of the lists would)
         ORBC_LAUNCH(c, k_cell_bounds, blocks_for(c->n_cells, 128), 128, 0, c->centroid, c->n_cells, L.cell_start, L.X(), P.n ? P.cell_start : nullptr, P.X(), c->lbound, c->pbound,
-                    mg ? c->mg.need : (const int *)nullptr, c->mg.need_epoch, (nl && !host_build) ? &nls->need : (const int *)nullptr);
+                    mg ? c->mg.need : (const int *)nullptr, c->mg.need_epoch, nl ? &nls->need : (const int *)nullptr);
         if (L.n && a.ce > a.cb) {
             // candidate runs merged over Morton-adjacent stencil cells, rebuilt after every rebuild of the partition
             if (!c->lruns_valid) {
@@ -368,22 +369,23 @@ int launch_pairwise(orbc_ctx *c, bool accumulate = true) {
                 // warp-per-cell tile kernel; the thread-per-lipid kernel takes the step when a cell does not fit the tile (device flag)
                 const unsigned warps = blocks_for((size_t)(a.ce - a.cb), kTileCells);
                 ORBC_LAUNCH(c, k_pair_ll_t, blocks_for(warps, kTileWarps), kTileWarps * 32, kTileWarps * kTileBytes, a, kc, c->lruns, c->lrun_cnt, c->tile_overflow);
-                ORBC_LAUNCH(c, (k_pair_ll_r<20, 4, false>), kSmallGrid, kLLBlock, 0, a, kc, c->lruns, c->lrun_cnt, c->tile_overflow, 1, LLList{}, 0.f);
+                ORBC_LAUNCH(c, (k_pair_ll_r<20, 4, false>), kSmallGrid, kLLBlock, 0, a, kc, c->lruns, c->lrun_cnt, c->tile_overflow, 1, LLList{}, 0.f, (unsigned *)nullptr);
             } else if (!nl) {
-                ORBC_LAUNCH(c, (k_pair_ll_r<20, 4, false>), blocks_for(nl_count, kLLBlock), kLLBlock, 0, a, kc, c->lruns, c->lrun_cnt, (const int *)nullptr, 0, LLList{}, 0.f);
+                ORBC_LAUNCH(c, (k_pair_ll_r<20, 4, false>), blocks_for(nl_count, kLLBlock), kLLBlock, 0, a, kc, c->lruns, c->lrun_cnt, (const int *)nullptr, 0, LLList{}, 0.f, (unsigned *)nullptr);
             } else {
+                // hit lists: the device decides (k_nl_gate) whether this evaluation walks the lists, searches and records them, or just
+                // searches; the three kernels are launched over a grid that fills the GPU once (their blocks draw 64-lipid groups from a
+                // ticket counter), two of them return at once
                 const LLList ll = {c->ll_list, c->ll_cnt, c->nl_cap_ll, nls};
-                if (host_build)                                  // right after a rebuild: record the lists while evaluating
-                    ORBC_LAUNCH(c, (k_pair_ll_r<16, 4, true>), blocks_for(nl_count, kLLBlock), kLLBlock, 0, a, kc, c->lruns, c->lrun_cnt, (const int *)nullptr, 0, ll, c->nl_skin);
-                else {                                           // walk the lists; the gate orders a fresh build only if a particle outran the skin
-                    if (!mg && c->ll_xn) {
-                        // single GPU: the partners as interleaved (x, n) records, one 256-bit gather per pair
-                        if (c->xn_cap < L.cap) { ORBC_TRY(dev_alloc(&c->xn, L.cap * 8)); c->xn_cap = L.cap; }
-                        ORBC_LAUNCH(c, k_pack_xn, blocks_for(L.n, kBlock), kBlock, 0, L.X(), L.N(), L.n, (XN *)c->xn);
-                        ORBC_LAUNCH(c, (k_pair_ll_list<16, true>), blocks_for(nl_count, kLLBlock), kLLBlock, 0, a, kc, &nls->need, 0, ll, (const XN *)c->xn);
-                    } else ORBC_LAUNCH(c, (k_pair_ll_list<16, false>), blocks_for(nl_count, kLLBlock), kLLBlock, 0, a, kc, &nls->need, 0, ll, (const XN *)nullptr);
-                    ORBC_LAUNCH(c, (k_pair_ll_r<16, 4, true>), kSmallGrid, kLLBlock, 0, a, kc, c->lruns, c->lrun_cnt, &nls->need, 1, ll, c->nl_skin);
-                }
+                const unsigned groups = blocks_for(nl_count, kLLBlock);
+                const unsigned g16 = std::min(groups, 148u * 16u), g20 = std::min(groups, 148u * 20u);   // (blocks per SM: the kernels' launch bounds)
+                if (!mg && c->ll_xn) {
+                    if (c->xn_cap < L.cap) { ORBC_TRY(dev_alloc(&c->xn, L.cap * 8)); c->xn_cap = L.cap; }
+                    ORBC_LAUNCH(c, k_pack_xn, blocks_for(L.n, kBlock), kBlock, 0, L.X(), L.N(), L.n, (XN *)c->xn);
+                    ORBC_LAUNCH(c, (k_pair_ll_list<16, true>), g16, kLLBlock, 0, a, kc, &nls->need, 0, ll, (const XN *)c->xn, nls->work + 0);
+                } else ORBC_LAUNCH(c, (k_pair_ll_list<16, false>), g16, kLLBlock, 0, a, kc, &nls->need, 0, ll, (const XN *)nullptr, nls->work + 0);
+                ORBC_LAUNCH(c, (k_pair_ll_r<16, 4, true>), g16, kLLBlock, 0, a, kc, c->lruns, c->lrun_cnt, &nls->need, 1, ll, c->nl_skin, nls->work + 1);
+                ORBC_LAUNCH(c, (k_pair_ll_r<20, 4, false>), g20, kLLBlock, 0, a, kc, c->lruns, c->lrun_cnt, &nls->need, 2, LLList{}, 0.f, nls->work + 2);
             }
         }
         // (decomposed: the lipid side of the protein-lipid pairs whose protein lives on another rank is the epilogue of the lipid kernels)
@@ -395,19 +397,16 @@ int launch_pairwise(orbc_ctx *c, bool accumulate = true) {
         // few owned proteins (a rank of a decomposed run): more lanes per protein, shorter dependent-load chains, more warps
         const PLists pls = {c->pl_list, c->pl_cnt, c->pp_list, c->pp_cnt, c->nl_cap_pl, c->nl_cap_pp, nls};
         const int lanes = prot_lanes(c, np);
-        const int *gate_b = (nl && !host_build) ? &nls->need : (const int *)nullptr;     // the build kernel is gated only on a list-walking step
-        const float skin = nl ? c->nl_skin : 0.f;
-        if (nl && !host_build) {
-            if (lanes == 4) ORBC_LAUNCH(c, k_pair_prot_list<4>, blocks_for(np * 4, kPBlock), kPBlock, 0, a, c->porder, &nls->need, 0, pls);
-            else if (lanes == 2) ORBC_LAUNCH(c, k_pair_prot_list<2>, blocks_for(np * 2, kPBlock), kPBlock, 0, a, c->porder, &nls->need, 0, pls);
-            else ORBC_LAUNCH(c, k_pair_prot_list<1>, blocks_for(np, kPBlock), kPBlock, 0, a, c->porder, &nls->need, 0, pls);
-        }
-        const unsigned grid = (nl && !host_build) ? kSmallGrid : blocks_for(np * lanes, kPBlock);
         if (nl) {
-            if (lanes == 4) ORBC_LAUNCH(c, (k_pair_prot<4, true>), grid, kPBlock, 0, a, c->lbound, c->pbound, ct, c->porder, gate_b, 1, pls, skin);
-            else if (lanes == 2) ORBC_LAUNCH(c, (k_pair_prot<2, true>), grid, kPBlock, 0, a, c->lbound, c->pbound, ct, c->porder, gate_b, 1, pls, skin);
-            else ORBC_LAUNCH(c, (k_pair_prot<1, true>), grid, kPBlock, 0, a, c->lbound, c->pbound, ct, c->porder, gate_b, 1, pls, skin);
+            const unsigned pieces = blocks_for(np * lanes, kPBlock);
+#define ORBC_PROT3(LPP) do { \
+                ORBC_LAUNCH(c, k_pair_prot_list<LPP>, pieces, kPBlock, 0, a, c->porder, &nls->need, 0, pls); \
+                ORBC_LAUNCH(c, (k_pair_prot<LPP, true>), pieces, kPBlock, 0, a, c->lbound, c->pbound, ct, c->porder, &nls->need, 1, pls, c->nl_skin); \
+                ORBC_LAUNCH(c, (k_pair_prot<LPP, false>), pieces, kPBlock, 0, a, c->lbound, c->pbound, ct, c->porder, &nls->need, 2, pls, 0.f); } while (0)
+            if (lanes == 4) ORBC_PROT3(4); else if (lanes == 2) ORBC_PROT3(2); else ORBC_PROT3(1);
+#undef ORBC_PROT3
         } else {
+            const unsigned grid = blocks_for(np * lanes, kPBlock);
             if (lanes == 4) ORBC_LAUNCH(c, (k_pair_prot<4, false>), grid, kPBlock, 0, a, c->lbound, c->pbound, ct, c->porder, (const int *)nullptr, 0, pls, 0.f);
             else if (lanes == 2) ORBC_LAUNCH(c, (k_pair_prot<2, false>), grid, kPBlock, 0, a, c->lbound, c->pbound, ct, c->porder, (const int *)nullptr, 0, pls, 0.f);
             else ORBC_LAUNCH(c, (k_pair_prot<1, false>), grid, kPBlock, 0, a, c->lbound, c->pbound, ct, c->porder, (const int *)nullptr, 0, pls, 0.f);
@@ -761,6 +760,10 @@ int orbc_set_option(orbc_ctx *c, const char *name, double value) { if (c) cudaSe
     if (!strcmp(name, "debug_tile_cap")) {                       // test aid: a smaller tile capacity, so that small systems reach the overflow path
         if (!(value >= 1 && value <= kTileCap)) return fail(ORBC_ERR_ARG, "debug_tile_cap must be in [1, %d]", kTileCap);
         c->tile_cap = (int)value; c->lruns_valid = false; return ORBC_OK;
+    }
+    if (!strcmp(name, "debug_nl_mode")) {                        // measurement aid: -1 the gate decides, 1 every evaluation records the hit lists, 2 every evaluation searches
+        if (value != -1 && value != 1 && value != 2) return fail(ORBC_ERR_ARG, "debug_nl_mode must be -1, 1 or 2");
+        c->nl_debug_mode = (int)value; c->nl_valid = false; return ORBC_OK;
     }
     if (!strcmp(name, "debug_own_slack")) {                      // test aid: slack of the owned-particle launch bounds (before orbc_mg_export), so that
         if (!(value >= 0)) return fail(ORBC_ERR_ARG, "debug_own_slack must be >= 0");   // small systems get launch bounds below their size
@@ -1588,7 +1591,7 @@ int orbc_debug_dump(orbc_ctx *c, int what, void *dst, size_t bytes) { if (c) cud
             NlState h;
             ORBC_CUDA(cudaMemcpyAsync(&h, c->nl_state, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
             ORBC_CUDA(cudaStreamSynchronize(c->stream));
-            out[0] = h.builds; out[1] = h.reuses; out[2] = (unsigned)h.overflow; out[3] = (unsigned)h.need;
+            out[0] = h.builds; out[1] = h.reuses; out[2] = (unsigned)h.overflow; out[3] = h.searches;
         }
         memcpy(dst, out, need);
         return check_flags(c); }

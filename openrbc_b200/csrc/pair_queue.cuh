@@ -35,7 +35,7 @@ struct CullTable {                 // per protein type: largest interaction rang
 __global__ void k_cell_bounds(const float4 *__restrict__ centroid, int n_cells, const int *__restrict__ cs_l, const float4 *__restrict__ xl,
                               const int *__restrict__ cs_p, const float4 *__restrict__ xp, float4 *__restrict__ lbound, float4 *__restrict__ pbound,
                               const int *__restrict__ need, int need_epoch, const int *__restrict__ gate) {
-    if (gate && *gate == 0) return;                          // a list-walking step: nobody culls
+    if (gate && *gate == 0) return;                          // a list-walking evaluation: nobody culls
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n_cells) return;
     if (need && need[c] != need_epoch) return;             // decomposed run: neither owned nor halo, its particles are stale here
@@ -224,25 +224,50 @@ __global__ void k_lipid_runs(int cb, int ce, const int *__restrict__ stencil, co
 // Layout: groups of 64 consecutive lipid slots, [group][entry][64] (coalesced for the thread-per-lipid readers), `cap` entries.
 struct NlState {                    // one per context, in device memory
     unsigned disp[64];              // largest squared displacement of a particle in the integration steps since the last gate (float bits)
-    float accum;                    // sum of the per-step maxima since the lists were built
-    int need;                       // 1: this evaluation (re)builds the lists; 0: it walks them
-    int overflow;                   // a list did not fit its row: the next evaluation builds again (and again: no reuse)
-    unsigned builds, reuses;        // statistics
+    float accum;                    // sum of the per-step maxima since the lists were recorded
+    int need;                       // what this evaluation does: 0 walks the lists, 1 searches AND records them, 2 searches without recording
+    int overflow;                   // a list did not fit its row: the lists are unusable until the next recording
+    unsigned builds, reuses;        // statistics: evaluations that recorded / that walked
+    int valid;                      // lists were recorded for the current partition
+    float d_last;                   // the largest single-step displacement seen last
+    unsigned searches;              // statistics: evaluations that searched without recording
+    int used, backoff, wait;        // walks of the current lists; rebuilds to sit out after lists that were never walked (doubles, halves)
+    unsigned work[8];               // tickets of the gated kernels of this evaluation (next_piece), zeroed by the gate
 };
+// The decision, once per force evaluation (one warp).  `force`: the partition has changed since the last evaluation (host's knowledge).
+//   after a rebuild   record, if the step just seen fits the skin -- unless lists were lately recorded and never walked (recording
+//                     costs ~25 % on top of a search and pays only if at least two of five recordings are walked): then sit out
+//                     1, 3, 7, 15 rebuilds (doubling with every such failure, halving with every recording that was walked)
+//   otherwise         walk, if lists exist and 2 x (sum of the per-step maxima since the recording) <= skin; search if not
 // `shared` (decomposed run): the per-rank maxima of the last integration step, published by k_nl_share into every rank's table
 // (the barrier behind the halo push stands between the two kernels): every rank takes the same maximum and decides alike.
-__global__ void k_nl_gate(NlState *st, int force, int moves, float skin, const unsigned *__restrict__ shared, int world) {
+__global__ void k_nl_gate(NlState *st, int force, int fixed_mode, int moves, float skin, const unsigned *__restrict__ shared, int world) {
     const int lane = threadIdx.x;
     unsigned m;
     if (shared) m = lane < world ? shared[lane] : 0u;
     else { m = max(st->disp[lane], st->disp[lane + 32]); st->disp[lane] = 0u; st->disp[lane + 32] = 0u; }
     m = __reduce_max_sync(0xffffffffu, m);
+    if (lane < 8) st->work[lane] = 0u;
     if (lane == 0) {
-        const float acc = st->accum + (float)moves * (sqrtf(__uint_as_float(m)) * 1.0001f + 1e-4f);   // + the rounding of x + v dt at |x| ~ 1000
-        const int need = (force || st->overflow || !(2.0f * acc <= skin)) ? 1 : 0;
-        st->accum = need ? 0.f : acc;
-        if (need) { st->overflow = 0; st->builds++; } else st->reuses++;
-        st->need = need;
+        const float d = sqrtf(__uint_as_float(m)) * 1.0001f + 1e-4f;          // + the rounding of x + v dt at |x| ~ 1000
+        if (moves > 0) st->d_last = d;
+        int mode;
+        if (force) {
+            if (fixed_mode > 0) mode = fixed_mode;               // (measurement aid)
+            else if (st->wait > 0) { st->wait--; mode = 2; }
+            else mode = (2.0f * st->d_last <= skin) ? 1 : 2;
+            st->valid = mode == 1; st->accum = 0.f; st->overflow = 0; st->used = 0;
+        } else if (!st->valid || st->overflow) { mode = 2; st->valid = 0; }
+        else {
+            const float acc = st->accum + (float)moves * d;
+            if (2.0f * acc <= skin) { mode = 0; st->accum = acc; if (st->used++ == 0) st->backoff >>= 1; }
+            else {
+                mode = 2; st->valid = 0;
+                if (st->used == 0) { st->backoff = min(2 * st->backoff + 1, 15); st->wait = st->backoff; }   // recorded for nothing
+            }
+        }
+        if (mode == 0) st->reuses++; else if (mode == 1) st->builds++; else st->searches++;
+        st->need = mode;
     }
 }
 // decomposed run, after the integrator kernels of a step: this rank's largest squared displacement -> slot `rank` of every rank
@@ -267,6 +292,20 @@ __device__ __forceinline__ void nl_track(unsigned *disp, float d2) {
     if (threadIdx.x == 0 && s_max) atomicMax(disp + (blockIdx.x & 63), s_max);
 }
 
+// The pieces of work of a block.  Without a ticket counter (work == nullptr): blockIdx.x, then on by the size of the grid.  The
+// gated kernels of the hit lists are launched three at a time (walk / record / search) and two of them return at once: they get a
+// grid that fills the GPU once, and their blocks draw pieces from a ticket counter, in order, as the block scheduler would have
+// handed them out.  (The lipid kernels only: the protein kernels, 8.8 k blocks with the expensive proteins first, are faster over
+// their natural grid -- walker 67 us against 107 us with tickets -- and a launch that returns at once costs them ~4 us.)
+__device__ __forceinline__ bool next_piece(unsigned *work, unsigned *s_piece, unsigned &piece, bool first) {
+    if (first) { piece = blockIdx.x; return true; }             // (no ticket for the first piece: a burst of same-address atomics costs ~10 us)
+    if (!work) { piece += gridDim.x; return true; }
+    __syncthreads();                                            // (everybody has read the previous ticket)
+    if (threadIdx.x == 0) *s_piece = gridDim.x + atomicAdd(work, 1u);
+    __syncthreads();
+    piece = *s_piece;
+    return true;
+}
 struct LLList { int *list; int *cnt; int cap; NlState *st; };
 __device__ __forceinline__ size_t ll_row(int i, int cap) { return ((size_t)(i >> 6) * cap) * 64 + (i & 63); }
 
@@ -280,8 +319,9 @@ __device__ __forceinline__ size_t ll_row(int i, int cap) { return ((size_t)(i >>
 // The grid may be smaller than the number of 64-lipid groups (grid-stride), so that a gated launch that returns costs nothing.
 template <int MINB, int W, bool BUILD>
 __global__ void __launch_bounds__(kLLBlock, MINB) k_pair_ll_r(PairArgs a, const LLConst kc, const int2 *__restrict__ lruns, const int *__restrict__ lrun_info,
-                                                               const int *__restrict__ gate, int want, LLList nl, float skin) {
+                                                               const int *__restrict__ gate, int want, LLList nl, float skin, unsigned *work) {
     if (gate && *gate != want) return;
+    __shared__ unsigned s_piece;
     __shared__ int s_q[kLLBlock / 32][kQCap * 32];
     const int lane = threadIdx.x & 31;
     int *const q = s_q[threadIdx.x >> 5] + lane;
@@ -295,7 +335,10 @@ __global__ void __launch_bounds__(kLLBlock, MINB) k_pair_ll_r(PairArgs a, const 
     const unsigned q0 = (unsigned)__cvta_generic_to_shared(q);
     const unsigned q_full = q0 + (kQCap - W) * 128;              // a group of W always fits below this mark
     const int l0 = a.range[0], l1 = a.range[1];
-    for (int base = l0 + blockIdx.x * kLLBlock; base < l1; base += gridDim.x * kLLBlock) {
+    unsigned piece;
+    for (bool first = true; next_piece(work, &s_piece, piece, first); first = false) {
+        const int base = l0 + (int)piece * kLLBlock;
+        if (base >= l1) break;
         const int i = base + threadIdx.x;
         const bool live = i < l1;
         float fx = 0, fy = 0, fz = 0, tx = 0, ty = 0, tz = 0, sB = 0;
@@ -327,10 +370,11 @@ __global__ void __launch_bounds__(kLLBlock, MINB) k_pair_ll_r(PairArgs a, const 
                     // the lane's own slot, which fails the guards): one coalesced 128-byte store per entry instead of 32 sectors
                     const unsigned len = __reduce_max_sync(0xffffffffu, qp - q0);
                     for (unsigned off = 0; off < len; off += 128) {
-                        const int j = off < qp - q0 ? lds_i32(q0 + off) : self;
+                        const bool have = off < qp - q0;
+                        const int j = have ? lds_i32(q0 + off) : self;
                         if (live && total < nl.cap) row[(size_t)total * 64] = j;
                         ++total;
-                        ll_eval<true>(kc, xl, nl_, xi, mi, j, fx, fy, fz, tx, ty, tz, sB);
+                        if (have) ll_eval<true>(kc, xl, nl_, xi, mi, j, fx, fy, fz, tx, ty, tz, sB);   // (a padding entry costs no gather)
                     }
                 } else
                     for (unsigned e = q0; e < qp; e += 128) ll_eval<false>(kc, xl, nl_, xi, mi, lds_i32(e), fx, fy, fz, tx, ty, tz, sB);
@@ -352,10 +396,11 @@ __global__ void __launch_bounds__(kLLBlock, MINB) k_pair_ll_r(PairArgs a, const 
         if (BUILD) {
             const unsigned len = __reduce_max_sync(0xffffffffu, qp - q0);
             for (unsigned off = 0; off < len; off += 128) {
-                const int j = off < qp - q0 ? lds_i32(q0 + off) : self;
+                const bool have = off < qp - q0;
+                const int j = have ? lds_i32(q0 + off) : self;
                 if (live && total < nl.cap) row[(size_t)total * 64] = j;
                 ++total;
-                ll_eval<true>(kc, xl, nl_, xi, mi, j, fx, fy, fz, tx, ty, tz, sB);
+                if (have) ll_eval<true>(kc, xl, nl_, xi, mi, j, fx, fy, fz, tx, ty, tz, sB);
             }
         } else
             for (unsigned e = q0; e < qp; e += 128) ll_eval<false>(kc, xl, nl_, xi, mi, lds_i32(e), fx, fy, fz, tx, ty, tz, sB);
@@ -371,12 +416,16 @@ __global__ void __launch_bounds__(kLLBlock, MINB) k_pair_ll_r(PairArgs a, const 
 // The list walker: one thread per lipid, entries read coalesced, two partners in flight per lane.  An entry beyond the lane's
 // count is replaced by the lane's own slot (r2 = 0 fails the guards), which keeps the loop free of branches around the loads.
 template <int MINB, bool XNREC>
-__global__ void __launch_bounds__(kLLBlock, MINB) k_pair_ll_list(PairArgs a, const LLConst kc, const int *__restrict__ gate, int want, LLList nl, const XN *__restrict__ xn) {
+__global__ void __launch_bounds__(kLLBlock, MINB) k_pair_ll_list(PairArgs a, const LLConst kc, const int *__restrict__ gate, int want, LLList nl, const XN *__restrict__ xn, unsigned *work) {
     if (gate && *gate != want) return;
+    __shared__ unsigned s_piece;
     const float4 *__restrict__ xl = a.xl;
     const float4 *__restrict__ nl_ = a.nl;
     const int l0 = a.range[0], l1 = a.range[1];
-    for (int base = l0 + blockIdx.x * kLLBlock; base < l1; base += gridDim.x * kLLBlock) {
+    unsigned piece;
+    for (bool first = true; next_piece(work, &s_piece, piece, first); first = false) {
+        const int base = l0 + (int)piece * kLLBlock;
+        if (base >= l1) break;
         const int i = base + threadIdx.x;
         const bool live = i < l1;
         float fx = 0, fy = 0, fz = 0, tx = 0, ty = 0, tz = 0, sB = 0;
@@ -393,11 +442,16 @@ __global__ void __launch_bounds__(kLLBlock, MINB) k_pair_ll_list(PairArgs a, con
         for (int s = 0; s < maxc; s += 4) {
             int j[4]; float4 xj[4], nj[4];
             #pragma unroll
-            for (int u = 0; u < 4; ++u) j[u] = s + u < cnt ? __ldg(row + (size_t)(s + u) * 64) : self;
+            for (int u = 0; u < 4; ++u) { j[u] = s + u < cnt ? __ldg(row + (size_t)(s + u) * 64) : -1; if (j[u] == self) j[u] = -1; }   // (recorded padding = the lane's own slot)
+            // four partners in flight per lane.  A gather costs one L1 request per LANE (the walker runs at that limit: 2 requests
+            // per pair, ~1 per cycle and SM), so padding entries must not gather: they get the lane's own position, which fails the guards
             #pragma unroll
-            for (int u = 0; u < 4; ++u) {                        // four partners in flight per lane
-                if (XNREC) ldg256(xn + j[u], xj[u], nj[u]);
-                else { xj[u] = __ldg(xl + j[u]); nj[u] = __ldg(nl_ + j[u]); }
+            for (int u = 0; u < 4; ++u) {
+                xj[u] = make_float4(xi.x, xi.y, xi.z, 0.f); nj[u] = xj[u];
+                if (j[u] >= 0) {
+                    if (XNREC) ldg256(xn + j[u], xj[u], nj[u]);
+                    else { xj[u] = __ldg(xl + j[u]); nj[u] = __ldg(nl_ + j[u]); }
+                }
             }
             #pragma unroll
             for (int u = 0; u < 4; ++u) ll_pair<true>(kc, xi, mi, xj[u], nj[u], fx, fy, fz, tx, ty, tz, sB);

@@ -18,7 +18,8 @@ st = bench.load_state(workload)
 sim = orbc.Simulation(st, kBT=0.22)
 sim.run_langevin(4)
 base = None
-for name, opts in (("run-list, search", dict(ll_variant=1, nl_reuse=0)), ("run-list, walking hit lists", dict(ll_variant=1, nl_reuse=1)), ("tile", dict(ll_variant=0))):
+for name, opts in (("run-list, search", dict(ll_variant=1, nl_reuse=0)), ("run-list, walking hit lists", dict(ll_variant=1, nl_reuse=1)),
+                   ("run-list, gated, recording", dict(debug_nl_mode=1)), ("run-list, gated, searching", dict(debug_nl_mode=2)), ("tile", dict(debug_nl_mode=-1, ll_variant=0))):
     for k, v in opts.items():
         sim.set_option(k, v)
     sim.clear_force(); sim.compute_pairwise_fused(); sim.synchronize()
@@ -34,7 +35,7 @@ for name, opts in (("run-list, search", dict(ll_variant=1, nl_reuse=0)), ("run-l
     msp, npr = sim.profile_read("pair_protein")
     sim.profile_enable(False)
     print(f"{name:30s}: pair_lipid {ms / n * 1e3:7.1f} us  pair_protein {msp / max(npr, 1) * 1e3:7.1f} us; max rel err vs the first {err:.2e}", flush=True)
-for name, opts in (("search", dict(ll_variant=1, nl_reuse=0)), ("hit lists, separate x / n gathers", dict(ll_variant=1, nl_reuse=1, ll_xn=0)), ("hit lists, (x, n) records", dict(ll_xn=1))):
+for name, opts in (("search", dict(ll_variant=1, nl_reuse=0)), ("hit lists", dict(ll_variant=1, nl_reuse=1, ll_xn=0))):
     for k, v in opts.items():
         sim.set_option(k, v)
     sim.run_langevin(4); sim.synchronize()
