@@ -95,10 +95,14 @@ ORBC_API int  orbc_set_stream(orbc_ctx *ctx, void *cuda_stream);
 /* tuning / test switches, by name.
  *   "pair_impl"   2 = production kernels (default), 1 = the simple thread-per-particle kernels kept as an independent cross-check
  *   "ll_variant"  lipid-lipid kernel: 1 = thread per lipid over candidate runs, with hit lists (default); 0 = warp-per-cell tile kernel
- *   "nl_reuse"    1 (default) = the force evaluation after a rebuild records per-particle hit lists with a skin and the evaluations up
- *                 to the next rebuild walk them (exact re-test of every entry, a displacement bound guards the skin: same hits, same
- *                 forces); 0 = every evaluation searches the stencils.  Single GPU only; ignored on a decomposed context.
+ *   "nl_reuse"    1 (default) = hit lists: a force evaluation after a rebuild may record, per particle, every candidate closer than
+ *                 cutoff + skin, and the evaluations up to the next rebuild walk those lists (exact re-test of every entry; a bound on
+ *                 the displacements guards the skin: same hits, same forces).  The device decides at every evaluation whether it
+ *                 walks, records or just searches (a recording that would not be walked is not made).  0 = every evaluation
+ *                 searches the stencils.  On a decomposed context the ranks exchange their displacement bounds and decide alike.
  *   "nl_skin"     the skin of those lists, default 0.1
+ *   "stencil_refresh"  1 (default) = rebuilds that keep the cell numbering re-classify the recorded r < 9 + 1 neighbours of every cell
+ *                 instead of searching the centroid grid (cells whose centroid jumped are searched in full; same stencils); 0 = always search
  *   "prot_lanes"  lanes per protein of the protein kernel (0 = automatic); debug_*: test aids */
 ORBC_API int  orbc_set_option(orbc_ctx *ctx, const char *name, double value);
 
@@ -227,7 +231,8 @@ typedef enum {
     ORBC_DUMP_STENCIL_COUNTS = 9,/* n_cells x 3 int: entries with centroid distance < 6, < 8, < 9 */
     ORBC_DUMP_STENCIL = 10,      /* n_cells x ORBC_STENCIL_STRIDE int, ordered (class, id) */
     ORBC_DUMP_TAG2IDX = 11,      /* protein tag -> index, (max_tag + 1) int */
-    ORBC_DUMP_COUNTERS = 12,     /* 8 x uint64 device counters (fallback searches, ...) */
+    ORBC_DUMP_COUNTERS = 12,     /* 8 x uint64 device counters: [0] nearest-centroid fallback searches, [1..6] pair tests / hits of the pair_impl 1 kernels,
+                                  * [7] stencil refresh: cells searched in full (low 40 bits), refreshes redone by a full search (high bits) */
     ORBC_DUMP_NL_STATS = 13      /* 4 x uint32: force evaluations that recorded the hit lists, that walked them, overflow flag, that searched without recording */
 } orbc_dump;
 #define ORBC_STENCIL_STRIDE 64

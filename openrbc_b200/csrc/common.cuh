@@ -25,6 +25,7 @@ inline int fail(int code, const char *fmt, ...) {
 
 constexpr int kNType = 6;              // forcefield_canonical.h:37
 constexpr int kStencilStride = ORBC_STENCIL_STRIDE;
+constexpr int kMoversCap = 4096;
 constexpr float kBin = 10.0f;          // centroid grid bin = largest centroid stencil radius (9, compute_pairwise_fused.h:183) + the margin of the wide stencils (rebuild.cuh)
 constexpr int kMaxWorld = 8;           // ranks of one spatially decomposed run (one B200 box)
 
@@ -132,7 +133,9 @@ struct orbc_ctx {
     int *stencil_cnt = nullptr;                   // n_cells, packed n6 | n8 << 8 | n9 << 16
     bool stencil_valid = false;
     int *wide = nullptr, *wide_cnt = nullptr; float4 *cen_ref = nullptr;   // wide stencils (r < 9 + margin) and the centroids they were recorded at (rebuild.cuh)
-    int *wide_ok = nullptr;                       // device flag: no centroid has outrun the margin since
+    bool wide_on = true;                          // option stencil_refresh
+    int *movers = nullptr;                        // cells whose centroid has outrun the margin, and cells a mover has newly reached (2 x kMoversCap; counts in wide_ok[1], [2])
+    int *wide_ok = nullptr;                       // device flag: the refreshed stencils can be trusted (no mover was missed, the list of movers did not overflow)
     bool wide_valid = false;                      // the wide stencils match the current numbering of the cells (host's view)
     float4 *cell_normal = nullptr;                // constrain_volume's persistent scratch
     float4 *lbound = nullptr, *pbound = nullptr;  // per-cell bounding spheres of the current lipids / proteins (pair_queue.cuh)

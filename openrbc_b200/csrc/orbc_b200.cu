@@ -174,15 +174,19 @@ int build_index(orbc_ctx *c, bool all_cells = true, bool renumbered = true) {
     const int c0 = part ? c->mg.cb : 0, c1 = part ? c->mg.ce : nc;
     const WideOut wide = {c->wide, c->wide_cnt, c->cen_ref};
     if (c1 > c0) {
-        if (c->wide_valid && !renumbered) {
+        if (c->wide_valid && !renumbered && c->wide_on) {
             // the cells kept their numbers since the last full search: re-classify the recorded neighbours (k_stencil_refresh); the full
             // search stands by behind a device flag in case a centroid has outrun the margin
+            const Movers mv = {c->movers, c->wide_ok + 1, kMoversCap}, patch = {c->movers + kMoversCap, c->wide_ok + 2, kMoversCap};
             ORBC_CUDA(cudaMemsetAsync(c->wide_ok, 0xff, sizeof(int), c->stream));
-            ORBC_LAUNCH(c, k_centroid_disp, blocks_for(nc, kBlock), kBlock, 0, c->centroid, c->cen_ref, nc, c->wide_ok);
+            ORBC_CUDA(cudaMemsetAsync(c->wide_ok + 1, 0, 2 * sizeof(int), c->stream));
+            ORBC_LAUNCH(c, k_centroid_disp, blocks_for(nc, kBlock), kBlock, 0, c->centroid, c->cen_ref, nc, c->wide_ok, mv);
             ORBC_LAUNCH(c, k_stencil_refresh, blocks_for(c1 - c0, kStencilWarps), kStencilWarps * 32, 0, c->centroid, c0, c1, c->wide, c->wide_cnt, c->stencil, c->stencil_cnt, c->d_flags, halo, c->wide_ok);
-            ORBC_LAUNCH(c, k_stencil_build, 148 * 4, kStencilWarps * 32, 0, c->centroid, c0, c1, gd, c->stencil, c->stencil_cnt, c->d_flags, halo, wide, c->wide_ok);
+            ORBC_LAUNCH(c, k_stencil_movers<true>, 148, kStencilWarps * 32, 0, c->centroid, c->cen_ref, c0, c1, gd, c->stencil, c->stencil_cnt, c->d_flags, halo, c->wide, c->wide_cnt, mv, patch, c->wide_ok, c->d_counters);
+            ORBC_LAUNCH(c, k_stencil_movers<false>, 148, kStencilWarps * 32, 0, c->centroid, c->cen_ref, c0, c1, gd, c->stencil, c->stencil_cnt, c->d_flags, halo, c->wide, c->wide_cnt, patch, patch, c->wide_ok, c->d_counters);
+            ORBC_LAUNCH(c, k_stencil_build, 148 * 4, kStencilWarps * 32, 0, c->centroid, nc, c0, c1, gd, c->stencil, c->stencil_cnt, c->d_flags, halo, wide, c->wide_ok, c->d_counters);
         } else {
-            ORBC_LAUNCH(c, k_stencil_build, blocks_for(c1 - c0, kStencilWarps), kStencilWarps * 32, 0, c->centroid, c0, c1, gd, c->stencil, c->stencil_cnt, c->d_flags, halo, wide, (const int *)nullptr);
+            ORBC_LAUNCH(c, k_stencil_build, blocks_for(c1 - c0, kStencilWarps), kStencilWarps * 32, 0, c->centroid, nc, c0, c1, gd, c->stencil, c->stencil_cnt, c->d_flags, halo, wide, (const int *)nullptr, c->d_counters);
             c->wide_valid = true;                                // (a rank's partial search records its own cells: all its refreshes need)
         }
     }
@@ -584,7 +588,7 @@ int preload_kernels() {
     ORBC_PRELOAD(k_pair_lipid); ORBC_PRELOAD(k_lipid_runs); ORBC_PRELOAD(k_rank_only); ORBC_PRELOAD(k_init_centroids); ORBC_PRELOAD(k_bbox); ORBC_PRELOAD((k_pair_ll_r<20, 4, false>)); ORBC_PRELOAD(k_pair_ll_t); ORBC_PRELOAD((k_pair_prot<1, false>)); ORBC_PRELOAD((k_pair_prot<2, false>)); ORBC_PRELOAD((k_pair_prot<4, false>)); ORBC_PRELOAD((k_pair_prot<1, true>)); ORBC_PRELOAD((k_pair_prot<2, true>)); ORBC_PRELOAD((k_pair_prot<4, true>)); ORBC_PRELOAD(k_pair_prot_list<1>); ORBC_PRELOAD(k_pair_prot_list<2>); ORBC_PRELOAD(k_pair_prot_list<4>); ORBC_PRELOAD((k_pair_ll_r<16, 4, true>)); ORBC_PRELOAD((k_pair_ll_list<16, false>)); ORBC_PRELOAD((k_pair_ll_list<16, true>)); ORBC_PRELOAD(k_pack_xn); ORBC_PRELOAD(k_nl_gate); ORBC_PRELOAD(k_nl_share); ORBC_PRELOAD(k_pair_protein);
     ORBC_PRELOAD(k_permute_centroids); ORBC_PRELOAD(k_porder_flag); ORBC_PRELOAD(k_porder_scatter); ORBC_PRELOAD(k_post_torque); ORBC_PRELOAD(k_radix_hist);
     ORBC_PRELOAD(k_radix_scatter); ORBC_PRELOAD(k_rank_and_move); ORBC_PRELOAD(k_remap_cellid); ORBC_PRELOAD(k_scan_onepass); ORBC_PRELOAD(k_set3); ORBC_PRELOAD(k_set_range); ORBC_PRELOAD(k_set_range_const); ORBC_PRELOAD(k_share_counts);
-    ORBC_PRELOAD(k_stencil_build); ORBC_PRELOAD(k_stencil_refresh); ORBC_PRELOAD(k_centroid_disp); ORBC_PRELOAD(k_stray_mask); ORBC_PRELOAD(k_unpack3); ORBC_PRELOAD(k_unpack_w); ORBC_PRELOAD(k_verlet_langevin); ORBC_PRELOAD(k_zero4);
+    ORBC_PRELOAD(k_stencil_build); ORBC_PRELOAD(k_stencil_refresh); ORBC_PRELOAD(k_stencil_movers<true>); ORBC_PRELOAD(k_stencil_movers<false>); ORBC_PRELOAD(k_centroid_disp); ORBC_PRELOAD(k_stray_mask); ORBC_PRELOAD(k_unpack3); ORBC_PRELOAD(k_unpack_w); ORBC_PRELOAD(k_verlet_langevin); ORBC_PRELOAD(k_zero4);
 #undef ORBC_PRELOAD
     return ORBC_OK;
 }
@@ -625,7 +629,7 @@ int alloc_voronoi(orbc_ctx *c, int nc) {
     ORBC_TRY(dev_alloc(&c->keys, nc)); ORBC_TRY(dev_alloc(&c->keys_tmp, nc)); ORBC_TRY(dev_alloc(&c->perm, nc)); ORBC_TRY(dev_alloc(&c->perm_tmp, nc)); ORBC_TRY(dev_alloc(&c->inv, nc));
     ORBC_TRY(dev_alloc(&c->grid.bin_items, nc)); ORBC_TRY(dev_alloc(&c->grid.bin_of, nc)); ORBC_TRY(dev_alloc(&c->grid.bin_slot, nc)); ORBC_TRY(dev_alloc(&c->grid.sorted, nc));
     ORBC_TRY(dev_alloc(&c->stencil, (size_t)nc * kStencilStride)); ORBC_TRY(dev_alloc(&c->stencil_cnt, nc));
-    ORBC_TRY(dev_alloc(&c->wide, (size_t)nc * kStencilStride)); ORBC_TRY(dev_alloc(&c->wide_cnt, nc)); ORBC_TRY(dev_alloc(&c->cen_ref, nc)); ORBC_TRY(dev_alloc(&c->wide_ok, 1));
+    ORBC_TRY(dev_alloc(&c->wide, (size_t)nc * kStencilStride)); ORBC_TRY(dev_alloc(&c->wide_cnt, nc)); ORBC_TRY(dev_alloc(&c->cen_ref, nc)); ORBC_TRY(dev_alloc(&c->wide_ok, 3)); ORBC_TRY(dev_alloc(&c->movers, 2 * kMoversCap));
     c->wide_valid = false;
     ORBC_TRY(dev_alloc(&c->cell_normal, nc)); ORBC_TRY(dev_alloc(&c->lbound, nc)); ORBC_TRY(dev_alloc(&c->pbound, nc));
     ORBC_TRY(dev_alloc(&c->lruns, (size_t)nc * kRunStride)); ORBC_TRY(dev_alloc(&c->lrun_cnt, (size_t)nc)); c->lruns_cells = (size_t)nc;
@@ -722,7 +726,7 @@ void orbc_destroy(orbc_ctx *c) { if (c) cudaSetDevice(c->device);
     free_species(c->sp[0]); free_species(c->sp[1]);
     dev_free(c->centroid); dev_free(c->centroid_tmp); dev_free(c->keys); dev_free(c->keys_tmp); dev_free(c->perm); dev_free(c->perm_tmp); dev_free(c->inv);
     dev_free(c->grid.bin_start); dev_free(c->grid.bin_items); dev_free(c->grid.bin_of); dev_free(c->grid.bin_slot); dev_free(c->grid.sorted);
-    dev_free(c->stencil); dev_free(c->stencil_cnt); dev_free(c->wide); dev_free(c->wide_cnt); dev_free(c->cen_ref); dev_free(c->wide_ok); dev_free(c->cell_normal); dev_free(c->lbound); dev_free(c->pbound); dev_free(c->porder); dev_free(c->lruns); dev_free(c->lrun_cnt); dev_free(c->bonds); dev_free(c->tag2idx);
+    dev_free(c->stencil); dev_free(c->stencil_cnt); dev_free(c->wide); dev_free(c->wide_cnt); dev_free(c->cen_ref); dev_free(c->wide_ok); dev_free(c->movers); dev_free(c->cell_normal); dev_free(c->lbound); dev_free(c->pbound); dev_free(c->porder); dev_free(c->lruns); dev_free(c->lrun_cnt); dev_free(c->bonds); dev_free(c->tag2idx);
     dev_free(c->scan_tmp); dev_free(c->radix_hist); dev_free(c->stage); dev_free(c->d_acc); dev_free(c->d_counters); dev_free(c->d_flags); dev_free(c->d_nh);
     dev_free(c->noise[0]); dev_free(c->noise[1]); dev_free(c->d_range); dev_free(c->tile_overflow); dev_free(c->xn);
     { NlState *st = (NlState *)c->nl_state; dev_free(st); } dev_free(c->ll_list); dev_free(c->ll_cnt); dev_free(c->pl_list); dev_free(c->pl_cnt); dev_free(c->pp_list); dev_free(c->pp_cnt);
@@ -761,6 +765,7 @@ int orbc_set_option(orbc_ctx *c, const char *name, double value) { if (c) cudaSe
         if (!(value >= 1 && value <= kTileCap)) return fail(ORBC_ERR_ARG, "debug_tile_cap must be in [1, %d]", kTileCap);
         c->tile_cap = (int)value; c->lruns_valid = false; return ORBC_OK;
     }
+    if (!strcmp(name, "stencil_refresh")) { c->wide_on = value != 0; return ORBC_OK; }   // 0: every rebuild searches the centroid grid in full
     if (!strcmp(name, "debug_nl_mode")) {                        // measurement aid: -1 the gate decides, 1 every evaluation records the hit lists, 2 every evaluation searches
         if (value != -1 && value != 1 && value != 2) return fail(ORBC_ERR_ARG, "debug_nl_mode must be -1, 1 or 2");
         c->nl_debug_mode = (int)value; c->nl_valid = false; return ORBC_OK;

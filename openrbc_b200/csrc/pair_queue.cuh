@@ -704,9 +704,14 @@ __global__ void __launch_bounds__(kPBlock) k_pair_prot_list(PairArgs a, const in
                 #pragma unroll
                 for (int u = 0; u < 4; ++u) pl_pair(a, type1, cutsq, ljcut, xi, mi, max(j[u], 0), xj[u], l0, l1, fx, fy, fz, tx, ty, tz);
             }
-            for (int s = 0; s < np_; ++s) {
-                const int j = __ldg(row_p + (size_t)s * 64);
-                pp_pair(type1, xi, __ldg(a.xp + j), s_cutsqpp, s_ljcutsq, fx, fy, fz);
+            for (int s = 0; s < np_; s += 4) {                   // (same: the padding is the protein itself, r2 = 0 fails the guard)
+                int j[4]; float4 xj[4];
+                #pragma unroll
+                for (int u = 0; u < 4; ++u) j[u] = s + u < np_ ? __ldg(row_p + (size_t)(s + u) * 64) : -1;
+                #pragma unroll
+                for (int u = 0; u < 4; ++u) xj[u] = j[u] >= 0 ? __ldg(a.xp + j[u]) : make_float4(xi.x, xi.y, xi.z, 0.f);
+                #pragma unroll
+                for (int u = 0; u < 4; ++u) pp_pair(type1, xi, xj[u], s_cutsqpp, s_ljcutsq, fx, fy, fz);
             }
         }
         #pragma unroll

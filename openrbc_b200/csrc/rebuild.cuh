@@ -139,8 +139,8 @@ struct HaloOut { unsigned char *dest_mask; int *need; int need_epoch; CellOwners
 // every rebuild.  The full search (27 grid bins, ~80 candidates per cell) therefore also records every cell closer than 9 + kWideMargin
 // together with the centroids it saw (cen_ref); the rebuilds that follow re-classify only those ~25 recorded neighbours with
 // the exact squared distances (k_stencil_refresh) — the same test on the same operands, so the same sets — as long as no centroid
-// has moved further than kWideMargin / 2 from its recorded position (k_centroid_disp raises the flag otherwise and the full
-// search runs again).  A Morton renumbering of the cells always forces the full search.
+// has moved further than kWideMargin / 2 from its recorded position; the few that have (the movers, below) are searched in full.
+// A Morton renumbering of the cells always forces the full search of all cells.
 constexpr float kWideMargin = 1.0f;
 struct WideOut { int *wide; int *wide_cnt; float4 *cen_ref; };    // wide == nullptr: not recorded
 
@@ -182,54 +182,65 @@ __device__ __forceinline__ void stencil_emit(const int *s_key, int count, int c,
     }
 }
 
+// the candidates of one cell: the 27 grid bins around q, every centroid closer than sqrt(lim) as a key in s_key (any order); returns
+// their number (which may exceed the row: the caller flags that).  One warp.
+__device__ __forceinline__ int stencil_search(const float4 q, const GridDev &g, float lim, int *__restrict__ s_key, int lane) {
+    int count = 0;
+    if (!(q.x == q.x && q.y == q.y && q.z == q.z)) return 0;      // an empty cell
+    int bx, by, bz; grid_bin(g, q, bx, by, bz);
+    const int x0 = max(bx - 1, 0), x1 = min(bx + 1, g.dx - 1);
+    // lanes 0..8 fetch the nine x-runs together, a warp scan turns them into one flat candidate list
+    int beg = 0, cnt = 0;
+    if (lane < 9) {
+        const int zz = bz - 1 + lane / 3, yy = by - 1 + lane % 3;
+        if (zz >= 0 && zz < g.dz && yy >= 0 && yy < g.dy) {
+            const int row = (zz * g.dy + yy) * g.dx;
+            beg = g.bin_start[row + x0];
+            cnt = g.bin_start[row + x1 + 1] - beg;
+        }
+    }
+    int incl = cnt;
+    #pragma unroll
+    for (int d = 1; d < 16; d <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += y; }
+    const int total = __shfl_sync(0xffffffffu, incl, 8);
+    int rb[9], re[9];                                             // run r covers flat slots [re[r] - cnt_r, re[r])
+    #pragma unroll
+    for (int r = 0; r < 9; ++r) { rb[r] = __shfl_sync(0xffffffffu, beg, r); re[r] = __shfl_sync(0xffffffffu, incl, r); }
+    for (int s0 = 0; s0 < total; s0 += 32) {
+        const int s = s0 + lane;
+        int key = -1;
+        if (s < total) {
+            int idx = rb[0] + s;
+            #pragma unroll
+            for (int r = 1; r < 9; ++r) if (s >= re[r - 1]) idx = rb[r] + (s - re[r - 1]);
+            const float4 p = g.sorted[idx];
+            const float d2 = dist2_rn(p, q);                      // normsq(pts_[i] - q), kdtree.h:274
+            if (d2 < lim) key = stencil_key(d2, __float_as_int(p.w));
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, key >= 0);
+        const int pos = count + __popc(m & ((1u << lane) - 1u));
+        if (key >= 0 && pos < kStencilStride) s_key[pos] = key;
+        count += __popc(m);
+    }
+    return count;
+}
+
 // the full search.  `gate`: run only if *gate == 0 (the refresh could not be trusted); grid-stride, so that a gated launch is cheap.
-__global__ void __launch_bounds__(kStencilWarps * 32) k_stencil_build(const float4 *__restrict__ centroid, int c_beg, int c_end, GridDev g,
+// With wide rows it also notes where EVERY centroid stood (cen_ref): the displacements are measured from this moment on.
+__global__ void __launch_bounds__(kStencilWarps * 32) k_stencil_build(const float4 *__restrict__ centroid, int n_cells, int c_beg, int c_end, GridDev g,
                                                                        int *__restrict__ stencil, int *__restrict__ stencil_cnt, int *__restrict__ flags, HaloOut halo,
-                                                                       WideOut wide, const int *__restrict__ gate) {
+                                                                       WideOut wide, const int *__restrict__ gate, unsigned long long *__restrict__ counters) {
     if (gate && *gate != 0) return;
+    if (gate && blockIdx.x == 0 && threadIdx.x == 0) counters[7] += 1ull << 40;             // statistics: refreshes that were not trusted (high part)
     __shared__ int s_key[kStencilWarps][kStencilStride];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float lim = wide.wide ? (9.0f + kWideMargin) * (9.0f + kWideMargin) : 81.0f;
+    if (wide.wide)                                               // (the cells of other ranks; the searched ones are noted below)
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_cells; i += gridDim.x * blockDim.x)
+            if (i < c_beg || i >= c_end) wide.cen_ref[i] = centroid[i];
     for (int c = c_beg + blockIdx.x * kStencilWarps + w; c < c_end; c += gridDim.x * kStencilWarps) {
         const float4 q = centroid[c];
-        int count = 0;
-        if (q.x == q.x && q.y == q.y && q.z == q.z) {
-            int bx, by, bz; grid_bin(g, q, bx, by, bz);
-            const int x0 = max(bx - 1, 0), x1 = min(bx + 1, g.dx - 1);
-            // lanes 0..8 fetch the nine x-runs together, a warp scan turns them into one flat candidate list
-            int beg = 0, cnt = 0;
-            if (lane < 9) {
-                const int zz = bz - 1 + lane / 3, yy = by - 1 + lane % 3;
-                if (zz >= 0 && zz < g.dz && yy >= 0 && yy < g.dy) {
-                    const int row = (zz * g.dy + yy) * g.dx;
-                    beg = g.bin_start[row + x0];
-                    cnt = g.bin_start[row + x1 + 1] - beg;
-                }
-            }
-            int incl = cnt;
-            #pragma unroll
-            for (int d = 1; d < 16; d <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += y; }
-            const int total = __shfl_sync(0xffffffffu, incl, 8);
-            int rb[9], re[9];                                     // run r covers flat slots [re[r] - cnt_r, re[r])
-            #pragma unroll
-            for (int r = 0; r < 9; ++r) { rb[r] = __shfl_sync(0xffffffffu, beg, r); re[r] = __shfl_sync(0xffffffffu, incl, r); }
-            for (int s0 = 0; s0 < total; s0 += 32) {
-                const int s = s0 + lane;
-                int key = -1;
-                if (s < total) {
-                    int idx = rb[0] + s;
-                    #pragma unroll
-                    for (int r = 1; r < 9; ++r) if (s >= re[r - 1]) idx = rb[r] + (s - re[r - 1]);
-                    const float4 p = g.sorted[idx];
-                    const float d2 = dist2_rn(p, q);              // normsq(pts_[i] - q), kdtree.h:274
-                    if (d2 < lim) key = stencil_key(d2, __float_as_int(p.w));
-                }
-                const unsigned m = __ballot_sync(0xffffffffu, key >= 0);
-                const int pos = count + __popc(m & ((1u << lane) - 1u));
-                if (key >= 0 && pos < kStencilStride) s_key[w][pos] = key;
-                count += __popc(m);
-            }
-        }
+        int count = stencil_search(q, g, lim, s_key[w], lane);
         if (count > kStencilStride) { if (lane == 0) atomicExch(&flags[0], c + 1); count = kStencilStride; }
         __syncwarp();
         if (wide.wide && lane == 0) wide.cen_ref[c] = q;
@@ -238,15 +249,63 @@ __global__ void __launch_bounds__(kStencilWarps * 32) k_stencil_build(const floa
     }
 }
 
-// largest displacement of a centroid since the wide stencils were recorded: *ok = 0 when 2 x displacement can exceed the margin
-__global__ void k_centroid_disp(const float4 *__restrict__ centroid, const float4 *__restrict__ cen_ref, int n, int *__restrict__ ok) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const float4 a = centroid[i], b = cen_ref[i];
+// Has a centroid stayed within kWideMargin / 2 of where it stood when the wide rows were recorded?  (Two cells that both have can
+// not have come closer than 9 without the one being in the other's wide row.)  An empty cell stays a NaN on both sides.
+__device__ __forceinline__ bool centroid_settled(const float4 a, const float4 b) {
     const float dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z;
     const float lim = 0.5f * kWideMargin - 1e-3f;
-    const bool fine = (dx * dx + dy * dy + dz * dz <= lim * lim) || (!(a.x == a.x) && !(b.x == b.x));   // (an empty cell stays a NaN on both sides)
-    if (!fine) atomicExch(ok, 0);
+    return (dx * dx + dy * dy + dz * dz <= lim * lim) || (!(a.x == a.x) && !(b.x == b.x));
+}
+// The MOVERS: the cells that have not.  ~70 of the 188 549 cells of the RBC per rebuild: small cells whose centroid jumps by 0.5 .. 1
+// when a member arrives or leaves.  They are listed (k_centroid_disp), searched in full (k_stencil_movers) and stay movers
+// until the next full search of all cells; only a list that overflows condemns the refresh as a whole (*ok = 0).
+struct Movers { int *list; int *count; int cap; };
+__global__ void k_centroid_disp(const float4 *__restrict__ centroid, const float4 *__restrict__ cen_ref, int n, int *__restrict__ ok, Movers mv) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (centroid_settled(centroid[i], cen_ref[i])) return;
+    const int slot = atomicAdd(mv.count, 1);
+    if (slot < mv.cap) mv.list[slot] = i; else atomicExch(ok, 0);
+}
+
+// After the refresh: every mover (of any rank: all ranks hold all centroids) is searched in full; the movers of this rank's cells
+// get their exact stencil row from it.  The relation is symmetric (the same squared distance on both sides), so every cell c2 of this
+// rank in a mover's stencil must have tested the mover in its refresh: it has if the mover is in its wide row -- or c2 is a mover
+// itself and searches in full.  If neither holds (the mover came from beyond 9 + kWideMargin: a few cells per rebuild on the RBC) c2
+// goes on a second list, `patch`, and a second launch of this kernel (VERIFY = false) searches those in full as well.  Only lists
+// that overflow raise *ok = 0, and the full search of all cells, which stands by behind that flag, runs.
+template <bool VERIFY>
+__global__ void __launch_bounds__(kStencilWarps * 32) k_stencil_movers(const float4 *__restrict__ centroid, const float4 *__restrict__ cen_ref, int c_beg, int c_end, GridDev g,
+                                                                        int *__restrict__ stencil, int *__restrict__ stencil_cnt, int *__restrict__ flags, HaloOut halo,
+                                                                        const int *__restrict__ wide_rows, const int *__restrict__ wide_cnt, Movers mv, Movers patch,
+                                                                        int *__restrict__ ok, unsigned long long *__restrict__ counters) {
+    if (*ok == 0) return;
+    __shared__ int s_key[kStencilWarps][kStencilStride];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n = min(*mv.count, mv.cap);
+    if (blockIdx.x == 0 && threadIdx.x == 0) counters[7] += (unsigned long long)n;      // statistics: cells searched in full (low 40 bits)
+    for (int k = blockIdx.x * kStencilWarps + w; k < n; k += gridDim.x * kStencilWarps) {
+        const int m = mv.list[k];
+        int count = stencil_search(centroid[m], g, 81.0f, s_key[w], lane);
+        if (count > kStencilStride) { if (lane == 0) atomicExch(&flags[0], m + 1); count = kStencilStride; }
+        __syncwarp();
+        if (m >= c_beg && m < c_end) stencil_emit(s_key[w], count, m, lane, stencil, stencil_cnt, flags, halo, WideOut{nullptr, nullptr, nullptr});
+        if (VERIFY) {
+            for (int e = lane; e < count; e += 32) {
+                const int c2 = s_key[w][e] & 0x0fffffff;
+                if (c2 == m || c2 < c_beg || c2 >= c_end) continue;
+                const int *row = wide_rows + (size_t)c2 * kStencilStride;      // ascending ids
+                const int len = min(wide_cnt[c2], kStencilStride);
+                int lo = 0, hi = len;
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if (row[mid] < m) lo = mid + 1; else hi = mid; }
+                if (!(lo < len && row[lo] == m) && centroid_settled(centroid[c2], cen_ref[c2])) {
+                    const int slot = atomicAdd(patch.count, 1);
+                    if (slot < patch.cap) patch.list[slot] = c2; else atomicExch(ok, 0);
+                }
+            }
+        }
+        __syncwarp();
+    }
 }
 
 // the refresh: the recorded neighbours of every cell re-classified with the exact squared distances.  `gate`: run only if *gate != 0.
