@@ -157,6 +157,7 @@ struct orbc_ctx {
     double *d_acc = nullptr;                              // 8 doubles: reductions
     unsigned long long *d_counters = nullptr;             // 8 counters
     int *d_flags = nullptr;                               // 4 ints: device-side error flags
+    int *d_check = nullptr, *h_check = nullptr;           // 8 ints: what the upload checks found (k_check_ids, k_check_bonds), and the pinned mirror
     float *d_nh = nullptr;                                // zeta, Q on the device for orbc_run_nh
     double *h_acc = nullptr; int *h_flags = nullptr; unsigned long long *h_counters = nullptr; float *h_nh = nullptr;  // pinned mirrors
     float *noise[2] = {nullptr, nullptr}; size_t noise_cap[2] = {0, 0};

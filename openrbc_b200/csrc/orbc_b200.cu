@@ -581,7 +581,7 @@ int preload_kernels() {
 #define ORBC_PRELOAD(k) ORBC_CUDA(cudaFuncGetAttributes(&fa, (const void *)(k)))
     ORBC_PRELOAD(k_assign_nearest); ORBC_PRELOAD(k_bin_count); ORBC_PRELOAD(k_bin_fill); ORBC_PRELOAD(k_bond_mask); ORBC_PRELOAD(k_bonded);
     ORBC_PRELOAD(k_bounce_back); ORBC_PRELOAD(k_build_tag2idx); ORBC_PRELOAD(k_cell_bounds); ORBC_PRELOAD(k_cell_scatter); ORBC_PRELOAD(k_cell_totals);
-    ORBC_PRELOAD(k_centroid_update); ORBC_PRELOAD(k_clear_force); ORBC_PRELOAD(k_compact); ORBC_PRELOAD(k_count_strays); ORBC_PRELOAD(k_cv_apply); ORBC_PRELOAD(k_cv_center); ORBC_PRELOAD(k_cv_share); ORBC_PRELOAD(k_sum_partials); ORBC_PRELOAD(k_opt_fused); ORBC_PRELOAD(k_frame_pack);
+    ORBC_PRELOAD(k_centroid_update); ORBC_PRELOAD(k_check_ids); ORBC_PRELOAD(k_check_bonds); ORBC_PRELOAD(k_clear_force); ORBC_PRELOAD(k_compact); ORBC_PRELOAD(k_count_strays); ORBC_PRELOAD(k_cv_apply); ORBC_PRELOAD(k_cv_center); ORBC_PRELOAD(k_cv_share); ORBC_PRELOAD(k_sum_partials); ORBC_PRELOAD(k_opt_fused); ORBC_PRELOAD(k_frame_pack);
     ORBC_PRELOAD(k_cv_normal_volume); ORBC_PRELOAD(k_fill_cellid); ORBC_PRELOAD(k_fill_int); ORBC_PRELOAD(k_halo_push); ORBC_PRELOAD(k_kinetic);
     ORBC_PRELOAD(k_mg_barrier); ORBC_PRELOAD(k_morton_keys); ORBC_PRELOAD(k_morton_keys_only); ORBC_PRELOAD(k_nh_final); ORBC_PRELOAD(k_nh_final_fused);
     ORBC_PRELOAD(k_nh_initial_fused); ORBC_PRELOAD(k_nh_zeta_update); ORBC_PRELOAD(k_share_ke); ORBC_PRELOAD(k_sum_ke); ORBC_PRELOAD(k_noise); ORBC_PRELOAD(k_opt_move); ORBC_PRELOAD(k_pack4);
@@ -705,14 +705,14 @@ int orbc_create(orbc_ctx **out, int device) {
     ORBC_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
     for (auto &e : c->ev) ORBC_CUDA(cudaEventCreate(&e));
-    ORBC_TRY(dev_alloc(&c->d_acc, 8)); ORBC_TRY(dev_alloc(&c->d_counters, 8)); ORBC_TRY(dev_alloc(&c->d_flags, 4)); ORBC_TRY(dev_alloc(&c->d_nh, 2));
+    ORBC_TRY(dev_alloc(&c->d_acc, 8)); ORBC_TRY(dev_alloc(&c->d_counters, 8)); ORBC_TRY(dev_alloc(&c->d_flags, 4)); ORBC_TRY(dev_alloc(&c->d_check, 8)); ORBC_TRY(dev_alloc(&c->d_nh, 2));
     ORBC_TRY(dev_alloc(&c->d_range, 4)); ORBC_CUDA(cudaMemset(c->d_range, 0, 4 * sizeof(int)));
     ORBC_TRY(dev_alloc(&c->tile_overflow, 1)); ORBC_CUDA(cudaMemset(c->tile_overflow, 0, sizeof(int)));
     // the tile kernel wants the whole shared-memory carve-out: five blocks of four 11 KB warp tiles per SM
     ORBC_CUDA(cudaFuncSetAttribute((const void *)k_pair_ll_t, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     ORBC_CUDA(cudaMemset(c->d_acc, 0, 8 * sizeof(double))); ORBC_CUDA(cudaMemset(c->d_counters, 0, 8 * sizeof(unsigned long long)));
     ORBC_CUDA(cudaMemset(c->d_flags, 0, 4 * sizeof(int))); ORBC_CUDA(cudaMemset(c->d_nh, 0, 2 * sizeof(float)));
-    ORBC_CUDA(cudaMallocHost((void **)&c->h_acc, 8 * sizeof(double))); ORBC_CUDA(cudaMallocHost((void **)&c->h_flags, 4 * sizeof(int)));
+    ORBC_CUDA(cudaMallocHost((void **)&c->h_acc, 8 * sizeof(double))); ORBC_CUDA(cudaMallocHost((void **)&c->h_flags, 4 * sizeof(int))); ORBC_CUDA(cudaMallocHost((void **)&c->h_check, 8 * sizeof(int)));
     ORBC_CUDA(cudaMallocHost((void **)&c->h_counters, 8 * sizeof(unsigned long long))); ORBC_CUDA(cudaMallocHost((void **)&c->h_nh, 2 * sizeof(float)));
     orbc_forcefield ff; orbc_forcefield_canonical(&ff);
     *out = c;
@@ -727,13 +727,13 @@ void orbc_destroy(orbc_ctx *c) { if (c) cudaSetDevice(c->device);
     dev_free(c->centroid); dev_free(c->centroid_tmp); dev_free(c->keys); dev_free(c->keys_tmp); dev_free(c->perm); dev_free(c->perm_tmp); dev_free(c->inv);
     dev_free(c->grid.bin_start); dev_free(c->grid.bin_items); dev_free(c->grid.bin_of); dev_free(c->grid.bin_slot); dev_free(c->grid.sorted);
     dev_free(c->stencil); dev_free(c->stencil_cnt); dev_free(c->wide); dev_free(c->wide_cnt); dev_free(c->cen_ref); dev_free(c->wide_ok); dev_free(c->movers); dev_free(c->cell_normal); dev_free(c->lbound); dev_free(c->pbound); dev_free(c->porder); dev_free(c->lruns); dev_free(c->lrun_cnt); dev_free(c->bonds); dev_free(c->tag2idx);
-    dev_free(c->scan_tmp); dev_free(c->radix_hist); dev_free(c->stage); dev_free(c->d_acc); dev_free(c->d_counters); dev_free(c->d_flags); dev_free(c->d_nh);
+    dev_free(c->scan_tmp); dev_free(c->radix_hist); dev_free(c->stage); dev_free(c->d_acc); dev_free(c->d_counters); dev_free(c->d_flags); dev_free(c->d_check); dev_free(c->d_nh);
     dev_free(c->noise[0]); dev_free(c->noise[1]); dev_free(c->d_range); dev_free(c->tile_overflow); dev_free(c->xn);
     { NlState *st = (NlState *)c->nl_state; dev_free(st); } dev_free(c->ll_list); dev_free(c->ll_cnt); dev_free(c->pl_list); dev_free(c->pl_cnt); dev_free(c->pp_list); dev_free(c->pp_cnt);
     for (void *m : c->mg.opened) cudaIpcCloseMemHandle(m);
     dev_free(c->mg.my_bonds); dev_free(c->mg.keep); dev_free(c->mg.ke_all); dev_free(c->mg.vol_all); dev_free(c->mg.cv_ptype); dev_free(c->mg.flags); dev_free(c->mg.dest_mask); dev_free(c->mg.pmask); dev_free(c->mg.need);
     for (int s = 0; s < 2; ++s) { dev_free(c->mg.cnt_all[s]); dev_free(c->mg.off_me[s]); dev_free(c->mg.cnt_prev[s]); }
-    if (c->h_acc) cudaFreeHost(c->h_acc); if (c->h_flags) cudaFreeHost(c->h_flags); if (c->h_counters) cudaFreeHost(c->h_counters); if (c->h_nh) cudaFreeHost(c->h_nh);
+    if (c->h_acc) cudaFreeHost(c->h_acc); if (c->h_flags) cudaFreeHost(c->h_flags); if (c->h_check) cudaFreeHost(c->h_check); if (c->h_counters) cudaFreeHost(c->h_counters); if (c->h_nh) cudaFreeHost(c->h_nh);
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
     for (auto &v : c->prof_ev) for (auto &e : v) cudaEventDestroy(e);
     for (auto &e : c->kprof_ev) cudaEventDestroy(e);
@@ -839,19 +839,23 @@ static int upload_rows(orbc_ctx *c, int sp, size_t n, size_t first, size_t count
     ORBC_LAUNCH(c, k_zero4, nb, kBlock, 0, S.f, n, (const int *)nullptr);
     ORBC_LAUNCH(c, k_zero4, nb, kBlock, 0, S.t, n, (const int *)nullptr);
     ORBC_LAUNCH(c, k_fill_int, nb, kBlock, 0, S.C(), n, -1);
-    ORBC_CUDA(cudaStreamSynchronize(c->stream));   // host arrays are borrowed only for the duration of the call
+    // type and tag are checked where they now are (k_check_ids); the call returns only when the host arrays are free again
     if (sp == ORBC_PROTEIN) {
         c->porder_valid = false;
-        c->type_mask = type ? 0u : 1u;
-        unsigned bad = 0, mask = 0;
-        if (type) for (size_t i = 0; i < n; ++i) { const unsigned t = (unsigned)type[i]; bad |= t >= (unsigned)kNType; mask |= 1u << (t & 31u); }
-        if (bad) for (size_t i = 0; i < n; ++i) if (type[i] < 0 || type[i] >= kNType) return fail(ORBC_ERR_ARG, "protein %zu has type %d outside [0,%d)", i, type[i], kNType);
-        c->type_mask |= mask;
+        ORBC_CUDA(cudaMemsetAsync(c->d_check, 0, 4 * sizeof(int), c->stream));
+        ORBC_LAUNCH(c, k_check_ids, nb, kBlock, 0, (const int *)(type ? w_type : nullptr), (const int *)(tag ? w_tag : nullptr), n, kNType, c->d_check);
+        ORBC_CUDA(cudaMemcpyAsync(c->h_check, c->d_check, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    }
+    ORBC_CUDA(cudaStreamSynchronize(c->stream));
+    int mx = 0;
+    if (sp == ORBC_PROTEIN) {
+        const int *h = c->h_check;
+        if (h[0]) { const size_t i = n - (size_t)h[0]; return fail(ORBC_ERR_ARG, "protein %zu has type %d outside [0,%d)", i, type[i], kNType); }
+        c->type_mask = type ? (unsigned)h[1] : 1u;
+        if (h[2]) return fail(ORBC_ERR_ARG, "negative protein tag");
+        mx = h[3];
     }
     if (sp == ORBC_PROTEIN && tag) {
-        int mx = 0, mn = 0;
-        for (size_t i = 0; i < n; ++i) { mn = std::min(mn, tag[i]); mx = std::max(mx, tag[i]); }
-        if (mn < 0) return fail(ORBC_ERR_ARG, "negative protein tag");
         if (c->tag2idx_size < (size_t)mx + 1) { ORBC_TRY(dev_alloc(&c->tag2idx, (size_t)mx + 1)); c->tag2idx_size = (size_t)mx + 1; }
         ORBC_CUDA(cudaMemsetAsync(c->tag2idx, 0xff, sizeof(int) * c->tag2idx_size, c->stream));
         ORBC_TRY(build_tag2idx(c));
@@ -880,23 +884,19 @@ int orbc_upload_range(orbc_ctx *c, int sp, size_t n, size_t first, size_t count,
 
 int orbc_upload_bonds(orbc_ctx *c, size_t n_bonds, const int *tij) { if (c) cudaSetDevice(c->device);
     if (!c || (n_bonds && !tij)) return fail(ORBC_ERR_ARG, "orbc_upload_bonds: bad argument");
-    // validation in two passes: a branch-free min / max sweep (vectorised by the compiler: the sweep sits inside the timed upload of
-    // every job), and the search for the offending bond only when the sweep found one
-    int tmin = 0, tmax = 0, gmin = 0, gmax = 0;
-    for (size_t b = 0; b < n_bonds; ++b) {
-        const int t = tij[3 * b], i = tij[3 * b + 1], j = tij[3 * b + 2];
-        tmin = std::min(tmin, t); tmax = std::max(tmax, t);
-        gmin = std::min(gmin, std::min(i, j)); gmax = std::max(gmax, std::max(i, j));
-    }
-    if (tmin < 0 || tmax >= 4 || gmin < 0 || (size_t)gmax >= c->tag2idx_size)
-        for (size_t b = 0; b < n_bonds; ++b) {
-            if (tij[3 * b] < 0 || tij[3 * b] >= 4) return fail(ORBC_ERR_ARG, "bond %zu has type %d outside [0,4)", b, tij[3 * b]);
-            if ((size_t)tij[3 * b + 1] >= c->tag2idx_size || (size_t)tij[3 * b + 2] >= c->tag2idx_size || tij[3 * b + 1] < 0 || tij[3 * b + 2] < 0)
-                return fail(ORBC_ERR_ARG, "bond %zu refers to a tag that no uploaded protein carries (upload proteins first)", b);
-        }
     if (!c->bonds || c->bonds_cap < 3 * n_bonds) { ORBC_TRY(dev_alloc(&c->bonds, 3 * n_bonds)); c->bonds_cap = 3 * n_bonds; }   // a re-upload keeps the allocation
+    c->n_bonds = 0;                                              // (until the new list has been checked)
     if (n_bonds) ORBC_CUDA(cudaMemcpyAsync(c->bonds, tij, sizeof(int) * 3 * n_bonds, cudaMemcpyHostToDevice, c->stream));
+    // checked on the device (k_check_bonds): the host's sweep over the 3 n integers cost ten times the copy
+    ORBC_CUDA(cudaMemsetAsync(c->d_check + 4, 0, sizeof(int), c->stream));
+    if (n_bonds) ORBC_LAUNCH(c, k_check_bonds, blocks_for(n_bonds, kBlock), kBlock, 0, c->bonds, n_bonds, c->tag2idx_size, c->d_check);
+    ORBC_CUDA(cudaMemcpyAsync(c->h_check + 4, c->d_check + 4, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     ORBC_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->h_check[4]) {
+        const size_t b = n_bonds - (size_t)c->h_check[4];
+        if (tij[3 * b] < 0 || tij[3 * b] >= 4) return fail(ORBC_ERR_ARG, "bond %zu has type %d outside [0,4)", b, tij[3 * b]);
+        return fail(ORBC_ERR_ARG, "bond %zu refers to a tag that no uploaded protein carries (upload proteins first)", b);
+    }
     c->n_bonds = n_bonds;
     return ORBC_OK;
 }

@@ -536,6 +536,37 @@ __global__ void k_bbox(const float4 *__restrict__ x, size_t n, int *__restrict__
     }
 }
 
+// The checks of an upload, on the device (the ids are there anyway; on the host the sweeps cost as much as the copy).  All results
+// are maxima over zero-initialised words: chk[0] = n - (first slot with a type outside [0, n_type)), chk[1] = mask of the types present,
+// chk[2] = the largest -tag, chk[3] = the largest tag.
+__global__ void k_check_ids(const int *__restrict__ type, const int *__restrict__ tag, size_t n, int n_type, int *__restrict__ chk) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int bad = 0, neg = 0, top = 0; unsigned mask = 0;
+    if (i < n) {
+        if (type) { const unsigned t = (unsigned)type[i]; if (t >= (unsigned)n_type) bad = (int)(n - i); mask = 1u << (t & 31u); }
+        if (tag) { const int g = tag[i]; neg = g < 0 ? (g == (int)0x80000000 ? 0x7fffffff : -g) : 0; top = max(g, 0); }
+    }
+    bad = __reduce_max_sync(0xffffffffu, bad); mask = __reduce_or_sync(0xffffffffu, mask);
+    neg = __reduce_max_sync(0xffffffffu, neg); top = __reduce_max_sync(0xffffffffu, top);
+    if ((threadIdx.x & 31) == 0) {
+        if (bad) atomicMax(&chk[0], bad);
+        if (mask) atomicOr((unsigned *)&chk[1], mask);
+        if (neg) atomicMax(&chk[2], neg);
+        if (top) atomicMax(&chk[3], top);
+    }
+}
+// chk[4] = n - (first bond with a type outside [0, 4) or a tag outside the tag -> index map)
+__global__ void k_check_bonds(const int *__restrict__ tij, size_t n, size_t map_size, int *__restrict__ chk) {
+    const size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int bad = 0;
+    if (b < n) {
+        const unsigned t = (unsigned)tij[3 * b], i = (unsigned)tij[3 * b + 1], j = (unsigned)tij[3 * b + 2];
+        if (t >= 4u || (size_t)i >= map_size || (size_t)j >= map_size) bad = (int)(n - b);
+    }
+    bad = __reduce_max_sync(0xffffffffu, bad);
+    if ((threadIdx.x & 31) == 0 && bad) atomicMax(&chk[4], bad);
+}
+
 // container.h:39-58
 __global__ void k_build_tag2idx(const float4 *__restrict__ nn, size_t n, int *__restrict__ map, size_t map_size, int *__restrict__ flags) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

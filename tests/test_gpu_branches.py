@@ -186,3 +186,23 @@ def test_delete_lipid_against_the_reference():
     sim.compute_pairwise_fused(); sim.compute_bonded()
     assert np.isfinite(sim.get(0, "f")).all() and np.isfinite(sim.get(1, "f")).all()
     sim.close()
+
+
+def test_upload_rejects_bad_ids():
+    """The ids of an upload are checked on the device (k_check_ids, k_check_bonds): same refusals, same messages as a host sweep."""
+    from openrbc_b200 import Simulation, engine
+    g = dict(np.load(os.path.join(GOLDEN, "branches_vesicle_ico0.npz")))
+    st = {k[3:]: v for k, v in g.items() if k.startswith("in_")}
+    assert len(st["px"]) > 8 and len(st["bonds"]) > 4
+    for field, slot, value, text in (("ptype", 5, 9, "protein 5 has type 9"), ("ptype", 3, -1, "protein 3 has type -1"), ("ptag", 2, -7, "negative protein tag")):
+        bad = dict(st); bad[field] = np.array(st[field], np.int32); bad[field][slot] = value
+        with pytest.raises(engine.OrbcError, match=text):
+            Simulation(bad, kBT=0.0)
+    for col, value, text in ((0, 4, "bond 2 has type 4"), (1, 10 ** 8, "bond 2 refers to a tag"), (2, -1, "bond 2 refers to a tag")):
+        bad = dict(st); bad["bonds"] = np.array(st["bonds"], np.int32).reshape(-1, 3).copy(); bad["bonds"][2, col] = value
+        with pytest.raises(engine.OrbcError, match=text):
+            Simulation(bad, kBT=0.0)
+    sim = Simulation(st, kBT=0.0)                # and the good state still loads
+    sim.rebuild(); sim.compute_pairwise_fused(); sim.compute_bonded()
+    assert np.isfinite(sim.get(1, "f")).all()
+    sim.close()
