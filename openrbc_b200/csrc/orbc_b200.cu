@@ -378,17 +378,19 @@ int launch_pairwise(orbc_ctx *c, bool accumulate = true) {
                 ORBC_LAUNCH(c, (k_pair_ll_r<20, 4, false>), blocks_for(nl_count, kLLBlock), kLLBlock, 0, a, kc, c->lruns, c->lrun_cnt, (const int *)nullptr, 0, LLList{}, 0.f, (unsigned *)nullptr);
             } else {
                 // hit lists: the device decides (k_nl_gate) whether this evaluation walks the lists, searches and records them, or just
-                // searches; the three kernels are launched over a grid that fills the GPU once (their blocks draw 64-lipid groups from a
-                // ticket counter), two of them return at once
+                // searches; the candidates are launched over a grid that fills the GPU once (their blocks draw 64-lipid groups from a
+                // ticket counter), all but one return at once
                 const LLList ll = {c->ll_list, c->ll_cnt, c->nl_cap_ll, nls};
                 const unsigned groups = blocks_for(nl_count, kLLBlock);
                 const unsigned g16 = std::min(groups, 148u * 16u), g20 = std::min(groups, 148u * 20u);   // (blocks per SM: the kernels' launch bounds)
-                if (!mg && c->ll_xn) {
-                    if (c->xn_cap < L.cap) { ORBC_TRY(dev_alloc(&c->xn, L.cap * 8)); c->xn_cap = L.cap; }
-                    ORBC_LAUNCH(c, k_pack_xn, blocks_for(L.n, kBlock), kBlock, 0, L.X(), L.N(), L.n, (XN *)c->xn);
-                    ORBC_LAUNCH(c, (k_pair_ll_list<16, true>), g16, kLLBlock, 0, a, kc, &nls->need, 0, ll, (const XN *)c->xn, nls->work + 0);
-                } else ORBC_LAUNCH(c, (k_pair_ll_list<16, false>), g16, kLLBlock, 0, a, kc, &nls->need, 0, ll, (const XN *)nullptr, nls->work + 0);
-                ORBC_LAUNCH(c, (k_pair_ll_r<16, 4, true>), g16, kLLBlock, 0, a, kc, c->lruns, c->lrun_cnt, &nls->need, 1, ll, c->nl_skin, nls->work + 1);
+                // (what the host knows: after a change of the partition the gate never orders a walk, and otherwise never a recording)
+                if (!host_build) {
+                    if (!mg && c->ll_xn) {
+                        if (c->xn_cap < L.cap) { ORBC_TRY(dev_alloc(&c->xn, L.cap * 8)); c->xn_cap = L.cap; }
+                        ORBC_LAUNCH(c, k_pack_xn, blocks_for(L.n, kBlock), kBlock, 0, L.X(), L.N(), L.n, (XN *)c->xn);
+                        ORBC_LAUNCH(c, (k_pair_ll_list<16, true>), g16, kLLBlock, 0, a, kc, &nls->need, 0, ll, (const XN *)c->xn, nls->work + 0);
+                    } else ORBC_LAUNCH(c, (k_pair_ll_list<16, false>), g16, kLLBlock, 0, a, kc, &nls->need, 0, ll, (const XN *)nullptr, nls->work + 0);
+                } else ORBC_LAUNCH(c, (k_pair_ll_r<16, 4, true>), g16, kLLBlock, 0, a, kc, c->lruns, c->lrun_cnt, &nls->need, 1, ll, c->nl_skin, nls->work + 1);
                 ORBC_LAUNCH(c, (k_pair_ll_r<20, 4, false>), g20, kLLBlock, 0, a, kc, c->lruns, c->lrun_cnt, &nls->need, 2, LLList{}, 0.f, nls->work + 2);
             }
         }
@@ -404,8 +406,8 @@ int launch_pairwise(orbc_ctx *c, bool accumulate = true) {
         if (nl) {
             const unsigned pieces = blocks_for(np * lanes, kPBlock);
 #define ORBC_PROT3(LPP) do { \
-                ORBC_LAUNCH(c, k_pair_prot_list<LPP>, pieces, kPBlock, 0, a, c->porder, &nls->need, 0, pls); \
-                ORBC_LAUNCH(c, (k_pair_prot<LPP, true>), pieces, kPBlock, 0, a, c->lbound, c->pbound, ct, c->porder, &nls->need, 1, pls, c->nl_skin); \
+                if (!host_build) ORBC_LAUNCH(c, k_pair_prot_list<LPP>, pieces, kPBlock, 0, a, c->porder, &nls->need, 0, pls); \
+                else ORBC_LAUNCH(c, (k_pair_prot<LPP, true>), pieces, kPBlock, 0, a, c->lbound, c->pbound, ct, c->porder, &nls->need, 1, pls, c->nl_skin); \
                 ORBC_LAUNCH(c, (k_pair_prot<LPP, false>), pieces, kPBlock, 0, a, c->lbound, c->pbound, ct, c->porder, &nls->need, 2, pls, 0.f); } while (0)
             if (lanes == 4) ORBC_PROT3(4); else if (lanes == 2) ORBC_PROT3(2); else ORBC_PROT3(1);
 #undef ORBC_PROT3
