@@ -259,12 +259,18 @@ def hbm_peak():
     return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(kernel):
-    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/ncu_traffic.json,
-    written by hand from profiles/*_pair_ncu.txt: dram__bytes_read.sum + dram__bytes_write.sum); None when absent."""
+def ncu_traffic(mix):
+    """DRAM bytes per launch of the dominant kernel -- the lipid pair evaluation, which is one of three kernels (search, record,
+    walk) by the gate's decision -- from the committed `ncu --set full` captures (profiles/ncu_traffic.json, written by hand from
+    profiles/r02_*_ncu.txt: dram__bytes_read.sum + dram__bytes_write.sum of one launch each), weighted by how often each ran in
+    the timed region (`mix` = {"search": n, "record": n, "walk": n}); None when absent."""
     try:
-        d = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[kernel]
-        return float(d["dram_bytes_read"]) + float(d["dram_bytes_write"]), d.get("source")
+        d = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        tot = sum(mix.values())
+        if not tot:
+            return None, None
+        t = sum(n * (float(d[k]["dram_bytes_read"]) + float(d[k]["dram_bytes_write"])) for k, n in mix.items() if n) / tot
+        return t, "; ".join("%s x%d: %s" % (k, n, d[k].get("source")) for k, n in mix.items() if n)
     except Exception:  # noqa: BLE001
         return None, None
 
@@ -353,6 +359,7 @@ def run_ours(args):
     sim = make_sim(st)
     run_chunked(sim, args.warmup)
     sim.synchronize()
+    nl_before = sim.dump("nl_stats").tolist()
     sim.profile_enable(True)
     l0 = sim.launch_count()
     barrier()
@@ -368,6 +375,7 @@ def run_ours(args):
     sim.profile_enable(False)
     n_now = sim.size(0) + sim.size(1)
     nl_stats = sim.dump("nl_stats").tolist()
+    nl_timed = [int(a) - int(b) for a, b in zip(nl_stats, nl_before)]      # [recorded, walked, -, searched] inside the timed region
     if world > 1:
         t = torch.tensor([ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -484,6 +492,8 @@ def run_ours(args):
     pl_ms, pl_cnt = prof["pair_lipid"]
     n_l = len(st["lx"]) / world          # lipids one launch of the kernel covers (this rank's share on N>1)
     achieved = (B_ALG_PAIR * n_l / (pl_ms / pl_cnt * 1e-3) / 1e9) if pl_cnt else None
+    # which of the three lipid kernels ran in the timed region (hit-list statistics of the timed steps; without lists: all searches)
+    ll_mix = {"search": nl_timed[3] if (nl_timed[0] + nl_timed[1] + nl_timed[3]) else int(pl_cnt), "record": nl_timed[0], "walk": nl_timed[1]}
     shares = {k: round(v[0] / ms, 4) for k, v in prof.items()}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -494,11 +504,12 @@ def run_ours(args):
                                                                 "by peer stores over NVLink, epoch-flag barriers"),
                    "integrator": "verlet_langevin kBT=0.22 dt=0.01, rebuild every 2 steps, Morton sort every 24, cleanup every 60" + (", constrain_volume(3.15, 0.05) every step" if args.cv else ""),
                    "particles_at_end": n_now, "temperature_at_end": temperature, "options": args.opt,
-                   "hit_lists": {"evaluations_that_recorded": nl_stats[0], "evaluations_that_walked": nl_stats[1], "evaluations_that_searched": nl_stats[3], "overflow": nl_stats[2]},
+                   "hit_lists": {"evaluations_that_recorded": nl_timed[0], "evaluations_that_walked": nl_timed[1], "evaluations_that_searched": nl_timed[3], "overflow": nl_stats[2], "of": "the timed steps"},
                    "hbm_roofline_frac_step": value / world * B_ALG_STEP / 1e9 / peak, "device_time_shares": shares},
-        "roofline": {"bound": "hbm", "kernel": "k_pair_lipid (lipid side of compute_pairwise_fused)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": (achieved / peak) if achieved else None, "traffic": (ncu_traffic("k_pair_ll")[0] if world == 1 else None),
-                     "traffic_source": ncu_traffic("k_pair_ll")[1], "peak_source": peak_src,
+        "roofline": {"bound": "hbm", "kernel": "lipid side of compute_pairwise_fused: k_pair_ll_r<.,4,false> (search), k_pair_ll_r<.,4,true> (search + record the hit lists) or "
+                               "k_pair_ll_list (walk them), by the device's gate; mean over the launches of the timed region", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": (achieved / peak) if achieved else None, "traffic": (ncu_traffic(ll_mix)[0] if world == 1 else None),
+                     "traffic_source": ncu_traffic(ll_mix)[1], "launch_mix": ll_mix, "peak_source": peak_src,
                      "launch_ms": pl_ms / pl_cnt if pl_cnt else None, "launches_timed": pl_cnt,
                      "algorithmic_bytes_per_launch": B_ALG_PAIR * n_l,
                      "note": "pair forces are FP32-ALU bound (~1.6-3 kFLOP per 48 B), see DESIGN.md; HBM fraction reported as the contract asks"},

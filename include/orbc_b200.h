@@ -99,7 +99,8 @@ ORBC_API int  orbc_set_stream(orbc_ctx *ctx, void *cuda_stream);
  *                 cutoff + skin, and the evaluations up to the next rebuild walk those lists (exact re-test of every entry; a bound on
  *                 the displacements guards the skin: same hits, same forces).  The device decides at every evaluation whether it
  *                 walks, records or just searches (a recording that would not be walked is not made).  0 = every evaluation
- *                 searches the stencils.  On a decomposed context the ranks exchange their displacement bounds and decide alike.
+ *                 searches the stencils.  On a decomposed context the ranks exchange their displacement bounds and decide alike;
+ *                 there the default means "up to two ranks" (measured: the lists lose with 8 ranks), 2 = on for every world size.
  *   "nl_skin"     the skin of those lists, default 0.1
  *   "stencil_refresh"  1 (default) = rebuilds that keep the cell numbering re-classify the recorded r < 9 + 1 neighbours of every cell
  *                 instead of searching the centroid grid (cells whose centroid jumped are searched in full; same stencils); 0 = always search

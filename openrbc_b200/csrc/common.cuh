@@ -26,6 +26,7 @@ inline int fail(int code, const char *fmt, ...) {
 constexpr int kNType = 6;              // forcefield_canonical.h:37
 constexpr int kStencilStride = ORBC_STENCIL_STRIDE;
 constexpr int kMoversCap = 4096;
+constexpr int kNlAutoWorld = 2;      // hit lists on a decomposed run: automatic up to this many ranks (orbc_b200.cu: nl_active)
 constexpr float kBin = 10.0f;          // centroid grid bin = largest centroid stencil radius (9, compute_pairwise_fused.h:183) + the margin of the wide stencils (rebuild.cuh)
 constexpr int kMaxWorld = 8;           // ranks of one spatially decomposed run (one B200 box)
 
@@ -168,7 +169,8 @@ struct orbc_ctx {
     int pair_impl = 2;
     int ll_variant = 1;                            // 1: thread-per-lipid run-list kernel k_pair_ll_r + hit lists (default); 0: warp-per-cell tile kernel k_pair_ll_t
     // hit lists with a skin (pair_queue.cuh): recorded by the force evaluation after a rebuild, walked until the next one
-    bool nl_on = true, nl_valid = false;           // option "nl_reuse"; lists match the current partition and were built (host's view)
+    int nl_on = 1;                                 // option "nl_reuse": 0 off, 1 automatic, 2 on
+    bool nl_valid = false;                         // lists match the current partition and were built (host's view)
     float nl_skin = 0.1f;                          // option "nl_skin"
     bool ll_xn = false;                            // list walker gathers interleaved (x, n) records (k_pack_xn); measured: no gain (243 vs 238 us), off
     float *xn = nullptr; size_t xn_cap = 0;        // those records, 32 B per lipid

@@ -232,7 +232,13 @@ float ff_rep(float cut, float req, float eps) { return eps / pow_chain(cut - req
 float ff_att(float cut, float req, float eps) { return (float)(-2.0 * eps / pow_chain(cut - req, 4)); }
 
 // hit lists go with the default kernels; on a decomposed run the ranks exchange their displacement bounds (k_nl_share)
-bool nl_active(const orbc_ctx *c) { return c->nl_on && (!mg_active(c) || c->mg.connected) && c->pair_impl == 2 && c->ll_variant == 1; }
+bool nl_active(const orbc_ctx *c) {
+    if (!c->nl_on || c->pair_impl != 2 || c->ll_variant != 1) return false;
+    if (!mg_active(c)) return true;
+    // decomposed: measured on the RBC (60 steps), the lists gain with 2 ranks and lose 3.5 % with 8 (a rank's share of the work shrinks,
+    // the gate, the exchange of the bounds and the launches that return at once do not): automatic = up to kNlAutoWorld ranks
+    return c->mg.connected && (c->nl_on == 2 || c->mg.world <= kNlAutoWorld);
+}
 int nl_share(orbc_ctx *c);
 int prot_lanes(const orbc_ctx *c, size_t np) { return c->prot_lanes ? c->prot_lanes : (np <= 400000 ? 4 : 1); }
 int nl_ensure(orbc_ctx *c) {
@@ -758,7 +764,12 @@ int orbc_set_option(orbc_ctx *c, const char *name, double value) { if (c) cudaSe
         c->ll_variant = (int)value; c->nl_valid = false; return ORBC_OK;
     }
     if (!strcmp(name, "ll_xn")) { c->ll_xn = value != 0; return ORBC_OK; }   // list walker: partners gathered as interleaved 32-byte (x, n) records (default off: measured no gain)
-    if (!strcmp(name, "nl_reuse")) { c->nl_on = value != 0; c->nl_valid = false; return ORBC_OK; }   // hit lists between rebuilds on / off
+    if (!strcmp(name, "nl_reuse")) {                             // hit lists between rebuilds: 0 off, 1 automatic (default), 2 on
+        if (value != 0 && value != 1 && value != 2) return fail(ORBC_ERR_ARG, "nl_reuse must be 0, 1 or 2");
+        c->nl_on = (int)value; c->nl_valid = false;
+        if (mg_active(c) && c->mg.connected && nl_active(c)) ORBC_TRY(nl_ensure(c));   // (not at the first launch, while peers may wait in a barrier)
+        return ORBC_OK;
+    }
     if (!strcmp(name, "nl_skin")) {
         if (!(value >= 0.0 && value <= 1.0)) return fail(ORBC_ERR_ARG, "nl_skin must be in [0, 1]");
         c->nl_skin = (float)value; c->nl_valid = false; return ORBC_OK;
@@ -1328,7 +1339,7 @@ int orbc_mg_export(orbc_ctx *c, void *blob_out, size_t bytes) { if (c) cudaSetDe
         ORBC_TRY(dev_alloc(&m.pmask, P.n + 4)); ORBC_CUDA(cudaMemsetAsync(m.pmask, 0, P.n + 4, c->stream));
         ORBC_TRY(dev_alloc(&m.need, nc)); ORBC_CUDA(cudaMemsetAsync(m.need, 0, sizeof(int) * nc, c->stream));
         ORBC_TRY(dev_alloc(&m.keep, L.n + 1));
-        if (c->nl_on) ORBC_TRY(nl_ensure(c));                    // the hit lists: allocated now, never while peers wait in a barrier
+        if (c->nl_on == 2 || (c->nl_on && w <= kNlAutoWorld)) ORBC_TRY(nl_ensure(c));   // the hit lists: allocated now, never while peers wait in a barrier
         // work list of the bonds with an owned atom (clipped and flagged at the capacity)
         m.my_bonds_cap = (int)std::min(c->n_bonds, c->n_bonds / w + c->n_bonds / (2 * (size_t)w) + (size_t)c->mg_own_slack);
         ORBC_TRY(dev_alloc(&m.my_bonds, (size_t)m.my_bonds_cap + 1));

@@ -114,7 +114,7 @@ def test_free_running_loop(name, world):
     from openrbc_b200 import Simulation
     st = load_state(name)
     one = Simulation(st, kBT=0.22)
-    sims = make_ranks(st, world, kBT=0.22)
+    sims = make_ranks(st, world, opts={"nl_reuse": 2}, kBT=0.22)      # hit lists on every world size (automatic: up to two ranks)
     for sim in [one] + sims:
         sim.nstep = 20
     one.run_langevin(8)

@@ -1,5 +1,5 @@
 """Minimal driver for ncu captures: load a state, advance a few steps, then N force evaluations.
-    python tools/pair_only.py [workload] [n] [pair_impl] [ll_variant]"""
+    python tools/pair_only.py [workload] [n] [pair_impl] [ll_variant] [debug_nl_mode: 1 every evaluation records the hit lists, 2 searches]"""
 import os
 import sys
 
@@ -16,6 +16,8 @@ if len(sys.argv) > 3:
 if len(sys.argv) > 4:
     sim.set_option("ll_variant", int(sys.argv[4]))
 sim.run_langevin(4)
+if len(sys.argv) > 5:
+    sim.set_option("debug_nl_mode", int(sys.argv[5]))
 for _ in range(n):
     sim.compute_pairwise_fused()
 sim.synchronize()
