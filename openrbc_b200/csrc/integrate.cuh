@@ -120,8 +120,8 @@ __global__ void k_bounce_back(IntegArgs a) {
 }
 
 // integrate_langevin.h:99-149 — one pass: torque -> omega -> director, noise, friction, kick, drift, clear f and t
-__global__ void __launch_bounds__(256) k_verlet_langevin(IntegArgs a) {
-    const size_t i = (size_t)a.range[0] + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void verlet_langevin_body(const unsigned bid, const IntegArgs &a) {
+    const size_t i = (size_t)a.range[0] + (size_t)bid * blockDim.x + threadIdx.x;
     float d2 = 0.f;
     if (i < (size_t)a.range[1]) {
         float4 x = a.x[i], v = a.v[i], n4 = a.nn[i], o = a.o[i];
@@ -153,6 +153,11 @@ __global__ void __launch_bounds__(256) k_verlet_langevin(IntegArgs a) {
         }
     }
     nl_track(a.disp, d2);
+}
+__global__ void __launch_bounds__(256) k_verlet_langevin(IntegArgs a) { verlet_langevin_body(blockIdx.x, a); }
+// both containers in one launch: blocks [0, blocks0) integrate a0's particles, the others a1's
+__global__ void __launch_bounds__(256) k_verlet_langevin2(IntegArgs a0, IntegArgs a1, unsigned blocks0) {
+    if (blockIdx.x < blocks0) verlet_langevin_body(blockIdx.x, a0); else verlet_langevin_body(blockIdx.x - blocks0, a1);
 }
 
 // integrate_nh.h:178-235 (operator()) — half kick with 1/(1 + dt zeta / 2), drift, bounce-back, KE, omega half kick, director, clear

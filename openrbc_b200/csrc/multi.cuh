@@ -56,37 +56,46 @@ __global__ void k_mg_barrier(BarrierArgs b) {
     }
 }
 
-// owned slot range of one species from the global cell_start (device side: the host never waits for it)
-__global__ void k_set_range(const int *__restrict__ cell_start, int cb, int ce, int *__restrict__ range2, int cap, int *__restrict__ flags) {
-    const int b = cell_start[cb], e = cell_start[ce];
-    range2[0] = b; range2[1] = e;
-    if (e - b > cap) atomicExch(flags + 3, -(e - b));
+// owned slot range of one or both containers from the global cell_start (device side: the host never waits for it)
+struct RangeArgs { const int *cell_start; int *range2; int cap; };
+__global__ void k_set_range(RangeArgs a0, RangeArgs a1, int count, int cb, int ce, int *__restrict__ flags) {
+    if ((int)threadIdx.x >= count) return;
+    const RangeArgs &a = threadIdx.x == 0 ? a0 : a1;
+    const int b = a.cell_start[cb], e = a.cell_start[ce];
+    a.range2[0] = b; a.range2[1] = e;
+    if (e - b > a.cap) atomicExch(flags + 3, -(e - b));
 }
 __global__ void k_set_range_const(int *__restrict__ range2, int b, int e) { range2[0] = b; range2[1] = e; }
 
 // arrival counts of this rank -> row `rank` of every peer's table.  A rank's particles only ever land in its own cells and
 // their neighbours, so the row is zero almost everywhere: only entries that are non-zero now or were non-zero at the last
 // exchange (prev, so the peers' copies get cleared) cross the link.
-struct CountRows { int *dst[kMaxWorld]; };
-__global__ void k_share_counts(const int *__restrict__ cnt_me, int *__restrict__ prev, int nc1, int rank, int world, CountRows rows) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+// (a0 for the blocks [0, blocks0), a1 for the others: both containers in one launch; the host passes the same set twice for one)
+struct ShareArgs { const int *cnt_me; int *prev; int *dst[kMaxWorld]; };
+__global__ void k_share_counts(ShareArgs a0, ShareArgs a1, unsigned blocks0, int nc1, int rank, int world) {
+    const bool first = blockIdx.x < blocks0;
+    const ShareArgs &a = first ? a0 : a1;
+    const int c = (int)((first ? blockIdx.x : blockIdx.x - blocks0) * blockDim.x + threadIdx.x);
     if (c >= nc1) return;
-    const int v = cnt_me[c];
-    if (v == 0 && prev[c] == 0) return;
-    prev[c] = v;
-    for (int r = 0; r < world; ++r) if (r != rank) rows.dst[r][(size_t)rank * nc1 + c] = v;
+    const int v = a.cnt_me[c];
+    if (v == 0 && a.prev[c] == 0) return;
+    a.prev[c] = v;
+    for (int r = 0; r < world; ++r) if (r != rank) a.dst[r][(size_t)rank * nc1 + c] = v;
 }
 // members of every cell over all ranks (-> global cell_start after the scan) and members that come from lower ranks
-__global__ void k_cell_totals(const int *__restrict__ cnt_all, int nc, int rank, int world, int *__restrict__ cell_start, int *__restrict__ off_me) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+struct TotalsArgs { const int *cnt_all; int *cell_start; int *off_me; };
+__global__ void k_cell_totals(TotalsArgs a0, TotalsArgs a1, unsigned blocks0, int nc, int rank, int world) {
+    const bool first = blockIdx.x < blocks0;
+    const TotalsArgs &a = first ? a0 : a1;
+    const int c = (int)((first ? blockIdx.x : blockIdx.x - blocks0) * blockDim.x + threadIdx.x);
     if (c >= nc) return;
     int tot = 0, off = 0;
     for (int g = 0; g < world; ++g) {
-        const int v = cnt_all[(size_t)g * (nc + 1) + c];
+        const int v = a.cnt_all[(size_t)g * (nc + 1) + c];
         if (g < rank) off += v;
         tot += v;
     }
-    cell_start[c] = tot; off_me[c] = off;
+    a.cell_start[c] = tot; a.off_me[c] = off;
 }
 
 // ranks that own a bonded partner of an owned protein (its x must reach them even if the cells are not stencil neighbours)
@@ -110,17 +119,19 @@ __global__ void k_bond_mask(const int *__restrict__ bonds, size_t n_bonds, const
 // x, n of the owned particles of boundary cells -> the ranks that read them (after a migration; the per-step push is fused
 // into the integrator)
 struct HaloDst { float4 *x[kMaxWorld], *nn[kMaxWorld]; };
-__global__ void k_halo_push(const int *__restrict__ range2, const unsigned char *__restrict__ cell_mask, const unsigned char *__restrict__ pmask,
-                            const int *__restrict__ cellid, const float4 *__restrict__ x, const float4 *__restrict__ nn, HaloDst d) {
-    const int i = range2[0] + blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= range2[1]) return;
-    unsigned m = cell_mask[cellid[i]];
-    if (pmask) m |= pmask[i];
+struct HaloArgs { const int *range2; const unsigned char *cell_mask, *pmask; const int *cellid; const float4 *x, *nn; HaloDst d; };
+__global__ void k_halo_push(HaloArgs a0, HaloArgs a1, unsigned blocks0) {
+    const bool first = blockIdx.x < blocks0;
+    const HaloArgs &a = first ? a0 : a1;
+    const int i = a.range2[0] + (int)((first ? blockIdx.x : blockIdx.x - blocks0) * blockDim.x + threadIdx.x);
+    if (i >= a.range2[1]) return;
+    unsigned m = a.cell_mask[a.cellid[i]];
+    if (a.pmask) m |= a.pmask[i];
     if (!m) return;
-    const float4 xv = x[i], nv = nn[i];
+    const float4 xv = a.x[i], nv = a.nn[i];
     while (m) {
         const int r = __ffs(m) - 1; m &= m - 1;
-        d.x[r][i] = xv; d.nn[r][i] = nv;
+        a.d.x[r][i] = xv; a.d.nn[r][i] = nv;
     }
 }
 

@@ -470,82 +470,127 @@ int do_voronoi_update(orbc_ctx *c, int nstep, int freq_sort_ctrd) {
 }
 
 // VCellList::update in three phases, so that a decomposed rebuild can run both containers through each phase between two
-// barriers.  Phase A: nearest centroid of every owned particle + arrival counts (voronoi.h:179-216), counts published.
-int cell_update_assign(orbc_ctx *c, int sp, const int *keep = nullptr) {
-    Species &S = c->sp[sp];
+// barriers.  `which`: the containers a phase works on (bit 0 lipids, bit 1 proteins); with both, every kernel of a phase is ONE
+// launch whose leading blocks take the lipids and whose trailing blocks take the proteins (the protein launches are short and
+// latency-bound -- 46 us of nearest-centroid search for a fifth of the particles -- and disappear behind the lipids' work).
+// Phase A: nearest centroid of every owned particle + arrival counts (voronoi.h:179-216), counts published.
+constexpr int kBothContainers = 3;
+int cell_update_assign(orbc_ctx *c, int which, const int *keep = nullptr) {
     if (!c->n_cells || !c->stencil_valid) return fail(ORBC_ERR_ARG, "cell_update: no Voronoi diagram");
     const int nc = c->n_cells;
     const bool mg = mg_active(c);
-    if (!S.cell_start) ORBC_TRY(dev_alloc(&S.cell_start, (size_t)nc + 1));
-    int *cnt = mg ? c->mg.cnt_all[sp] + (size_t)c->mg.rank * (nc + 1) : S.cell_start;
-    ORBC_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int) * ((size_t)nc + 1), c->stream));
-    if (S.n) {
-        const GridDev gd = grid_dev(c);
-        ORBC_LAUNCH(c, k_assign_nearest, blocks_for(owned_bound(c, sp), kBlock), kBlock, 0, S.X(), S.has_partition ? S.C() : nullptr, c->d_range + 2 * sp, c->centroid, nc,
-                    c->stencil, c->stencil_cnt, gd, S.aff, S.li, cnt, c->d_counters, c->d_flags, keep);
+    AssignArgs a[2]; unsigned blocks[2] = {0, 0}; int m = 0;
+    ShareArgs sh[2]; int ms = 0;
+    for (int sp = 0; sp < 2; ++sp) {
+        if (!((which >> sp) & 1)) continue;
+        Species &S = c->sp[sp];
+        if (!S.cell_start) ORBC_TRY(dev_alloc(&S.cell_start, (size_t)nc + 1));
+        int *cnt = mg ? c->mg.cnt_all[sp] + (size_t)c->mg.rank * (nc + 1) : S.cell_start;
+        ORBC_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int) * ((size_t)nc + 1), c->stream));
+        if (S.n) {
+            a[m] = AssignArgs{S.X(), S.has_partition ? S.C() : nullptr, c->d_range + 2 * sp, S.aff, S.li, cnt, sp == ORBC_LIPID ? keep : nullptr};
+            blocks[m++] = blocks_for(owned_bound(c, sp), kBlock);
+        }
+        if (mg) { sh[ms].cnt_me = cnt; sh[ms].prev = c->mg.cnt_prev[sp]; for (int r = 0; r < kMaxWorld; ++r) sh[ms].dst[r] = c->mg.peers.cnt_all[sp][r]; ++ms; }
     }
-    if (mg) {
-        CountRows rows; for (int r = 0; r < kMaxWorld; ++r) rows.dst[r] = c->mg.peers.cnt_all[sp][r];
-        ORBC_LAUNCH(c, k_share_counts, blocks_for((size_t)nc + 1, kBlock), kBlock, 0, cnt, c->mg.cnt_prev[sp], nc + 1, c->mg.rank, c->mg.world, rows);
+    const AssignCommon common = {c->centroid, nc, c->stencil, c->stencil_cnt, grid_dev(c), c->d_counters, c->d_flags};
+    if (m == 2) ORBC_LAUNCH(c, k_assign_nearest2, blocks[0] + blocks[1], kBlock, 0, a[0], a[1], blocks[0], common);
+    else if (m == 1) ORBC_LAUNCH(c, k_assign_nearest, blocks[0], kBlock, 0, a[0], common);
+    if (ms) {
+        const unsigned nb = blocks_for((size_t)nc + 1, kBlock);
+        ORBC_LAUNCH(c, k_share_counts, nb * ms, kBlock, 0, sh[0], sh[ms - 1], nb, nc + 1, c->mg.rank, c->mg.world);   // (ms sets of nb blocks)
     }
     return ORBC_OK;
 }
 // Phase B: global cell_start (voronoi.h:217-227), then every particle moves to its new slot on its new owner (voronoi.h:228-231
 // + reorder.h:73-149 as one scatter; the migration of a decomposed run is the same store, into a peer's memory)
-int cell_update_move(orbc_ctx *c, int sp) {
-    Species &S = c->sp[sp];
+int cell_update_move(orbc_ctx *c, int which) {
     const int nc = c->n_cells;
     const bool mg = mg_active(c);
-    const int *cnt_me = nullptr, *off_me = nullptr;
-    if (mg) {
-        ORBC_LAUNCH(c, k_cell_totals, blocks_for(nc, kBlock), kBlock, 0, c->mg.cnt_all[sp], nc, c->mg.rank, c->mg.world, S.cell_start, c->mg.off_me[sp]);
-        cnt_me = c->mg.cnt_all[sp] + (size_t)c->mg.rank * (nc + 1); off_me = c->mg.off_me[sp];
+    ScatterArgs sc[2]; MoveArgs mv[2]; unsigned blocks[2] = {0, 0}; int m = 0;
+    TotalsArgs tt[2]; int mt = 0;
+    for (int sp = 0; sp < 2; ++sp) {
+        if (!((which >> sp) & 1)) continue;
+        Species &S = c->sp[sp];
+        if (mg) tt[mt++] = TotalsArgs{c->mg.cnt_all[sp], S.cell_start, c->mg.off_me[sp]};
     }
-    ORBC_TRY(scan_exclusive(c, S.cell_start, nc));
-    if (S.n) {
-        const size_t nb = owned_bound(c, sp);
-        ORBC_LAUNCH(c, k_cell_scatter, blocks_for(nb, kBlock), kBlock, 0, S.aff, S.li, c->d_range + 2 * sp, S.cell_start, off_me, S.cells_tmp);
-        const int nx = S.cur ^ 1, nxn = S.cur_xn ^ 1;
-        MoveDst d; d.own = cell_owners(c);
-        for (int r = 0; r < kMaxWorld; ++r) {
-            d.x[r] = mg ? c->mg.peers.x[sp][nxn][r] : S.x[nxn]; d.nn[r] = mg ? c->mg.peers.nn[sp][nxn][r] : S.nn[nxn];
-            d.v[r] = mg ? c->mg.peers.v[sp][nx][r] : S.v[nx]; d.o[r] = mg ? c->mg.peers.o[sp][nx][r] : S.o[nx];
-            d.cellid[r] = mg ? c->mg.peers.cellid[sp][nx][r] : S.cellid[nx];
-            d.tag2idx[r] = mg ? c->mg.peers.tag2idx[r] : c->tag2idx;
+    if (mt) {
+        const unsigned nb = blocks_for(nc, kBlock);
+        ORBC_LAUNCH(c, k_cell_totals, nb * mt, kBlock, 0, tt[0], tt[mt - 1], nb, nc, c->mg.rank, c->mg.world);
+    }
+    for (int sp = 0; sp < 2; ++sp) {
+        if (!((which >> sp) & 1)) continue;
+        Species &S = c->sp[sp];
+        const int *cnt_me = nullptr, *off_me = nullptr;
+        if (mg) { cnt_me = c->mg.cnt_all[sp] + (size_t)c->mg.rank * (nc + 1); off_me = c->mg.off_me[sp]; }
+        ORBC_TRY(scan_exclusive(c, S.cell_start, nc));
+        if (S.n) {
+            const int nx = S.cur ^ 1, nxn = S.cur_xn ^ 1;
+            sc[m] = ScatterArgs{S.aff, S.li, c->d_range + 2 * sp, S.cell_start, off_me, S.cells_tmp};
+            MoveArgs &v = mv[m];
+            v.aff = S.aff; v.range = c->d_range + 2 * sp; v.cell_start = S.cell_start; v.cnt_me = cnt_me; v.off_me = off_me; v.cells_tmp = S.cells_tmp; v.cells = S.cells;
+            v.x0 = S.X(); v.n0 = S.N(); v.v0 = S.V(); v.o0 = S.O();
+            v.announce_tags = (mg && sp == ORBC_PROTEIN) ? 1 : 0;
+            v.d.own = cell_owners(c);
+            for (int r = 0; r < kMaxWorld; ++r) {
+                v.d.x[r] = mg ? c->mg.peers.x[sp][nxn][r] : S.x[nxn]; v.d.nn[r] = mg ? c->mg.peers.nn[sp][nxn][r] : S.nn[nxn];
+                v.d.v[r] = mg ? c->mg.peers.v[sp][nx][r] : S.v[nx]; v.d.o[r] = mg ? c->mg.peers.o[sp][nx][r] : S.o[nx];
+                v.d.cellid[r] = mg ? c->mg.peers.cellid[sp][nx][r] : S.cellid[nx];
+                v.d.tag2idx[r] = mg ? c->mg.peers.tag2idx[r] : c->tag2idx;
+            }
+            blocks[m++] = blocks_for(owned_bound(c, sp), kBlock);
+            S.cur = nx; S.cur_xn = nxn;
         }
-        ORBC_LAUNCH(c, k_rank_and_move, blocks_for(nb, kBlock), kBlock, 0, S.aff, c->d_range + 2 * sp, S.cell_start, cnt_me, off_me, S.cells_tmp, S.cells,
-                    S.X(), S.N(), S.V(), S.O(), d, (mg && sp == ORBC_PROTEIN) ? 1 : 0);
-        S.cur = nx; S.cur_xn = nxn;
+        S.has_partition = true;
+        if (sp == ORBC_LIPID) c->lruns_valid = false;
     }
-    S.has_partition = true;
+    if (m == 2) {
+        ORBC_LAUNCH(c, k_cell_scatter2, blocks[0] + blocks[1], kBlock, 0, sc[0], sc[1], blocks[0]);
+        ORBC_LAUNCH(c, k_rank_and_move2, blocks[0] + blocks[1], kBlock, 0, mv[0], mv[1], blocks[0]);
+    } else if (m == 1) {
+        ORBC_LAUNCH(c, k_cell_scatter, blocks[0], kBlock, 0, sc[0]);
+        ORBC_LAUNCH(c, k_rank_and_move, blocks[0], kBlock, 0, mv[0]);
+    }
     c->nl_valid = false;
-    if (sp == ORBC_LIPID) c->lruns_valid = false;
     return ORBC_OK;
 }
 // Phase C: tag -> index map (container.h:39-58); decomposed: new owned range, bonded-partner masks, halo copies of the moved particles
-int cell_update_finish(orbc_ctx *c, int sp) {
-    Species &S = c->sp[sp];
+int cell_update_finish(orbc_ctx *c, int which) {
     const bool mg = mg_active(c);
-    if (sp == ORBC_PROTEIN) c->porder_valid = false;
-    if (!mg) { if (sp == ORBC_PROTEIN) ORBC_TRY(build_tag2idx(c)); return ORBC_OK; }
-    ORBC_LAUNCH(c, k_set_range, 1, 1, 0, S.cell_start, c->mg.cb, c->mg.ce, c->d_range + 2 * sp, (int)c->mg.own_cap[sp], c->d_flags);
-    if (!S.n) return ORBC_OK;
-    if (sp == ORBC_PROTEIN && c->n_bonds) {
-        ORBC_CUDA(cudaMemsetAsync(c->mg.pmask, 0, (S.n + 3) / 4 * 4, c->stream));
+    if (which & 2) c->porder_valid = false;
+    if (!mg) { if (which & 2) ORBC_TRY(build_tag2idx(c)); return ORBC_OK; }
+    RangeArgs rg[2]; HaloArgs ha[2]; unsigned blocks[2] = {0, 0}; int mr = 0, m = 0;
+    for (int sp = 0; sp < 2; ++sp) {
+        if (!((which >> sp) & 1)) continue;
+        Species &S = c->sp[sp];
+        rg[mr++] = RangeArgs{S.cell_start, c->d_range + 2 * sp, (int)c->mg.own_cap[sp]};
+    }
+    ORBC_LAUNCH(c, k_set_range, 1, 32, 0, rg[0], rg[mr - 1], mr, c->mg.cb, c->mg.ce, c->d_flags);
+    Species &P = c->sp[1];
+    if ((which & 2) && P.n && c->n_bonds) {
+        ORBC_CUDA(cudaMemsetAsync(c->mg.pmask, 0, (P.n + 3) / 4 * 4, c->stream));
         ORBC_CUDA(cudaMemsetAsync(c->mg.my_bonds, 0, sizeof(int), c->stream));
-        ORBC_LAUNCH(c, k_bond_mask, blocks_for(c->n_bonds, kBlock), kBlock, 0, c->bonds, c->n_bonds, c->tag2idx, c->d_range, S.cell_start, cell_owners(c), (unsigned *)c->mg.pmask,
+        ORBC_LAUNCH(c, k_bond_mask, blocks_for(c->n_bonds, kBlock), kBlock, 0, c->bonds, c->n_bonds, c->tag2idx, c->d_range, P.cell_start, cell_owners(c), (unsigned *)c->mg.pmask,
                     c->mg.my_bonds, c->mg.my_bonds_cap, c->d_flags);
     }
-    HaloDst d; for (int r = 0; r < kMaxWorld; ++r) { d.x[r] = c->mg.peers.x[sp][S.cur_xn][r]; d.nn[r] = c->mg.peers.nn[sp][S.cur_xn][r]; }
-    ORBC_LAUNCH(c, k_halo_push, blocks_for(owned_bound(c, sp), kBlock), kBlock, 0, c->d_range + 2 * sp, c->mg.dest_mask, sp == ORBC_PROTEIN ? c->mg.pmask : (const unsigned char *)nullptr,
-                S.C(), S.X(), S.N(), d);
+    for (int sp = 0; sp < 2; ++sp) {
+        if (!((which >> sp) & 1)) continue;
+        Species &S = c->sp[sp];
+        if (!S.n) continue;
+        HaloArgs &h = ha[m];
+        h.range2 = c->d_range + 2 * sp; h.cell_mask = c->mg.dest_mask; h.pmask = sp == ORBC_PROTEIN ? c->mg.pmask : (const unsigned char *)nullptr;
+        h.cellid = S.C(); h.x = S.X(); h.nn = S.N();
+        for (int r = 0; r < kMaxWorld; ++r) { h.d.x[r] = c->mg.peers.x[sp][S.cur_xn][r]; h.d.nn[r] = c->mg.peers.nn[sp][S.cur_xn][r]; }
+        blocks[m++] = blocks_for(owned_bound(c, sp), kBlock);
+    }
+    if (m) ORBC_LAUNCH(c, k_halo_push, blocks[0] + (m == 2 ? blocks[1] : 0), kBlock, 0, ha[0], ha[m - 1], blocks[0]);
     return ORBC_OK;
 }
 
 int do_cell_update(orbc_ctx *c, int sp) {
-    ORBC_TRY(cell_update_assign(c, sp)); ORBC_TRY(mg_barrier(c));
-    ORBC_TRY(cell_update_move(c, sp));   ORBC_TRY(mg_barrier(c));
-    ORBC_TRY(cell_update_finish(c, sp)); return mg_barrier(c);
+    ORBC_TRY(cell_update_assign(c, 1 << sp)); ORBC_TRY(mg_barrier(c));
+    ORBC_TRY(cell_update_move(c, 1 << sp));   ORBC_TRY(mg_barrier(c));
+    ORBC_TRY(cell_update_finish(c, 1 << sp)); return mg_barrier(c);
 }
 
 // `rebuild_follows`: the caller rebuilds next; the first barrier of the rebuild then also covers the arrival of this push
@@ -554,20 +599,24 @@ int do_integrate_langevin(orbc_ctx *c, const orbc_step_params *p, bool rebuild_f
     ++c->nl_moves;                                               // one tracked integration step (hit lists: displacement bound)
     {
         ProfScope ps(c, ORBC_PROF_INTEGRATE);
+        // both containers in one launch (leading blocks the lipids, trailing blocks the proteins)
+        IntegArgs a[2]; unsigned blocks[2] = {0, 0}; int m = 0;
         for (int sp = 0; sp < 2; ++sp) {
             Species &S = c->sp[sp];
             if (!S.n) continue;
-            IntegArgs a; fill_integ(a, c, sp, p); langevin_coeffs(c, a, p);
-            a.clear = clear ? 1 : 0;
+            fill_integ(a[m], c, sp, p); langevin_coeffs(c, a[m], p);
+            a[m].clear = clear ? 1 : 0;
             const float *hn = sp == 0 ? p->noise_lipid : p->noise_protein;
             if (hn) {
                 if (c->noise_cap[sp] < 3 * S.n) { ORBC_TRY(dev_alloc(&c->noise[sp], 3 * S.n)); c->noise_cap[sp] = 3 * S.n; }
                 ORBC_CUDA(cudaMemcpyAsync(c->noise[sp], hn, sizeof(float) * 3 * S.n, cudaMemcpyHostToDevice, c->stream));
-                a.noise = c->noise[sp];
+                a[m].noise = c->noise[sp];
             }
-            ORBC_LAUNCH(c, k_verlet_langevin, blocks_for(owned_bound(c, sp), 256), 256, 0, a);
+            blocks[m++] = blocks_for(owned_bound(c, sp), 256);
             if (mg_active(c)) S.cur_xn ^= 1;
         }
+        if (m == 2) ORBC_LAUNCH(c, k_verlet_langevin2, blocks[0] + blocks[1], 256, 0, a[0], a[1], blocks[0]);
+        else if (m == 1) ORBC_LAUNCH(c, k_verlet_langevin, blocks[0], 256, 0, a[0]);
         ORBC_TRY(nl_share(c));
     }
     return rebuild_follows ? ORBC_OK : mg_barrier(c);            // the pushed halo has landed everywhere
@@ -596,7 +645,7 @@ int preload_kernels() {
     ORBC_PRELOAD(k_pair_lipid); ORBC_PRELOAD(k_lipid_runs); ORBC_PRELOAD(k_rank_only); ORBC_PRELOAD(k_init_centroids); ORBC_PRELOAD(k_bbox); ORBC_PRELOAD((k_pair_ll_r<20, 4, false>)); ORBC_PRELOAD(k_pair_ll_t); ORBC_PRELOAD((k_pair_prot<1, false>)); ORBC_PRELOAD((k_pair_prot<2, false>)); ORBC_PRELOAD((k_pair_prot<4, false>)); ORBC_PRELOAD((k_pair_prot<1, true>)); ORBC_PRELOAD((k_pair_prot<2, true>)); ORBC_PRELOAD((k_pair_prot<4, true>)); ORBC_PRELOAD(k_pair_prot_list<1>); ORBC_PRELOAD(k_pair_prot_list<2>); ORBC_PRELOAD(k_pair_prot_list<4>); ORBC_PRELOAD((k_pair_ll_r<16, 4, true>)); ORBC_PRELOAD((k_pair_ll_list<16, false>)); ORBC_PRELOAD((k_pair_ll_list<16, true>)); ORBC_PRELOAD(k_pack_xn); ORBC_PRELOAD(k_nl_gate); ORBC_PRELOAD(k_nl_share); ORBC_PRELOAD(k_pair_protein);
     ORBC_PRELOAD(k_permute_centroids); ORBC_PRELOAD(k_porder_flag); ORBC_PRELOAD(k_porder_scatter); ORBC_PRELOAD(k_post_torque); ORBC_PRELOAD(k_radix_hist);
     ORBC_PRELOAD(k_radix_scatter); ORBC_PRELOAD(k_rank_and_move); ORBC_PRELOAD(k_remap_cellid); ORBC_PRELOAD(k_scan_onepass); ORBC_PRELOAD(k_set3); ORBC_PRELOAD(k_set_range); ORBC_PRELOAD(k_set_range_const); ORBC_PRELOAD(k_share_counts);
-    ORBC_PRELOAD(k_stencil_build); ORBC_PRELOAD(k_stencil_refresh); ORBC_PRELOAD(k_stencil_movers<true>); ORBC_PRELOAD(k_stencil_movers<false>); ORBC_PRELOAD(k_centroid_disp); ORBC_PRELOAD(k_stray_mask); ORBC_PRELOAD(k_unpack3); ORBC_PRELOAD(k_unpack_w); ORBC_PRELOAD(k_verlet_langevin); ORBC_PRELOAD(k_zero4);
+    ORBC_PRELOAD(k_stencil_build); ORBC_PRELOAD(k_stencil_refresh); ORBC_PRELOAD(k_stencil_movers<true>); ORBC_PRELOAD(k_stencil_movers<false>); ORBC_PRELOAD(k_centroid_disp); ORBC_PRELOAD(k_stray_mask); ORBC_PRELOAD(k_unpack3); ORBC_PRELOAD(k_unpack_w); ORBC_PRELOAD(k_verlet_langevin); ORBC_PRELOAD(k_verlet_langevin2); ORBC_PRELOAD(k_assign_nearest2); ORBC_PRELOAD(k_cell_scatter2); ORBC_PRELOAD(k_rank_and_move2); ORBC_PRELOAD(k_zero4);
 #undef ORBC_PRELOAD
     return ORBC_OK;
 }
@@ -984,15 +1033,15 @@ int orbc_voronoi_init(orbc_ctx *c, int nc, int n_iterate) { if (c) cudaSetDevice
         if (k > 0) ORBC_LAUNCH(c, k_remap_cellid, blocks_for(L.n, kBlock), kBlock, 0, L.C(), c->d_range, c->inv);   // last round's cell = this round's search hint
         ORBC_TRY(build_index(c));
         // cell_list.partition(cont, *this)
-        ORBC_TRY(cell_update_assign(c, ORBC_LIPID));
+        ORBC_TRY(cell_update_assign(c, 1));
         const bool reorder = (k & (~k + 1)) == k || k == last;
         if (reorder) {
-            ORBC_TRY(cell_update_move(c, ORBC_LIPID));            // scan, arrival lists, rank + move (reorder.h:73-149)
+            ORBC_TRY(cell_update_move(c, 1));                     // scan, arrival lists, rank + move (reorder.h:73-149)
             for (int r = 0; r < kMaxWorld; ++r) out.dst[r] = c->centroid;
             ORBC_LAUNCH(c, k_centroid_update, blocks_for(nc, kBlock), kBlock, 0, L.cell_start, L.X(), 0, nc, out, (const int *)nullptr);
         } else {
             ORBC_TRY(scan_exclusive(c, L.cell_start, nc));
-            ORBC_LAUNCH(c, k_cell_scatter, blocks_for(L.n, kBlock), kBlock, 0, L.aff, L.li, c->d_range, L.cell_start, (const int *)nullptr, L.cells_tmp);
+            ORBC_LAUNCH(c, k_cell_scatter, blocks_for(L.n, kBlock), kBlock, 0, ScatterArgs{L.aff, L.li, c->d_range, L.cell_start, (const int *)nullptr, L.cells_tmp});
             ORBC_LAUNCH(c, k_rank_only, blocks_for(L.n, kBlock), kBlock, 0, L.aff, c->d_range, L.cell_start, L.cells_tmp, L.cells);
             for (int r = 0; r < kMaxWorld; ++r) out.dst[r] = c->centroid;
             ORBC_LAUNCH(c, k_centroid_update, blocks_for(nc, kBlock), kBlock, 0, L.cell_start, L.X(), 0, nc, out, L.cells);
@@ -1032,11 +1081,11 @@ int orbc_cell_update(orbc_ctx *c, int sp, int nstep, int freq_sort_bond) { if (c
 int do_rebuild(orbc_ctx *c, int nstep, int freq_sort_ctrd) {
     ProfScope ps(c, ORBC_PROF_REBUILD);
     ORBC_TRY(do_voronoi_update(c, nstep, freq_sort_ctrd));
-    for (int sp = 0; sp < 2; ++sp) ORBC_TRY(cell_update_assign(c, sp));
+    ORBC_TRY(cell_update_assign(c, kBothContainers));
     ORBC_TRY(mg_barrier(c));
-    for (int sp = 0; sp < 2; ++sp) ORBC_TRY(cell_update_move(c, sp));
+    ORBC_TRY(cell_update_move(c, kBothContainers));
     ORBC_TRY(mg_barrier(c));
-    for (int sp = 0; sp < 2; ++sp) ORBC_TRY(cell_update_finish(c, sp));
+    ORBC_TRY(cell_update_finish(c, kBothContainers));
     return mg_barrier(c);
 }
 
@@ -1067,9 +1116,9 @@ int orbc_delete_lipid(orbc_ctx *c, float tol, size_t *n_out) { if (c) cudaSetDev
         ORBC_CUDA(cudaMemcpyAsync(c->h_acc, c->d_acc, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         ORBC_CUDA(cudaStreamSynchronize(c->stream));
         if (c->h_acc[0] == 0.0) { if (n_out) *n_out = L.n; return check_flags(c); }
-        ORBC_TRY(cell_update_assign(c, ORBC_LIPID, c->mg.keep)); ORBC_TRY(mg_barrier(c));
-        ORBC_TRY(cell_update_move(c, ORBC_LIPID));               ORBC_TRY(mg_barrier(c));
-        ORBC_TRY(cell_update_finish(c, ORBC_LIPID));             ORBC_TRY(mg_barrier(c));
+        ORBC_TRY(cell_update_assign(c, 1, c->mg.keep)); ORBC_TRY(mg_barrier(c));
+        ORBC_TRY(cell_update_move(c, 1));               ORBC_TRY(mg_barrier(c));
+        ORBC_TRY(cell_update_finish(c, 1));             ORBC_TRY(mg_barrier(c));
         int total = 0;
         ORBC_CUDA(cudaMemcpyAsync(&total, L.cell_start + nc, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         ORBC_CUDA(cudaStreamSynchronize(c->stream));
@@ -1353,7 +1402,7 @@ int orbc_mg_export(orbc_ctx *c, void *blob_out, size_t bytes) { if (c) cudaSetDe
     }
     // owned ranges, halo masks and the cells this rank reads, from the uploaded (complete, everywhere identical) state
     if (w > 1) {
-        for (int sp = 0; sp < 2; ++sp) ORBC_LAUNCH(c, k_set_range, 1, 1, 0, c->sp[sp].cell_start, m.cb, m.ce, c->d_range + 2 * sp, (int)m.own_cap[sp], c->d_flags);
+        ORBC_LAUNCH(c, k_set_range, 1, 32, 0, RangeArgs{c->sp[0].cell_start, c->d_range, (int)m.own_cap[0]}, RangeArgs{c->sp[1].cell_start, c->d_range + 2, (int)m.own_cap[1]}, 2, m.cb, m.ce, c->d_flags);
         ORBC_TRY(build_index(c, true));
         ORBC_CUDA(cudaMemsetAsync(m.my_bonds, 0, sizeof(int), c->stream));
         if (P.n && c->n_bonds)
@@ -1369,9 +1418,12 @@ int orbc_mg_export(orbc_ctx *c, void *blob_out, size_t bytes) { if (c) cudaSetDe
         for (int sp = 0; sp < 2; ++sp) {
             Species &S = c->sp[sp];
             if (!S.n) continue;
-            HaloDst d; for (int r = 0; r < kMaxWorld; ++r) { d.x[r] = m.peers.x[sp][S.cur_xn][r]; d.nn[r] = m.peers.nn[sp][S.cur_xn][r]; }
-            ORBC_LAUNCH(c, k_halo_push, blocks_for(owned_bound(c, sp), kBlock), kBlock, 0, c->d_range + 2 * sp, m.dest_mask, sp == ORBC_PROTEIN ? m.pmask : (const unsigned char *)nullptr,
-                        S.C(), S.X(), S.N(), d);
+            HaloArgs h;
+            h.range2 = c->d_range + 2 * sp; h.cell_mask = m.dest_mask; h.pmask = sp == ORBC_PROTEIN ? m.pmask : (const unsigned char *)nullptr;
+            h.cellid = S.C(); h.x = S.X(); h.nn = S.N();
+            for (int r = 0; r < kMaxWorld; ++r) { h.d.x[r] = m.peers.x[sp][S.cur_xn][r]; h.d.nn[r] = m.peers.nn[sp][S.cur_xn][r]; }
+            const unsigned nb = blocks_for(owned_bound(c, sp), kBlock);
+            ORBC_LAUNCH(c, k_halo_push, nb, kBlock, 0, h, h, nb);
         }
         ORBC_TRY(mg_barrier(c));
     }

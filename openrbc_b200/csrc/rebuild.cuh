@@ -398,11 +398,15 @@ __device__ int nearest_by_grid(float4 p, const GridDev &g, const float4 *__restr
 // One thread per particle.  Fast path: the particle's previous cell g and g's r<9 centroid stencil; it is exact whenever
 // d(best) + d(g) < 9 (every centroid at least that close to the particle is then inside the stencil).  Otherwise the grid
 // search above.  Ties in the squared distance go to the lower cell id.
-__global__ void k_assign_nearest(const float4 *__restrict__ x, const int *__restrict__ cellid, const int *__restrict__ range, const float4 *__restrict__ centroid, int n_cells,
-                                 const int *__restrict__ stencil, const int *__restrict__ stencil_cnt, GridDev g,
-                                 int *__restrict__ aff, int *__restrict__ li, int *__restrict__ cell_cnt,
-                                 unsigned long long *__restrict__ counters, int *__restrict__ flags, const int *__restrict__ keep) {
-    const int i = range[0] + blockIdx.x * blockDim.x + threadIdx.x;
+// (the per-container arguments and the ones both containers share: k_assign_nearest2 runs both containers in one launch)
+struct AssignArgs { const float4 *x; const int *cellid; const int *range; int *aff; int *li; int *cell_cnt; const int *keep; };
+struct AssignCommon { const float4 *centroid; int n_cells; const int *stencil; const int *stencil_cnt; GridDev g; unsigned long long *counters; int *flags; };
+__device__ __forceinline__ void assign_nearest_body(const unsigned bid, const AssignArgs &a, const AssignCommon &s) {
+    const float4 *__restrict__ x = a.x; const int *__restrict__ cellid = a.cellid; const int *__restrict__ range = a.range;
+    int *__restrict__ aff = a.aff; int *__restrict__ li = a.li; int *__restrict__ cell_cnt = a.cell_cnt; const int *__restrict__ keep = a.keep;
+    const float4 *__restrict__ centroid = s.centroid; const int n_cells = s.n_cells; const int *__restrict__ stencil = s.stencil;
+    const int *__restrict__ stencil_cnt = s.stencil_cnt; const GridDev &g = s.g; unsigned long long *__restrict__ counters = s.counters; int *__restrict__ flags = s.flags;
+    const int i = range[0] + bid * blockDim.x + threadIdx.x;
     const bool live = i < range[1];
     const bool gone = live && keep && !keep[i];                  // stray lipid being deleted (cleanup.h:29-91): it joins no cell
     int bi = -1;
@@ -453,15 +457,25 @@ __global__ void k_assign_nearest(const float4 *__restrict__ x, const int *__rest
     }
 }
 
+__global__ void k_assign_nearest(AssignArgs a, AssignCommon s) { assign_nearest_body(blockIdx.x, a, s); }
+// both containers: blocks [0, blocks0) take a0's particles, the others a1's (a block never mixes the two)
+__global__ void k_assign_nearest2(AssignArgs a0, AssignArgs a1, unsigned blocks0, AssignCommon s) {
+    if (blockIdx.x < blocks0) assign_nearest_body(blockIdx.x, a0, s); else assign_nearest_body(blockIdx.x - blocks0, a1, s);
+}
+
 // cells_tmp[cell_start[aff] + arrival slot] = i   (voronoi.h:228-231 with an arbitrary arrival order ...)
 // (decomposed: this rank's members of cell c take the slots [cell_start[c] + off_me[c], + cnt_me[c]) of the arrival list)
-__global__ void k_cell_scatter(const int *__restrict__ aff, const int *__restrict__ li, const int *__restrict__ range, const int *__restrict__ cell_start,
-                               const int *__restrict__ off_me, int *__restrict__ cells_tmp) {
-    const int i = range[0] + blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= range[1]) return;
-    const int c = aff[i];
+struct ScatterArgs { const int *aff; const int *li; const int *range; const int *cell_start; const int *off_me; int *cells_tmp; };
+__device__ __forceinline__ void cell_scatter_body(const unsigned bid, const ScatterArgs &a) {
+    const int i = a.range[0] + bid * blockDim.x + threadIdx.x;
+    if (i >= a.range[1]) return;
+    const int c = a.aff[i];
     if (c < 0) return;
-    cells_tmp[cell_start[c] + (off_me ? off_me[c] : 0) + li[i]] = i;
+    a.cells_tmp[a.cell_start[c] + (a.off_me ? a.off_me[c] : 0) + a.li[i]] = i;
+}
+__global__ void k_cell_scatter(ScatterArgs a) { cell_scatter_body(blockIdx.x, a); }
+__global__ void k_cell_scatter2(ScatterArgs a0, ScatterArgs a1, unsigned blocks0) {
+    if (blockIdx.x < blocks0) cell_scatter_body(blockIdx.x, a0); else cell_scatter_body(blockIdx.x - blocks0, a1);
 }
 // Sorting every cell's arrival list and the gather-reorder in one pass, one thread per particle: the slot of particle i inside its new cell is
 // the number of members with a lower index (= arrival order of the reference at one thread, voronoi.h:214-215), found by
@@ -477,11 +491,17 @@ struct MoveDst {
     int *cellid[kMaxWorld], *tag2idx[kMaxWorld];
     CellOwners own;
 };
-__global__ void k_rank_and_move(const int *__restrict__ aff, const int *__restrict__ range, const int *__restrict__ cell_start, const int *__restrict__ cnt_me,
-                                const int *__restrict__ off_me, const int *__restrict__ cells_tmp, int *__restrict__ cells,
-                                const float4 *__restrict__ x0, const float4 *__restrict__ n0, const float4 *__restrict__ v0, const float4 *__restrict__ o0,
-                                MoveDst d, int announce_tags) {
-    const int i = range[0] + blockIdx.x * blockDim.x + threadIdx.x;
+struct MoveArgs {
+    const int *aff, *range, *cell_start, *cnt_me, *off_me, *cells_tmp; int *cells;
+    const float4 *x0, *n0, *v0, *o0;
+    MoveDst d; int announce_tags;
+};
+__device__ __forceinline__ void rank_and_move_body(const unsigned bid, const MoveArgs &a) {
+    const int *__restrict__ aff = a.aff; const int *__restrict__ range = a.range; const int *__restrict__ cell_start = a.cell_start;
+    const int *__restrict__ cnt_me = a.cnt_me; const int *__restrict__ off_me = a.off_me; const int *__restrict__ cells_tmp = a.cells_tmp; int *__restrict__ cells = a.cells;
+    const float4 *__restrict__ x0 = a.x0; const float4 *__restrict__ n0 = a.n0; const float4 *__restrict__ v0 = a.v0; const float4 *__restrict__ o0 = a.o0;
+    const MoveDst &d = a.d; const int announce_tags = a.announce_tags;
+    const int i = range[0] + bid * blockDim.x + threadIdx.x;
     if (i >= range[1]) return;
     const int c = aff[i];
     if (c < 0) return;
@@ -498,6 +518,11 @@ __global__ void k_rank_and_move(const int *__restrict__ aff, const int *__restri
         const int tag = __float_as_int(nn.w);
         for (int r = 0; r < d.own.world; ++r) d.tag2idx[r][tag] = j;
     }
+}
+
+__global__ void k_rank_and_move(MoveArgs a) { rank_and_move_body(blockIdx.x, a); }
+__global__ void k_rank_and_move2(MoveArgs a0, MoveArgs a1, unsigned blocks0) {
+    if (blockIdx.x < blocks0) rank_and_move_body(blockIdx.x, a0); else rank_and_move_body(blockIdx.x - blocks0, a1);
 }
 
 // the sorting half of k_rank_and_move alone: cells[] = the members of every cell in ascending index (VCellList::cells after

@@ -1,5 +1,5 @@
 """What the three-way gated launch costs: per-kernel times (event pairs around every launch) of force evaluations in a fixed mode.
-    python tools/gate_cost.py [workload]"""
+    python tools/gate_cost.py [workload] [option=value ...]"""
 import os
 import sys
 
@@ -10,6 +10,8 @@ import openrbc_b200 as orbc  # noqa: E402
 
 st = bench.load_state(sys.argv[1] if len(sys.argv) > 1 else "rbc")
 sim = orbc.Simulation(st, kBT=0.22)
+for kv in sys.argv[2:]:
+    sim.set_option(kv.split("=")[0], float(kv.split("=")[1]))
 sim.run_langevin(4)
 for name, opts in (("no lists", dict(nl_reuse=0)), ("walking", dict(nl_reuse=1)), ("recording", dict(debug_nl_mode=1)), ("searching", dict(debug_nl_mode=2))):
     for k, v in opts.items():
