@@ -1449,12 +1449,16 @@ int orbc_mg_connect(orbc_ctx *c, const void *blobs, size_t bytes_each) { if (c) 
         if (b->magic != kMgMagic || b->rank != r || b->world != m.world) return fail(ORBC_ERR_ARG, "orbc_mg_connect: blob %d is not rank %d of %d", r, r, m.world);
         if (b->n_cells != c->n_cells || b->n_l != c->sp[0].n || b->n_p != c->sp[1].n) return fail(ORBC_ERR_ARG, "orbc_mg_connect: rank %d holds a different system", r);
         void *ptr[kMgShared];
+        if (b->pid == (int)getpid() && b->device != c->device) { // same process, another device: peer access, once per pair of devices
+            cudaError_t e = cudaDeviceEnablePeerAccess(b->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) ORBC_CUDA(e);
+            cudaGetLastError();                                  // (another context of this process may have enabled it already)
+        }
         for (int k = 0; k < kMgShared; ++k) {
             ptr[k] = nullptr;
             if (!b->e[k].raw) continue;
             if (b->pid == (int)getpid()) {                       // same process (several ranks driven by one host program): plain pointers
                 ptr[k] = (void *)(uintptr_t)b->e[k].raw;
-                if (b->device != c->device) { cudaError_t e = cudaDeviceEnablePeerAccess(b->device, 0); if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) ORBC_CUDA(e); cudaGetLastError(); }
             } else {                                             // one process per GPU: CUDA IPC mapping of the peer's allocation
                 ORBC_CUDA(cudaIpcOpenMemHandle(&ptr[k], b->e[k].handle, cudaIpcMemLazyEnablePeerAccess));
                 m.opened.push_back(ptr[k]);

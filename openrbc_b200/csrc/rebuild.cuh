@@ -574,10 +574,11 @@ __global__ void k_check_ids(const int *__restrict__ type, const int *__restrict_
     bad = __reduce_max_sync(0xffffffffu, bad); mask = __reduce_or_sync(0xffffffffu, mask);
     neg = __reduce_max_sync(0xffffffffu, neg); top = __reduce_max_sync(0xffffffffu, top);
     if ((threadIdx.x & 31) == 0) {
-        if (bad) atomicMax(&chk[0], bad);
-        if (mask) atomicOr((unsigned *)&chk[1], mask);
-        if (neg) atomicMax(&chk[2], neg);
-        if (top) atomicMax(&chk[3], top);
+        // the words only grow: an atomic is needed only if this warp would still raise what it reads (17 000 warps on four words otherwise)
+        if (bad > __ldcg(&chk[0])) atomicMax(&chk[0], bad);
+        if (mask & ~(unsigned)__ldcg(&chk[1])) atomicOr((unsigned *)&chk[1], mask);
+        if (neg > __ldcg(&chk[2])) atomicMax(&chk[2], neg);
+        if (top > __ldcg(&chk[3])) atomicMax(&chk[3], top);
     }
 }
 // chk[4] = n - (first bond with a type outside [0, 4) or a tag outside the tag -> index map)
