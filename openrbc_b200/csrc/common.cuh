@@ -172,8 +172,6 @@ struct orbc_ctx {
     int nl_on = 1;                                 // option "nl_reuse": 0 off, 1 automatic, 2 on
     bool nl_valid = false;                         // lists match the current partition and were built (host's view)
     float nl_skin = 0.1f;                          // option "nl_skin"
-    bool ll_xn = false;                            // list walker gathers interleaved (x, n) records (k_pack_xn); measured: no gain (243 vs 238 us), off
-    float *xn = nullptr; size_t xn_cap = 0;        // those records, 32 B per lipid
     int nl_moves = 0;                              // tracked integration steps since the last gate
     void *nl_state = nullptr;                      // orbc::NlState on the device
     int *ll_list = nullptr, *ll_cnt = nullptr; size_t ll_list_lipids = 0;

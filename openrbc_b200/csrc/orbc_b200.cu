@@ -391,11 +391,7 @@ int launch_pairwise(orbc_ctx *c, bool accumulate = true) {
                 const unsigned g16 = std::min(groups, 148u * 16u), g20 = std::min(groups, 148u * 20u);   // (blocks per SM: the kernels' launch bounds)
                 // (what the host knows: after a change of the partition the gate never orders a walk, and otherwise never a recording)
                 if (!host_build) {
-                    if (!mg && c->ll_xn) {
-                        if (c->xn_cap < L.cap) { ORBC_TRY(dev_alloc(&c->xn, L.cap * 8)); c->xn_cap = L.cap; }
-                        ORBC_LAUNCH(c, k_pack_xn, blocks_for(L.n, kBlock), kBlock, 0, L.X(), L.N(), L.n, (XN *)c->xn);
-                        ORBC_LAUNCH(c, (k_pair_ll_list<16, true>), g16, kLLBlock, 0, a, kc, &nls->need, 0, ll, (const XN *)c->xn, nls->work + 0);
-                    } else ORBC_LAUNCH(c, (k_pair_ll_list<16, false>), g16, kLLBlock, 0, a, kc, &nls->need, 0, ll, (const XN *)nullptr, nls->work + 0);
+                    ORBC_LAUNCH(c, k_pair_ll_list<16>, g16, kLLBlock, 0, a, kc, &nls->need, 0, ll, nls->work + 0);
                 } else ORBC_LAUNCH(c, (k_pair_ll_r<16, 4, true>), g16, kLLBlock, 0, a, kc, c->lruns, c->lrun_cnt, &nls->need, 1, ll, c->nl_skin, nls->work + 1);
                 ORBC_LAUNCH(c, (k_pair_ll_r<20, 4, false>), g20, kLLBlock, 0, a, kc, c->lruns, c->lrun_cnt, &nls->need, 2, LLList{}, 0.f, nls->work + 2);
             }
@@ -642,7 +638,7 @@ int preload_kernels() {
     ORBC_PRELOAD(k_cv_normal_volume); ORBC_PRELOAD(k_fill_cellid); ORBC_PRELOAD(k_fill_int); ORBC_PRELOAD(k_halo_push); ORBC_PRELOAD(k_kinetic);
     ORBC_PRELOAD(k_mg_barrier); ORBC_PRELOAD(k_morton_keys); ORBC_PRELOAD(k_morton_keys_only); ORBC_PRELOAD(k_nh_final); ORBC_PRELOAD(k_nh_final_fused);
     ORBC_PRELOAD(k_nh_initial_fused); ORBC_PRELOAD(k_nh_zeta_update); ORBC_PRELOAD(k_share_ke); ORBC_PRELOAD(k_sum_ke); ORBC_PRELOAD(k_noise); ORBC_PRELOAD(k_opt_move); ORBC_PRELOAD(k_pack4);
-    ORBC_PRELOAD(k_pair_lipid); ORBC_PRELOAD(k_lipid_runs); ORBC_PRELOAD(k_rank_only); ORBC_PRELOAD(k_init_centroids); ORBC_PRELOAD(k_bbox); ORBC_PRELOAD((k_pair_ll_r<20, 4, false>)); ORBC_PRELOAD(k_pair_ll_t); ORBC_PRELOAD((k_pair_prot<1, false>)); ORBC_PRELOAD((k_pair_prot<2, false>)); ORBC_PRELOAD((k_pair_prot<4, false>)); ORBC_PRELOAD((k_pair_prot<1, true>)); ORBC_PRELOAD((k_pair_prot<2, true>)); ORBC_PRELOAD((k_pair_prot<4, true>)); ORBC_PRELOAD(k_pair_prot_list<1>); ORBC_PRELOAD(k_pair_prot_list<2>); ORBC_PRELOAD(k_pair_prot_list<4>); ORBC_PRELOAD((k_pair_ll_r<16, 4, true>)); ORBC_PRELOAD((k_pair_ll_list<16, false>)); ORBC_PRELOAD((k_pair_ll_list<16, true>)); ORBC_PRELOAD(k_pack_xn); ORBC_PRELOAD(k_nl_gate); ORBC_PRELOAD(k_nl_share); ORBC_PRELOAD(k_pair_protein);
+    ORBC_PRELOAD(k_pair_lipid); ORBC_PRELOAD(k_lipid_runs); ORBC_PRELOAD(k_rank_only); ORBC_PRELOAD(k_init_centroids); ORBC_PRELOAD(k_bbox); ORBC_PRELOAD((k_pair_ll_r<20, 4, false>)); ORBC_PRELOAD(k_pair_ll_t); ORBC_PRELOAD((k_pair_prot<1, false>)); ORBC_PRELOAD((k_pair_prot<2, false>)); ORBC_PRELOAD((k_pair_prot<4, false>)); ORBC_PRELOAD((k_pair_prot<1, true>)); ORBC_PRELOAD((k_pair_prot<2, true>)); ORBC_PRELOAD((k_pair_prot<4, true>)); ORBC_PRELOAD(k_pair_prot_list<1>); ORBC_PRELOAD(k_pair_prot_list<2>); ORBC_PRELOAD(k_pair_prot_list<4>); ORBC_PRELOAD((k_pair_ll_r<16, 4, true>)); ORBC_PRELOAD(k_pair_ll_list<16>); ORBC_PRELOAD(k_nl_gate); ORBC_PRELOAD(k_nl_share); ORBC_PRELOAD(k_pair_protein);
     ORBC_PRELOAD(k_permute_centroids); ORBC_PRELOAD(k_porder_flag); ORBC_PRELOAD(k_porder_scatter); ORBC_PRELOAD(k_post_torque); ORBC_PRELOAD(k_radix_hist);
     ORBC_PRELOAD(k_radix_scatter); ORBC_PRELOAD(k_rank_and_move); ORBC_PRELOAD(k_remap_cellid); ORBC_PRELOAD(k_scan_onepass); ORBC_PRELOAD(k_set3); ORBC_PRELOAD(k_set_range); ORBC_PRELOAD(k_set_range_const); ORBC_PRELOAD(k_share_counts);
     ORBC_PRELOAD(k_stencil_build); ORBC_PRELOAD(k_stencil_refresh); ORBC_PRELOAD(k_stencil_movers<true>); ORBC_PRELOAD(k_stencil_movers<false>); ORBC_PRELOAD(k_centroid_disp); ORBC_PRELOAD(k_stray_mask); ORBC_PRELOAD(k_unpack3); ORBC_PRELOAD(k_unpack_w); ORBC_PRELOAD(k_verlet_langevin); ORBC_PRELOAD(k_verlet_langevin2); ORBC_PRELOAD(k_assign_nearest2); ORBC_PRELOAD(k_cell_scatter2); ORBC_PRELOAD(k_rank_and_move2); ORBC_PRELOAD(k_zero4);
@@ -785,7 +781,7 @@ void orbc_destroy(orbc_ctx *c) { if (c) cudaSetDevice(c->device);
     dev_free(c->grid.bin_start); dev_free(c->grid.bin_items); dev_free(c->grid.bin_of); dev_free(c->grid.bin_slot); dev_free(c->grid.sorted);
     dev_free(c->stencil); dev_free(c->stencil_cnt); dev_free(c->wide); dev_free(c->wide_cnt); dev_free(c->cen_ref); dev_free(c->wide_ok); dev_free(c->movers); dev_free(c->cell_normal); dev_free(c->lbound); dev_free(c->pbound); dev_free(c->porder); dev_free(c->lruns); dev_free(c->lrun_cnt); dev_free(c->bonds); dev_free(c->tag2idx);
     dev_free(c->scan_tmp); dev_free(c->radix_hist); dev_free(c->stage); dev_free(c->d_acc); dev_free(c->d_counters); dev_free(c->d_flags); dev_free(c->d_check); dev_free(c->d_nh);
-    dev_free(c->noise[0]); dev_free(c->noise[1]); dev_free(c->d_range); dev_free(c->tile_overflow); dev_free(c->xn);
+    dev_free(c->noise[0]); dev_free(c->noise[1]); dev_free(c->d_range); dev_free(c->tile_overflow);
     { NlState *st = (NlState *)c->nl_state; dev_free(st); } dev_free(c->ll_list); dev_free(c->ll_cnt); dev_free(c->pl_list); dev_free(c->pl_cnt); dev_free(c->pp_list); dev_free(c->pp_cnt);
     for (void *m : c->mg.opened) cudaIpcCloseMemHandle(m);
     dev_free(c->mg.my_bonds); dev_free(c->mg.keep); dev_free(c->mg.ke_all); dev_free(c->mg.vol_all); dev_free(c->mg.cv_ptype); dev_free(c->mg.flags); dev_free(c->mg.dest_mask); dev_free(c->mg.pmask); dev_free(c->mg.need);
@@ -812,7 +808,6 @@ int orbc_set_option(orbc_ctx *c, const char *name, double value) { if (c) cudaSe
         if (value != 0 && value != 1) return fail(ORBC_ERR_ARG, "ll_variant must be 1 (run-list kernel + hit lists) or 0 (tile kernel)");
         c->ll_variant = (int)value; c->nl_valid = false; return ORBC_OK;
     }
-    if (!strcmp(name, "ll_xn")) { c->ll_xn = value != 0; return ORBC_OK; }   // list walker: partners gathered as interleaved 32-byte (x, n) records (default off: measured no gain)
     if (!strcmp(name, "nl_reuse")) {                             // hit lists between rebuilds: 0 off, 1 automatic (default), 2 on
         if (value != 0 && value != 1 && value != 2) return fail(ORBC_ERR_ARG, "nl_reuse must be 0, 1 or 2");
         c->nl_on = (int)value; c->nl_valid = false;

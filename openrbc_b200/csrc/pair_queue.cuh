@@ -116,21 +116,6 @@ __device__ __forceinline__ void ll_pair(const LLConst &k, F3 xi, F3 mi, float4 x
     tx = fmaf(B, dx, fmaf(-aua, nj.x, tx)); ty = fmaf(B, dy, fmaf(-aua, nj.y, ty)); tz = fmaf(B, dz, fmaf(-aua, nj.z, tz));
     sB = __fadd_rn(sB, B);
 }
-// Interleaved (x, n) records of the lipids, 32 B each: ONE 256-bit load (LDG.E.256) fetches a partner instead of two 128-bit loads
-// from two arrays.  A gather instruction touches 32 different sectors, one L1 wavefront each; the list walker does nothing but
-// gather, so halving its wavefronts is what counts (the searching kernel did not gain: it waits for its phase-1 loads).
-struct __align__(32) XN { float x, y, z, pad0, nx, ny, nz, pad1; };
-__device__ __forceinline__ void ldg256(const XN *p, float4 &a, float4 &b) {
-    asm("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-        : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
-}
-__global__ void k_pack_xn(const float4 *__restrict__ x, const float4 *__restrict__ n, size_t count, XN *__restrict__ xn) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= count) return;
-    const float4 a = x[i], b = n[i];
-    float4 *o = reinterpret_cast<float4 *>(xn + i);
-    o[0] = make_float4(a.x, a.y, a.z, 0.f); o[1] = make_float4(b.x, b.y, b.z, 0.f);
-}
 template <bool RECHECK>
 __device__ __forceinline__ void ll_eval(const LLConst &k, const float4 *__restrict__ xl, const float4 *__restrict__ nl, F3 xi, F3 mi, int j,
                                         float &fx, float &fy, float &fz, float &tx, float &ty, float &tz, float &sB) {
@@ -415,8 +400,10 @@ __global__ void __launch_bounds__(kLLBlock, MINB) k_pair_ll_r(PairArgs a, const 
 
 // The list walker: one thread per lipid, entries read coalesced, two partners in flight per lane.  An entry beyond the lane's
 // count is replaced by the lane's own slot (r2 = 0 fails the guards), which keeps the loop free of branches around the loads.
-template <int MINB, bool XNREC>
-__global__ void __launch_bounds__(kLLBlock, MINB) k_pair_ll_list(PairArgs a, const LLConst kc, const int *__restrict__ gate, int want, LLList nl, const XN *__restrict__ xn, unsigned *work) {
+// (Interleaved 32-byte (x, n) records, one 256-bit load per partner instead of two 128-bit loads, were measured and removed: 243 against
+// 238 us per launch -- the walker is limited by the bytes through the L1 data path, not by the number of requests.)
+template <int MINB>
+__global__ void __launch_bounds__(kLLBlock, MINB) k_pair_ll_list(PairArgs a, const LLConst kc, const int *__restrict__ gate, int want, LLList nl, unsigned *work) {
     if (gate && *gate != want) return;
     __shared__ unsigned s_piece;
     const float4 *__restrict__ xl = a.xl;
@@ -448,10 +435,7 @@ __global__ void __launch_bounds__(kLLBlock, MINB) k_pair_ll_list(PairArgs a, con
             #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 xj[u] = make_float4(xi.x, xi.y, xi.z, 0.f); nj[u] = xj[u];
-                if (j[u] >= 0) {
-                    if (XNREC) ldg256(xn + j[u], xj[u], nj[u]);
-                    else { xj[u] = __ldg(xl + j[u]); nj[u] = __ldg(nl_ + j[u]); }
-                }
+                if (j[u] >= 0) { xj[u] = __ldg(xl + j[u]); nj[u] = __ldg(nl_ + j[u]); }
             }
             #pragma unroll
             for (int u = 0; u < 4; ++u) ll_pair<true>(kc, xi, mi, xj[u], nj[u], fx, fy, fz, tx, ty, tz, sB);

@@ -35,7 +35,7 @@ for name, opts in (("run-list, search", dict(ll_variant=1, nl_reuse=0)), ("run-l
     msp, npr = sim.profile_read("pair_protein")
     sim.profile_enable(False)
     print(f"{name:30s}: pair_lipid {ms / n * 1e3:7.1f} us  pair_protein {msp / max(npr, 1) * 1e3:7.1f} us; max rel err vs the first {err:.2e}", flush=True)
-for name, opts in (("search", dict(ll_variant=1, nl_reuse=0)), ("hit lists", dict(ll_variant=1, nl_reuse=1, ll_xn=0))):
+for name, opts in (("search", dict(ll_variant=1, nl_reuse=0)), ("hit lists", dict(ll_variant=1, nl_reuse=1))):
     for k, v in opts.items():
         sim.set_option(k, v)
     sim.run_langevin(4); sim.synchronize()
