@@ -514,12 +514,13 @@ int cell_update_move(orbc_ctx *c, int which) {
         const unsigned nb = blocks_for(nc, kBlock);
         ORBC_LAUNCH(c, k_cell_totals, nb * mt, kBlock, 0, tt[0], tt[mt - 1], nb, nc, c->mg.rank, c->mg.world);
     }
+    if (which == kBothContainers) ORBC_TRY(scan_exclusive(c, c->sp[0].cell_start, nc, c->sp[1].cell_start));   // both cell_start arrays in one launch
+    else ORBC_TRY(scan_exclusive(c, c->sp[which >> 1].cell_start, nc));
     for (int sp = 0; sp < 2; ++sp) {
         if (!((which >> sp) & 1)) continue;
         Species &S = c->sp[sp];
         const int *cnt_me = nullptr, *off_me = nullptr;
         if (mg) { cnt_me = c->mg.cnt_all[sp] + (size_t)c->mg.rank * (nc + 1); off_me = c->mg.off_me[sp]; }
-        ORBC_TRY(scan_exclusive(c, S.cell_start, nc));
         if (S.n) {
             const int nx = S.cur ^ 1, nxn = S.cur_xn ^ 1;
             sc[m] = ScatterArgs{S.aff, S.li, c->d_range + 2 * sp, S.cell_start, off_me, S.cells_tmp};

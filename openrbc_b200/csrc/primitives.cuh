@@ -43,9 +43,12 @@ __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long
 __device__ __forceinline__ void st_release_u64(unsigned long long *p, unsigned long long v) {
     asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
 }
-__global__ void __launch_bounds__(kScanThreads) k_scan_onepass(int *__restrict__ data, int n, int n_tiles, unsigned long long *__restrict__ desc,
+// (data1: a second array of the same length scanned by the same launch -- blocks [n_tiles, 2 n_tiles) -- with its own descriptors
+// and tile counter behind those of the first)
+__global__ void __launch_bounds__(kScanThreads) k_scan_onepass(int *__restrict__ data, int *__restrict__ data1, int n, int n_tiles, unsigned long long *__restrict__ desc,
                                                                unsigned *__restrict__ counter, unsigned epoch) {
     __shared__ int s_tile, s_prefix;
+    if (data1 && (int)blockIdx.x >= n_tiles) { data = data1; desc += n_tiles; counter += 1; }
     if (threadIdx.x == 0) s_tile = (int)atomicAdd(counter, 1u);
     __syncthreads();
     const int tile = s_tile;
@@ -106,12 +109,12 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_onepass(int *__restrict__
     }
 }
 
-// counts in data[0..n) -> exclusive offsets in data[0..n], data[n] = total.
-inline int scan_exclusive(orbc_ctx *c, int *data, int n) {
+// counts in data[0..n) -> exclusive offsets in data[0..n], data[n] = total; data1 (optional): a second array of the same length
+inline int scan_exclusive(orbc_ctx *c, int *data, int n, int *data1 = nullptr) {
     if (n <= 0) return ORBC_OK;
     const int n_tiles = (n + kScanTile - 1) / kScanTile;
-    // descriptors (2 ints each) + the tile counter live in scan_tmp; a new buffer starts zeroed (epoch 0 is never used)
-    const size_t need = 2 * (size_t)n_tiles + 4;
+    // the two tile counters + descriptors (2 ints each, two sets) live in scan_tmp; a new buffer starts zeroed (epoch 0 is never used)
+    const size_t need = 4 * (size_t)n_tiles + 4;
     if (c->scan_tmp_cap < need) {
         const size_t cap = need < 65540 ? 65540 : need;
         ORBC_TRY(dev_alloc(&c->scan_tmp, cap)); c->scan_tmp_cap = cap;
@@ -124,7 +127,7 @@ inline int scan_exclusive(orbc_ctx *c, int *data, int n) {
     }
     unsigned *counter = (unsigned *)c->scan_tmp;
     unsigned long long *desc = (unsigned long long *)(c->scan_tmp + 2);
-    ORBC_LAUNCH(c, k_scan_onepass, n_tiles, kScanThreads, 0, data, n, n_tiles, desc, counter, c->scan_epoch);
+    ORBC_LAUNCH(c, k_scan_onepass, data1 ? 2 * n_tiles : n_tiles, kScanThreads, 0, data, data1, n, n_tiles, desc, counter, c->scan_epoch);
     return ORBC_OK;
 }
 
