@@ -294,6 +294,39 @@ __device__ __forceinline__ bool next_piece(unsigned *work, unsigned *s_piece, un
 struct LLList { int *list; int *cnt; int cap; NlState *st; };
 __device__ __forceinline__ size_t ll_row(int i, int cap) { return ((size_t)(i >> 6) * cap) * 64 + (i & 63); }
 
+// Phase 2 of the searching kernels: the lane's queue of hits, two at a time -- both partners' x and n are gathered before the first
+// force body starts, so the second pair's loads fly under the first pair's arithmetic (the bodies run in queue order: same sums).
+__device__ __forceinline__ void ll_drain(const LLConst &kc, const float4 *__restrict__ xl, const float4 *__restrict__ nl_, F3 xi, F3 mi, unsigned q0, unsigned qp,
+                                         float &fx, float &fy, float &fz, float &tx, float &ty, float &tz, float &sB) {
+    for (unsigned e = q0; e < qp; e += 256) {
+        const bool two = e + 128 < qp;
+        const int j0 = lds_i32(e), j1 = two ? lds_i32(e + 128) : j0;
+        const float4 x0 = __ldg(xl + j0), x1 = __ldg(xl + j1), n0 = __ldg(nl_ + j0), n1 = __ldg(nl_ + j1);
+        ll_pair<false>(kc, xi, mi, x0, n0, fx, fy, fz, tx, ty, tz, sB);
+        if (two) ll_pair<false>(kc, xi, mi, x1, n1, fx, fy, fz, tx, ty, tz, sB);
+    }
+}
+// The same while recording: the warp's lanes write the same row index (the longest queue decides, `len`; shorter queues are padded
+// with the lane's own slot, which fails the guards and costs no gather): one coalesced 128-byte store per entry instead of 32 sectors.
+__device__ __forceinline__ void ll_drain_record(const LLConst &kc, const float4 *__restrict__ xl, const float4 *__restrict__ nl_, F3 xi, F3 mi, unsigned q0, unsigned qp,
+                                                unsigned len, int self, bool live, int *__restrict__ row, int cap, int &total,
+                                                float &fx, float &fy, float &fz, float &tx, float &ty, float &tz, float &sB) {
+    const unsigned mine = qp - q0;
+    const float4 own = make_float4(xi.x, xi.y, xi.z, 0.f);
+    for (unsigned off = 0; off < len; off += 256) {
+        const bool h0 = off < mine, h1 = off + 128 < mine, second = off + 128 < len;
+        const int j0 = h0 ? lds_i32(q0 + off) : self, j1 = h1 ? lds_i32(q0 + off + 128) : self;
+        if (live && total < cap) row[(size_t)total * 64] = j0;
+        ++total;
+        if (second) { if (live && total < cap) row[(size_t)total * 64] = j1; ++total; }
+        float4 x0 = own, x1 = own, n0 = own, n1 = own;
+        if (h0) { x0 = __ldg(xl + j0); n0 = __ldg(nl_ + j0); }
+        if (h1) { x1 = __ldg(xl + j1); n1 = __ldg(nl_ + j1); }
+        if (h0) ll_pair<true>(kc, xi, mi, x0, n0, fx, fy, fz, tx, ty, tz, sB);
+        if (h1) ll_pair<true>(kc, xi, mi, x1, n1, fx, fy, fz, tx, ty, tz, sB);
+    }
+}
+
 // W = candidates per lane and iteration.  Measured on the full RBC (B200): W = 4 with 20 resident blocks 470 us; W = 8 505-515 us
 // (longer partial groups, 64 registers); 24 resident blocks at 40 registers 538 us (spills); an L1 prefetch 4-16 candidates ahead
 // of the stream changes nothing.  Round 2 (profiles/r02_*): partners gathered as interleaved 32-byte (x, n) records with one
@@ -302,7 +335,10 @@ __device__ __forceinline__ size_t ll_row(int i, int cap) { return ((size_t)(i >>
 // BUILD: also record the hit lists (window 0 <= r2 < (cut + skin)^2, exact guards at evaluation).  `gate`/`want`: run only if
 // *gate == want (the list walker and this kernel are launched together on steps without a rebuild; one of them returns at once).
 // The grid may be smaller than the number of 64-lipid groups (grid-stride), so that a gated launch that returns costs nothing.
-template <int MINB, int W, bool BUILD>
+// BATCH: phase 2 takes two hits at a time (ll_drain*).  It pays where the registers are there anyway -- the recording kernel, 64
+// registers at 16 blocks per SM: 587 -> 528 us -- and not in the plain search (48 registers at 20 blocks: 457 us; batched it spills
+// at 20 blocks, 500 us, and runs at 465 / 467 us with 16 / 18 blocks).
+template <int MINB, int W, bool BUILD, bool BATCH = BUILD>
 __global__ void __launch_bounds__(kLLBlock, MINB) k_pair_ll_r(PairArgs a, const LLConst kc, const int2 *__restrict__ lruns, const int *__restrict__ lrun_info,
                                                                const int *__restrict__ gate, int want, LLList nl, float skin, unsigned *work) {
     if (gate && *gate != want) return;
@@ -354,15 +390,10 @@ __global__ void __launch_bounds__(kLLBlock, MINB) k_pair_ll_r(PairArgs a, const 
                     // recording: the warp's lanes write the same row index (the longest queue decides, shorter ones are padded with
                     // the lane's own slot, which fails the guards): one coalesced 128-byte store per entry instead of 32 sectors
                     const unsigned len = __reduce_max_sync(0xffffffffu, qp - q0);
-                    for (unsigned off = 0; off < len; off += 128) {
-                        const bool have = off < qp - q0;
-                        const int j = have ? lds_i32(q0 + off) : self;
-                        if (live && total < nl.cap) row[(size_t)total * 64] = j;
-                        ++total;
-                        if (have) ll_eval<true>(kc, xl, nl_, xi, mi, j, fx, fy, fz, tx, ty, tz, sB);   // (a padding entry costs no gather)
-                    }
+                    ll_drain_record(kc, xl, nl_, xi, mi, q0, qp, len, self, live, row, nl.cap, total, fx, fy, fz, tx, ty, tz, sB);
                 } else
-                    for (unsigned e = q0; e < qp; e += 128) ll_eval<false>(kc, xl, nl_, xi, mi, lds_i32(e), fx, fy, fz, tx, ty, tz, sB);
+                    if (BATCH) ll_drain(kc, xl, nl_, xi, mi, q0, qp, fx, fy, fz, tx, ty, tz, sB);
+                    else for (unsigned e = q0; e < qp; e += 128) ll_eval<false>(kc, xl, nl_, xi, mi, lds_i32(e), fx, fy, fz, tx, ty, tz, sB);
                 qp = q0;
             }
             const float4 *__restrict__ p = xl + cur;
@@ -380,15 +411,10 @@ __global__ void __launch_bounds__(kLLBlock, MINB) k_pair_ll_r(PairArgs a, const 
         }
         if (BUILD) {
             const unsigned len = __reduce_max_sync(0xffffffffu, qp - q0);
-            for (unsigned off = 0; off < len; off += 128) {
-                const bool have = off < qp - q0;
-                const int j = have ? lds_i32(q0 + off) : self;
-                if (live && total < nl.cap) row[(size_t)total * 64] = j;
-                ++total;
-                if (have) ll_eval<true>(kc, xl, nl_, xi, mi, j, fx, fy, fz, tx, ty, tz, sB);
-            }
+            ll_drain_record(kc, xl, nl_, xi, mi, q0, qp, len, self, live, row, nl.cap, total, fx, fy, fz, tx, ty, tz, sB);
         } else
-            for (unsigned e = q0; e < qp; e += 128) ll_eval<false>(kc, xl, nl_, xi, mi, lds_i32(e), fx, fy, fz, tx, ty, tz, sB);
+            if (BATCH) ll_drain(kc, xl, nl_, xi, mi, q0, qp, fx, fy, fz, tx, ty, tz, sB);
+            else for (unsigned e = q0; e < qp; e += 128) ll_eval<false>(kc, xl, nl_, xi, mi, lds_i32(e), fx, fy, fz, tx, ty, tz, sB);
         if (BUILD && live) {
             nl.cnt[i] = min(total, nl.cap);
             if (total > nl.cap) atomicExch(&nl.st->overflow, 1);
