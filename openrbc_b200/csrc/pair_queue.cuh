@@ -294,19 +294,9 @@ __device__ __forceinline__ bool next_piece(unsigned *work, unsigned *s_piece, un
 struct LLList { int *list; int *cnt; int cap; NlState *st; };
 __device__ __forceinline__ size_t ll_row(int i, int cap) { return ((size_t)(i >> 6) * cap) * 64 + (i & 63); }
 
-// Phase 2 of the searching kernels: the lane's queue of hits, two at a time -- both partners' x and n are gathered before the first
-// force body starts, so the second pair's loads fly under the first pair's arithmetic (the bodies run in queue order: same sums).
-__device__ __forceinline__ void ll_drain(const LLConst &kc, const float4 *__restrict__ xl, const float4 *__restrict__ nl_, F3 xi, F3 mi, unsigned q0, unsigned qp,
-                                         float &fx, float &fy, float &fz, float &tx, float &ty, float &tz, float &sB) {
-    for (unsigned e = q0; e < qp; e += 256) {
-        const bool two = e + 128 < qp;
-        const int j0 = lds_i32(e), j1 = two ? lds_i32(e + 128) : j0;
-        const float4 x0 = __ldg(xl + j0), x1 = __ldg(xl + j1), n0 = __ldg(nl_ + j0), n1 = __ldg(nl_ + j1);
-        ll_pair<false>(kc, xi, mi, x0, n0, fx, fy, fz, tx, ty, tz, sB);
-        if (two) ll_pair<false>(kc, xi, mi, x1, n1, fx, fy, fz, tx, ty, tz, sB);
-    }
-}
-// The same while recording: the warp's lanes write the same row index (the longest queue decides, `len`; shorter queues are padded
+// Phase 2 of the recording kernel: the lane's queue of hits, two at a time -- both partners' x and n are gathered before the first force
+// body starts, so the second pair's loads fly under the first pair's arithmetic (the bodies run in queue order: same sums).  The
+// warp's lanes write the same row index (the longest queue decides, `len`; shorter queues are padded
 // with the lane's own slot, which fails the guards and costs no gather): one coalesced 128-byte store per entry instead of 32 sectors.
 __device__ __forceinline__ void ll_drain_record(const LLConst &kc, const float4 *__restrict__ xl, const float4 *__restrict__ nl_, F3 xi, F3 mi, unsigned q0, unsigned qp,
                                                 unsigned len, int self, bool live, int *__restrict__ row, int cap, int &total,
@@ -335,10 +325,10 @@ __device__ __forceinline__ void ll_drain_record(const LLConst &kc, const float4 
 // BUILD: also record the hit lists (window 0 <= r2 < (cut + skin)^2, exact guards at evaluation).  `gate`/`want`: run only if
 // *gate == want (the list walker and this kernel are launched together on steps without a rebuild; one of them returns at once).
 // The grid may be smaller than the number of 64-lipid groups (grid-stride), so that a gated launch that returns costs nothing.
-// BATCH: phase 2 takes two hits at a time (ll_drain*).  It pays where the registers are there anyway -- the recording kernel, 64
-// registers at 16 blocks per SM: 587 -> 528 us -- and not in the plain search (48 registers at 20 blocks: 457 us; batched it spills
-// at 20 blocks, 500 us, and runs at 465 / 467 us with 16 / 18 blocks).
-template <int MINB, int W, bool BUILD, bool BATCH = BUILD>
+// (Two hits at a time in phase 2 -- ll_drain_record -- pays where the registers are there anyway: the recording kernel, 64 registers at 16
+// blocks per SM, 587 -> 528 us.  The plain search stays one at a time: 48 registers at 20 blocks, 457 us; two at a time it spills at 20
+// blocks, 500 us, and runs at 465 / 467 us with 16 / 18 blocks; a depth-one software pipeline of the gathers: 460 us.)
+template <int MINB, int W, bool BUILD>
 __global__ void __launch_bounds__(kLLBlock, MINB) k_pair_ll_r(PairArgs a, const LLConst kc, const int2 *__restrict__ lruns, const int *__restrict__ lrun_info,
                                                                const int *__restrict__ gate, int want, LLList nl, float skin, unsigned *work) {
     if (gate && *gate != want) return;
@@ -392,8 +382,7 @@ __global__ void __launch_bounds__(kLLBlock, MINB) k_pair_ll_r(PairArgs a, const 
                     const unsigned len = __reduce_max_sync(0xffffffffu, qp - q0);
                     ll_drain_record(kc, xl, nl_, xi, mi, q0, qp, len, self, live, row, nl.cap, total, fx, fy, fz, tx, ty, tz, sB);
                 } else
-                    if (BATCH) ll_drain(kc, xl, nl_, xi, mi, q0, qp, fx, fy, fz, tx, ty, tz, sB);
-                    else for (unsigned e = q0; e < qp; e += 128) ll_eval<false>(kc, xl, nl_, xi, mi, lds_i32(e), fx, fy, fz, tx, ty, tz, sB);
+                    for (unsigned e = q0; e < qp; e += 128) ll_eval<false>(kc, xl, nl_, xi, mi, lds_i32(e), fx, fy, fz, tx, ty, tz, sB);
                 qp = q0;
             }
             const float4 *__restrict__ p = xl + cur;
@@ -413,8 +402,7 @@ __global__ void __launch_bounds__(kLLBlock, MINB) k_pair_ll_r(PairArgs a, const 
             const unsigned len = __reduce_max_sync(0xffffffffu, qp - q0);
             ll_drain_record(kc, xl, nl_, xi, mi, q0, qp, len, self, live, row, nl.cap, total, fx, fy, fz, tx, ty, tz, sB);
         } else
-            if (BATCH) ll_drain(kc, xl, nl_, xi, mi, q0, qp, fx, fy, fz, tx, ty, tz, sB);
-            else for (unsigned e = q0; e < qp; e += 128) ll_eval<false>(kc, xl, nl_, xi, mi, lds_i32(e), fx, fy, fz, tx, ty, tz, sB);
+            for (unsigned e = q0; e < qp; e += 128) ll_eval<false>(kc, xl, nl_, xi, mi, lds_i32(e), fx, fy, fz, tx, ty, tz, sB);
         if (BUILD && live) {
             nl.cnt[i] = min(total, nl.cap);
             if (total > nl.cap) atomicExch(&nl.st->overflow, 1);
