@@ -297,7 +297,8 @@ def alu_roofline(prof, counts, world):
            "pairs": {"ll_tests": t_ll, "ll_hits_one_sided": h_ll, "pl_tests": t_pl, "pl_hits": h_pl, "pp_tests": t_pp, "pp_hits_one_sided": h_pp},
            "gflop_executed": executed / 1e9, "gflop_algorithmic": algorithmic / 1e9,
            "achieved_executed": executed / sec / 1e12 if sec else None, "achieved_algorithmic": algorithmic / sec / 1e12 if sec else None,
-           "ncu": "profiles/r02_runlist_kernel_ncu.txt (k_pair_ll_r: sm__throughput 63 %, fma pipe 34 %, alu pipe 38 %, issue active 64 %), profiles/r02_list_walker_ncu.txt, profiles/r01_v4_pair_ncu.txt (k_pair_prot)"}
+           "ncu": "profiles/r02_search_kernel_ncu.txt (sm__throughput 63 %, fma pipe 34 %, alu pipe 38 %, issue active 65 %), profiles/r02_record_kernel_ncu.txt (issue 68 %), "
+                  "profiles/r02_list_walker_ncu.txt (issue 69 %, fma pipe 43 %), profiles/r02_prot_search_ncu.txt (issue 50 %), profiles/r02_prot_walker_ncu.txt (issue 18 %)"}
     if peak and sec:
         out["frac_executed"] = out["achieved_executed"] / peak; out["frac_algorithmic"] = out["achieved_algorithmic"] / peak
     return out
