@@ -207,6 +207,7 @@ __global__ void k_lipid_runs(int cb, int ce, const int *__restrict__ stencil, co
 // step (NlState::disp), k_nl_gate adds them up and orders a fresh build when 2 x (sum of maxima) exceeds the skin.  Same hits,
 // same order of evaluation per lipid: the forces are bit-identical to an evaluation without lists.
 // Layout: groups of 64 consecutive lipid slots, [group][entry][64] (coalesced for the thread-per-lipid readers), `cap` entries.
+constexpr int kNlBackoffMax = 3;    // rebuilds to sit out, at most, after a recording that was never walked
 struct NlState {                    // one per context, in device memory
     unsigned disp[64];              // largest squared displacement of a particle in the integration steps since the last gate (float bits)
     float accum;                    // sum of the per-step maxima since the lists were recorded
@@ -222,7 +223,7 @@ struct NlState {                    // one per context, in device memory
 // The decision, once per force evaluation (one warp).  `force`: the partition has changed since the last evaluation (host's knowledge).
 //   after a rebuild   record, if the step just seen fits the skin -- unless lists were lately recorded and never walked (recording
 //                     costs ~25 % on top of a search and pays only if at least two of five recordings are walked): then sit out
-//                     1, 3, 7, 15 rebuilds (doubling with every such failure, halving with every recording that was walked)
+//                     1, then 3 rebuilds (kNlBackoffMax; halving with every recording that was walked)
 //   otherwise         walk, if lists exist and 2 x (sum of the per-step maxima since the recording) <= skin; search if not
 // `shared` (decomposed run): the per-rank maxima of the last integration step, published by k_nl_share into every rank's table
 // (the barrier behind the halo push stands between the two kernels): every rank takes the same maximum and decides alike.
@@ -248,7 +249,7 @@ __global__ void k_nl_gate(NlState *st, int force, int fixed_mode, int moves, flo
             if (2.0f * acc <= skin) { mode = 0; st->accum = acc; if (st->used++ == 0) st->backoff >>= 1; }
             else {
                 mode = 2; st->valid = 0;
-                if (st->used == 0) { st->backoff = min(2 * st->backoff + 1, 15); st->wait = st->backoff; }   // recorded for nothing
+                if (st->used == 0) { st->backoff = min(2 * st->backoff + 1, kNlBackoffMax); st->wait = st->backoff; }   // recorded for nothing
             }
         }
         if (mode == 0) st->reuses++; else if (mode == 1) st->builds++; else st->searches++;
