@@ -101,7 +101,8 @@ ORBC_API int  orbc_set_stream(orbc_ctx *ctx, void *cuda_stream);
  *                 walks, records or just searches (a recording that would not be walked is not made).  0 = every evaluation
  *                 searches the stencils.  On a decomposed context the ranks exchange their displacement bounds and decide alike;
  *                 there the default means "up to two ranks" (measured: the lists lose with 8 ranks), 2 = on for every world size.
- *   "nl_skin"     the skin of those lists, default 0.1
+ *   "nl_skin", "nl_skin_max"  the skin of those lists: at least nl_skin (default 0.1); the gate thickens it up to nl_skin_max (default 0.3)
+ *                 when the fastest particle of the last step would outrun the thinner one
  *   "stencil_refresh"  1 (default) = rebuilds that keep the cell numbering re-classify the recorded r < 9 + 1 neighbours of every cell
  *                 instead of searching the centroid grid (cells whose centroid jumped are searched in full; same stencils); 0 = always search
  *   "prot_lanes"  lanes per protein of the protein kernel (0 = automatic); debug_*: test aids */

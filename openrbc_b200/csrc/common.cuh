@@ -171,7 +171,7 @@ struct orbc_ctx {
     // hit lists with a skin (pair_queue.cuh): recorded by the force evaluation after a rebuild, walked until the next one
     int nl_on = 1;                                 // option "nl_reuse": 0 off, 1 automatic, 2 on
     bool nl_valid = false;                         // lists match the current partition and were built (host's view)
-    float nl_skin = 0.1f;                          // option "nl_skin"
+    float nl_skin = 0.1f, nl_skin_max = 0.3f;      // options "nl_skin", "nl_skin_max": the gate picks the skin of a recording between them
     int nl_moves = 0;                              // tracked integration steps since the last gate
     void *nl_state = nullptr;                      // orbc::NlState on the device
     int *ll_list = nullptr, *ll_cnt = nullptr; size_t ll_list_lipids = 0;

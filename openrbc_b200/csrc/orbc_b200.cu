@@ -358,7 +358,7 @@ int launch_pairwise(orbc_ctx *c, bool accumulate = true) {
         host_build = !c->nl_valid;
         if (mg && c->nl_moves > 1) host_build = true;             // (the ranks exchange the bound of ONE step)
         if (c->nl_debug_mode > 0) host_build = true;
-        ORBC_LAUNCH(c, k_nl_gate, 1, 32, 0, nls, host_build ? 1 : 0, c->nl_debug_mode, c->nl_moves, c->nl_skin,
+        ORBC_LAUNCH(c, k_nl_gate, 1, 32, 0, nls, host_build ? 1 : 0, c->nl_debug_mode, c->nl_moves, c->nl_skin, c->nl_skin_max,
                     mg ? (const unsigned *)(c->mg.flags + kMaxWorld * (1 + c->mg.disp_par)) : (const unsigned *)nullptr, mg ? c->mg.world : 1);
         c->nl_moves = 0; c->nl_valid = true;
     }
@@ -380,9 +380,9 @@ int launch_pairwise(orbc_ctx *c, bool accumulate = true) {
                 // warp-per-cell tile kernel; the thread-per-lipid kernel takes the step when a cell does not fit the tile (device flag)
                 const unsigned warps = blocks_for((size_t)(a.ce - a.cb), kTileCells);
                 ORBC_LAUNCH(c, k_pair_ll_t, blocks_for(warps, kTileWarps), kTileWarps * 32, kTileWarps * kTileBytes, a, kc, c->lruns, c->lrun_cnt, c->tile_overflow);
-                ORBC_LAUNCH(c, (k_pair_ll_r<20, 4, false>), kSmallGrid, kLLBlock, 0, a, kc, c->lruns, c->lrun_cnt, c->tile_overflow, 1, LLList{}, 0.f, (unsigned *)nullptr);
+                ORBC_LAUNCH(c, (k_pair_ll_r<20, 4, false>), kSmallGrid, kLLBlock, 0, a, kc, c->lruns, c->lrun_cnt, c->tile_overflow, 1, LLList{}, (unsigned *)nullptr);
             } else if (!nl) {
-                ORBC_LAUNCH(c, (k_pair_ll_r<20, 4, false>), blocks_for(nl_count, kLLBlock), kLLBlock, 0, a, kc, c->lruns, c->lrun_cnt, (const int *)nullptr, 0, LLList{}, 0.f, (unsigned *)nullptr);
+                ORBC_LAUNCH(c, (k_pair_ll_r<20, 4, false>), blocks_for(nl_count, kLLBlock), kLLBlock, 0, a, kc, c->lruns, c->lrun_cnt, (const int *)nullptr, 0, LLList{}, (unsigned *)nullptr);
             } else {
                 // hit lists: the device decides (k_nl_gate) whether this evaluation walks the lists, searches and records them, or just
                 // searches; the candidates are launched over a grid that fills the GPU once (their blocks draw 64-lipid groups from a
@@ -393,8 +393,8 @@ int launch_pairwise(orbc_ctx *c, bool accumulate = true) {
                 // (what the host knows: after a change of the partition the gate never orders a walk, and otherwise never a recording)
                 if (!host_build) {
                     ORBC_LAUNCH(c, k_pair_ll_list<16>, g16, kLLBlock, 0, a, kc, &nls->need, 0, ll, nls->work + 0);
-                } else ORBC_LAUNCH(c, (k_pair_ll_r<16, 4, true>), g16, kLLBlock, 0, a, kc, c->lruns, c->lrun_cnt, &nls->need, 1, ll, c->nl_skin, nls->work + 1);
-                ORBC_LAUNCH(c, (k_pair_ll_r<20, 4, false>), g20, kLLBlock, 0, a, kc, c->lruns, c->lrun_cnt, &nls->need, 2, LLList{}, 0.f, nls->work + 2);
+                } else ORBC_LAUNCH(c, (k_pair_ll_r<16, 4, true>), g16, kLLBlock, 0, a, kc, c->lruns, c->lrun_cnt, &nls->need, 1, ll, nls->work + 1);
+                ORBC_LAUNCH(c, (k_pair_ll_r<20, 4, false>), g20, kLLBlock, 0, a, kc, c->lruns, c->lrun_cnt, &nls->need, 2, LLList{}, nls->work + 2);
             }
         }
         // (decomposed: the lipid side of the protein-lipid pairs whose protein lives on another rank is the epilogue of the lipid kernels)
@@ -410,15 +410,15 @@ int launch_pairwise(orbc_ctx *c, bool accumulate = true) {
             const unsigned pieces = blocks_for(np * lanes, kPBlock);
 #define ORBC_PROT3(LPP) do { \
                 if (!host_build) ORBC_LAUNCH(c, k_pair_prot_list<LPP>, pieces, kPBlock, 0, a, c->porder, &nls->need, 0, pls); \
-                else ORBC_LAUNCH(c, (k_pair_prot<LPP, true>), pieces, kPBlock, 0, a, c->lbound, c->pbound, ct, c->porder, &nls->need, 1, pls, c->nl_skin); \
-                ORBC_LAUNCH(c, (k_pair_prot<LPP, false>), pieces, kPBlock, 0, a, c->lbound, c->pbound, ct, c->porder, &nls->need, 2, pls, 0.f); } while (0)
+                else ORBC_LAUNCH(c, (k_pair_prot<LPP, true>), pieces, kPBlock, 0, a, c->lbound, c->pbound, ct, c->porder, &nls->need, 1, pls); \
+                ORBC_LAUNCH(c, (k_pair_prot<LPP, false>), pieces, kPBlock, 0, a, c->lbound, c->pbound, ct, c->porder, &nls->need, 2, pls); } while (0)
             if (lanes == 4) ORBC_PROT3(4); else if (lanes == 2) ORBC_PROT3(2); else ORBC_PROT3(1);
 #undef ORBC_PROT3
         } else {
             const unsigned grid = blocks_for(np * lanes, kPBlock);
-            if (lanes == 4) ORBC_LAUNCH(c, (k_pair_prot<4, false>), grid, kPBlock, 0, a, c->lbound, c->pbound, ct, c->porder, (const int *)nullptr, 0, pls, 0.f);
-            else if (lanes == 2) ORBC_LAUNCH(c, (k_pair_prot<2, false>), grid, kPBlock, 0, a, c->lbound, c->pbound, ct, c->porder, (const int *)nullptr, 0, pls, 0.f);
-            else ORBC_LAUNCH(c, (k_pair_prot<1, false>), grid, kPBlock, 0, a, c->lbound, c->pbound, ct, c->porder, (const int *)nullptr, 0, pls, 0.f);
+            if (lanes == 4) ORBC_LAUNCH(c, (k_pair_prot<4, false>), grid, kPBlock, 0, a, c->lbound, c->pbound, ct, c->porder, (const int *)nullptr, 0, pls);
+            else if (lanes == 2) ORBC_LAUNCH(c, (k_pair_prot<2, false>), grid, kPBlock, 0, a, c->lbound, c->pbound, ct, c->porder, (const int *)nullptr, 0, pls);
+            else ORBC_LAUNCH(c, (k_pair_prot<1, false>), grid, kPBlock, 0, a, c->lbound, c->pbound, ct, c->porder, (const int *)nullptr, 0, pls);
         }
     }
     return ORBC_OK;
@@ -815,6 +815,10 @@ int orbc_set_option(orbc_ctx *c, const char *name, double value) { if (c) cudaSe
         c->nl_on = (int)value; c->nl_valid = false;
         if (mg_active(c) && c->mg.connected && nl_active(c)) ORBC_TRY(nl_ensure(c));   // (not at the first launch, while peers may wait in a barrier)
         return ORBC_OK;
+    }
+    if (!strcmp(name, "nl_skin_max")) {
+        if (!(value >= 0.0 && value <= 1.0)) return fail(ORBC_ERR_ARG, "nl_skin_max must be in [0, 1]");
+        c->nl_skin_max = (float)value; c->nl_valid = false; return ORBC_OK;
     }
     if (!strcmp(name, "nl_skin")) {
         if (!(value >= 0.0 && value <= 1.0)) return fail(ORBC_ERR_ARG, "nl_skin must be in [0, 1]");

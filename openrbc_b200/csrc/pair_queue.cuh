@@ -217,17 +217,20 @@ struct NlState {                    // one per context, in device memory
     int valid;                      // lists were recorded for the current partition
     float d_last;                   // the largest single-step displacement seen last
     unsigned searches;              // statistics: evaluations that searched without recording
+    float skin;                     // the skin of the current lists (chosen by the gate at the recording, between the option's value and its ceiling)
     int used, backoff, wait;        // walks of the current lists; rebuilds to sit out after lists that were never walked (doubles, halves)
     unsigned work[8];               // tickets of the gated kernels of this evaluation (next_piece), zeroed by the gate
 };
 // The decision, once per force evaluation (one warp).  `force`: the partition has changed since the last evaluation (host's knowledge).
-//   after a rebuild   record, if the step just seen fits the skin -- unless lists were lately recorded and never walked (recording
-//                     costs ~25 % on top of a search and pays only if at least two of five recordings are walked): then sit out
+//   after a rebuild   record, with a skin that leaves room for a step 25 % longer than the one just seen (at least the option's skin;
+//                     a system with a few fast particles gets thicker lists instead of none), if that skin stays under the ceiling
+//                     (skin_max: lists grow with the cube of cutoff + skin) -- unless lists were lately recorded and never walked
+//                     (recording costs ~16 % on top of a search and pays if one of three recordings is walked): then sit out
 //                     1, then 3 rebuilds (kNlBackoffMax; halving with every recording that was walked)
-//   otherwise         walk, if lists exist and 2 x (sum of the per-step maxima since the recording) <= skin; search if not
+//   otherwise         walk, if lists exist and 2 x (sum of the per-step maxima since the recording) <= their skin; search if not
 // `shared` (decomposed run): the per-rank maxima of the last integration step, published by k_nl_share into every rank's table
 // (the barrier behind the halo push stands between the two kernels): every rank takes the same maximum and decides alike.
-__global__ void k_nl_gate(NlState *st, int force, int fixed_mode, int moves, float skin, const unsigned *__restrict__ shared, int world) {
+__global__ void k_nl_gate(NlState *st, int force, int fixed_mode, int moves, float skin_min, float skin_max, const unsigned *__restrict__ shared, int world) {
     const int lane = threadIdx.x;
     unsigned m;
     if (shared) m = lane < world ? shared[lane] : 0u;
@@ -239,14 +242,16 @@ __global__ void k_nl_gate(NlState *st, int force, int fixed_mode, int moves, flo
         if (moves > 0) st->d_last = d;
         int mode;
         if (force) {
+            const float skin = fmaxf(skin_min, 2.5f * st->d_last);
+            st->skin = fminf(skin, fmaxf(skin_min, skin_max));
             if (fixed_mode > 0) mode = fixed_mode;               // (measurement aid)
             else if (st->wait > 0) { st->wait--; mode = 2; }
-            else mode = (2.0f * st->d_last <= skin) ? 1 : 2;
+            else mode = skin <= st->skin ? 1 : 2;
             st->valid = mode == 1; st->accum = 0.f; st->overflow = 0; st->used = 0;
         } else if (!st->valid || st->overflow) { mode = 2; st->valid = 0; }
         else {
             const float acc = st->accum + (float)moves * d;
-            if (2.0f * acc <= skin) { mode = 0; st->accum = acc; if (st->used++ == 0) st->backoff >>= 1; }
+            if (2.0f * acc <= st->skin) { mode = 0; st->accum = acc; if (st->used++ == 0) st->backoff >>= 1; }
             else {
                 mode = 2; st->valid = 0;
                 if (st->used == 0) { st->backoff = min(2 * st->backoff + 1, kNlBackoffMax); st->wait = st->backoff; }   // recorded for nothing
@@ -331,8 +336,9 @@ __device__ __forceinline__ void ll_drain_record(const LLConst &kc, const float4 
 // blocks, 500 us, and runs at 465 / 467 us with 16 / 18 blocks; a depth-one software pipeline of the gathers: 460 us.)
 template <int MINB, int W, bool BUILD>
 __global__ void __launch_bounds__(kLLBlock, MINB) k_pair_ll_r(PairArgs a, const LLConst kc, const int2 *__restrict__ lruns, const int *__restrict__ lrun_info,
-                                                               const int *__restrict__ gate, int want, LLList nl, float skin, unsigned *work) {
+                                                               const int *__restrict__ gate, int want, LLList nl, unsigned *work) {
     if (gate && *gate != want) return;
+    const float skin = BUILD ? nl.st->skin : 0.f;                // (the gate's choice for this recording)
     __shared__ unsigned s_piece;
     __shared__ int s_q[kLLBlock / 32][kQCap * 32];
     const int lane = threadIdx.x & 31;
@@ -539,8 +545,9 @@ __device__ __forceinline__ void pp_pair(int type1, F3 xi, float4 xj, const float
 // + skin and every protein closer than the pair's range + skin (the hit lists of k_pair_prot_list, see the lipid kernels above).
 template <int LPP, bool BUILD>
 __global__ void __launch_bounds__(kPBlock, 16) k_pair_prot(PairArgs a, const float4 *__restrict__ lbound, const float4 *__restrict__ pbound, CullTable ct,
-                                                             const int *__restrict__ porder, const int *__restrict__ gate, int want, PLists nl, float skin) {
+                                                             const int *__restrict__ porder, const int *__restrict__ gate, int want, PLists nl) {
     if (gate && *gate != want) return;
+    const float skin = BUILD ? nl.st->skin : 0.f;                // (the gate's choice for this recording)
     __shared__ float s_cutsqpp[36], s_ljcutsq[36], s_recsq[36];
     __shared__ int s_jb[2][kPBlock / 32][kRangeCap * 32];
     __shared__ unsigned short s_len[2][kPBlock / 32][kRangeCap * 32];

@@ -48,9 +48,9 @@ def test_lists_do_not_change_the_trajectory(name):
                 np.testing.assert_array_equal(got[s][f], ref[s][f], err_msg=f)
             else:
                 assert rel_err(got[s][f], ref[s][f]) < 1e-5, (s, f)
-    # a skin thinner than twice the largest step: the gate never walks -- and does not bother to record either: every evaluation is a
+    # a skin thinner than twice the largest step (and no leave to thicken it): the gate never walks -- and does not bother to record either: every evaluation is a
     # plain search (the fourth counter), and nothing changes
-    thin, s2 = run(st, steps, dt, nl_reuse=1, nl_skin=1e-7)
+    thin, s2 = run(st, steps, dt, nl_reuse=1, nl_skin=1e-7, nl_skin_max=1e-7)
     assert s2[0] <= 1 and s2[1] == 0 and s2[0] + s2[3] == steps, s2      # (the very first evaluation has seen no step yet)
     for s in (0, 1):
         for f in "xvno":
@@ -82,3 +82,18 @@ def test_lists_call_by_call_and_forces():
     assert list(a.dump("nl_stats")[:2]) == [2, 1]
     assert rel_err(a.get(0, "f"), b.get(0, "f")) < 1e-6
     a.close(); b.close()
+
+
+def test_gate_thickens_the_skin_for_a_hot_system():
+    """The fastest particles of the freshly initialised sphere outrun a skin of 0.002 even with a tenth of the production time step;
+    allowed up to 0.3 the gate records thicker lists and walks them -- and the trajectory is still the one of the plain search."""
+    st = load("sphere_r12")
+    ref, _ = run(st, 10, 1e-3, nl_reuse=0)
+    thin, s_thin = run(st, 10, 1e-3, nl_reuse=1, nl_skin=0.002, nl_skin_max=0.002)
+    thick, s_thick = run(st, 10, 1e-3, nl_reuse=1, nl_skin=0.002, nl_skin_max=0.3)
+    assert s_thick[1] > s_thin[1], (s_thin, s_thick)
+    assert s_thick[2] == 0
+    for got in (thin, thick):
+        for s in (0, 1):
+            for f in "xvno":
+                np.testing.assert_array_equal(got[s][f], ref[s][f], err_msg=f)
