@@ -100,7 +100,7 @@ ORBC_API int  orbc_set_stream(orbc_ctx *ctx, void *cuda_stream);
  *                 the displacements guards the skin: same hits, same forces).  The device decides at every evaluation whether it
  *                 walks, records or just searches (a recording that would not be walked is not made).  0 = every evaluation
  *                 searches the stencils.  On a decomposed context the ranks exchange their displacement bounds and decide alike;
- *                 there the default means "up to two ranks" (measured: the lists lose with 8 ranks), 2 = on for every world size.
+ *                 there the default means "up to four ranks" (measured: the gain shrinks with the rank's share of the work), 2 = on for every world size.
  *   "nl_skin", "nl_skin_max"  the skin of those lists: at least nl_skin (default 0.1); the gate thickens it up to nl_skin_max (default 0.3)
  *                 when the fastest particle of the last step would outrun the thinner one
  *   "stencil_refresh"  1 (default) = rebuilds that keep the cell numbering re-classify the recorded r < 9 + 1 neighbours of every cell

@@ -26,7 +26,7 @@ inline int fail(int code, const char *fmt, ...) {
 constexpr int kNType = 6;              // forcefield_canonical.h:37
 constexpr int kStencilStride = ORBC_STENCIL_STRIDE;
 constexpr int kMoversCap = 4096;
-constexpr int kNlAutoWorld = 2;      // hit lists on a decomposed run: automatic up to this many ranks (orbc_b200.cu: nl_active)
+constexpr int kNlAutoWorld = 4;      // hit lists on a decomposed run: automatic up to this many ranks (orbc_b200.cu: nl_active)
 constexpr float kBin = 10.0f;          // centroid grid bin = largest centroid stencil radius (9, compute_pairwise_fused.h:183) + the margin of the wide stencils (rebuild.cuh)
 constexpr int kMaxWorld = 8;           // ranks of one spatially decomposed run (one B200 box)
 

@@ -235,9 +235,9 @@ float ff_att(float cut, float req, float eps) { return (float)(-2.0 * eps / pow_
 bool nl_active(const orbc_ctx *c) {
     if (!c->nl_on || c->pair_impl != 2 || c->ll_variant != 1) return false;
     if (!mg_active(c)) return true;
-    // decomposed: measured on the RBC, the lists gain 3 % with 2 ranks while every recording is walked (-1 % over 60 steps of the heating
-    // system) and lose 2 % / 3.5 % with 4 / 8 ranks (a rank's share of the work shrinks, the gate, the exchange of the bounds and the
-    // launches that return at once do not): automatic = up to kNlAutoWorld ranks
+    // decomposed: measured on the RBC (profiles/r02_configs/r02_lists_*), the lists gain 3 % with 2 ranks and 1.4 % with 4; with 8 they lost
+    // 3.5 % before the gate chose its skin (half of the recordings were then never walked) and were not measured again: a rank's share of the
+    // work shrinks, the gate, the exchange of the bounds and the launches that return at once do not.  Automatic = up to kNlAutoWorld ranks
     return c->mg.connected && (c->nl_on == 2 || c->mg.world <= kNlAutoWorld);
 }
 int nl_share(orbc_ctx *c);
