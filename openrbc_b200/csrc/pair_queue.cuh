@@ -248,7 +248,10 @@ __global__ void k_nl_gate(NlState *st, int force, int fixed_mode, int moves, flo
             else if (st->wait > 0) { st->wait--; mode = 2; }
             else mode = skin <= st->skin ? 1 : 2;
             st->valid = mode == 1; st->accum = 0.f; st->overflow = 0; st->used = 0;
-        } else if (!st->valid || st->overflow) { mode = 2; st->valid = 0; }
+        } else if (!st->valid || st->overflow) {
+            if (st->valid && st->used == 0) { st->backoff = min(2 * st->backoff + 1, kNlBackoffMax); st->wait = st->backoff; }   // (rows overflowed: recorded for nothing)
+            mode = 2; st->valid = 0;
+        }
         else {
             const float acc = st->accum + (float)moves * d;
             if (2.0f * acc <= st->skin) { mode = 0; st->accum = acc; if (st->used++ == 0) st->backoff >>= 1; }
