@@ -829,6 +829,12 @@ int orbc_set_option(orbc_ctx *c, const char *name, double value) { if (c) cudaSe
         c->tile_cap = (int)value; c->lruns_valid = false; return ORBC_OK;
     }
     if (!strcmp(name, "stencil_refresh")) { c->wide_on = value != 0; return ORBC_OK; }   // 0: every rebuild searches the centroid grid in full
+    if (!strcmp(name, "debug_nl_cap")) {                         // test aid: rows of the hit lists this short (before the lists are first used), so that they overflow
+        if (!(value >= 1 && value <= 96)) return fail(ORBC_ERR_ARG, "debug_nl_cap must be in [1, 96]");
+        if (c->ll_list || c->pl_list) return fail(ORBC_ERR_STATE, "debug_nl_cap: the lists are allocated already");
+        c->nl_cap_ll = (int)value; c->nl_cap_pl = std::min(c->nl_cap_pl, (int)value); c->nl_cap_pp = std::min(c->nl_cap_pp, (int)value);
+        return ORBC_OK;
+    }
     if (!strcmp(name, "debug_nl_mode")) {                        // measurement aid: -1 the gate decides, 1 every evaluation records the hit lists, 2 every evaluation searches
         if (value != -1 && value != 1 && value != 2) return fail(ORBC_ERR_ARG, "debug_nl_mode must be -1, 1 or 2");
         c->nl_debug_mode = (int)value; c->nl_valid = false; return ORBC_OK;

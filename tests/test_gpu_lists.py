@@ -97,3 +97,20 @@ def test_gate_thickens_the_skin_for_a_hot_system():
         for s in (0, 1):
             for f in "xvno":
                 np.testing.assert_array_equal(got[s][f], ref[s][f], err_msg=f)
+
+
+@pytest.mark.parametrize("name", ["sphere_r12", "vesicle_ico0"])
+def test_rows_that_overflow_fall_back_to_the_search(name):
+    """List rows too short for the partners of a particle: the recording raises the overflow flag, the evaluations that follow search,
+    the gate backs off -- and nothing changes in the trajectory."""
+    st = load(name)
+    exact = len(st["px"]) == 0
+    ref, _ = run(st, 10, 1e-3, nl_reuse=0)
+    got, stats = run(st, 10, 1e-3, nl_reuse=1, debug_nl_cap=4)
+    assert stats[1] == 0 and stats[0] >= 1 and stats[0] + stats[3] == 10, stats     # recorded (in vain), never walked
+    for s in (0, 1):
+        for f in "xvno":
+            if exact:
+                np.testing.assert_array_equal(got[s][f], ref[s][f], err_msg=f)
+            else:
+                assert rel_err(got[s][f], ref[s][f]) < 1e-5, (s, f)
