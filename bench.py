@@ -304,15 +304,25 @@ def alu_roofline(prof, counts, world):
     return out
 
 
-def run_chunked(sim, n_steps):
-    """n_steps of the main loop through the fused entry point, with delete_lipid at multiples of freq_cleanup (openrbc.cpp:201)."""
-    done = 0
+def run_chunked(sim, n_steps, nh=False, frames=0, sink=None):
+    """n_steps of the main loop through the fused entry point, with delete_lipid at multiples of freq_cleanup (openrbc.cpp:201).
+    nh: the Nose-Hoover branch (orbc_run_nh).  frames: a trajectory frame (dump_field 7: x, n, affiliation, ids) every `frames` steps,
+    assembled on the device and copied out while the run continues (openrbc.cpp:248-250); sink(frame bytes) receives it."""
+    done, pending = 0, False
     while done < n_steps:
         if sim.nstep % FREQ_CLEANUP == 0:
             sim.delete_lipid(sim.stray_tolerance)
         k = min(n_steps - done, FREQ_CLEANUP - sim.nstep % FREQ_CLEANUP)
-        sim.run_langevin(k)
+        if frames:
+            k = min(k, frames - sim.nstep % frames)
+        (sim.run_nh if nh else sim.run_langevin)(k)
         done += k
+        if frames and sim.nstep % frames == 0:
+            if pending:
+                sink(sim.save_frame_end())
+            sim.save_frame_begin(7); pending = True
+    if pending:
+        sink(sim.save_frame_end())
 
 
 def run_ours(args):
@@ -358,19 +368,34 @@ def run_ours(args):
 
     # ---- device-resident leg ------------------------------------------------------------------------------------------
     sim = make_sim(st)
-    run_chunked(sim, args.warmup)
+    frame_bytes = [0]
+    devnull = open(os.devnull, "wb")
+
+    def sink(fr):
+        devnull.write(memoryview(fr)); frame_bytes[0] += fr.nbytes
+    if args.frames and world > 1:
+        raise SystemExit("bench.py: --frames is a single-GPU option (a rank's frame holds its own slots only)")
+    if args.nh:
+        sim.zeta = 0.0
+    if args.frames:                      # the two pinned frame buffers are allocated on first use: not part of the steady state
+        sim.save_frame_begin(7); sim.save_frame_begin(7); sim.save_frame_end(); sim.save_frame_end()
+    run_chunked(sim, args.warmup, args.nh)
     sim.synchronize()
     nl_before = sim.dump("nl_stats").tolist()
     sim.profile_enable(True)
     l0 = sim.launch_count()
     barrier()
     with Clocks(local) as clk:
+        t_dev0 = time.perf_counter()
         sim.event_record(0)
-        run_chunked(sim, args.steps)
+        run_chunked(sim, args.steps, args.nh, args.frames, sink)
         sim.event_record(1)
         sim.synchronize()
+        t_dev1 = time.perf_counter()
         barrier()
     ms = sim.event_elapsed_ms(0, 1)
+    if args.frames:                      # the frames leave on a second stream: the job is done when the last one has arrived
+        ms = max(ms, (t_dev1 - t_dev0) * 1e3)
     launches = sim.launch_count() - l0
     prof = {k: sim.profile_read(k) for k in orbc.engine.PROF}
     sim.profile_enable(False)
@@ -442,7 +467,9 @@ def run_ours(args):
         if e2e_sim.nstep % FREQ_CLEANUP == 0:
             e2e_sim.delete_lipid(e2e_sim.stray_tolerance); d2h += 8
             slow.append(((time.perf_counter() - t0) * 1e3, "delete_lipid@%d" % e2e_sim.nstep)); t0 = time.perf_counter()
-        if args.cv:
+        if args.nh:
+            e2e_sim.step_nh_checked(); d2h += 32
+        elif args.cv:
             e2e_sim.step_langevin_cv_checked(3.15, 0.05); d2h += 20
         else:
             e2e_sim.step_langevin_checked(); d2h += 16
@@ -503,7 +530,10 @@ def run_ours(args):
         "config": {"workload": workload_name(args.workload, st), "l2": "inputs larger than L2 (state %.0f MB resident in HBM, no flush needed)" % (n_total * 6 * 16 / 1e6),
                    "multi_gpu": "single GPU" if world == 1 else (f"one cell decomposed over {world} ranks: contiguous ranges of Morton-ordered Voronoi cells, halo push + migration "
                                                                 "by peer stores over NVLink, epoch-flag barriers"),
-                   "integrator": "verlet_langevin kBT=0.22 dt=0.01, rebuild every 2 steps, Morton sort every 24, cleanup every 60" + (", constrain_volume(3.15, 0.05) every step" if args.cv else ""),
+                   "integrator": ("Nose-Hoover (fused initial / final kernels) kBT=0.22 dt=0.01" if args.nh else "verlet_langevin kBT=0.22 dt=0.01") + ", rebuild every 2 steps, Morton sort every 24, cleanup every 60"
+                                 + (", constrain_volume(3.15, 0.05) every step" if args.cv else "")
+                                 + ((", a %.0f MB trajectory frame every %d steps assembled on the device and copied out while the run continues (%d frames in the timed region)"
+                                     % (frame_bytes[0] / max(1, args.steps // args.frames) / 1e6, args.frames, args.steps // args.frames)) if args.frames else ""),
                    "particles_at_end": n_now, "temperature_at_end": temperature, "options": args.opt,
                    "hit_lists": {"evaluations_that_recorded": nl_timed[0], "evaluations_that_walked": nl_timed[1], "evaluations_that_searched": nl_timed[3], "overflow": nl_stats[2], "of": "the timed steps"},
                    "hbm_roofline_frac_step": value / world * B_ALG_STEP / 1e9 / peak, "device_time_shares": shares},
@@ -540,6 +570,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--opt", action="append", default=[], help="library option name=value (orbc_set_option), e.g. --opt nl_skin=0.2")
     ap.add_argument("--cv", action="store_true", help="BASELINE.json configs[2]: constrain_volume(3.15, 0.05) at the place of openrbc.cpp:229 in every step")
+    ap.add_argument("--nh", action="store_true", help="BASELINE.json configs[4]: the Nose-Hoover branch of the loop instead of Langevin")
+    ap.add_argument("--frames", type=int, default=0, help="configs[4]: a trajectory frame every N steps of the device-resident leg (single GPU)")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"], help="label of the run (weak: the workload was sized with the number of GPUs, e.g. patch:<N x 1.05e6>)")
     args = ap.parse_args()
     if args.impl == "reference":

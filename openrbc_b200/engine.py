@@ -485,6 +485,17 @@ class Simulation:
         self.nstep += 1
         self.synchronize()
 
+    def step_nh_checked(self):
+        """One iteration of the Nose-Hoover branch of the loop (openrbc.cpp:193-240), call for call, then the status read-back."""
+        self.nh_initial_fused()                      # :193 (its destructor updates zeta from the kinetic energy)
+        if self.nstep % self.freq_voronoi == 0:
+            self.rebuild()
+        self.compute_pairwise_fused()
+        self.compute_bonded()
+        self.nh_final_fused()                        # :236
+        self.nstep += 1
+        self.synchronize()
+
     def step_langevin_checked(self):
         """One loop iteration call by call, then wait for it and read the device status back (16 B D2H)."""
         self.step_langevin()
