@@ -161,8 +161,8 @@ __global__ void __launch_bounds__(256) k_verlet_langevin2(IntegArgs a0, IntegArg
 }
 
 // integrate_nh.h:178-235 (operator()) — half kick with 1/(1 + dt zeta / 2), drift, bounce-back, KE, omega half kick, director, clear
-__global__ void __launch_bounds__(256) k_nh_initial_fused(IntegArgs a) {
-    const size_t i = (size_t)a.range[0] + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void nh_initial_fused_body(const unsigned bid, const IntegArgs &a) {
+    const size_t i = (size_t)a.range[0] + (size_t)bid * blockDim.x + threadIdx.x;
     double ke = 0.0;
     float d2 = 0.f;
     if (i < (size_t)a.range[1]) {
@@ -197,10 +197,14 @@ __global__ void __launch_bounds__(256) k_nh_initial_fused(IntegArgs a) {
     nl_track(a.disp, d2);
     block_add_double(ke, a.acc);
 }
+__global__ void __launch_bounds__(256) k_nh_initial_fused(IntegArgs a) { nh_initial_fused_body(blockIdx.x, a); }
+__global__ void __launch_bounds__(256) k_nh_initial_fused2(IntegArgs a0, IntegArgs a1, unsigned blocks0) {   // both containers, as k_verlet_langevin2
+    if (blockIdx.x < blocks0) nh_initial_fused_body(blockIdx.x, a0); else nh_initial_fused_body(blockIdx.x - blocks0, a1);
+}
 
 // integrate_nh.h:237-273 — t = n x t, second half kick with -zeta v, omega half kick, KE
-__global__ void __launch_bounds__(256) k_nh_final_fused(IntegArgs a) {
-    const size_t i = (size_t)a.range[0] + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void nh_final_fused_body(const unsigned bid, const IntegArgs &a) {
+    const size_t i = (size_t)a.range[0] + (size_t)bid * blockDim.x + threadIdx.x;
     double ke = 0.0;
     if (i < (size_t)a.range[1]) {
         const float zeta = a.zeta_dev ? a.zeta_dev[0] : a.zeta;
@@ -216,6 +220,10 @@ __global__ void __launch_bounds__(256) k_nh_final_fused(IntegArgs a) {
         a.v[i] = v; a.o[i] = o; a.t[i] = make_float4(tq.x, tq.y, tq.z, 0);
     }
     block_add_double(ke, a.acc);
+}
+__global__ void __launch_bounds__(256) k_nh_final_fused(IntegArgs a) { nh_final_fused_body(blockIdx.x, a); }
+__global__ void __launch_bounds__(256) k_nh_final_fused2(IntegArgs a0, IntegArgs a1, unsigned blocks0) {
+    if (blockIdx.x < blocks0) nh_final_fused_body(blockIdx.x, a0); else nh_final_fused_body(blockIdx.x - blocks0, a1);
 }
 
 // integrate_nh.h:156-176 (unfused second half: no torque conversion, no KE)

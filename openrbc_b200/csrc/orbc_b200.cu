@@ -643,7 +643,7 @@ int preload_kernels() {
     ORBC_PRELOAD(k_pair_lipid); ORBC_PRELOAD(k_lipid_runs); ORBC_PRELOAD(k_rank_only); ORBC_PRELOAD(k_init_centroids); ORBC_PRELOAD(k_bbox); ORBC_PRELOAD((k_pair_ll_r<20, 4, false>)); ORBC_PRELOAD(k_pair_ll_t); ORBC_PRELOAD((k_pair_prot<1, false>)); ORBC_PRELOAD((k_pair_prot<2, false>)); ORBC_PRELOAD((k_pair_prot<4, false>)); ORBC_PRELOAD((k_pair_prot<1, true>)); ORBC_PRELOAD((k_pair_prot<2, true>)); ORBC_PRELOAD((k_pair_prot<4, true>)); ORBC_PRELOAD(k_pair_prot_list<1>); ORBC_PRELOAD(k_pair_prot_list<2>); ORBC_PRELOAD(k_pair_prot_list<4>); ORBC_PRELOAD((k_pair_ll_r<16, 4, true>)); ORBC_PRELOAD(k_pair_ll_list<16>); ORBC_PRELOAD(k_nl_gate); ORBC_PRELOAD(k_nl_share); ORBC_PRELOAD(k_pair_protein);
     ORBC_PRELOAD(k_permute_centroids); ORBC_PRELOAD(k_porder_flag); ORBC_PRELOAD(k_porder_scatter); ORBC_PRELOAD(k_post_torque); ORBC_PRELOAD(k_radix_hist);
     ORBC_PRELOAD(k_radix_scatter); ORBC_PRELOAD(k_rank_and_move); ORBC_PRELOAD(k_remap_cellid); ORBC_PRELOAD(k_scan_onepass); ORBC_PRELOAD(k_set3); ORBC_PRELOAD(k_set_range); ORBC_PRELOAD(k_set_range_const); ORBC_PRELOAD(k_share_counts);
-    ORBC_PRELOAD(k_stencil_build); ORBC_PRELOAD(k_stencil_refresh); ORBC_PRELOAD(k_stencil_movers<true>); ORBC_PRELOAD(k_stencil_movers<false>); ORBC_PRELOAD(k_centroid_disp); ORBC_PRELOAD(k_stray_mask); ORBC_PRELOAD(k_unpack3); ORBC_PRELOAD(k_unpack_w); ORBC_PRELOAD(k_verlet_langevin); ORBC_PRELOAD(k_verlet_langevin2); ORBC_PRELOAD(k_assign_nearest2); ORBC_PRELOAD(k_cell_scatter2); ORBC_PRELOAD(k_rank_and_move2); ORBC_PRELOAD(k_zero4);
+    ORBC_PRELOAD(k_stencil_build); ORBC_PRELOAD(k_stencil_refresh); ORBC_PRELOAD(k_stencil_movers<true>); ORBC_PRELOAD(k_stencil_movers<false>); ORBC_PRELOAD(k_centroid_disp); ORBC_PRELOAD(k_stray_mask); ORBC_PRELOAD(k_unpack3); ORBC_PRELOAD(k_unpack_w); ORBC_PRELOAD(k_verlet_langevin); ORBC_PRELOAD(k_verlet_langevin2); ORBC_PRELOAD(k_nh_initial_fused2); ORBC_PRELOAD(k_nh_final_fused2); ORBC_PRELOAD(k_assign_nearest2); ORBC_PRELOAD(k_cell_scatter2); ORBC_PRELOAD(k_rank_and_move2); ORBC_PRELOAD(k_zero4);
 #undef ORBC_PRELOAD
     return ORBC_OK;
 }
@@ -1316,10 +1316,15 @@ int orbc_run_nh(orbc_ctx *c, const orbc_step_params *p, int n_steps, int freq_vo
     const int world = mg ? c->mg.world : 1;
     for (int s = 0; s < n_steps; ++s, ++q.nstep) {
         ++c->nl_moves;
-        for (int sp = 0; sp < 2; ++sp) if (c->sp[sp].n) {
-            IntegArgs a; fill_integ(a, c, sp, &q); a.zeta_dev = c->d_nh;
-            ORBC_LAUNCH(c, k_nh_initial_fused, blocks_for(owned_bound(c, sp), 256), 256, 0, a);
-            if (mg) c->sp[sp].cur_xn ^= 1;
+        {
+            IntegArgs a[2]; unsigned blocks[2] = {0, 0}; int m = 0;                  // both containers in one launch
+            for (int sp = 0; sp < 2; ++sp) if (c->sp[sp].n) {
+                fill_integ(a[m], c, sp, &q); a[m].zeta_dev = c->d_nh;
+                blocks[m++] = blocks_for(owned_bound(c, sp), 256);
+                if (mg) c->sp[sp].cur_xn ^= 1;
+            }
+            if (m == 2) ORBC_LAUNCH(c, k_nh_initial_fused2, blocks[0] + blocks[1], 256, 0, a[0], a[1], blocks[0]);
+            else if (m == 1) ORBC_LAUNCH(c, k_nh_initial_fused, blocks[0], 256, 0, a[0]);
         }
         ORBC_TRY(nl_share(c));
         // decomposed: one barrier stands behind both the halo push of the drift and the exchange of the partial kinetic energies
@@ -1329,9 +1334,14 @@ int orbc_run_nh(orbc_ctx *c, const orbc_step_params *p, int n_steps, int freq_vo
         ORBC_TRY(launch_pairwise(c));
         ORBC_TRY(launch_bonded(c));
         if (c->cv_on) ORBC_TRY(do_constrain_volume(c, c->cv_target, c->cv_strength));   // openrbc.cpp:229
-        for (int sp = 0; sp < 2; ++sp) if (c->sp[sp].n) {
-            IntegArgs a; fill_integ(a, c, sp, &q); a.zeta_dev = c->d_nh;
-            ORBC_LAUNCH(c, k_nh_final_fused, blocks_for(owned_bound(c, sp), 256), 256, 0, a);
+        {
+            IntegArgs a[2]; unsigned blocks[2] = {0, 0}; int m = 0;
+            for (int sp = 0; sp < 2; ++sp) if (c->sp[sp].n) {
+                fill_integ(a[m], c, sp, &q); a[m].zeta_dev = c->d_nh;
+                blocks[m++] = blocks_for(owned_bound(c, sp), 256);
+            }
+            if (m == 2) ORBC_LAUNCH(c, k_nh_final_fused2, blocks[0] + blocks[1], 256, 0, a[0], a[1], blocks[0]);
+            else if (m == 1) ORBC_LAUNCH(c, k_nh_final_fused, blocks[0], 256, 0, a[0]);
         }
         ORBC_TRY(mg_share_ke(c)); ORBC_TRY(mg_barrier(c));
         ORBC_LAUNCH(c, k_nh_zeta_update, 1, 32, 0, c->d_nh, c->d_acc, q.dt, q.kBT, n, mg ? mg_ke_slots(c) : (const double *)nullptr, world);
