@@ -107,14 +107,15 @@ def test_forces_and_rebuild_call_by_call(name, world):
         sim.close()
 
 
+@pytest.mark.parametrize("lists", [2, 0])
 @pytest.mark.parametrize("name,world", [("vesicle_ico0", 2), ("vesicle_ico0", 4), ("sphere_r12", 4)])
-def test_free_running_loop(name, world):
+def test_free_running_loop(name, world, lists):
     """orbc_run_langevin with thermal noise over several rebuilds (Morton step included): the counter-based generator is
     keyed by the global slot, so a decomposed run follows the single-GPU trajectory."""
     from openrbc_b200 import Simulation
     st = load_state(name)
     one = Simulation(st, kBT=0.22)
-    sims = make_ranks(st, world, opts={"nl_reuse": 2}, kBT=0.22)      # hit lists on every world size (automatic: up to two ranks)
+    sims = make_ranks(st, world, opts={"nl_reuse": lists}, kBT=0.22)  # hit lists forced on / off (automatic: on up to four ranks, off beyond)
     for sim in [one] + sims:
         sim.nstep = 20
     one.run_langevin(8)
