@@ -51,6 +51,20 @@ def test_zeta_update_host_helper(lib):
     assert a == b and q1.value == q2.value
 
 
+def test_unfused_zeta_update_host_helper(lib):
+    """verlet_nh_update's destructor (integrate_nh.h:72-76): its 1.5f * n * kBT is a float product, one ulp away from the fused
+    kernel's; the library's host helper against the oracle's restatement over a few values."""
+    import ctypes as C
+    from oracle import port
+    lib.orbc_nh_zeta_update_unfused.restype = C.c_float
+    lib.orbc_nh_zeta_update_unfused.argtypes = [C.c_float, C.POINTER(C.c_float), C.c_double, C.c_float, C.c_double, C.c_long]
+    for zeta, ke, n in ((0.03, 1234.5, 3544), (0.0, 75341.25, 174102), (-0.2, 1.0e6, 3205506)):
+        q1, q2 = C.c_float(0.0), C.c_float(0.0)
+        a = lib.orbc_nh_zeta_update_unfused(zeta, C.byref(q1), 1e-2, 0.22, ke, n)
+        b = port.lib().orc_nh_zeta_update_unfused(C.c_float(zeta), C.byref(q2), C.c_double(1e-2), C.c_float(0.22), C.c_double(ke), n)
+        assert a == b and q1.value == q2.value, (zeta, ke, n)
+
+
 def test_no_cpu_fallback_without_device(lib):
     """Creating a context must fail loudly when no CUDA device is present (it must never fall back to the CPU)."""
     import ctypes as C
