@@ -52,7 +52,7 @@ def test_zeta_update_host_helper(lib):
 
 
 def test_unfused_zeta_update_host_helper(lib):
-    """verlet_nh_update's destructor (integrate_nh.h:72-76): its 1.5f * n * kBT is a float product, one ulp away from the fused
+    """verlet_nh_update's destructor (integrate_nh.h:74-77): its 1.5f * n * kBT is a float product, one ulp away from the fused
     kernel's; the library's host helper against the oracle's restatement over a few values."""
     import ctypes as C
     from oracle import port
